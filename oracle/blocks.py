@@ -1,0 +1,175 @@
+"""
+Functional CPU restatement of the reference's recurrent cells and conv blocks (test infrastructure).
+
+All tensors are fp32 NCHW, as in the reference.  Parameters are passed explicitly (taken from a
+``state_dict`` by the callers in ``oracle/models.py``) so that the same functions check both the
+reference's modules and the drop-in modules of ``vp_suite_b200``.
+"""
+import math
+
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------------------------------
+# Shi et al. ConvLSTM with peepholes          (vp_suite/model_blocks/conv_lstm_hzzone.py:38-70)
+# --------------------------------------------------------------------------------------------------
+def convlstm_shi_step(x, h, c, w, b, wci, wcf, wco, padding=1):
+    """One timestep.  Gate conv over cat(x, h) (conv_lstm_hzzone.py:59-60), chunk order i,f,g,o
+    (:62), peephole terms on c_{t-1} for i,f and on c_t for o (:64-67), h = o*tanh(c) (:68)."""
+    z = F.conv2d(torch.cat([x, h], dim=1), w, b, stride=1, padding=padding)
+    zi, zf, zg, zo = torch.chunk(z, 4, dim=1)
+    i = torch.sigmoid(zi + wci * c)
+    f = torch.sigmoid(zf + wcf * c)
+    c_new = f * c + i * torch.tanh(zg)
+    o = torch.sigmoid(zo + wco * c_new)
+    h_new = o * torch.tanh(c_new)
+    return h_new, c_new
+
+
+def convlstm_shi_sequence(inputs, states, seq_len, w, b, wci, wcf, wco, in_channels, padding=1):
+    """Whole-sequence driver (conv_lstm_hzzone.py:38-70): zero initial state when ``states`` is None
+    (:39-45), all-zero input when ``inputs`` is None (:53-56), returns (stack of h, (h, c)) (:70)."""
+    C = w.shape[0] // 4
+    sh, sw = wci.shape[-2:]
+    if states is None:
+        bsz = inputs.shape[0]
+        h = torch.zeros(bsz, C, sh, sw, dtype=torch.float32)
+        c = torch.zeros(bsz, C, sh, sw, dtype=torch.float32)
+    else:
+        h, c = states
+        bsz = h.shape[0]
+    outs = []
+    for t in range(seq_len):
+        x = torch.zeros(bsz, in_channels, sh, sw) if inputs is None else inputs[:, t]
+        h, c = convlstm_shi_step(x, h, c, w, b, wci, wcf, wco, padding)
+        outs.append(h)
+    return torch.stack(outs, dim=1), (h, c)
+
+
+# --------------------------------------------------------------------------------------------------
+# ndrplz ConvLSTM cell                          (vp_suite/model_blocks/conv_lstm_ndrplz.py:28-43)
+# --------------------------------------------------------------------------------------------------
+def convlstm_cell_step(x, h, c, w, b):
+    """Gate conv over cat(x, h) with 'same' padding (:31-33); split order i,f,o,g (:34);
+    no peepholes (:35-41)."""
+    pad = (w.shape[2] // 2, w.shape[3] // 2)
+    z = F.conv2d(torch.cat([x, h], dim=1), w, b, padding=pad)
+    C = w.shape[0] // 4
+    zi, zf, zo, zg = torch.split(z, C, dim=1)
+    c_new = torch.sigmoid(zf) * c + torch.sigmoid(zi) * torch.tanh(zg)
+    h_new = torch.sigmoid(zo) * torch.tanh(c_new)
+    return h_new, c_new
+
+
+# --------------------------------------------------------------------------------------------------
+# ST-LSTM v2 cell, layer_norm=False             (vp_suite/model_blocks/predrnn.py:57-83)
+# --------------------------------------------------------------------------------------------------
+def stlstm_step(x, h, c, m, w_x, w_h, w_m, w_o, w_last, forget_bias=1.0):
+    """conv_x/conv_h/conv_m are bias-free 'same' convs (:58-60); split orders (:61-63); gate math
+    (:65-76); o uses conv_o over cat(c', m') (:78-79); h' = o * tanh(conv_last(mem)) (:80).
+    Returns (h', c', m', delta_c, delta_m) (:82)."""
+    C = w_h.shape[0] // 4
+    pad = w_x.shape[-1] // 2
+    X = F.conv2d(x, w_x, None, padding=pad)
+    H = F.conv2d(h, w_h, None, padding=pad)
+    M = F.conv2d(m, w_m, None, padding=pad)
+    i_x, f_x, g_x, ip_x, fp_x, gp_x, o_x = torch.split(X, C, dim=1)
+    i_h, f_h, g_h, o_h = torch.split(H, C, dim=1)
+    i_m, f_m, g_m = torch.split(M, C, dim=1)
+    i_t = torch.sigmoid(i_x + i_h)
+    f_t = torch.sigmoid(f_x + f_h + forget_bias)
+    g_t = torch.tanh(g_x + g_h)
+    delta_c = i_t * g_t
+    c_new = f_t * c + delta_c
+    ip = torch.sigmoid(ip_x + i_m)
+    fp = torch.sigmoid(fp_x + f_m + forget_bias)
+    gp = torch.tanh(gp_x + g_m)
+    delta_m = ip * gp
+    m_new = fp * m + delta_m
+    mem = torch.cat([c_new, m_new], dim=1)
+    o_t = torch.sigmoid(o_x + o_h + F.conv2d(mem, w_o, None, padding=pad))
+    h_new = o_t * torch.tanh(F.conv2d(mem, w_last, None))
+    return h_new, c_new, m_new, delta_c, delta_m
+
+
+# --------------------------------------------------------------------------------------------------
+# PhyCell cell, action_conditional=False        (vp_suite/model_blocks/phydnet.py:49-62)
+# --------------------------------------------------------------------------------------------------
+def find_divisor_for_group_norm(x):
+    """vp_suite/model_blocks/phydnet.py:348-362 -- largest co-divisor of the divisor closest below sqrt(x)."""
+    sq = math.floor(math.sqrt(x))
+    while x % sq != 0:
+        sq -= 1
+    return x // sq
+
+
+def phycell_step(x, h, p):
+    """``p`` holds F.conv1.{weight,bias}, F.bn1.{weight,bias}, F.conv2.{weight,bias}, convgate.{weight,bias}.
+    K = sigmoid(convgate(cat[x, h])) (:57-59); h~ = h + F(h) with F = conv1 -> GroupNorm -> conv2 (:33-39, :60);
+    h' = h~ + K * (x - h~) (:61)."""
+    k1 = p["F.conv1.weight"]
+    hid = k1.shape[0]
+    groups = find_divisor_for_group_norm(hid)
+    f = F.conv2d(h, k1, p["F.conv1.bias"], padding=(k1.shape[2] // 2, k1.shape[3] // 2))
+    f = F.group_norm(f, groups, p["F.bn1.weight"], p["F.bn1.bias"], eps=1e-5)
+    f = F.conv2d(f, p["F.conv2.weight"], p["F.conv2.bias"])
+    gate = torch.sigmoid(F.conv2d(torch.cat([x, h], dim=1), p["convgate.weight"], p["convgate.bias"], padding=1))
+    h_tilde = h + f
+    return h_tilde + gate * (x - h_tilde)
+
+
+# --------------------------------------------------------------------------------------------------
+# DCGAN conv blocks                              (vp_suite/model_blocks/conv.py:58-95)
+# --------------------------------------------------------------------------------------------------
+def dcgan_conv(x, w, b, gn_w, gn_b, stride):
+    """Conv3x3(stride, pad 1) -> GroupNorm(16) -> LeakyReLU(0.2)  (conv.py:66-70)."""
+    y = F.conv2d(x, w, b, stride=stride, padding=1)
+    y = F.group_norm(y, 16, gn_w, gn_b, eps=1e-5)
+    return F.leaky_relu(y, 0.2)
+
+
+def dcgan_conv_transpose(x, w, b, gn_w, gn_b, stride):
+    """ConvT3x3(stride, pad 1, output_padding = [stride == 2]) -> GroupNorm(16) -> LeakyReLU(0.2)  (conv.py:85-92)."""
+    y = F.conv_transpose2d(x, w, b, stride=stride, padding=1, output_padding=int(stride == 2))
+    y = F.group_norm(y, 16, gn_w, gn_b, eps=1e-5)
+    return F.leaky_relu(y, 0.2)
+
+
+def _sub(sd, prefix):
+    """View of a state dict below ``prefix`` (keys with the prefix stripped)."""
+    n = len(prefix)
+    return {k[n:]: v for k, v in sd.items() if k.startswith(prefix)}
+
+
+def dcgan_block(x, sd, prefix, stride, transpose):
+    p = _sub(sd, prefix)
+    fn = dcgan_conv_transpose if transpose else dcgan_conv
+    return fn(x, p["main.0.weight"], p["main.0.bias"], p["main.1.weight"], p["main.1.bias"], stride)
+
+
+def dcgan_encoder(x, sd, prefix):
+    """DCGANEncoder: c1 stride 2, c2 stride 1, c3 stride 2  (enc.py:107-118)."""
+    h = dcgan_block(x, sd, prefix + "c1.", 2, False)
+    h = dcgan_block(h, sd, prefix + "c2.", 1, False)
+    return dcgan_block(h, sd, prefix + "c3.", 2, False)
+
+
+def dcgan_decoder(x, sd, prefix):
+    """DCGANDecoder: upc1 stride 2, upc2 stride 1, upc3 = bare ConvT stride 2 (enc.py:128-141).
+    The trailing Resize is the identity whenever the stride arithmetic already lands on the image size
+    (SURVEY.md App. D); other sizes are rejected here rather than silently interpolated."""
+    d = dcgan_block(x, sd, prefix + "upc1.", 2, True)
+    d = dcgan_block(d, sd, prefix + "upc2.", 1, True)
+    return F.conv_transpose2d(d, sd[prefix + "upc3.weight"], sd[prefix + "upc3.bias"],
+                              stride=2, padding=1, output_padding=1)
+
+
+def encoder_split(x, sd, prefix):
+    """EncoderSplit: two stride-1 DCGANConv (phydnet.py:184-192)."""
+    return dcgan_block(dcgan_block(x, sd, prefix + "c1.", 1, False), sd, prefix + "c2.", 1, False)
+
+
+def decoder_split(x, sd, prefix):
+    """DecoderSplit: two stride-1 DCGANConvTranspose (phydnet.py:201-209)."""
+    return dcgan_block(dcgan_block(x, sd, prefix + "upc1.", 1, True), sd, prefix + "upc2.", 1, True)

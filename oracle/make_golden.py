@@ -1,0 +1,160 @@
+"""
+Golden-vector generator (test infrastructure; runs only in the authoring container).
+
+Imports the REAL vp-suite reference from /root/reference through ``oracle.ref_shim``, loads the deterministic
+synthetic weights of ``oracle.weights`` into the reference's own modules, runs them on deterministic synthetic
+frames and stores the outputs as small ``.npz`` fixtures under ``tests/golden/`` plus ``manifest.json``
+(configs, seeds and the reference's state-dict key->shape listing).  Weights and inputs are NOT stored: tests
+regenerate them from the seeds.
+
+    python -m oracle.make_golden            # rewrites tests/golden/
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim                      # noqa: E402
+from oracle.weights import synth_state_dict, synth_frames   # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+MODEL_CASES = [
+    # name,           key,            img_shape,   b, t_ctx, pred, wseed, xseed, gain
+    ("ef_1x64",       "convlstm-shi", (1, 64, 64), 2, 4,     3,    0,     1234,  2.5),
+    ("ef_3x32",       "convlstm-shi", (3, 32, 32), 1, 3,     4,    1,     77,    2.5),
+    ("predrnn_1x64",  "predrnn-pp",   (1, 64, 64), 2, 3,     3,    2,     99,    1.5),
+    ("predrnn_3x32",  "predrnn-pp",   (3, 32, 32), 1, 2,     2,    3,     5,     1.5),
+    ("phy_3x64",      "phy",          (3, 64, 64), 2, 2,     3,    4,     42,    1.5),
+    ("phy_1x64",      "phy",          (1, 64, 64), 1, 3,     2,    5,     43,    1.5),
+]
+
+
+def shapes_of(module):
+    return {k: list(v.shape) for k, v in module.state_dict().items()}
+
+
+def run_models(classes, manifest):
+    for name, key, img, b, t, p, wseed, xseed, gain in MODEL_CASES:
+        torch.manual_seed(0)
+        m = classes[key]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+        shp = shapes_of(m)
+        m.load_state_dict(synth_state_dict(shp, wseed, gain))
+        total_t = t + p if key == "predrnn-pp" else t          # NEEDS_COMPLETE_INPUT (predrnn_v2.py:32)
+        x = synth_frames(b, total_t, *img, seed=xseed)
+        with torch.no_grad():
+            pred, aux = m(x, pred_frames=p)
+        arrays = {"pred": pred.numpy()}
+        if aux is not None:
+            (lk, lv), = aux.items()
+            arrays["loss"] = np.asarray(float(lv), dtype=np.float64)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+        manifest["models"][name] = dict(key=key, img_shape=list(img), batch=b, context=t, pred=p,
+                                        wseed=wseed, xseed=xseed, gain=gain, shapes=shp,
+                                        pred_std=float(pred.std()), pred_mean=float(pred.mean()))
+        print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
+
+
+def run_branch(classes, manifest):
+    """BASELINE config 2 composition (ours), built from the reference PhyDNet's own sub-modules."""
+    name, img, b, t, p, wseed, xseed = "branch_1x64", (1, 64, 64), 2, 3, 3, 6, 44
+    m = classes["phy"]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+    shp = shapes_of(m)
+    m.load_state_dict(synth_state_dict(shp, wseed))
+    x = synth_frames(b, t, *img, seed=xseed)
+
+    def step(frame, first):
+        er = m.encoder_Er(m.encoder_E(frame))
+        _, out = m.convcell(er, None, first)
+        return torch.sigmoid(m.decoder_D(m.decoder_Dr(out[-1])))
+
+    outs = []
+    with torch.no_grad():
+        for ei in range(t - 1):
+            step(x[:, ei], ei == 0)
+        frame = x[:, t - 1]
+        for di in range(p):
+            frame = step(frame, t == 1 and di == 0)
+            outs.append(frame)
+    pred = torch.stack(outs, 1)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), pred=pred.numpy())
+    manifest["models"][name] = dict(key="convlstm-branch", img_shape=list(img), batch=b, context=t, pred=p,
+                                    wseed=wseed, xseed=xseed, gain=1.5, shapes=shp,
+                                    pred_std=float(pred.std()), pred_mean=float(pred.mean()))
+    print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
+
+
+def run_blocks(manifest):
+    """Single-block vectors from the reference's own block classes."""
+    from vp_suite.model_blocks import ConvLSTM, SpatioTemporalLSTMCell, PhyCell_Cell
+    from vp_suite.model_blocks.conv_lstm_ndrplz import ConvLSTMCell
+    arrays = {}
+
+    # hzzone ConvLSTM: sequence with given inputs / zero state, then inputs=None continuing from that state
+    blk = ConvLSTM("cpu", in_channels=8, enc_channels=16, state_h=12, state_w=10, kernel_size=3).eval()
+    shp = shapes_of(blk)
+    blk.load_state_dict(synth_state_dict(shp, 21))
+    xin = torch.rand((2, 3, 8, 12, 10), generator=torch.Generator().manual_seed(5)) * 2 - 1
+    with torch.no_grad():
+        o1, (h1, c1) = blk(xin, None, seq_len=3)
+        o2, (h2, c2) = blk(None, (h1, c1), seq_len=2)
+    arrays.update(hz_out1=o1.numpy(), hz_h1=h1.numpy(), hz_c1=c1.numpy(), hz_out2=o2.numpy(), hz_c2=c2.numpy())
+    manifest["blocks"]["hzzone"] = dict(shapes=shp, wseed=21, xseed=5, x_shape=[2, 3, 8, 12, 10])
+
+    cell = ConvLSTMCell(input_dim=8, hidden_dim=16, kernel_size=(3, 3), bias=True).eval()
+    shp = shapes_of(cell)
+    cell.load_state_dict(synth_state_dict(shp, 22))
+    g = torch.Generator().manual_seed(6)
+    x, h, c = (torch.rand((2, 8, 10, 10), generator=g) * 2 - 1, torch.rand((2, 16, 10, 10), generator=g) * 2 - 1,
+               torch.rand((2, 16, 10, 10), generator=g) * 2 - 1)
+    with torch.no_grad():
+        hn, cn = cell(x, (h, c))
+    arrays.update(nd_h=hn.numpy(), nd_c=cn.numpy())
+    manifest["blocks"]["ndrplz"] = dict(shapes=shp, wseed=22, xseed=6)
+
+    st = SpatioTemporalLSTMCell(16, 32, 8, 8, 5, 1, False).eval()
+    shp = shapes_of(st)
+    st.load_state_dict(synth_state_dict(shp, 23))
+    g = torch.Generator().manual_seed(7)
+    x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+    h, c, mm = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(3)]
+    with torch.no_grad():
+        res = st(x, h, c, mm)
+    for nm, v in zip(("st_h", "st_c", "st_m", "st_dc", "st_dm"), res):
+        arrays[nm] = v.numpy()
+    manifest["blocks"]["stlstm"] = dict(shapes=shp, wseed=23, xseed=7)
+
+    pc = PhyCell_Cell(input_dim=16, action_conditional=False, action_size=0, hidden_dim=49, kernel_size=(7, 7)).eval()
+    shp = shapes_of(pc)
+    pc.load_state_dict(synth_state_dict(shp, 24))
+    g = torch.Generator().manual_seed(8)
+    x, h = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1, torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+    with torch.no_grad():
+        hn = pc(x, None, h)
+    arrays.update(phy_h=hn.numpy())
+    manifest["blocks"]["phycell"] = dict(shapes=shp, wseed=24, xseed=8)
+
+    np.savez_compressed(os.path.join(OUT, "blocks.npz"), **arrays)
+    print("blocks:", sorted(arrays))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    classes = ref_shim.load_reference()
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    manifest = {"generator": "oracle/make_golden.py", "reference": "AIS-Bonn/vp-suite v0.0.9 (/root/reference)",
+                "torch": torch.__version__, "models": {}, "blocks": {}}
+    run_models(classes, manifest)
+    run_branch(classes, manifest)
+    run_blocks(manifest)
+    with open(os.path.join(OUT, "manifest.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,233 @@
+"""
+Functional CPU restatement of the three rollout loops on the hot path (test infrastructure).
+
+Each function takes a ``state_dict`` with the reference's key layout, the input
+frames ``x[b, t, c, h, w]`` (fp32) and ``pred_frames`` and returns what the reference's
+``VPModel.forward`` returns in eval mode.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import blocks as B
+
+# Default hyper-parameters of the reference models (class attributes there).
+EF_DEFAULTS = dict(                       # models/precipitation_nowcasting/ef_conv_lstm.py:31-65
+    num_layers=3, enc_c=[16, 64, 64, 96, 96, 96], dec_c=[96, 96, 96, 96, 64, 16],
+    enc_conv_k=[3, 3, 3], enc_conv_s=[1, 2, 2], enc_conv_p=[1, 1, 1],
+    dec_conv_k=[4, 4, 3], dec_conv_s=[2, 2, 1], dec_conv_p=[1, 1, 1],
+    enc_rnn_k=[3, 3, 3], enc_rnn_p=[1, 1, 1], dec_rnn_k=[3, 3, 3], dec_rnn_p=[1, 1, 1],
+    enc_conv_names=["conv1_leaky_1", "conv2_leaky_1", "conv3_leaky_1"],
+    dec_conv_names=["deconv1_leaky_1", "deconv2_leaky_1", "deconv3_leaky_1"],
+    final_conv_2_name="conv3_3",
+)
+PREDRNN_DEFAULTS = dict(                  # models/predrnn_v2.py:34-43
+    patch_size=4, num_layers=3, num_hidden=[128, 128, 128, 128], filter_size=5,
+    decoupling_loss_scale=100.0,
+)
+PHYDNET_DEFAULTS = dict(                  # models/phydnet.py:28-33
+    phycell_n_layers=1, phycell_channels=49, phycell_kernel_size=(7, 7),
+    convlstm_n_layers=3, convlstm_hidden_dims=[128, 128, 64], convlstm_kernel_size=(3, 3),
+)
+
+
+# --------------------------------------------------------------------------------------------------
+# convlstm-shi  (EF_ConvLSTM)
+# --------------------------------------------------------------------------------------------------
+def _ef_rnn(sd, prefix, inputs, states, seq_len, in_channels, pad):
+    """One hzzone ConvLSTM driver with parameters below ``prefix``.  Peepholes missing from the state
+    dict (CUDA-constructed reference) are zeros."""
+    w, b = sd[prefix + "_conv.weight"], sd[prefix + "_conv.bias"]
+    C = w.shape[0] // 4
+    if states is not None:
+        hw = states[0].shape[-2:]
+    else:
+        hw = inputs.shape[-2:]
+    zeros = torch.zeros(1, C, *hw)
+    wci = sd.get(prefix + "Wci", zeros)
+    wcf = sd.get(prefix + "Wcf", zeros)
+    wco = sd.get(prefix + "Wco", zeros)
+    return B.convlstm_shi_sequence(inputs, states, seq_len, w, b, wci, wcf, wco, in_channels, pad)
+
+
+def ef_convlstm_forward(sd, x, pred_frames, cfg=None):
+    """EF_ConvLSTM.forward (ef_blocks.py:184-187): layer-major encoder (:67-82) then layer-major
+    forecaster (:100-114) whose top RNN is fed zeros (``inputs=None``)."""
+    cfg = {**EF_DEFAULTS, **(cfg or {})}
+    L = cfg["num_layers"]
+    b, t = x.shape[:2]
+    seq = x
+    states = []
+    for n in range(L):                                                  # Encoder.forward  :76-82
+        name = cfg["enc_conv_names"][n]
+        flat = seq.reshape(b * t, *seq.shape[2:])                       # forward_by_stage :68-71
+        flat = F.conv2d(flat, sd[f"encoder.stage{n + 1}.{name}.weight"], sd[f"encoder.stage{n + 1}.{name}.bias"],
+                        stride=cfg["enc_conv_s"][n], padding=cfg["enc_conv_p"][n])
+        flat = F.leaky_relu(flat, 0.2)                                  # _make_layers :45
+        seq = flat.reshape(b, t, *flat.shape[1:])
+        seq, st = _ef_rnn(sd, f"encoder.rnn{n + 1}.", seq, None, t, seq.shape[2], cfg["enc_rnn_p"][n])
+        states.append(st)
+
+    seq = None
+    for n in range(L):                                                  # Forecaster.forward :108-114
+        idx = L - n                                                     # rnn3/stage3 first
+        in_c = cfg["enc_c"][-1] if n == 0 else cfg["dec_c"][2 * n - 1]
+        seq, _ = _ef_rnn(sd, f"forecaster.rnn{idx}.", seq, states[idx - 1], pred_frames, in_c, cfg["dec_rnn_p"][n])
+        name = cfg["dec_conv_names"][n]
+        flat = seq.reshape(b * pred_frames, *seq.shape[2:])
+        flat = F.conv_transpose2d(flat, sd[f"forecaster.stage{idx}.{name}.weight"],
+                                  sd[f"forecaster.stage{idx}.{name}.bias"],
+                                  stride=cfg["dec_conv_s"][n], padding=cfg["dec_conv_p"][n])
+        flat = F.leaky_relu(flat, 0.2)
+        if n == L - 1:                                                  # identity + final 1x1 conv  (ef_conv_lstm.py:99-104)
+            fname = cfg["final_conv_2_name"]
+            flat = F.conv2d(flat, sd[f"forecaster.stage{idx}.{fname}.weight"], sd[f"forecaster.stage{idx}.{fname}.bias"])
+        seq = flat.reshape(b, pred_frames, *flat.shape[1:])
+    return seq, None
+
+
+# --------------------------------------------------------------------------------------------------
+# predrnn-pp  (PredRNN_V2, non action-conditional, layer_norm=False, eval)
+# --------------------------------------------------------------------------------------------------
+def reshape_patch(x, p):
+    """predrnn_v2.py:232-240 -- channel order (p_h, p_w, c)."""
+    b, t, c, h, w = x.shape
+    x = x.reshape(b, t, c, h // p, p, w // p, p).permute(0, 1, 4, 6, 2, 3, 5)
+    return x.reshape(b, t, p * p * c, h // p, w // p)
+
+
+def reshape_patch_back(xp, p):
+    """predrnn_v2.py:242-250."""
+    b, t, cpp, hp, wp = xp.shape
+    c = cpp // (p * p)
+    xp = xp.reshape(b, t, p, p, c, hp, wp).permute(0, 1, 4, 5, 2, 6, 3)
+    return xp.reshape(b, t, c, hp * p, wp * p)
+
+
+def predrnn_v2_forward(sd, x, pred_frames, cfg=None, return_states=False):
+    """PredRNN_V2.forward in eval mode (predrnn_v2.py:131-230).  ``x`` holds context + target frames (:134-137);
+    the eval mask is all zeros (:300-309) so from t >= context_frames the model's own x_gen is the input
+    (:172-176); zig-zag ``memory`` (:196-204); decouple loss over all (t, layer) (:197-211, :229)."""
+    cfg = {**PREDRNN_DEFAULTS, **(cfg or {})}
+    p, L, hid = cfg["patch_size"], cfg["num_layers"], cfg["num_hidden"]
+    b, total = x.shape[:2]
+    ctx = total - pred_frames
+    if ctx < 1:
+        raise ValueError("input must hold context and target frames")
+    xp = reshape_patch(x, p)
+    hp, wp = xp.shape[-2:]
+    h_t = [torch.zeros(b, hid[i], hp, wp) for i in range(L)]
+    c_t = [torch.zeros(b, hid[i], hp, wp) for i in range(L)]
+    memory = torch.zeros(b, hid[0], hp, wp)
+    w_adapter = sd["adapter.weight"]
+    x_gen = None
+    frames, dec = [], []
+    for t in range(total - 1):
+        net = xp[:, t] if t < ctx else x_gen
+        for i in range(L):
+            inp = net if i == 0 else h_t[i - 1]
+            pre = f"cell_list.{i}."
+            h_t[i], c_t[i], memory, dc, dm = B.stlstm_step(
+                inp, h_t[i], c_t[i], memory, sd[pre + "conv_x.0.weight"], sd[pre + "conv_h.0.weight"],
+                sd[pre + "conv_m.0.weight"], sd[pre + "conv_o.0.weight"], sd[pre + "conv_last.weight"])
+            dcn = F.normalize(F.conv2d(dc, w_adapter).flatten(2), dim=2)
+            dmn = F.normalize(F.conv2d(dm, w_adapter).flatten(2), dim=2)
+            dec.append(torch.mean(torch.abs(F.cosine_similarity(dcn, dmn, dim=2))))
+        x_gen = F.conv2d(h_t[L - 1], sd["conv_last.weight"])
+        frames.append(x_gen)
+    pred = reshape_patch_back(torch.stack(frames[-pred_frames:], dim=1), p)
+    loss = cfg["decoupling_loss_scale"] * torch.mean(torch.stack(dec))
+    out = (pred, {"ST-LSTM decouple loss": loss})
+    if return_states:
+        return out + ((h_t, c_t, memory),)
+    return out
+
+
+# --------------------------------------------------------------------------------------------------
+# phy  (PhyDNet, non action-conditional, eval)  and the cfg-2 composition (its residual branch alone)
+# --------------------------------------------------------------------------------------------------
+def _convcell_stack(sd, prefix, frame, H, C, n_layers):
+    """SingleStepConvLSTM.forward (model_blocks/phydnet.py:147-163) for one frame; H, C are lists (mutated)."""
+    inp = frame
+    for j in range(n_layers):
+        H[j], C[j] = B.convlstm_cell_step(inp, H[j], C[j], sd[f"{prefix}cell_list.{j}.conv.weight"],
+                                          sd[f"{prefix}cell_list.{j}.conv.bias"])
+        inp = H[j]
+    return H[-1]
+
+
+def phydnet_forward(sd, x, pred_frames, cfg=None):
+    """PhyDNet.forward in eval mode (models/phydnet.py:94-137) with encoder_fwd (:73-89): T_in-1 warm-up steps
+    on context frames, then autoregression from the last context frame.  Only ``output_image`` (:87-88) is
+    computed -- the two visualisation-only decoder passes (:84-85) do not influence the result."""
+    cfg = {**PHYDNET_DEFAULTS, **(cfg or {})}
+    b, t_in = x.shape[:2]
+    hd = cfg["convlstm_hidden_dims"]
+    nl = cfg["convlstm_n_layers"]
+    n_phy = cfg["phycell_n_layers"]
+    state = {}
+
+    def step(frame, first):
+        e = B.dcgan_encoder(frame, sd, "encoder_E.")
+        ep = B.encoder_split(e, sd, "encoder_Ep.")
+        er = B.encoder_split(e, sd, "encoder_Er.")
+        if first:                                                        # init_hidden (:107-111, :165-171)
+            state["Hp"] = [torch.zeros_like(ep) for _ in range(n_phy)]
+            state["H"] = [torch.zeros(b, hd[j], *er.shape[-2:]) for j in range(nl)]
+            state["C"] = [torch.zeros(b, hd[j], *er.shape[-2:]) for j in range(nl)]
+        inp = ep
+        for j in range(n_phy):                                           # PhyCell.forward :95-105
+            state["Hp"][j] = B.phycell_step(inp, state["Hp"][j], B._sub(sd, f"phycell.cell_list.{j}."))
+            inp = state["Hp"][j]
+        out_r = _convcell_stack(sd, "convcell.", er, state["H"], state["C"], nl)
+        dp = B.decoder_split(state["Hp"][-1], sd, "decoder_Dp.")
+        dr = B.decoder_split(out_r, sd, "decoder_Dr.")
+        return torch.sigmoid(B.dcgan_decoder(dp + dr, sd, "decoder_D."))
+
+    idx = 0
+    for ei in range(t_in - 1):
+        step(x[:, ei], idx == 0)
+        idx += 1
+    frame = x[:, t_in - 1]
+    outs = []
+    for _ in range(pred_frames):
+        frame = step(frame, idx == 0)
+        outs.append(frame)
+        idx += 1
+    return torch.stack(outs, dim=1), None
+
+
+def convlstm_branch_forward(sd, x, pred_frames, cfg=None):
+    """BASELINE config 2 ("custom ConvLSTM: encoder + stacked ConvLSTM cells"): OUR composition of reference
+    blocks -- PhyDNet's residual branch alone:
+    DCGANEncoder -> EncoderSplit -> SingleStepConvLSTM[128,128,64] -> DecoderSplit -> DCGANDecoder -> sigmoid,
+    driven with PhyDNet's rollout schedule (T_in-1 warm-up steps, then autoregression).  The cells and blocks
+    are pinned by the reference; the composition is not a registered reference model."""
+    cfg = {**PHYDNET_DEFAULTS, **(cfg or {})}
+    b, t_in = x.shape[:2]
+    hd, nl = cfg["convlstm_hidden_dims"], cfg["convlstm_n_layers"]
+    state = {}
+
+    def step(frame, first):
+        er = B.encoder_split(B.dcgan_encoder(frame, sd, "encoder_E."), sd, "encoder_Er.")
+        if first:
+            state["H"] = [torch.zeros(b, hd[j], *er.shape[-2:]) for j in range(nl)]
+            state["C"] = [torch.zeros(b, hd[j], *er.shape[-2:]) for j in range(nl)]
+        out_r = _convcell_stack(sd, "convcell.", er, state["H"], state["C"], nl)
+        return torch.sigmoid(B.dcgan_decoder(B.decoder_split(out_r, sd, "decoder_Dr."), sd, "decoder_D."))
+
+    for ei in range(t_in - 1):
+        step(x[:, ei], ei == 0)
+    frame = x[:, t_in - 1]
+    outs = []
+    for di in range(pred_frames):
+        frame = step(frame, t_in == 1 and di == 0)
+        outs.append(frame)
+    return torch.stack(outs, dim=1), None
+
+
+FORWARDS = {
+    "convlstm-shi": ef_convlstm_forward,
+    "predrnn-pp": predrnn_v2_forward,
+    "phy": phydnet_forward,
+    "convlstm-branch": convlstm_branch_forward,
+}
