@@ -1,0 +1,151 @@
+"""GPU parity: the CUDA path (through the C ABI) against the golden vectors of the reference and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fp32-operand mode <= 1e-4 max abs; bf16-operand mode <= 5e-3 on the first
+predicted frame and <= 2e-2 at the end of the rollout.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from oracle import models as OM
+from oracle.weights import synth_state_dict, synth_frames
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_TOL_FIRST = 5e-3
+BF16_TOL_LAST = 2e-2
+
+
+def _cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return "cuda:0"
+
+
+def _build(key, meta, **kw):
+    import vp_suite_b200 as V
+    dev = _cuda()
+    m = V.MODEL_CLASSES[key](dev, img_shape=tuple(meta["img_shape"]), action_size=0, tensor_value_range=[0.0, 1.0],
+                             **kw).eval()
+    sd = synth_state_dict(meta["shapes"], meta["wseed"], meta["gain"])
+    m.load_state_dict(sd)
+    return m, sd
+
+
+def _input(meta):
+    t = meta["context"] + (meta["pred"] if meta["key"] == "predrnn-pp" else 0)
+    return synth_frames(meta["batch"], t, *meta["img_shape"], seed=meta["xseed"])
+
+
+def _frame_errs(a, b):
+    d = np.abs(a - b)
+    return [float(d[:, t].max()) for t in range(d.shape[1])]
+
+
+EF_CASES = ["ef_1x64", "ef_3x32"]
+
+
+@pytest.mark.parametrize("name", EF_CASES)
+def test_fp32_mode_matches_reference_golden(manifest, name):
+    meta = manifest["models"][name]
+    m, sd = _build(meta["key"], meta, precision="fp32")
+    x = _input(meta)
+    with torch.no_grad():
+        pred, aux = m(x.cuda(), pred_frames=meta["pred"])
+    gold = load_golden(name)
+    errs = _frame_errs(pred.cpu().numpy(), gold["pred"])
+    assert max(errs) <= FP32_TOL, f"{name}: per-frame max abs err {errs}"
+    assert m.last_launch_count() > 0
+
+
+@pytest.mark.parametrize("backend", ["simt", "auto"])
+@pytest.mark.parametrize("name", EF_CASES)
+def test_bf16_mode_within_tolerance(manifest, name, backend):
+    meta = manifest["models"][name]
+    m, sd = _build(meta["key"], meta, precision="bf16", backend=backend)
+    x = _input(meta)
+    with torch.no_grad():
+        pred, aux = m(x.cuda(), pred_frames=meta["pred"])
+    gold = load_golden(name)
+    errs = _frame_errs(pred.cpu().numpy(), gold["pred"])
+    assert errs[0] <= BF16_TOL_FIRST, f"{name}/{backend}: first-frame err {errs}"
+    assert max(errs) <= BF16_TOL_LAST, f"{name}/{backend}: rollout err {errs}"
+
+
+@pytest.mark.parametrize("name", EF_CASES)
+def test_tcgen05_agrees_with_cuda_core_kernel(manifest, name):
+    """Same bf16 operands, fp32 accumulation: the two kernels may only differ by summation order and by the bf16
+    rounding of h that this flips now and then."""
+    meta = manifest["models"][name]
+    x = _input(meta).cuda()
+    outs = []
+    for backend in ("simt", "auto"):
+        m, _ = _build(meta["key"], meta, precision="bf16", backend=backend)
+        with torch.no_grad():
+            outs.append(m(x, pred_frames=meta["pred"])[0].cpu().numpy())
+    errs = _frame_errs(outs[0], outs[1])
+    assert max(errs) <= 2e-3, f"{name}: tcgen05 vs CUDA-core per-frame diff {errs}"
+
+
+def test_ef_ten_frame_rollout_vs_oracle(manifest):
+    """cfg-1 shape (1x64x64, 10 context + 10 predicted) at a batch the CPU oracle finishes in seconds."""
+    meta = dict(manifest["models"]["ef_1x64"])
+    meta.update(batch=2, context=10, pred=10, xseed=7)
+    x = _input(meta)
+    sd = synth_state_dict(meta["shapes"], meta["wseed"], meta["gain"])
+    with torch.no_grad():
+        ref, _ = OM.ef_convlstm_forward(sd, x, 10)
+    for precision, tol_first, tol_last in (("fp32", FP32_TOL, FP32_TOL), ("bf16", BF16_TOL_FIRST, BF16_TOL_LAST)):
+        m, _ = _build(meta["key"], meta, precision=precision)
+        with torch.no_grad():
+            pred, _ = m(x.cuda(), pred_frames=10)
+        errs = _frame_errs(pred.cpu().numpy(), ref.numpy())
+        assert errs[0] <= tol_first and max(errs) <= tol_last, f"{precision}: {errs}"
+
+
+def test_ef_microbatching_and_graph_are_invisible(manifest):
+    """Batch split into microbatches (incl. a ragged tail) and CUDA-graph replay give the same frames."""
+    meta = dict(manifest["models"]["ef_3x32"])
+    meta.update(batch=5)
+    x = _input(meta).cuda()
+    m0, _ = _build(meta["key"], meta, precision="bf16")
+    m1, _ = _build(meta["key"], meta, precision="bf16", max_microbatch=2)
+    m2, _ = _build(meta["key"], meta, precision="bf16", max_microbatch=2, use_cuda_graph=True)
+    with torch.no_grad():
+        a = m0(x, pred_frames=3)[0]
+        b = m1(x, pred_frames=3)[0]
+        c = m2(x, pred_frames=3)[0]
+        c2 = m2(x, pred_frames=3)[0]
+    assert torch.equal(a, b)
+    assert torch.equal(a, c) and torch.equal(c, c2)
+
+
+def test_ef_forward_host_matches_device_path(manifest):
+    meta = dict(manifest["models"]["ef_3x32"])
+    meta.update(batch=3)
+    x = _input(meta)
+    m, _ = _build(meta["key"], meta, precision="bf16", max_microbatch=2)
+    with torch.no_grad():
+        a = m(x.cuda(), pred_frames=2)[0].cpu()
+        b, _ = m.forward_host(x.pin_memory(), pred_frames=2)
+    assert torch.equal(a, b)
+
+
+def test_ef_pred_1_and_missing_peepholes(manifest):
+    meta = manifest["models"]["ef_3x32"]
+    m, sd = _build(meta["key"], meta, precision="fp32")
+    x = _input(meta).cuda()
+    with torch.no_grad():
+        p1 = m.pred_1(x)
+        full = m(x, pred_frames=1)[0]
+    assert p1.shape == (meta["batch"], *meta["img_shape"])
+    assert torch.equal(p1, full[:, 0])
+    # CUDA-built reference checkpoints have no Wci/Wcf/Wco: zeros
+    sd_nopeep = {k: v for k, v in sd.items() if k.rsplit(".", 1)[-1] not in ("Wci", "Wcf", "Wco")}
+    m.load_state_dict(sd_nopeep)
+    with torch.no_grad():
+        got = m(x, pred_frames=2)[0].cpu()
+        ref, _ = OM.ef_convlstm_forward(sd_nopeep, x.cpu(), 2)
+    assert (got - ref).abs().max() <= FP32_TOL

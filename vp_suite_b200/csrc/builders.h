@@ -1,0 +1,171 @@
+// Spec builders shared by the rollouts and the single-cell entry points: each returns the generalised-convolution
+// spec of one reference operation.
+#pragma once
+#include "lowering.h"
+
+namespace vpk {
+
+struct ActInfo {          // activation storage of the current precision mode
+  int dtype;
+  int esize;
+};
+
+inline SrcView make_view(const void* p, int H, int W, int C) {
+  return SrcView{p, H, W, C, static_cast<long long>(H) * W * C, static_cast<long long>(W) * C, C};
+}
+// channels [c_off, c_off + C) of a dense NHWC tensor with C_total channels
+inline SrcView make_channel_view(const void* p, int H, int W, int C_total, int c_off, int C, int esize) {
+  return SrcView{static_cast<const char*>(p) + static_cast<size_t>(c_off) * esize, H, W, C,
+                 static_cast<long long>(H) * W * C_total, static_cast<long long>(W) * C_total, C_total};
+}
+
+inline void dense_out(EpiParams& e, void* out, int H, int W, int C) {
+  e.out = out;
+  e.oB = static_cast<long long>(H) * W * C;
+  e.oY = static_cast<long long>(W) * C;
+  e.oX = C;
+  e.oC = 1;
+}
+
+// ConvLSTM gate conv + fused update.
+//   reference: ConvLSTM.forward loop body (model_blocks/conv_lstm_hzzone.py:52-69), rows (i,f,g,o), peepholes
+//              ConvLSTMCell.forward (model_blocks/conv_lstm_ndrplz.py:28-43), rows (i,f,o,g), no peepholes
+//   x may be null (zero input, conv_lstm_hzzone.py:54-56): its K-steps are dropped, not multiplied.
+struct LstmArgs {
+  std::string name;
+  int B, H, W, Cin, C, k;
+  const void* x;            // [B,H,W,Cin] activation type or nullptr
+  const void* h_in;         // [B,H,W,C]
+  void* h_out;              // [B,H,W,C] (must differ from h_in)
+  float* c;                 // [B,H,W,C] fp32, updated in place
+  const float* weight;      // host [4C, Cin+C, k, k]
+  const float* bias;        // host [4C] or nullptr
+  bool order_ifog;          // true: reference rows are (i,f,o,g)
+  const float *wci, *wcf, *wco;   // device fp32 [H,W,C] or nullptr
+};
+inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
+  ConvSpec s;
+  s.name = a.name;
+  s.B = a.B;
+  s.G = 4;
+  s.C = a.C;
+  s.is_gate_gemm = true;
+  WeightRef w;
+  w.w = a.weight;
+  w.O = 4 * a.C;
+  w.I = a.Cin + a.C;
+  w.KH = w.KW = a.k;
+  const int hz[4] = {0, 1, 2, 3}, nd[4] = {0, 1, 3, 2};   // packed gates are always (i, f, g, o)
+  for (int g = 0; g < 4; ++g) w.gate_block[g] = a.order_ifog ? nd[g] : hz[g];
+  s.wrefs.push_back(w);
+  if (a.bias) {
+    BiasRef b;
+    b.b = a.bias;
+    for (int g = 0; g < 4; ++g) b.gate_block[g] = w.gate_block[g];
+    s.biases.push_back(b);
+  }
+  std::vector<ConvInput> in;
+  if (a.x) in.push_back(ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0});
+  in.push_back(ConvInput{make_view(a.h_in, a.H, a.W, a.C), 0, a.Cin});
+  int oh, ow;
+  lower_conv(s, a.k, 1, a.k / 2, in, a.H, a.W, act.esize, &oh, &ow);
+  EpiParams& e = s.phases[0].epi;
+  e.kind = EPI_LSTM;
+  e.s0 = a.c;
+  e.p0 = a.wci;
+  e.p1 = a.wcf;
+  e.p2 = a.wco;
+  dense_out(e, a.h_out, a.H, a.W, a.C);
+  return s;
+}
+
+// Conv2d(k, stride, pad) + bias + activation, NHWC activation-type output (dense) or fp32 output with explicit strides.
+struct ConvArgs {
+  std::string name;
+  int B, H, W, Cin, Cout, k, stride, pad;
+  const void* x;
+  const float* weight;      // host [Cout, Cin, k, k]
+  const float* bias;        // host [Cout] or nullptr
+  int act;
+  void* out;                // dense [B, OH, OW, Cout] activation type unless f32_strided
+  bool f32_strided = false; // out is float*, strides below
+  long long oB = 0, oY = 0, oX = 0, oC = 0;
+};
+inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* ow) {
+  ConvSpec s;
+  s.name = a.name;
+  s.B = a.B;
+  s.G = 1;
+  s.C = a.Cout;
+  WeightRef w;
+  w.w = a.weight;
+  w.O = a.Cout;
+  w.I = a.Cin;
+  w.KH = w.KW = a.k;
+  s.wrefs.push_back(w);
+  if (a.bias) {
+    BiasRef b;
+    b.b = a.bias;
+    s.biases.push_back(b);
+  }
+  lower_conv(s, a.k, a.stride, a.pad, {ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0}}, a.H, a.W, act.esize, oh, ow);
+  EpiParams& e = s.phases[0].epi;
+  e.kind = EPI_BIAS_ACT;
+  e.act = a.act;
+  if (a.f32_strided) {
+    e.out = a.out;
+    e.out_f32 = 1;
+    e.oB = a.oB; e.oY = a.oY; e.oX = a.oX; e.oC = a.oC;
+  } else {
+    dense_out(e, a.out, *oh, *ow, a.Cout);
+  }
+  return s;
+}
+
+// ConvTranspose2d(k, stride, pad, output_padding) + bias + activation, dense NHWC activation-type output
+// (weight layout [Cin, Cout, k, k]); one launch per output parity.
+struct DeconvArgs {
+  std::string name;
+  int B, H, W, Cin, Cout, k, stride, pad, out_pad;
+  const void* x;
+  const float* weight;
+  const float* bias;
+  int act;
+  void* out;                // dense [B, OH, OW, Cout]
+};
+inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
+  ConvSpec s;
+  s.name = a.name;
+  s.B = a.B;
+  s.G = 1;
+  s.C = a.Cout;
+  WeightRef w;
+  w.w = a.weight;
+  w.O = a.Cout;
+  w.I = a.Cin;
+  w.KH = w.KW = a.k;
+  w.transposed = true;
+  s.wrefs.push_back(w);
+  if (a.bias) {
+    BiasRef b;
+    b.b = a.bias;
+    s.biases.push_back(b);
+  }
+  const int C = a.Cout, esz = act.esize, actk = a.act;
+  void* out = a.out;
+  lower_conv_transpose(s, a.k, a.stride, a.pad, a.out_pad, ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0}, a.H, a.W,
+                       oh, ow, [=](int ry, int rx, int stride, int OH, int OW) {
+                         EpiParams e{};
+                         e.kind = EPI_BIAS_ACT;
+                         e.act = actk;
+                         e.out = static_cast<char*>(out) + (static_cast<size_t>(ry) * OW + rx) * C * esz;
+                         e.oB = static_cast<long long>(OH) * OW * C;
+                         e.oY = static_cast<long long>(stride) * OW * C;
+                         e.oX = static_cast<long long>(stride) * C;
+                         e.oC = 1;
+                         return e;
+                       });
+  return s;
+}
+
+}  // namespace vpk

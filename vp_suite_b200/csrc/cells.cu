@@ -1,0 +1,190 @@
+// Single-step cells (VPModelBlock boundary): NCHW fp32 in/out, internally the same generalised-conv launches as the
+// rollouts.  The handle owns its scratch (activation-layout copies of the operands) per batch size.
+#include "cells.h"
+
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/vpk.h"
+#include "builders.h"
+#include "elementwise.h"
+#include "stlstm.h"
+
+namespace vpk {
+
+namespace {
+
+class CellBase : public Cell {
+ public:
+  CellBase(int precision, int backend_) : backend(backend_) {
+    dtype = (precision == VPK_PREC_BF16) ? DT_BF16 : DT_F32;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      VPK_THROW(2, "no CUDA device: libvpk has no CPU fallback");
+    }
+    int dev = 0, sms = 0;
+    VPK_CUDA(cudaGetDevice(&dev));
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) num_sms = sms;
+  }
+  ~CellBase() override {
+    for (auto& kv : scratch) cudaFree(kv.second.first);
+  }
+
+ protected:
+  int dtype, backend, num_sms = 148;
+  DeviceStore store;
+  std::map<std::string, std::vector<PackedWeights>> cache;
+  std::map<std::string, std::pair<void*, size_t>> scratch;
+  int built_batch = -1;
+  std::vector<BuiltConv> convs;
+
+  int esize() const { return static_cast<int>(dtype_size(dtype)); }
+  ActInfo act() const { return ActInfo{dtype, esize()}; }
+
+  void* buf(const std::string& name, size_t bytes) {
+    auto it = scratch.find(name);
+    if (it != scratch.end() && it->second.second >= bytes) return it->second.first;
+    if (it != scratch.end()) {
+      cudaFree(it->second.first);
+      scratch.erase(it);
+      built_batch = -1;
+    }
+    void* p = nullptr;
+    VPK_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 256)));
+    scratch[name] = {p, bytes};
+    return p;
+  }
+  void to_nhwc(const float* src, void* dst, int out_dtype, int B, int C, int H, int W, cudaStream_t s) {
+    launch_frames_to_nhwc(src, dst, out_dtype, B, 1, C, H, W, num_sms, s);
+  }
+  void run(const BuiltConv& bc, cudaStream_t s) {
+    if (bc.use_tc) launch_conv_tc(bc.tc, s);
+    else launch_conv_simt(bc.L, dtype, s);
+  }
+  void add(const ConvSpec& spec, cudaStream_t s) {
+    for (BuiltConv& bc : build_conv(spec, dtype, backend, store, cache, s, num_sms, false)) convs.push_back(bc);
+  }
+  void finish_build(cudaStream_t s) {
+    VPK_CUDA(cudaStreamSynchronize(s));
+    store.staging.clear();
+  }
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+class ConvLstmCell : public CellBase {
+ public:
+  ConvLstmCell(int precision, int backend_, int cin_, int ch_, int h_, int w_, int k_, int order, const float* weight,
+               const float* bias)
+      : CellBase(precision, backend_), cin(cin_), ch(ch_), h(h_), w(w_), k(k_), ifog(order == 1) {
+    VPK_REQUIRE(cin >= 0 && ch > 0 && h > 0 && w > 0 && k % 2 == 1, "bad ConvLSTM cell shape");
+    hw.assign(weight, weight + static_cast<size_t>(4) * ch * (cin + ch) * k * k);
+    if (bias) hb.assign(bias, bias + 4 * ch);
+  }
+  // in: x, h, c, wci, wcf, wco   out: h', c'
+  void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    const float* x = in[0];
+    const bool peep = in[3] != nullptr;
+    VPK_REQUIRE(!peep || (in[4] && in[5]), "peepholes must be given together");
+    const size_t px = static_cast<size_t>(B) * h * w;
+    void* xb = buf("x", px * std::max(cin, 1) * esize());
+    void* hi = buf("h_in", px * ch * esize());
+    void* ho = buf("h_out", px * ch * esize());
+    float* cb = static_cast<float*>(buf("c", px * ch * sizeof(float)));
+    float* pw[3] = {nullptr, nullptr, nullptr};
+    if (peep)
+      for (int i = 0; i < 3; ++i) pw[i] = static_cast<float*>(buf("peep" + std::to_string(i), sizeof(float) * ch * h * w));
+    const int variant = (x ? 1 : 0) | (peep ? 2 : 0);
+    if (built_batch != B || built_variant != variant) {
+      convs.clear();
+      LstmArgs a{std::string("cell.") + (x ? "xh" : "h"), B, h, w, cin, ch, k, x ? xb : nullptr, hi, ho, cb, hw.data(),
+                 hb.empty() ? nullptr : hb.data(), ifog, pw[0], pw[1], pw[2]};
+      add(lstm_spec(a, act()), s);
+      finish_build(s);
+      built_batch = B;
+      built_variant = variant;
+    }
+    if (x) to_nhwc(x, xb, dtype, B, cin, h, w, s);
+    to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
+    to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
+    if (peep)
+      for (int i = 0; i < 3; ++i) to_nhwc(in[3 + i], pw[i], DT_F32, 1, ch, h, w, s);
+    for (const BuiltConv& bc : convs) run(bc, s);
+    launch_nhwc_to_nchw(ho, dtype, out[0], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(cb, DT_F32, out[1], B, ch, h, w, num_sms, s);
+  }
+
+ private:
+  int cin, ch, h, w, k;
+  bool ifog;
+  int built_variant = -1;
+  std::vector<float> hw, hb;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+class StLstmCell : public CellBase {
+ public:
+  StLstmCell(int precision, int backend_, int cin_, int ch_, int h_, int w_, int k_, const float* w_x, const float* w_h,
+             const float* w_m, const float* w_o, const float* w_last)
+      : CellBase(precision, backend_), cin(cin_), ch(ch_), h(h_), w(w_), k(k_) {
+    VPK_REQUIRE(cin > 0 && ch > 0 && h > 0 && w > 0 && k % 2 == 1, "bad ST-LSTM cell shape");
+    const size_t kk = static_cast<size_t>(k) * k;
+    wx.assign(w_x, w_x + 7 * ch * cin * kk);
+    wh.assign(w_h, w_h + 4 * ch * ch * kk);
+    wm.assign(w_m, w_m + 3 * ch * ch * kk);
+    wo.assign(w_o, w_o + static_cast<size_t>(ch) * 2 * ch * kk);
+    wl.assign(w_last, w_last + static_cast<size_t>(ch) * 2 * ch);
+  }
+  // in: x, h, c, m    out: h', c', m', delta_c, delta_m
+  void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    const size_t px = static_cast<size_t>(B) * h * w;
+    void* xb = buf("x", px * cin * esize());
+    void* hi = buf("h_in", px * ch * esize());
+    void* mi = buf("m_in", px * ch * esize());
+    void* ho = buf("h_out", px * ch * esize());
+    void* mem = buf("mem", px * 2 * ch * esize());
+    void* dc = buf("dc", px * ch * esize());
+    void* dm = buf("dm", px * ch * esize());
+    float* cb = static_cast<float*>(buf("c", px * ch * sizeof(float)));
+    float* mb = static_cast<float*>(buf("m", px * ch * sizeof(float)));
+    float* op = static_cast<float*>(buf("o_part", px * ch * sizeof(float)));
+    if (built_batch != B) {
+      convs.clear();
+      StLstmArgs a{"cell.", B, h, w, cin, ch, k, xb, hi, make_view(mi, h, w, ch), ho, cb, mb, op, mem, dc, dm,
+                   wx.data(), wh.data(), wm.data(), wo.data(), wl.data()};
+      for (const ConvSpec& sp : stlstm_specs(a, act())) add(sp, s);
+      finish_build(s);
+      built_batch = B;
+    }
+    to_nhwc(in[0], xb, dtype, B, cin, h, w, s);
+    to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
+    to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
+    to_nhwc(in[3], mi, dtype, B, ch, h, w, s);
+    to_nhwc(in[3], mb, DT_F32, B, ch, h, w, s);
+    for (const BuiltConv& bc : convs) run(bc, s);
+    launch_nhwc_to_nchw(ho, dtype, out[0], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(cb, DT_F32, out[1], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(mb, DT_F32, out[2], B, ch, h, w, num_sms, s);
+    if (out[3]) launch_nhwc_to_nchw(dc, dtype, out[3], B, ch, h, w, num_sms, s);
+    if (out[4]) launch_nhwc_to_nchw(dm, dtype, out[4], B, ch, h, w, num_sms, s);
+  }
+
+ private:
+  int cin, ch, h, w, k;
+  std::vector<float> wx, wh, wm, wo, wl;
+};
+
+}  // namespace
+
+Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, int gate_order,
+                         const float* weight, const float* bias) {
+  return new ConvLstmCell(precision, backend, cin, ch, h, w, k, gate_order, weight, bias);
+}
+
+Cell* make_stlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* w_x,
+                       const float* w_h, const float* w_m, const float* w_o, const float* w_last) {
+  return new StLstmCell(precision, backend, cin, ch, h, w, k, w_x, w_h, w_m, w_o, w_last);
+}
+
+}  // namespace vpk

@@ -1,0 +1,22 @@
+// Single-step cells behind the VPModelBlock boundary (fp32 NCHW device tensors in and out).
+#pragma once
+#include "common.h"
+
+namespace vpk {
+
+class Cell {
+ public:
+  virtual ~Cell() {}
+  // in / out: up to 8 device pointers each, meaning defined per cell kind (see api.cu)
+  virtual void step(int batch, const float* const* in, float* const* out, cudaStream_t stream) = 0;
+};
+
+Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, int gate_order,
+                         const float* weight, const float* bias);
+Cell* make_stlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* w_x,
+                       const float* w_h, const float* w_m, const float* w_o, const float* w_last);
+Cell* make_phycell_cell(int precision, int backend, int ch, int hid, int h, int w, int k, const float* conv1_w,
+                        const float* conv1_b, const float* gn_w, const float* gn_b, const float* conv2_w,
+                        const float* conv2_b, const float* gate_w, const float* gate_b);
+
+}  // namespace vpk

@@ -1,0 +1,114 @@
+// Shared host/device definitions of libvpk (the generalised convolution "launch" every hot-path op lowers to).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace vpk {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define VPK_THROW(code, msg) throw ::vpk::Error((code), std::string(msg))
+#define VPK_REQUIRE(cond, msg)                                              \
+  do {                                                                      \
+    if (!(cond)) VPK_THROW(1, std::string(msg) + " [" #cond "]");           \
+  } while (0)
+#define VPK_CUDA(expr)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (expr);                                                                             \
+    if (e_ != cudaSuccess)                                                                               \
+      VPK_THROW(2, std::string(#expr) + " failed: " + cudaGetErrorString(e_) + " (" __FILE__ ":" +       \
+                       std::to_string(__LINE__) + ")");                                                  \
+  } while (0)
+
+enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+__host__ __device__ inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Generalised convolution launch.
+//
+// Output positions form a grid (B, H, W).  The contraction runs over a list of K-steps; step s multiplies the
+// channels [c0, c0+kc) of source view `src`, read at spatial offset (dy, dx) from the output position (zero outside
+// the view), with columns [wk, wk+kc) of the packed weight matrix Wp[N_pad][K_pad].  Ordinary convs, the concat-free
+// gate conv of the recurrent cells (x, h, m are separate sources), stride-2 convs (4 parity views of the input) and
+// transposed convs (one launch per output parity, strided output) are all instances of this.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kMaxSrc = 4;
+constexpr int kMaxSteps = 256;
+
+struct SrcView {          // NHWC view, channels contiguous; strides in elements
+  const void* base;
+  int H, W, C;
+  long long sB, sY, sX;
+};
+
+struct ConvStep {         // 12 bytes
+  short src;
+  signed char dy, dx;
+  short c0;               // first channel of the source covered by this step
+  short kc;               // valid channels (<= 64)
+  int wk;                 // column offset in the packed weights (multiple of 16)
+};
+
+enum EpiKind : int {
+  EPI_BIAS_ACT = 0,       // G=1  y = act(acc + bias)
+  EPI_LSTM = 1,           // G=4  (i,f,g,o) ConvLSTM update with optional peepholes
+  EPI_ST_C = 2,           // G=4  (i,f,g,o_part) ST-LSTM temporal-memory update
+  EPI_ST_M = 3,           // G=3  (i',f',g') ST-LSTM spatio-temporal-memory update
+  EPI_ST_O = 4,           // G=2  (conv_o, conv_last) ST-LSTM output gate
+  EPI_PHY_GATE = 5,       // G=1  PhyCell Kalman-style blend
+};
+enum ActKind : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_SIGMOID = 2, ACT_RELU = 3 };
+
+struct EpiParams {
+  int kind;
+  int C;                  // real output channels per gate
+  int act;
+  int out_f32;            // primary output element type: 0 = activation type T, 1 = float
+  const float* bias;      // packed order [N_pad] or nullptr
+  // primary output (BIAS_ACT: y; LSTM / ST_O / PHY_GATE: h'), address = out + b*oB + y*oY + x*oX + ch*oC
+  void* out;
+  long long oB, oY, oX, oC;
+  // fp32 state tensors, dense NHWC [B, H, W, C]
+  float* s0;              // LSTM: c (in/out)   ST_C: c (in/out)   ST_M: m (in/out)   ST_O: o_part (in)
+  float* s1;              // ST_C: o_part (out)
+  // peepholes, fp32 [H, W, C] (LSTM) or nullptr
+  const float *p0, *p1, *p2;
+  // secondary activation-type outputs
+  void* t0;               // ST_C / ST_M: mem buffer [B,H,W,2C] (channel offset applied by caller)
+  long long t0_pix;       // elements per pixel of t0 (2C)
+  void* t1;               // ST_C: delta_c, ST_M: delta_m   dense [B,H,W,C]
+  // PhyCell blend inputs (activation type, dense [B,H,W,C])
+  const void* q0;         // x (frame)
+  const void* q1;         // h~ = h + F(h)
+  float forget_bias;
+  // optional per-(b, group) statistics for a following GroupNorm: sums[b][g][2] (sum, sum of squares)
+  float* gn_sums;
+  int gn_group_size;      // channels per group (0 = disabled)
+};
+
+struct ConvLaunch {
+  // problem
+  int B, H, W;            // output grid
+  int nsrc;
+  SrcView src[kMaxSrc];
+  int nsteps;
+  const ConvStep* steps;  // device pointer
+  const void* wpacked;    // device, activation type, [N_pad][K_pad]
+  int K_pad, N_pad;
+  int G;                  // gates per channel; packed row n = ch*G + gate
+  int Cn;                 // channels per N tile for the tensor-core kernel (tile N = Cn*G)
+  EpiParams epi;
+  // bookkeeping
+  double flops;           // 2*M*N*K of the real (unpadded) contraction
+  int is_gate_gemm;       // counted in the gate-GEMM roofline figure
+};
+
+}  // namespace vpk

@@ -1,0 +1,31 @@
+// Launchers of the memory-bound helper kernels (elementwise.cu).
+#pragma once
+#include <algorithm>
+
+#include "common.h"
+
+namespace vpk {
+
+// x fp32 [B, T, C, H, W] -> out (activation type) [T][B][H][W][C]
+void launch_frames_to_nhwc(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int num_sms,
+                           cudaStream_t stream);
+// PredRNN patchify: x fp32 [B, T, c, H, W] -> out [T][B][H/p][W/p][p*p*c]
+void launch_patchify(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int p, int num_sms,
+                     cudaStream_t stream);
+// one patch frame [B][H/p][W/p][p*p*c] -> frame t of fp32 [B, P, c, H, W]
+void launch_unpatchify(const void* in, float* out, int dtype, int B, int P, int t, int C, int H, int W, int p,
+                       int num_sms, cudaStream_t stream);
+
+// in (activation type or fp32) [B][H][W][C] -> out fp32 [B][C][H][W]
+void launch_nhwc_to_nchw(const void* in, int dtype, float* out, int B, int C, int H, int W, int num_sms,
+                         cudaStream_t stream);
+
+// same with an explicit batch stride (elements) of x: frames of one sequence stay contiguous
+void launch_frames_to_nhwc_strided(const float* x, long long bstride, void* out, int dtype, int B, int T, int C, int H,
+                                   int W, int num_sms, cudaStream_t stream);
+void launch_cast_f32_to_bf16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);
+// PredRNN-V2 decouple loss: ad fp32 [2B][HW][C] (adapter(delta_c) then adapter(delta_m)); *acc += sum_{b,ch} |cos|
+void launch_decouple_reduce(const float* ad, int B, int HW, int C, double* acc, cudaStream_t stream);
+void launch_decouple_finalize(const double* acc, float* aux, double scale, cudaStream_t stream);
+
+}  // namespace vpk

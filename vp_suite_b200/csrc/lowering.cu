@@ -1,0 +1,257 @@
+#include "lowering.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace vpk {
+
+namespace {
+
+inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+void add_steps_for(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int wref, int ky, int kx, int wc0) {
+  for (int c0 = 0; c0 < C; c0 += 64) {
+    HostStep h{};
+    h.s.src = static_cast<short>(src);
+    h.s.dy = static_cast<signed char>(dy);
+    h.s.dx = static_cast<signed char>(dx);
+    h.s.c0 = static_cast<short>(c0);
+    h.s.kc = static_cast<short>(std::min(64, C - c0));
+    h.s.wk = 0;
+    h.wref = wref;
+    h.ky = ky;
+    h.kx = kx;
+    h.wc0 = wc0;
+    steps.push_back(h);
+  }
+}
+
+}  // namespace
+
+void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<ConvInput>& inputs, int in_h, int in_w,
+                int esize, int* oh, int* ow) {
+  VPK_REQUIRE(stride == 1 || stride == 2, "conv stride must be 1 or 2");
+  const int OH = (in_h + 2 * pad - k) / stride + 1;
+  const int OW = (in_w + 2 * pad - k) / stride + 1;
+  if (spec.phases.empty()) spec.phases.emplace_back();
+  PhaseSpec& ph = spec.phases[0];
+  ph.H = OH;
+  ph.W = OW;
+  if (stride == 1) {
+    std::vector<int> src_idx;
+    for (const ConvInput& in : inputs) {
+      VPK_REQUIRE(in.view.H == in_h && in.view.W == in_w, "conv input size mismatch");
+      src_idx.push_back(static_cast<int>(spec.srcs.size()));
+      spec.srcs.push_back(in.view);
+    }
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx)
+        for (size_t i = 0; i < inputs.size(); ++i)
+          add_steps_for(ph.steps, src_idx[i], ky - pad, kx - pad, inputs[i].view.C, inputs[i].wref, ky, kx,
+                        inputs[i].wc0);
+  } else {
+    VPK_REQUIRE(inputs.size() == 1, "stride-2 conv takes a single input");
+    VPK_REQUIRE(in_h % 2 == 0 && in_w % 2 == 0, "stride-2 conv needs even input size");
+    const ConvInput& in = inputs[0];
+    const int base_idx = static_cast<int>(spec.srcs.size());
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {   // parity view: rows py, py+2, ...; columns px, px+2, ...
+        SrcView v = in.view;
+        v.H = in_h / 2;
+        v.W = in_w / 2;
+        v.sY = in.view.sY * 2;
+        v.sX = in.view.sX * 2;
+        v.base = static_cast<const char*>(in.view.base) + (py * in.view.sY + px * in.view.sX) * esize;
+        spec.srcs.push_back(v);
+      }
+    for (int ky = 0; ky < k; ++ky) {
+      const int ty = ky - pad;
+      const int py = ((ty % 2) + 2) % 2;
+      const int dy = floordiv(ty - py, 2);
+      for (int kx = 0; kx < k; ++kx) {
+        const int tx = kx - pad;
+        const int px = ((tx % 2) + 2) % 2;
+        const int dx = floordiv(tx - px, 2);
+        add_steps_for(ph.steps, base_idx + py * 2 + px, dy, dx, in.view.C, in.wref, ky, kx, in.wc0);
+      }
+    }
+  }
+  VPK_REQUIRE(spec.srcs.size() <= static_cast<size_t>(kMaxSrc), "too many conv sources");
+  *oh = OH;
+  *ow = OW;
+}
+
+void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pad, const ConvInput& input, int in_h,
+                          int in_w, int* oh, int* ow,
+                          const std::function<EpiParams(int, int, int, int, int)>& epi_for_phase) {
+  VPK_REQUIRE(stride == 1 || stride == 2, "transposed-conv stride must be 1 or 2");
+  const int OH = (in_h - 1) * stride - 2 * pad + k + out_pad;
+  const int OW = (in_w - 1) * stride - 2 * pad + k + out_pad;
+  const int src = static_cast<int>(spec.srcs.size());
+  spec.srcs.push_back(input.view);
+  for (int ry = 0; ry < stride; ++ry)
+    for (int rx = 0; rx < stride; ++rx) {
+      PhaseSpec ph;
+      ph.H = (OH - ry + stride - 1) / stride;
+      ph.W = (OW - rx + stride - 1) / stride;
+      // y = stride*iy - pad + ky  with  y = stride*q + ry   =>   iy = q + (ry + pad - ky) / stride
+      for (int ky = 0; ky < k; ++ky) {
+        if (((ry + pad - ky) % stride + stride) % stride != 0) continue;
+        const int dy = floordiv(ry + pad - ky, stride);
+        for (int kx = 0; kx < k; ++kx) {
+          if (((rx + pad - kx) % stride + stride) % stride != 0) continue;
+          const int dx = floordiv(rx + pad - kx, stride);
+          add_steps_for(ph.steps, src, dy, dx, input.view.C, input.wref, ky, kx, input.wc0);
+        }
+      }
+      ph.epi = epi_for_phase(ry, rx, stride, OH, OW);
+      spec.phases.push_back(ph);
+    }
+  *oh = OH;
+  *ow = OW;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+void* DeviceStore::upload(const void* host, size_t bytes, cudaStream_t stream) {
+  void* d = nullptr;
+  VPK_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+  ptrs.push_back(d);
+  staging.emplace_back(static_cast<const char*>(host), static_cast<const char*>(host) + bytes);
+  VPK_CUDA(cudaMemcpyAsync(d, staging.back().data(), bytes, cudaMemcpyHostToDevice, stream));
+  return d;
+}
+void* DeviceStore::zeros(size_t bytes, cudaStream_t stream) {
+  void* d = nullptr;
+  VPK_CUDA(cudaMalloc(&d, std::max<size_t>(bytes, 16)));
+  ptrs.push_back(d);
+  VPK_CUDA(cudaMemsetAsync(d, 0, bytes, stream));
+  return d;
+}
+void DeviceStore::release() {
+  for (void* p : ptrs) cudaFree(p);
+  ptrs.clear();
+  staging.clear();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+int choose_cn(int C, int G) {
+  const int step = (G % 2 == 0) ? 8 : 16;
+  int ntiles = std::max(1, (C * G + 255) / 256);
+  for (;; ++ntiles) {
+    const int cn = round_up((C + ntiles - 1) / ntiles, step);
+    if (cn * G <= 256) return cn;
+  }
+}
+
+float weight_at(const WeightRef& w, int oc, int ic, int ky, int kx) {
+  if (!w.transposed) return w.w[((static_cast<size_t>(oc) * w.I + ic) * w.KH + ky) * w.KW + kx];
+  return w.w[((static_cast<size_t>(ic) * w.O + oc) * w.KH + ky) * w.KW + kx];
+}
+
+}  // namespace
+
+std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, DeviceStore& store,
+                                  std::map<std::string, std::vector<PackedWeights>>& cache, cudaStream_t stream,
+                                  int num_sms, bool measure_only) {
+  std::vector<BuiltConv> out;
+  const int G = spec.G, C = spec.C;
+  VPK_REQUIRE(G >= 1 && G <= 4 && C > 0, "bad conv spec");
+  const int Cn = choose_cn(C, G);
+  const int N_pad = (C + Cn - 1) / Cn * Cn * G;
+
+  std::vector<PackedWeights>* packed = nullptr;
+  if (!measure_only) {
+    auto it = cache.find(spec.name);
+    if (it == cache.end()) {
+      std::vector<PackedWeights> pw(spec.phases.size());
+      // bias (shared by the phases)
+      float* d_bias = nullptr;
+      if (!spec.biases.empty()) {
+        std::vector<float> hb(N_pad, 0.f);
+        for (const BiasRef& br : spec.biases)
+          for (int ch = 0; ch < C; ++ch)
+            for (int g = 0; g < G; ++g)
+              if (br.gate_block[g] >= 0) hb[ch * G + g] += br.b[br.gate_block[g] * C + ch];
+        d_bias = static_cast<float*>(store.upload(hb.data(), hb.size() * sizeof(float), stream));
+      }
+      for (size_t p = 0; p < spec.phases.size(); ++p) {
+        std::vector<HostStep> steps = spec.phases[p].steps;
+        VPK_REQUIRE(!steps.empty() && steps.size() <= static_cast<size_t>(kMaxSteps), "conv step count out of range");
+        int k = 0;
+        for (HostStep& h : steps) {
+          h.s.wk = k;
+          k += round_up(h.s.kc, 16);
+        }
+        const int K_pad = round_up(k, 64);
+        std::vector<float> wf(static_cast<size_t>(N_pad) * K_pad, 0.f);
+        for (const HostStep& h : steps) {
+          const WeightRef& w = spec.wrefs[h.wref];
+          for (int ch = 0; ch < C; ++ch)
+            for (int g = 0; g < G; ++g) {
+              if (w.gate_block[g] < 0) continue;
+              const int oc = w.gate_block[g] * C + ch;
+              float* row = wf.data() + static_cast<size_t>(ch * G + g) * K_pad + h.s.wk;
+              for (int j = 0; j < h.s.kc; ++j) row[j] = weight_at(w, oc, h.wc0 + h.s.c0 + j, h.ky, h.kx);
+            }
+        }
+        PackedWeights& q = pw[p];
+        q.K_pad = K_pad;
+        q.N_pad = N_pad;
+        q.Cn = Cn;
+        q.bias = d_bias;
+        if (dtype == DT_F32) {
+          q.w = store.upload(wf.data(), wf.size() * sizeof(float), stream);
+        } else {
+          std::vector<__nv_bfloat16> wb(wf.size());
+          for (size_t i = 0; i < wf.size(); ++i) wb[i] = __float2bfloat16_rn(wf[i]);
+          q.w = store.upload(wb.data(), wb.size() * sizeof(__nv_bfloat16), stream);
+        }
+        std::vector<ConvStep> cs(steps.size());
+        for (size_t i = 0; i < steps.size(); ++i) cs[i] = steps[i].s;
+        q.steps = static_cast<ConvStep*>(store.upload(cs.data(), cs.size() * sizeof(ConvStep), stream));
+      }
+      it = cache.emplace(spec.name, std::move(pw)).first;
+    }
+    packed = &it->second;
+    VPK_REQUIRE(packed->size() == spec.phases.size(), "packed-weight cache mismatch for " + spec.name);
+  }
+
+  for (size_t p = 0; p < spec.phases.size(); ++p) {
+    const PhaseSpec& ph = spec.phases[p];
+    BuiltConv bc;
+    bc.name = spec.name + (spec.phases.size() > 1 ? "#" + std::to_string(p) : "");
+    ConvLaunch& L = bc.L;
+    std::memset(&L, 0, sizeof L);
+    L.B = spec.B;
+    L.H = ph.H;
+    L.W = ph.W;
+    L.nsrc = static_cast<int>(spec.srcs.size());
+    for (int i = 0; i < L.nsrc; ++i) L.src[i] = spec.srcs[i];
+    L.nsteps = static_cast<int>(ph.steps.size());
+    L.G = G;
+    L.Cn = Cn;
+    L.N_pad = N_pad;
+    L.epi = ph.epi;
+    L.epi.C = C;
+    L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
+    double kreal = 0;
+    for (const HostStep& h : ph.steps) kreal += h.s.kc;
+    L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;
+    if (!measure_only) {
+      const PackedWeights& q = (*packed)[p];
+      L.steps = q.steps;
+      L.wpacked = q.w;
+      L.K_pad = q.K_pad;
+      L.epi.bias = q.bias;
+      bc.use_tc = (backend == 0) && tc_eligible(L, dtype);
+      if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);
+    }
+    out.push_back(std::move(bc));
+  }
+  return out;
+}
+
+}  // namespace vpk

@@ -1,0 +1,117 @@
+// Host-side lowering of conv / transposed-conv / gated-cell contractions to the generalised convolution launch,
+// weight packing (reference OIHW fp32 -> [N_pad][K_pad] activation-type, gate-interleaved rows) and the device arena.
+#pragma once
+#include <functional>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "common.h"
+#include "conv_tc.h"
+
+namespace vpk {
+
+// A reference-layout weight tensor on the host.  conv: [O][I][KH][KW]; transposed conv: [I][O][KH][KW].
+struct WeightRef {
+  const float* w = nullptr;
+  int O = 0, I = 0, KH = 0, KW = 0;
+  bool transposed = false;
+  // row block (of C rows) of this tensor that feeds packed gate g, or -1 if this tensor does not feed gate g
+  int gate_block[4] = {0, -1, -1, -1};
+};
+
+struct BiasRef {
+  const float* b = nullptr;
+  int gate_block[4] = {0, -1, -1, -1};
+};
+
+struct HostStep {
+  ConvStep s;
+  int wref;      // index into ConvSpec::wrefs
+  int ky, kx;    // tap of that weight tensor
+  int wc0;       // input-channel index of that weight tensor that corresponds to channel 0 of the source
+};
+
+struct PhaseSpec {
+  int H = 0, W = 0;                 // output grid of this phase
+  std::vector<HostStep> steps;
+  EpiParams epi{};                  // per-phase (output offsets differ between transposed-conv parities)
+};
+
+struct ConvSpec {
+  std::string name;
+  int B = 0;
+  int G = 1;                        // gates per channel
+  int C = 0;                        // output channels per gate
+  std::vector<SrcView> srcs;
+  std::vector<WeightRef> wrefs;
+  std::vector<BiasRef> biases;
+  std::vector<PhaseSpec> phases;
+  bool is_gate_gemm = false;
+};
+
+struct ConvInput {                  // one logical input tensor of a conv (full-resolution NHWC view)
+  SrcView view;
+  int wref;                         // weight tensor it multiplies
+  int wc0;                          // its channel offset inside that weight's input-channel dimension
+};
+
+// Appends the K-steps of a k x k conv with the given stride (1 or 2) and padding over `inputs` to spec.phases[0]
+// (creating it) and registers the (parity) source views.  Returns the output size through oh / ow.
+void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<ConvInput>& inputs, int in_h, int in_w,
+                int esize, int* oh, int* ow);
+
+// Transposed conv (stride 1 or 2): one phase per output parity.  `epi_for_phase(ry, rx, stride, OH, OW)` supplies the
+// epilogue (strided output) of each phase.
+void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pad, const ConvInput& input, int in_h,
+                          int in_w, int* oh, int* ow,
+                          const std::function<EpiParams(int ry, int rx, int stride, int OH, int OW)>& epi_for_phase);
+
+// Simple bump allocator over a caller-provided (or library-owned) device range; base == nullptr only measures.
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0, cap = 0;
+  void* alloc(size_t bytes, size_t align = 1024) {
+    off = (off + align - 1) / align * align;
+    void* p = base ? base + off : nullptr;
+    off += bytes;
+    if (base && off > cap) VPK_THROW(4, "workspace too small");
+    return p;
+  }
+  bool measuring() const { return base == nullptr; }
+};
+
+// Library-owned device buffers (packed weights, step tables, biases).
+struct DeviceStore {
+  std::vector<void*> ptrs;
+  void* upload(const void* host, size_t bytes, cudaStream_t stream);
+  void* zeros(size_t bytes, cudaStream_t stream);
+  void release();
+  ~DeviceStore() { release(); }
+  // host staging kept alive until the upload stream has been synchronised
+  std::vector<std::vector<char>> staging;
+};
+
+// A built phase: device-resident step table / packed weights / bias + the launch description.
+struct BuiltConv {
+  std::string name;
+  ConvLaunch L;
+  bool use_tc = false;
+  TcPlan tc;
+};
+
+// Packed-weight cache key -> device pointers, so the per-timestep launches of one layer share one packed copy.
+struct PackedWeights {
+  void* w = nullptr;
+  float* bias = nullptr;
+  ConvStep* steps = nullptr;
+  int K_pad = 0, N_pad = 0, Cn = 0;
+};
+
+// Packs the weights of every phase of `spec` for activation type `dtype` and returns one BuiltConv per phase (device
+// pointers of the sources / outputs inside spec must already be final unless `measure_only`).
+std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, DeviceStore& store,
+                                  std::map<std::string, std::vector<PackedWeights>>& cache, cudaStream_t stream,
+                                  int num_sms, bool measure_only);
+
+}  // namespace vpk

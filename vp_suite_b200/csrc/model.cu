@@ -1,0 +1,342 @@
+#include "model.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace vpk {
+
+Model::Model(const vpk_model_desc& d) : desc(d) {
+  dtype = (d.precision == VPK_PREC_BF16) ? DT_BF16 : DT_F32;
+  backend = d.backend;
+  int dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0) num_sms = sms;
+  } else {
+    cudaGetLastError();
+  }
+}
+
+struct Model::HostPipe {
+  void* d_x[2] = {nullptr, nullptr};
+  void* d_out[2] = {nullptr, nullptr};
+  void* ws = nullptr;
+  float* d_aux = nullptr;
+  size_t x_bytes = 0, out_bytes = 0, ws_bytes = 0;
+  cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
+  cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+  bool init = false;
+  ~HostPipe() {
+    for (int i = 0; i < 2; ++i) {
+      if (d_x[i]) cudaFree(d_x[i]);
+      if (d_out[i]) cudaFree(d_out[i]);
+    }
+    if (ws) cudaFree(ws);
+    if (d_aux) cudaFree(d_aux);
+    if (init) {
+      for (int i = 0; i < 2; ++i) {
+        cudaEventDestroy(ev_in[i]);
+        cudaEventDestroy(ev_comp[i]);
+        cudaEventDestroy(ev_out[i]);
+      }
+      cudaStreamDestroy(s_in);
+      cudaStreamDestroy(s_comp);
+      cudaStreamDestroy(s_out);
+    }
+  }
+};
+
+Model::~Model() {
+  programs.clear();
+  for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
+}
+
+void Model::declare(const std::string& key, std::vector<int64_t> shape) {
+  HostParam p;
+  size_t n = 1;
+  for (int64_t s : shape) n *= static_cast<size_t>(s);
+  p.shape = std::move(shape);
+  p.data.assign(n, 0.f);
+  params.emplace(key, std::move(p));
+  keys.push_back(key);
+}
+
+bool Model::has(const std::string& key) const {
+  auto it = params.find(key);
+  return it != params.end() && it->second.provided;
+}
+
+const float* Model::hp(const std::string& key) const {
+  auto it = params.find(key);
+  VPK_REQUIRE(it != params.end(), "unknown parameter " + key);
+  return it->second.data.data();
+}
+
+void Model::set_param(const std::string& key, const float* data, const int64_t* shape, int ndim) {
+  auto it = params.find(key);
+  if (it == params.end()) VPK_THROW(1, "unexpected state_dict key '" + key + "'");
+  HostParam& p = it->second;
+  bool ok = static_cast<size_t>(ndim) == p.shape.size();
+  for (int i = 0; ok && i < ndim; ++i) ok = (shape[i] == p.shape[i]);
+  if (!ok) VPK_THROW(1, "shape mismatch for state_dict key '" + key + "'");
+  VPK_REQUIRE(data != nullptr, "null data for " + key);
+  std::memcpy(p.data.data(), data, p.data.size() * sizeof(float));
+  p.provided = true;
+  if (finalized) {   // weights changed after packing: drop every derived device object
+    programs.clear();
+    packed_cache.clear();
+    f32_cache.clear();
+    store.release();
+  }
+}
+
+void Model::finalize(cudaStream_t) {
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    VPK_THROW(2, "no CUDA device: libvpk has no CPU fallback");
+  }
+  finalized = true;
+}
+
+float* Model::dev_f32(const std::string& name, const std::vector<float>& host, cudaStream_t stream) {
+  auto it = f32_cache.find(name);
+  if (it != f32_cache.end()) return it->second;
+  float* d = static_cast<float*>(store.upload(host.data(), host.size() * sizeof(float), stream));
+  f32_cache[name] = d;
+  return d;
+}
+
+void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream) {
+  std::vector<BuiltConv> built = build_conv(spec, dtype, backend, store, packed_cache, stream, num_sms, measure);
+  if (measure) return;
+  for (BuiltConv& bc : built) {
+    Op op;
+    op.name = bc.name;
+    op.flops = bc.L.flops;
+    op.gate = bc.L.is_gate_gemm != 0;
+    const int dt = dtype;
+    if (bc.use_tc) {
+      auto plan = std::make_shared<TcPlan>(bc.tc);
+      op.fn = [plan](cudaStream_t s, const RunCtx&) { launch_conv_tc(*plan, s); };
+    } else {
+      ConvLaunch L = bc.L;
+      op.fn = [L, dt](cudaStream_t s, const RunCtx&) { launch_conv_simt(L, dt, s); };
+    }
+    prog.body.push_back(std::move(op));
+  }
+}
+
+void Model::add_memset(Program& prog, void* p, size_t bytes, const char* name) {
+  Op op;
+  op.name = name;
+  op.is_kernel = false;
+  op.fn = [p, bytes](cudaStream_t s, const RunCtx&) { VPK_CUDA(cudaMemsetAsync(p, 0, bytes, s)); };
+  prog.body.push_back(std::move(op));
+}
+
+int Model::microbatch(int batch) const {
+  int mb = desc.max_microbatch > 0 ? desc.max_microbatch : default_microbatch();
+  return std::max(1, std::min(mb, batch));
+}
+
+size_t Model::workspace_bytes(int batch, int t_in, int pred) {
+  validate(t_in, pred);
+  VPK_REQUIRE(batch > 0, "batch must be positive");
+  Program tmp;
+  Arena arena;
+  build(tmp, arena, microbatch(batch), t_in, pred, /*measure=*/true, nullptr);
+  return arena.off + 4096;
+}
+
+Program* Model::get_program(int B, int t_in, int pred, void* ws, size_t ws_bytes, cudaStream_t stream) {
+  for (auto& p : programs)
+    if (p->B == B && p->t_in == t_in && p->pred == pred && p->ws_base == ws && p->ws_bytes <= ws_bytes) return p.get();
+  if (programs.size() >= 8) programs.erase(programs.begin());
+  auto prog = std::make_unique<Program>();
+  prog->B = B;
+  prog->t_in = t_in;
+  prog->pred = pred;
+  prog->ws_base = ws;
+  Arena arena;
+  arena.base = static_cast<char*>(ws);
+  arena.cap = ws_bytes;
+  build(*prog, arena, B, t_in, pred, /*measure=*/false, stream);
+  prog->ws_bytes = arena.off;
+  // weights uploaded during build() live in pageable staging: make sure they have landed before staging is reused
+  VPK_CUDA(cudaStreamSynchronize(stream));
+  store.staging.clear();
+  if (desc.use_cuda_graph && !timing) {
+    cudaStream_t cs;
+    VPK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    RunCtx ctx{};
+    cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+    if (e == cudaSuccess) {
+      try {
+        for (Op& op : prog->body) op.fn(cs, ctx);
+      } catch (...) {
+        cudaStreamEndCapture(cs, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        throw;
+      }
+      VPK_CUDA(cudaStreamEndCapture(cs, &graph));
+      VPK_CUDA(cudaGraphInstantiate(&prog->graph, graph, 0));
+      cudaGraphDestroy(graph);
+    }
+    cudaStreamDestroy(cs);
+    VPK_CUDA(e);
+  }
+  programs.push_back(std::move(prog));
+  return programs.back().get();
+}
+
+void Model::run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx) {
+  for (Op& op : ops) {
+    const bool t = timing && op.gate;
+    if (t) {
+      while (ev_pool.size() < ev_used + 2) {
+        cudaEvent_t e;
+        VPK_CUDA(cudaEventCreate(&e));
+        ev_pool.push_back(e);
+      }
+      VPK_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
+    }
+    op.fn(stream, ctx);
+    if (t) {
+      VPK_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
+      ev_used += 2;
+      timed_flops += op.flops;
+      timed_launches += 1;
+    }
+    if (op.is_kernel) ++last_launches;
+  }
+}
+
+void Model::gemm_stats(float* ms, int64_t* launches, double* flops) {
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < ev_used; i += 2) {
+    VPK_CUDA(cudaEventSynchronize(ev_pool[i + 1]));
+    float t = 0.f;
+    VPK_CUDA(cudaEventElapsedTime(&t, ev_pool[i], ev_pool[i + 1]));
+    total += t;
+  }
+  *ms = total;
+  *launches = timed_launches;
+  *flops = timed_flops;
+}
+
+void Model::forward(const float* x, int batch, int t_in, int pred, float* out, float* aux, void* ws, size_t ws_bytes,
+                    cudaStream_t stream) {
+  VPK_REQUIRE(finalized, "forward before finalize");
+  VPK_REQUIRE(x != nullptr && out != nullptr && ws != nullptr, "null buffer");
+  VPK_REQUIRE(batch > 0 && pred > 0 && t_in > 0, "bad batch / frame counts");
+  validate(t_in, pred);
+  last_launches = 0;
+  ev_used = 0;
+  timed_flops = 0;
+  timed_launches = 0;
+  const int mb = microbatch(batch);
+  const size_t in_stride = static_cast<size_t>(in_frames(t_in, pred)) * desc.img_c * desc.img_h * desc.img_w;
+  const size_t out_stride = static_cast<size_t>(pred) * desc.img_c * desc.img_h * desc.img_w;
+  begin_call(batch, aux, stream);
+  for (int mb0 = 0; mb0 < batch; mb0 += mb) {
+    const int nb = std::min(mb, batch - mb0);
+    Program* prog = get_program(nb, t_in, pred, ws, ws_bytes, stream);
+    RunCtx ctx{x + mb0 * in_stride, out + mb0 * out_stride, aux, mb0, nb, batch};
+    run_ops(prog->pre, stream, ctx);
+    if (prog->graph != nullptr && !timing) {
+      VPK_CUDA(cudaGraphLaunch(prog->graph, stream));
+      for (const Op& op : prog->body)
+        if (op.is_kernel) ++last_launches;
+    } else {
+      run_ops(prog->body, stream, ctx);
+    }
+    run_ops(prog->post, stream, ctx);
+  }
+  end_call(batch, aux, stream);
+}
+
+void Model::forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux) {
+  VPK_REQUIRE(finalized, "forward before finalize");
+  VPK_REQUIRE(x != nullptr && out != nullptr, "null buffer");
+  validate(t_in, pred);
+  const int mb = microbatch(batch);
+  const size_t in_stride = static_cast<size_t>(in_frames(t_in, pred)) * desc.img_c * desc.img_h * desc.img_w;
+  const size_t out_stride = static_cast<size_t>(pred) * desc.img_c * desc.img_h * desc.img_w;
+  if (!pipe) pipe = std::make_unique<HostPipe>();
+  HostPipe& hpipe = *pipe;
+  if (!hpipe.init) {
+    VPK_CUDA(cudaStreamCreateWithFlags(&hpipe.s_in, cudaStreamNonBlocking));
+    VPK_CUDA(cudaStreamCreateWithFlags(&hpipe.s_comp, cudaStreamNonBlocking));
+    VPK_CUDA(cudaStreamCreateWithFlags(&hpipe.s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      VPK_CUDA(cudaEventCreateWithFlags(&hpipe.ev_in[i], cudaEventDisableTiming));
+      VPK_CUDA(cudaEventCreateWithFlags(&hpipe.ev_comp[i], cudaEventDisableTiming));
+      VPK_CUDA(cudaEventCreateWithFlags(&hpipe.ev_out[i], cudaEventDisableTiming));
+    }
+    VPK_CUDA(cudaMalloc(&hpipe.d_aux, 256));
+    hpipe.init = true;
+  }
+  const size_t xb = mb * in_stride * sizeof(float), ob = mb * out_stride * sizeof(float);
+  const size_t wb = workspace_bytes(batch, t_in, pred);
+  if (xb > hpipe.x_bytes || ob > hpipe.out_bytes || wb > hpipe.ws_bytes) {
+    VPK_CUDA(cudaDeviceSynchronize());
+    programs.clear();
+    for (int i = 0; i < 2; ++i) {
+      if (hpipe.d_x[i]) cudaFree(hpipe.d_x[i]);
+      if (hpipe.d_out[i]) cudaFree(hpipe.d_out[i]);
+      VPK_CUDA(cudaMalloc(&hpipe.d_x[i], xb));
+      VPK_CUDA(cudaMalloc(&hpipe.d_out[i], ob));
+    }
+    if (hpipe.ws) cudaFree(hpipe.ws);
+    VPK_CUDA(cudaMalloc(&hpipe.ws, wb));
+    hpipe.x_bytes = xb;
+    hpipe.out_bytes = ob;
+    hpipe.ws_bytes = wb;
+  }
+  last_launches = 0;
+  ev_used = 0;
+  timed_flops = 0;
+  timed_launches = 0;
+  begin_call(batch, hpipe.d_aux, hpipe.s_comp);
+  int it = 0;
+  for (int mb0 = 0; mb0 < batch; mb0 += mb, ++it) {
+    const int nb = std::min(mb, batch - mb0);
+    const int buf = it & 1;
+    // H2D of this microbatch; d_x[buf] was last read by the compute of iteration it-2
+    if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_in, hpipe.ev_comp[buf], 0));
+    VPK_CUDA(cudaMemcpyAsync(hpipe.d_x[buf], x + mb0 * in_stride, nb * in_stride * sizeof(float),
+                             cudaMemcpyHostToDevice, hpipe.s_in));
+    VPK_CUDA(cudaEventRecord(hpipe.ev_in[buf], hpipe.s_in));
+    // compute; d_out[buf] was last read by the D2H of iteration it-2
+    VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_in[buf], 0));
+    if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_out[buf], 0));
+    Program* prog = get_program(nb, t_in, pred, hpipe.ws, hpipe.ws_bytes, hpipe.s_comp);
+    RunCtx ctx{static_cast<const float*>(hpipe.d_x[buf]), static_cast<float*>(hpipe.d_out[buf]), hpipe.d_aux, mb0, nb,
+               batch};
+    run_ops(prog->pre, hpipe.s_comp, ctx);
+    if (prog->graph != nullptr && !timing) {
+      VPK_CUDA(cudaGraphLaunch(prog->graph, hpipe.s_comp));
+      for (const Op& op : prog->body)
+        if (op.is_kernel) ++last_launches;
+    } else {
+      run_ops(prog->body, hpipe.s_comp, ctx);
+    }
+    run_ops(prog->post, hpipe.s_comp, ctx);
+    VPK_CUDA(cudaEventRecord(hpipe.ev_comp[buf], hpipe.s_comp));
+    // D2H
+    VPK_CUDA(cudaStreamWaitEvent(hpipe.s_out, hpipe.ev_comp[buf], 0));
+    VPK_CUDA(cudaMemcpyAsync(out + mb0 * out_stride, hpipe.d_out[buf], nb * out_stride * sizeof(float),
+                             cudaMemcpyDeviceToHost, hpipe.s_out));
+    VPK_CUDA(cudaEventRecord(hpipe.ev_out[buf], hpipe.s_out));
+  }
+  end_call(batch, hpipe.d_aux, hpipe.s_comp);
+  if (aux != nullptr)
+    VPK_CUDA(cudaMemcpyAsync(aux, hpipe.d_aux, sizeof(float), cudaMemcpyDeviceToHost, hpipe.s_comp));
+  VPK_CUDA(cudaStreamSynchronize(hpipe.s_comp));
+  VPK_CUDA(cudaStreamSynchronize(hpipe.s_out));
+}
+
+}  // namespace vpk

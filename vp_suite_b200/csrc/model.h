@@ -1,0 +1,118 @@
+// Model runtime of libvpk: parameters, launch programs (one per microbatch shape), workspace planning, CUDA-graph
+// replay, microbatch loop and the host-buffer pipeline.  Concrete rollouts (EF-ConvLSTM, PredRNN-V2, PhyDNet) only
+// implement build().
+#pragma once
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/vpk.h"
+#include "common.h"
+#include "lowering.h"
+
+namespace vpk {
+
+struct HostParam {
+  std::vector<int64_t> shape;
+  std::vector<float> data;
+  bool provided = false;
+};
+
+struct RunCtx {          // pointers of the current microbatch (already offset)
+  const float* x;
+  float* out;
+  float* aux;
+  int mb0;               // first sequence of the microbatch
+  int nb;                // sequences in it
+  int batch;             // sequences of the whole call
+};
+
+struct Op {
+  std::string name;
+  std::function<void(cudaStream_t, const RunCtx&)> fn;
+  double flops = 0;
+  bool gate = false;     // counted in the gate-GEMM roofline figure
+  bool is_kernel = true; // false for memsets / copies
+};
+
+struct Program {
+  int B = 0, t_in = 0, pred = 0;
+  void* ws_base = nullptr;
+  size_t ws_bytes = 0;
+  std::vector<Op> pre, body, post;
+  cudaGraphExec_t graph = nullptr;
+  ~Program() {
+    if (graph) cudaGraphExecDestroy(graph);
+  }
+};
+
+class Model {
+ public:
+  explicit Model(const vpk_model_desc& d);
+  virtual ~Model();
+
+  void set_param(const std::string& key, const float* data, const int64_t* shape, int ndim);
+  void finalize(cudaStream_t stream);
+  size_t workspace_bytes(int batch, int t_in, int pred);
+  void forward(const float* x, int batch, int t_in, int pred, float* out, float* aux, void* ws, size_t ws_bytes,
+               cudaStream_t stream);
+  void forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux);
+
+  vpk_model_desc desc;
+  std::vector<std::string> keys;
+  std::map<std::string, HostParam> params;
+  int64_t last_launches = 0;
+  bool timing = false;
+  void gemm_stats(float* ms, int64_t* launches, double* flops);
+
+ protected:
+  // ---- implemented by the concrete rollouts ----
+  virtual void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) = 0;
+  virtual void validate(int t_in, int pred) const {}
+  virtual int default_microbatch() const { return 64; }
+  virtual int in_frames(int t_in, int pred) const { return t_in; }
+  virtual void begin_call(int batch, float* aux, cudaStream_t stream) {}
+  virtual void end_call(int batch, float* aux, cudaStream_t stream) {}
+
+  // ---- helpers for build() ----
+  void declare(const std::string& key, std::vector<int64_t> shape);
+  const float* hp(const std::string& key) const;           // host data of a parameter
+  bool has(const std::string& key) const;
+  float* dev_f32(const std::string& name, const std::vector<float>& host, cudaStream_t stream);  // cached upload
+  void add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream);
+  void add_memset(Program& prog, void* p, size_t bytes, const char* name);
+  int esize() const { return static_cast<int>(dtype_size(dtype)); }
+  SrcView dense_view(void* p, int H, int W, int C) const {
+    return SrcView{p, H, W, C, static_cast<long long>(H) * W * C, static_cast<long long>(W) * C, C};
+  }
+
+  int dtype = DT_F32;
+  int backend = 0;
+  int num_sms = 148;
+  bool finalized = false;
+  DeviceStore store;
+  std::map<std::string, std::vector<PackedWeights>> packed_cache;
+  std::map<std::string, float*> f32_cache;
+
+ private:
+  Program* get_program(int B, int t_in, int pred, void* ws, size_t ws_bytes, cudaStream_t stream);
+  void run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx);
+  int microbatch(int batch) const;
+  std::vector<std::unique_ptr<Program>> programs;
+  // gate-GEMM timing
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  double timed_flops = 0;
+  int64_t timed_launches = 0;
+  // host pipeline resources
+  struct HostPipe;
+  std::unique_ptr<HostPipe> pipe;
+};
+
+Model* make_ef_convlstm(const vpk_model_desc& d);
+Model* make_predrnn(const vpk_model_desc& d);
+Model* make_phydnet(const vpk_model_desc& d, bool branch_only);
+
+}  // namespace vpk

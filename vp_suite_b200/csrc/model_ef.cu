@@ -1,0 +1,230 @@
+// convlstm-shi: Encoder-Forecaster ConvLSTM rollout (reference: models/precipitation_nowcasting/ef_blocks.py:52-187,
+// ef_conv_lstm.py:7-108, model_blocks/conv_lstm_hzzone.py:38-70).
+//
+// Schedule: TIME-MAJOR.  The reference runs each layer over all timesteps before the next layer (layer-major,
+// ef_blocks.py:67-82,100-114) and materialises [b,t,C,H,W] between layers; since layer l at step t only needs layer
+// l-1 at step t and its own state from step t-1, running all layers for step t and then t+1 is the same computation
+//  and keeps exactly one h/c state per layer resident.  The forecaster's top RNN is fed
+// `inputs=None` by the reference (zeros, conv_lstm_hzzone.py:54-56): its x-side K-steps are dropped.
+#include "builders.h"
+#include "elementwise.h"
+#include "model.h"
+
+namespace vpk {
+
+namespace {
+
+class EfConvLstm : public Model {
+ public:
+  explicit EfConvLstm(const vpk_model_desc& d) : Model(d) {
+    VPK_REQUIRE(d.img_c > 0 && d.img_h > 0 && d.img_w > 0, "bad img_shape");
+    // state sizes (ef_blocks.py:145-158; utils/models.py:131-161 and :164-193)
+    int hh = d.img_h, ww = d.img_w;
+    for (int n = 0; n < 3; ++n) {
+      VPK_REQUIRE(d.enc_conv_s[n] == 1 || d.enc_conv_s[n] == 2, "enc_conv_s must be 1 or 2");
+      hh = (hh + 2 * d.enc_conv_p[n] - d.enc_conv_k[n]) / d.enc_conv_s[n] + 1;
+      ww = (ww + 2 * d.enc_conv_p[n] - d.enc_conv_k[n]) / d.enc_conv_s[n] + 1;
+      eh[n] = hh;
+      ew[n] = ww;
+    }
+    dh[0] = hh;
+    dw[0] = ww;
+    for (int n = 0; n < 3; ++n) {
+      // the reference's own (non-standard) formula, utils/models.py:190-191
+      hh = (hh - 1) * d.dec_conv_s[n] - 2 * d.dec_conv_p[n] + (d.dec_conv_k[n] - 1) + d.dec_conv_p[n];
+      ww = (ww - 1) * d.dec_conv_s[n] - 2 * d.dec_conv_p[n] + (d.dec_conv_k[n] - 1) + d.dec_conv_p[n];
+      // what ConvTranspose2d really produces (no output_padding in _make_layers, ef_blocks.py:29-31)
+      const int th = (dh[n] - 1) * d.dec_conv_s[n] - 2 * d.dec_conv_p[n] + d.dec_conv_k[n];
+      const int tw = (dw[n] - 1) * d.dec_conv_s[n] - 2 * d.dec_conv_p[n] + d.dec_conv_k[n];
+      VPK_REQUIRE(th == hh && tw == ww, "decoder conv hyper-parameters give inconsistent sizes");
+      dh[n + 1] = hh;
+      dw[n + 1] = ww;
+    }
+    // AttributeError in the reference (ef_blocks.py:160-167)
+    VPK_REQUIRE(dh[3] == d.img_h && dw[3] == d.img_w, "model layer hyper-parameters yield wrong output size");
+    for (int n = 0; n < 3; ++n) {
+      // forecaster rnn n starts from encoder state 2-n (ef_blocks.py:109-113): sizes must agree
+      VPK_REQUIRE(dh[n] == eh[2 - n] && dw[n] == ew[2 - n], "encoder / forecaster state sizes differ");
+      VPK_REQUIRE(d.dec_c[2 * n] == d.enc_c[2 * (2 - n) + 1], "encoder / forecaster state channels differ");
+      VPK_REQUIRE(d.enc_rnn_k[n] % 2 == 1 && d.dec_rnn_k[n] % 2 == 1, "rnn kernel size must be odd");
+    }
+    int in_c = d.img_c;
+    for (int n = 0; n < 3; ++n) {
+      const std::string st = "encoder.stage" + std::to_string(n + 1) + ".conv.";
+      const std::string rn = "encoder.rnn" + std::to_string(n + 1) + ".";
+      const int mid = d.enc_c[2 * n], outc = d.enc_c[2 * n + 1];
+      declare(st + "weight", {mid, in_c, d.enc_conv_k[n], d.enc_conv_k[n]});
+      declare(st + "bias", {mid});
+      for (const char* pk : {"Wci", "Wcf", "Wco"}) declare(rn + pk, {1, outc, eh[n], ew[n]});
+      declare(rn + "_conv.weight", {4 * outc, mid + outc, d.enc_rnn_k[n], d.enc_rnn_k[n]});
+      declare(rn + "_conv.bias", {4 * outc});
+      in_c = outc;
+    }
+    for (int n = 0; n < 3; ++n) {
+      const int idx = 3 - n;
+      const std::string rn = "forecaster.rnn" + std::to_string(idx) + ".";
+      const std::string st = "forecaster.stage" + std::to_string(idx) + ".deconv.";
+      const int mid = d.dec_c[2 * n], outc = d.dec_c[2 * n + 1];
+      for (const char* pk : {"Wci", "Wcf", "Wco"}) declare(rn + pk, {1, mid, dh[n], dw[n]});
+      declare(rn + "_conv.weight", {4 * mid, in_c + mid, d.dec_rnn_k[n], d.dec_rnn_k[n]});
+      declare(rn + "_conv.bias", {4 * mid});
+      declare(st + "weight", {mid, outc, d.dec_conv_k[n], d.dec_conv_k[n]});
+      declare(st + "bias", {outc});
+      dec_in_c[n] = in_c;
+      in_c = outc;
+    }
+    VPK_REQUIRE(d.final_conv_c == d.dec_c[5], "identity final block must keep the channel count");
+    declare("forecaster.stage1.final.weight", {d.img_c, d.final_conv_c, 1, 1});
+    declare("forecaster.stage1.final.bias", {d.img_c});
+  }
+
+ protected:
+  int default_microbatch() const override {
+    // keep one microbatch's activations around 8 GB: rnn1 state is the largest tensor
+    const double per_seq = static_cast<double>(eh[0]) * ew[0] * 2200.0;   // bytes, all layers, rough
+    int mb = static_cast<int>(8e9 / per_seq);
+    return std::max(1, std::min(mb, 256));
+  }
+
+  std::vector<float> peephole_hwc(const std::string& key, int C, int H, int W) const {
+    // reference layout [1, C, H, W] -> [H, W, C]
+    const float* p = hp(key);
+    std::vector<float> out(static_cast<size_t>(C) * H * W);
+    for (int c = 0; c < C; ++c)
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) out[(static_cast<size_t>(y) * W + x) * C + c] = p[(static_cast<size_t>(c) * H + y) * W + x];
+    return out;
+  }
+
+  void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) override {
+    const vpk_model_desc& d = desc;
+    const ActInfo act{dtype, esize()};
+    const int esz = esize();
+    const int c = d.img_c, h = d.img_h, w = d.img_w;
+    const size_t frame_px = static_cast<size_t>(B) * h * w;
+
+    char* frames_in = static_cast<char*>(arena.alloc(frame_px * c * esz * t_in));
+    float* out_stage = static_cast<float*>(arena.alloc(frame_px * c * sizeof(float) * pred));
+
+    void* xin[3];
+    void* hbuf[3][2];
+    float* cbuf[3];
+    for (int n = 0; n < 3; ++n) {
+      const size_t px = static_cast<size_t>(B) * eh[n] * ew[n];
+      xin[n] = arena.alloc(px * d.enc_c[2 * n] * esz);
+      hbuf[n][0] = arena.alloc(px * d.enc_c[2 * n + 1] * esz);
+      hbuf[n][1] = arena.alloc(px * d.enc_c[2 * n + 1] * esz);
+      cbuf[n] = static_cast<float*>(arena.alloc(px * d.enc_c[2 * n + 1] * sizeof(float)));
+    }
+    void* ybuf[3];
+    for (int n = 0; n < 3; ++n)
+      ybuf[n] = arena.alloc(static_cast<size_t>(B) * dh[n + 1] * dw[n + 1] * d.dec_c[2 * n + 1] * esz);
+
+    // peepholes (device fp32 [H,W,C]); all three absent => plain gates
+    const float* peep[2][3][3] = {};
+    if (!measure) {
+      for (int side = 0; side < 2; ++side)
+        for (int n = 0; n < 3; ++n) {
+          const std::string rn = std::string(side == 0 ? "encoder.rnn" : "forecaster.rnn") + std::to_string(n + 1) + ".";
+          const int C = d.enc_c[2 * n + 1];
+          if (!has(rn + "Wci") && !has(rn + "Wcf") && !has(rn + "Wco")) continue;
+          const char* names[3] = {"Wci", "Wcf", "Wco"};
+          for (int k = 0; k < 3; ++k)
+            peep[side][n][k] = dev_f32(rn + names[k], peephole_hwc(rn + names[k], C, eh[n], ew[n]), stream);
+        }
+    }
+
+    if (!measure) {
+      const int ns = num_sms, dt = dtype;
+      Op pre;
+      pre.name = "frames_to_nhwc";
+      pre.fn = [=](cudaStream_t s, const RunCtx& ctx) {
+        launch_frames_to_nhwc(ctx.x, frames_in, dt, B, t_in, c, h, w, ns, s);
+      };
+      prog.pre.push_back(std::move(pre));
+      for (int n = 0; n < 3; ++n) {
+        const size_t px = static_cast<size_t>(B) * eh[n] * ew[n];
+        add_memset(prog, hbuf[n][0], px * d.enc_c[2 * n + 1] * esz, "zero_h");
+        add_memset(prog, cbuf[n], px * d.enc_c[2 * n + 1] * sizeof(float), "zero_c");
+      }
+    }
+
+    int par[3] = {0, 0, 0};
+    // ------------------------------------------ encoder (ef_blocks.py:67-82) ---------------------------------
+    for (int t = 0; t < t_in; ++t) {
+      const void* in = frames_in + static_cast<size_t>(t) * frame_px * c * esz;
+      int in_h = h, in_w = w, in_c = c;
+      for (int n = 0; n < 3; ++n) {
+        const std::string st = "encoder.stage" + std::to_string(n + 1) + ".conv.";
+        const std::string rn = "encoder.rnn" + std::to_string(n + 1) + ".";
+        const int mid = d.enc_c[2 * n], outc = d.enc_c[2 * n + 1];
+        int oh, ow;
+        ConvArgs ca{st, B, in_h, in_w, in_c, mid, d.enc_conv_k[n], d.enc_conv_s[n], d.enc_conv_p[n], in,
+                    hp(st + "weight"), hp(st + "bias"), d.ef_act, xin[n]};
+        add_conv(prog, conv_spec(ca, act, &oh, &ow), measure, stream);
+        VPK_REQUIRE(oh == eh[n] && ow == ew[n], "encoder stage size mismatch");
+        LstmArgs la{rn, B, eh[n], ew[n], mid, outc, d.enc_rnn_k[n], xin[n], hbuf[n][par[n]], hbuf[n][par[n] ^ 1],
+                    cbuf[n], hp(rn + "_conv.weight"), hp(rn + "_conv.bias"), false,
+                    peep[0][n][0], peep[0][n][1], peep[0][n][2]};
+        add_conv(prog, lstm_spec(la, act), measure, stream);
+        par[n] ^= 1;
+        in = hbuf[n][par[n]];
+        in_h = eh[n];
+        in_w = ew[n];
+        in_c = outc;
+      }
+    }
+    // ------------------------------------------ forecaster (ef_blocks.py:100-114) ----------------------------
+    for (int t = 0; t < pred; ++t) {
+      const void* in = nullptr;   // rnn3 gets inputs=None
+      for (int n = 0; n < 3; ++n) {
+        const int idx = 3 - n, e = 2 - n;   // forecaster.rnn{idx} continues encoder state e
+        const std::string rn = "forecaster.rnn" + std::to_string(idx) + ".";
+        const std::string st = "forecaster.stage" + std::to_string(idx) + ".deconv.";
+        const int mid = d.dec_c[2 * n], outc = d.dec_c[2 * n + 1];
+        // the packed weights of rnn3 hold only the h-side columns: name them apart from a (hypothetical) full pack
+        LstmArgs la{rn + (in ? "" : "h_only."), B, dh[n], dw[n], dec_in_c[n], mid, d.dec_rnn_k[n], in,
+                    hbuf[e][par[e]], hbuf[e][par[e] ^ 1], cbuf[e], hp(rn + "_conv.weight"), hp(rn + "_conv.bias"),
+                    false, peep[1][idx - 1][0], peep[1][idx - 1][1], peep[1][idx - 1][2]};
+        add_conv(prog, lstm_spec(la, act), measure, stream);
+        par[e] ^= 1;
+        int oh, ow;
+        DeconvArgs da{st, B, dh[n], dw[n], mid, outc, d.dec_conv_k[n], d.dec_conv_s[n], d.dec_conv_p[n], 0,
+                      hbuf[e][par[e]], hp(st + "weight"), hp(st + "bias"), d.ef_act, ybuf[n]};
+        add_conv(prog, deconv_spec(da, act, &oh, &ow), measure, stream);
+        VPK_REQUIRE(oh == dh[n + 1] && ow == dw[n + 1], "forecaster stage size mismatch");
+        in = ybuf[n];
+      }
+      // identity + final 1x1 conv (ef_conv_lstm.py:99-104), written as fp32 NCHW frame t of the staging tensor
+      int oh, ow;
+      ConvArgs fa{"forecaster.stage1.final.", B, h, w, d.final_conv_c, c, 1, 1, 0, ybuf[2],
+                  hp("forecaster.stage1.final.weight"), hp("forecaster.stage1.final.bias"), ACT_NONE,
+                  out_stage + static_cast<size_t>(t) * c * h * w};
+      fa.f32_strided = true;
+      fa.oB = static_cast<long long>(pred) * c * h * w;
+      fa.oC = static_cast<long long>(h) * w;
+      fa.oY = w;
+      fa.oX = 1;
+      add_conv(prog, conv_spec(fa, act, &oh, &ow), measure, stream);
+    }
+    if (!measure) {
+      const size_t bytes = frame_px * c * sizeof(float) * pred;
+      Op post;
+      post.name = "copy_out";
+      post.is_kernel = false;
+      post.fn = [=](cudaStream_t s, const RunCtx& ctx) {
+        VPK_CUDA(cudaMemcpyAsync(ctx.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s));
+      };
+      prog.post.push_back(std::move(post));
+    }
+  }
+
+ private:
+  int eh[3], ew[3], dh[4], dw[4], dec_in_c[3];
+};
+
+}  // namespace
+
+Model* make_ef_convlstm(const vpk_model_desc& d) { return new EfConvLstm(d); }
+
+}  // namespace vpk

@@ -1,0 +1,210 @@
+"""
+Drop-in VPModel classes whose ``forward`` runs the whole rollout in libvpk (hand-written sm_100a kernels).
+
+Each class keeps the reference's constructor signature, hyper-parameter attributes, ``forward(x, pred_frames)`` /
+``pred_1`` contract and ``state_dict`` layout, so reference checkpoints and random-init weights
+load unchanged:  ``ours.load_state_dict(reference_model.state_dict())``.
+
+    EF_ConvLSTM      <- vp_suite/models/precipitation_nowcasting/ef_conv_lstm.py:7-108  (key "convlstm-shi")
+    PredRNN_V2       <- vp_suite/models/predrnn_v2.py:11-230                           (key "predrnn-pp")
+    PhyDNet          <- vp_suite/models/phydnet.py:12-137                              (key "phy")
+    ConvLSTMBranch   <- BASELINE config 2: PhyDNet's residual branch alone (our composition of reference blocks)
+"""
+from collections import OrderedDict
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .base import VPModel, NativeRollout
+
+
+def _conv_out(hw, k, s, p):
+    """vp_suite/utils/models.py:131-161."""
+    return tuple((v + 2 * p - (k - 1) - 1) // s + 1 for v in hw)
+
+
+def _convt_out(hw, k, s, p):
+    """vp_suite/utils/models.py:164-193 (the reference's own formula)."""
+    return tuple((v - 1) * s - 2 * p + (k - 1) + p for v in hw)
+
+
+class _Params(nn.Module):
+    """Parameter holder: gives sub-modules the attribute names the reference's state_dict keys are built from."""
+
+
+def _stage(layers):
+    return nn.Sequential(OrderedDict(layers))
+
+
+def _act_code(name):
+    if "leaky" in name:
+        return 1
+    if "relu" in name:
+        return 3
+    return 0
+
+
+class EF_ConvLSTM(VPModel, NativeRollout):
+    NAME = "EF-ConvLSTM (Shi et al.)"
+    PAPER_REFERENCE = "https://arxiv.org/abs/1506.04214"
+    CODE_REFERENCE = "https://github.com/Hzzone/Precipitation-Nowcasting"
+    MATCHES_REFERENCE = "Yes"
+
+    # hyper-parameters: ef_conv_lstm.py:31-65
+    num_layers = 3
+    enc_c = [16, 64, 64, 96, 96, 96]
+    dec_c = [96, 96, 96, 96, 64, 16]
+    enc_conv_names = ["conv1_leaky_1", "conv2_leaky_1", "conv3_leaky_1"]
+    enc_conv_k = [3, 3, 3]
+    enc_conv_s = [1, 2, 2]
+    enc_conv_p = [1, 1, 1]
+    dec_conv_names = ["deconv1_leaky_1", "deconv2_leaky_1", "deconv3_leaky_1"]
+    dec_conv_k = [4, 4, 3]
+    dec_conv_s = [2, 2, 1]
+    dec_conv_p = [1, 1, 1]
+    enc_rnn_k = [3, 3, 3]
+    enc_rnn_s = [1, 1, 1]
+    enc_rnn_p = [1, 1, 1]
+    dec_rnn_k = [3, 3, 3]
+    dec_rnn_s = [1, 1, 1]
+    dec_rnn_p = [1, 1, 1]
+    final_conv_1_name = "identity"
+    final_conv_1_c = 16
+    final_conv_1_k = 3
+    final_conv_1_s = 1
+    final_conv_1_p = 1
+    final_conv_2_name = "conv3_3"
+    final_conv_2_k = 1
+    final_conv_2_s = 1
+    final_conv_2_p = 0
+
+    def __init__(self, device, **model_kwargs):
+        super().__init__(device, **model_kwargs)
+        self._native_init()
+        L = self.num_layers
+        if L != 3:                                     # Forecaster.forward hard-codes rnn3/stage3 (ef_blocks.py:109-110)
+            raise AttributeError("the Encoder-Forecaster structure needs num_layers == 3")
+        for name, val in [(k, v) for k, v in vars(self).items() if k.startswith(("enc_", "dec_"))]:
+            want = 2 * L if name in ("enc_c", "dec_c") else L            # ef_blocks.py:134-143
+            if isinstance(val, (list, tuple)) and len(val) != want:
+                raise AttributeError(f"Speficied {L} layers, but len of attribute '{name}' doesn't match that ({val}).")
+        if any(s != 1 for s in self.enc_rnn_s + self.dec_rnn_s) or \
+                any(p != k // 2 for p, k in zip(self.enc_rnn_p + self.dec_rnn_p, self.enc_rnn_k + self.dec_rnn_k)):
+            raise AttributeError("rnn stride must be 1 and padding k//2 (anything else changes the state size)")
+        if self.final_conv_1_name != "identity" or self.final_conv_2_k != 1 or self.final_conv_2_s != 1 \
+                or self.final_conv_2_p != 0:
+            raise AttributeError("only the reference's final block (identity + 1x1 conv) is supported")
+        acts = {_act_code(n) for n in self.enc_conv_names + self.dec_conv_names}
+        if len(acts) != 1:
+            raise AttributeError("all stage convs must share one activation")
+        self._ef_act = acts.pop()
+
+        # state sizes (ef_blocks.py:145-167)
+        hw = (self.img_h, self.img_w)
+        enc_hw = []
+        for n in range(L):
+            hw = _conv_out(hw, self.enc_conv_k[n], self.enc_conv_s[n], self.enc_conv_p[n])
+            enc_hw.append(hw)
+        dec_hw = [hw]
+        for n in range(L - 1):
+            hw = _convt_out(hw, self.dec_conv_k[n], self.dec_conv_s[n], self.dec_conv_p[n])
+            dec_hw.append(hw)
+        final = _convt_out(hw, self.dec_conv_k[-1], self.dec_conv_s[-1], self.dec_conv_p[-1])
+        if final != (self.img_h, self.img_w):
+            raise AttributeError(f"Model layer hyperparameters yield wrong output size: {final} "
+                                 f"(expected: {(self.img_h, self.img_w)}). All hidden sizes: {enc_hw + dec_hw}")
+        self.enc_rnn_state_h = [v[0] for v in enc_hw]
+        self.enc_rnn_state_w = [v[1] for v in enc_hw]
+        self.dec_rnn_state_h = [v[0] for v in dec_hw]
+        self.dec_rnn_state_w = [v[1] for v in dec_hw]
+
+        def rnn(in_c, c, hw_, k):
+            m = _Params()
+            m._conv = nn.Conv2d(in_c + c, 4 * c, k, 1, k // 2)
+            for nm in ("Wci", "Wcf", "Wco"):                             # registered on every device (sec. 0.4)
+                setattr(m, nm, nn.Parameter(torch.zeros(1, c, *hw_)))
+            return m
+
+        # same construction order as the reference (ef_conv_lstm.py:70-108), so a given torch seed yields the same init
+        self.encoder = _Params()
+        self.forecaster = _Params()
+        in_c = self.img_c
+        enc = []
+        for n in range(L):
+            mid, out_c = self.enc_c[2 * n], self.enc_c[2 * n + 1]
+            name = self.enc_conv_names[n]
+            enc.append((_stage([(name, nn.Conv2d(in_c, mid, self.enc_conv_k[n], self.enc_conv_s[n],
+                                                 self.enc_conv_p[n]))]), rnn(mid, out_c, enc_hw[n], self.enc_rnn_k[n])))
+            in_c = out_c
+        dec = []
+        for n in range(L):
+            mid, out_c = self.dec_c[2 * n], self.dec_c[2 * n + 1]
+            r = rnn(in_c, mid, dec_hw[n], self.dec_rnn_k[n])
+            layers = [(self.dec_conv_names[n], nn.ConvTranspose2d(mid, out_c, self.dec_conv_k[n], self.dec_conv_s[n],
+                                                                  self.dec_conv_p[n]))]
+            if n == L - 1:
+                layers.append((self.final_conv_1_name, nn.Identity()))
+                layers.append((self.final_conv_2_name, nn.Conv2d(self.final_conv_1_c, self.img_c, 1, 1, 0)))
+            dec.append((_stage(layers), r))
+            in_c = out_c
+        for n, (st, r) in enumerate(enc, 1):                             # Encoder.__init__   ef_blocks.py:63-65
+            setattr(self.encoder, f"stage{n}", st)
+            setattr(self.encoder, f"rnn{n}", r)
+        for n, (st, r) in enumerate(dec):                                # Forecaster.__init__ ef_blocks.py:96-98
+            setattr(self.forecaster, f"rnn{L - n}", r)
+            setattr(self.forecaster, f"stage{L - n}", st)
+        self.NON_CONFIG_VARS = list(self.NON_CONFIG_VARS) + ["encoder", "forecaster"]
+        self.to(device)
+
+    # -- native glue ------------------------------------------------------------------------------------------------
+    def _native_desc(self):
+        d = N.ModelDesc()
+        d.kind = N.VPK_MODEL_CONVLSTM_SHI
+        d.img_c, d.img_h, d.img_w = self.img_c, self.img_h, self.img_w
+        for f in ("enc_c", "dec_c", "enc_conv_k", "enc_conv_s", "enc_conv_p", "dec_conv_k", "dec_conv_s",
+                  "dec_conv_p", "enc_rnn_k", "dec_rnn_k"):
+            arr = getattr(d, f)
+            for i, v in enumerate(getattr(self, f)):
+                arr[i] = int(v)
+        d.final_conv_c = int(self.final_conv_1_c)
+        d.ef_act = self._ef_act
+        return d
+
+    def _native_key(self, key):
+        parts = key.split(".")
+        if parts[1].startswith("stage"):
+            if parts[2] == self.final_conv_2_name:
+                parts[2] = "final"
+            elif parts[0] == "encoder":
+                parts[2] = "conv"
+            else:
+                parts[2] = "deconv"
+        return ".".join(parts)
+
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Checkpoints of a CUDA-constructed reference model lack Wci/Wcf/Wco (conv_lstm_hzzone.py:30-32 registers
+        them only on CPU): missing peepholes mean zeros, as in the reference."""
+        peep = [k for k in self.state_dict() if k.rsplit(".", 1)[-1] in ("Wci", "Wcf", "Wco")]
+        if strict and not any(k in state_dict for k in peep):
+            state_dict = dict(state_dict)
+            own = self.state_dict()
+            for k in peep:
+                state_dict[k] = torch.zeros_like(own[k])
+        return super().load_state_dict(state_dict, strict=strict, **kw)
+
+    # -- VPModel contract -------------------------------------------------------------------------------------------
+    def pred_1(self, x, **kwargs):
+        return self(x, pred_frames=1, **kwargs)[0].squeeze(dim=1)        # ef_blocks.py:181-182
+
+    def forward(self, x, pred_frames: int = 1, **kwargs):
+        b, t, c, h, w = x.shape
+        if (c, h, w) != (self.img_c, self.img_h, self.img_w):
+            raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        pred, _ = self._native_forward(x, int(pred_frames), t)
+        return pred, None                                                # ef_blocks.py:184-187
+
+
+MODEL_CLASSES = {
+    "convlstm-shi": EF_ConvLSTM,
+}
