@@ -16,4 +16,4 @@ stores inputs seeds + outputs under ``tests/golden/``.  ``tests/test_oracle_gold
 restatement against those vectors, so the oracle is pinned to outputs of the reference itself.
 The reference holds no golden vectors of its own (its tests assert shapes only).
 """
-from . import blocks, models, weights  # noqa: F401
+from . import blocks, models, weights, shapes  # noqa: F401

@@ -1,0 +1,118 @@
+"""state_dict key -> shape of the reference models at their default hyper-parameters (test infrastructure).
+
+Lets the CPU baseline build weights for any image size without importing the reference or the product package.
+Checked against the reference's own listings in tests/golden/manifest.json (tests/test_oracle_golden.py).
+"""
+from .models import EF_DEFAULTS, PREDRNN_DEFAULTS, PHYDNET_DEFAULTS
+
+
+def _conv_out(v, k, s, p):
+    return (v + 2 * p - (k - 1) - 1) // s + 1
+
+
+def ef_shapes(img_shape, cfg=None):
+    """SURVEY.md App. B; models/precipitation_nowcasting/ef_conv_lstm.py:70-108."""
+    cfg = {**EF_DEFAULTS, **(cfg or {})}
+    c, h, w = img_shape
+    out = {}
+    in_c = c
+    sizes = []
+    for n in range(3):
+        mid, oc = cfg["enc_c"][2 * n], cfg["enc_c"][2 * n + 1]
+        k, s, p = cfg["enc_conv_k"][n], cfg["enc_conv_s"][n], cfg["enc_conv_p"][n]
+        h, w = _conv_out(h, k, s, p), _conv_out(w, k, s, p)
+        sizes.append((h, w))
+        name = cfg["enc_conv_names"][n]
+        out[f"encoder.stage{n + 1}.{name}.weight"] = (mid, in_c, k, k)
+        out[f"encoder.stage{n + 1}.{name}.bias"] = (mid,)
+        for pk in ("Wci", "Wcf", "Wco"):
+            out[f"encoder.rnn{n + 1}.{pk}"] = (1, oc, h, w)
+        rk = cfg["enc_rnn_k"][n]
+        out[f"encoder.rnn{n + 1}._conv.weight"] = (4 * oc, mid + oc, rk, rk)
+        out[f"encoder.rnn{n + 1}._conv.bias"] = (4 * oc,)
+        in_c = oc
+    for n in range(3):
+        idx = 3 - n
+        mid, oc = cfg["dec_c"][2 * n], cfg["dec_c"][2 * n + 1]
+        hh, ww = sizes[2 - n]
+        for pk in ("Wci", "Wcf", "Wco"):
+            out[f"forecaster.rnn{idx}.{pk}"] = (1, mid, hh, ww)
+        rk = cfg["dec_rnn_k"][n]
+        out[f"forecaster.rnn{idx}._conv.weight"] = (4 * mid, in_c + mid, rk, rk)
+        out[f"forecaster.rnn{idx}._conv.bias"] = (4 * mid,)
+        k = cfg["dec_conv_k"][n]
+        name = cfg["dec_conv_names"][n]
+        out[f"forecaster.stage{idx}.{name}.weight"] = (mid, oc, k, k)
+        out[f"forecaster.stage{idx}.{name}.bias"] = (oc,)
+        in_c = oc
+    out[f"forecaster.stage1.{cfg['final_conv_2_name']}.weight"] = (c, in_c, 1, 1)
+    out[f"forecaster.stage1.{cfg['final_conv_2_name']}.bias"] = (c,)
+    return out
+
+
+def predrnn_shapes(img_shape, cfg=None):
+    """SURVEY.md App. B; models/predrnn_v2.py:92-119, model_blocks/predrnn.py:41-55."""
+    cfg = {**PREDRNN_DEFAULTS, **(cfg or {})}
+    c = img_shape[0]
+    p, L, hid, k = cfg["patch_size"], cfg["num_layers"], cfg["num_hidden"], cfg["filter_size"]
+    out = {}
+    for i in range(L):
+        cin = p * p * c if i == 0 else hid[i - 1]
+        C = hid[i]
+        out[f"cell_list.{i}.conv_x.0.weight"] = (7 * C, cin, k, k)
+        out[f"cell_list.{i}.conv_h.0.weight"] = (4 * C, C, k, k)
+        out[f"cell_list.{i}.conv_m.0.weight"] = (3 * C, C, k, k)
+        out[f"cell_list.{i}.conv_o.0.weight"] = (C, 2 * C, k, k)
+        out[f"cell_list.{i}.conv_last.weight"] = (C, 2 * C, 1, 1)
+    out["conv_last.weight"] = (p * p * c, hid[L - 1], 1, 1)
+    out["adapter.weight"] = (hid[0], hid[0], 1, 1)
+    return out
+
+
+def phydnet_shapes(img_shape, cfg=None):
+    """SURVEY.md App. B; models/phydnet.py:38-63, model_blocks/{enc,conv,phydnet}.py."""
+    cfg = {**PHYDNET_DEFAULTS, **(cfg or {})}
+    c = img_shape[0]
+    out = {}
+
+    def dcgan(prefix, cin, cout, transpose):
+        out[prefix + "main.0.weight"] = (cin, cout, 3, 3) if transpose else (cout, cin, 3, 3)
+        out[prefix + "main.0.bias"] = (cout,)
+        out[prefix + "main.1.weight"] = (cout,)
+        out[prefix + "main.1.bias"] = (cout,)
+
+    dcgan("encoder_E.c1.", c, 32, False)
+    dcgan("encoder_E.c2.", 32, 32, False)
+    dcgan("encoder_E.c3.", 32, 64, False)
+    for e in ("encoder_Ep.", "encoder_Er."):
+        dcgan(e + "c1.", 64, 64, False)
+        dcgan(e + "c2.", 64, 64, False)
+    for d in ("decoder_Dp.", "decoder_Dr."):
+        dcgan(d + "upc1.", 64, 64, True)
+        dcgan(d + "upc2.", 64, 64, True)
+    dcgan("decoder_D.upc1.", 64, 32, True)
+    dcgan("decoder_D.upc2.", 32, 32, True)
+    out["decoder_D.upc3.weight"] = (32, c, 3, 3)
+    out["decoder_D.upc3.bias"] = (c,)
+    hidp, kp = cfg["phycell_channels"], cfg["phycell_kernel_size"][0]
+    for j in range(cfg["phycell_n_layers"]):
+        pre = f"phycell.cell_list.{j}."
+        out[pre + "F.conv1.weight"] = (hidp, 64, kp, kp)
+        out[pre + "F.conv1.bias"] = (hidp,)
+        out[pre + "F.bn1.weight"] = (hidp,)
+        out[pre + "F.bn1.bias"] = (hidp,)
+        out[pre + "F.conv2.weight"] = (64, hidp, 1, 1)
+        out[pre + "F.conv2.bias"] = (64,)
+        out[pre + "convgate.weight"] = (64, 128, 3, 3)
+        out[pre + "convgate.bias"] = (64,)
+    cin = 64
+    kc = cfg["convlstm_kernel_size"][0]
+    for j, hd in enumerate(cfg["convlstm_hidden_dims"][:cfg["convlstm_n_layers"]]):
+        out[f"convcell.cell_list.{j}.conv.weight"] = (4 * hd, cin + hd, kc, kc)
+        out[f"convcell.cell_list.{j}.conv.bias"] = (4 * hd,)
+        cin = hd
+    return out
+
+
+SHAPES = {"convlstm-shi": ef_shapes, "predrnn-pp": predrnn_shapes, "phy": phydnet_shapes,
+          "convlstm-branch": phydnet_shapes}

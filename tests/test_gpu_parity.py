@@ -44,7 +44,7 @@ def _frame_errs(a, b):
     return [float(d[:, t].max()) for t in range(d.shape[1])]
 
 
-EF_CASES = ["ef_1x64", "ef_3x32"]
+EF_CASES = ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64", "branch_1x64"]
 
 
 @pytest.mark.parametrize("name", EF_CASES)
@@ -58,6 +58,10 @@ def test_fp32_mode_matches_reference_golden(manifest, name):
     errs = _frame_errs(pred.cpu().numpy(), gold["pred"])
     assert max(errs) <= FP32_TOL, f"{name}: per-frame max abs err {errs}"
     assert m.last_launch_count() > 0
+    if "loss" in gold:
+        (k, v), = aux.items()
+        assert k == "ST-LSTM decouple loss"
+        assert abs(float(v) - float(gold["loss"])) <= 1e-3 * abs(float(gold["loss"])) + 1e-4
 
 
 @pytest.mark.parametrize("backend", ["simt", "auto"])
@@ -72,6 +76,9 @@ def test_bf16_mode_within_tolerance(manifest, name, backend):
     errs = _frame_errs(pred.cpu().numpy(), gold["pred"])
     assert errs[0] <= BF16_TOL_FIRST, f"{name}/{backend}: first-frame err {errs}"
     assert max(errs) <= BF16_TOL_LAST, f"{name}/{backend}: rollout err {errs}"
+    if "loss" in gold:
+        (k, v), = aux.items()
+        assert abs(float(v) - float(gold["loss"])) <= 0.05 * abs(float(gold["loss"])) + 1e-2
 
 
 @pytest.mark.parametrize("name", EF_CASES)
@@ -149,3 +156,74 @@ def test_ef_pred_1_and_missing_peepholes(manifest):
         got = m(x, pred_frames=2)[0].cpu()
         ref, _ = OM.ef_convlstm_forward(sd_nopeep, x.cpu(), 2)
     assert (got - ref).abs().max() <= FP32_TOL
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# VPModelBlock boundary: single-step cells through vpk_*_cell_step against the reference's block golden vectors
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+def test_blocks_match_reference_golden(manifest, precision, tol):
+    from vp_suite_b200 import model_blocks as MB
+    dev = _cuda()
+    gold = load_golden("blocks")
+    mb = manifest["blocks"]
+
+    def close(a, key):
+        err = np.abs(a.detach().cpu().numpy() - gold[key]).max()
+        assert err <= tol, f"{key} ({precision}): max abs err {err}"
+
+    with torch.no_grad():
+        # Shi et al. ConvLSTM: sequence with inputs from a zero state, then inputs=None from that state
+        blk = MB.ConvLSTM(dev, in_channels=8, enc_channels=16, state_h=12, state_w=10, kernel_size=3)
+        blk.precision = precision
+        blk.load_state_dict(synth_state_dict(mb["hzzone"]["shapes"], mb["hzzone"]["wseed"]))
+        xin = (torch.rand(tuple(mb["hzzone"]["x_shape"]), generator=torch.Generator().manual_seed(5)) * 2 - 1).to(dev)
+        o1, (h1, c1) = blk(xin, None, seq_len=3)
+        o2, (h2, c2) = blk(None, (h1, c1), seq_len=2)
+        for t, k in ((o1, "hz_out1"), (h1, "hz_h1"), (c1, "hz_c1"), (o2, "hz_out2"), (c2, "hz_c2")):
+            close(t, k)
+
+        cell = MB.ConvLSTMCell(input_dim=8, hidden_dim=16, kernel_size=(3, 3), bias=True).to(dev)
+        cell.precision = precision
+        cell.load_state_dict(synth_state_dict(mb["ndrplz"]["shapes"], mb["ndrplz"]["wseed"]))
+        g = torch.Generator().manual_seed(6)
+        x, h, c = (torch.rand((2, 8, 10, 10), generator=g) * 2 - 1, torch.rand((2, 16, 10, 10), generator=g) * 2 - 1,
+                   torch.rand((2, 16, 10, 10), generator=g) * 2 - 1)
+        hn, cn = cell(x.to(dev), (h.to(dev), c.to(dev)))
+        close(hn, "nd_h")
+        close(cn, "nd_c")
+
+        st = MB.SpatioTemporalLSTMCell(16, 32, 8, 8, 5, 1, False).to(dev)
+        st.precision = precision
+        st.load_state_dict(synth_state_dict(mb["stlstm"]["shapes"], mb["stlstm"]["wseed"]))
+        g = torch.Generator().manual_seed(7)
+        x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+        h, c, m = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(3)]
+        res = st(x.to(dev), h.to(dev), c.to(dev), m.to(dev))
+        for t, k in zip(res, ("st_h", "st_c", "st_m", "st_dc", "st_dm")):
+            close(t, k)
+
+        pc = MB.PhyCell_Cell(input_dim=16, action_conditional=False, action_size=0, hidden_dim=49,
+                             kernel_size=(7, 7)).to(dev)
+        pc.precision = precision
+        pc.load_state_dict(synth_state_dict(mb["phycell"]["shapes"], mb["phycell"]["wseed"]))
+        g = torch.Generator().manual_seed(8)
+        x, h = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1, torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+        close(pc(x.to(dev), None, h.to(dev)), "phy_h")
+
+
+def test_stateful_blocks_reset_on_first_timestep():
+    """PhyCell / SingleStepConvLSTM keep per-sequence state on the module (model_blocks/phydnet.py:95-105, 147-163)."""
+    from vp_suite_b200 import model_blocks as MB
+    dev = _cuda()
+    torch.manual_seed(0)
+    blk = MB.SingleStepConvLSTM((8, 8), 8, [16, 8], 2, (3, 3), False, 0, dev).to(dev)
+    x = torch.rand(2, 8, 8, 8, device=dev)
+    with torch.no_grad():
+        (_, _), out_a = blk(x, None, first_timestep=True)
+        a1 = out_a[-1].clone()
+        (_, _), out_b = blk(x, None, first_timestep=False)
+        b1 = out_b[-1].clone()
+        (_, _), out_c = blk(x, None, first_timestep=True)
+    assert not torch.equal(a1, b1)
+    assert torch.equal(a1, out_c[-1])

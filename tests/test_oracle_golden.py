@@ -98,3 +98,11 @@ def test_group_norm_divisor():
 def test_patch_roundtrip():
     x = torch.rand(2, 3, 3, 16, 24)
     assert torch.equal(OM.reshape_patch_back(OM.reshape_patch(x, 4), 4), x)
+
+
+def test_shape_listing_matches_reference(manifest):
+    from oracle.shapes import SHAPES
+    for name, meta in manifest["models"].items():
+        want = {k: tuple(v) for k, v in meta["shapes"].items()}
+        got = SHAPES[meta["key"]](tuple(meta["img_shape"]))
+        assert got == want, (name, set(got.items()) ^ set(want.items()))

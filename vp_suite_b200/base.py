@@ -114,6 +114,14 @@ class NativeRollout:
     # -- handle lifecycle ---------------------------------------------------------------------------------------
     def _native_handle(self):
         lib = N.lib()
+        self._create_handle()
+        versions = tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items())
+        if versions != self._versions:
+            self._push_weights()
+            self._versions = versions
+        return self._handle
+
+    def _create_handle(self):
         if self._handle is None:
             desc = self._native_desc()
             desc.precision = N.PRECISIONS[self.precision]
@@ -121,14 +129,9 @@ class NativeRollout:
             desc.max_microbatch = int(self.max_microbatch)
             desc.use_cuda_graph = int(bool(self.use_cuda_graph))
             h = C.c_void_p()
-            N.check(lib.vpk_model_create(C.byref(desc), C.byref(h)))
+            N.check(N.lib().vpk_model_create(C.byref(desc), C.byref(h)))
             self._handle = h
             self._versions = None
-        versions = tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items())
-        if versions != self._versions:
-            self._push_weights()
-            self._versions = versions
-        return self._handle
 
     def _push_weights(self):
         lib = N.lib()
@@ -143,11 +146,7 @@ class NativeRollout:
     def native_param_layout(self):
         """{native key: shape} the library expects (for layout tests)."""
         lib = N.lib()
-        if self._handle is None:
-            desc = self._native_desc()
-            h = C.c_void_p()
-            N.check(lib.vpk_model_create(C.byref(desc), C.byref(h)))
-            self._handle = h
+        self._create_handle()
         n = C.c_int32()
         N.check(lib.vpk_model_num_params(self._handle, C.byref(n)))
         out = {}
@@ -194,17 +193,24 @@ class NativeRollout:
                                       ws.numel(), C.c_void_p(stream)))
         return out, aux
 
-    def forward_host(self, x, pred_frames=1):
+    def forward_host(self, x, pred_frames=1, out=None):
         """Same as ``forward`` for HOST tensors (pinned memory recommended): microbatches are staged through the
-        device with copies overlapped with compute; returns host tensors."""
+        device with copies overlapped with compute; returns host tensors.  ``out`` may be a caller-owned (pinned)
+        result buffer; otherwise a pinned buffer owned by the module is reused across calls of the same shape."""
         if x.is_cuda:
             raise ValueError("forward_host takes host tensors")
         lib = N.lib()
         h = self._native_handle()
         x = x.detach().to(torch.float32).contiguous()
         b, t_in = x.shape[:2]
-        out = torch.empty((b, pred_frames, self.img_c, self.img_h, self.img_w), dtype=torch.float32,
-                          pin_memory=x.is_pinned())
+        shape = (b, pred_frames, self.img_c, self.img_h, self.img_w)
+        if out is None:
+            out = getattr(self, "_host_out", None)
+            if out is None or tuple(out.shape) != shape:
+                out = torch.empty(shape, dtype=torch.float32, pin_memory=True)
+                self._host_out = out
+        elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.is_cuda:
+            raise ValueError("out must be a contiguous host fp32 tensor of shape %s" % (shape,))
         aux = torch.zeros(1, dtype=torch.float32)
         N.check(lib.vpk_model_forward_host(h, N.ptr(x), b, self._native_t_in(t_in, pred_frames), pred_frames,
                                            N.ptr(out), N.ptr(aux)))

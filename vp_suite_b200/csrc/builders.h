@@ -90,6 +90,9 @@ struct ConvArgs {
   void* out;                // dense [B, OH, OW, Cout] activation type unless f32_strided
   bool f32_strided = false; // out is float*, strides below
   long long oB = 0, oY = 0, oX = 0, oC = 0;
+  bool out_f32_dense = false;   // out is float*, dense NHWC [B, OH, OW, out_pix] (out_pix >= Cout channels per pixel)
+  int out_pix = 0;              // pixel stride of a dense output (0: Cout)
+  const float* res = nullptr;   // fp32 dense [B, OH, OW, Cout] residual added after the activation
 };
 inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -117,13 +120,16 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
     e.out_f32 = 1;
     e.oB = a.oB; e.oY = a.oY; e.oX = a.oX; e.oC = a.oC;
   } else {
-    dense_out(e, a.out, *oh, *ow, a.Cout);
+    dense_out(e, a.out, *oh, *ow, a.out_pix > 0 ? a.out_pix : a.Cout);
+    e.out_f32 = a.out_f32_dense ? 1 : 0;
   }
+  e.res = a.res;
   return s;
 }
 
-// ConvTranspose2d(k, stride, pad, output_padding) + bias + activation, dense NHWC activation-type output
-// (weight layout [Cin, Cout, k, k]); one launch per output parity.
+// ConvTranspose2d(k, stride, pad, output_padding) + bias + activation (weight layout [Cin, Cout, k, k]); one launch per
+// output parity.  Output: dense NHWC [B, OH, OW, Cout] of `out_dtype`, or (nchw) fp32 [.., Cout, OH, OW] with batch
+// stride oB_nchw (a frame inside a [B, P, c, h, w] tensor).
 struct DeconvArgs {
   std::string name;
   int B, H, W, Cin, Cout, k, stride, pad, out_pad;
@@ -131,7 +137,10 @@ struct DeconvArgs {
   const float* weight;
   const float* bias;
   int act;
-  void* out;                // dense [B, OH, OW, Cout]
+  void* out;
+  bool out_f32 = false;       // element type of `out` is float regardless of the activation type
+  bool nchw = false;          // fp32 NCHW output (implies out_f32)
+  long long oB_nchw = 0;
 };
 inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -151,18 +160,30 @@ inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, in
     b.b = a.bias;
     s.biases.push_back(b);
   }
-  const int C = a.Cout, esz = act.esize, actk = a.act;
+  const int C = a.Cout, actk = a.act;
+  const bool f32 = a.out_f32 || a.nchw, nchw = a.nchw;
+  const size_t esz = f32 ? sizeof(float) : static_cast<size_t>(act.esize);
+  const long long oBn = a.oB_nchw;
   void* out = a.out;
   lower_conv_transpose(s, a.k, a.stride, a.pad, a.out_pad, ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0}, a.H, a.W,
                        oh, ow, [=](int ry, int rx, int stride, int OH, int OW) {
                          EpiParams e{};
                          e.kind = EPI_BIAS_ACT;
                          e.act = actk;
-                         e.out = static_cast<char*>(out) + (static_cast<size_t>(ry) * OW + rx) * C * esz;
-                         e.oB = static_cast<long long>(OH) * OW * C;
-                         e.oY = static_cast<long long>(stride) * OW * C;
-                         e.oX = static_cast<long long>(stride) * C;
-                         e.oC = 1;
+                         e.out_f32 = f32 ? 1 : 0;
+                         if (nchw) {   // element (b, ch, Y, X) with Y = stride*q_y + ry, X = stride*q_x + rx
+                           e.out = static_cast<char*>(out) + (static_cast<size_t>(ry) * OW + rx) * esz;
+                           e.oB = oBn;
+                           e.oC = static_cast<long long>(OH) * OW;
+                           e.oY = static_cast<long long>(stride) * OW;
+                           e.oX = stride;
+                         } else {
+                           e.out = static_cast<char*>(out) + (static_cast<size_t>(ry) * OW + rx) * C * esz;
+                           e.oB = static_cast<long long>(OH) * OW * C;
+                           e.oY = static_cast<long long>(stride) * OW * C;
+                           e.oX = static_cast<long long>(stride) * C;
+                           e.oC = 1;
+                         }
                          return e;
                        });
   return s;

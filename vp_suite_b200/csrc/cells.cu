@@ -9,6 +9,7 @@
 #include "../../include/vpk.h"
 #include "builders.h"
 #include "elementwise.h"
+#include "phycell.h"
 #include "stlstm.h"
 
 namespace vpk {
@@ -175,7 +176,73 @@ class StLstmCell : public CellBase {
   std::vector<float> wx, wh, wm, wo, wl;
 };
 
+// ------------------------------------------------------------------------------------------------------------------
+class PhyCellCell : public CellBase {
+ public:
+  PhyCellCell(int precision, int backend_, int ch_, int hid_, int h_, int w_, int k_, const float* c1w, const float* c1b,
+              const float* gnw, const float* gnb, const float* c2w, const float* c2b, const float* gw, const float* gb)
+      : CellBase(precision, backend_), ch(ch_), hid(hid_), h(h_), w(w_), k(k_) {
+    VPK_REQUIRE(ch > 0 && hid > 0 && h > 0 && w > 0 && k % 2 == 1, "bad PhyCell shape");
+    w1.assign(c1w, c1w + static_cast<size_t>(hid) * ch * k * k);
+    b1.assign(c1b, c1b + hid);
+    gw_.assign(gnw, gnw + hid);
+    gb_.assign(gnb, gnb + hid);
+    w2.assign(c2w, c2w + static_cast<size_t>(ch) * hid);
+    b2.assign(c2b, c2b + ch);
+    wg.assign(gw, gw + static_cast<size_t>(ch) * 2 * ch * 9);
+    bg.assign(gb, gb + ch);
+    int sq = 1;
+    while ((sq + 1) * (sq + 1) <= hid) ++sq;          // floor(sqrt(hid)); model_blocks/phydnet.py:348-362
+    while (hid % sq != 0) --sq;
+    groups = hid / sq;
+  }
+  // in: x, h    out: h'
+  void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    const size_t px = static_cast<size_t>(B) * h * w;
+    const int Cp = phycell_padded_channels(hid);
+    void* xb = buf("x", px * ch * esize());
+    void* hi = buf("h_act", px * ch * esize());
+    void* ho = buf("h_act_out", px * ch * esize());
+    float* hm = static_cast<float*>(buf("h_master", px * ch * sizeof(float)));
+    float* ht = static_cast<float*>(buf("htilde", px * ch * sizeof(float)));
+    float* f1 = static_cast<float*>(buf("f1raw", px * Cp * sizeof(float)));
+    void* f1n = buf("f1n", px * Cp * esize());
+    if (built_batch != B) {
+      convs.clear();
+      PhyCellArgs a{"cell.", B, h, w, ch, hid, k, xb, hi, ho, hm, ht, f1, f1n, w1.data(), b1.data(), w2.data(),
+                    b2.data(), wg.data(), bg.data()};
+      for (const ConvSpec& sp : phycell_specs(a, act())) add(sp, s);
+      d_gamma = static_cast<float*>(store.upload(gw_.data(), gw_.size() * sizeof(float), s));
+      d_beta = static_cast<float*>(store.upload(gb_.data(), gb_.size() * sizeof(float), s));
+      finish_build(s);
+      VPK_CUDA(cudaMemsetAsync(f1n, 0, px * Cp * esize(), s));   // padded channels stay zero
+      built_batch = B;
+    }
+    to_nhwc(in[0], xb, dtype, B, ch, h, w, s);
+    to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
+    to_nhwc(in[1], hm, DT_F32, B, ch, h, w, s);
+    run(convs[0], s);
+    launch_groupnorm_act(f1, DT_F32, f1n, dtype, nullptr, B, h * w, hid, Cp, Cp, groups, d_gamma, d_beta, 1e-5f,
+                         ACT_NONE, s);
+    run(convs[1], s);
+    run(convs[2], s);
+    launch_nhwc_to_nchw(hm, DT_F32, out[0], B, ch, h, w, num_sms, s);
+  }
+
+ private:
+  int ch, hid, h, w, k, groups = 1;
+  std::vector<float> w1, b1, gw_, gb_, w2, b2, wg, bg;
+  float *d_gamma = nullptr, *d_beta = nullptr;
+};
+
 }  // namespace
+
+Cell* make_phycell_cell(int precision, int backend, int ch, int hid, int h, int w, int k, const float* conv1_w,
+                        const float* conv1_b, const float* gn_w, const float* gn_b, const float* conv2_w,
+                        const float* conv2_b, const float* gate_w, const float* gate_b) {
+  return new PhyCellCell(precision, backend, ch, hid, h, w, k, conv1_w, conv1_b, gn_w, gn_b, conv2_w, conv2_b, gate_w,
+                         gate_b);
+}
 
 Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, int gate_order,
                          const float* weight, const float* bias) {

@@ -85,9 +85,12 @@ struct EpiParams {
   void* t0;               // ST_C / ST_M: mem buffer [B,H,W,2C] (channel offset applied by caller)
   long long t0_pix;       // elements per pixel of t0 (2C)
   void* t1;               // ST_C: delta_c, ST_M: delta_m   dense [B,H,W,C]
-  // PhyCell blend inputs (activation type, dense [B,H,W,C])
-  const void* q0;         // x (frame)
-  const void* q1;         // h~ = h + F(h)
+  // fp32 dense [B,H,W,C]: BIAS_ACT: residual added after the activation; PHY_GATE: h~ = h + F(h)
+  const float* res;
+  // PHY_GATE: x (frame), activation type, dense [B,H,W,C]
+  const void* q0;
+  // LSTM: optional fp32 copy of h' (dense), for consumers that run in fp32
+  float* h32;
   float forget_bias;
   // optional per-(b, group) statistics for a following GroupNorm: sums[b][g][2] (sum, sum of squares)
   float* gn_sums;

@@ -36,8 +36,8 @@ __global__ void frames_to_nhwc_kernel(const float* __restrict__ x, long long bst
 // PredRNN patchify (models/predrnn_v2.py:232-240): x fp32 [B, T, c, H, W] -> out T [T][B][H/p][W/p][p*p*c],
 // patch-channel order (p_h, p_w, c).
 template <typename T>
-__global__ void patchify_kernel(const float* __restrict__ x, T* __restrict__ out, int B, int Tn, int C, int H, int W,
-                                int p) {
+__global__ void patchify_kernel(const float* __restrict__ x, long long bstride, T* __restrict__ out, int B, int Tn,
+                                int C, int H, int W, int p) {
   const int hp = H / p, wp = W / p, cp = p * p * C;
   const long long total = static_cast<long long>(B) * Tn * hp * wp * cp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -51,7 +51,8 @@ __global__ void patchify_kernel(const float* __restrict__ x, T* __restrict__ out
     const int c = ch % C;
     const int pw = (ch / C) % p;
     const int ph = ch / (C * p);
-    const float v = x[(((static_cast<long long>(b) * Tn + t) * C + c) * H + (yy * p + ph)) * W + (xx * p + pw)];
+    const float v = x[static_cast<long long>(b) * bstride +
+                      ((static_cast<long long>(t) * C + c) * H + (yy * p + ph)) * W + (xx * p + pw)];
     out[i] = from_f32<T>(v);
   }
 }
@@ -126,6 +127,60 @@ __global__ void decouple_reduce_kernel(const float* __restrict__ ad, int B, int 
   if (threadIdx.x == 0) atomicAdd(acc, static_cast<double>(ws[0] + ws[1] + ws[2] + ws[3]));
 }
 
+// GroupNorm (+ optional LeakyReLU(0.2), + optional residual add) over one sample per CTA, NHWC.
+//   in  [B][HW][Cs_in]  (first C channels are real), out [B][HW][Cs_out]; statistics per (sample, group) over
+//   (C/groups) channels x HW positions, two-pass (mean, then centred variance) like ATen's kernel; eps inside the
+//   sqrt; affine gamma/beta per channel.  Thread layout: tx = channel (coalesced), ty strides over positions.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict__ in, TO* __restrict__ out,
+                                                            const TO* __restrict__ add, int HW, int C, int Cs_in,
+                                                            int Cs_out, int groups, int TC,
+                                                            const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, int act) {
+  __shared__ float s_acc[64], s_mean[64], s_rstd[64];
+  const int b = blockIdx.x;
+  const int tx = threadIdx.x % TC, ty = threadIdx.x / TC, rows = 256 / TC;
+  const int cg = C / groups;
+  const bool live = tx < C;
+  const int g = live ? tx / cg : 0;
+  const TI* ip = in + static_cast<size_t>(b) * HW * Cs_in + tx;
+  const float n = static_cast<float>(cg) * HW;
+  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  float a = 0.f;
+  if (live)
+    for (int p = ty; p < HW; p += rows) a += to_f32(ip[static_cast<size_t>(p) * Cs_in]);
+  if (live) atomicAdd(&s_acc[g], a);
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    s_mean[threadIdx.x] = s_acc[threadIdx.x] / n;
+    s_acc[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const float mean = s_mean[g];
+  a = 0.f;
+  if (live)
+    for (int p = ty; p < HW; p += rows) {
+      const float d = to_f32(ip[static_cast<size_t>(p) * Cs_in]) - mean;
+      a = fmaf(d, d, a);
+    }
+  if (live) atomicAdd(&s_acc[g], a);
+  __syncthreads();
+  if (threadIdx.x < groups) s_rstd[threadIdx.x] = rsqrtf(s_acc[threadIdx.x] / n + eps);
+  __syncthreads();
+  if (!live) return;
+  const float sc = s_rstd[g] * gamma[tx];
+  const float sh = beta[tx] - mean * sc;
+  TO* op = out + static_cast<size_t>(b) * HW * Cs_out + tx;
+  const TO* ap = add ? add + static_cast<size_t>(b) * HW * Cs_out + tx : nullptr;
+  for (int p = ty; p < HW; p += rows) {
+    float v = fmaf(to_f32(ip[static_cast<size_t>(p) * Cs_in]), sc, sh);
+    if (act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
+    if (ap) v += to_f32(ap[static_cast<size_t>(p) * Cs_out]);
+    op[static_cast<size_t>(p) * Cs_out] = from_f32<TO>(v);
+  }
+}
+
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
   aux[0] = static_cast<float>(acc[0] * scale);
 }
@@ -169,17 +224,38 @@ void launch_decouple_reduce(const float* ad, int B, int HW, int C, double* acc, 
   VPK_CUDA(cudaGetLastError());
 }
 
+void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype, const void* add, int B, int HW, int C,
+                          int Cs_in, int Cs_out, int groups, const float* gamma, const float* beta, float eps,
+                          int act, cudaStream_t stream) {
+  VPK_REQUIRE(C <= 256 && groups <= 64 && C % groups == 0, "groupnorm: unsupported channel / group count");
+  int TC = 1;
+  while (TC < C) TC <<= 1;
+#define VPK_GN(TI, TO)                                                                                          \
+  groupnorm_act_kernel<TI, TO><<<B, 256, 0, stream>>>(static_cast<const TI*>(in), static_cast<TO*>(out),           \
+                                                      static_cast<const TO*>(add), HW, C, Cs_in, Cs_out, groups, TC, \
+                                                      gamma, beta, eps, act)
+  if (in_dtype == DT_F32 && out_dtype == DT_F32) VPK_GN(float, float);
+  else if (in_dtype == DT_F32 && out_dtype == DT_BF16) VPK_GN(float, __nv_bfloat16);
+  else if (in_dtype == DT_BF16 && out_dtype == DT_BF16) VPK_GN(__nv_bfloat16, __nv_bfloat16);
+  else VPK_THROW(1, "groupnorm: unsupported dtype combination");
+#undef VPK_GN
+  VPK_CUDA(cudaGetLastError());
+}
+
 void launch_decouple_finalize(const double* acc, float* aux, double scale, cudaStream_t stream) {
   decouple_finalize_kernel<<<1, 1, 0, stream>>>(acc, aux, scale);
   VPK_CUDA(cudaGetLastError());
 }
 
-void launch_patchify(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int p, int num_sms,
-                     cudaStream_t stream) {
+void launch_patchify_strided(const float* x, long long bstride, void* out, int dtype, int B, int T, int C, int H, int W,
+                             int p, int num_sms, cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * T * C * H * W;
   const int g = grid_for(total, 256, num_sms);
-  if (dtype == DT_F32) patchify_kernel<float><<<g, 256, 0, stream>>>(x, static_cast<float*>(out), B, T, C, H, W, p);
-  else patchify_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(x, static_cast<__nv_bfloat16*>(out), B, T, C, H, W, p);
+  if (dtype == DT_F32)
+    patchify_kernel<float><<<g, 256, 0, stream>>>(x, bstride, static_cast<float*>(out), B, T, C, H, W, p);
+  else
+    patchify_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C, H, W,
+                                                         p);
   VPK_CUDA(cudaGetLastError());
 }
 

@@ -9,9 +9,10 @@ namespace vpk {
 // x fp32 [B, T, C, H, W] -> out (activation type) [T][B][H][W][C]
 void launch_frames_to_nhwc(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int num_sms,
                            cudaStream_t stream);
-// PredRNN patchify: x fp32 [B, T, c, H, W] -> out [T][B][H/p][W/p][p*p*c]
-void launch_patchify(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int p, int num_sms,
-                     cudaStream_t stream);
+// PredRNN patchify: the first T frames of x fp32 [B, *, c, H, W] (sequence stride `bstride` elements)
+// -> out [T][B][H/p][W/p][p*p*c]
+void launch_patchify_strided(const float* x, long long bstride, void* out, int dtype, int B, int T, int C, int H, int W,
+                             int p, int num_sms, cudaStream_t stream);
 // one patch frame [B][H/p][W/p][p*p*c] -> frame t of fp32 [B, P, c, H, W]
 void launch_unpatchify(const void* in, float* out, int dtype, int B, int P, int t, int C, int H, int W, int p,
                        int num_sms, cudaStream_t stream);
@@ -27,5 +28,11 @@ void launch_cast_f32_to_bf16(const float* in, void* out, long long n, int num_sm
 // PredRNN-V2 decouple loss: ad fp32 [2B][HW][C] (adapter(delta_c) then adapter(delta_m)); *acc += sum_{b,ch} |cos|
 void launch_decouple_reduce(const float* ad, int B, int HW, int C, double* acc, cudaStream_t stream);
 void launch_decouple_finalize(const double* acc, float* aux, double scale, cudaStream_t stream);
+
+// GroupNorm(groups, C) + optional LeakyReLU(0.2) + optional residual add, one sample per CTA; NHWC with pixel strides
+// Cs_in / Cs_out (>= C).  nn.GroupNorm semantics (eps inside the sqrt, affine).
+void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype, const void* add, int B, int HW, int C,
+                          int Cs_in, int Cs_out, int groups, const float* gamma, const float* beta, float eps,
+                          int act, cudaStream_t stream);
 
 }  // namespace vpk

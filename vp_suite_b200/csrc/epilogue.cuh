@@ -119,6 +119,12 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y,
       float v[NCH];
 #pragma unroll
       for (int j = 0; j < NCH; ++j) v[j] = apply_act(acc[0][j], E.act);
+      if (E.res != nullptr) {
+        float r[NCH];
+        load_f32<NCH>(E.res + pix * C + ch0, r, nvalid);
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) v[j] += r[j];
+      }
       const long long off = b * E.oB + y * E.oY + x * E.oX;
       if (E.oC == 1) {
         if (E.out_f32) store_f32<NCH>(static_cast<float*>(E.out) + off + ch0, v, nvalid);
@@ -135,10 +141,11 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y,
     } else {   // EPI_PHY_GATE: h' = h~ + sigmoid(acc) * (x - h~)      (model_blocks/phydnet.py:58-61)
       float xf[NCH], ht[NCH], v[NCH];
       load_act<NCH>(static_cast<const T*>(E.q0) + pix * C + ch0, xf, nvalid);
-      load_act<NCH>(static_cast<const T*>(E.q1) + pix * C + ch0, ht, nvalid);
+      load_f32<NCH>(E.res + pix * C + ch0, ht, nvalid);
 #pragma unroll
       for (int j = 0; j < NCH; ++j) v[j] = ht[j] + sigmoid_f(acc[0][j]) * (xf[j] - ht[j]);
-      store_act<NCH>(static_cast<T*>(E.out) + pix * C + ch0, v, nvalid);
+      store_f32<NCH>(E.s0 + pix * C + ch0, v, nvalid);                       // fp32 master of the hidden state
+      store_act<NCH>(static_cast<T*>(E.out) + pix * C + ch0, v, nvalid);     // conv-operand copy
     }
   } else if constexpr (G == 4) {
     float c[NCH];
@@ -172,6 +179,7 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y,
       }
       store_f32<NCH>(cp, c, nvalid);
       store_act<NCH>(static_cast<T*>(E.out) + b * E.oB + y * E.oY + x * E.oX + ch0, h, nvalid);
+      if (E.h32 != nullptr) store_f32<NCH>(E.h32 + pix * C + ch0, h, nvalid);
     } else {   // EPI_ST_C: predrnn.py:65-70; acc = (i, f, g, o_x + o_h)
       float dc[NCH], op[NCH];
 #pragma unroll

@@ -10,7 +10,9 @@ namespace {
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-void add_steps_for(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int wref, int ky, int kx, int wc0) {
+void add_steps_for(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int wref, int ky, int kx, int wc0,
+                   int wc_count) {
+  if (wc_count < 0) wc_count = C;
   for (int c0 = 0; c0 < C; c0 += 64) {
     HostStep h{};
     h.s.src = static_cast<short>(src);
@@ -19,6 +21,7 @@ void add_steps_for(std::vector<HostStep>& steps, int src, int dy, int dx, int C,
     h.s.c0 = static_cast<short>(c0);
     h.s.kc = static_cast<short>(std::min(64, C - c0));
     h.s.wk = 0;
+    h.kw_valid = std::max(0, std::min<int>(h.s.kc, wc_count - c0));
     h.wref = wref;
     h.ky = ky;
     h.kx = kx;
@@ -49,7 +52,7 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
       for (int kx = 0; kx < k; ++kx)
         for (size_t i = 0; i < inputs.size(); ++i)
           add_steps_for(ph.steps, src_idx[i], ky - pad, kx - pad, inputs[i].view.C, inputs[i].wref, ky, kx,
-                        inputs[i].wc0);
+                        inputs[i].wc0, inputs[i].wc_count);
   } else {
     VPK_REQUIRE(inputs.size() == 1, "stride-2 conv takes a single input");
     VPK_REQUIRE(in_h % 2 == 0 && in_w % 2 == 0, "stride-2 conv needs even input size");
@@ -73,7 +76,7 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
         const int tx = kx - pad;
         const int px = ((tx % 2) + 2) % 2;
         const int dx = floordiv(tx - px, 2);
-        add_steps_for(ph.steps, base_idx + py * 2 + px, dy, dx, in.view.C, in.wref, ky, kx, in.wc0);
+        add_steps_for(ph.steps, base_idx + py * 2 + px, dy, dx, in.view.C, in.wref, ky, kx, in.wc0, in.wc_count);
       }
     }
   }
@@ -102,7 +105,7 @@ void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pa
         for (int kx = 0; kx < k; ++kx) {
           if (((rx + pad - kx) % stride + stride) % stride != 0) continue;
           const int dx = floordiv(rx + pad - kx, stride);
-          add_steps_for(ph.steps, src, dy, dx, input.view.C, input.wref, ky, kx, input.wc0);
+          add_steps_for(ph.steps, src, dy, dx, input.view.C, input.wref, ky, kx, input.wc0, input.wc_count);
         }
       }
       ph.epi = epi_for_phase(ry, rx, stride, OH, OW);
@@ -194,7 +197,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
               if (w.gate_block[g] < 0) continue;
               const int oc = w.gate_block[g] * C + ch;
               float* row = wf.data() + static_cast<size_t>(ch * G + g) * K_pad + h.s.wk;
-              for (int j = 0; j < h.s.kc; ++j) row[j] = weight_at(w, oc, h.wc0 + h.s.c0 + j, h.ky, h.kx);
+              for (int j = 0; j < h.kw_valid; ++j) row[j] = weight_at(w, oc, h.wc0 + h.s.c0 + j, h.ky, h.kx);
             }
         }
         PackedWeights& q = pw[p];
@@ -238,7 +241,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
     double kreal = 0;
-    for (const HostStep& h : ph.steps) kreal += h.s.kc;
+    for (const HostStep& h : ph.steps) kreal += h.kw_valid;
     L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;
     if (!measure_only) {
       const PackedWeights& q = (*packed)[p];

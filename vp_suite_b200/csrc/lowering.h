@@ -27,6 +27,7 @@ struct BiasRef {
 
 struct HostStep {
   ConvStep s;
+  int kw_valid;  // channels of this step that exist in the weight tensor (<= s.kc; the rest is zero padding)
   int wref;      // index into ConvSpec::wrefs
   int ky, kx;    // tap of that weight tensor
   int wc0;       // input-channel index of that weight tensor that corresponds to channel 0 of the source
@@ -54,6 +55,8 @@ struct ConvInput {                  // one logical input tensor of a conv (full-
   SrcView view;
   int wref;                         // weight tensor it multiplies
   int wc0;                          // its channel offset inside that weight's input-channel dimension
+  int wc_count = -1;                // channels the weight really has for this input (-1: view.C); a view may carry
+                                    // zero-padded extra channels (e.g. 49 -> 56 so that TMA strides are 16-byte)
 };
 
 // Appends the K-steps of a k x k conv with the given stride (1 or 2) and padding over `inputs` to spec.phases[0]

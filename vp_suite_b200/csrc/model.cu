@@ -107,15 +107,15 @@ float* Model::dev_f32(const std::string& name, const std::vector<float>& host, c
   return d;
 }
 
-void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream) {
-  std::vector<BuiltConv> built = build_conv(spec, dtype, backend, store, packed_cache, stream, num_sms, measure);
+void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream, int dt_override) {
+  const int dt = dt_override >= 0 ? dt_override : dtype;
+  std::vector<BuiltConv> built = build_conv(spec, dt, backend, store, packed_cache, stream, num_sms, measure);
   if (measure) return;
   for (BuiltConv& bc : built) {
     Op op;
     op.name = bc.name;
     op.flops = bc.L.flops;
     op.gate = bc.L.is_gate_gemm != 0;
-    const int dt = dtype;
     if (bc.use_tc) {
       auto plan = std::make_shared<TcPlan>(bc.tc);
       op.fn = [plan](cudaStream_t s, const RunCtx&) { launch_conv_tc(*plan, s); };

@@ -81,7 +81,8 @@ class Model {
   const float* hp(const std::string& key) const;           // host data of a parameter
   bool has(const std::string& key) const;
   float* dev_f32(const std::string& name, const std::vector<float>& host, cudaStream_t stream);  // cached upload
-  void add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream);
+  // dt: operand type of this launch (-1: the model's precision); lets one program mix bf16 cells with fp32 convs
+  void add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream, int dt = -1);
   void add_memset(Program& prog, void* p, size_t bytes, const char* name);
   int esize() const { return static_cast<int>(dtype_size(dtype)); }
   SrcView dense_view(void* p, int H, int W, int C) const {

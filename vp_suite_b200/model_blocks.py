@@ -1,0 +1,318 @@
+"""
+Drop-in VPModelBlock classes: the recurrent cells of the hot path, one native call per timestep.
+
+Signatures, parameter names/shapes and stateful behaviour follow the reference blocks (file:line in each class);
+the arithmetic happens in libvpk's single-step cell entry points (include/vpk.h), never in Python.
+
+    ConvLSTM                <- vp_suite/model_blocks/conv_lstm_hzzone.py:7-70     (Shi et al., peepholes)
+    ConvLSTMCell            <- vp_suite/model_blocks/conv_lstm_ndrplz.py:7-48     (ndrplz cell)
+    SingleStepConvLSTM      <- vp_suite/model_blocks/phydnet.py:117-175
+    SpatioTemporalLSTMCell  <- vp_suite/model_blocks/predrnn.py:7-83              (layer_norm=False)
+    PhyCell_Cell / PhyCell  <- vp_suite/model_blocks/phydnet.py:13-114            (action_conditional=False)
+"""
+import ctypes as C
+
+import torch
+import torch.nn as nn
+
+from . import _native as N
+from .base import VPModelBlock
+from .models import _gn_divisor
+
+
+class _NativeCell:
+    """Owns a ``vpk_cell`` handle; rebuilt when the module's weights change."""
+    precision: str = "fp32"      #: cells default to the fp32-operand mode (the reference's own numerics)
+    backend: str = "auto"
+
+    def _cell_init(self):
+        self._cell = None
+        self._cell_versions = None
+
+    def _cell_handle(self):
+        versions = tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items()) + (self.precision,
+                                                                                               self.backend)
+        if self._cell is None or versions != self._cell_versions:
+            self._cell_release()
+            self._cell = self._cell_create()
+            self._cell_versions = versions
+        return self._cell
+
+    def _cell_release(self):
+        if getattr(self, "_cell", None) is not None:
+            N.lib().vpk_cell_destroy(self._cell)
+            self._cell = None
+
+    def __del__(self):
+        try:
+            self._cell_release()
+        except Exception:
+            pass
+
+    @staticmethod
+    def _host(t):
+        return t.detach().to("cpu", torch.float32).contiguous()
+
+    @staticmethod
+    def _dev(t):
+        if not t.is_cuda:
+            raise N.NativeError("vp_suite_b200 blocks run on CUDA tensors only (there is no CPU path)")
+        return t.detach().to(torch.float32).contiguous()
+
+    @staticmethod
+    def _stream(t):
+        return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+class ConvLSTMCell(nn.Module, _NativeCell):
+    """conv_lstm_ndrplz.py:7-48: gate conv over cat(x, h), split order (i, f, o, g), no peepholes."""
+
+    def __init__(self, input_dim, hidden_dim, kernel_size, bias):
+        super().__init__()
+        self._cell_init()
+        self.input_dim, self.hidden_dim, self.kernel_size, self.bias = input_dim, hidden_dim, kernel_size, bias
+        if kernel_size[0] != kernel_size[1] or kernel_size[0] % 2 == 0:
+            raise ValueError("square odd kernels only")
+        self.padding = kernel_size[0] // 2, kernel_size[1] // 2
+        self.conv = nn.Conv2d(input_dim + hidden_dim, 4 * hidden_dim, kernel_size, padding=self.padding, bias=bias)
+        self._hw = None
+
+    def _cell_create(self):
+        h, w = self._hw
+        cell = C.c_void_p()
+        wt = self._host(self.conv.weight)
+        b = self._host(self.conv.bias) if self.conv.bias is not None else None
+        N.check(N.lib().vpk_convlstm_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend],
+                                                 self.input_dim, self.hidden_dim, h, w, self.kernel_size[0], 1,
+                                                 N.ptr(wt), N.ptr(b), C.byref(cell)))
+        return cell
+
+    def forward(self, input_tensor, cur_state):
+        h_cur, c_cur = cur_state
+        x, h, c = self._dev(input_tensor), self._dev(h_cur), self._dev(c_cur)
+        if self._hw != tuple(x.shape[-2:]):
+            self._hw = tuple(x.shape[-2:])
+            self._cell_release()
+        cell = self._cell_handle()
+        h_next, c_next = torch.empty_like(h), torch.empty_like(c)
+        N.check(N.lib().vpk_convlstm_cell_step(cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), None, None, None,
+                                               N.ptr(h_next), N.ptr(c_next), self._stream(x)))
+        return h_next, c_next
+
+    def init_hidden(self, batch_size, image_size):                       # conv_lstm_ndrplz.py:45-48
+        height, width = image_size
+        dev = self.conv.weight.device
+        return (torch.zeros(batch_size, self.hidden_dim, height, width, device=dev),
+                torch.zeros(batch_size, self.hidden_dim, height, width, device=dev))
+
+
+class ConvLSTM(VPModelBlock, _NativeCell):
+    """conv_lstm_hzzone.py:7-70: whole-sequence driver of the Shi-et-al. ConvLSTM with peepholes."""
+    NAME = "ConvLSTM (Shi et al.)"
+    PAPER_REFERENCE = "https://arxiv.org/abs/1506.04214"
+    CODE_REFERENCE = "https://github.com/Hzzone/Precipitation-Nowcasting"
+    MATCHES_REFERENCE = "Yes"
+
+    def __init__(self, device, in_channels, enc_channels, state_h, state_w, kernel_size, stride=1, padding=1):
+        super().__init__()
+        self._cell_init()
+        if stride != 1 or padding != kernel_size // 2 or kernel_size % 2 == 0:
+            raise ValueError("only stride 1 / 'same' padding keeps the state size (as all reference configs do)")
+        self.device = device
+        self._conv = nn.Conv2d(in_channels + enc_channels, enc_channels * 4, kernel_size, stride, padding)
+        self.state_h, self.state_w = state_h, state_w
+        # registered on every device (the reference registers them on CPU only, conv_lstm_hzzone.py:30-32)
+        self.Wci = nn.Parameter(torch.zeros(1, enc_channels, state_h, state_w))
+        self.Wcf = nn.Parameter(torch.zeros(1, enc_channels, state_h, state_w))
+        self.Wco = nn.Parameter(torch.zeros(1, enc_channels, state_h, state_w))
+        self.in_c, self.enc_c, self._k = in_channels, enc_channels, kernel_size
+        self.to(device)
+
+    def _cell_create(self):
+        cell = C.c_void_p()
+        wt, b = self._host(self._conv.weight), self._host(self._conv.bias)
+        N.check(N.lib().vpk_convlstm_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], self.in_c,
+                                                 self.enc_c, self.state_h, self.state_w, self._k, 0, N.ptr(wt),
+                                                 N.ptr(b), C.byref(cell)))
+        return cell
+
+    def forward(self, inputs, states, seq_len):
+        dev = self._conv.weight.device
+        if states is None:                                               # conv_lstm_hzzone.py:39-45
+            b = inputs.shape[0]
+            c = torch.zeros((b, self.enc_c, self.state_h, self.state_w), dtype=torch.float, device=dev)
+            h = torch.zeros((b, self.enc_c, self.state_h, self.state_w), dtype=torch.float, device=dev)
+        else:
+            h, c = states
+            b = h.shape[0]
+        h, c = self._dev(h), self._dev(c)
+        cell = self._cell_handle()
+        peep = [self._dev(p)[0] for p in (self.Wci, self.Wcf, self.Wco)]
+        outputs = []
+        for t in range(seq_len):                                         # conv_lstm_hzzone.py:52-69
+            x = None if inputs is None else self._dev(inputs[:, t])      # None = all-zero input (:54-56)
+            h_new, c_new = torch.empty_like(h), torch.empty_like(c)
+            N.check(N.lib().vpk_convlstm_cell_step(cell, b, N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(peep[0]),
+                                                   N.ptr(peep[1]), N.ptr(peep[2]), N.ptr(h_new), N.ptr(c_new),
+                                                   self._stream(h)))
+            h, c = h_new, c_new
+            outputs.append(h)
+        return torch.stack(outputs, dim=1), (h, c)
+
+
+class SingleStepConvLSTM(nn.Module):
+    """model_blocks/phydnet.py:117-175: time-major stack of ConvLSTMCell with module-held state."""
+
+    def __init__(self, input_size, input_dim, hidden_dims, n_layers, kernel_size, action_conditional, action_size,
+                 device):
+        super().__init__()
+        if action_conditional:
+            raise NotImplementedError("action-conditional variant: SURVEY 8(f)")
+        self.input_size, self.input_dim, self.hidden_dims = input_size, input_dim, hidden_dims
+        self.n_layers, self.kernel_size = n_layers, kernel_size
+        self.H, self.C = [], []
+        self.action_size, self.action_conditional, self.device = action_size, action_conditional, device
+        cells, cur = [], input_dim
+        for i in range(n_layers):
+            cells.append(ConvLSTMCell(cur, hidden_dims[i], kernel_size, True))
+            cur = hidden_dims[i]
+        self.cell_list = nn.ModuleList(cells)
+
+    def forward(self, frame, action, first_timestep=False):
+        if first_timestep:
+            self.init_hidden(frame.shape[0], frame.device)
+        inp = frame
+        for j, cell in enumerate(self.cell_list):                        # phydnet.py:157-161
+            self.H[j], self.C[j] = cell(inp, (self.H[j], self.C[j]))
+            inp = self.H[j]
+        return (self.H, self.C), self.H
+
+    def init_hidden(self, batch_size, device=None):                      # phydnet.py:165-171 (states on the input's device)
+        device = device or self.device
+        self.H = [torch.zeros(batch_size, hd, *self.input_size, device=device) for hd in self.hidden_dims[:self.n_layers]]
+        self.C = [torch.zeros(batch_size, hd, *self.input_size, device=device) for hd in self.hidden_dims[:self.n_layers]]
+
+    def set_hidden(self, hidden):
+        self.H, self.C = hidden
+
+
+class SpatioTemporalLSTMCell(VPModelBlock, _NativeCell):
+    """model_blocks/predrnn.py:7-83 with layer_norm=False."""
+    NAME = "Spatio-Temporal LSTM Cell"
+    PAPER_REFERENCE = "https://arxiv.org/abs/2103.09504"
+    CODE_REFERENCE = "https://github.com/thuml/predrnn-pytorch"
+    MATCHES_REFERENCE = "Yes"
+
+    def __init__(self, in_channel, num_hidden, height, width, filter_size, stride, layer_norm):
+        super().__init__()
+        self._cell_init()
+        if layer_norm:
+            raise NotImplementedError("layer_norm=True: SURVEY 8(f)")
+        if stride != 1 or filter_size % 2 == 0:
+            raise ValueError("stride 1 and odd filter sizes only")
+        self.num_hidden, self.padding, self._forget_bias = num_hidden, filter_size // 2, 1.0
+        self._shape = (in_channel, height, width, filter_size)
+
+        def conv(ci, co):
+            return nn.Sequential(nn.Conv2d(ci, co, filter_size, stride, self.padding, bias=False))
+        self.conv_x = conv(in_channel, num_hidden * 7)
+        self.conv_h = conv(num_hidden, num_hidden * 4)
+        self.conv_m = conv(num_hidden, num_hidden * 3)
+        self.conv_o = conv(num_hidden * 2, num_hidden)
+        self.conv_last = nn.Conv2d(num_hidden * 2, num_hidden, 1, 1, 0, bias=False)
+
+    def _cell_create(self):
+        cin, h, w, k = self._shape
+        cell = C.c_void_p()
+        ws = [self._host(m) for m in (self.conv_x[0].weight, self.conv_h[0].weight, self.conv_m[0].weight,
+                                      self.conv_o[0].weight, self.conv_last.weight)]
+        N.check(N.lib().vpk_stlstm_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], cin,
+                                               self.num_hidden, h, w, k, *[N.ptr(t) for t in ws], C.byref(cell)))
+        return cell
+
+    def forward(self, x_t, h_t, c_t, m_t):
+        x, h, c, m = (self._dev(t) for t in (x_t, h_t, c_t, m_t))
+        cell = self._cell_handle()
+        outs = [torch.empty_like(h) for _ in range(5)]
+        N.check(N.lib().vpk_stlstm_cell_step(cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(m),
+                                             *[N.ptr(o) for o in outs], self._stream(x)))
+        return tuple(outs)                                               # h', c', m', delta_c, delta_m (predrnn.py:82)
+
+
+class PhyCell_Cell(VPModelBlock, _NativeCell):
+    """model_blocks/phydnet.py:13-62 with action_conditional=False."""
+    NAME = "PhyCell - Cell"
+    PAPER_REFERENCE = "https://arxiv.org/abs/2003.01460"
+    CODE_REFERENCE = "https://github.com/vincent-leguen/PhyDNet"
+    MATCHES_REFERENCE = "Not Yet"
+
+    def __init__(self, input_dim, action_conditional, action_size, hidden_dim, kernel_size, bias=True):
+        super().__init__()
+        self._cell_init()
+        if action_conditional:
+            raise NotImplementedError("action-conditional variant: SURVEY 8(f)")
+        if not bias or kernel_size[0] != kernel_size[1] or kernel_size[0] % 2 == 0:
+            raise ValueError("bias=True and square odd kernels only")
+        self.input_dim, self.action_size, self.action_conditional = input_dim, action_size, action_conditional
+        self.F_hidden_dim, self.kernel_size, self.bias = hidden_dim, kernel_size, bias
+        self.padding = kernel_size[0] // 2, kernel_size[1] // 2
+        self.F = nn.Sequential()
+        self.F.add_module("conv1", nn.Conv2d(input_dim, hidden_dim, kernel_size, (1, 1), self.padding))
+        self.F.add_module("bn1", nn.GroupNorm(_gn_divisor(hidden_dim), hidden_dim))
+        self.F.add_module("conv2", nn.Conv2d(hidden_dim, input_dim, (1, 1), (1, 1), (0, 0)))
+        self.convgate = nn.Conv2d(2 * input_dim, input_dim, (3, 3), padding=(1, 1), bias=bias)
+        self._hw = None
+
+    def _cell_create(self):
+        h, w = self._hw
+        cell = C.c_void_p()
+        ts = [self._host(t) for t in (self.F.conv1.weight, self.F.conv1.bias, self.F.bn1.weight, self.F.bn1.bias,
+                                      self.F.conv2.weight, self.F.conv2.bias, self.convgate.weight, self.convgate.bias)]
+        N.check(N.lib().vpk_phycell_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend],
+                                                self.input_dim, self.F_hidden_dim, h, w, self.kernel_size[0],
+                                                *[N.ptr(t) for t in ts], C.byref(cell)))
+        return cell
+
+    def forward(self, frame, action, hidden):
+        x, h = self._dev(frame), self._dev(hidden)
+        if self._hw != tuple(x.shape[-2:]):
+            self._hw = tuple(x.shape[-2:])
+            self._cell_release()
+        cell = self._cell_handle()
+        out = torch.empty_like(h)
+        N.check(N.lib().vpk_phycell_cell_step(cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(out), self._stream(x)))
+        return out
+
+
+class PhyCell(VPModelBlock):
+    """model_blocks/phydnet.py:65-114: stack of PhyCell_Cell with module-held state."""
+    NAME = "PhyCell"
+    PAPER_REFERENCE = "https://arxiv.org/abs/2003.01460"
+    CODE_REFERENCE = "https://github.com/vincent-leguen/PhyDNet"
+    MATCHES_REFERENCE = "Not Yet"
+
+    def __init__(self, input_size, input_dim, hidden_dims, n_layers, kernel_size, action_conditional, action_size,
+                 device):
+        super().__init__()
+        self.input_size, self.input_dim, self.hidden_dims = input_size, input_dim, hidden_dims
+        self.n_layers, self.kernel_size, self.H, self.device = n_layers, kernel_size, [], device
+        self.cell_list = nn.ModuleList([PhyCell_Cell(input_dim, action_conditional, action_size, hidden_dims[i],
+                                                     kernel_size) for i in range(n_layers)])
+
+    def forward(self, frame, action, first_timestep=False):
+        if first_timestep:
+            self.init_hidden(frame.shape[0], frame.device)
+        for j, cell in enumerate(self.cell_list):                        # phydnet.py:100-104
+            self.H[j] = cell(frame if j == 0 else self.H[j - 1], action, self.H[j])
+        return self.H, self.H
+
+    def init_hidden(self, batch_size, device=None):
+        device = device or self.device
+        self.H = [torch.zeros(batch_size, self.input_dim, self.input_size[0], self.input_size[1], device=device)
+                  for _ in range(self.n_layers)]
+
+    def _set_hidden(self, H):
+        self.H = H
+
+
+MODEL_BLOCK_CLASSES = [ConvLSTM, SpatioTemporalLSTMCell, PhyCell_Cell, PhyCell]

@@ -205,6 +205,232 @@ class EF_ConvLSTM(VPModel, NativeRollout):
         return pred, None                                                # ef_blocks.py:184-187
 
 
+class PredRNN_V2(VPModel, NativeRollout):
+    NAME = "PredRNN++"
+    PAPER_REFERENCE = "https://arxiv.org/abs/2103.09504"
+    CODE_REFERENCE = "https://github.com/thuml/predrnn-pytorch"
+    MATCHES_REFERENCE: str = "Yes"
+    CAN_HANDLE_ACTIONS = False
+    NEEDS_COMPLETE_INPUT = True
+
+    # hyper-parameters: predrnn_v2.py:34-54 (training-only ones are kept so that configs round-trip)
+    patch_size = 4
+    num_layers = 3
+    num_hidden = [128, 128, 128, 128]
+    filter_size = 5
+    stride = 1
+    inflated_action_dim = 3
+    layer_norm: bool = False
+    conv_actions_on_input: bool = True
+    residual_on_action_conv: bool = True
+    reverse_input: bool = True
+    decoupling_loss_scale = 100.0
+    scheduled_sampling: bool = True
+    sampling_stop_iter: int = 50000
+    sampling_changing_rate = 2e-5
+    reverse_scheduled_sampling: bool = False
+    r_sampling_step_1: int = 25000
+    r_sampling_step_2: int = 50000
+    r_exp_alpha: int = 5000
+    training_iteration: int = None
+    sampling_eta: float = None
+
+    def __init__(self, device, **model_kwargs):
+        super().__init__(device, **model_kwargs)
+        self._native_init()
+        if self.action_conditional:
+            raise NotImplementedError("the native rollout covers the non action-conditional PredRNN-V2 (SURVEY 8(f))")
+        if self.layer_norm:
+            raise NotImplementedError("the native rollout covers layer_norm=False (SURVEY 8(f))")
+        if self.stride != 1:
+            raise AttributeError("ST-LSTM stride must be 1")
+        self.patch_c = self.patch_size * self.patch_size * self.img_c          # predrnn_v2.py:59-62
+        self.patch_a = self.action_size
+        self.patch_h = self.rnn_h = self.img_h // self.patch_size
+        self.patch_w = self.rnn_w = self.img_w // self.patch_size
+        self.conv_actions_on_input = False                                     # predrnn_v2.py:68-70
+        self.residual_on_action_conv = False
+        cells = []
+        for i in range(self.num_layers):                                       # predrnn_v2.py:92-108
+            cin = self.patch_c if i == 0 else self.num_hidden[i - 1]
+            C, k = self.num_hidden[i], self.filter_size
+            cell = _Params()
+            for name, (o, ci) in (("conv_x", (7 * C, cin)), ("conv_h", (4 * C, C)), ("conv_m", (3 * C, C)),
+                                  ("conv_o", (C, 2 * C))):
+                setattr(cell, name, nn.Sequential(nn.Conv2d(ci, o, k, 1, k // 2, bias=False)))
+            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
+            cells.append(cell)
+        self.cell_list = nn.ModuleList(cells)
+        self.conv_last = nn.Conv2d(self.num_hidden[self.num_layers - 1], self.patch_c, 1, 1, 0, bias=False)
+        self.adapter = nn.Conv2d(self.num_hidden[0], self.num_hidden[0], 1, 1, 0, bias=False)
+        self.training_iteration = 1                                            # predrnn_v2.py:124-126
+        self.sampling_eta = 1.0
+        self.to(device)
+
+    def _native_desc(self):
+        d = N.ModelDesc()
+        d.kind = N.VPK_MODEL_PREDRNN_PP
+        d.img_c, d.img_h, d.img_w = self.img_c, self.img_h, self.img_w
+        d.patch_size, d.num_layers, d.filter_size = self.patch_size, self.num_layers, self.filter_size
+        for i, v in enumerate(self.num_hidden[:8]):
+            d.num_hidden[i] = int(v)
+        d.decoupling_loss_scale = float(self.decoupling_loss_scale)
+        return d
+
+    def _native_key(self, key):
+        return key
+
+    def pred_1(self, x, **kwargs):
+        return self(x, pred_frames=1, **kwargs)[0].squeeze(dim=1)              # predrnn_v2.py:128-129
+
+    def forward(self, x, pred_frames: int = 1, **kwargs):
+        b, total, c, h, w = x.shape
+        if total - pred_frames < 1:                                            # predrnn_v2.py:134-137
+            raise ValueError(f"Model {self.NAME} needs input sequences that also include the target frames!")
+        if (c, h, w) != (self.img_c, self.img_h, self.img_w):                  # predrnn_v2.py:234-236
+            raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        if kwargs.get("train", False):
+            raise NotImplementedError("the native rollout is inference-only")
+        pred, aux = self._native_forward(x, int(pred_frames), total, want_aux=True)
+        return pred, {"ST-LSTM decouple loss": aux[0]}                         # predrnn_v2.py:229-230
+
+
+def _dcgan(cin, cout, stride, transpose):
+    """DCGANConv / DCGANConvTranspose parameter layout (model_blocks/conv.py:58-95): main.0 conv, main.1 GroupNorm."""
+    m = _Params()
+    if transpose:
+        conv = nn.ConvTranspose2d(cin, cout, (3, 3), stride, 1, output_padding=int(stride == 2))
+    else:
+        conv = nn.Conv2d(cin, cout, (3, 3), stride, 1)
+    m.main = nn.Sequential(conv, nn.GroupNorm(16, cout), nn.LeakyReLU(0.2, inplace=True))
+    return m
+
+
+def _gn_divisor(x):
+    """model_blocks/phydnet.py:348-362."""
+    sq = int(x ** 0.5)
+    while (sq + 1) * (sq + 1) <= x:
+        sq += 1
+    while x % sq != 0:
+        sq -= 1
+    return x // sq
+
+
+class PhyDNet(VPModel, NativeRollout):
+    NAME = "PhyDNet"
+    PAPER_REFERENCE = "https://arxiv.org/abs/2003.01460"
+    CODE_REFERENCE = "https://github.com/vincent-leguen/PhyDNet"
+    MATCHES_REFERENCE: str = "Not Yet"
+    CAN_HANDLE_ACTIONS = True
+
+    # hyper-parameters: models/phydnet.py:28-36
+    phycell_n_layers = 1
+    phycell_channels = 49
+    phycell_kernel_size = (7, 7)
+    convlstm_n_layers = 3
+    convlstm_hidden_dims = [128, 128, 64]
+    convlstm_kernel_size = (3, 3)
+    moment_loss_scale = 1.0
+    teacher_forcing_decay = 0.003
+
+    _KIND = N.VPK_MODEL_PHY
+
+    def __init__(self, device, **model_kwargs):
+        super().__init__(device, **model_kwargs)
+        self._native_init()
+        if self.action_conditional:
+            raise NotImplementedError("the native rollout covers the non action-conditional PhyDNet (SURVEY 8(f))")
+        if self.img_h % 4 or self.img_w % 4:
+            raise AttributeError("image size must be a multiple of 4 (other sizes need the reference's Resize)")
+        c = self.img_c
+        # construction order of the reference (models/phydnet.py:41-63) so that a given seed yields the same init
+        self.encoder_E = _Params()
+        self.encoder_E.c1 = _dcgan(c, 32, 2, False)
+        self.encoder_E.c2 = _dcgan(32, 32, 1, False)
+        self.encoder_E.c3 = _dcgan(32, 64, 2, False)
+        for name in ("encoder_Ep", "encoder_Er"):
+            e = _Params()
+            e.c1 = _dcgan(64, 64, 1, False)
+            e.c2 = _dcgan(64, 64, 1, False)
+            setattr(self, name, e)
+        self.shape_Ep = self.shape_Er = torch.Size((64, self.img_h // 4, self.img_w // 4))
+        for name in ("decoder_Dp", "decoder_Dr"):
+            dd = _Params()
+            dd.upc1 = _dcgan(64, 64, 1, True)
+            dd.upc2 = _dcgan(64, 64, 1, True)
+            setattr(self, name, dd)
+        self.decoder_D = _Params()
+        self.decoder_D.upc1 = _dcgan(64, 32, 2, True)
+        self.decoder_D.upc2 = _dcgan(32, 32, 1, True)
+        self.decoder_D.upc3 = nn.ConvTranspose2d(32, c, (3, 3), 2, 1, output_padding=1)
+        hid, kp = self.phycell_channels, self.phycell_kernel_size
+        self.phycell = _Params()
+        cells = []
+        for _ in range(self.phycell_n_layers):
+            cell = _Params()
+            cell.F = nn.Sequential()
+            cell.F.add_module("conv1", nn.Conv2d(64, hid, kp, (1, 1), (kp[0] // 2, kp[1] // 2)))
+            cell.F.add_module("bn1", nn.GroupNorm(_gn_divisor(hid), hid))
+            cell.F.add_module("conv2", nn.Conv2d(hid, 64, (1, 1)))
+            cell.convgate = nn.Conv2d(128, 64, (3, 3), padding=(1, 1))
+            cells.append(cell)
+        self.phycell.cell_list = nn.ModuleList(cells)
+        self.convcell = _Params()
+        cells, cin = [], 64
+        kc = self.convlstm_kernel_size
+        for hd in self.convlstm_hidden_dims[:self.convlstm_n_layers]:
+            cell = _Params()
+            cell.conv = nn.Conv2d(cin + hd, 4 * hd, kc, padding=(kc[0] // 2, kc[1] // 2))
+            cells.append(cell)
+            cin = hd
+        self.convcell.cell_list = nn.ModuleList(cells)
+        self.to(device)
+
+    def _native_desc(self):
+        d = N.ModelDesc()
+        d.kind = self._KIND
+        d.img_c, d.img_h, d.img_w = self.img_c, self.img_h, self.img_w
+        d.phycell_n_layers = self.phycell_n_layers
+        d.phycell_channels = self.phycell_channels
+        if self.phycell_kernel_size[0] != self.phycell_kernel_size[1] or \
+                self.convlstm_kernel_size[0] != self.convlstm_kernel_size[1]:
+            raise AttributeError("square kernels only")
+        d.phycell_kernel_size = self.phycell_kernel_size[0]
+        d.convlstm_n_layers = self.convlstm_n_layers
+        for i, v in enumerate(self.convlstm_hidden_dims[:8]):
+            d.convlstm_hidden_dims[i] = int(v)
+        d.convlstm_kernel_size = self.convlstm_kernel_size[0]
+        return d
+
+    def _native_key(self, key):
+        return key
+
+    def pred_1(self, x, **kwargs):
+        return self(x, pred_frames=1, **kwargs)[0].squeeze(dim=1)              # models/phydnet.py:91-92
+
+    def forward(self, x, pred_frames=1, **kwargs):
+        if kwargs.get("train", False):
+            raise NotImplementedError("the native rollout is inference-only")
+        b, t, c, h, w = x.shape
+        if (c, h, w) != (self.img_c, self.img_h, self.img_w):
+            raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        pred, _ = self._native_forward(x, int(pred_frames), t)
+        return pred, None                                                      # models/phydnet.py:134-137 (eval)
+
+
+class ConvLSTMBranch(PhyDNet):
+    """BASELINE config 2 ("custom ConvLSTM: encoder + stacked ConvLSTM cells"): PhyDNet's residual branch alone --
+    DCGANEncoder -> EncoderSplit -> SingleStepConvLSTM[128,128,64] -> DecoderSplit -> DCGANDecoder -> sigmoid.  It is
+    OUR composition of reference blocks (the reference registers no such model); it keeps PhyDNet's state_dict layout
+    (the PhyCell / Ep / Dp entries are simply unused) so that a PhyDNet checkpoint loads unchanged."""
+    NAME = "ConvLSTM branch of PhyDNet"
+    CAN_HANDLE_ACTIONS = False
+    _KIND = N.VPK_MODEL_CONVLSTM_BRANCH
+
+
 MODEL_CLASSES = {
     "convlstm-shi": EF_ConvLSTM,
+    "predrnn-pp": PredRNN_V2,
+    "phy": PhyDNet,
+    "convlstm-branch": ConvLSTMBranch,
 }
