@@ -126,34 +126,39 @@ class EF_ConvLSTM(VPModel, NativeRollout):
                 setattr(m, nm, nn.Parameter(torch.zeros(1, c, *hw_)))
             return m
 
-        # same construction order as the reference (ef_conv_lstm.py:70-108), so a given torch seed yields the same init
+        # Same module-construction order as the reference, so that a given torch seed yields the same init:
+        # _build_encoder_decoder creates the six ConvLSTMs first (ef_conv_lstm.py:70-108); the stage convs are created
+        # later by _make_layers inside Encoder.__init__ / Forecaster.__init__ (ef_blocks.py:63-65, 96-98).
         self.encoder = _Params()
         self.forecaster = _Params()
         in_c = self.img_c
-        enc = []
+        enc_rnn, enc_io = [], []
         for n in range(L):
             mid, out_c = self.enc_c[2 * n], self.enc_c[2 * n + 1]
-            name = self.enc_conv_names[n]
-            enc.append((_stage([(name, nn.Conv2d(in_c, mid, self.enc_conv_k[n], self.enc_conv_s[n],
-                                                 self.enc_conv_p[n]))]), rnn(mid, out_c, enc_hw[n], self.enc_rnn_k[n])))
+            enc_rnn.append(rnn(mid, out_c, enc_hw[n], self.enc_rnn_k[n]))
+            enc_io.append((in_c, mid))
             in_c = out_c
-        dec = []
+        dec_rnn, dec_io = [], []
         for n in range(L):
             mid, out_c = self.dec_c[2 * n], self.dec_c[2 * n + 1]
-            r = rnn(in_c, mid, dec_hw[n], self.dec_rnn_k[n])
-            layers = [(self.dec_conv_names[n], nn.ConvTranspose2d(mid, out_c, self.dec_conv_k[n], self.dec_conv_s[n],
+            dec_rnn.append(rnn(in_c, mid, dec_hw[n], self.dec_rnn_k[n]))
+            dec_io.append((mid, out_c))
+            in_c = out_c
+        for n in range(L):                                               # Encoder.__init__   ef_blocks.py:63-65
+            ci, co = enc_io[n]
+            st = _stage([(self.enc_conv_names[n], nn.Conv2d(ci, co, self.enc_conv_k[n], self.enc_conv_s[n],
+                                                            self.enc_conv_p[n]))])
+            setattr(self.encoder, f"stage{n + 1}", st)
+            setattr(self.encoder, f"rnn{n + 1}", enc_rnn[n])
+        for n in range(L):                                               # Forecaster.__init__ ef_blocks.py:96-98
+            ci, co = dec_io[n]
+            layers = [(self.dec_conv_names[n], nn.ConvTranspose2d(ci, co, self.dec_conv_k[n], self.dec_conv_s[n],
                                                                   self.dec_conv_p[n]))]
             if n == L - 1:
                 layers.append((self.final_conv_1_name, nn.Identity()))
                 layers.append((self.final_conv_2_name, nn.Conv2d(self.final_conv_1_c, self.img_c, 1, 1, 0)))
-            dec.append((_stage(layers), r))
-            in_c = out_c
-        for n, (st, r) in enumerate(enc, 1):                             # Encoder.__init__   ef_blocks.py:63-65
-            setattr(self.encoder, f"stage{n}", st)
-            setattr(self.encoder, f"rnn{n}", r)
-        for n, (st, r) in enumerate(dec):                                # Forecaster.__init__ ef_blocks.py:96-98
-            setattr(self.forecaster, f"rnn{L - n}", r)
-            setattr(self.forecaster, f"stage{L - n}", st)
+            setattr(self.forecaster, f"rnn{L - n}", dec_rnn[n])
+            setattr(self.forecaster, f"stage{L - n}", _stage(layers))
         self.NON_CONFIG_VARS = list(self.NON_CONFIG_VARS) + ["encoder", "forecaster"]
         self.to(device)
 
