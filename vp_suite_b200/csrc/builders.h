@@ -41,7 +41,8 @@ struct LstmArgs {
   const float* weight;      // host [4C, Cin+C, k, k]
   const float* bias;        // host [4C] or nullptr
   bool order_ifog;          // true: reference rows are (i,f,o,g)
-  const float *wci, *wcf, *wco;   // device fp32 [H,W,C] or nullptr
+  const float *wci, *wcf, *wco;   // device fp32 [H,W,C] (or [C/4,H,W,4] when c4) or nullptr
+  bool c4 = false;          // c and the peepholes use the channel-quad layout [.., C/4, H, W, 4] (needs C % 4 == 0)
 };
 inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   ConvSpec s;
@@ -75,6 +76,7 @@ inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   e.p0 = a.wci;
   e.p1 = a.wcf;
   e.p2 = a.wco;
+  e.state_c4 = (a.c4 && a.C % 4 == 0) ? 1 : 0;
   dense_out(e, a.h_out, a.H, a.W, a.C);
   return s;
 }

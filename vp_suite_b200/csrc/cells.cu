@@ -62,6 +62,7 @@ class CellBase : public Cell {
   }
   void run(const BuiltConv& bc, cudaStream_t s) {
     if (bc.use_tc) launch_conv_tc(bc.tc, s);
+    else if (bc.use_direct) launch_conv_direct(bc.L, dtype, num_sms, s);
     else launch_conv_simt(bc.L, dtype, s);
   }
   void add(const ConvSpec& spec, cudaStream_t s) {

@@ -15,6 +15,7 @@
 //
 // Warp roles: 0 = TMA producer, 1 = MMA issuer, 2..5 = epilogue (warp 2 also owns the TMEM allocation).
 #include <cstdio>
+#include <cstdlib>
 #include <mutex>
 
 #include "common.h"
@@ -26,7 +27,8 @@ namespace vpk {
 
 namespace {
 
-constexpr int kTcThreads = 192;
+constexpr int kTcThreads = 320;          // warps 0,1: TMA / MMA;  warps 2..9: epilogue (two per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
 constexpr uint32_t kAStageBytes = 128 * 128;   // 128 rows x 64 bf16
 constexpr unsigned kMaxSmem = 232448;          // 227 KB
 
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar + 8 * i, 1);
-      ptx::mbar_init(tempty_bar + 8 * i, 128);
+      ptx::mbar_init(tempty_bar + 8 * i, kEpiThreads);
     }
     ptx::fence_barrier_init();
   } else if (warp == 2) {
@@ -98,10 +100,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           const ConvStep st = s_steps[s];
           ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
           const uint32_t fb = full_bar + 8 * stage;
-          ptx::mbar_arrive_expect_tx(fb, kAStageBytes + b_stage_bytes);
-          ptx::tma_load_4d(&P.amap[st.src], fb, ptx::smem_u32(smem_a + stage * kAStageBytes), st.c0, x0 + st.dx,
-                           y0 + st.dy, b0);
-          ptx::tma_load_2d(&P.bmap, fb, ptx::smem_u32(smem_b + stage * b_stage_bytes), st.wk, n0);
+          if (P.debug & 4) {
+            ptx::mbar_arrive(fb);
+          } else {
+            ptx::mbar_arrive_expect_tx(fb, kAStageBytes + b_stage_bytes);
+            ptx::tma_load_4d(&P.amap[st.src], fb, ptx::smem_u32(smem_a + stage * kAStageBytes), st.c0, x0 + st.dx,
+                             y0 + st.dy, b0);
+            ptx::tma_load_2d(&P.bmap, fb, ptx::smem_u32(smem_b + stage * b_stage_bytes), st.wk, n0);
+          }
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
         if (ptx::elect_one()) {
           const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * kAStageBytes));
           const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * b_stage_bytes));
-          for (int k = 0; k < nk; ++k)   // +32 B per K=16 slice inside the 128-B swizzle row
+          for (int k = 0; k < ((P.debug & 2) ? 0 : nk); ++k)   // +32 B per K=16 slice inside the 128-B swizzle row
             ptx::mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
           ptx::mma_commit(empty_bar + 8 * stage);              // frees the smem slot when these MMAs retire
           if (s == nsteps - 1) ptx::mma_commit(tfull_bar + 8 * acc);   // accumulator complete
@@ -137,6 +143,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
   } else {
     // ===================================== epilogue (warps 2..5) ============================================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // the two warps of a quadrant take alternate 8-channel chunks
     const int row = quad * 32 + lane;          // accumulator row = output position inside the tile
     const int rx = row % P.TW;
     const int ry = (row / P.TW) % P.TH;
@@ -149,19 +156,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
       const int x = (mt % P.tiles_x) * P.TW + rx;
       const int y = ((mt / P.tiles_x) % P.tiles_y) * P.TH + ry;
       const int b = (mt / (P.tiles_x * P.tiles_y)) * P.TB + rb;
-      const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B);
+      const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
+      EpiOperands<8> ops0, ops1;
+      // operands of this warp's first chunk are requested before the accumulator is even complete
+      if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + half * 8, ops0);
       ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
-      for (int ch = 0; ch < Cn; ch += 8) {
+      auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
         uint32_t r[8 * G];
         const uint32_t ta = taddr + static_cast<uint32_t>(ch * G);
         if constexpr (G == 4) ptx::tmem_ld32(ta, r);
         else if constexpr (G == 2) ptx::tmem_ld16(ta, r);
         else if constexpr (G == 1) ptx::tmem_ld8(ta, r);
         else { ptx::tmem_ld8(ta, r); ptx::tmem_ld8(ta + 8, r + 8); ptx::tmem_ld8(ta + 16, r + 16); }
+        if (valid && ch + 16 < Cn)   // next chunk's global operands fly while this chunk is computed
+          epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch + 16, nxt);
         ptx::tmem_ld_wait();
         if (valid) {
           float a[G][8];
@@ -169,8 +181,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
           for (int j = 0; j < 8; ++j)
 #pragma unroll
             for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
-          epilogue_apply<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch, a);
+          epilogue_finish<bf16, G, 8, true>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch, a, cur);
         }
+      };
+      for (int ch = half * 8; ch < Cn; ch += 32) {
+        do_chunk(ch, ops0, ops1);
+        if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive(tempty_bar + 8 * acc);
@@ -259,7 +275,14 @@ void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms) {
   P.tiles_b = (L.B + P.TB - 1) / P.TB;
   P.tmem_cols = std::max(32, pow2_at_least(2 * P.tileN));
   VPK_REQUIRE(P.tmem_cols <= 512, "tcgen05 plan: accumulators exceed TMEM");
-  const unsigned stage_bytes = kAStageBytes + static_cast<unsigned>(P.tileN) * 128u;
+  const long long m_tiles_total = static_cast<long long>(P.tiles_x) * P.tiles_y * P.tiles_b;
+  // CTA pairs pay off once every SM pair has at least one 256-position tile; VPK_TC_PAIR=0/1 overrides (testing)
+  P.cta2 = (P.tileN % 16 == 0 && m_tiles_total * P.n_tiles >= num_sms) ? 1 : 0;
+  P.debug = 0;
+  if (const char* env = getenv("VPK_TC_DEBUG")) P.debug = atoi(env);
+  if (const char* env = getenv("VPK_TC_PAIR")) P.cta2 = (atoi(env) != 0 && P.tileN % 16 == 0) ? 1 : 0;
+  const unsigned b_rows = static_cast<unsigned>(P.cta2 ? P.tileN / 2 : P.tileN);
+  const unsigned stage_bytes = kAStageBytes + b_rows * 128u;
   const unsigned fixed = 1024 /*alignment slack*/ + 512 /*barriers, tmem slot*/ +
                          static_cast<unsigned>(L.nsteps) * sizeof(ConvStep) + 64;
   int stages = static_cast<int>((kMaxSmem - fixed) / stage_bytes);
@@ -268,8 +291,13 @@ void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms) {
   P.stages = stages;
   P.smem_bytes = fixed + static_cast<unsigned>(stages) * stage_bytes;
   VPK_REQUIRE(P.smem_bytes <= kMaxSmem, "tcgen05 plan: shared memory budget exceeded");
-  const long long total = static_cast<long long>(P.tiles_x) * P.tiles_y * P.tiles_b * P.n_tiles;
-  P.grid = static_cast<int>(std::min<long long>(total, num_sms));
+  if (P.cta2) {
+    const long long pairs = (m_tiles_total + 1) / 2 * P.n_tiles;
+    P.grid = 2 * static_cast<int>(std::min<long long>(pairs, num_sms / 2));
+  } else {
+    const long long total = m_tiles_total * P.n_tiles;
+    P.grid = static_cast<int>(std::min<long long>(total, num_sms));
+  }
 
   for (int i = 0; i < L.nsrc; ++i) {
     const SrcView& s = L.src[i];
@@ -284,12 +312,16 @@ void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms) {
   {
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.K_pad), static_cast<cuuint64_t>(L.N_pad)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.K_pad) * 2};
-    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(P.tileN)};
+    cuuint32_t box[2] = {64, static_cast<cuuint32_t>(b_rows)};
     encode(&P.bmap, 2, L.wpacked, dims, strides, box, "packed weights");
   }
 }
 
 void launch_conv_tc(const TcPlan& P, cudaStream_t stream) {
+  if (P.cta2) {
+    launch_conv_tc2(P, stream);
+    return;
+  }
   switch (P.L.G) {
     case 1: set_smem_attr<1>(); conv_tc_kernel<1><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
     case 2: set_smem_attr<2>(); conv_tc_kernel<2><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;

@@ -16,14 +16,22 @@ struct alignas(64) TcPlan {
   int tmem_cols;               // power of two >= 2 * tileN
   unsigned smem_bytes;
   int grid;
+  int debug;                   // VPK_TC_DEBUG bit mask (perf experiments only; results are wrong when set):
+                               //   1 = skip epilogue math/IO, 2 = skip MMA issue, 4 = skip TMA loads
+  int cta2;                    // 1: CTA-pair kernel (conv_tc2.cu): weight box holds tileN/2 rows, grid is even
 };
 
 // True when the launch can run on the tensor-core kernel (bf16, channel counts TMA-addressable, ...).
 bool tc_eligible(const ConvLaunch& L, int dtype);
 // Fills tensor maps and tiling for a launch whose device pointers are final.
 void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms);
-void launch_conv_tc(const TcPlan& plan, cudaStream_t stream);
+void launch_conv_tc(const TcPlan& plan, cudaStream_t stream);   // dispatches on plan.cta2
+void launch_conv_tc2(const TcPlan& plan, cudaStream_t stream);
 
 void launch_conv_simt(const ConvLaunch& L, int dtype, cudaStream_t stream);
+
+// Direct kernel for small, memory-bound convs (total K <= 128, N <= 32): conv_direct.cu
+bool direct_eligible(const ConvLaunch& L);
+void launch_conv_direct(const ConvLaunch& L, int dtype, int num_sms, cudaStream_t stream);
 
 }  // namespace vpk

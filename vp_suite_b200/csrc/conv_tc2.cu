@@ -1,0 +1,230 @@
+// 2-CTA (cta_group::2) variant of the tcgen05 / TMEM / TMA implicit-GEMM kernel (see conv_tc.cu for the single-CTA one).
+//
+// A CTA pair (cluster of 2, one TPC) computes a 256-position x tileN tile: each CTA TMA-loads its own 128-position
+// activation box and HALF of the weight tile (tileN/2 rows), the leader CTA issues tcgen05.mma.cta_group::2 (M = 256)
+// which reads both CTAs' shared memory and writes both CTAs' TMEM.  Per CTA and K-step this moves 16 KB + tileN*64 B
+// instead of 16 KB + tileN*128 B: the kernel is bound by operand delivery (L2 -> smem), so halving the weight traffic
+// per FLOP is the point.  Barrier protocol:
+//   full[s]   (leader only, 2 arrivals + tx bytes of both CTAs)   TMA of both CTAs -> leader's MMA warp
+//   empty[s]  (both CTAs, 1 arrival via multicast tcgen05.commit) leader's MMA     -> both producers
+//   tfull[a]  (both CTAs, multicast commit)                       leader's MMA     -> both epilogues
+//   tempty[a] (leader only, 256 arrivals)                         both epilogues   -> leader's MMA
+#include <cstdio>
+#include <mutex>
+
+#include "common.h"
+#include "conv_tc.h"
+#include "epilogue.cuh"
+#include "ptx.cuh"
+
+namespace vpk {
+
+namespace {
+
+constexpr int kTcThreads = 320;          // warps 0,1: TMA / MMA;  warps 2..9: epilogue (two per TMEM lane quadrant)
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kAStageBytes = 128 * 128;
+constexpr unsigned kMaxSmem = 232448;
+
+template <int G>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
+    conv_tc2_kernel(const __grid_constant__ TcPlan P) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  using bf16 = __nv_bfloat16;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int stages = P.stages;
+  const int tileN = P.tileN;
+  const int halfN = tileN / 2;
+  const uint32_t b_stage_bytes = static_cast<uint32_t>(halfN) * 128u;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + stages * kAStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + stages * b_stage_bytes);
+  const uint32_t full_bar = ptx::smem_u32(bars);
+  const uint32_t empty_bar = ptx::smem_u32(bars + stages);
+  const uint32_t tfull_bar = ptx::smem_u32(bars + 2 * stages);
+  const uint32_t tempty_bar = ptx::smem_u32(bars + 2 * stages + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
+  ConvStep* s_steps = reinterpret_cast<ConvStep*>(tmem_slot + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int nsteps = P.L.nsteps;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const int npairs = gridDim.x >> 1;
+
+  for (int i = threadIdx.x; i < nsteps; i += kTcThreads) s_steps[i] = P.L.steps[i];
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int i = 0; i < P.L.nsrc; ++i) ptx::prefetch_tensormap(&P.amap[i]);
+    ptx::prefetch_tensormap(&P.bmap);
+  } else if (warp == 1 && ptx::elect_one()) {
+    for (int i = 0; i < stages; ++i) {
+      ptx::mbar_init(full_bar + 8 * i, 2);
+      ptx::mbar_init(empty_bar + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull_bar + 8 * i, 1);
+      ptx::mbar_init(tempty_bar + 8 * i, 2 * kEpiThreads);
+    }
+    ptx::fence_barrier_init();
+  }
+  ptx::cluster_sync_all();          // both CTAs' barriers exist before anything may signal them
+  if (warp == 2) {
+    ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), static_cast<uint32_t>(P.tmem_cols));
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // tiles: a pair owns M tiles (2p, 2p+1); CTA `rank` loads / finalises tile 2p + rank
+  const int m_tiles = P.tiles_b * P.tiles_y * P.tiles_x;
+  const int m_pairs = (m_tiles + 1) / 2;
+  const int total = m_pairs * P.n_tiles;
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =========================================
+    if (ptx::elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < total; t += npairs) {
+        const int nt = t % P.n_tiles;
+        const int mt = (t / P.n_tiles) * 2 + static_cast<int>(rank);
+        const int x0 = (mt % P.tiles_x) * P.TW;
+        const int y0 = ((mt / P.tiles_x) % P.tiles_y) * P.TH;
+        const int b0 = (mt / (P.tiles_x * P.tiles_y)) * P.TB;      // mt == m_tiles (odd tail) -> b0 >= B: all zero fill
+        const int n0 = nt * tileN + static_cast<int>(rank) * halfN;
+        for (int s = 0; s < nsteps; ++s) {
+          const ConvStep st = s_steps[s];
+          ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+          const uint32_t fb = full_bar + 8 * stage;
+          if (P.debug & 4) {
+            if (leader) ptx::mbar_arrive(fb);
+            else ptx::mbar_arrive_cluster(fb, 0);
+          } else {
+            if (leader) ptx::mbar_arrive_expect_tx(fb, 2u * (kAStageBytes + b_stage_bytes));
+            else ptx::mbar_arrive_cluster(fb, 0);
+            ptx::tma_load_4d_pair(&P.amap[st.src], fb, ptx::smem_u32(smem_a + stage * kAStageBytes), st.c0,
+                                  x0 + st.dx, y0 + st.dy, b0);
+            ptx::tma_load_2d_pair(&P.bmap, fb, ptx::smem_u32(smem_b + stage * b_stage_bytes), st.wk, n0);
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) =====================================
+    if (leader) {
+      const uint32_t idesc = ptx::idesc_bf16_f32(256, tileN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = pair; t < total; t += npairs, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
+        for (int s = 0; s < nsteps; ++s) {
+          const int nk = (s_steps[s].kc + 15) >> 4;
+          ptx::mbar_wait(full_bar + 8 * stage, phase);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * kAStageBytes));
+            const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * b_stage_bytes));
+            for (int k = 0; k < ((P.debug & 2) ? 0 : nk); ++k)
+              ptx::mma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
+            ptx::mma_commit_pair(empty_bar + 8 * stage, 3);
+            if (s == nsteps - 1) ptx::mma_commit_pair(tfull_bar + 8 * acc, 3);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue (warps 2..5, both CTAs) =================================
+    const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
+    const int half = (warp - 2) >> 2;          // the two warps of a quadrant take alternate 8-channel chunks
+    const int row = quad * 32 + lane;          // accumulator row = output position inside the tile
+    const int rx = row % P.TW;
+    const int ry = (row / P.TW) % P.TH;
+    const int rb = row / (P.TW * P.TH);
+    const int Cn = tileN / G;
+    int iter = 0;
+    for (int t = pair; t < total; t += npairs, ++iter) {
+      const int nt = t % P.n_tiles;
+      const int mt = (t / P.n_tiles) * 2 + static_cast<int>(rank);
+      const int x = (mt % P.tiles_x) * P.TW + rx;
+      const int y = ((mt / P.tiles_x) % P.tiles_y) * P.TH + ry;
+      const int b = (mt / (P.tiles_x * P.tiles_y)) * P.TB + rb;
+      const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+      EpiOperands<8> ops0, ops1;
+      // operands of this warp's first chunk are requested before the accumulator is even complete
+      if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + half * 8, ops0);
+      ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
+      auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+        uint32_t r[8 * G];
+        const uint32_t ta = taddr + static_cast<uint32_t>(ch * G);
+        if constexpr (G == 4) ptx::tmem_ld32(ta, r);
+        else if constexpr (G == 2) ptx::tmem_ld16(ta, r);
+        else if constexpr (G == 1) ptx::tmem_ld8(ta, r);
+        else { ptx::tmem_ld8(ta, r); ptx::tmem_ld8(ta + 8, r + 8); ptx::tmem_ld8(ta + 16, r + 16); }
+        if (valid && ch + 16 < Cn)   // next chunk's global operands fly while this chunk is computed
+          epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch + 16, nxt);
+        ptx::tmem_ld_wait();
+        if (valid) {
+          float a[G][8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+#pragma unroll
+            for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
+          epilogue_finish<bf16, G, 8, true>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch, a, cur);
+        }
+      };
+      for (int ch = half * 8; ch < Cn; ch += 32) {
+        do_chunk(ch, ops0, ops1);
+        if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster(tempty_bar + 8 * acc, 0);      // the leader's MMA warp owns the accumulator hand-off
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();          // no CTA leaves (or frees TMEM) while its peer may still signal / read it
+  if (warp == 2) ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(P.tmem_cols));
+#endif
+}
+
+template <int G> void set_smem_attr2() {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(conv_tc2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
+  });
+}
+
+}  // namespace
+
+void launch_conv_tc2(const TcPlan& P, cudaStream_t stream) {
+  switch (P.L.G) {
+    case 1: set_smem_attr2<1>(); conv_tc2_kernel<1><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
+    case 2: set_smem_attr2<2>(); conv_tc2_kernel<2><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
+    case 3: set_smem_attr2<3>(); conv_tc2_kernel<3><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
+    case 4: set_smem_attr2<4>(); conv_tc2_kernel<4><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
+    default: VPK_THROW(1, "conv_tc2: unsupported gate count");
+  }
+  VPK_CUDA(cudaGetLastError());
+}
+
+}  // namespace vpk

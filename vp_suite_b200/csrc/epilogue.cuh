@@ -18,6 +18,17 @@ __device__ __forceinline__ float tanh_f(float x) {
   float e = __expf(2.f * fminf(fmaxf(x, -15.f), 15.f));
   return __fdividef(e - 1.f, e + 1.f);
 }
+// Fast variants for the bf16 tensor-core path: one MUFU op each (tanh.approx.f32, max rel. error 2^-11 -- an order of
+// magnitude below the bf16 operand rounding of that path; measured effect on a 10+10 rollout: ~2e-4).
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+template <bool FAST> __device__ __forceinline__ float sigmoid_t(float x) { return FAST ? sigmoid_fast(x) : sigmoid_f(x); }
+template <bool FAST> __device__ __forceinline__ float tanh_t(float x) { return FAST ? tanh_fast(x) : tanh_f(x); }
+
 __device__ __forceinline__ float apply_act(float v, int act) {
   if (act == ACT_LEAKY) return v > 0.f ? v : 0.2f * v;
   if (act == ACT_SIGMOID) return sigmoid_f(v);
@@ -93,12 +104,101 @@ template <int N> __device__ __forceinline__ void store_act(__nv_bfloat16* p, con
   }
 }
 
+// ---- epilogue-private fp32 state tensors: NHWC or channel-quad layout [B][C/4][H][W][4] -----------------------------
+struct StateAddr {
+  long long off;      // element offset of channel ch0 at this position
+  long long gstride;  // distance between consecutive channel quads (0 = NHWC: channels contiguous)
+};
+__device__ __forceinline__ StateAddr state_addr(const EpiParams& E, int b, int y, int x, int H, int W, int ch0,
+                                                bool with_batch) {
+  StateAddr a;
+  if (E.state_c4) {
+    const long long hw = static_cast<long long>(H) * W;
+    const long long q = (with_batch ? static_cast<long long>(b) * (E.C >> 2) : 0) + (ch0 >> 2);
+    a.off = (q * hw + static_cast<long long>(y) * W + x) * 4 + (ch0 & 3);
+    a.gstride = hw * 4;
+  } else {
+    a.off = ((with_batch ? static_cast<long long>(b) * H : 0) + y) * W * static_cast<long long>(E.C) +
+            static_cast<long long>(x) * E.C + ch0;
+    a.gstride = 0;
+  }
+  return a;
+}
+template <int N> __device__ __forceinline__ void load_state(const float* base, const StateAddr& a, float (&v)[N],
+                                                            int nvalid) {
+  if (a.gstride == 0) {
+    load_f32<N>(base + a.off, v, nvalid);
+  } else if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+      if (4 * i < nvalid) {
+        const float4 t = *reinterpret_cast<const float4*>(base + a.off + i * a.gstride);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+      } else {
+        v[4 * i] = v[4 * i + 1] = v[4 * i + 2] = v[4 * i + 3] = 0.f;
+      }
+    }
+  } else {   // short runs (N = 2) stay inside one quad
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = (i < nvalid) ? base[a.off + i] : 0.f;
+  }
+}
+template <int N> __device__ __forceinline__ void store_state(float* base, const StateAddr& a, const float (&v)[N],
+                                                             int nvalid) {
+  if (a.gstride == 0) {
+    store_f32<N>(base + a.off, v, nvalid);
+  } else if constexpr (N % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i)
+      if (4 * i < nvalid)
+        *reinterpret_cast<float4*>(base + a.off + i * a.gstride) =
+            make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i)
+      if (i < nvalid) base[a.off + i] = v[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
+// The epilogue of one (position, NCH-channel chunk) is split in two so that the tcgen05 kernel can issue the global
+// loads of chunk k+1 before it does the math of chunk k (the loads' L2 latency is then hidden behind the MUFU work):
+//   epilogue_prefetch : loads the fp32 / activation operands the kind needs (state, peepholes, residual, ...)
+//   epilogue_finish   : bias, gate math, state update, stores
 // acc[g][j]: gate g of channel ch0 + j at output position (b, y, x) of an (H, W) grid.
 // ---------------------------------------------------------------------------------------------------------------
+template <int NCH> struct EpiOperands {
+  float a[NCH], b[NCH], c[NCH], d[NCH];
+};
+
 template <typename T, int G, int NCH>
-__device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y, int x, int H, int W, int ch0,
-                                               float (&acc)[G][NCH]) {
+__device__ __forceinline__ void epilogue_prefetch(const EpiParams& E, int b, int y, int x, int H, int W, int ch0,
+                                                  EpiOperands<NCH>& o) {
+  const int C = E.C;
+  const int nvalid = min(NCH, C - ch0);
+  if (nvalid <= 0) return;
+  const size_t pix = (static_cast<size_t>(b) * H + y) * W + x;
+  if constexpr (G == 1) {
+    if (E.kind == EPI_PHY_GATE) {
+      load_act<NCH>(static_cast<const T*>(E.q0) + pix * C + ch0, o.a, nvalid);
+      load_f32<NCH>(E.res + pix * C + ch0, o.b, nvalid);
+    } else if (E.res != nullptr) {
+      load_f32<NCH>(E.res + pix * C + ch0, o.a, nvalid);
+    }
+  } else {
+    load_state<NCH>(E.s0, state_addr(E, b, y, x, H, W, ch0, true), o.a, nvalid);       // c / m / o_part
+    if (G == 4 && E.kind == EPI_LSTM && E.p0 != nullptr) {
+      const StateAddr pa = state_addr(E, b, y, x, H, W, ch0, false);
+      load_state<NCH>(E.p0, pa, o.b, nvalid);
+      load_state<NCH>(E.p1, pa, o.c, nvalid);
+      load_state<NCH>(E.p2, pa, o.d, nvalid);
+    }
+  }
+}
+
+template <typename T, int G, int NCH, bool FAST = false>
+__device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y, int x, int H, int W, int ch0,
+                                                float (&acc)[G][NCH], EpiOperands<NCH>& o) {
   const int C = E.C;
   const int nvalid = min(NCH, C - ch0);
   if (nvalid <= 0) return;
@@ -120,10 +220,8 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y,
 #pragma unroll
       for (int j = 0; j < NCH; ++j) v[j] = apply_act(acc[0][j], E.act);
       if (E.res != nullptr) {
-        float r[NCH];
-        load_f32<NCH>(E.res + pix * C + ch0, r, nvalid);
 #pragma unroll
-        for (int j = 0; j < NCH; ++j) v[j] += r[j];
+        for (int j = 0; j < NCH; ++j) v[j] += o.a[j];
       }
       const long long off = b * E.oB + y * E.oY + x * E.oX;
       if (E.oC == 1) {
@@ -133,89 +231,85 @@ __device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y,
 #pragma unroll
         for (int j = 0; j < NCH; ++j)
           if (j < nvalid) {
-            const long long o = off + static_cast<long long>(ch0 + j) * E.oC;
-            if (E.out_f32) static_cast<float*>(E.out)[o] = v[j];
-            else static_cast<T*>(E.out)[o] = from_f32<T>(v[j]);
+            const long long oo = off + static_cast<long long>(ch0 + j) * E.oC;
+            if (E.out_f32) static_cast<float*>(E.out)[oo] = v[j];
+            else static_cast<T*>(E.out)[oo] = from_f32<T>(v[j]);
           }
       }
     } else {   // EPI_PHY_GATE: h' = h~ + sigmoid(acc) * (x - h~)      (model_blocks/phydnet.py:58-61)
-      float xf[NCH], ht[NCH], v[NCH];
-      load_act<NCH>(static_cast<const T*>(E.q0) + pix * C + ch0, xf, nvalid);
-      load_f32<NCH>(E.res + pix * C + ch0, ht, nvalid);
+      float v[NCH];
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) v[j] = ht[j] + sigmoid_f(acc[0][j]) * (xf[j] - ht[j]);
+      for (int j = 0; j < NCH; ++j) v[j] = o.b[j] + sigmoid_t<FAST>(acc[0][j]) * (o.a[j] - o.b[j]);
       store_f32<NCH>(E.s0 + pix * C + ch0, v, nvalid);                       // fp32 master of the hidden state
       store_act<NCH>(static_cast<T*>(E.out) + pix * C + ch0, v, nvalid);     // conv-operand copy
     }
   } else if constexpr (G == 4) {
-    float c[NCH];
-    float* cp = E.s0 + pix * C + ch0;
-    load_f32<NCH>(cp, c, nvalid);
+    const StateAddr sa = state_addr(E, b, y, x, H, W, ch0, true);
     if (E.kind == EPI_LSTM) {
       // conv_lstm_hzzone.py:62-68 (with peepholes) and conv_lstm_ndrplz.py:34-41 (without); rows packed as i,f,g,o
       float h[NCH];
       if (E.p0 != nullptr) {
-        const size_t pp = (static_cast<size_t>(y) * W + x) * C + ch0;
-        float wi[NCH], wf[NCH], wo[NCH];
-        load_f32<NCH>(E.p0 + pp, wi, nvalid);
-        load_f32<NCH>(E.p1 + pp, wf, nvalid);
-        load_f32<NCH>(E.p2 + pp, wo, nvalid);
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-          const float ig = sigmoid_f(acc[0][j] + wi[j] * c[j]);
-          const float fg = sigmoid_f(acc[1][j] + wf[j] * c[j]);
-          const float cn = fg * c[j] + ig * tanh_f(acc[2][j]);
-          const float og = sigmoid_f(acc[3][j] + wo[j] * cn);
-          c[j] = cn;
-          h[j] = og * tanh_f(cn);
+          const float ig = sigmoid_t<FAST>(acc[0][j] + o.b[j] * o.a[j]);
+          const float fg = sigmoid_t<FAST>(acc[1][j] + o.c[j] * o.a[j]);
+          const float cn = fg * o.a[j] + ig * tanh_t<FAST>(acc[2][j]);
+          const float og = sigmoid_t<FAST>(acc[3][j] + o.d[j] * cn);
+          o.a[j] = cn;
+          h[j] = og * tanh_t<FAST>(cn);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < NCH; ++j) {
-          const float cn = sigmoid_f(acc[1][j]) * c[j] + sigmoid_f(acc[0][j]) * tanh_f(acc[2][j]);
-          c[j] = cn;
-          h[j] = sigmoid_f(acc[3][j]) * tanh_f(cn);
+          const float cn = sigmoid_t<FAST>(acc[1][j]) * o.a[j] + sigmoid_t<FAST>(acc[0][j]) * tanh_t<FAST>(acc[2][j]);
+          o.a[j] = cn;
+          h[j] = sigmoid_t<FAST>(acc[3][j]) * tanh_t<FAST>(cn);
         }
       }
-      store_f32<NCH>(cp, c, nvalid);
+      store_state<NCH>(E.s0, sa, o.a, nvalid);
       store_act<NCH>(static_cast<T*>(E.out) + b * E.oB + y * E.oY + x * E.oX + ch0, h, nvalid);
       if (E.h32 != nullptr) store_f32<NCH>(E.h32 + pix * C + ch0, h, nvalid);
     } else {   // EPI_ST_C: predrnn.py:65-70; acc = (i, f, g, o_x + o_h)
       float dc[NCH], op[NCH];
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
-        const float ig = sigmoid_f(acc[0][j]);
-        const float fg = sigmoid_f(acc[1][j] + E.forget_bias);
-        dc[j] = ig * tanh_f(acc[2][j]);
-        c[j] = fg * c[j] + dc[j];
+        const float ig = sigmoid_t<FAST>(acc[0][j]);
+        const float fg = sigmoid_t<FAST>(acc[1][j] + E.forget_bias);
+        dc[j] = ig * tanh_t<FAST>(acc[2][j]);
+        o.a[j] = fg * o.a[j] + dc[j];
         op[j] = acc[3][j];
       }
-      store_f32<NCH>(cp, c, nvalid);
-      store_f32<NCH>(E.s1 + pix * C + ch0, op, nvalid);
-      store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, c, nvalid);
+      store_state<NCH>(E.s0, sa, o.a, nvalid);
+      store_state<NCH>(E.s1, sa, op, nvalid);
+      store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, o.a, nvalid);
       store_act<NCH>(static_cast<T*>(E.t1) + pix * C + ch0, dc, nvalid);
     }
   } else if constexpr (G == 3) {   // EPI_ST_M: predrnn.py:72-77; acc = (i', f', g')
-    float m[NCH], dm[NCH];
-    float* mp = E.s0 + pix * C + ch0;
-    load_f32<NCH>(mp, m, nvalid);
+    float dm[NCH];
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-      const float ig = sigmoid_f(acc[0][j]);
-      const float fg = sigmoid_f(acc[1][j] + E.forget_bias);
-      dm[j] = ig * tanh_f(acc[2][j]);
-      m[j] = fg * m[j] + dm[j];
+      const float ig = sigmoid_t<FAST>(acc[0][j]);
+      const float fg = sigmoid_t<FAST>(acc[1][j] + E.forget_bias);
+      dm[j] = ig * tanh_t<FAST>(acc[2][j]);
+      o.a[j] = fg * o.a[j] + dm[j];
     }
-    store_f32<NCH>(mp, m, nvalid);
-    store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, m, nvalid);
+    store_state<NCH>(E.s0, state_addr(E, b, y, x, H, W, ch0, true), o.a, nvalid);
+    store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, o.a, nvalid);
     store_act<NCH>(static_cast<T*>(E.t1) + pix * C + ch0, dm, nvalid);
   } else if constexpr (G == 2) {   // EPI_ST_O: predrnn.py:79-80; acc = (conv_o(mem), conv_last(mem))
-    float op[NCH], h[NCH];
-    load_f32<NCH>(E.s0 + pix * C + ch0, op, nvalid);
+    float h[NCH];
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) h[j] = sigmoid_f(op[j] + acc[0][j]) * tanh_f(acc[1][j]);
+    for (int j = 0; j < NCH; ++j) h[j] = sigmoid_t<FAST>(o.a[j] + acc[0][j]) * tanh_t<FAST>(acc[1][j]);
     store_act<NCH>(static_cast<T*>(E.out) + b * E.oB + y * E.oY + x * E.oX + ch0, h, nvalid);
   }
+}
+
+template <typename T, int G, int NCH>
+__device__ __forceinline__ void epilogue_apply(const EpiParams& E, int b, int y, int x, int H, int W, int ch0,
+                                               float (&acc)[G][NCH]) {
+  EpiOperands<NCH> o;
+  epilogue_prefetch<T, G, NCH>(E, b, y, x, H, W, ch0, o);
+  epilogue_finish<T, G, NCH>(E, b, y, x, H, W, ch0, acc, o);
 }
 
 }  // namespace vpk

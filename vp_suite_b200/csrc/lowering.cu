@@ -249,7 +249,8 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       L.wpacked = q.w;
       L.K_pad = q.K_pad;
       L.epi.bias = q.bias;
-      bc.use_tc = (backend == 0) && tc_eligible(L, dtype);
+      bc.use_direct = direct_eligible(L);
+      bc.use_tc = !bc.use_direct && (backend == 0) && tc_eligible(L, dtype);
       if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);
     }
     out.push_back(std::move(bc));

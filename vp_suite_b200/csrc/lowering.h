@@ -100,6 +100,7 @@ struct BuiltConv {
   std::string name;
   ConvLaunch L;
   bool use_tc = false;
+  bool use_direct = false;
   TcPlan tc;
 };
 

@@ -119,6 +119,10 @@ void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStre
     if (bc.use_tc) {
       auto plan = std::make_shared<TcPlan>(bc.tc);
       op.fn = [plan](cudaStream_t s, const RunCtx&) { launch_conv_tc(*plan, s); };
+    } else if (bc.use_direct) {
+      ConvLaunch L = bc.L;
+      const int ns = num_sms;
+      op.fn = [L, dt, ns](cudaStream_t s, const RunCtx&) { launch_conv_direct(L, dt, ns, s); };
     } else {
       ConvLaunch L = bc.L;
       op.fn = [L, dt](cudaStream_t s, const RunCtx&) { launch_conv_simt(L, dt, s); };

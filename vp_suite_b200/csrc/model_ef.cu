@@ -86,13 +86,20 @@ class EfConvLstm : public Model {
     return std::max(1, std::min(mb, 256));
   }
 
-  std::vector<float> peephole_hwc(const std::string& key, int C, int H, int W) const {
-    // reference layout [1, C, H, W] -> [H, W, C]
+  std::vector<float> peephole_packed(const std::string& key, int C, int H, int W) const {
+    // reference layout [1, C, H, W] -> channel-quad layout [C/4, H, W, 4] (or [H, W, C] when C % 4 != 0), the layout
+    // of the cell state it multiplies (epilogue.cuh: state_addr)
     const float* p = hp(key);
     std::vector<float> out(static_cast<size_t>(C) * H * W);
+    const bool c4 = C % 4 == 0;
     for (int c = 0; c < C; ++c)
       for (int y = 0; y < H; ++y)
-        for (int x = 0; x < W; ++x) out[(static_cast<size_t>(y) * W + x) * C + c] = p[(static_cast<size_t>(c) * H + y) * W + x];
+        for (int x = 0; x < W; ++x) {
+          const size_t src = (static_cast<size_t>(c) * H + y) * W + x;
+          const size_t dst = c4 ? ((static_cast<size_t>(c / 4) * H + y) * W + x) * 4 + (c & 3)
+                                : (static_cast<size_t>(y) * W + x) * C + c;
+          out[dst] = p[src];
+        }
     return out;
   }
 
@@ -130,7 +137,7 @@ class EfConvLstm : public Model {
           if (!has(rn + "Wci") && !has(rn + "Wcf") && !has(rn + "Wco")) continue;
           const char* names[3] = {"Wci", "Wcf", "Wco"};
           for (int k = 0; k < 3; ++k)
-            peep[side][n][k] = dev_f32(rn + names[k], peephole_hwc(rn + names[k], C, eh[n], ew[n]), stream);
+            peep[side][n][k] = dev_f32(rn + names[k], peephole_packed(rn + names[k], C, eh[n], ew[n]), stream);
         }
     }
 
@@ -166,6 +173,7 @@ class EfConvLstm : public Model {
         LstmArgs la{rn, B, eh[n], ew[n], mid, outc, d.enc_rnn_k[n], xin[n], hbuf[n][par[n]], hbuf[n][par[n] ^ 1],
                     cbuf[n], hp(rn + "_conv.weight"), hp(rn + "_conv.bias"), false,
                     peep[0][n][0], peep[0][n][1], peep[0][n][2]};
+        la.c4 = true;
         add_conv(prog, lstm_spec(la, act), measure, stream);
         par[n] ^= 1;
         in = hbuf[n][par[n]];
@@ -186,6 +194,7 @@ class EfConvLstm : public Model {
         LstmArgs la{rn + (in ? "" : "h_only."), B, dh[n], dw[n], dec_in_c[n], mid, d.dec_rnn_k[n], in,
                     hbuf[e][par[e]], hbuf[e][par[e] ^ 1], cbuf[e], hp(rn + "_conv.weight"), hp(rn + "_conv.bias"),
                     false, peep[1][idx - 1][0], peep[1][idx - 1][1], peep[1][idx - 1][2]};
+        la.c4 = true;
         add_conv(prog, lstm_spec(la, act), measure, stream);
         par[e] ^= 1;
         int oh, ow;

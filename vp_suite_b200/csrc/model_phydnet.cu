@@ -241,6 +241,7 @@ class PhyDNetModel : public Model {
           const std::string p = "convcell.cell_list." + std::to_string(j) + ".conv.";
           LstmArgs la{p, B, h4, w4, cin, hd, kl, xin, hb[2 * j + lpar[j]], hb[2 * j + (lpar[j] ^ 1)], cb[j],
                       hp(p + "weight"), hp(p + "bias"), true, nullptr, nullptr, nullptr};
+          la.c4 = true;
           ConvSpec s = lstm_spec(la, ca);
           if (j == n_lstm - 1) s.phases[0].epi.h32 = h_top32;
           add_conv(prog, s, measure, stream, cdt);

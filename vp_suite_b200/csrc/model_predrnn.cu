@@ -124,6 +124,7 @@ class PredRnnV2 : public Model {
                      opart, memb[2 * i + (t & 1)], dcdm, dcdm + px * C * esz,
                      hp(pre + "conv_x.0.weight"), hp(pre + "conv_h.0.weight"), hp(pre + "conv_m.0.weight"),
                      hp(pre + "conv_o.0.weight"), hp(pre + "conv_last.weight")};
+        a.c4 = true;
         for (const ConvSpec& sp : stlstm_specs(a, act)) add_conv(prog, sp, measure, stream);
         par[i] ^= 1;
         // decoupling-loss term: adapter (1x1, no bias) over [delta_c ; delta_m], then the per-(b, ch) cosine

@@ -30,6 +30,7 @@ struct StLstmArgs {
   void* dc;               // [B,H,W,C] delta_c
   void* dm;               // [B,H,W,C] delta_m
   const float *w_x, *w_h, *w_m, *w_o, *w_last;   // host, reference layouts
+  bool c4 = false;        // c, m, o_part use the channel-quad layout (rollouts); the NCHW-boundary cell keeps NHWC
 };
 
 inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& act) {
@@ -61,6 +62,7 @@ inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& ac
                a.W, act.esize, &oh, &ow);
     EpiParams& e = s.phases[0].epi;
     e.kind = EPI_ST_C;
+    e.state_c4 = (a.c4 && C % 4 == 0) ? 1 : 0;
     e.forget_bias = 1.0f;   // predrnn.py:23
     e.s0 = a.c;
     e.s1 = a.o_part;
@@ -82,6 +84,7 @@ inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& ac
                act.esize, &oh, &ow);
     EpiParams& e = s.phases[0].epi;
     e.kind = EPI_ST_M;
+    e.state_c4 = (a.c4 && C % 4 == 0) ? 1 : 0;
     e.forget_bias = 1.0f;
     e.s0 = a.m;
     e.t0 = static_cast<char*>(a.mem) + static_cast<size_t>(C) * act.esize;
@@ -103,6 +106,7 @@ inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& ac
     lower_conv(s, 1, 1, 0, {ConvInput{mv, 1, 0}}, a.H, a.W, act.esize, &oh, &ow);
     EpiParams& e = s.phases[0].epi;
     e.kind = EPI_ST_O;
+    e.state_c4 = (a.c4 && C % 4 == 0) ? 1 : 0;
     e.s0 = a.o_part;
     dense_out(e, a.h_out, a.H, a.W, C);
     out.push_back(std::move(s));
