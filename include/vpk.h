@@ -117,6 +117,10 @@ int vpk_model_last_launch_count(vpk_model* m, int64_t* launches);
 int vpk_model_set_timing(vpk_model* m, int32_t enable);
 int vpk_model_last_gemm_ms(vpk_model* m, float* ms, int64_t* gemm_launches, double* gemm_flops);
 
+/* Per-layer device times of the last forward when timing was enabled with vpk_model_set_timing(m, 2): writes lines
+ * "<layer name> <launches> <ms> <gflop>" (sorted by time) into buf (NUL-terminated, truncated to n). */
+int vpk_model_profile(vpk_model* m, char* buf, size_t n);
+
 void vpk_model_destroy(vpk_model* m);
 
 /* ---- single-step cells: the VPModelBlock boundary ------------------------------------------------------------ */

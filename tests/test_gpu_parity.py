@@ -231,18 +231,22 @@ def test_stateful_blocks_reset_on_first_timestep():
 
 @pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "phy_1x64"])
 @pytest.mark.parametrize("pair", ["0", "1"])
-def test_cta_pair_and_single_cta_kernels_agree(manifest, name, pair, monkeypatch):
-    """The cta_group::2 (CTA-pair, M=256) and the single-CTA tcgen05 kernels are forced in turn (the library picks
-    by problem size otherwise); both must reproduce the CUDA-core result on the same bf16 operands."""
+@pytest.mark.parametrize("halo", ["0", "1"])
+def test_every_tcgen05_kernel_variant_agrees_with_cuda_cores(manifest, name, pair, halo, monkeypatch):
+    """The four tensor-core kernel variants -- per-tap or halo-reuse activation loads (VPK_TC_HALO) x single CTA or
+    cta_group::2 CTA pair (VPK_TC_PAIR) -- are forced in turn (the library picks by problem size otherwise); each must
+    reproduce the CUDA-core result on the same bf16 operands."""
     meta = manifest["models"][name]
     x = _input(meta).cuda()
     monkeypatch.setenv("VPK_TC_PAIR", pair)
+    monkeypatch.setenv("VPK_TC_HALO", halo)
     m, _ = _build(meta["key"], meta, precision="bf16", backend="auto")
     with torch.no_grad():
         got = m(x, pred_frames=meta["pred"])[0].cpu().numpy()
     monkeypatch.delenv("VPK_TC_PAIR")
+    monkeypatch.delenv("VPK_TC_HALO")
     ref_m, _ = _build(meta["key"], meta, precision="bf16", backend="simt")
     with torch.no_grad():
         ref = ref_m(x, pred_frames=meta["pred"])[0].cpu().numpy()
     errs = _frame_errs(got, ref)
-    assert max(errs) <= 2e-3, f"{name} pair={pair}: {errs}"
+    assert max(errs) <= 2e-3, f"{name} pair={pair} halo={halo}: {errs}"

@@ -225,7 +225,18 @@ class NativeRollout:
         return n.value
 
     def set_timing(self, enable):
-        N.check(N.lib().vpk_model_set_timing(self._native_handle(), int(bool(enable))))
+        """0 off, 1 CUDA events around the gate GEMMs, 2 around every kernel (see ``layer_profile``)."""
+        N.check(N.lib().vpk_model_set_timing(self._native_handle(), int(enable)))
+
+    def layer_profile(self):
+        """[(layer, launches, ms, gflop)] of the last forward run with ``set_timing(2)``, sorted by time."""
+        buf = C.create_string_buffer(1 << 16)
+        N.check(N.lib().vpk_model_profile(self._native_handle(), buf, len(buf)))
+        rows = []
+        for line in buf.value.decode().splitlines():
+            name, n, ms, gf = line.rsplit(" ", 3)
+            rows.append((name, int(n), float(ms), float(gf)))
+        return rows
 
     def last_gemm_stats(self):
         ms, n, fl = C.c_float(), C.c_int64(), C.c_double()

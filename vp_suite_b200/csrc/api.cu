@@ -1,4 +1,5 @@
 // extern "C" surface of libvpk.so (include/vpk.h).  No C++ exception crosses this file.
+#include <algorithm>
 #include <cstring>
 #include <string>
 
@@ -134,7 +135,7 @@ int vpk_model_last_launch_count(vpk_model* m, int64_t* launches) {
 int vpk_model_set_timing(vpk_model* m, int32_t enable) {
   return guarded([&] {
     VPK_REQUIRE(m, "null argument");
-    m->impl->timing = enable != 0;
+    m->impl->timing = enable;
   });
 }
 
@@ -142,6 +143,16 @@ int vpk_model_last_gemm_ms(vpk_model* m, float* ms, int64_t* gemm_launches, doub
   return guarded([&] {
     VPK_REQUIRE(m && ms && gemm_launches && gemm_flops, "null argument");
     m->impl->gemm_stats(ms, gemm_launches, gemm_flops);
+  });
+}
+
+int vpk_model_profile(vpk_model* m, char* buf, size_t n) {
+  return guarded([&] {
+    VPK_REQUIRE(m && buf && n > 0, "null argument");
+    const std::string t = m->impl->profile_text();
+    const size_t k = std::min(n - 1, t.size());
+    std::memcpy(buf, t.data(), k);
+    buf[k] = 0;
   });
 }
 

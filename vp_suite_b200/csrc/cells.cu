@@ -61,7 +61,8 @@ class CellBase : public Cell {
     launch_frames_to_nhwc(src, dst, out_dtype, B, 1, C, H, W, num_sms, s);
   }
   void run(const BuiltConv& bc, cudaStream_t s) {
-    if (bc.use_tc) launch_conv_tc(bc.tc, s);
+    if (bc.use_halo) launch_conv_halo(bc.halo, s);
+    else if (bc.use_tc) launch_conv_tc(bc.tc, s);
     else if (bc.use_direct) launch_conv_direct(bc.L, dtype, num_sms, s);
     else launch_conv_simt(bc.L, dtype, s);
   }

@@ -95,6 +95,7 @@ struct EpiParams {
   // 1: the fp32 tensors only the epilogue touches (s0, s1, p0..p2) use the channel-quad layout [B][C/4][H][W][4]
   // instead of NHWC, so that the 32 positions of a warp read/write contiguous 16-byte pieces (coalesced); needs C % 4 == 0
   int state_c4;
+  int debug;              // perf experiments only (VPK_TC_DEBUG): 8 = skip activation-type stores, 16 = skip bias loads
   // optional per-(b, group) statistics for a following GroupNorm: sums[b][g][2] (sum, sum of squares)
   float* gn_sums;
   int gn_group_size;      // channels per group (0 = disabled)

@@ -1,0 +1,502 @@
+// Halo-reuse tcgen05 / TMEM / TMA implicit-GEMM kernel (sm_100a): the main tensor-core kernel of libvpk.
+//
+// Difference to conv_tc.cu / conv_tc2.cu (one activation load per tap): here the activation tile of one (source,
+// 64-channel block) is loaded ONCE, with its k x k halo, as a (64 ch, 8+2P, 16+2P) TMA box, and every tap reads it
+// through a SHIFTED UMMA shared-memory descriptor: start address = slot + ((P+dy)*(8+2P) + (P+dx)) * 128 B, stride
+// between 8-row groups (SBO) = (8+2P) * 128 B.  This relies on the hardware applying the 128-byte swizzle from the
+// absolute shared-memory address bits (so that a view starting at any 128-byte row of what TMA wrote stays
+// consistent); tools/umma_probe.cu verifies exactly that on the B200 (start rows 1..26, SBO 1280/1536/2048, exact).
+// Activation traffic L2 -> smem drops from k*k * 16 KB to one ~23 KB (3x3) / 30 KB (5x5) / 39 KB (7x7) box per block;
+// only the weight tiles still stream per tap.
+//
+// Output tile: 8 (x) x 16 (y) positions of one image = 128 accumulator rows, row r = ty*8 + tx, so each 8-row core
+// group is one image row segment.  PAIR = true: cta_group::2, M = 256 across a cluster of two CTAs (each CTA its own
+// spatial tile and half of the weight rows), as in conv_tc2.cu.
+//
+// Warps: 0 activation-TMA producer, 1 weight-TMA producer, 2 MMA issuer, 3 TMEM allocator, 4..11 epilogue
+// (two warps per TMEM lane quadrant, operands prefetched one 8-channel chunk ahead).
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+
+#include "common.h"
+#include "conv_tc.h"
+#include "epilogue_tc.cuh"
+#include "ptx.cuh"
+
+namespace vpk {
+
+namespace {
+
+constexpr int kHaloThreads = 384;
+constexpr int kEpiThreads = 256;
+constexpr int kTW = 8, kTH = 16;
+constexpr unsigned kMaxSmem = 232448;
+
+__device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;     // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;     // SWIZZLE_128B; base_offset stays 0: the swizzle follows absolute addresses
+  return d;
+}
+
+__host__ __device__ constexpr int gates_of(int kind) {
+  return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
+}
+
+template <int KIND, bool PAIR>
+__global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloPlan P) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+  using bf16 = __nv_bfloat16;
+  constexpr int G = gates_of(KIND);
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+
+  const int SA = P.SA, SB = P.SB;
+  const int tileN = P.tileN;
+  const int rowsB = PAIR ? tileN / 2 : tileN;
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + SA * P.a_slot_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + SB * P.b_slot_bytes);
+  const uint32_t afull = ptx::smem_u32(bars);
+  const uint32_t aempty = ptx::smem_u32(bars + SA);
+  const uint32_t bfull = ptx::smem_u32(bars + 2 * SA);
+  const uint32_t bempty = ptx::smem_u32(bars + 2 * SA + SB);
+  const uint32_t tfull = ptx::smem_u32(bars + 2 * SA + 2 * SB);
+  const uint32_t tempty = ptx::smem_u32(bars + 2 * SA + 2 * SB + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
+  HaloBlock* s_blocks = reinterpret_cast<HaloBlock*>(tmem_slot + 4);
+  HaloTap* s_taps = reinterpret_cast<HaloTap*>(s_blocks + P.nblocks);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_taps + P.ntaps) + 15) & ~uintptr_t(15));
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
+  const int nunits = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int nblocks = P.nblocks;
+
+  for (int i = threadIdx.x; i < nblocks; i += kHaloThreads) s_blocks[i] = P.blocks[i];
+  for (int i = threadIdx.x; i < P.ntaps; i += kHaloThreads) s_taps[i] = P.taps[i];
+  if (P.L.epi.bias != nullptr)
+    for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias[i];
+
+  if (warp == 0 && ptx::elect_one()) {
+    for (int i = 0; i < P.L.nsrc; ++i) ptx::prefetch_tensormap(&P.amap[i]);
+    ptx::prefetch_tensormap(&P.bmap);
+  } else if (warp == 1 && ptx::elect_one()) {
+    const uint32_t prod = PAIR ? 2u : 1u;
+    for (int i = 0; i < SA; ++i) {
+      ptx::mbar_init(afull + 8 * i, prod);
+      ptx::mbar_init(aempty + 8 * i, 1);
+    }
+    for (int i = 0; i < SB; ++i) {
+      ptx::mbar_init(bfull + 8 * i, prod);
+      ptx::mbar_init(bempty + 8 * i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(tfull + 8 * i, 1);
+      ptx::mbar_init(tempty + 8 * i, prod * kEpiThreads);
+    }
+    ptx::fence_barrier_init();
+  }
+  if constexpr (PAIR) ptx::cluster_sync_all();
+  if (warp == 3) {
+    if constexpr (PAIR) {
+      ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), static_cast<uint32_t>(P.tmem_cols));
+      ptx::tmem_relinquish_pair();
+    } else {
+      ptx::tmem_alloc(ptx::smem_u32(tmem_slot), static_cast<uint32_t>(P.tmem_cols));
+      ptx::tmem_relinquish();
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = P.L.B * P.tiles_y * P.tiles_x;
+  const int units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int total = units * P.n_tiles;
+  const int rad = P.P;
+  const int HWp = kTW + 2 * rad;
+  const uint32_t a_box_bytes = static_cast<uint32_t>((kTH + 2 * rad) * HWp * 128);
+  const uint32_t b_box_bytes = static_cast<uint32_t>(rowsB) * 128u;
+  const uint32_t ncta = PAIR ? 2u : 1u;
+
+  if (warp == 0) {
+    // ===================================== activation (halo tile) producer ==================================
+    if (ptx::elect_one()) {
+      int sa = 0;
+      uint32_t ph = 0;
+      for (int t = unit0; t < total; t += nunits) {
+        const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+        const int x0 = (mt % P.tiles_x) * kTW;
+        const int y0 = ((mt / P.tiles_x) % P.tiles_y) * kTH;
+        const int b0 = mt / (P.tiles_x * P.tiles_y);            // odd tail of a pair: b0 == B -> zero fill
+        for (int bi = 0; bi < nblocks; ++bi) {
+          const HaloBlock blk = s_blocks[bi];
+          ptx::mbar_wait(aempty + 8 * sa, ph ^ 1u);
+          const uint32_t fb = afull + 8 * sa;
+          const uint32_t dst = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
+          if (P.debug & 4) {
+            if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, 0);
+          } else if constexpr (PAIR) {
+            if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * a_box_bytes); else ptx::mbar_arrive_cluster(fb, 0);
+            ptx::tma_load_4d_pair(&P.amap[blk.src], fb, dst, blk.c0, x0 - rad, y0 - rad, b0);
+          } else {
+            ptx::mbar_arrive_expect_tx(fb, a_box_bytes);
+            ptx::tma_load_4d(&P.amap[blk.src], fb, dst, blk.c0, x0 - rad, y0 - rad, b0);
+          }
+          if (++sa == SA) { sa = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== weight producer (groups of taps per slot) ========================
+    if (ptx::elect_one()) {
+      int sb = 0;
+      uint32_t ph = 0;
+      for (int t = unit0; t < total; t += nunits) {
+        const int n0 = (t % P.n_tiles) * tileN + static_cast<int>(rank) * (PAIR ? rowsB : 0);
+        for (int bi = 0; bi < nblocks; ++bi) {
+          const HaloBlock blk = s_blocks[bi];
+          for (int q0 = 0; q0 < blk.ntaps; q0 += P.bgroup) {
+            const int gn = min(P.bgroup, blk.ntaps - q0);
+            ptx::mbar_wait(bempty + 8 * sb, ph ^ 1u);
+            const uint32_t fb = bfull + 8 * sb;
+            const uint32_t dst = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
+            if (P.debug & 4) {
+              if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, 0);
+            } else {
+              if constexpr (PAIR) {
+                if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * b_box_bytes * gn); else ptx::mbar_arrive_cluster(fb, 0);
+              } else {
+                ptx::mbar_arrive_expect_tx(fb, b_box_bytes * gn);
+              }
+              for (int q = 0; q < gn; ++q) {
+                const int wk = s_taps[blk.first_tap + q0 + q].wk;
+                if constexpr (PAIR) ptx::tma_load_2d_pair(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0);
+                else ptx::tma_load_2d(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0);
+              }
+            }
+            if (++sb == SB) { sb = 0; ph ^= 1u; }
+          }
+        }
+      }
+    }
+  } else if (warp == 2) {
+    // ===================================== MMA issuer (leader CTA of a pair) ================================
+    if (leader) {
+      const uint32_t idesc = ptx::idesc_bf16_f32(PAIR ? 256 : 128, tileN);
+      const uint32_t sbo = static_cast<uint32_t>(HWp * 128);
+      int sa = 0, sb = 0;
+      uint32_t pha = 0, phb = 0;
+      int iter = 0;
+      for (int t = unit0; t < total; t += nunits, ++iter) {
+        const int acc = iter & 1;
+        const uint32_t acc_phase = (iter >> 1) & 1u;
+        ptx::mbar_wait(tempty + 8 * acc, acc_phase ^ 1u);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
+        bool first = true;
+        for (int bi = 0; bi < nblocks; ++bi) {
+          const HaloBlock blk = s_blocks[bi];
+          ptx::mbar_wait(afull + 8 * sa, pha);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
+          for (int q0 = 0; q0 < blk.ntaps; q0 += P.bgroup) {
+            const int gn = min(P.bgroup, blk.ntaps - q0);
+            ptx::mbar_wait(bfull + 8 * sb, phb);
+            ptx::tc_fence_after();
+            if (ptx::elect_one()) {
+              const uint32_t b_base = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
+              for (int q = 0; q < gn; ++q) {
+                const HaloTap tap = s_taps[blk.first_tap + q0 + q];
+                const uint32_t a_addr = a_base + static_cast<uint32_t>(((rad + tap.dy) * HWp + (rad + tap.dx)) * 128);
+                const uint64_t adesc = smem_desc_sw128_sbo(a_addr, sbo);
+                const uint64_t bdesc = ptx::smem_desc_sw128(b_base + q * P.b_tap_stride);
+                const int nk = (P.debug & 2) ? 0 : tap.nk;
+                for (int k = 0; k < nk; ++k) {
+                  const uint32_t accum = (first && q == 0 && k == 0) ? 0u : 1u;
+                  if constexpr (PAIR) ptx::mma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                  else ptx::mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                }
+              }
+              const bool last_grp = q0 + gn >= blk.ntaps;
+              if constexpr (PAIR) {
+                ptx::mma_commit_pair(bempty + 8 * sb, 3);
+                if (last_grp) ptx::mma_commit_pair(aempty + 8 * sa, 3);
+                if (last_grp && bi == nblocks - 1) ptx::mma_commit_pair(tfull + 8 * acc, 3);
+              } else {
+                ptx::mma_commit(bempty + 8 * sb);
+                if (last_grp) ptx::mma_commit(aempty + 8 * sa);
+                if (last_grp && bi == nblocks - 1) ptx::mma_commit(tfull + 8 * acc);
+              }
+            }
+            __syncwarp();
+            first = false;
+            if (++sb == SB) { sb = 0; phb ^= 1u; }
+          }
+          if (++sa == SA) { sa = 0; pha ^= 1u; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===================================== epilogue (warps 4..11) ===========================================
+    const int quad = warp & 3;
+    const int half = (warp - 4) >> 2;
+    const int row = quad * 32 + lane;
+    const int rx = row % kTW;
+    const int ry = row / kTW;
+    const int Cn = tileN / G;
+    int iter = 0;
+    for (int t = unit0; t < total; t += nunits, ++iter) {
+      const int nt = t % P.n_tiles;
+      const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+      const int x = (mt % P.tiles_x) * kTW + rx;
+      const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
+      const int b = mt / (P.tiles_x * P.tiles_y);
+      const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
+      const int acc = iter & 1;
+      const uint32_t acc_phase = (iter >> 1) & 1u;
+      EpiOperands<8> ops0, ops1;
+      const int C = P.L.epi.C;
+      const int ch_base = nt * Cn;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
+      auto tmem_chunk = [&](int ch, uint32_t (&r)[8 * G]) {
+        const uint32_t ta = taddr + static_cast<uint32_t>(ch * G);
+        if constexpr (G == 4) ptx::tmem_ld32(ta, r);
+        else if constexpr (G == 2) ptx::tmem_ld16(ta, r);
+        else if constexpr (G == 1) ptx::tmem_ld8(ta, r);
+        else { ptx::tmem_ld8(ta, r); ptx::tmem_ld8(ta + 8, r + 8); ptx::tmem_ld8(ta + 16, r + 16); }
+      };
+      if (P.fast_epi) {
+        // ---- lean path: kind known at compile time, offsets hoisted, bias from shared memory ----
+        EpiTile et;
+        if (valid) et = epi_tile(P.L.epi, b, y, x, P.L.H, P.L.W);
+        const float* bias = P.L.epi.bias ? s_bias : nullptr;
+        if (valid && ch_base + half * 8 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + half * 8, ops0);
+        ptx::mbar_wait(tfull + 8 * acc, acc_phase);
+        ptx::tc_fence_after();
+        auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+          uint32_t r[8 * G];
+          tmem_chunk(ch, r);
+          if (valid && ch + 16 < Cn && ch_base + ch + 16 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + ch + 16, nxt);
+          ptx::tmem_ld_wait();
+          if (valid && ch_base + ch < C) {
+            float a[G][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
+            epi_tc_finish<KIND, G>(P.L.epi, et, ch_base + ch, bias, a, cur);
+          }
+        };
+        for (int ch = half * 8; ch < Cn; ch += 32) {
+          do_chunk(ch, ops0, ops1);
+          if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+        }
+      } else {
+        // ---- generic path (ragged channel counts, channel-strided outputs) ----
+        if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + half * 8, ops0);
+        ptx::mbar_wait(tfull + 8 * acc, acc_phase);
+        ptx::tc_fence_after();
+        auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+          uint32_t r[8 * G];
+          tmem_chunk(ch, r);
+          if (valid && ch + 16 < Cn)
+            epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + ch + 16, nxt);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            float a[G][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
+            epilogue_finish<bf16, G, 8, true>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + ch, a, cur);
+          }
+        };
+        for (int ch = half * 8; ch < Cn; ch += 32) {
+          do_chunk(ch, ops0, ops1);
+          if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+        }
+      }
+      ptx::tc_fence_before();
+      if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+      else ptx::mbar_arrive(tempty + 8 * acc);
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (PAIR) ptx::cluster_sync_all();
+  else __syncthreads();
+  if (warp == 3) {
+    if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(P.tmem_cols));
+    else ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(P.tmem_cols));
+  }
+#endif
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  if (!fn) VPK_THROW(2, "cuTensorMapEncodeTiled is not available from the CUDA driver");
+  return fn;
+}
+void encode(CUtensorMap* map, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
+            const cuuint32_t* box, const char* what) {
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                           const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[200];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled(%s) failed with CUresult %d", what, static_cast<int>(r));
+    VPK_THROW(2, buf);
+  }
+}
+int pow2_at_least(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+template <int KIND, bool PAIR> void launch_one(const HaloPlan& P, cudaStream_t stream) {
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(conv_halo_kernel<KIND, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(kMaxSmem));
+  });
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(P.grid));
+  cfg.blockDim = dim3(kHaloThreads);
+  cfg.dynamicSmemBytes = P.smem_bytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VPK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KIND, PAIR>, P));
+}
+
+}  // namespace
+
+bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps) {
+  if (!tc_eligible(L, dtype)) return false;
+  if (const char* env = getenv("VPK_TC_HALO"))
+    if (atoi(env) == 0) return false;
+  return radius >= 0 && radius <= 3 && nblocks >= 1 && nblocks <= 64 && ntaps <= kMaxSteps;
+}
+
+void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
+                    int radius, HaloPlan* plan, int num_sms) {
+  HaloPlan& P = *plan;
+  P.L = L;
+  P.blocks = d_blocks;
+  P.taps = d_taps;
+  P.nblocks = nblocks;
+  P.ntaps = ntaps;
+  P.P = radius;
+  P.tileN = L.Cn * L.G;
+  P.n_tiles = L.N_pad / P.tileN;
+  P.tiles_x = (L.W + kTW - 1) / kTW;
+  P.tiles_y = (L.H + kTH - 1) / kTH;
+  const long long m_tiles = static_cast<long long>(L.B) * P.tiles_x * P.tiles_y;
+  P.pair = (P.tileN % 16 == 0 && m_tiles * P.n_tiles >= num_sms) ? 1 : 0;
+  if (const char* env = getenv("VPK_TC_PAIR")) P.pair = (atoi(env) != 0 && P.tileN % 16 == 0) ? 1 : 0;
+  P.debug = 0;
+  if (const char* env = getenv("VPK_TC_DEBUG")) P.debug = atoi(env);
+  P.L.epi.debug = P.debug;
+  P.fast_epi = (epi_tc_fast_ok(L.epi) && gates_of(L.epi.kind) == L.G) ? 1 : 0;
+  if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
+  P.tmem_cols = std::max(32, pow2_at_least(2 * P.tileN));
+  VPK_REQUIRE(P.tmem_cols <= 512, "halo plan: accumulators exceed TMEM");
+  const int HWp = kTW + 2 * radius, HHp = kTH + 2 * radius;
+  const unsigned a_box = static_cast<unsigned>(HWp * HHp * 128);
+  P.a_slot_bytes = (a_box + 1023u) / 1024u * 1024u;
+  const unsigned b_rows = static_cast<unsigned>(P.pair ? P.tileN / 2 : P.tileN);
+  P.b_tap_stride = (b_rows * 128u + 1023u) / 1024u * 1024u;
+  // several taps share one weight slot (one barrier round trip) when the tiles are small: per-tap barrier latency,
+  // not bytes, bounds the small-N layers
+  P.bgroup = std::max(1, std::min<int>(9, static_cast<int>(12288u / P.b_tap_stride)));
+  if (const char* env = getenv("VPK_HALO_BGROUP")) P.bgroup = std::max(1, atoi(env));
+  P.b_slot_bytes = P.bgroup * P.b_tap_stride;
+  const unsigned fixed = 1024 + 1024 + static_cast<unsigned>(nblocks) * sizeof(HaloBlock) +
+                         static_cast<unsigned>(ntaps) * sizeof(HaloTap) + static_cast<unsigned>(L.N_pad) * 4 + 128;
+  // Ring depths by bytes: ~60 % of shared memory for weight tiles (4..24 slots), the rest for activation halo tiles
+  // (2..8).  What matters is the number of TMA operations in flight against their ~2 us latency: small-N layers have
+  // small weight tiles and get deep rings, the N = 256 gate GEMMs get 7-8 x 16 KB.
+  const unsigned avail = kMaxSmem - fixed;
+  int sb = static_cast<int>(avail * 6 / 10 / P.b_slot_bytes);
+  sb = std::max(4, std::min(24, sb));
+  while (sb > 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes > avail) --sb;
+  VPK_REQUIRE(sb >= 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail, "halo plan: shared memory budget exceeded");
+  P.SB = sb;
+  P.SA = std::max(2, std::min<int>(8, static_cast<int>((avail - P.SB * P.b_slot_bytes) / P.a_slot_bytes)));
+  if (const char* env = getenv("VPK_HALO_SA")) {
+    const int sa = atoi(env);
+    if (sa >= 2 && fixed + sa * P.a_slot_bytes + 2 * P.b_slot_bytes <= kMaxSmem) {
+      P.SA = sa;
+      P.SB = std::min<int>(24, static_cast<int>((avail - P.SA * P.a_slot_bytes) / P.b_slot_bytes));
+    }
+  }
+  P.smem_bytes = fixed + P.SA * P.a_slot_bytes + P.SB * P.b_slot_bytes;
+  if (P.pair) {
+    const long long units = (m_tiles + 1) / 2 * P.n_tiles;
+    P.grid = 2 * static_cast<int>(std::min<long long>(units, num_sms / 2));
+  } else {
+    P.grid = static_cast<int>(std::min<long long>(m_tiles * P.n_tiles, num_sms));
+  }
+  for (int i = 0; i < L.nsrc; ++i) {
+    const SrcView& s = L.src[i];
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(s.C), static_cast<cuuint64_t>(s.W), static_cast<cuuint64_t>(s.H),
+                          static_cast<cuuint64_t>(L.B)};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(s.sX) * 2, static_cast<cuuint64_t>(s.sY) * 2,
+                             static_cast<cuuint64_t>(s.sB) * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(HWp), static_cast<cuuint32_t>(HHp), 1};
+    encode(&P.amap[i], 4, s.base, dims, strides, box, "activation halo view");
+  }
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(L.K_pad), static_cast<cuuint64_t>(L.N_pad)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.K_pad) * 2};
+  cuuint32_t box[2] = {64, b_rows};
+  encode(&P.bmap, 2, L.wpacked, dims, strides, box, "packed weights");
+}
+
+void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
+#define VPK_HALO(KIND)                                         \
+  if (P.pair) launch_one<KIND, true>(P, stream);               \
+  else launch_one<KIND, false>(P, stream);                     \
+  break
+  switch (P.L.epi.kind) {
+    case EPI_BIAS_ACT: VPK_HALO(EPI_BIAS_ACT);
+    case EPI_LSTM: VPK_HALO(EPI_LSTM);
+    case EPI_ST_C: VPK_HALO(EPI_ST_C);
+    case EPI_ST_M: VPK_HALO(EPI_ST_M);
+    case EPI_ST_O: VPK_HALO(EPI_ST_O);
+    case EPI_PHY_GATE: VPK_HALO(EPI_PHY_GATE);
+    default: VPK_THROW(1, "conv_halo: unsupported epilogue kind");
+  }
+#undef VPK_HALO
+}
+
+}  // namespace vpk

@@ -21,6 +21,42 @@ struct alignas(64) TcPlan {
   int cta2;                    // 1: CTA-pair kernel (conv_tc2.cu): weight box holds tileN/2 rows, grid is even
 };
 
+// ---- halo-reuse kernel (conv_halo.cu) ----------------------------------------------------------------------------
+struct HaloBlock {             // one (source, 64-channel block): its activation halo tile is loaded once
+  short src, c0, kc, ntaps;
+  int first_tap;
+};
+struct HaloTap {               // one tap of a block: shifted view of the halo tile x one weight tile
+  signed char dy, dx;
+  short nk;                    // K=16 MMA slices (ceil(kc / 16))
+  int wk;                      // column offset in the packed weights
+};
+struct alignas(64) HaloPlan {
+  CUtensorMap amap[kMaxSrc];   // 4-D (C, W, H, B) views, box (64, 8+2P, 16+2P, 1), 128B swizzle
+  CUtensorMap bmap;            // 2-D packed weights, box (64, tileN or tileN/2)
+  ConvLaunch L;
+  const HaloBlock* blocks;     // device
+  const HaloTap* taps;         // device
+  int nblocks, ntaps;
+  int P;                       // halo radius = max |dy|, |dx|
+  int tiles_x, tiles_y;        // 8 x 16 output tiles per image
+  int n_tiles, tileN;
+  int SA, SB;                  // activation / weight ring depths
+  unsigned a_slot_bytes, b_slot_bytes;
+  unsigned b_tap_stride;       // bytes between the weight tiles of the taps sharing one slot
+  int bgroup;                  // taps per weight slot
+  int tmem_cols;
+  unsigned smem_bytes;
+  int grid;
+  int pair;                    // cta_group::2
+  int fast_epi;                // lean compile-time-specialised epilogue (epilogue_tc.cuh) usable for this launch
+  int debug;
+};
+bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps);
+void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
+                    int radius, HaloPlan* plan, int num_sms);
+void launch_conv_halo(const HaloPlan& plan, cudaStream_t stream);
+
 // True when the launch can run on the tensor-core kernel (bf16, channel counts TMA-addressable, ...).
 bool tc_eligible(const ConvLaunch& L, int dtype);
 // Fills tensor maps and tiling for a launch whose device pointers are final.

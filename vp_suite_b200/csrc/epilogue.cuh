@@ -204,7 +204,7 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y
   if (nvalid <= 0) return;
   const size_t pix = (static_cast<size_t>(b) * H + y) * W + x;
 
-  if (E.bias != nullptr) {   // packed order: (ch0 + j) * G + g
+  if (E.bias != nullptr && !(E.debug & 16)) {   // packed order: (ch0 + j) * G + g
     const float* bp = E.bias + static_cast<size_t>(ch0) * G;
 #pragma unroll
     for (int j = 0; j < NCH; ++j)
@@ -224,7 +224,9 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y
         for (int j = 0; j < NCH; ++j) v[j] += o.a[j];
       }
       const long long off = b * E.oB + y * E.oY + x * E.oX;
-      if (E.oC == 1) {
+      if (E.debug & 8) {
+        if (v[0] == 123.456f) static_cast<float*>(E.out)[0] = v[1];   // keep the math alive
+      } else if (E.oC == 1) {
         if (E.out_f32) store_f32<NCH>(static_cast<float*>(E.out) + off + ch0, v, nvalid);
         else store_act<NCH>(static_cast<T*>(E.out) + off + ch0, v, nvalid);
       } else {

@@ -1,0 +1,215 @@
+// Lean epilogue for the tcgen05 kernels: same arithmetic as epilogue.cuh (which stays the CUDA-core kernels' epilogue
+// and the cross-check), specialised at COMPILE time on the epilogue kind, with everything that does not depend on the
+// channel chunk hoisted to once per (thread, tile): position decode, 64-bit offsets, layout selection.  The packed
+// bias lives in shared memory (every lane reads the same float4: one broadcast wavefront).  One call = 8 channels.
+#pragma once
+#include "epilogue.cuh"
+
+namespace vpk {
+
+struct EpiTile {            // per thread, per output tile
+  long long out_off;        // b*oB + y*oY + x*oX of the primary output
+  long long pix_c;          // dense pixel index * C  (NHWC tensors: t1, res, q0, h32, PHY state)
+  long long pix_t0;         // dense pixel index * t0_pix (ST-LSTM mem buffer)
+  long long st_off;         // fp32 state tensors: offset of channel 0 at this position ...
+  long long st_g;           // ... and the stride between channel quads (0: NHWC, channels contiguous)
+  long long pp_off;         // peepholes (no batch dimension), same layout rule
+};
+
+__device__ __forceinline__ EpiTile epi_tile(const EpiParams& E, int b, int y, int x, int H, int W) {
+  EpiTile t;
+  const long long pix = (static_cast<long long>(b) * H + y) * W + x;
+  t.out_off = b * E.oB + y * E.oY + x * E.oX;
+  t.pix_c = pix * E.C;
+  t.pix_t0 = pix * E.t0_pix;
+  if (E.state_c4) {
+    const long long hw = static_cast<long long>(H) * W;
+    const long long p = static_cast<long long>(y) * W + x;
+    t.st_off = (static_cast<long long>(b) * (E.C >> 2) * hw + p) * 4;
+    t.pp_off = p * 4;
+    t.st_g = hw * 4;
+  } else {
+    t.st_off = pix * E.C;
+    t.pp_off = (static_cast<long long>(y) * W + x) * E.C;
+    t.st_g = 0;
+  }
+  return t;
+}
+
+// 8 consecutive channels of an fp32 state tensor (full chunks only: the tcgen05 path requires C % 8 == 0 for these)
+__device__ __forceinline__ void ld_state8(const float* base, long long off, long long g, int ch, float (&v)[8]) {
+  const float* p = base + off + (g ? (ch >> 2) * g : ch);
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + (g ? g : 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void st_state8(float* base, long long off, long long g, int ch, const float (&v)[8]) {
+  float* p = base + off + (g ? (ch >> 2) * g : ch);
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + (g ? g : 4)) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void st_bf16x8(__nv_bfloat16* p, const float (&v)[8]) {
+  uint4 t;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) h[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+  *reinterpret_cast<uint4*>(p) = t;
+}
+__device__ __forceinline__ void ld_bf16x8(const __nv_bfloat16* p, float (&v)[8]) {
+  const uint4 t = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 f = __bfloat1622float2(h[k]);
+    v[2 * k] = f.x; v[2 * k + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void st_f32x8(float* p, const float (&v)[8]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void ld_f32x8(const float* p, float (&v)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+
+// Whether the fast path may be used for this launch: whole 8-channel chunks, 16-byte aligned rows.
+__host__ __device__ inline bool epi_tc_fast_ok(const EpiParams& E) {
+  if (E.C % 8 != 0) return false;
+  if (E.kind == EPI_BIAS_ACT) {
+    if (E.oC != 1) return false;                             // channel-strided (NCHW) outputs use the generic path
+    const long long m = E.out_f32 ? 4 : 8;
+    if ((E.oB % m) || (E.oY % m) || (E.oX % m)) return false;
+  }
+  return true;
+}
+
+// ---- prefetch: the global operands of channels [ch, ch+8) ---------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ void epi_tc_prefetch(const EpiParams& E, const EpiTile& t, int ch, EpiOperands<8>& o) {
+  using bf16 = __nv_bfloat16;
+  if constexpr (KIND == EPI_LSTM) {
+    ld_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+    if (E.p0 != nullptr) {
+      ld_state8(E.p0, t.pp_off, t.st_g, ch, o.b);
+      ld_state8(E.p1, t.pp_off, t.st_g, ch, o.c);
+      ld_state8(E.p2, t.pp_off, t.st_g, ch, o.d);
+    }
+  } else if constexpr (KIND == EPI_ST_C || KIND == EPI_ST_M || KIND == EPI_ST_O) {
+    ld_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+  } else if constexpr (KIND == EPI_PHY_GATE) {
+    ld_bf16x8(static_cast<const bf16*>(E.q0) + t.pix_c + ch, o.a);
+    ld_f32x8(E.res + t.pix_c + ch, o.b);
+  } else {   // EPI_BIAS_ACT
+    if (E.res != nullptr) ld_f32x8(E.res + t.pix_c + ch, o.a);
+  }
+}
+
+// ---- finish: acc[g][j] = gate g of channel ch + j; s_bias = packed bias of this N tile in shared memory ----------
+template <int KIND, int G>
+__device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile& t, int ch, const float* s_bias,
+                                              float (&acc)[G][8], EpiOperands<8>& o) {
+  using bf16 = __nv_bfloat16;
+  if (s_bias != nullptr) {   // packed order (ch + j) * G + g: 8*G consecutive floats
+    const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * G);
+#pragma unroll
+    for (int q = 0; q < 2 * G; ++q) {
+      const float4 bv = bp[q];
+      const float e[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const int idx = 4 * q + r;      // = j * G + g
+        acc[idx % G][idx / G] += e[r];
+      }
+    }
+  }
+  if constexpr (KIND == EPI_BIAS_ACT) {
+    float v[8];
+    switch (E.act) {
+      case ACT_LEAKY:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = acc[0][j] > 0.f ? acc[0][j] : 0.2f * acc[0][j];
+        break;
+      case ACT_SIGMOID:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sigmoid_fast(acc[0][j]);
+        break;
+      case ACT_RELU:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = fmaxf(acc[0][j], 0.f);
+        break;
+      default:
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = acc[0][j];
+    }
+    if (E.res != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] += o.a[j];
+    }
+    if (E.out_f32) st_f32x8(static_cast<float*>(E.out) + t.out_off + ch, v);
+    else st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, v);
+  } else if constexpr (KIND == EPI_PHY_GATE) {   // h' = h~ + sigmoid(acc) * (x - h~)
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = o.b[j] + sigmoid_fast(acc[0][j]) * (o.a[j] - o.b[j]);
+    st_f32x8(E.s0 + t.pix_c + ch, v);
+    st_bf16x8(static_cast<bf16*>(E.out) + t.pix_c + ch, v);
+  } else if constexpr (KIND == EPI_LSTM) {
+    float h[8];
+    if (E.p0 != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float ig = sigmoid_fast(fmaf(o.b[j], o.a[j], acc[0][j]));
+        const float fg = sigmoid_fast(fmaf(o.c[j], o.a[j], acc[1][j]));
+        const float cn = fmaf(fg, o.a[j], ig * tanh_fast(acc[2][j]));
+        const float og = sigmoid_fast(fmaf(o.d[j], cn, acc[3][j]));
+        o.a[j] = cn;
+        h[j] = og * tanh_fast(cn);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float cn = fmaf(sigmoid_fast(acc[1][j]), o.a[j], sigmoid_fast(acc[0][j]) * tanh_fast(acc[2][j]));
+        o.a[j] = cn;
+        h[j] = sigmoid_fast(acc[3][j]) * tanh_fast(cn);
+      }
+    }
+    st_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+    st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
+    if (E.h32 != nullptr) st_f32x8(E.h32 + t.pix_c + ch, h);
+  } else if constexpr (KIND == EPI_ST_C) {   // acc = (i, f, g, o_x + o_h)
+    float dc[8], op[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ig = sigmoid_fast(acc[0][j]);
+      const float fg = sigmoid_fast(acc[1][j] + E.forget_bias);
+      dc[j] = ig * tanh_fast(acc[2][j]);
+      o.a[j] = fmaf(fg, o.a[j], dc[j]);
+      op[j] = acc[3][j];
+    }
+    st_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+    st_state8(E.s1, t.st_off, t.st_g, ch, op);
+    st_bf16x8(static_cast<bf16*>(E.t0) + t.pix_t0 + ch, o.a);
+    st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dc);
+  } else if constexpr (KIND == EPI_ST_M) {   // acc = (i', f', g')
+    float dm[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float ig = sigmoid_fast(acc[0][j]);
+      const float fg = sigmoid_fast(acc[1][j] + E.forget_bias);
+      dm[j] = ig * tanh_fast(acc[2][j]);
+      o.a[j] = fmaf(fg, o.a[j], dm[j]);
+    }
+    st_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+    st_bf16x8(static_cast<bf16*>(E.t0) + t.pix_t0 + ch, o.a);
+    st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dm);
+  } else {   // EPI_ST_O: acc = (conv_o(mem), conv_last(mem))
+    float h[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) h[j] = sigmoid_fast(o.a[j] + acc[0][j]) * tanh_fast(acc[1][j]);
+    st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
+  }
+}
+
+}  // namespace vpk

@@ -1,6 +1,7 @@
 #include "lowering.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 namespace vpk {
@@ -10,10 +11,12 @@ namespace {
 inline int floordiv(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 
-void add_steps_for(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int wref, int ky, int kx, int wc0,
-                   int wc_count) {
+// One step per (tap, 64-channel block).  Steps are emitted BLOCK-MAJOR (all taps of one (source, channel block) are
+// consecutive) so that the halo kernel can load that block's activation tile once and reuse it for every tap.
+void add_step(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int c0, int wref, int ky, int kx, int wc0,
+              int wc_count) {
   if (wc_count < 0) wc_count = C;
-  for (int c0 = 0; c0 < C; c0 += 64) {
+  {
     HostStep h{};
     h.s.src = static_cast<short>(src);
     h.s.dy = static_cast<signed char>(dy);
@@ -48,11 +51,12 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
       src_idx.push_back(static_cast<int>(spec.srcs.size()));
       spec.srcs.push_back(in.view);
     }
-    for (int ky = 0; ky < k; ++ky)
-      for (int kx = 0; kx < k; ++kx)
-        for (size_t i = 0; i < inputs.size(); ++i)
-          add_steps_for(ph.steps, src_idx[i], ky - pad, kx - pad, inputs[i].view.C, inputs[i].wref, ky, kx,
-                        inputs[i].wc0, inputs[i].wc_count);
+    for (size_t i = 0; i < inputs.size(); ++i)
+      for (int c0 = 0; c0 < inputs[i].view.C; c0 += 64)
+        for (int ky = 0; ky < k; ++ky)
+          for (int kx = 0; kx < k; ++kx)
+            add_step(ph.steps, src_idx[i], ky - pad, kx - pad, inputs[i].view.C, c0, inputs[i].wref, ky, kx,
+                     inputs[i].wc0, inputs[i].wc_count);
   } else {
     VPK_REQUIRE(inputs.size() == 1, "stride-2 conv takes a single input");
     VPK_REQUIRE(in_h % 2 == 0 && in_w % 2 == 0, "stride-2 conv needs even input size");
@@ -68,17 +72,20 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
         v.base = static_cast<const char*>(in.view.base) + (py * in.view.sY + px * in.view.sX) * esize;
         spec.srcs.push_back(v);
       }
-    for (int ky = 0; ky < k; ++ky) {
-      const int ty = ky - pad;
-      const int py = ((ty % 2) + 2) % 2;
-      const int dy = floordiv(ty - py, 2);
-      for (int kx = 0; kx < k; ++kx) {
-        const int tx = kx - pad;
-        const int px = ((tx % 2) + 2) % 2;
-        const int dx = floordiv(tx - px, 2);
-        add_steps_for(ph.steps, base_idx + py * 2 + px, dy, dx, in.view.C, in.wref, ky, kx, in.wc0, in.wc_count);
-      }
-    }
+    for (int par = 0; par < 4; ++par)          // block-major: parity view, channel block, then its taps
+      for (int c0 = 0; c0 < in.view.C; c0 += 64)
+        for (int ky = 0; ky < k; ++ky) {
+          const int ty = ky - pad;
+          const int py = ((ty % 2) + 2) % 2;
+          const int dy = floordiv(ty - py, 2);
+          for (int kx = 0; kx < k; ++kx) {
+            const int tx = kx - pad;
+            const int px = ((tx % 2) + 2) % 2;
+            const int dx = floordiv(tx - px, 2);
+            if (py * 2 + px != par) continue;
+            add_step(ph.steps, base_idx + par, dy, dx, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count);
+          }
+        }
   }
   VPK_REQUIRE(spec.srcs.size() <= static_cast<size_t>(kMaxSrc), "too many conv sources");
   *oh = OH;
@@ -99,15 +106,16 @@ void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pa
       ph.H = (OH - ry + stride - 1) / stride;
       ph.W = (OW - rx + stride - 1) / stride;
       // y = stride*iy - pad + ky  with  y = stride*q + ry   =>   iy = q + (ry + pad - ky) / stride
-      for (int ky = 0; ky < k; ++ky) {
-        if (((ry + pad - ky) % stride + stride) % stride != 0) continue;
-        const int dy = floordiv(ry + pad - ky, stride);
-        for (int kx = 0; kx < k; ++kx) {
-          if (((rx + pad - kx) % stride + stride) % stride != 0) continue;
-          const int dx = floordiv(rx + pad - kx, stride);
-          add_steps_for(ph.steps, src, dy, dx, input.view.C, input.wref, ky, kx, input.wc0, input.wc_count);
+      for (int c0 = 0; c0 < input.view.C; c0 += 64)
+        for (int ky = 0; ky < k; ++ky) {
+          if (((ry + pad - ky) % stride + stride) % stride != 0) continue;
+          const int dy = floordiv(ry + pad - ky, stride);
+          for (int kx = 0; kx < k; ++kx) {
+            if (((rx + pad - kx) % stride + stride) % stride != 0) continue;
+            const int dx = floordiv(rx + pad - kx, stride);
+            add_step(ph.steps, src, dy, dx, input.view.C, c0, input.wref, ky, kx, input.wc0, input.wc_count);
+          }
         }
-      }
       ph.epi = epi_for_phase(ry, rx, stride, OH, OW);
       spec.phases.push_back(ph);
     }
@@ -215,6 +223,34 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         std::vector<ConvStep> cs(steps.size());
         for (size_t i = 0; i < steps.size(); ++i) cs[i] = steps[i].s;
         q.steps = static_cast<ConvStep*>(store.upload(cs.data(), cs.size() * sizeof(ConvStep), stream));
+        // halo-kernel tables: consecutive steps of one (source, channel block) form a block
+        std::vector<HaloBlock> hb;
+        std::vector<HaloTap> ht;
+        int radius = 0;
+        for (const ConvStep& c : cs) {
+          if (hb.empty() || hb.back().src != c.src || hb.back().c0 != c.c0) {
+            HaloBlock b{};
+            b.src = c.src;
+            b.c0 = c.c0;
+            b.kc = c.kc;
+            b.ntaps = 0;
+            b.first_tap = static_cast<int>(ht.size());
+            hb.push_back(b);
+          }
+          HaloTap t{};
+          t.dy = c.dy;
+          t.dx = c.dx;
+          t.nk = static_cast<short>((c.kc + 15) / 16);
+          t.wk = c.wk;
+          ht.push_back(t);
+          hb.back().ntaps++;
+          radius = std::max(radius, std::max(std::abs(static_cast<int>(c.dy)), std::abs(static_cast<int>(c.dx))));
+        }
+        q.blocks = static_cast<HaloBlock*>(store.upload(hb.data(), hb.size() * sizeof(HaloBlock), stream));
+        q.taps = static_cast<HaloTap*>(store.upload(ht.data(), ht.size() * sizeof(HaloTap), stream));
+        q.nblocks = static_cast<int>(hb.size());
+        q.ntaps = static_cast<int>(ht.size());
+        q.radius = radius;
       }
       it = cache.emplace(spec.name, std::move(pw)).first;
     }
@@ -250,7 +286,9 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       L.K_pad = q.K_pad;
       L.epi.bias = q.bias;
       bc.use_direct = direct_eligible(L);
-      bc.use_tc = !bc.use_direct && (backend == 0) && tc_eligible(L, dtype);
+      bc.use_halo = !bc.use_direct && (backend == 0) && halo_eligible(L, dtype, q.radius, q.nblocks, q.ntaps);
+      bc.use_tc = !bc.use_direct && !bc.use_halo && (backend == 0) && tc_eligible(L, dtype);
+      if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);
       if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);
     }
     out.push_back(std::move(bc));

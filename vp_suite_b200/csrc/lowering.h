@@ -101,7 +101,9 @@ struct BuiltConv {
   ConvLaunch L;
   bool use_tc = false;
   bool use_direct = false;
+  bool use_halo = false;
   TcPlan tc;
+  HaloPlan halo;
 };
 
 // Packed-weight cache key -> device pointers, so the per-timestep launches of one layer share one packed copy.
@@ -110,6 +112,10 @@ struct PackedWeights {
   float* bias = nullptr;
   ConvStep* steps = nullptr;
   int K_pad = 0, N_pad = 0, Cn = 0;
+  // halo-kernel view of the same steps (block-major): device tables
+  HaloBlock* blocks = nullptr;
+  HaloTap* taps = nullptr;
+  int nblocks = 0, ntaps = 0, radius = 0;
 };
 
 // Packs the weights of every phase of `spec` for activation type `dtype` and returns one BuiltConv per phase (device

@@ -1,6 +1,7 @@
 #include "model.h"
 
 #include <algorithm>
+#include <cstdio>
 #include <cstring>
 
 namespace vpk {
@@ -116,7 +117,10 @@ void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStre
     op.name = bc.name;
     op.flops = bc.L.flops;
     op.gate = bc.L.is_gate_gemm != 0;
-    if (bc.use_tc) {
+    if (bc.use_halo) {
+      auto plan = std::make_shared<HaloPlan>(bc.halo);
+      op.fn = [plan](cudaStream_t s, const RunCtx&) { launch_conv_halo(*plan, s); };
+    } else if (bc.use_tc) {
       auto plan = std::make_shared<TcPlan>(bc.tc);
       op.fn = [plan](cudaStream_t s, const RunCtx&) { launch_conv_tc(*plan, s); };
     } else if (bc.use_direct) {
@@ -170,7 +174,7 @@ Program* Model::get_program(int B, int t_in, int pred, void* ws, size_t ws_bytes
   // weights uploaded during build() live in pageable staging: make sure they have landed before staging is reused
   VPK_CUDA(cudaStreamSynchronize(stream));
   store.staging.clear();
-  if (desc.use_cuda_graph && !timing) {
+  if (desc.use_cuda_graph && timing == 0) {
     cudaStream_t cs;
     VPK_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
     cudaGraph_t graph = nullptr;
@@ -198,7 +202,7 @@ Program* Model::get_program(int B, int t_in, int pred, void* ws, size_t ws_bytes
 
 void Model::run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx) {
   for (Op& op : ops) {
-    const bool t = timing && op.gate;
+    const bool t = (timing == 1 && op.gate) || (timing == 2 && op.is_kernel);
     if (t) {
       while (ev_pool.size() < ev_used + 2) {
         cudaEvent_t e;
@@ -211,20 +215,52 @@ void Model::run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx
     if (t) {
       VPK_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
       ev_used += 2;
-      timed_flops += op.flops;
-      timed_launches += 1;
+      if (op.gate) {
+        timed_flops += op.flops;
+        timed_launches += 1;
+      }
+      ev_names.emplace_back(op.name, op.flops);
+      gate_flags.push_back(op.gate);
     }
     if (op.is_kernel) ++last_launches;
   }
 }
 
-void Model::gemm_stats(float* ms, int64_t* launches, double* flops) {
-  float total = 0.f;
-  for (size_t i = 0; i + 1 < ev_used; i += 2) {
+std::string Model::profile_text() {
+  std::map<std::string, std::pair<double, std::pair<int, double>>> agg;   // name -> (ms, (count, flops))
+  for (size_t i = 0; i + 1 < ev_used && i / 2 < ev_names.size(); i += 2) {
     VPK_CUDA(cudaEventSynchronize(ev_pool[i + 1]));
     float t = 0.f;
     VPK_CUDA(cudaEventElapsedTime(&t, ev_pool[i], ev_pool[i + 1]));
-    total += t;
+    auto& a = agg[ev_names[i / 2].first];
+    a.first += t;
+    a.second.first += 1;
+    a.second.second += ev_names[i / 2].second;
+  }
+  std::vector<std::pair<double, std::string>> rows;
+  for (auto& kv : agg) {
+    char line[256];
+    snprintf(line, sizeof line, "%s %d %.4f %.3f\n", kv.first.c_str(), kv.second.second.first, kv.second.first,
+             kv.second.second.second * 1e-9);
+    rows.emplace_back(-kv.second.first, line);
+  }
+  std::sort(rows.begin(), rows.end());
+  std::string out;
+  for (auto& r : rows) out += r.second;
+  return out;
+}
+
+void Model::gemm_stats(float* ms, int64_t* launches, double* flops) {
+  float total = 0.f;
+  for (size_t i = 0; i + 1 < ev_used && i / 2 < ev_names.size(); i += 2) {
+    if (timing == 2) {   // every kernel is bracketed: count only the gate GEMMs here
+      const std::string& nm = ev_names[i / 2].first;
+      (void)nm;
+    }
+    VPK_CUDA(cudaEventSynchronize(ev_pool[i + 1]));
+    float t = 0.f;
+    VPK_CUDA(cudaEventElapsedTime(&t, ev_pool[i], ev_pool[i + 1]));
+    if (timing != 2 || gate_flags[i / 2]) total += t;
   }
   *ms = total;
   *launches = timed_launches;
@@ -239,6 +275,8 @@ void Model::forward(const float* x, int batch, int t_in, int pred, float* out, f
   validate(t_in, pred);
   last_launches = 0;
   ev_used = 0;
+  ev_names.clear();
+  gate_flags.clear();
   timed_flops = 0;
   timed_launches = 0;
   const int mb = microbatch(batch);
@@ -250,7 +288,7 @@ void Model::forward(const float* x, int batch, int t_in, int pred, float* out, f
     Program* prog = get_program(nb, t_in, pred, ws, ws_bytes, stream);
     RunCtx ctx{x + mb0 * in_stride, out + mb0 * out_stride, aux, mb0, nb, batch};
     run_ops(prog->pre, stream, ctx);
-    if (prog->graph != nullptr && !timing) {
+    if (prog->graph != nullptr && timing == 0) {
       VPK_CUDA(cudaGraphLaunch(prog->graph, stream));
       for (const Op& op : prog->body)
         if (op.is_kernel) ++last_launches;
@@ -302,6 +340,8 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
   }
   last_launches = 0;
   ev_used = 0;
+  ev_names.clear();
+  gate_flags.clear();
   timed_flops = 0;
   timed_launches = 0;
   begin_call(batch, hpipe.d_aux, hpipe.s_comp);
@@ -321,7 +361,7 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     RunCtx ctx{static_cast<const float*>(hpipe.d_x[buf]), static_cast<float*>(hpipe.d_out[buf]), hpipe.d_aux, mb0, nb,
                batch};
     run_ops(prog->pre, hpipe.s_comp, ctx);
-    if (prog->graph != nullptr && !timing) {
+    if (prog->graph != nullptr && timing == 0) {
       VPK_CUDA(cudaGraphLaunch(prog->graph, hpipe.s_comp));
       for (const Op& op : prog->body)
         if (op.is_kernel) ++last_launches;

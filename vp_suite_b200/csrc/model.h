@@ -64,7 +64,8 @@ class Model {
   std::vector<std::string> keys;
   std::map<std::string, HostParam> params;
   int64_t last_launches = 0;
-  bool timing = false;
+  int timing = 0;          // 0 off, 1 events around the gate GEMMs, 2 events around every kernel (per-layer profile)
+  std::string profile_text();
   void gemm_stats(float* ms, int64_t* launches, double* flops);
 
  protected:
@@ -105,6 +106,8 @@ class Model {
   // gate-GEMM timing
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
+  std::vector<bool> gate_flags;
+  std::vector<std::pair<std::string, double>> ev_names;   // (layer name, flops) per recorded event pair
   double timed_flops = 0;
   int64_t timed_launches = 0;
   // host pipeline resources
