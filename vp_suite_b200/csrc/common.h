@@ -40,7 +40,7 @@ __host__ __device__ inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 :
 // gate conv of the recurrent cells (x, h, m are separate sources), stride-2 convs (4 parity views of the input) and
 // transposed convs (one launch per output parity, strided output) are all instances of this.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int kMaxSrc = 4;
+constexpr int kMaxSrc = 8;
 constexpr int kMaxSteps = 256;
 
 struct SrcView {          // NHWC view, channels contiguous; strides in elements

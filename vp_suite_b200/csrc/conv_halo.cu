@@ -218,8 +218,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               const uint32_t b_base = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
               for (int q = 0; q < gn; ++q) {
                 const HaloTap tap = s_taps[blk.first_tap + q0 + q];
-                const uint32_t a_addr = a_base + static_cast<uint32_t>(((rad + tap.dy) * HWp + (rad + tap.dx)) * 128);
-                const uint64_t adesc = smem_desc_sw128_sbo(a_addr, sbo);
+                const uint32_t a_addr = a_base + ((P.debug & 32) ? 0u : static_cast<uint32_t>(((rad + tap.dy) * HWp + (rad + tap.dx)) * 128));
+                const uint64_t adesc = smem_desc_sw128_sbo(a_addr, (P.debug & 64) ? 1024u : sbo);
                 const uint64_t bdesc = ptx::smem_desc_sw128(b_base + q * P.b_tap_stride);
                 const int nk = (P.debug & 2) ? 0 : tap.nk;
                 for (int k = 0; k < nk; ++k) {
@@ -403,8 +403,6 @@ template <int KIND, bool PAIR> void launch_one(const HaloPlan& P, cudaStream_t s
 
 bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps) {
   if (!tc_eligible(L, dtype)) return false;
-  if (const char* env = getenv("VPK_TC_HALO"))
-    if (atoi(env) == 0) return false;
   return radius >= 0 && radius <= 3 && nblocks >= 1 && nblocks <= 64 && ntaps <= kMaxSteps;
 }
 

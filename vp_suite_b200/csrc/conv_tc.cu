@@ -20,7 +20,7 @@
 
 #include "common.h"
 #include "conv_tc.h"
-#include "epilogue.cuh"
+#include "epilogue_tc.cuh"
 #include "ptx.cuh"
 
 namespace vpk {
@@ -280,11 +280,14 @@ void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms) {
   P.cta2 = (P.tileN % 16 == 0 && m_tiles_total * P.n_tiles >= num_sms) ? 1 : 0;
   P.debug = 0;
   if (const char* env = getenv("VPK_TC_DEBUG")) P.debug = atoi(env);
+  P.L.epi.debug = P.debug;
+  const int gk = (L.epi.kind == EPI_LSTM || L.epi.kind == EPI_ST_C) ? 4 : (L.epi.kind == EPI_ST_M) ? 3 : (L.epi.kind == EPI_ST_O) ? 2 : 1;
+  P.fast_epi = (epi_tc_fast_ok(L.epi) && gk == L.G) ? 1 : 0;
   if (const char* env = getenv("VPK_TC_PAIR")) P.cta2 = (atoi(env) != 0 && P.tileN % 16 == 0) ? 1 : 0;
   const unsigned b_rows = static_cast<unsigned>(P.cta2 ? P.tileN / 2 : P.tileN);
   const unsigned stage_bytes = kAStageBytes + b_rows * 128u;
   const unsigned fixed = 1024 /*alignment slack*/ + 512 /*barriers, tmem slot*/ +
-                         static_cast<unsigned>(L.nsteps) * sizeof(ConvStep) + 64;
+                         static_cast<unsigned>(L.nsteps) * sizeof(ConvStep) + static_cast<unsigned>(L.N_pad) * 4 + 128;
   int stages = static_cast<int>((kMaxSmem - fixed) / stage_bytes);
   stages = std::max(2, std::min(stages, 8));
   stages = std::min(stages, std::max(2, L.nsteps));

@@ -18,6 +18,7 @@ struct alignas(64) TcPlan {
   int grid;
   int debug;                   // VPK_TC_DEBUG bit mask (perf experiments only; results are wrong when set):
                                //   1 = skip epilogue math/IO, 2 = skip MMA issue, 4 = skip TMA loads
+  int fast_epi;                // lean compile-time-specialised epilogue usable (CTA-pair kernel)
   int cta2;                    // 1: CTA-pair kernel (conv_tc2.cu): weight box holds tileN/2 rows, grid is even
 };
 

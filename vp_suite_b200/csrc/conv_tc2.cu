@@ -14,7 +14,7 @@
 
 #include "common.h"
 #include "conv_tc.h"
-#include "epilogue.cuh"
+#include "epilogue_tc.cuh"
 #include "ptx.cuh"
 
 namespace vpk {
@@ -26,11 +26,16 @@ constexpr int kEpiThreads = 256;
 constexpr uint32_t kAStageBytes = 128 * 128;
 constexpr unsigned kMaxSmem = 232448;
 
-template <int G>
+__host__ __device__ constexpr int gates_of2(int kind) {
+  return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
+}
+
+template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     conv_tc2_kernel(const __grid_constant__ TcPlan P) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using bf16 = __nv_bfloat16;
+  constexpr int G = gates_of2(KIND);
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -48,6 +53,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   const uint32_t tempty_bar = ptx::smem_u32(bars + 2 * stages + 2);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
   ConvStep* s_steps = reinterpret_cast<ConvStep*>(tmem_slot + 4);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_steps + P.L.nsteps) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -58,6 +64,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   const int npairs = gridDim.x >> 1;
 
   for (int i = threadIdx.x; i < nsteps; i += kTcThreads) s_steps[i] = P.L.steps[i];
+  if (P.L.epi.bias != nullptr)
+    for (int i = threadIdx.x; i < P.L.N_pad; i += kTcThreads) s_bias[i] = P.L.epi.bias[i];
 
   if (warp == 0 && ptx::elect_one()) {
     for (int i = 0; i < P.L.nsrc; ++i) ptx::prefetch_tensormap(&P.amap[i]);
@@ -168,33 +176,64 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
       const int acc = iter & 1;
       const uint32_t acc_phase = (iter >> 1) & 1u;
       EpiOperands<8> ops0, ops1;
-      // operands of this warp's first chunk are requested before the accumulator is even complete
-      if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + half * 8, ops0);
-      ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      ptx::tc_fence_after();
+      const int C = P.L.epi.C;
+      const int ch_base = nt * Cn;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
-      auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
-        uint32_t r[8 * G];
+      auto tmem_chunk = [&](int ch, uint32_t (&r)[8 * G]) {
         const uint32_t ta = taddr + static_cast<uint32_t>(ch * G);
         if constexpr (G == 4) ptx::tmem_ld32(ta, r);
         else if constexpr (G == 2) ptx::tmem_ld16(ta, r);
         else if constexpr (G == 1) ptx::tmem_ld8(ta, r);
         else { ptx::tmem_ld8(ta, r); ptx::tmem_ld8(ta + 8, r + 8); ptx::tmem_ld8(ta + 16, r + 16); }
-        if (valid && ch + 16 < Cn)   // next chunk's global operands fly while this chunk is computed
-          epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch + 16, nxt);
-        ptx::tmem_ld_wait();
-        if (valid) {
-          float a[G][8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-#pragma unroll
-            for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
-          epilogue_finish<bf16, G, 8, true>(P.L.epi, b, y, x, P.L.H, P.L.W, nt * Cn + ch, a, cur);
-        }
       };
-      for (int ch = half * 8; ch < Cn; ch += 32) {
-        do_chunk(ch, ops0, ops1);
-        if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+      if (P.fast_epi) {
+        EpiTile et;
+        if (valid) et = epi_tile(P.L.epi, b, y, x, P.L.H, P.L.W);
+        const float* bias = P.L.epi.bias ? s_bias : nullptr;
+        if (valid && ch_base + half * 8 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + half * 8, ops0);
+        ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        ptx::tc_fence_after();
+        auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+          uint32_t r[8 * G];
+          tmem_chunk(ch, r);
+          if (valid && ch + 16 < Cn && ch_base + ch + 16 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + ch + 16, nxt);
+          ptx::tmem_ld_wait();
+          if (valid && ch_base + ch < C) {
+            float a[G][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
+            epi_tc_finish<KIND, G>(P.L.epi, et, ch_base + ch, bias, a, cur);
+          }
+        };
+        for (int ch = half * 8; ch < Cn; ch += 32) {
+          do_chunk(ch, ops0, ops1);
+          if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+        }
+      } else {
+        if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + half * 8, ops0);
+        ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        ptx::tc_fence_after();
+        auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
+          uint32_t r[8 * G];
+          tmem_chunk(ch, r);
+          if (valid && ch + 16 < Cn)
+            epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + ch + 16, nxt);
+          ptx::tmem_ld_wait();
+          if (valid) {
+            float a[G][8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+#pragma unroll
+              for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
+            epilogue_finish<bf16, G, 8, true>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + ch, a, cur);
+          }
+        };
+        for (int ch = half * 8; ch < Cn; ch += 32) {
+          do_chunk(ch, ops0, ops1);
+          if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+        }
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive_cluster(tempty_bar + 8 * acc, 0);      // the leader's MMA warp owns the accumulator hand-off
@@ -207,22 +246,25 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 #endif
 }
 
-template <int G> void set_smem_attr2() {
+template <int KIND> void launch_kind(const TcPlan& P, cudaStream_t stream) {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(conv_tc2_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
+    cudaFuncSetAttribute(conv_tc2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
   });
+  conv_tc2_kernel<KIND><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P);
 }
 
 }  // namespace
 
 void launch_conv_tc2(const TcPlan& P, cudaStream_t stream) {
-  switch (P.L.G) {
-    case 1: set_smem_attr2<1>(); conv_tc2_kernel<1><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
-    case 2: set_smem_attr2<2>(); conv_tc2_kernel<2><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
-    case 3: set_smem_attr2<3>(); conv_tc2_kernel<3><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
-    case 4: set_smem_attr2<4>(); conv_tc2_kernel<4><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P); break;
-    default: VPK_THROW(1, "conv_tc2: unsupported gate count");
+  switch (P.L.epi.kind) {
+    case EPI_BIAS_ACT: launch_kind<EPI_BIAS_ACT>(P, stream); break;
+    case EPI_LSTM: launch_kind<EPI_LSTM>(P, stream); break;
+    case EPI_ST_C: launch_kind<EPI_ST_C>(P, stream); break;
+    case EPI_ST_M: launch_kind<EPI_ST_M>(P, stream); break;
+    case EPI_ST_O: launch_kind<EPI_ST_O>(P, stream); break;
+    case EPI_PHY_GATE: launch_kind<EPI_PHY_GATE>(P, stream); break;
+    default: VPK_THROW(1, "conv_tc2: unsupported epilogue kind");
   }
   VPK_CUDA(cudaGetLastError());
 }

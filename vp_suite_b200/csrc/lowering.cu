@@ -14,7 +14,7 @@ inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
 // One step per (tap, 64-channel block).  Steps are emitted BLOCK-MAJOR (all taps of one (source, channel block) are
 // consecutive) so that the halo kernel can load that block's activation tile once and reuse it for every tap.
 void add_step(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int c0, int wref, int ky, int kx, int wc0,
-              int wc_count) {
+              int wc_count, int wsplit = 0) {
   if (wc_count < 0) wc_count = C;
   {
     HostStep h{};
@@ -29,6 +29,7 @@ void add_step(std::vector<HostStep>& steps, int src, int dy, int dx, int C, int 
     h.ky = ky;
     h.kx = kx;
     h.wc0 = wc0;
+    h.wsplit = wsplit;
     steps.push_back(h);
   }
 }
@@ -45,47 +46,76 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
   ph.H = OH;
   ph.W = OW;
   if (stride == 1) {
-    std::vector<int> src_idx;
+    // Split-bf16 inputs (view = high parts, lo_view = low parts) contribute three products per tap:
+    // A_hi*W_hi + A_hi*W_lo (same activation block: one halo tile, 2 k*k taps) and A_lo*W_hi (second block).
     for (const ConvInput& in : inputs) {
       VPK_REQUIRE(in.view.H == in_h && in.view.W == in_w, "conv input size mismatch");
-      src_idx.push_back(static_cast<int>(spec.srcs.size()));
+      const bool split = in.lo_view.base != nullptr || in.lo_view.C > 0;
+      const int hi = static_cast<int>(spec.srcs.size());
       spec.srcs.push_back(in.view);
+      int lo = -1;
+      if (split) {
+        lo = static_cast<int>(spec.srcs.size());
+        spec.srcs.push_back(in.lo_view);
+      }
+      for (int c0 = 0; c0 < in.view.C; c0 += 64) {
+        for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part)
+          for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx)
+              add_step(ph.steps, hi, ky - pad, kx - pad, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count, part);
+        if (split)
+          for (int ky = 0; ky < k; ++ky)
+            for (int kx = 0; kx < k; ++kx)
+              add_step(ph.steps, lo, ky - pad, kx - pad, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count, 1);
+      }
     }
-    for (size_t i = 0; i < inputs.size(); ++i)
-      for (int c0 = 0; c0 < inputs[i].view.C; c0 += 64)
-        for (int ky = 0; ky < k; ++ky)
-          for (int kx = 0; kx < k; ++kx)
-            add_step(ph.steps, src_idx[i], ky - pad, kx - pad, inputs[i].view.C, c0, inputs[i].wref, ky, kx,
-                     inputs[i].wc0, inputs[i].wc_count);
   } else {
     VPK_REQUIRE(inputs.size() == 1, "stride-2 conv takes a single input");
     VPK_REQUIRE(in_h % 2 == 0 && in_w % 2 == 0, "stride-2 conv needs even input size");
     const ConvInput& in = inputs[0];
-    const int base_idx = static_cast<int>(spec.srcs.size());
-    for (int py = 0; py < 2; ++py)
-      for (int px = 0; px < 2; ++px) {   // parity view: rows py, py+2, ...; columns px, px+2, ...
-        SrcView v = in.view;
-        v.H = in_h / 2;
-        v.W = in_w / 2;
-        v.sY = in.view.sY * 2;
-        v.sX = in.view.sX * 2;
-        v.base = static_cast<const char*>(in.view.base) + (py * in.view.sY + px * in.view.sX) * esize;
-        spec.srcs.push_back(v);
-      }
-    for (int par = 0; par < 4; ++par)          // block-major: parity view, channel block, then its taps
-      for (int c0 = 0; c0 < in.view.C; c0 += 64)
-        for (int ky = 0; ky < k; ++ky) {
-          const int ty = ky - pad;
-          const int py = ((ty % 2) + 2) % 2;
-          const int dy = floordiv(ty - py, 2);
-          for (int kx = 0; kx < k; ++kx) {
-            const int tx = kx - pad;
-            const int px = ((tx % 2) + 2) % 2;
-            const int dx = floordiv(tx - px, 2);
-            if (py * 2 + px != par) continue;
-            add_step(ph.steps, base_idx + par, dy, dx, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count);
-          }
+    const bool split = in.lo_view.base != nullptr || in.lo_view.C > 0;
+    auto parity_views = [&](const SrcView& full) {
+      const int first = static_cast<int>(spec.srcs.size());
+      for (int py = 0; py < 2; ++py)
+        for (int px = 0; px < 2; ++px) {   // parity view: rows py, py+2, ...; columns px, px+2, ...
+          SrcView v = full;
+          v.H = in_h / 2;
+          v.W = in_w / 2;
+          v.sY = full.sY * 2;
+          v.sX = full.sX * 2;
+          v.base = static_cast<const char*>(full.base) + (py * full.sY + px * full.sX) * esize;
+          spec.srcs.push_back(v);
         }
+      return first;
+    };
+    const int hi_idx = parity_views(in.view);
+    const int lo_idx = split ? parity_views(in.lo_view) : -1;
+    auto emit = [&](int base_idx, int wsplit, int par, int c0) {
+      for (int ky = 0; ky < k; ++ky) {
+        const int ty = ky - pad;
+        const int py = ((ty % 2) + 2) % 2;
+        const int dy = floordiv(ty - py, 2);
+        for (int kx = 0; kx < k; ++kx) {
+          const int tx = kx - pad;
+          const int px = ((tx % 2) + 2) % 2;
+          const int dx = floordiv(tx - px, 2);
+          if (py * 2 + px != par) continue;
+          add_step(ph.steps, base_idx + par, dy, dx, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count, wsplit);
+        }
+      }
+    };
+    for (int par = 0; par < 4; ++par)          // block-major: parity view, channel block, then its taps
+      for (int c0 = 0; c0 < in.view.C; c0 += 64) {
+        if (!split) {
+          emit(hi_idx, 0, par, c0);
+        } else {
+          emit(hi_idx, 1, par, c0);
+          emit(hi_idx, 2, par, c0);
+        }
+      }
+    if (split)
+      for (int par = 0; par < 4; ++par)
+        for (int c0 = 0; c0 < in.view.C; c0 += 64) emit(lo_idx, 1, par, c0);
   }
   VPK_REQUIRE(spec.srcs.size() <= static_cast<size_t>(kMaxSrc), "too many conv sources");
   *oh = OH;
@@ -98,24 +128,41 @@ void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pa
   VPK_REQUIRE(stride == 1 || stride == 2, "transposed-conv stride must be 1 or 2");
   const int OH = (in_h - 1) * stride - 2 * pad + k + out_pad;
   const int OW = (in_w - 1) * stride - 2 * pad + k + out_pad;
+  const bool split = input.lo_view.base != nullptr || input.lo_view.C > 0;
   const int src = static_cast<int>(spec.srcs.size());
   spec.srcs.push_back(input.view);
+  int src_lo = -1;
+  if (split) {
+    src_lo = static_cast<int>(spec.srcs.size());
+    spec.srcs.push_back(input.lo_view);
+  }
   for (int ry = 0; ry < stride; ++ry)
     for (int rx = 0; rx < stride; ++rx) {
       PhaseSpec ph;
       ph.H = (OH - ry + stride - 1) / stride;
       ph.W = (OW - rx + stride - 1) / stride;
       // y = stride*iy - pad + ky  with  y = stride*q + ry   =>   iy = q + (ry + pad - ky) / stride
-      for (int c0 = 0; c0 < input.view.C; c0 += 64)
+      auto emit = [&](int s_idx, int wsplit, int c0) {
         for (int ky = 0; ky < k; ++ky) {
           if (((ry + pad - ky) % stride + stride) % stride != 0) continue;
           const int dy = floordiv(ry + pad - ky, stride);
           for (int kx = 0; kx < k; ++kx) {
             if (((rx + pad - kx) % stride + stride) % stride != 0) continue;
             const int dx = floordiv(rx + pad - kx, stride);
-            add_step(ph.steps, src, dy, dx, input.view.C, c0, input.wref, ky, kx, input.wc0, input.wc_count);
+            add_step(ph.steps, s_idx, dy, dx, input.view.C, c0, input.wref, ky, kx, input.wc0, input.wc_count, wsplit);
           }
         }
+      };
+      for (int c0 = 0; c0 < input.view.C; c0 += 64) {
+        if (!split) {
+          emit(src, 0, c0);
+        } else {
+          emit(src, 1, c0);
+          emit(src, 2, c0);
+        }
+      }
+      if (split)
+        for (int c0 = 0; c0 < input.view.C; c0 += 64) emit(src_lo, 1, c0);
       ph.epi = epi_for_phase(ry, rx, stride, OH, OW);
       spec.phases.push_back(ph);
     }
@@ -205,7 +252,14 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
               if (w.gate_block[g] < 0) continue;
               const int oc = w.gate_block[g] * C + ch;
               float* row = wf.data() + static_cast<size_t>(ch * G + g) * K_pad + h.s.wk;
-              for (int j = 0; j < h.kw_valid; ++j) row[j] = weight_at(w, oc, h.wc0 + h.s.c0 + j, h.ky, h.kx);
+              for (int j = 0; j < h.kw_valid; ++j) {
+                float v = weight_at(w, oc, h.wc0 + h.s.c0 + j, h.ky, h.kx);
+                if (h.wsplit != 0) {   // split-bf16: high part, or what the high part misses
+                  const float hi = __bfloat162float(__float2bfloat16_rn(v));
+                  v = (h.wsplit == 1) ? hi : v - hi;
+                }
+                row[j] = v;
+              }
             }
         }
         PackedWeights& q = pw[p];
@@ -277,7 +331,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
     double kreal = 0;
-    for (const HostStep& h : ph.steps) kreal += h.kw_valid;
+    for (const HostStep& h : ph.steps) kreal += h.kw_valid;   // split-bf16 layers count their three products
     L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;
     if (!measure_only) {
       const PackedWeights& q = (*packed)[p];
@@ -286,7 +340,14 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       L.K_pad = q.K_pad;
       L.epi.bias = q.bias;
       bc.use_direct = direct_eligible(L);
-      bc.use_halo = !bc.use_direct && (backend == 0) && halo_eligible(L, dtype, q.radius, q.nblocks, q.ntaps);
+      // Measured on the B200 (profiles/): with tileN >= 192 the per-tap CTA-pair kernel's mainloop is ~25 % faster than
+      // the halo kernel's (weight tiles dominate the traffic there and its single ring pipelines better); for narrower N
+      // the activation tile dominates and the halo kernel wins by up to 2x.
+      const bool wide = L.Cn * L.G >= 192;
+      bool prefer_halo = !wide;
+      if (const char* env = getenv("VPK_TC_HALO")) prefer_halo = atoi(env) != 0;
+      bc.use_halo = !bc.use_direct && (backend == 0) && prefer_halo &&
+                    halo_eligible(L, dtype, q.radius, q.nblocks, q.ntaps);
       bc.use_tc = !bc.use_direct && !bc.use_halo && (backend == 0) && tc_eligible(L, dtype);
       if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);
       if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);

@@ -28,6 +28,7 @@ struct BiasRef {
 struct HostStep {
   ConvStep s;
   int kw_valid;  // channels of this step that exist in the weight tensor (<= s.kc; the rest is zero padding)
+  int wsplit;    // 0: weight value as is; 1 / 2: high / low bf16 part of it (split-bf16 operands)
   int wref;      // index into ConvSpec::wrefs
   int ky, kx;    // tap of that weight tensor
   int wc0;       // input-channel index of that weight tensor that corresponds to channel 0 of the source
@@ -55,6 +56,7 @@ struct ConvInput {                  // one logical input tensor of a conv (full-
   SrcView view;
   int wref;                         // weight tensor it multiplies
   int wc0;                          // its channel offset inside that weight's input-channel dimension
+  SrcView lo_view{nullptr, 0, 0, 0, 0, 0, 0};   // split-bf16 operand: `view` holds the high parts, `lo_view` the low parts
   int wc_count = -1;                // channels the weight really has for this input (-1: view.C); a view may carry
                                     // zero-padded extra channels (e.g. 49 -> 56 so that TMA strides are 16-byte)
 };
