@@ -95,6 +95,8 @@ struct ConvArgs {
   bool out_f32_dense = false;   // out is float*, dense NHWC [B, OH, OW, out_pix] (out_pix >= Cout channels per pixel)
   int out_pix = 0;              // pixel stride of a dense output (0: Cout)
   const float* res = nullptr;   // fp32 dense [B, OH, OW, Cout] residual added after the activation
+  bool split = false;           // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
+  const void* x_lo = nullptr;
 };
 inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -113,7 +115,9 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
     b.b = a.bias;
     s.biases.push_back(b);
   }
-  lower_conv(s, a.k, a.stride, a.pad, {ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0}}, a.H, a.W, act.esize, oh, ow);
+  ConvInput in{make_view(a.x, a.H, a.W, a.Cin), 0, 0};
+  if (a.split) in.lo_view = make_view(a.x_lo, a.H, a.W, a.Cin);
+  lower_conv(s, a.k, a.stride, a.pad, {in}, a.H, a.W, act.esize, oh, ow);
   EpiParams& e = s.phases[0].epi;
   e.kind = EPI_BIAS_ACT;
   e.act = a.act;
@@ -143,6 +147,8 @@ struct DeconvArgs {
   bool out_f32 = false;       // element type of `out` is float regardless of the activation type
   bool nchw = false;          // fp32 NCHW output (implies out_f32)
   long long oB_nchw = 0;
+  bool split = false;         // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
+  const void* x_lo = nullptr;
 };
 inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -167,7 +173,9 @@ inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, in
   const size_t esz = f32 ? sizeof(float) : static_cast<size_t>(act.esize);
   const long long oBn = a.oB_nchw;
   void* out = a.out;
-  lower_conv_transpose(s, a.k, a.stride, a.pad, a.out_pad, ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0}, a.H, a.W,
+  ConvInput cin{make_view(a.x, a.H, a.W, a.Cin), 0, 0};
+  if (a.split) cin.lo_view = make_view(a.x_lo, a.H, a.W, a.Cin);
+  lower_conv_transpose(s, a.k, a.stride, a.pad, a.out_pad, cin, a.H, a.W,
                        oh, ow, [=](int ry, int rx, int stride, int OH, int OW) {
                          EpiParams e{};
                          e.kind = EPI_BIAS_ACT;

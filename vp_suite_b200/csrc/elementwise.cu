@@ -1,6 +1,8 @@
 // Memory-bound helper kernels: boundary layout conversion (fp32 NCHW frames <-> NHWC activations), PredRNN
 // patchify / un-patchify, GroupNorm (+LeakyReLU), decouple-loss reduction.  Vectorised, coalesced on the side that
 // dominates the traffic; grid-stride loops sized in multiples of the SM count.
+#include <mutex>
+
 #include "common.h"
 #include "elementwise.h"
 #include "epilogue.cuh"
@@ -181,6 +183,139 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict
   }
 }
 
+// GroupNorm (+ LeakyReLU(0.2), + fp32 residual add) with the whole sample staged in shared memory: HBM sees one read
+// and one write of the tensor (the generic kernel above reads it three times).  in fp32 dense [B][HW][C] with
+// (4 * blockDim) % C == 0, so every thread owns the same four channels in each of its float4 pieces; statistics are
+// two-pass (mean, then centred sum of squares) over the staged copy, like ATen.  OUT selects the output encoding:
+// 0 fp32, 1 bf16, 2 split-bf16 (hi = bf16(v), lo = bf16(v - hi): together 16 mantissa bits, the operand format of the
+// three-product tensor-core convs that replace fp32 convs).  STAGED = false re-reads global memory instead (samples
+// larger than shared memory).
+// lanes of a warp that own the same four channels (4 * lane distance is a multiple of C) are summed by shuffles first,
+// then one lane per channel quad adds to the per-group accumulators in shared memory
+__device__ __forceinline__ void gn_commit(float* s_acc, int C, int cg, int c0, float a0, float a1, float a2, float a3) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    if ((o * 4) % C == 0) {
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, o);
+    }
+  }
+  const int lane = threadIdx.x & 31;
+  if (lane * 4 < C) {
+    atomicAdd(&s_acc[(c0 + 0) / cg], a0);
+    atomicAdd(&s_acc[(c0 + 1) / cg], a1);
+    atomicAdd(&s_acc[(c0 + 2) / cg], a2);
+    atomicAdd(&s_acc[(c0 + 3) / cg], a3);
+  }
+}
+
+constexpr int kGnThreads = 512;
+template <int OUT, bool STAGED>
+__global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float* __restrict__ in, void* __restrict__ out,
+                                                                    void* __restrict__ out_lo,
+                                                                    const float* __restrict__ add, int HW, int C,
+                                                                    int groups, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, float eps, int act) {
+  extern __shared__ float4 gn_stage[];
+  __shared__ float s_acc[64], s_mean[64], s_rstd[64];
+  const int b = blockIdx.x;
+  const int n4 = HW * C / 4;
+  const float4* src = reinterpret_cast<const float4*>(in + static_cast<size_t>(b) * HW * C);
+  const int c0 = (threadIdx.x * 4) % C;
+  const int cg = C / groups;
+  const float n = static_cast<float>(cg) * HW;
+  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.f;
+  __syncthreads();
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int i = threadIdx.x; i < n4; i += kGnThreads) {
+    const float4 v = src[i];
+    if (STAGED) gn_stage[i] = v;
+    a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+  }
+  gn_commit(s_acc, C, cg, c0, a0, a1, a2, a3);
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    s_mean[threadIdx.x] = s_acc[threadIdx.x] / n;
+    s_acc[threadIdx.x] = 0.f;
+  }
+  __syncthreads();
+  const float m0 = s_mean[(c0 + 0) / cg], m1 = s_mean[(c0 + 1) / cg], m2 = s_mean[(c0 + 2) / cg],
+              m3 = s_mean[(c0 + 3) / cg];
+  a0 = a1 = a2 = a3 = 0.f;
+  for (int i = threadIdx.x; i < n4; i += kGnThreads) {
+    const float4 v = STAGED ? gn_stage[i] : src[i];
+    a0 = fmaf(v.x - m0, v.x - m0, a0);
+    a1 = fmaf(v.y - m1, v.y - m1, a1);
+    a2 = fmaf(v.z - m2, v.z - m2, a2);
+    a3 = fmaf(v.w - m3, v.w - m3, a3);
+  }
+  gn_commit(s_acc, C, cg, c0, a0, a1, a2, a3);
+  __syncthreads();
+  if (threadIdx.x < groups) s_rstd[threadIdx.x] = rsqrtf(s_acc[threadIdx.x] / n + eps);
+  __syncthreads();
+  float sc[4], sh[4];
+  const float mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = s_rstd[(c0 + j) / cg] * gamma[c0 + j];
+    sh[j] = beta[c0 + j] - mm[j] * sc[j];
+  }
+  const float4* addp = add ? reinterpret_cast<const float4*>(add + static_cast<size_t>(b) * HW * C) : nullptr;
+  const size_t obase = static_cast<size_t>(b) * n4;
+  for (int i = threadIdx.x; i < n4; i += kGnThreads) {
+    const float4 x = STAGED ? gn_stage[i] : src[i];
+    float v[4] = {fmaf(x.x, sc[0], sh[0]), fmaf(x.y, sc[1], sh[1]), fmaf(x.z, sc[2], sh[2]), fmaf(x.w, sc[3], sh[3])};
+    if (act == ACT_LEAKY) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+    }
+    if (addp) {
+      const float4 r = addp[i];
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    if (OUT == 0) {
+      reinterpret_cast<float4*>(out)[obase + i] = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 hv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+      hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(out)[obase + i] = hv;
+      if (OUT == 2) {
+        const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+        const __nv_bfloat162 l01 = __floats2bfloat162_rn(v[0] - f01.x, v[1] - f01.y),
+                             l23 = __floats2bfloat162_rn(v[2] - f23.x, v[3] - f23.y);
+        uint2 lv;
+        lv.x = *reinterpret_cast<const uint32_t*>(&l01);
+        lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+        reinterpret_cast<uint2*>(out_lo)[obase + i] = lv;
+      }
+    }
+  }
+}
+
+// fp32 -> split-bf16 (hi, lo); n % 4 == 0
+__global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, long long n4) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    const __nv_bfloat162 h01 = __floats2bfloat162_rn(v.x, v.y), h23 = __floats2bfloat162_rn(v.z, v.w);
+    const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+    const __nv_bfloat162 l01 = __floats2bfloat162_rn(v.x - f01.x, v.y - f01.y),
+                         l23 = __floats2bfloat162_rn(v.z - f23.x, v.w - f23.y);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+    hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l01);
+    lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    reinterpret_cast<uint2*>(hi)[i] = hv;
+    reinterpret_cast<uint2*>(lo)[i] = lv;
+  }
+}
+
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
   aux[0] = static_cast<float>(acc[0] * scale);
 }
@@ -239,6 +374,46 @@ void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype
   else if (in_dtype == DT_BF16 && out_dtype == DT_BF16) VPK_GN(__nv_bfloat16, __nv_bfloat16);
   else VPK_THROW(1, "groupnorm: unsupported dtype combination");
 #undef VPK_GN
+  VPK_CUDA(cudaGetLastError());
+}
+
+bool groupnorm_smem_supported(int HW, int C, int groups) {
+  return C >= 4 && (kGnThreads * 4) % C == 0 && groups <= 64 && C % groups == 0 && (HW * C) % 4 == 0;
+}
+
+void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kind, const float* add, int B, int HW,
+                           int C, int groups, const float* gamma, const float* beta, float eps, int act,
+                           cudaStream_t stream) {
+  VPK_REQUIRE(groupnorm_smem_supported(HW, C, groups), "groupnorm_smem: unsupported shape");
+  VPK_REQUIRE(out_kind >= 0 && out_kind <= 2 && (out_kind != 2 || out_lo != nullptr), "groupnorm_smem: bad output kind");
+  const size_t bytes = static_cast<size_t>(HW) * C * sizeof(float);
+  const bool staged = bytes <= 200 * 1024;
+#define VPK_GNS(OUT, ST)                                                                                           \
+  do {                                                                                                             \
+    static std::once_flag once;                                                                                    \
+    std::call_once(once, [] {                                                                                      \
+      cudaFuncSetAttribute(groupnorm_smem_kernel<OUT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+    });                                                                                                            \
+    groupnorm_smem_kernel<OUT, ST><<<B, kGnThreads, (ST) ? bytes : 0, stream>>>(in, out, out_lo, add, HW, C, groups, \
+                                                                                gamma, beta, eps, act);            \
+  } while (0)
+  if (staged) {
+    if (out_kind == 0) VPK_GNS(0, true);
+    else if (out_kind == 1) VPK_GNS(1, true);
+    else VPK_GNS(2, true);
+  } else {
+    if (out_kind == 0) VPK_GNS(0, false);
+    else if (out_kind == 1) VPK_GNS(1, false);
+    else VPK_GNS(2, false);
+  }
+#undef VPK_GNS
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream) {
+  VPK_REQUIRE(n % 4 == 0, "split_bf16: element count must be a multiple of 4");
+  split_bf16_kernel<<<grid_for(n / 4, 256, num_sms), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(hi),
+                                                                       static_cast<__nv_bfloat16*>(lo), n / 4);
   VPK_CUDA(cudaGetLastError());
 }
 

@@ -35,4 +35,14 @@ void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype
                           int Cs_in, int Cs_out, int groups, const float* gamma, const float* beta, float eps,
                           int act, cudaStream_t stream);
 
+// Same operation with the sample staged in shared memory (one HBM read + one write).  in: fp32 dense [B][HW][C];
+// out_kind 0: fp32 out; 1: bf16 out; 2: split-bf16 (out = high parts, out_lo = low parts); add: optional fp32 dense
+// residual added after the activation.
+bool groupnorm_smem_supported(int HW, int C, int groups);
+void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kind, const float* add, int B, int HW,
+                           int C, int groups, const float* gamma, const float* beta, float eps, int act,
+                           cudaStream_t stream);
+// fp32 -> split-bf16: hi = bf16(v), lo = bf16(v - hi)
+void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
+
 }  // namespace vpk

@@ -9,9 +9,12 @@
 // Warm-up steps on context frames only advance the recurrent state (their images are discarded in eval, :108-113), so
 // the decoders are skipped there; of the three decoder_D passes per step only `output_image` (:87-88) is computed.
 //
-// Precision in bf16 mode: the recurrent cells (85 % of the FLOPs) run bf16 on the tensor cores; the DCGAN encoder /
+// Precision in bf16 mode: the recurrent cells (85 % of the FLOPs) run bf16 on the tensor cores.  The DCGAN encoder /
 // decoder convs feed GroupNorm, which amplifies operand rounding past the 5e-3 single-step bound,
-// so they keep fp32 operands.
+// so they need ~fp32 operands: their feature maps are kept as SPLIT bf16 (hi + lo, 16 mantissa bits) and each conv is
+// three bf16 tensor-core products (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulation in TMEM) through the same
+// tcgen05 kernel -- the dropped A_lo W_lo term is ~2^-18 relative.  Only encoder_E.c1 (image frames, 1 or 3 input
+// channels: not TMA-addressable) stays on the CUDA-core fp32 kernel.
 #include <cmath>
 
 #include "builders.h"
@@ -95,11 +98,19 @@ class PhyDNetModel : public Model {
     return p.data;
   }
 
+  // An encoder / decoder feature map.  fp32 mode: `a` is a float tensor.  bf16 mode: split-bf16, `a` holds the high
+  // parts and `lo` the low parts (hi = bf16(v), lo = bf16(v - hi)), both NHWC bf16.
+  struct Feat {
+    void* a = nullptr;
+    void* lo = nullptr;
+  };
+  enum OutKind { OUT_FEAT, OUT_CELL, OUT_F32 };
+
   void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) override {
     const vpk_model_desc& d = desc;
-    const int edt = DT_F32;               // encoder / decoder operand type (see header comment)
     const int cdt = dtype;                // recurrent-cell operand type
-    const ActInfo ea{edt, 4}, ca{cdt, esize()};
+    const bool split = (cdt == DT_BF16);  // encoder / decoder convs: three bf16 products on the tensor cores
+    const ActInfo f32a{DT_F32, 4}, sa{DT_BF16, 2}, ca{cdt, esize()};
     const int esz_c = esize();
     const int c = d.img_c, h = d.img_h, w = d.img_w;
     const int h2 = h / 2, w2 = w / 2, h4 = h / 4, w4 = w / 4;
@@ -108,14 +119,21 @@ class PhyDNetModel : public Model {
     const int Cp = phycell_padded_channels(hid);
     const int ns = num_sms;
 
+    auto feat = [&](size_t elems) {
+      Feat f;
+      if (split) {
+        f.a = arena.alloc(elems * 2);
+        f.lo = arena.alloc(elems * 2);
+      } else {
+        f.a = arena.alloc(elems * 4);
+      }
+      return f;
+    };
     float* frames_in = static_cast<float*>(arena.alloc(px1 * c * 4 * t_in));
     float* out_stage = static_cast<float*>(arena.alloc(px1 * c * 4 * pred));
     float* frame_fb = static_cast<float*>(arena.alloc(px1 * c * 4));          // fed-back frame, NHWC
     float* raw = static_cast<float*>(arena.alloc(std::max(px2 * 32, px4 * 64) * 4));   // pre-GroupNorm conv output
-    float* e1 = static_cast<float*>(arena.alloc(px2 * 32 * 4));
-    float* e2 = static_cast<float*>(arena.alloc(px2 * 32 * 4));
-    float* e3 = static_cast<float*>(arena.alloc(px4 * 64 * 4));
-    float* mid = static_cast<float*>(arena.alloc(px4 * 64 * 4));
+    Feat e1 = feat(px2 * 32), e2 = feat(px2 * 32), e3 = feat(px4 * 64), mid = feat(px4 * 64);
     void* ep = arena.alloc(px4 * 64 * esz_c);
     void* er = arena.alloc(px4 * 64 * esz_c);
     // PhyCell state
@@ -141,38 +159,66 @@ class PhyDNetModel : public Model {
     }
     float* h_top32 = static_cast<float*>(arena.alloc(px4 * 64 * 4));
     float* dp = static_cast<float*>(arena.alloc(px4 * 64 * 4));
-    float* dsum = static_cast<float*>(arena.alloc(px4 * 64 * 4));
-    float* d1 = static_cast<float*>(arena.alloc(px2 * 32 * 4));
-    float* d2 = static_cast<float*>(arena.alloc(px2 * 32 * 4));
+    Feat dsum = feat(px4 * 64), d1 = feat(px2 * 32), d2 = feat(px2 * 32);
+    Feat dec_p, dec_r;                   // decoder inputs: PhyCell h and top ConvLSTM h as feature maps
+    if (split) {
+      dec_p = feat(px4 * 64);
+      dec_r = feat(px4 * 64);
+    }
 
-    auto gn_op = [&](const std::string& key, const float* in, void* out, int out_dt, const void* add, int HW, int C,
-                     int Cs_in, int Cs_out, int groups, int actk) {
+    // GroupNorm (+ LeakyReLU) of the fp32 conv output `in` into a feature map / cell operand / fp32 tensor
+    auto gn_op = [&](const std::string& key, const float* in, OutKind kind, Feat out, const float* add, int HW, int C,
+                     int groups, int actk) {
       if (measure) return;
       const float* g = dev_f32(key + "weight", vec(key + "weight"), stream);
       const float* bta = dev_f32(key + "bias", vec(key + "bias"), stream);
+      const int out_dt = (kind == OUT_F32) ? DT_F32 : (kind == OUT_CELL) ? cdt : (split ? DT_BF16 : DT_F32);
+      const bool two = (kind == OUT_FEAT) && split;
       Op op;
       op.name = "groupnorm " + key;
-      op.fn = [=](cudaStream_t s, const RunCtx&) {
-        launch_groupnorm_act(in, DT_F32, out, out_dt, add, B, HW, C, Cs_in, Cs_out, groups, g, bta, 1e-5f, actk, s);
-      };
+      if (groupnorm_smem_supported(HW, C, groups)) {
+        const int ok = two ? 2 : (out_dt == DT_BF16 ? 1 : 0);
+        op.fn = [=](cudaStream_t s, const RunCtx&) {
+          launch_groupnorm_smem(in, out.a, out.lo, ok, add, B, HW, C, groups, g, bta, 1e-5f, actk, s);
+        };
+      } else {
+        VPK_REQUIRE(!two && (add == nullptr || out_dt == DT_F32), "groupnorm: shape needs the shared-memory kernel");
+        op.fn = [=](cudaStream_t s, const RunCtx&) {
+          launch_groupnorm_act(in, DT_F32, out.a, out_dt, add, B, HW, C, C, C, groups, g, bta, 1e-5f, actk, s);
+        };
+      }
       prog.body.push_back(std::move(op));
     };
     // DCGANConv / DCGANConvTranspose: conv -> GroupNorm(16) -> LeakyReLU(0.2)   (model_blocks/conv.py:58-95)
-    auto dcgan = [&](const std::string& p, bool transpose, const void* in, int H, int W, int Cin, int Cout, int stride,
-                     void* out, int out_dt, const void* add) {
+    // `in_f32`: the input is a plain fp32 tensor (image frames: CUDA-core kernel), otherwise a feature map
+    auto dcgan = [&](const std::string& p, bool transpose, Feat in, bool in_f32, int H, int W, int Cin, int Cout,
+                     int stride, OutKind kind, Feat out, const float* add) {
       int oh, ow;
+      const bool sp = split && !in_f32;
+      const ActInfo& ai = sp ? sa : f32a;
       if (!transpose) {
-        ConvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, in, hp(p + "main.0.weight"), hp(p + "main.0.bias"),
+        ConvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, in.a, hp(p + "main.0.weight"), hp(p + "main.0.bias"),
                    ACT_NONE, raw};
         a.out_f32_dense = true;
-        add_conv(prog, conv_spec(a, ea, &oh, &ow), measure, stream, edt);
+        a.split = sp;
+        a.x_lo = in.lo;
+        add_conv(prog, conv_spec(a, ai, &oh, &ow), measure, stream, ai.dtype);
       } else {
-        DeconvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, stride == 2 ? 1 : 0, in, hp(p + "main.0.weight"),
+        DeconvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, stride == 2 ? 1 : 0, in.a, hp(p + "main.0.weight"),
                      hp(p + "main.0.bias"), ACT_NONE, raw};
         a.out_f32 = true;
-        add_conv(prog, deconv_spec(a, ea, &oh, &ow), measure, stream, edt);
+        a.split = sp;
+        a.x_lo = in.lo;
+        add_conv(prog, deconv_spec(a, ai, &oh, &ow), measure, stream, ai.dtype);
       }
-      gn_op(p + "main.1.", raw, out, out_dt, add, oh * ow, Cout, Cout, Cout, 16, ACT_LEAKY);
+      gn_op(p + "main.1.", raw, kind, out, add, oh * ow, Cout, 16, ACT_LEAKY);
+    };
+    auto split_op = [&](const float* src, Feat dst, size_t n, const char* name) {
+      if (measure) return;
+      Op op;
+      op.name = name;
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_split_bf16(src, dst.a, dst.lo, static_cast<long long>(n), ns, s); };
+      prog.body.push_back(std::move(op));
     };
 
     if (!measure) {
@@ -200,17 +246,18 @@ class PhyDNetModel : public Model {
     for (int st = 0; st < n_steps; ++st) {
       const bool decode = st >= t_in - 1;                        // produces a predicted frame
       const int di = st - (t_in - 1);
-      const float* frame = (st < t_in) ? frames_in + static_cast<size_t>(st) * px1 * c : frame_fb;
+      Feat frame;
+      frame.a = (st < t_in) ? frames_in + static_cast<size_t>(st) * px1 * c : frame_fb;
       // ---- encoders ----
-      dcgan("encoder_E.c1.", false, frame, h, w, c, 32, 2, e1, DT_F32, nullptr);
-      dcgan("encoder_E.c2.", false, e1, h2, w2, 32, 32, 1, e2, DT_F32, nullptr);
-      dcgan("encoder_E.c3.", false, e2, h2, w2, 32, 64, 2, e3, DT_F32, nullptr);
+      dcgan("encoder_E.c1.", false, frame, true, h, w, c, 32, 2, OUT_FEAT, e1, nullptr);
+      dcgan("encoder_E.c2.", false, e1, false, h2, w2, 32, 32, 1, OUT_FEAT, e2, nullptr);
+      dcgan("encoder_E.c3.", false, e2, false, h2, w2, 32, 64, 2, OUT_FEAT, e3, nullptr);
       if (!branch_only) {
-        dcgan("encoder_Ep.c1.", false, e3, h4, w4, 64, 64, 1, mid, DT_F32, nullptr);
-        dcgan("encoder_Ep.c2.", false, mid, h4, w4, 64, 64, 1, ep, cdt, nullptr);
+        dcgan("encoder_Ep.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
+        dcgan("encoder_Ep.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{ep, nullptr}, nullptr);
       }
-      dcgan("encoder_Er.c1.", false, e3, h4, w4, 64, 64, 1, mid, DT_F32, nullptr);
-      dcgan("encoder_Er.c2.", false, mid, h4, w4, 64, 64, 1, er, cdt, nullptr);
+      dcgan("encoder_Er.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
+      dcgan("encoder_Er.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{er, nullptr}, nullptr);
 
       // ---- PhyCell stack (model_blocks/phydnet.py:95-105) ----
       if (!branch_only) {
@@ -225,7 +272,19 @@ class PhyDNetModel : public Model {
           std::vector<ConvSpec> specs = phycell_specs(pa, ca);
           add_conv(prog, specs[0], measure, stream, cdt);
           // F.bn1 = GroupNorm(find_divisor(hid), hid), no activation
-          gn_op(p + "F.bn1.", f1raw, f1n, cdt, nullptr, h4 * w4, hid, Cp, Cp, group_norm_divisor(hid), ACT_NONE);
+          if (!measure) {
+            const std::string key = p + "F.bn1.";
+            const float* g = dev_f32(key + "weight", vec(key + "weight"), stream);
+            const float* bta = dev_f32(key + "bias", vec(key + "bias"), stream);
+            const int groups = group_norm_divisor(hid), HW = h4 * w4, hid_ = hid;
+            Op op;
+            op.name = "groupnorm " + key;
+            op.fn = [=](cudaStream_t s, const RunCtx&) {
+              launch_groupnorm_act(f1raw, DT_F32, f1n, cdt, nullptr, B, HW, hid_, Cp, Cp, groups, g, bta, 1e-5f,
+                                   ACT_NONE, s);
+            };
+            prog.body.push_back(std::move(op));
+          }
           add_conv(prog, specs[1], measure, stream, cdt);
           add_conv(prog, specs[2], measure, stream, cdt);
           ppar[j] ^= 1;
@@ -252,23 +311,35 @@ class PhyDNetModel : public Model {
       }
       if (!decode) continue;
       // ---- decoders ----
-      const float* dec_in = h_top32;
-      if (!branch_only) {
-        dcgan("decoder_Dp.upc1.", true, hp_master[n_phy - 1], h4, w4, 64, 64, 1, mid, DT_F32, nullptr);
-        dcgan("decoder_Dp.upc2.", true, mid, h4, w4, 64, 64, 1, dp, DT_F32, nullptr);
+      Feat in_p, in_r;
+      if (split) {
+        if (!branch_only) split_op(hp_master[n_phy - 1], dec_p, px4 * 64, "split_phy_h");
+        split_op(h_top32, dec_r, px4 * 64, "split_lstm_h");
+        in_p = dec_p;
+        in_r = dec_r;
+      } else {
+        if (!branch_only) in_p.a = hp_master[n_phy - 1];
+        in_r.a = h_top32;
       }
-      dcgan("decoder_Dr.upc1.", true, dec_in, h4, w4, 64, 64, 1, mid, DT_F32, nullptr);
+      if (!branch_only) {
+        dcgan("decoder_Dp.upc1.", true, in_p, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
+        dcgan("decoder_Dp.upc2.", true, mid, false, h4, w4, 64, 64, 1, OUT_F32, Feat{dp, nullptr}, nullptr);
+      }
+      dcgan("decoder_Dr.upc1.", true, in_r, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
       // concat = decoded_phys + decoded_conv (models/phydnet.py:87) folded into the last GroupNorm pass
-      dcgan("decoder_Dr.upc2.", true, mid, h4, w4, 64, 64, 1, dsum, DT_F32, branch_only ? nullptr : dp);
-      dcgan("decoder_D.upc1.", true, dsum, h4, w4, 64, 32, 2, d1, DT_F32, nullptr);
-      dcgan("decoder_D.upc2.", true, d1, h2, w2, 32, 32, 1, d2, DT_F32, nullptr);
+      dcgan("decoder_Dr.upc2.", true, mid, false, h4, w4, 64, 64, 1, OUT_FEAT, dsum, branch_only ? nullptr : dp);
+      dcgan("decoder_D.upc1.", true, dsum, false, h4, w4, 64, 32, 2, OUT_FEAT, d1, nullptr);
+      dcgan("decoder_D.upc2.", true, d1, false, h2, w2, 32, 32, 1, OUT_FEAT, d2, nullptr);
       {
         int oh, ow;
-        DeconvArgs a{"decoder_D.upc3.", B, h2, w2, 32, c, 3, 2, 1, 1, d2, hp("decoder_D.upc3.weight"),
+        DeconvArgs a{"decoder_D.upc3.", B, h2, w2, 32, c, 3, 2, 1, 1, d2.a, hp("decoder_D.upc3.weight"),
                      hp("decoder_D.upc3.bias"), ACT_SIGMOID, out_stage + static_cast<size_t>(di) * c * h * w};
         a.nchw = true;
         a.oB_nchw = static_cast<long long>(pred) * c * h * w;
-        add_conv(prog, deconv_spec(a, ea, &oh, &ow), measure, stream, edt);
+        a.split = split;
+        a.x_lo = d2.lo;
+        const ActInfo& ai = split ? sa : f32a;
+        add_conv(prog, deconv_spec(a, ai, &oh, &ow), measure, stream, ai.dtype);
         VPK_REQUIRE(oh == h && ow == w, "decoder output size mismatch");
       }
       if (!measure && di + 1 < pred) {   // next decoder input = output_image (models/phydnet.py:121)
