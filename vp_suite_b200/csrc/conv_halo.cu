@@ -13,8 +13,9 @@
 // group is one image row segment.  PAIR = true: cta_group::2, M = 256 across a cluster of two CTAs (each CTA its own
 // spatial tile and half of the weight rows), as in conv_tc2.cu.
 //
-// Warps: 0 activation-TMA producer, 1 weight-TMA producer, 2 MMA issuer, 3 TMEM allocator, 4..11 epilogue
-// (two warps per TMEM lane quadrant, operands prefetched one 8-channel chunk ahead).
+// Warps: 0 activation-TMA producer, 1 weight-TMA producer, 2 MMA issuer (one elected thread; the warp also owns the
+// TMEM allocation), 3..10 epilogue (two warps per TMEM lane quadrant = warp % 4, operands prefetched one 8-channel
+// chunk ahead).  352 threads leave 184 registers per thread: the LSTM epilogue holds two operand chunks in flight.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -29,7 +30,7 @@ namespace vpk {
 
 namespace {
 
-constexpr int kHaloThreads = 384;
+constexpr int kHaloThreads = 352;   // warps 0..2: activation TMA, weight TMA, MMA issue (+ TMEM alloc); warps 3..10: epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kTW = 8, kTH = 16;
 constexpr unsigned kMaxSmem = 232448;
@@ -47,7 +48,7 @@ __host__ __device__ constexpr int gates_of(int kind) {
   return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
 }
 
-template <int KIND, bool PAIR>
+template <int KIND, bool PAIR, bool FAST>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloPlan P) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using bf16 = __nv_bfloat16;
@@ -71,7 +72,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * SA + 2 * SB + 4);
   HaloBlock* s_blocks = reinterpret_cast<HaloBlock*>(tmem_slot + 4);
   HaloTap* s_taps = reinterpret_cast<HaloTap*>(s_blocks + P.nblocks);
-  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_taps + P.ntaps) + 15) & ~uintptr_t(15));
+  // per tap, for the MMA thread: x = offset of the shifted activation view in descriptor units (16 B), y = K=16 slices
+  uint2* s_tapmma = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(s_taps + P.ntaps) + 15) & ~uintptr_t(15));
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapmma + P.ntaps) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -82,9 +85,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int nblocks = P.nblocks;
 
   for (int i = threadIdx.x; i < nblocks; i += kHaloThreads) s_blocks[i] = P.blocks[i];
-  for (int i = threadIdx.x; i < P.ntaps; i += kHaloThreads) s_taps[i] = P.taps[i];
-  if (P.L.epi.bias != nullptr)
-    for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias[i];
+  for (int i = threadIdx.x; i < P.ntaps; i += kHaloThreads) {
+    const HaloTap tp = P.taps[i];
+    s_taps[i] = tp;
+    const int hwp = kTW + 2 * P.P;
+    const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
+    s_tapmma[i] = make_uint2(off >> 4, static_cast<uint32_t>((P.debug & 2) ? 0 : tp.nk));
+  }
+  for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
 
   if (warp == 0 && ptx::elect_one()) {
     for (int i = 0; i < P.L.nsrc; ++i) ptx::prefetch_tensormap(&P.amap[i]);
@@ -106,7 +114,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     ptx::fence_barrier_init();
   }
   if constexpr (PAIR) ptx::cluster_sync_all();
-  if (warp == 3) {
+  if (warp == 2) {
     if constexpr (PAIR) {
       ptx::tmem_alloc_pair(ptx::smem_u32(tmem_slot), static_cast<uint32_t>(P.tmem_cols));
       ptx::tmem_relinquish_pair();
@@ -141,7 +149,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int b0 = mt / (P.tiles_x * P.tiles_y);            // odd tail of a pair: b0 == B -> zero fill
         for (int bi = 0; bi < nblocks; ++bi) {
           const HaloBlock blk = s_blocks[bi];
-          ptx::mbar_wait(aempty + 8 * sa, ph ^ 1u);
+          ptx::mbar_wait_fast(aempty + 8 * sa, ph ^ 1u);
           const uint32_t fb = afull + 8 * sa;
           const uint32_t dst = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
           if (P.debug & 4) {
@@ -168,7 +176,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const HaloBlock blk = s_blocks[bi];
           for (int q0 = 0; q0 < blk.ntaps; q0 += P.bgroup) {
             const int gn = min(P.bgroup, blk.ntaps - q0);
-            ptx::mbar_wait(bempty + 8 * sb, ph ^ 1u);
+            ptx::mbar_wait_fast(bempty + 8 * sb, ph ^ 1u);
             const uint32_t fb = bfull + 8 * sb;
             const uint32_t dst = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
             if (P.debug & 4) {
@@ -192,65 +200,69 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else if (warp == 2) {
     // ===================================== MMA issuer (leader CTA of a pair) ================================
-    if (leader) {
+    // ONE thread runs the whole loop: between two tcgen05.mma there is a shared-memory table read, two 64-bit adds and
+    // the predicate; descriptors are advanced arithmetically (the start-address field counts 16-byte units and never
+    // carries out of its 14 bits: shared memory is < 256 KB).
+    if (leader && ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_bf16_f32(PAIR ? 256 : 128, tileN);
-      const uint32_t sbo = static_cast<uint32_t>(HWp * 128);
+      const uint32_t sbo = (P.debug & 64) ? 1024u : static_cast<uint32_t>(HWp * 128);
+      const uint64_t adesc0 = smem_desc_sw128_sbo(ptx::smem_u32(smem_a), sbo);
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
+      const uint32_t a_slot_u = P.a_slot_bytes >> 4, b_slot_u = P.b_slot_bytes >> 4, b_tap_u = P.b_tap_stride >> 4;
+      const int bgroup = P.bgroup;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
       int iter = 0;
       for (int t = unit0; t < total; t += nunits, ++iter) {
         const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1u;
-        ptx::mbar_wait(tempty + 8 * acc, acc_phase ^ 1u);
+        ptx::mbar_wait_fast(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
-        bool first = true;
+        uint32_t accum = 0;
         for (int bi = 0; bi < nblocks; ++bi) {
           const HaloBlock blk = s_blocks[bi];
-          ptx::mbar_wait(afull + 8 * sa, pha);
+          ptx::mbar_wait_fast(afull + 8 * sa, pha);
           ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
-          for (int q0 = 0; q0 < blk.ntaps; q0 += P.bgroup) {
-            const int gn = min(P.bgroup, blk.ntaps - q0);
-            ptx::mbar_wait(bfull + 8 * sb, phb);
+          const uint64_t a_d = adesc0 + static_cast<uint64_t>(sa * a_slot_u);
+          const uint2* tp = s_tapmma + blk.first_tap;
+          for (int q0 = 0; q0 < blk.ntaps; q0 += bgroup) {
+            const int gn = min(bgroup, blk.ntaps - q0);
+            ptx::mbar_wait_fast(bfull + 8 * sb, phb);
             ptx::tc_fence_after();
-            if (ptx::elect_one()) {
-              const uint32_t b_base = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
-              for (int q = 0; q < gn; ++q) {
-                const HaloTap tap = s_taps[blk.first_tap + q0 + q];
-                const uint32_t a_addr = a_base + ((P.debug & 32) ? 0u : static_cast<uint32_t>(((rad + tap.dy) * HWp + (rad + tap.dx)) * 128));
-                const uint64_t adesc = smem_desc_sw128_sbo(a_addr, (P.debug & 64) ? 1024u : sbo);
-                const uint64_t bdesc = ptx::smem_desc_sw128(b_base + q * P.b_tap_stride);
-                const int nk = (P.debug & 2) ? 0 : tap.nk;
-                for (int k = 0; k < nk; ++k) {
-                  const uint32_t accum = (first && q == 0 && k == 0) ? 0u : 1u;
-                  if constexpr (PAIR) ptx::mma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-                  else ptx::mma_bf16_ss(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
-                }
-              }
-              const bool last_grp = q0 + gn >= blk.ntaps;
+            uint64_t b_d = bdesc0 + static_cast<uint64_t>(sb * b_slot_u);
+            for (int q = 0; q < gn; ++q, b_d += b_tap_u) {
+              const uint2 ti = tp[q0 + q];
+              const uint64_t ad = a_d + ti.x;
               if constexpr (PAIR) {
-                ptx::mma_commit_pair(bempty + 8 * sb, 3);
-                if (last_grp) ptx::mma_commit_pair(aempty + 8 * sa, 3);
-                if (last_grp && bi == nblocks - 1) ptx::mma_commit_pair(tfull + 8 * acc, 3);
+                if (ti.y > 0) ptx::mma_bf16_ss_pair(tmem_d, ad, b_d, idesc, accum);
+                if (ti.y > 1) ptx::mma_bf16_ss_pair(tmem_d, ad + 2, b_d + 2, idesc, 1u);
+                if (ti.y > 2) ptx::mma_bf16_ss_pair(tmem_d, ad + 4, b_d + 4, idesc, 1u);
+                if (ti.y > 3) ptx::mma_bf16_ss_pair(tmem_d, ad + 6, b_d + 6, idesc, 1u);
               } else {
-                ptx::mma_commit(bempty + 8 * sb);
-                if (last_grp) ptx::mma_commit(aempty + 8 * sa);
-                if (last_grp && bi == nblocks - 1) ptx::mma_commit(tfull + 8 * acc);
+                if (ti.y > 0) ptx::mma_bf16_ss(tmem_d, ad, b_d, idesc, accum);
+                if (ti.y > 1) ptx::mma_bf16_ss(tmem_d, ad + 2, b_d + 2, idesc, 1u);
+                if (ti.y > 2) ptx::mma_bf16_ss(tmem_d, ad + 4, b_d + 4, idesc, 1u);
+                if (ti.y > 3) ptx::mma_bf16_ss(tmem_d, ad + 6, b_d + 6, idesc, 1u);
               }
+              accum = 1u;
             }
-            __syncwarp();
-            first = false;
+            if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, 3);
+            else ptx::mma_commit(bempty + 8 * sb);
             if (++sb == SB) { sb = 0; phb ^= 1u; }
           }
+          if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, 3);
+          else ptx::mma_commit(aempty + 8 * sa);
           if (++sa == SA) { sa = 0; pha ^= 1u; }
         }
+        if constexpr (PAIR) ptx::mma_commit_pair(tfull + 8 * acc, 3);
+        else ptx::mma_commit(tfull + 8 * acc);
       }
     }
-  } else if (warp >= 4) {
+    __syncwarp();
+  } else if (warp >= 3) {
     // ===================================== epilogue (warps 4..11) ===========================================
     const int quad = warp & 3;
-    const int half = (warp - 4) >> 2;
+    const int half = (warp - 3) >> 2;
     const int row = quad * 32 + lane;
     const int rx = row % kTW;
     const int ry = row / kTW;
@@ -276,13 +288,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         else if constexpr (G == 1) ptx::tmem_ld8(ta, r);
         else { ptx::tmem_ld8(ta, r); ptx::tmem_ld8(ta + 8, r + 8); ptx::tmem_ld8(ta + 16, r + 16); }
       };
-      if (P.fast_epi) {
+      if constexpr (FAST) {
         // ---- lean path: kind known at compile time, offsets hoisted, bias from shared memory ----
         EpiTile et;
         if (valid) et = epi_tile(P.L.epi, b, y, x, P.L.H, P.L.W);
-        const float* bias = P.L.epi.bias ? s_bias : nullptr;
+        const float* bias = s_bias;
         if (valid && ch_base + half * 8 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + half * 8, ops0);
-        ptx::mbar_wait(tfull + 8 * acc, acc_phase);
+        ptx::mbar_wait_fast(tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
         auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
           uint32_t r[8 * G];
@@ -305,7 +317,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       } else {
         // ---- generic path (ragged channel counts, channel-strided outputs) ----
         if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + half * 8, ops0);
-        ptx::mbar_wait(tfull + 8 * acc, acc_phase);
+        ptx::mbar_wait_fast(tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
         auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
           uint32_t r[8 * G];
@@ -336,7 +348,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   ptx::tc_fence_before();
   if constexpr (PAIR) ptx::cluster_sync_all();
   else __syncthreads();
-  if (warp == 3) {
+  if (warp == 2) {
     if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(P.tmem_cols));
     else ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(P.tmem_cols));
   }
@@ -378,10 +390,10 @@ int pow2_at_least(int v) {
   return p;
 }
 
-template <int KIND, bool PAIR> void launch_one(const HaloPlan& P, cudaStream_t stream) {
+template <int KIND, bool PAIR, bool FAST> void launch_one(const HaloPlan& P, cudaStream_t stream) {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(conv_halo_kernel<KIND, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(conv_halo_kernel<KIND, PAIR, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(kMaxSmem));
   });
   cudaLaunchConfig_t cfg{};
@@ -396,7 +408,7 @@ template <int KIND, bool PAIR> void launch_one(const HaloPlan& P, cudaStream_t s
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VPK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KIND, PAIR>, P));
+  VPK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KIND, PAIR, FAST>, P));
 }
 
 }  // namespace
@@ -440,7 +452,7 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   if (const char* env = getenv("VPK_HALO_BGROUP")) P.bgroup = std::max(1, atoi(env));
   P.b_slot_bytes = P.bgroup * P.b_tap_stride;
   const unsigned fixed = 1024 + 1024 + static_cast<unsigned>(nblocks) * sizeof(HaloBlock) +
-                         static_cast<unsigned>(ntaps) * sizeof(HaloTap) + static_cast<unsigned>(L.N_pad) * 4 + 128;
+                         static_cast<unsigned>(ntaps) * (sizeof(HaloTap) + 8) + static_cast<unsigned>(L.N_pad) * 4 + 160;
   // Ring depths by bytes: ~60 % of shared memory for weight tiles (4..24 slots), the rest for activation halo tiles
   // (2..8).  What matters is the number of TMA operations in flight against their ~2 us latency: small-N layers have
   // small weight tiles and get deep rings, the N = 256 gate GEMMs get 7-8 x 16 KB.
@@ -481,9 +493,14 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
 }
 
 void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
-#define VPK_HALO(KIND)                                         \
-  if (P.pair) launch_one<KIND, true>(P, stream);               \
-  else launch_one<KIND, false>(P, stream);                     \
+#define VPK_HALO(KIND)                                                                   \
+  if (P.pair) {                                                                          \
+    if (P.fast_epi) launch_one<KIND, true, true>(P, stream);                             \
+    else launch_one<KIND, true, false>(P, stream);                                       \
+  } else {                                                                               \
+    if (P.fast_epi) launch_one<KIND, false, true>(P, stream);                            \
+    else launch_one<KIND, false, false>(P, stream);                                      \
+  }                                                                                      \
   break
   switch (P.L.epi.kind) {
     case EPI_BIAS_ACT: VPK_HALO(EPI_BIAS_ACT);

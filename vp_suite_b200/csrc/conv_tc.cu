@@ -287,7 +287,7 @@ void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms) {
   const unsigned b_rows = static_cast<unsigned>(P.cta2 ? P.tileN / 2 : P.tileN);
   const unsigned stage_bytes = kAStageBytes + b_rows * 128u;
   const unsigned fixed = 1024 /*alignment slack*/ + 512 /*barriers, tmem slot*/ +
-                         static_cast<unsigned>(L.nsteps) * sizeof(ConvStep) + static_cast<unsigned>(L.N_pad) * 4 + 128;
+                         static_cast<unsigned>(L.nsteps) * (sizeof(ConvStep) + 4) + static_cast<unsigned>(L.N_pad) * 4 + 160;
   int stages = static_cast<int>((kMaxSmem - fixed) / stage_bytes);
   stages = std::max(2, std::min(stages, 8));
   stages = std::min(stages, std::max(2, L.nsteps));

@@ -30,7 +30,7 @@ __host__ __device__ constexpr int gates_of2(int kind) {
   return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
 }
 
-template <int KIND>
+template <int KIND, bool FAST>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     conv_tc2_kernel(const __grid_constant__ TcPlan P) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
@@ -54,6 +54,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * stages + 4);
   ConvStep* s_steps = reinterpret_cast<ConvStep*>(tmem_slot + 4);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_steps + P.L.nsteps) + 15) & ~uintptr_t(15));
+  int* s_nk = reinterpret_cast<int*>(s_bias + P.L.N_pad);     // K=16 slices per step, for the MMA thread
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -63,9 +64,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
   const int pair = blockIdx.x >> 1;
   const int npairs = gridDim.x >> 1;
 
-  for (int i = threadIdx.x; i < nsteps; i += kTcThreads) s_steps[i] = P.L.steps[i];
-  if (P.L.epi.bias != nullptr)
-    for (int i = threadIdx.x; i < P.L.N_pad; i += kTcThreads) s_bias[i] = P.L.epi.bias[i];
+  for (int i = threadIdx.x; i < nsteps; i += kTcThreads) {
+    const ConvStep st = P.L.steps[i];
+    s_steps[i] = st;
+    s_nk[i] = (st.kc + 15) >> 4;
+  }
+  for (int i = threadIdx.x; i < P.L.N_pad; i += kTcThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
 
   if (warp == 0 && ptx::elect_one()) {
     for (int i = 0; i < P.L.nsrc; ++i) ptx::prefetch_tensormap(&P.amap[i]);
@@ -110,7 +114,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         const int n0 = nt * tileN + static_cast<int>(rank) * halfN;
         for (int s = 0; s < nsteps; ++s) {
           const ConvStep st = s_steps[s];
-          ptx::mbar_wait(empty_bar + 8 * stage, phase ^ 1u);
+          ptx::mbar_wait_fast(empty_bar + 8 * stage, phase ^ 1u);
           const uint32_t fb = full_bar + 8 * stage;
           if (P.debug & 4) {
             if (leader) ptx::mbar_arrive(fb);
@@ -128,34 +132,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer (leader CTA only) =====================================
-    if (leader) {
+    // ONE thread runs the whole loop; descriptors advance arithmetically (16-byte units, no carry out of the field).
+    if (leader && ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_bf16_f32(256, tileN);
+      const uint64_t adesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_a));
+      const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
+      const uint32_t a_u = kAStageBytes >> 4, b_u = b_stage_bytes >> 4;
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
       for (int t = pair; t < total; t += npairs, ++iter) {
         const int acc = iter & 1;
-        const uint32_t acc_phase = (iter >> 1) & 1u;
-        ptx::mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1u);
+        ptx::mbar_wait_fast(tempty_bar + 8 * acc, ((iter >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
+        uint32_t accum = 0;
         for (int s = 0; s < nsteps; ++s) {
-          const int nk = (s_steps[s].kc + 15) >> 4;
-          ptx::mbar_wait(full_bar + 8 * stage, phase);
+          const int nk = (P.debug & 2) ? 0 : s_nk[s];
+          ptx::mbar_wait_fast(full_bar + 8 * stage, phase);
           ptx::tc_fence_after();
-          if (ptx::elect_one()) {
-            const uint64_t adesc = ptx::smem_desc_sw128(ptx::smem_u32(smem_a + stage * kAStageBytes));
-            const uint64_t bdesc = ptx::smem_desc_sw128(ptx::smem_u32(smem_b + stage * b_stage_bytes));
-            for (int k = 0; k < ((P.debug & 2) ? 0 : nk); ++k)
-              ptx::mma_bf16_ss_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (s > 0 || k > 0) ? 1u : 0u);
-            ptx::mma_commit_pair(empty_bar + 8 * stage, 3);
-            if (s == nsteps - 1) ptx::mma_commit_pair(tfull_bar + 8 * acc, 3);
-          }
-          __syncwarp();
+          const uint64_t ad = adesc0 + static_cast<uint64_t>(stage * a_u);
+          const uint64_t bd = bdesc0 + static_cast<uint64_t>(stage * b_u);
+          if (nk > 0) ptx::mma_bf16_ss_pair(tmem_d, ad, bd, idesc, accum);
+          if (nk > 1) ptx::mma_bf16_ss_pair(tmem_d, ad + 2, bd + 2, idesc, 1u);
+          if (nk > 2) ptx::mma_bf16_ss_pair(tmem_d, ad + 4, bd + 4, idesc, 1u);
+          if (nk > 3) ptx::mma_bf16_ss_pair(tmem_d, ad + 6, bd + 6, idesc, 1u);
+          accum = 1u;
+          ptx::mma_commit_pair(empty_bar + 8 * stage, 3);
           if (++stage == stages) { stage = 0; phase ^= 1u; }
         }
+        ptx::mma_commit_pair(tfull_bar + 8 * acc, 3);
       }
     }
+    __syncwarp();
   } else {
     // ===================================== epilogue (warps 2..5, both CTAs) =================================
     const int quad = warp & 3;                 // TMEM lane quadrant this warp may access
@@ -186,12 +195,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         else if constexpr (G == 1) ptx::tmem_ld8(ta, r);
         else { ptx::tmem_ld8(ta, r); ptx::tmem_ld8(ta + 8, r + 8); ptx::tmem_ld8(ta + 16, r + 16); }
       };
-      if (P.fast_epi) {
+      if constexpr (FAST) {
         EpiTile et;
         if (valid) et = epi_tile(P.L.epi, b, y, x, P.L.H, P.L.W);
-        const float* bias = P.L.epi.bias ? s_bias : nullptr;
+        const float* bias = s_bias;
         if (valid && ch_base + half * 8 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + half * 8, ops0);
-        ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        ptx::mbar_wait_fast(tfull_bar + 8 * acc, acc_phase);
         ptx::tc_fence_after();
         auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
           uint32_t r[8 * G];
@@ -213,7 +222,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         }
       } else {
         if (valid && half * 8 < Cn) epilogue_prefetch<bf16, G, 8>(P.L.epi, b, y, x, P.L.H, P.L.W, ch_base + half * 8, ops0);
-        ptx::mbar_wait(tfull_bar + 8 * acc, acc_phase);
+        ptx::mbar_wait_fast(tfull_bar + 8 * acc, acc_phase);
         ptx::tc_fence_after();
         auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
           uint32_t r[8 * G];
@@ -246,12 +255,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
 #endif
 }
 
-template <int KIND> void launch_kind(const TcPlan& P, cudaStream_t stream) {
+template <int KIND, bool FAST> void launch_kind_f(const TcPlan& P, cudaStream_t stream) {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(conv_tc2_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
+    cudaFuncSetAttribute(conv_tc2_kernel<KIND, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         static_cast<int>(kMaxSmem));
   });
-  conv_tc2_kernel<KIND><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P);
+  conv_tc2_kernel<KIND, FAST><<<P.grid, kTcThreads, P.smem_bytes, stream>>>(P);
+}
+template <int KIND> void launch_kind(const TcPlan& P, cudaStream_t stream) {
+  if (P.fast_epi) launch_kind_f<KIND, true>(P, stream);
+  else launch_kind_f<KIND, false>(P, stream);
 }
 
 }  // namespace

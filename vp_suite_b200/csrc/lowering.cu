@@ -339,7 +339,9 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       L.wpacked = q.w;
       L.K_pad = q.K_pad;
       L.epi.bias = q.bias;
-      bc.use_direct = direct_eligible(L);
+      // the CUDA-core direct kernel is for what the tensor-core path cannot address (image-channel stems) and for
+      // single-K-chunk heads; anything larger runs ~4x faster through tcgen05 even at N = 16 (profiles/)
+      bc.use_direct = direct_eligible(L) && !(backend == 0 && tc_eligible(L, dtype) && L.K_pad > 64);
       // Measured on the B200 (profiles/): with tileN >= 192 the per-tap CTA-pair kernel's mainloop is ~25 % faster than
       // the halo kernel's (weight tiles dominate the traffic there and its single ring pipelines better); for narrower N
       // the activation tile dominates and the halo kernel wins by up to 2x.

@@ -63,6 +63,25 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Hot-loop wait: a bounded spin without clock reads or printf (no stack frame, a handful of instructions), for the
+// single-thread producer / MMA-issue loops where every instruction between two tcgen05.mma counts.  A failed try_wait
+// sleeps on the barrier (NANOSLEEP.SYNCS, up to the 10 ms hint) and is woken by the phase completion, so a healthy wait
+// needs one or two tries; 8192 failed tries mean a protocol bug: trap (the launch fails) instead of hanging the device.
+__device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
+  uint32_t tries = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++tries > 8192u) __trap();
+  }
+}
+
+// Register re-allocation between warpgroups (4 consecutive warps): producers give registers to the epilogue.
+template <int N> __device__ __forceinline__ void setmaxnreg_dec() {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void setmaxnreg_inc() {
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
 // ---- TMA -------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const void* desc) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
