@@ -43,6 +43,7 @@ struct LstmArgs {
   bool order_ifog;          // true: reference rows are (i,f,o,g)
   const float *wci, *wcf, *wco;   // device fp32 [H,W,C] (or [C/4,H,W,4] when c4) or nullptr
   bool c4 = false;          // c and the peepholes use the channel-quad layout [.., C/4, H, W, 4] (needs C % 4 == 0)
+  const void* pp16 = nullptr;   // device: the three peepholes as packed bf16 [C/8][H][W][3][8] (tcgen05 epilogue), optional
 };
 inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   ConvSpec s;
@@ -76,6 +77,7 @@ inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   e.p0 = a.wci;
   e.p1 = a.wcf;
   e.p2 = a.wco;
+  e.pp16 = a.pp16;
   e.state_c4 = (a.c4 && a.C % 4 == 0) ? 1 : 0;
   dense_out(e, a.h_out, a.H, a.W, a.C);
   return s;

@@ -81,6 +81,9 @@ struct EpiParams {
   float* s1;              // ST_C: o_part (out)
   // peepholes, fp32 [H, W, C] (LSTM) or nullptr
   const float *p0, *p1, *p2;
+  // LSTM, tcgen05 path only: the same three peepholes as bf16, packed [C/8][H][W][3][8] (48 contiguous bytes per
+  // position and 8-channel chunk, positions contiguous: coalesced); nullptr: use p0..p2
+  const void* pp16;
   // secondary activation-type outputs
   void* t0;               // ST_C / ST_M: mem buffer [B,H,W,2C] (channel offset applied by caller)
   long long t0_pix;       // elements per pixel of t0 (2C)

@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "common.h"
 #include "conv_tc.h"
@@ -48,11 +49,13 @@ __host__ __device__ constexpr int gates_of(int kind) {
   return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
 }
 
-template <int KIND, bool PAIR, bool FAST>
+// MODE: 0 generic epilogue, 1 lean compile-time epilogue, 2 ConvLSTM epilogue with a whole tile of operands in flight
+template <int KIND, bool PAIR, int MODE>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloPlan P) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using bf16 = __nv_bfloat16;
   constexpr int G = gates_of(KIND);
+  constexpr bool FAST = MODE >= 1;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -268,6 +271,104 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int ry = row / kTW;
     const int Cn = tileN / G;
     int iter = 0;
+    constexpr bool rolled = (MODE == 2 && KIND == EPI_LSTM);
+    if constexpr (rolled) {
+      {
+        // ---- whole-tile operand prefetch (epilogue_tc.cuh: LstmOps) ----
+        auto run = [&](auto peep_c, auto nch_c) {
+          constexpr bool PEEP = decltype(peep_c)::value;
+          constexpr int NCH = decltype(nch_c)::value;      // this warp's chunks: channels (half + 2k) * 8 of the tile
+          constexpr int PPD = (NCH % 2 == 0) ? 2 : NCH;    // peephole prefetch distance in chunks (= ring size)
+          const EpiParams& E = P.L.epi;
+          const int C = E.C;
+          const long long hw = static_cast<long long>(P.L.H) * P.L.W;
+          LstmOps ops[NCH];
+          LstmPeep pps[PPD];
+          auto locate = [&](int t, LstmTile& et, int& chb) -> bool {
+            const int nt = t % P.n_tiles;
+            const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+            const int x = (mt % P.tiles_x) * kTW + rx;
+            const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
+            const int b = mt / (P.tiles_x * P.tiles_y);
+            chb = nt * Cn;
+            const bool ok = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
+            if (ok) et = lstm_tile(E, b, y, x, P.L.H, P.L.W);
+            return ok;
+          };
+          LstmTile et{};
+          int chb = 0;
+          bool valid = false;
+          int t = unit0;
+          if (t < total) {
+            valid = locate(t, et, chb);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const int chl = (half + 2 * k) * 8;
+              if (valid && chb + chl < C) {
+                lstm_c_load(E, et, hw, chb + chl, ops[k]);
+                if constexpr (PEEP)
+                  if (k < PPD) lstm_peep_load(E, et, hw, chb + chl, pps[k]);
+              }
+            }
+          }
+          for (; t < total; t += nunits, ++iter) {
+            LstmTile etn{};
+            int chbn = 0;
+            bool validn = false;
+            if (t + nunits < total) validn = locate(t + nunits, etn, chbn);
+            const int acc = iter & 1;
+            ptx::mbar_wait_fast(tfull + 8 * acc, (iter >> 1) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const int chl = (half + 2 * k) * 8;
+              uint32_t r[32];
+              ptx::tmem_ld32(taddr + static_cast<uint32_t>(chl * 4), r);
+              ptx::tmem_ld_wait();
+              if (valid && chb + chl < C) {
+                float a[4][8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) a[g][j] = __uint_as_float(r[j * 4 + g]);
+                lstm_finish<PEEP>(E, et, hw, chb + chl, s_bias, a, ops[k], pps[k % PPD]);
+              }
+              if (validn && chbn + chl < C) lstm_c_load(E, etn, hw, chbn + chl, ops[k]);
+              if constexpr (PEEP) {
+                const int kk = k + PPD;                    // chunk whose peepholes take this ring slot next
+                if (kk < NCH) {
+                  const int chl2 = (half + 2 * kk) * 8;
+                  if (valid && chb + chl2 < C) lstm_peep_load(E, et, hw, chb + chl2, pps[k % PPD]);
+                } else {
+                  const int chl2 = (half + 2 * (kk - NCH)) * 8;
+                  if (validn && chbn + chl2 < C) lstm_peep_load(E, etn, hw, chbn + chl2, pps[k % PPD]);
+                }
+              }
+            }
+            ptx::tc_fence_before();
+            if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+            else ptx::mbar_arrive(tempty + 8 * acc);
+            et = etn;
+            chb = chbn;
+            valid = validn;
+          }
+        };
+        auto run_n = [&](auto peep_c) {
+          switch ((Cn / 8 - half + 1) / 2) {
+            case 1: run(peep_c, std::integral_constant<int, 1>{}); break;
+            case 2: run(peep_c, std::integral_constant<int, 2>{}); break;
+            case 3: run(peep_c, std::integral_constant<int, 3>{}); break;
+            case 4: run(peep_c, std::integral_constant<int, 4>{}); break;
+            default: __trap();      // the plan only selects this kernel for 8 <= Cn <= 64
+          }
+        };
+        if (P.L.epi.pp16 != nullptr) run_n(std::true_type{});
+        else run_n(std::false_type{});
+      }
+    }
+    if constexpr (!rolled)
     for (int t = unit0; t < total; t += nunits, ++iter) {
       const int nt = t % P.n_tiles;
       const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
@@ -390,10 +491,10 @@ int pow2_at_least(int v) {
   return p;
 }
 
-template <int KIND, bool PAIR, bool FAST> void launch_one(const HaloPlan& P, cudaStream_t stream) {
+template <int KIND, bool PAIR, int MODE> void launch_one(const HaloPlan& P, cudaStream_t stream) {
   static std::once_flag once;
   std::call_once(once, [] {
-    cudaFuncSetAttribute(conv_halo_kernel<KIND, PAIR, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    cudaFuncSetAttribute(conv_halo_kernel<KIND, PAIR, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          static_cast<int>(kMaxSmem));
   });
   cudaLaunchConfig_t cfg{};
@@ -408,7 +509,7 @@ template <int KIND, bool PAIR, bool FAST> void launch_one(const HaloPlan& P, cud
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  VPK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KIND, PAIR, FAST>, P));
+  VPK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KIND, PAIR, MODE>, P));
 }
 
 }  // namespace
@@ -439,6 +540,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   P.L.epi.debug = P.debug;
   P.fast_epi = (epi_tc_fast_ok(L.epi) && gates_of(L.epi.kind) == L.G) ? 1 : 0;
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
+  P.roll = (P.fast_epi && L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) ? 1 : 0;
+  if (const char* env = getenv("VPK_EPI_ROLL")) P.roll = P.roll && atoi(env) != 0;
   P.tmem_cols = std::max(32, pow2_at_least(2 * P.tileN));
   VPK_REQUIRE(P.tmem_cols <= 512, "halo plan: accumulators exceed TMEM");
   const int HWp = kTW + 2 * radius, HHp = kTH + 2 * radius;
@@ -495,13 +598,18 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
 void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
 #define VPK_HALO(KIND)                                                                   \
   if (P.pair) {                                                                          \
-    if (P.fast_epi) launch_one<KIND, true, true>(P, stream);                             \
-    else launch_one<KIND, true, false>(P, stream);                                       \
+    if (P.fast_epi) launch_one<KIND, true, 1>(P, stream);                                \
+    else launch_one<KIND, true, 0>(P, stream);                                           \
   } else {                                                                               \
-    if (P.fast_epi) launch_one<KIND, false, true>(P, stream);                            \
-    else launch_one<KIND, false, false>(P, stream);                                      \
+    if (P.fast_epi) launch_one<KIND, false, 1>(P, stream);                               \
+    else launch_one<KIND, false, 0>(P, stream);                                          \
   }                                                                                      \
   break
+  if (P.L.epi.kind == EPI_LSTM && P.roll) {
+    if (P.pair) launch_one<EPI_LSTM, true, 2>(P, stream);
+    else launch_one<EPI_LSTM, false, 2>(P, stream);
+    return;
+  }
   switch (P.L.epi.kind) {
     case EPI_BIAS_ACT: VPK_HALO(EPI_BIAS_ACT);
     case EPI_LSTM: VPK_HALO(EPI_LSTM);

@@ -51,6 +51,7 @@ struct alignas(64) HaloPlan {
   int grid;
   int pair;                    // cta_group::2
   int fast_epi;                // lean compile-time-specialised epilogue (epilogue_tc.cuh) usable for this launch
+  int roll;                    // ConvLSTM epilogue with a whole tile of operands in flight (lstm_ops_load / lstm_finish)
   int debug;
 };
 bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps);

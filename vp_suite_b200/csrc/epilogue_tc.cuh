@@ -14,6 +14,7 @@ struct EpiTile {            // per thread, per output tile
   long long st_off;         // fp32 state tensors: offset of channel 0 at this position ...
   long long st_g;           // ... and the stride between channel quads (0: NHWC, channels contiguous)
   long long pp_off;         // peepholes (no batch dimension), same layout rule
+  int pos, hw;              // y * W + x and H * W (packed bf16 peepholes)
 };
 
 __device__ __forceinline__ EpiTile epi_tile(const EpiParams& E, int b, int y, int x, int H, int W) {
@@ -22,6 +23,8 @@ __device__ __forceinline__ EpiTile epi_tile(const EpiParams& E, int b, int y, in
   t.out_off = b * E.oB + y * E.oY + x * E.oX;
   t.pix_c = pix * E.C;
   t.pix_t0 = pix * E.t0_pix;
+  t.pos = y * W + x;
+  t.hw = H * W;
   if (E.state_c4) {
     const long long hw = static_cast<long long>(H) * W;
     const long long p = static_cast<long long>(y) * W + x;
@@ -210,6 +213,101 @@ __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile&
     for (int j = 0; j < 8; ++j) h[j] = sigmoid_fast(o.a[j] + acc[0][j]) * tanh_fast(acc[1][j]);
     st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
   }
+}
+
+// ---- ConvLSTM epilogue with the operands of a WHOLE tile in flight ----------------------------------------------
+// The gate GEMMs of the Shi et al. ConvLSTM have a short K (720 .. 1728): their epilogue (c in/out, three peepholes,
+// five transcendentals per channel) is as long as the MMA main loop, and with operands requested only one chunk ahead
+// every chunk exposed a global-memory round trip.  Here a thread keeps the cell state of all its (up to four) chunks of
+// the NEXT tile in registers: chunk k of tile i+1 is requested right after chunk k of tile i has been consumed, a
+// full tile epilogue before it is needed (HBM latency).  Peepholes (L2-resident, shared by the whole batch) come as
+// packed bf16, 12 registers per chunk, requested two chunks ahead when the chunk count is even, else a tile ahead.
+struct LstmOps {            // cell state of one 8-channel chunk ...
+  float c[8];
+};
+struct LstmPeep {           // ... and its three peepholes (bf16 x 8 each)
+  uint4 p[3];
+};
+struct LstmTile {           // per thread and tile; everything else is warp-uniform and re-derived from EpiParams
+  long long out_off;        // h' (dense NHWC, so also the offset into the optional fp32 copy h32)
+  long long st_off;         // c
+  int pos;                  // y * W + x
+};
+__device__ __forceinline__ LstmTile lstm_tile(const EpiParams& E, int b, int y, int x, int H, int W) {
+  LstmTile t;
+  t.pos = y * W + x;
+  t.out_off = b * E.oB + y * E.oY + x * E.oX;
+  const long long hw = static_cast<long long>(H) * W;
+  t.st_off = E.state_c4 ? (static_cast<long long>(b) * (E.C >> 2) * hw + t.pos) * 4 : (b * hw + t.pos) * E.C;
+  return t;
+}
+
+__device__ __forceinline__ void lstm_c_load(const EpiParams& E, const LstmTile& t, long long hw, int ch, LstmOps& o) {
+  ld_state8(E.s0, t.st_off, E.state_c4 ? hw * 4 : 0, ch, o.c);
+}
+__device__ __forceinline__ void lstm_peep_load(const EpiParams& E, const LstmTile& t, long long hw, int ch, LstmPeep& o) {
+  const uint4* p = static_cast<const uint4*>(E.pp16) + (static_cast<long long>(ch >> 3) * hw + t.pos) * 3;
+  o.p[0] = __ldg(p);
+  o.p[1] = __ldg(p + 1);
+  o.p[2] = __ldg(p + 2);
+}
+
+__device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = __bfloat1622float2(h[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+
+template <bool PEEP>
+__device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& t, long long hw, int ch,
+                                            const float* s_bias, float (&acc)[4][8], LstmOps& o, const LstmPeep& pp) {
+  using bf16 = __nv_bfloat16;
+  const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 4);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 bv = bp[j];
+    acc[0][j] += bv.x;
+    acc[1][j] += bv.y;
+    acc[2][j] += bv.z;
+    acc[3][j] += bv.w;
+  }
+  float h[8];
+  if constexpr (PEEP) {
+    // peepholes are decoded two channels at a time (one 32-bit word of each gate): 6 transient registers, not 24
+    const uint32_t* pi = reinterpret_cast<const uint32_t*>(&pp.p[0]);
+    const uint32_t* pf = reinterpret_cast<const uint32_t*>(&pp.p[1]);
+    const uint32_t* po = reinterpret_cast<const uint32_t*>(&pp.p[2]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float wi[2] = {__uint_as_float(pi[q] << 16), __uint_as_float(pi[q] & 0xFFFF0000u)};
+      const float wf[2] = {__uint_as_float(pf[q] << 16), __uint_as_float(pf[q] & 0xFFFF0000u)};
+      const float wo[2] = {__uint_as_float(po[q] << 16), __uint_as_float(po[q] & 0xFFFF0000u)};
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = 2 * q + e;
+        const float ig = sigmoid_fast(fmaf(wi[e], o.c[j], acc[0][j]));
+        const float fg = sigmoid_fast(fmaf(wf[e], o.c[j], acc[1][j]));
+        const float cn = fmaf(fg, o.c[j], ig * tanh_fast(acc[2][j]));
+        const float og = sigmoid_fast(fmaf(wo[e], cn, acc[3][j]));
+        o.c[j] = cn;
+        h[j] = og * tanh_fast(cn);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float cn = fmaf(sigmoid_fast(acc[1][j]), o.c[j], sigmoid_fast(acc[0][j]) * tanh_fast(acc[2][j]));
+      o.c[j] = cn;
+      h[j] = sigmoid_fast(acc[3][j]) * tanh_fast(cn);
+    }
+  }
+  st_state8(E.s0, t.st_off, E.state_c4 ? hw * 4 : 0, ch, o.c);
+  st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
+  if (E.h32 != nullptr) st_f32x8(E.h32 + t.out_off + ch, h);
 }
 
 }  // namespace vpk

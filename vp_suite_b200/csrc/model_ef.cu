@@ -6,6 +6,8 @@
 // l-1 at step t and its own state from step t-1, running all layers for step t and then t+1 is the same computation
 //  and keeps exactly one h/c state per layer resident.  The forecaster's top RNN is fed
 // `inputs=None` by the reference (zeros, conv_lstm_hzzone.py:54-56): its x-side K-steps are dropped.
+#include <cstring>
+
 #include "builders.h"
 #include "elementwise.h"
 #include "model.h"
@@ -103,6 +105,27 @@ class EfConvLstm : public Model {
     return out;
   }
 
+  // the three peepholes of one cell as bf16, packed [C/8][H][W][3][8] (raw bits carried in a float vector for the
+  // upload cache): what the tcgen05 epilogue reads, 48 contiguous bytes per position and 8-channel chunk
+  std::vector<float> peephole_bf16_packed(const std::string& rn, int C, int H, int W) const {
+    const char* names[3] = {"Wci", "Wcf", "Wco"};
+    std::vector<uint16_t> bits(static_cast<size_t>(C) * H * W * 3);
+    for (int k = 0; k < 3; ++k) {
+      const float* p = hp(rn + names[k]);
+      for (int c = 0; c < C; ++c)
+        for (int y = 0; y < H; ++y)
+          for (int x = 0; x < W; ++x) {
+            const __nv_bfloat16 v = __float2bfloat16_rn(p[(static_cast<size_t>(c) * H + y) * W + x]);
+            uint16_t u;
+            std::memcpy(&u, &v, 2);
+            bits[(((static_cast<size_t>(c >> 3) * H + y) * W + x) * 3 + k) * 8 + (c & 7)] = u;
+          }
+    }
+    std::vector<float> out(bits.size() / 2);
+    std::memcpy(out.data(), bits.data(), bits.size() * 2);
+    return out;
+  }
+
   void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) override {
     const vpk_model_desc& d = desc;
     const ActInfo act{dtype, esize()};
@@ -129,6 +152,7 @@ class EfConvLstm : public Model {
 
     // peepholes (device fp32 [H,W,C]); all three absent => plain gates
     const float* peep[2][3][3] = {};
+    const void* peep16[2][3] = {};
     if (!measure) {
       for (int side = 0; side < 2; ++side)
         for (int n = 0; n < 3; ++n) {
@@ -138,6 +162,8 @@ class EfConvLstm : public Model {
           const char* names[3] = {"Wci", "Wcf", "Wco"};
           for (int k = 0; k < 3; ++k)
             peep[side][n][k] = dev_f32(rn + names[k], peephole_packed(rn + names[k], C, eh[n], ew[n]), stream);
+          if (dtype == DT_BF16 && C % 8 == 0)
+            peep16[side][n] = dev_f32(rn + "peepholes.bf16", peephole_bf16_packed(rn, C, eh[n], ew[n]), stream);
         }
     }
 
@@ -174,6 +200,7 @@ class EfConvLstm : public Model {
                     cbuf[n], hp(rn + "_conv.weight"), hp(rn + "_conv.bias"), false,
                     peep[0][n][0], peep[0][n][1], peep[0][n][2]};
         la.c4 = true;
+        la.pp16 = peep16[0][n];
         add_conv(prog, lstm_spec(la, act), measure, stream);
         par[n] ^= 1;
         in = hbuf[n][par[n]];
@@ -195,6 +222,7 @@ class EfConvLstm : public Model {
                     hbuf[e][par[e]], hbuf[e][par[e] ^ 1], cbuf[e], hp(rn + "_conv.weight"), hp(rn + "_conv.bias"),
                     false, peep[1][idx - 1][0], peep[1][idx - 1][1], peep[1][idx - 1][2]};
         la.c4 = true;
+        la.pp16 = peep16[1][idx - 1];
         add_conv(prog, lstm_spec(la, act), measure, stream);
         par[e] ^= 1;
         int oh, ow;

@@ -63,14 +63,28 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
-// Hot-loop wait: a bounded spin without clock reads or printf (no stack frame, a handful of instructions), for the
-// single-thread producer / MMA-issue loops where every instruction between two tcgen05.mma counts.  A failed try_wait
-// sleeps on the barrier (NANOSLEEP.SYNCS, up to the 10 ms hint) and is woken by the phase completion, so a healthy wait
-// needs one or two tries; 8192 failed tries mean a protocol bug: trap (the launch fails) instead of hanging the device.
+// Hot-loop wait for the tcgen05 pipelines.  No suspend-time hint: with a hint a failed try_wait parks the thread
+// (NANOSLEEP.SYNCS) and the wake-up costs far more than the barrier round trip it waits for -- measured: the bare
+// barrier skeleton of the gate GEMM (no MMA, no TMA, no epilogue math) took 5.3 us per tile that way.  The default
+// try_wait returns after a short hardware-defined window, so this is a polite spin.  No clock reads or printf (no stack
+// frame).  ~2^26 failed tries (seconds) mean a protocol bug: trap, so the launch fails instead of hanging the device.
+__device__ __forceinline__ bool mbar_try_wait_nohint(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
   uint32_t tries = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++tries > 8192u) __trap();
+  while (!mbar_try_wait_nohint(bar, parity)) {
+    if (++tries > (1u << 26)) __trap();
   }
 }
 
