@@ -35,6 +35,7 @@ constexpr int kHaloThreads = 352;   // warps 0..2: activation TMA, weight TMA, M
 constexpr int kEpiThreads = 256;
 constexpr int kTW = 8, kTH = 16;
 constexpr unsigned kMaxSmem = 232448;
+constexpr uint32_t kTapFirstOfBlock = 1, kTapLastOfBlock = 2, kTapFirstOfGroup = 4, kTapLastOfGroup = 8;
 
 __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -91,9 +92,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   for (int i = threadIdx.x; i < P.ntaps; i += kHaloThreads) {
     const HaloTap tp = P.taps[i];
     s_taps[i] = tp;
+    // MMA-thread table, one entry per tap in issue order:
+    //   x = offset of the shifted activation view (16-byte units) | flags << 16 | K=16 slices << 24
+    //   y = offset of this tap's weight tile inside its ring slot (16-byte units)
+    int bi = 0;
+    while (bi + 1 < nblocks && P.blocks[bi + 1].first_tap <= i) ++bi;
+    const HaloBlock blk = P.blocks[bi];
+    const int q = i - blk.first_tap, g = q % P.bgroup;
+    uint32_t flags = 0;
+    if (q == 0) flags |= kTapFirstOfBlock;
+    if (q == blk.ntaps - 1) flags |= kTapLastOfBlock;
+    if (g == 0) flags |= kTapFirstOfGroup;
+    if (g == P.bgroup - 1 || q == blk.ntaps - 1) flags |= kTapLastOfGroup;
     const int hwp = kTW + 2 * P.P;
     const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
-    s_tapmma[i] = make_uint2(off >> 4, static_cast<uint32_t>((P.debug & 2) ? 0 : tp.nk));
+    const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk);
+    s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24), static_cast<uint32_t>(g) * (P.b_tap_stride >> 4));
   }
   for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
 
@@ -203,18 +217,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else if (warp == 2) {
     // ===================================== MMA issuer (leader CTA of a pair) ================================
-    // ONE thread runs the whole loop: between two tcgen05.mma there is a shared-memory table read, two 64-bit adds and
-    // the predicate; descriptors are advanced arithmetically (the start-address field counts 16-byte units and never
-    // carries out of its 14 bits: shared memory is < 256 KB).
+    // ONE thread runs a flat, table-driven loop over the taps of a tile (s_tapmma): per tap one 8-byte table read, at
+    // most two barrier waits, one asm block with the (up to four) tcgen05.mma of the tap, at most two commits.  Every
+    // instruction here competes for issue slots with two epilogue warps on the same scheduler, and the tensor pipe
+    // idles whenever this thread falls behind (ncu: 73 % tensor-active with the previous ~60-instruction tap).
+    // Descriptors move by their low word only (start address in 16-byte units; shared memory < 256 KB: no carry).
     if (leader && ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_bf16_f32(PAIR ? 256 : 128, tileN);
       const uint32_t sbo = (P.debug & 64) ? 1024u : static_cast<uint32_t>(HWp * 128);
       const uint64_t adesc0 = smem_desc_sw128_sbo(ptx::smem_u32(smem_a), sbo);
       const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
-      const uint32_t a_slot_u = P.a_slot_bytes >> 4, b_slot_u = P.b_slot_bytes >> 4, b_tap_u = P.b_tap_stride >> 4;
-      const int bgroup = P.bgroup;
+      const uint32_t a_hi = static_cast<uint32_t>(adesc0 >> 32), b_hi = static_cast<uint32_t>(bdesc0 >> 32);
+      const uint32_t a_lo0 = static_cast<uint32_t>(adesc0), b_lo0 = static_cast<uint32_t>(bdesc0);
+      const uint32_t a_slot_u = P.a_slot_bytes >> 4, b_slot_u = P.b_slot_bytes >> 4;
+      const int ntaps = P.ntaps;
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
+      uint32_t a_lo = a_lo0, b_lo = b_lo0;
       int iter = 0;
       for (int t = unit0; t < total; t += nunits, ++iter) {
         const int acc = iter & 1;
@@ -222,40 +241,34 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
         uint32_t accum = 0;
-        for (int bi = 0; bi < nblocks; ++bi) {
-          const HaloBlock blk = s_blocks[bi];
-          ptx::mbar_wait_fast(afull + 8 * sa, pha);
-          ptx::tc_fence_after();
-          const uint64_t a_d = adesc0 + static_cast<uint64_t>(sa * a_slot_u);
-          const uint2* tp = s_tapmma + blk.first_tap;
-          for (int q0 = 0; q0 < blk.ntaps; q0 += bgroup) {
-            const int gn = min(bgroup, blk.ntaps - q0);
+        uint2 ti = s_tapmma[0];
+        for (int i = 0; i < ntaps; ++i) {
+          const uint2 cur = ti;
+          if (i + 1 < ntaps) ti = s_tapmma[i + 1];
+          const uint32_t flags = cur.x >> 16;
+          if (flags & kTapFirstOfBlock) {
+            ptx::mbar_wait_fast(afull + 8 * sa, pha);
+            a_lo = a_lo0 + static_cast<uint32_t>(sa) * a_slot_u;
+          }
+          if (flags & kTapFirstOfGroup) {
             ptx::mbar_wait_fast(bfull + 8 * sb, phb);
-            ptx::tc_fence_after();
-            uint64_t b_d = bdesc0 + static_cast<uint64_t>(sb * b_slot_u);
-            for (int q = 0; q < gn; ++q, b_d += b_tap_u) {
-              const uint2 ti = tp[q0 + q];
-              const uint64_t ad = a_d + ti.x;
-              if constexpr (PAIR) {
-                if (ti.y > 0) ptx::mma_bf16_ss_pair(tmem_d, ad, b_d, idesc, accum);
-                if (ti.y > 1) ptx::mma_bf16_ss_pair(tmem_d, ad + 2, b_d + 2, idesc, 1u);
-                if (ti.y > 2) ptx::mma_bf16_ss_pair(tmem_d, ad + 4, b_d + 4, idesc, 1u);
-                if (ti.y > 3) ptx::mma_bf16_ss_pair(tmem_d, ad + 6, b_d + 6, idesc, 1u);
-              } else {
-                if (ti.y > 0) ptx::mma_bf16_ss(tmem_d, ad, b_d, idesc, accum);
-                if (ti.y > 1) ptx::mma_bf16_ss(tmem_d, ad + 2, b_d + 2, idesc, 1u);
-                if (ti.y > 2) ptx::mma_bf16_ss(tmem_d, ad + 4, b_d + 4, idesc, 1u);
-                if (ti.y > 3) ptx::mma_bf16_ss(tmem_d, ad + 6, b_d + 6, idesc, 1u);
-              }
-              accum = 1u;
-            }
+            b_lo = b_lo0 + static_cast<uint32_t>(sb) * b_slot_u;
+          }
+          if constexpr (PAIR)
+            ptx::mma_bf16_ss_tap_pair(tmem_d, a_lo + (cur.x & 0xFFFFu), a_hi, b_lo + cur.y, b_hi, idesc, accum, cur.x >> 24);
+          else
+            ptx::mma_bf16_ss_tap(tmem_d, a_lo + (cur.x & 0xFFFFu), a_hi, b_lo + cur.y, b_hi, idesc, accum, cur.x >> 24);
+          accum = 1u;
+          if (flags & kTapLastOfGroup) {
             if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, 3);
             else ptx::mma_commit(bempty + 8 * sb);
             if (++sb == SB) { sb = 0; phb ^= 1u; }
           }
-          if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, 3);
-          else ptx::mma_commit(aempty + 8 * sa);
-          if (++sa == SA) { sa = 0; pha ^= 1u; }
+          if (flags & kTapLastOfBlock) {
+            if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, 3);
+            else ptx::mma_commit(aempty + 8 * sa);
+            if (++sa == SA) { sa = 0; pha ^= 1u; }
+          }
         }
         if constexpr (PAIR) ptx::mma_commit_pair(tfull + 8 * acc, 3);
         else ptx::mma_commit(tfull + 8 * acc);

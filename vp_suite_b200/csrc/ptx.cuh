@@ -238,6 +238,80 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t cta_mask)
       : "memory");
 }
 
+// One tap = up to four K=16 slices issued back to back from ONE asm block (straight-line, predicated: no branches, no
+// 64-bit arithmetic in the caller).  Descriptors are passed as (low word, high word): only the low word -- start
+// address in 16-byte units -- moves between slices (+2 = 32 bytes = 16 bf16) and taps.
+__device__ __forceinline__ void mma_bf16_ss_tap(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t nk) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pacc, pt, p0, p1, p2, p3;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl;\n"
+      "setp.ne.b32 pacc, %6, 0;\n"
+      "setp.eq.b32 pt, %5, %5;\n"
+      "setp.gt.u32 p0, %7, 0;\n"
+      "setp.gt.u32 p1, %7, 1;\n"
+      "setp.gt.u32 p2, %7, 2;\n"
+      "setp.gt.u32 p3, %7, 3;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@p0 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pacc;\n"
+      "add.u32 al, %1, 2;\n"
+      "add.u32 bl, %3, 2;\n"
+      "mov.b64 da, {al, %2};\n"
+      "mov.b64 db, {bl, %4};\n"
+      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n"
+      "add.u32 al, %1, 4;\n"
+      "add.u32 bl, %3, 4;\n"
+      "mov.b64 da, {al, %2};\n"
+      "mov.b64 db, {bl, %4};\n"
+      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n"
+      "add.u32 al, %1, 6;\n"
+      "add.u32 bl, %3, 6;\n"
+      "mov.b64 da, {al, %2};\n"
+      "mov.b64 db, {bl, %4};\n"
+      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(nk)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ss_tap_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                     uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t nk) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pacc, pt, p0, p1, p2, p3;\n"
+      ".reg .b64 da, db;\n"
+      ".reg .b32 al, bl;\n"
+      "setp.ne.b32 pacc, %6, 0;\n"
+      "setp.eq.b32 pt, %5, %5;\n"
+      "setp.gt.u32 p0, %7, 0;\n"
+      "setp.gt.u32 p1, %7, 1;\n"
+      "setp.gt.u32 p2, %7, 2;\n"
+      "setp.gt.u32 p3, %7, 3;\n"
+      "mov.b64 da, {%1, %2};\n"
+      "mov.b64 db, {%3, %4};\n"
+      "@p0 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pacc;\n"
+      "add.u32 al, %1, 2;\n"
+      "add.u32 bl, %3, 2;\n"
+      "mov.b64 da, {al, %2};\n"
+      "mov.b64 db, {bl, %4};\n"
+      "@p1 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pt;\n"
+      "add.u32 al, %1, 4;\n"
+      "add.u32 bl, %3, 4;\n"
+      "mov.b64 da, {al, %2};\n"
+      "mov.b64 db, {bl, %4};\n"
+      "@p2 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pt;\n"
+      "add.u32 al, %1, 6;\n"
+      "add.u32 bl, %3, 6;\n"
+      "mov.b64 da, {al, %2};\n"
+      "mov.b64 db, {bl, %4};\n"
+      "@p3 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pt;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(nk)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 B with the 128-byte swizzle
 // (what TMA writes for a {64 x bf16, rows...} box with CU_TENSOR_MAP_SWIZZLE_128B): 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
