@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   HaloTap* s_taps = reinterpret_cast<HaloTap*>(s_blocks + P.nblocks);
   // per tap, for the MMA thread: x = offset of the shifted activation view in descriptor units (16 B), y = K=16 slices
   uint2* s_tapmma = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(s_taps + P.ntaps) + 15) & ~uintptr_t(15));
-  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapmma + P.ntaps) + 15) & ~uintptr_t(15));
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapmma + P.ntaps + 1) + 15) & ~uintptr_t(15));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -102,13 +102,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     uint32_t flags = 0;
     if (q == 0) flags |= kTapFirstOfBlock;
     if (q == blk.ntaps - 1) flags |= kTapLastOfBlock;
-    if (g == 0) flags |= kTapFirstOfGroup;
-    if (g == P.bgroup - 1 || q == blk.ntaps - 1) flags |= kTapLastOfGroup;
+    if (!P.resident) {
+      if (g == 0) flags |= kTapFirstOfGroup;
+      if (g == P.bgroup - 1 || q == blk.ntaps - 1) flags |= kTapLastOfGroup;
+    }
     const int hwp = kTW + 2 * P.P;
     const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
     const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk);
-    s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24), static_cast<uint32_t>(g) * (P.b_tap_stride >> 4));
+    s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24),
+                             static_cast<uint32_t>(P.resident ? i : g) * (P.b_tap_stride >> 4));
   }
+  if (threadIdx.x == 0) s_tapmma[P.ntaps] = make_uint2(0u, 0u);
   for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
 
   if (warp == 0 && ptx::elect_one()) {
@@ -126,7 +130,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull + 8 * i, 1);
-      ptx::mbar_init(tempty + 8 * i, prod * kEpiThreads);
+      ptx::mbar_init(tempty + 8 * i, prod * (kEpiThreads / 32));   // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int b0 = mt / (P.tiles_x * P.tiles_y);            // odd tail of a pair: b0 == B -> zero fill
         for (int bi = 0; bi < nblocks; ++bi) {
           const HaloBlock blk = s_blocks[bi];
-          ptx::mbar_wait_fast(aempty + 8 * sa, ph ^ 1u);
+          ptx::mbar_wait_spin(aempty + 8 * sa, ph ^ 1u);
           const uint32_t fb = afull + 8 * sa;
           const uint32_t dst = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
           if (P.debug & 4) {
@@ -184,7 +188,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   } else if (warp == 1) {
     // ===================================== weight producer (groups of taps per slot) ========================
-    if (ptx::elect_one()) {
+    if (P.resident) {
+      // small layers (one N tile, all taps fit): the whole packed weight matrix is loaded once and stays resident
+      if (ptx::elect_one() && unit0 < total) {
+        const int n0 = static_cast<int>(rank) * (PAIR ? rowsB : 0);
+        const uint32_t dst = ptx::smem_u32(smem_b);
+        if (P.debug & 4) {
+          if (leader) ptx::mbar_arrive(bfull); else ptx::mbar_arrive_cluster(bfull, 0);
+        } else {
+          if constexpr (PAIR) {
+            if (leader) ptx::mbar_arrive_expect_tx(bfull, ncta * b_box_bytes * P.ntaps); else ptx::mbar_arrive_cluster(bfull, 0);
+          } else {
+            ptx::mbar_arrive_expect_tx(bfull, b_box_bytes * P.ntaps);
+          }
+          for (int q = 0; q < P.ntaps; ++q) {
+            if constexpr (PAIR) ptx::tma_load_2d_pair(&P.bmap, bfull, dst + q * P.b_tap_stride, s_taps[q].wk, n0);
+            else ptx::tma_load_2d(&P.bmap, bfull, dst + q * P.b_tap_stride, s_taps[q].wk, n0);
+          }
+        }
+      }
+    } else if (ptx::elect_one()) {
       int sb = 0;
       uint32_t ph = 0;
       for (int t = unit0; t < total; t += nunits) {
@@ -193,7 +216,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const HaloBlock blk = s_blocks[bi];
           for (int q0 = 0; q0 < blk.ntaps; q0 += P.bgroup) {
             const int gn = min(P.bgroup, blk.ntaps - q0);
-            ptx::mbar_wait_fast(bempty + 8 * sb, ph ^ 1u);
+            ptx::mbar_wait_spin(bempty + 8 * sb, ph ^ 1u);
             const uint32_t fb = bfull + 8 * sb;
             const uint32_t dst = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
             if (P.debug & 4) {
@@ -227,47 +250,51 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const uint32_t sbo = (P.debug & 64) ? 1024u : static_cast<uint32_t>(HWp * 128);
       const uint64_t adesc0 = smem_desc_sw128_sbo(ptx::smem_u32(smem_a), sbo);
       const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
-      const uint32_t a_hi = static_cast<uint32_t>(adesc0 >> 32), b_hi = static_cast<uint32_t>(bdesc0 >> 32);
-      const uint32_t a_lo0 = static_cast<uint32_t>(adesc0), b_lo0 = static_cast<uint32_t>(bdesc0);
       const uint32_t a_slot_u = P.a_slot_bytes >> 4, b_slot_u = P.b_slot_bytes >> 4;
       const int ntaps = P.ntaps;
+      const uint32_t tab0 = ptx::smem_u32(s_tapmma);
       int sa = 0, sb = 0;
       uint32_t pha = 0, phb = 0;
-      uint32_t a_lo = a_lo0, b_lo = b_lo0;
+      uint64_t a_d = adesc0, b_d = bdesc0;
       int iter = 0;
+      if (P.resident && unit0 < total) ptx::mbar_wait_spin(bfull, 0);
       for (int t = unit0; t < total; t += nunits, ++iter) {
         const int acc = iter & 1;
-        ptx::mbar_wait_fast(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u);
+        ptx::mbar_wait_spin(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u);
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
         uint32_t accum = 0;
-        uint2 ti = s_tapmma[0];
+        uint32_t tab = tab0;
+        uint2 ti = ptx::lds_u2(tab);
         for (int i = 0; i < ntaps; ++i) {
           const uint2 cur = ti;
-          if (i + 1 < ntaps) ti = s_tapmma[i + 1];
+          tab += 8;
+          ti = ptx::lds_u2(tab);            // the table has one padding entry: no bounds test on the prefetch
           const uint32_t flags = cur.x >> 16;
-          if (flags & kTapFirstOfBlock) {
-            ptx::mbar_wait_fast(afull + 8 * sa, pha);
-            a_lo = a_lo0 + static_cast<uint32_t>(sa) * a_slot_u;
+          if (flags & (kTapFirstOfBlock | kTapFirstOfGroup)) {
+            if (flags & kTapFirstOfBlock) {
+              ptx::mbar_wait_spin(afull + 8 * sa, pha);
+              a_d = adesc0 + static_cast<uint32_t>(sa) * a_slot_u;
+            }
+            if (flags & kTapFirstOfGroup) {
+              ptx::mbar_wait_spin(bfull + 8 * sb, phb);
+              b_d = bdesc0 + static_cast<uint32_t>(sb) * b_slot_u;
+            }
           }
-          if (flags & kTapFirstOfGroup) {
-            ptx::mbar_wait_fast(bfull + 8 * sb, phb);
-            b_lo = b_lo0 + static_cast<uint32_t>(sb) * b_slot_u;
-          }
-          if constexpr (PAIR)
-            ptx::mma_bf16_ss_tap_pair(tmem_d, a_lo + (cur.x & 0xFFFFu), a_hi, b_lo + cur.y, b_hi, idesc, accum, cur.x >> 24);
-          else
-            ptx::mma_bf16_ss_tap(tmem_d, a_lo + (cur.x & 0xFFFFu), a_hi, b_lo + cur.y, b_hi, idesc, accum, cur.x >> 24);
+          if constexpr (PAIR) ptx::mma_bf16_ss_tap_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, cur.x >> 24);
+          else ptx::mma_bf16_ss_tap(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, cur.x >> 24);
           accum = 1u;
-          if (flags & kTapLastOfGroup) {
-            if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, 3);
-            else ptx::mma_commit(bempty + 8 * sb);
-            if (++sb == SB) { sb = 0; phb ^= 1u; }
-          }
-          if (flags & kTapLastOfBlock) {
-            if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, 3);
-            else ptx::mma_commit(aempty + 8 * sa);
-            if (++sa == SA) { sa = 0; pha ^= 1u; }
+          if (flags & (kTapLastOfGroup | kTapLastOfBlock)) {
+            if (flags & kTapLastOfGroup) {
+              if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, 3);
+              else ptx::mma_commit(bempty + 8 * sb);
+              if (++sb == SB) { sb = 0; phb ^= 1u; }
+            }
+            if (flags & kTapLastOfBlock) {
+              if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, 3);
+              else ptx::mma_commit(aempty + 8 * sa);
+              if (++sa == SA) { sa = 0; pha ^= 1u; }
+            }
           }
         }
         if constexpr (PAIR) ptx::mma_commit_pair(tfull + 8 * acc, 3);
@@ -361,8 +388,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
             }
             ptx::tc_fence_before();
-            if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
-            else ptx::mbar_arrive(tempty + 8 * acc);
+            __syncwarp();            // every lane's tcgen05.ld has completed (wait::ld) and is fenced: one arrival per warp
+            if (lane == 0) {
+              if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+              else ptx::mbar_arrive(tempty + 8 * acc);
+            }
             et = etn;
             chb = chbn;
             valid = validn;
@@ -454,8 +484,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
       ptx::tc_fence_before();
-      if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
-      else ptx::mbar_arrive(tempty + 8 * acc);
+      __syncwarp();              // one arrival per warp (512 per-thread remote arrivals per tile serialised on the barrier)
+      if (lane == 0) {
+        if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+        else ptx::mbar_arrive(tempty + 8 * acc);
+      }
     }
   }
 
@@ -567,8 +600,16 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   P.bgroup = std::max(1, std::min<int>(9, static_cast<int>(12288u / P.b_tap_stride)));
   if (const char* env = getenv("VPK_HALO_BGROUP")) P.bgroup = std::max(1, atoi(env));
   P.b_slot_bytes = P.bgroup * P.b_tap_stride;
+  // Resident weights: with one N tile and <= 96 KB of weight tiles the ring (and its per-group wait + commit in the
+  // MMA thread, which bounds these small-N layers: ~250 ns per tap whatever N is) disappears.
+  P.resident = (P.n_tiles == 1 && static_cast<unsigned>(ntaps) * P.b_tap_stride <= 96u * 1024u) ? 1 : 0;
+  if (const char* env = getenv("VPK_HALO_RESIDENT")) P.resident = P.resident && atoi(env) != 0;
+  if (P.resident) {
+    P.bgroup = ntaps;
+    P.b_slot_bytes = static_cast<unsigned>(ntaps) * P.b_tap_stride;
+  }
   const unsigned fixed = 1024 + 1024 + static_cast<unsigned>(nblocks) * sizeof(HaloBlock) +
-                         static_cast<unsigned>(ntaps) * (sizeof(HaloTap) + 8) + static_cast<unsigned>(L.N_pad) * 4 + 160;
+                         static_cast<unsigned>(ntaps) * (sizeof(HaloTap) + 8) + static_cast<unsigned>(L.N_pad) * 4 + 176;
   // Ring depths by bytes: ~60 % of shared memory for weight tiles (4..24 slots), the rest for activation halo tiles
   // (2..8).  What matters is the number of TMA operations in flight against their ~2 us latency: small-N layers have
   // small weight tiles and get deep rings, the N = 256 gate GEMMs get 7-8 x 16 KB.
@@ -576,12 +617,14 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   int sb = static_cast<int>(avail * 6 / 10 / P.b_slot_bytes);
   sb = std::max(4, std::min(24, sb));
   while (sb > 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes > avail) --sb;
-  VPK_REQUIRE(sb >= 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail, "halo plan: shared memory budget exceeded");
+  if (P.resident) sb = 1;
+  VPK_REQUIRE((sb >= 2 || P.resident) && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail,
+              "halo plan: shared memory budget exceeded");
   P.SB = sb;
   P.SA = std::max(2, std::min<int>(8, static_cast<int>((avail - P.SB * P.b_slot_bytes) / P.a_slot_bytes)));
   if (const char* env = getenv("VPK_HALO_SA")) {
     const int sa = atoi(env);
-    if (sa >= 2 && fixed + sa * P.a_slot_bytes + 2 * P.b_slot_bytes <= kMaxSmem) {
+    if (!P.resident && sa >= 2 && fixed + sa * P.a_slot_bytes + 2 * P.b_slot_bytes <= kMaxSmem) {
       P.SA = sa;
       P.SB = std::min<int>(24, static_cast<int>((avail - P.SA * P.a_slot_bytes) / P.b_slot_bytes));
     }

@@ -46,6 +46,7 @@ struct alignas(64) HaloPlan {
   unsigned a_slot_bytes, b_slot_bytes;
   unsigned b_tap_stride;       // bytes between the weight tiles of the taps sharing one slot
   int bgroup;                  // taps per weight slot
+  int resident;                // 1: every tap's weight tile is loaded ONCE per CTA and stays in shared memory (SB = 1)
   int tmem_cols;
   unsigned smem_bytes;
   int grid;

@@ -8,7 +8,7 @@
 //   full[s]   (leader only, 2 arrivals + tx bytes of both CTAs)   TMA of both CTAs -> leader's MMA warp
 //   empty[s]  (both CTAs, 1 arrival via multicast tcgen05.commit) leader's MMA     -> both producers
 //   tfull[a]  (both CTAs, multicast commit)                       leader's MMA     -> both epilogues
-//   tempty[a] (leader only, 256 arrivals)                         both epilogues   -> leader's MMA
+//   tempty[a] (leader only, 16 arrivals)                          both epilogues   -> leader's MMA
 #include <cstdio>
 #include <mutex>
 
@@ -81,7 +81,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull_bar + 8 * i, 1);
-      ptx::mbar_init(tempty_bar + 8 * i, 2 * kEpiThreads);
+      ptx::mbar_init(tempty_bar + 8 * i, 2 * (kEpiThreads / 32));   // one arrival per epilogue warp
     }
     ptx::fence_barrier_init();
   }
@@ -245,7 +245,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
         }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive_cluster(tempty_bar + 8 * acc, 0);      // the leader's MMA warp owns the accumulator hand-off
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(tempty_bar + 8 * acc, 0);   // the leader's MMA warp owns the accumulator hand-off
     }
   }
 

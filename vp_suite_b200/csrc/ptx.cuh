@@ -24,6 +24,12 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ uint2 lds_u2(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 // ---- mbarrier --------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -85,6 +91,28 @@ __device__ __forceinline__ void mbar_wait_fast(uint32_t bar, uint32_t parity) {
   uint32_t tries = 0;
   while (!mbar_try_wait_nohint(bar, parity)) {
     if (++tries > (1u << 26)) __trap();
+  }
+}
+
+// Pure spin on mbarrier.test_wait (never parks the thread): for the single-thread producer / MMA-issue loops, where
+// the wake-up latency of a parked try_wait would sit on the critical path of every pipeline hand-off.
+__device__ __forceinline__ bool mbar_test_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+  uint32_t tries = 0;
+  while (!mbar_test_wait(bar, parity)) {
+    if (++tries > (1u << 28)) __trap();
   }
 }
 
@@ -238,78 +266,91 @@ __device__ __forceinline__ void mma_commit_pair(uint32_t bar, uint16_t cta_mask)
       : "memory");
 }
 
-// One tap = up to four K=16 slices issued back to back from ONE asm block (straight-line, predicated: no branches, no
-// 64-bit arithmetic in the caller).  Descriptors are passed as (low word, high word): only the low word -- start
-// address in 16-byte units -- moves between slices (+2 = 32 bytes = 16 bf16) and taps.
-__device__ __forceinline__ void mma_bf16_ss_tap(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                                uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t nk) {
-  asm volatile(
-      "{\n"
-      ".reg .pred pacc, pt, p0, p1, p2, p3;\n"
-      ".reg .b64 da, db;\n"
-      ".reg .b32 al, bl;\n"
-      "setp.ne.b32 pacc, %6, 0;\n"
-      "setp.eq.b32 pt, %5, %5;\n"
-      "setp.gt.u32 p0, %7, 0;\n"
-      "setp.gt.u32 p1, %7, 1;\n"
-      "setp.gt.u32 p2, %7, 2;\n"
-      "setp.gt.u32 p3, %7, 3;\n"
-      "mov.b64 da, {%1, %2};\n"
-      "mov.b64 db, {%3, %4};\n"
-      "@p0 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pacc;\n"
-      "add.u32 al, %1, 2;\n"
-      "add.u32 bl, %3, 2;\n"
-      "mov.b64 da, {al, %2};\n"
-      "mov.b64 db, {bl, %4};\n"
-      "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n"
-      "add.u32 al, %1, 4;\n"
-      "add.u32 bl, %3, 4;\n"
-      "mov.b64 da, {al, %2};\n"
-      "mov.b64 db, {bl, %4};\n"
-      "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n"
-      "add.u32 al, %1, 6;\n"
-      "add.u32 bl, %3, 6;\n"
-      "mov.b64 da, {al, %2};\n"
-      "mov.b64 db, {bl, %4};\n"
-      "@p3 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, pt;\n"
-      "}\n" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(nk)
-      : "memory");
+// One tap = up to four K=16 slices issued back to back from one asm block.  The start-address field of a descriptor
+// counts 16-byte units: +2 = 32 bytes = 16 bf16 along K (no carry out of the 14-bit field: shared memory < 256 KB).
+__device__ __forceinline__ void mma_bf16_ss_tap(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate, uint32_t nk) {
+  if (nk == 4) {      // the common case, no predicates: four tcgen05.mma and six 64-bit immediate adds
+    asm volatile(
+        "{\n"
+        ".reg .pred pacc;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 pacc, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pacc;\n"
+        "add.s64 da, %1, 2;\n"
+        "add.s64 db, %2, 2;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+        "add.s64 da, %1, 4;\n"
+        "add.s64 db, %2, 4;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+        "add.s64 da, %1, 6;\n"
+        "add.s64 db, %2, 6;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred pacc, p0, p1, p2;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 pacc, %4, 0;\n"
+        "setp.gt.u32 p0, %5, 0;\n"
+        "setp.gt.u32 p1, %5, 1;\n"
+        "setp.gt.u32 p2, %5, 2;\n"
+        "@p0 tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, pacc;\n"
+        "add.s64 da, %1, 2;\n"
+        "add.s64 db, %2, 2;\n"
+        "@p1 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+        "add.s64 da, %1, 4;\n"
+        "add.s64 db, %2, 4;\n"
+        "@p2 tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %3, 1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(nk)
+        : "memory");
+  }
 }
-__device__ __forceinline__ void mma_bf16_ss_tap_pair(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                                     uint32_t b_hi, uint32_t idesc, uint32_t accumulate, uint32_t nk) {
-  asm volatile(
-      "{\n"
-      ".reg .pred pacc, pt, p0, p1, p2, p3;\n"
-      ".reg .b64 da, db;\n"
-      ".reg .b32 al, bl;\n"
-      "setp.ne.b32 pacc, %6, 0;\n"
-      "setp.eq.b32 pt, %5, %5;\n"
-      "setp.gt.u32 p0, %7, 0;\n"
-      "setp.gt.u32 p1, %7, 1;\n"
-      "setp.gt.u32 p2, %7, 2;\n"
-      "setp.gt.u32 p3, %7, 3;\n"
-      "mov.b64 da, {%1, %2};\n"
-      "mov.b64 db, {%3, %4};\n"
-      "@p0 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pacc;\n"
-      "add.u32 al, %1, 2;\n"
-      "add.u32 bl, %3, 2;\n"
-      "mov.b64 da, {al, %2};\n"
-      "mov.b64 db, {bl, %4};\n"
-      "@p1 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pt;\n"
-      "add.u32 al, %1, 4;\n"
-      "add.u32 bl, %3, 4;\n"
-      "mov.b64 da, {al, %2};\n"
-      "mov.b64 db, {bl, %4};\n"
-      "@p2 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pt;\n"
-      "add.u32 al, %1, 6;\n"
-      "add.u32 bl, %3, 6;\n"
-      "mov.b64 da, {al, %2};\n"
-      "mov.b64 db, {bl, %4};\n"
-      "@p3 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, pt;\n"
-      "}\n" ::"r"(tmem_d),
-      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate), "r"(nk)
-      : "memory");
+__device__ __forceinline__ void mma_bf16_ss_tap_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                     uint32_t accumulate, uint32_t nk) {
+  if (nk == 4) {      // the common case, no predicates: four tcgen05.mma and six 64-bit immediate adds
+    asm volatile(
+        "{\n"
+        ".reg .pred pacc;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 pacc, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pacc;\n"
+        "add.s64 da, %1, 2;\n"
+        "add.s64 db, %2, 2;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+        "add.s64 da, %1, 4;\n"
+        "add.s64 db, %2, 4;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+        "add.s64 da, %1, 6;\n"
+        "add.s64 db, %2, 6;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n"
+        ".reg .pred pacc, p0, p1, p2;\n"
+        ".reg .b64 da, db;\n"
+        "setp.ne.b32 pacc, %4, 0;\n"
+        "setp.gt.u32 p0, %5, 0;\n"
+        "setp.gt.u32 p1, %5, 1;\n"
+        "setp.gt.u32 p2, %5, 2;\n"
+        "@p0 tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, pacc;\n"
+        "add.s64 da, %1, 2;\n"
+        "add.s64 db, %2, 2;\n"
+        "@p1 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+        "add.s64 da, %1, 4;\n"
+        "add.s64 db, %2, 4;\n"
+        "@p2 tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %3, 1;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(nk)
+        : "memory");
+  }
 }
 
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 B with the 128-byte swizzle
