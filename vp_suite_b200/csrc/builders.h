@@ -151,6 +151,11 @@ struct DeconvArgs {
   long long oB_nchw = 0;
   bool split = false;         // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
   const void* x_lo = nullptr;
+  // fused 1x1 projection of the activated output to proj_n <= 4 channels (tcgen05 path, stride 1 only): `out` is then
+  // the fp32 NCHW tensor of the projection (nchw / oB_nchw describe it) and Cout never reaches memory
+  const float* proj_w = nullptr;   // device fp32 [proj_n][Cout]
+  const float* proj_b = nullptr;   // device fp32 [proj_n]
+  int proj_n = 0;
 };
 inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -175,6 +180,9 @@ inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, in
   const size_t esz = f32 ? sizeof(float) : static_cast<size_t>(act.esize);
   const long long oBn = a.oB_nchw;
   void* out = a.out;
+  const float* pw = a.proj_w;
+  const float* pb = a.proj_b;
+  const int pn = a.proj_n;
   ConvInput cin{make_view(a.x, a.H, a.W, a.Cin), 0, 0};
   if (a.split) cin.lo_view = make_view(a.x_lo, a.H, a.W, a.Cin);
   lower_conv_transpose(s, a.k, a.stride, a.pad, a.out_pad, cin, a.H, a.W,
@@ -183,6 +191,9 @@ inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, in
                          e.kind = EPI_BIAS_ACT;
                          e.act = actk;
                          e.out_f32 = f32 ? 1 : 0;
+                         e.proj_w = pw;
+                         e.proj_b = pb;
+                         e.proj_n = pn;
                          if (nchw) {   // element (b, ch, Y, X) with Y = stride*q_y + ry, X = stride*q_x + rx
                            e.out = static_cast<char*>(out) + (static_cast<size_t>(ry) * OW + rx) * esz;
                            e.oB = oBn;

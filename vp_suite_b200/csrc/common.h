@@ -99,6 +99,12 @@ struct EpiParams {
   // instead of NHWC, so that the 32 positions of a warp read/write contiguous 16-byte pieces (coalesced); needs C % 4 == 0
   int state_c4;
   int debug;              // perf experiments only (VPK_TC_DEBUG): 8 = skip activation-type stores, 16 = skip bias loads
+  // BIAS_ACT on the tcgen05 path only: a fused 1x1 projection of the activated channels to proj_n <= 4 outputs,
+  // z[p] = proj_b[p] + sum_ch proj_w[p][ch] * act(acc[ch] + bias[ch]); `out` is then the fp32 strided (NCHW frame) tensor
+  // of z and the C-channel intermediate never reaches memory (EF forecaster: last deconv + final 1x1 conv)
+  const float* proj_w;    // device fp32 [proj_n][C]
+  const float* proj_b;    // device fp32 [proj_n] or nullptr
+  int proj_n;
   // optional per-(b, group) statistics for a following GroupNorm: sums[b][g][2] (sum, sum of squares)
   float* gn_sums;
   int gn_group_size;      // channels per group (0 = disabled)

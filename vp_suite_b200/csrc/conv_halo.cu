@@ -50,13 +50,14 @@ __host__ __device__ constexpr int gates_of(int kind) {
   return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
 }
 
-// MODE: 0 generic epilogue, 1 lean compile-time epilogue, 2 ConvLSTM epilogue with a whole tile of operands in flight
+// MODE: 0 generic epilogue, 1 lean compile-time epilogue, 2 ConvLSTM epilogue with a whole tile of operands in flight,
+//       3 bias + activation + fused 1x1 projection to <= 4 channels (fp32 strided output)
 template <int KIND, bool PAIR, int MODE>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloPlan P) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using bf16 = __nv_bfloat16;
   constexpr int G = gates_of(KIND);
-  constexpr bool FAST = MODE >= 1;
+  constexpr bool FAST = MODE == 1 || MODE == 2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
@@ -80,6 +81,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint2* s_tapmma = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(s_taps + P.ntaps) + 15) & ~uintptr_t(15));
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapmma + P.ntaps + 1) + 15) & ~uintptr_t(15));
 
+  float* s_proj = s_bias + P.L.N_pad;      // MODE 3: [4][N_pad] projection weights, then 4 projection biases
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
@@ -111,6 +113,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk);
     s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24),
                              static_cast<uint32_t>(P.resident ? i : g) * (P.b_tap_stride >> 4));
+  }
+  if constexpr (MODE == 3) {
+    const int np = P.L.N_pad;
+    for (int i = threadIdx.x; i < 4 * np + 4; i += kHaloThreads) {
+      float v = 0.f;
+      if (i < 4 * np) {
+        const int pr = i / np, ch = i - pr * np;
+        if (pr < P.L.epi.proj_n && ch < P.L.epi.C) v = P.L.epi.proj_w[pr * P.L.epi.C + ch];
+      } else if (P.L.epi.proj_b != nullptr && i - 4 * np < P.L.epi.proj_n) {
+        v = P.L.epi.proj_b[i - 4 * np];
+      }
+      s_proj[i] = v;
+    }
   }
   if (threadIdx.x == 0) s_tapmma[P.ntaps] = make_uint2(0u, 0u);
   for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
@@ -411,7 +426,53 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         else run_n(std::false_type{});
       }
     }
-    if constexpr (!rolled)
+    if constexpr (MODE == 3) {
+      // ---- bias + activation + 1x1 projection: one warp per TMEM quadrant reads all channels of its positions ----
+      const EpiParams& E = P.L.epi;
+      const int np = P.L.N_pad;
+      for (int t = unit0; t < total; t += nunits, ++iter) {
+        const int mt = t * (PAIR ? 2 : 1) + static_cast<int>(rank);          // n_tiles == 1
+        const int x = (mt % P.tiles_x) * kTW + rx;
+        const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
+        const int b = mt / (P.tiles_x * P.tiles_y);
+        const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
+        const int acc = iter & 1;
+        ptx::mbar_wait_fast(tfull + 8 * acc, (iter >> 1) & 1u);
+        ptx::tc_fence_after();
+        if (half == 0) {
+          const uint32_t taddr =
+              tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
+          float z[4] = {s_proj[4 * np], s_proj[4 * np + 1], s_proj[4 * np + 2], s_proj[4 * np + 3]};
+          for (int ch = 0; ch < Cn; ch += 8) {
+            uint32_t r[8];
+            ptx::tmem_ld8(taddr + static_cast<uint32_t>(ch), r);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float v = __uint_as_float(r[j]) + s_bias[ch + j];
+              if (E.act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
+              else if (E.act == ACT_RELU) v = fmaxf(v, 0.f);
+              else if (E.act == ACT_SIGMOID) v = sigmoid_fast(v);
+#pragma unroll
+              for (int pr = 0; pr < 4; ++pr) z[pr] = fmaf(s_proj[pr * np + ch + j], v, z[pr]);
+            }
+          }
+          if (valid) {
+            float* o = static_cast<float*>(E.out) + b * E.oB + y * E.oY + x * E.oX;
+#pragma unroll
+            for (int pr = 0; pr < 4; ++pr)
+              if (pr < E.proj_n) o[pr * E.oC] = z[pr];
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+          else ptx::mbar_arrive(tempty + 8 * acc);
+        }
+      }
+    }
+    if constexpr (!rolled && MODE != 3)
     for (int t = unit0; t < total; t += nunits, ++iter) {
       const int nt = t % P.n_tiles;
       const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
@@ -562,6 +623,7 @@ template <int KIND, bool PAIR, int MODE> void launch_one(const HaloPlan& P, cuda
 
 bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps) {
   if (!tc_eligible(L, dtype)) return false;
+  if (L.epi.proj_n > 0 && (L.epi.kind != EPI_BIAS_ACT || L.epi.proj_n > 4 || L.N_pad != L.Cn || L.Cn > 256)) return false;
   return radius >= 0 && radius <= 3 && nblocks >= 1 && nblocks <= 64 && ntaps <= kMaxSteps;
 }
 
@@ -609,7 +671,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
     P.b_slot_bytes = static_cast<unsigned>(ntaps) * P.b_tap_stride;
   }
   const unsigned fixed = 1024 + 1024 + static_cast<unsigned>(nblocks) * sizeof(HaloBlock) +
-                         static_cast<unsigned>(ntaps) * (sizeof(HaloTap) + 8) + static_cast<unsigned>(L.N_pad) * 4 + 176;
+                         static_cast<unsigned>(ntaps) * (sizeof(HaloTap) + 8) + static_cast<unsigned>(L.N_pad) * 4 + 176 +
+                         (L.epi.proj_n > 0 ? static_cast<unsigned>(L.N_pad) * 16 + 16 : 0u);
   // Ring depths by bytes: ~60 % of shared memory for weight tiles (4..24 slots), the rest for activation halo tiles
   // (2..8).  What matters is the number of TMA operations in flight against their ~2 us latency: small-N layers have
   // small weight tiles and get deep rings, the N = 256 gate GEMMs get 7-8 x 16 KB.
@@ -661,6 +724,11 @@ void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
     else launch_one<KIND, false, 0>(P, stream);                                          \
   }                                                                                      \
   break
+  if (P.L.epi.kind == EPI_BIAS_ACT && P.L.epi.proj_n > 0) {
+    if (P.pair) launch_one<EPI_BIAS_ACT, true, 3>(P, stream);
+    else launch_one<EPI_BIAS_ACT, false, 3>(P, stream);
+    return;
+  }
   if (P.L.epi.kind == EPI_LSTM && P.roll) {
     if (P.pair) launch_one<EPI_LSTM, true, 2>(P, stream);
     else launch_one<EPI_LSTM, false, 2>(P, stream);

@@ -349,11 +349,17 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       // (conv_halo.cu, MODE 2) more than makes up for it.
       const bool wide = L.Cn * L.G >= 192;
       const bool lstm256 = L.epi.kind == EPI_LSTM && L.Cn * L.G == 256 && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr);
-      bool prefer_halo = !wide || lstm256;
+      bool prefer_halo = !wide || lstm256 || L.epi.proj_n > 0;
       if (const char* env = getenv("VPK_TC_HALO")) prefer_halo = atoi(env) != 0;
       bc.use_halo = !bc.use_direct && (backend == 0) && prefer_halo &&
                     halo_eligible(L, dtype, q.radius, q.nblocks, q.ntaps);
       bc.use_tc = !bc.use_direct && !bc.use_halo && (backend == 0) && tc_eligible(L, dtype);
+      if (L.epi.proj_n > 0) {
+        bc.use_direct = false;
+        bc.use_halo = (backend == 0) && halo_eligible(L, dtype, q.radius, q.nblocks, q.ntaps);
+        bc.use_tc = false;
+        VPK_REQUIRE(bc.use_halo, "fused projection epilogue needs the tcgen05 halo kernel for " + spec.name);
+      }
       if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);
       if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);
     }

@@ -6,6 +6,7 @@
 // l-1 at step t and its own state from step t-1, running all layers for step t and then t+1 is the same computation
 //  and keeps exactly one h/c state per layer resident.  The forecaster's top RNN is fed
 // `inputs=None` by the reference (zeros, conv_lstm_hzzone.py:54-56): its x-side K-steps are dropped.
+#include <cstdlib>
 #include <cstring>
 
 #include "builders.h"
@@ -183,6 +184,10 @@ class EfConvLstm : public Model {
     }
 
     int par[3] = {0, 0, 0};
+    // tcgen05 path only (the CUDA-core kernels keep the two launches): stride-1 last deconv, <= 4 image channels
+    const bool fuse_final = dtype == DT_BF16 && backend == 0 && d.dec_conv_s[2] == 1 && c <= 4 &&
+                            d.dec_c[4] % 8 == 0 && d.dec_c[5] % 8 == 0 && d.dec_c[5] <= 64 && d.final_conv_c == d.dec_c[5] &&
+                            getenv("VPK_EF_NO_FUSE") == nullptr;
     // ------------------------------------------ encoder (ef_blocks.py:67-82) ---------------------------------
     for (int t = 0; t < t_in; ++t) {
       const void* in = frames_in + static_cast<size_t>(t) * frame_px * c * esz;
@@ -228,10 +233,26 @@ class EfConvLstm : public Model {
         int oh, ow;
         DeconvArgs da{st, B, dh[n], dw[n], mid, outc, d.dec_conv_k[n], d.dec_conv_s[n], d.dec_conv_p[n], 0,
                       hbuf[e][par[e]], hp(st + "weight"), hp(st + "bias"), d.ef_act, ybuf[n]};
+        if (n == 2 && fuse_final) {
+          // last deconv + LeakyReLU + final 1x1 conv (ef_conv_lstm.py:99-104) in one launch: the 16-channel map stays
+          // in registers and the fp32 NCHW frame t of the staging tensor is written directly
+          da.name = st + "final_fused.";
+          da.out = out_stage + static_cast<size_t>(t) * c * h * w;
+          da.nchw = true;
+          da.oB_nchw = static_cast<long long>(pred) * c * h * w;
+          da.proj_n = c;
+          if (!measure) {
+            const HostParam& fw = params.at("forecaster.stage1.final.weight");
+            const HostParam& fb = params.at("forecaster.stage1.final.bias");
+            da.proj_w = dev_f32("forecaster.stage1.final.weight", fw.data, stream);
+            da.proj_b = dev_f32("forecaster.stage1.final.bias", fb.data, stream);
+          }
+        }
         add_conv(prog, deconv_spec(da, act, &oh, &ow), measure, stream);
         VPK_REQUIRE(oh == dh[n + 1] && ow == dw[n + 1], "forecaster stage size mismatch");
         in = ybuf[n];
       }
+      if (fuse_final) continue;
       // identity + final 1x1 conv (ef_conv_lstm.py:99-104), written as fp32 NCHW frame t of the staging tensor
       int oh, ow;
       ConvArgs fa{"forecaster.stage1.final.", B, h, w, d.final_conv_c, c, 1, 1, 0, ybuf[2],
