@@ -261,10 +261,20 @@ def main():
     peaks, peak_kind = load_peaks()
     peak = peaks.get("bf16_tflops_sustained" if ms_per_step > 50 else "bf16_tflops", 1590.0)
     achieved = gs["flops"] / max(gs["ms"], 1e-9) * 1e-9 if gs["launches"] else 0.0     # TFLOP/s
+    traffic, traffic_note = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath) and args.workload == "cfg5":
+        with open(tpath) as f:
+            tj = json.load(f)["cfg5"]
+        mb = model.microbatch_size(B)
+        traffic = tj["dram_bytes_in_capture"] / tj["sequences_in_capture"] * mb
+        traffic_note = (f"DRAM bytes per launch of {tj['kernel']} at this run's microbatch of {mb} sequences, scaled from the "
+                        f"ncu capture at {tj['sequences_in_capture']} sequences (profiles/r01_ncu_halo_rnn1_deconv3_cfg5_b64.md); "
+                        f"algorithmic bytes of that launch = {tj['algorithmic_bytes_per_position'] * tj['positions_per_sequence'] * mb:.3e}")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak if peak else None, "traffic": None,
-                "kernel": "conv_tc_kernel<4> (ConvLSTM gate GEMM + fused update)" if key != "predrnn-pp"
-                else "conv_tc_kernel<G> (ST-LSTM gate GEMMs + fused update)",
+                "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
+                "kernel": "conv_halo_kernel / conv_tc2_kernel <EPI_LSTM> (tcgen05 ConvLSTM gate GEMMs + fused state update)"
+                if key != "predrnn-pp" else "conv_tc2_kernel / conv_halo_kernel <EPI_ST_*> (tcgen05 ST-LSTM gate GEMMs + fused update)",
                 "gemm_launches_per_step": gs["launches"], "gemm_ms_per_step": gs["ms"],
                 "gemm_share_of_step": gs["ms"] / ms_per_step if ms_per_step else None,
                 "algorithmic_gflop_per_step": gs["flops"] * 1e-9,

@@ -109,6 +109,9 @@ int vpk_model_forward(vpk_model* m, const float* x, int32_t batch, int32_t t_in,
 int vpk_model_forward_host(vpk_model* m, const float* x_host, int32_t batch, int32_t t_in, int32_t pred_frames,
                            float* out_host, float* aux_host);
 
+/* Sequences the library processes per pass over the layers (its microbatch) for a call with `batch` sequences. */
+int vpk_model_microbatch(vpk_model* m, int32_t batch, int32_t* sequences);
+
 /* Number of kernel launches (the library's own kernels) enqueued by the last forward call. */
 int vpk_model_last_launch_count(vpk_model* m, int64_t* launches);
 

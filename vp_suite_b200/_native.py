@@ -51,6 +51,7 @@ SYMBOLS = {
     "vpk_model_workspace_bytes": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "vpk_model_forward": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vpk_model_forward_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "vpk_model_microbatch": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int32)]),
     "vpk_model_last_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "vpk_model_set_timing": (C.c_int, [_vp, C.c_int32]),
     "vpk_model_last_gemm_ms": (C.c_int, [_vp, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_double)]),

@@ -219,6 +219,12 @@ class NativeRollout:
     def _native_t_in(self, t_total, pred_frames):
         return t_total
 
+    def microbatch_size(self, batch):
+        """Sequences per pass over the layers for a call with ``batch`` sequences."""
+        n = C.c_int32()
+        N.check(N.lib().vpk_model_microbatch(self._native_handle(), int(batch), C.byref(n)))
+        return n.value
+
     def last_launch_count(self):
         n = C.c_int64()
         N.check(N.lib().vpk_model_last_launch_count(self._native_handle(), C.byref(n)))

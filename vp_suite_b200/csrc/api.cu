@@ -125,6 +125,13 @@ int vpk_model_forward_host(vpk_model* m, const float* x_host, int32_t batch, int
   });
 }
 
+int vpk_model_microbatch(vpk_model* m, int32_t batch, int32_t* sequences) {
+  return guarded([&] {
+    VPK_REQUIRE(m && sequences && batch > 0, "bad argument");
+    *sequences = m->impl->microbatch(batch);
+  });
+}
+
 int vpk_model_last_launch_count(vpk_model* m, int64_t* launches) {
   return guarded([&] {
     VPK_REQUIRE(m && launches, "null argument");

@@ -144,8 +144,12 @@ void Model::add_memset(Program& prog, void* p, size_t bytes, const char* name) {
 }
 
 int Model::microbatch(int batch) const {
+  // balanced: the fewest passes the cap allows, then equal shares (512 with a cap of 222 -> 171 + 171 + 170, not
+  // 222 + 222 + 68: a short tail pass runs the persistent kernels at a fraction of their steady-state efficiency)
   int mb = desc.max_microbatch > 0 ? desc.max_microbatch : default_microbatch();
-  return std::max(1, std::min(mb, batch));
+  mb = std::max(1, std::min(mb, batch));
+  const int passes = (batch + mb - 1) / mb;
+  return (batch + passes - 1) / passes;
 }
 
 size_t Model::workspace_bytes(int batch, int t_in, int pred) {

@@ -60,6 +60,8 @@ class Model {
                cudaStream_t stream);
   void forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux);
 
+  int microbatch(int batch) const;
+
   vpk_model_desc desc;
   std::vector<std::string> keys;
   std::map<std::string, HostParam> params;
@@ -101,7 +103,6 @@ class Model {
  private:
   Program* get_program(int B, int t_in, int pred, void* ws, size_t ws_bytes, cudaStream_t stream);
   void run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx);
-  int microbatch(int batch) const;
   std::vector<std::unique_ptr<Program>> programs;
   // gate-GEMM timing
   std::vector<cudaEvent_t> ev_pool;
