@@ -105,28 +105,54 @@ __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
 // PredRNN-V2 decoupling loss term (models/predrnn_v2.py:197-211): ad = adapter(delta) as fp32 [2B][HW][C] with
 // delta_c in the first B samples and delta_m in the last B.  Per (b, ch): |cos| between the two HW-vectors, each
 // L2-normalised first (F.normalize eps 1e-12).  Adds sum over (b, ch) to *acc.
-__global__ void decouple_reduce_kernel(const float* __restrict__ ad, int B, int HW, int C, double* acc) {
+// Thread layout: 32 channel quads (float4, coalesced 512-byte rows) x 8 position slices per block of 256 threads; the
+// slices are combined through shared memory, then one warp finishes |cos| and the block adds one fp64 atomic.
+__global__ void __launch_bounds__(256) decouple_reduce_kernel(const float* __restrict__ ad, int B, int HW, int C,
+                                                              double* acc) {
+  __shared__ float s_part[8][3][128];
   const int b = blockIdx.x;
-  const int ch = blockIdx.y * 128 + threadIdx.x;
-  float v = 0.f;
+  const int q = threadIdx.x & 31;            // channel quad inside this block's 128-channel range
+  const int sl = threadIdx.x >> 5;           // position slice
+  const int ch = blockIdx.y * 128 + q * 4;
+  float dot[4] = {0.f, 0.f, 0.f, 0.f}, nc[4] = {0.f, 0.f, 0.f, 0.f}, nm[4] = {0.f, 0.f, 0.f, 0.f};
   if (ch < C) {
     const float* pc = ad + static_cast<size_t>(b) * HW * C + ch;
     const float* pm = ad + (static_cast<size_t>(B) + b) * HW * C + ch;
-    float dot = 0.f, nc = 0.f, nm = 0.f;
-    for (int p = 0; p < HW; ++p) {
-      const float a = pc[static_cast<size_t>(p) * C], m = pm[static_cast<size_t>(p) * C];
-      dot = fmaf(a, m, dot);
-      nc = fmaf(a, a, nc);
-      nm = fmaf(m, m, nm);
+    for (int p = sl; p < HW; p += 8) {
+      const float4 a = *reinterpret_cast<const float4*>(pc + static_cast<size_t>(p) * C);
+      const float4 m = *reinterpret_cast<const float4*>(pm + static_cast<size_t>(p) * C);
+      dot[0] = fmaf(a.x, m.x, dot[0]); nc[0] = fmaf(a.x, a.x, nc[0]); nm[0] = fmaf(m.x, m.x, nm[0]);
+      dot[1] = fmaf(a.y, m.y, dot[1]); nc[1] = fmaf(a.y, a.y, nc[1]); nm[1] = fmaf(m.y, m.y, nm[1]);
+      dot[2] = fmaf(a.z, m.z, dot[2]); nc[2] = fmaf(a.z, a.z, nc[2]); nm[2] = fmaf(m.z, m.z, nm[2]);
+      dot[3] = fmaf(a.w, m.w, dot[3]); nc[3] = fmaf(a.w, a.w, nc[3]); nm[3] = fmaf(m.w, m.w, nm[3]);
     }
-    v = fabsf(dot) / (fmaxf(sqrtf(nc), 1e-12f) * fmaxf(sqrtf(nm), 1e-12f));
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  __shared__ float ws[4];
-  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+  for (int j = 0; j < 4; ++j) {
+    s_part[sl][0][q * 4 + j] = dot[j];
+    s_part[sl][1][q * 4 + j] = nc[j];
+    s_part[sl][2][q * 4 + j] = nm[j];
+  }
   __syncthreads();
-  if (threadIdx.x == 0) atomicAdd(acc, static_cast<double>(ws[0] + ws[1] + ws[2] + ws[3]));
+  if (threadIdx.x < 128) {
+    const int c = threadIdx.x;
+    float d = 0.f, a = 0.f, m = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      d += s_part[k][0][c];
+      a += s_part[k][1][c];
+      m += s_part[k][2][c];
+    }
+    float v = 0.f;
+    if (blockIdx.y * 128 + c < C) v = fabsf(d) / (fmaxf(sqrtf(a), 1e-12f) * fmaxf(sqrtf(m), 1e-12f));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __shared__ float ws[4];
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncwarp();
+    asm volatile("bar.sync 1, 128;");
+    if (threadIdx.x == 0) atomicAdd(acc, static_cast<double>(ws[0] + ws[1] + ws[2] + ws[3]));
+  }
 }
 
 // GroupNorm (+ optional LeakyReLU(0.2), + optional residual add) over one sample per CTA, NHWC.
@@ -354,8 +380,9 @@ void launch_cast_f32_to_bf16(const float* in, void* out, long long n, int num_sm
 }
 
 void launch_decouple_reduce(const float* ad, int B, int HW, int C, double* acc, cudaStream_t stream) {
+  VPK_REQUIRE(C % 4 == 0, "decouple_reduce: channel count must be a multiple of 4");
   dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>((C + 127) / 128));
-  decouple_reduce_kernel<<<grid, 128, 0, stream>>>(ad, B, HW, C, acc);
+  decouple_reduce_kernel<<<grid, 256, 0, stream>>>(ad, B, HW, C, acc);
   VPK_CUDA(cudaGetLastError());
 }
 
