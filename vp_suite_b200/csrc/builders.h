@@ -99,6 +99,7 @@ struct ConvArgs {
   const float* res = nullptr;   // fp32 dense [B, OH, OW, Cout] residual added after the activation
   bool split = false;           // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
   const void* x_lo = nullptr;
+  int cin_w = -1;               // input channels the weight tensor really has (-1: Cin); x may carry zero padding channels
 };
 inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -109,7 +110,7 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
   WeightRef w;
   w.w = a.weight;
   w.O = a.Cout;
-  w.I = a.Cin;
+  w.I = a.cin_w > 0 ? a.cin_w : a.Cin;
   w.KH = w.KW = a.k;
   s.wrefs.push_back(w);
   if (a.bias) {
@@ -118,6 +119,7 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
     s.biases.push_back(b);
   }
   ConvInput in{make_view(a.x, a.H, a.W, a.Cin), 0, 0};
+  in.wc_count = a.cin_w;
   if (a.split) in.lo_view = make_view(a.x_lo, a.H, a.W, a.Cin);
   lower_conv(s, a.k, a.stride, a.pad, {in}, a.H, a.W, act.esize, oh, ow);
   EpiParams& e = s.phases[0].epi;

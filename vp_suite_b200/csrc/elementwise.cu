@@ -35,6 +35,33 @@ __global__ void frames_to_nhwc_kernel(const float* __restrict__ x, long long bst
   }
 }
 
+// x fp32 [B, T, C, H, W] -> bf16 [T][B][H][W][8] with channels C..7 zero: one 16-byte store per pixel, and the frame
+// becomes TMA-addressable (16-byte pixel stride), so the image-channel stem convs run on the tensor-core kernel.
+// `lo` != nullptr: split-bf16, hi = bf16(v) and lo = bf16(v - hi) in two tensors of the same layout.
+__global__ void frames_to_nhwc8_kernel(const float* __restrict__ x, long long bstride, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo, int B, int Tn, int C, int H, int W) {
+  const long long HW = static_cast<long long>(H) * W;
+  const long long total = static_cast<long long>(B) * Tn * HW;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i % HW;
+    const long long bt = i / HW;
+    const int t = static_cast<int>(bt % Tn);
+    const int b = static_cast<int>(bt / Tn);
+    const float* src = x + static_cast<long long>(b) * bstride + static_cast<long long>(t) * C * HW + p;
+    __align__(16) __nv_bfloat16 vh[8], vl[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float v = (c < C) ? src[c * HW] : 0.f;
+      vh[c] = __float2bfloat16_rn(v);
+      vl[c] = __float2bfloat16_rn(v - __bfloat162float(vh[c]));
+    }
+    const long long o = ((static_cast<long long>(t) * B + b) * HW + p);
+    reinterpret_cast<uint4*>(hi)[o] = *reinterpret_cast<const uint4*>(vh);
+    if (lo != nullptr) reinterpret_cast<uint4*>(lo)[o] = *reinterpret_cast<const uint4*>(vl);
+  }
+}
+
 // PredRNN patchify (models/predrnn_v2.py:232-240): x fp32 [B, T, c, H, W] -> out T [T][B][H/p][W/p][p*p*c],
 // patch-channel order (p_h, p_w, c).
 template <typename T>
@@ -366,6 +393,15 @@ void launch_frames_to_nhwc_strided(const float* x, long long bstride, void* out,
   else
     frames_to_nhwc_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C,
                                                                H, W);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_frames_to_nhwc8(const float* x, long long bstride, void* hi, void* lo, int B, int T, int C, int H, int W,
+                            int num_sms, cudaStream_t stream) {
+  VPK_REQUIRE(C >= 1 && C <= 8, "frames_to_nhwc8: 1..8 image channels");
+  const long long total = static_cast<long long>(B) * T * H * W;
+  frames_to_nhwc8_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(
+      x, bstride, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, T, C, H, W);
   VPK_CUDA(cudaGetLastError());
 }
 

@@ -9,6 +9,10 @@ namespace vpk {
 // x fp32 [B, T, C, H, W] -> out (activation type) [T][B][H][W][C]
 void launch_frames_to_nhwc(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int num_sms,
                            cudaStream_t stream);
+// x fp32 [B, *, C, H, W] (sequence stride `bstride` elements), first T frames -> bf16 [T][B][H][W][8], channels C..7
+// zero (TMA-addressable frames); lo != nullptr: split-bf16 (hi, lo) pair
+void launch_frames_to_nhwc8(const float* x, long long bstride, void* hi, void* lo, int B, int T, int C, int H, int W,
+                            int num_sms, cudaStream_t stream);
 // PredRNN patchify: the first T frames of x fp32 [B, *, c, H, W] (sequence stride `bstride` elements)
 // -> out [T][B][H/p][W/p][p*p*c]
 void launch_patchify_strided(const float* x, long long bstride, void* out, int dtype, int B, int T, int C, int H, int W,

@@ -134,7 +134,10 @@ class EfConvLstm : public Model {
     const int c = d.img_c, h = d.img_h, w = d.img_w;
     const size_t frame_px = static_cast<size_t>(B) * h * w;
 
-    char* frames_in = static_cast<char*>(arena.alloc(frame_px * c * esz * t_in));
+    // tcgen05 path: frames are stored with 8 channels per pixel (zero padded) so that the stem conv is TMA-addressable
+    const bool pad8 = dtype == DT_BF16 && backend == 0 && c <= 8 && getenv("VPK_NO_PAD8") == nullptr;
+    const int cs = pad8 ? 8 : c;
+    char* frames_in = static_cast<char*>(arena.alloc(frame_px * cs * esz * t_in));
     float* out_stage = static_cast<float*>(arena.alloc(frame_px * c * sizeof(float) * pred));
 
     void* xin[3];
@@ -173,7 +176,10 @@ class EfConvLstm : public Model {
       Op pre;
       pre.name = "frames_to_nhwc";
       pre.fn = [=](cudaStream_t s, const RunCtx& ctx) {
-        launch_frames_to_nhwc(ctx.x, frames_in, dt, B, t_in, c, h, w, ns, s);
+        if (pad8)
+          launch_frames_to_nhwc8(ctx.x, static_cast<long long>(t_in) * c * h * w, frames_in, nullptr, B, t_in, c, h, w, ns, s);
+        else
+          launch_frames_to_nhwc(ctx.x, frames_in, dt, B, t_in, c, h, w, ns, s);
       };
       prog.pre.push_back(std::move(pre));
       for (int n = 0; n < 3; ++n) {
@@ -190,8 +196,8 @@ class EfConvLstm : public Model {
                             getenv("VPK_EF_NO_FUSE") == nullptr;
     // ------------------------------------------ encoder (ef_blocks.py:67-82) ---------------------------------
     for (int t = 0; t < t_in; ++t) {
-      const void* in = frames_in + static_cast<size_t>(t) * frame_px * c * esz;
-      int in_h = h, in_w = w, in_c = c;
+      const void* in = frames_in + static_cast<size_t>(t) * frame_px * cs * esz;
+      int in_h = h, in_w = w, in_c = cs;
       for (int n = 0; n < 3; ++n) {
         const std::string st = "encoder.stage" + std::to_string(n + 1) + ".conv.";
         const std::string rn = "encoder.rnn" + std::to_string(n + 1) + ".";
@@ -199,6 +205,7 @@ class EfConvLstm : public Model {
         int oh, ow;
         ConvArgs ca{st, B, in_h, in_w, in_c, mid, d.enc_conv_k[n], d.enc_conv_s[n], d.enc_conv_p[n], in,
                     hp(st + "weight"), hp(st + "bias"), d.ef_act, xin[n]};
+        if (n == 0) ca.cin_w = c;
         add_conv(prog, conv_spec(ca, act, &oh, &ow), measure, stream);
         VPK_REQUIRE(oh == eh[n] && ow == ew[n], "encoder stage size mismatch");
         LstmArgs la{rn, B, eh[n], ew[n], mid, outc, d.enc_rnn_k[n], xin[n], hbuf[n][par[n]], hbuf[n][par[n] ^ 1],

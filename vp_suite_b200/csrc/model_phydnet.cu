@@ -129,9 +129,21 @@ class PhyDNetModel : public Model {
       }
       return f;
     };
-    float* frames_in = static_cast<float*>(arena.alloc(px1 * c * 4 * t_in));
+    // split mode: frames as split-bf16 with 8 channels per pixel (zero padded): TMA-addressable, so encoder_E.c1 runs on
+    // the tensor cores like every other conv; fp32 mode: plain fp32 NHWC frames for the CUDA-core kernel
+    const bool pad8 = split && backend == 0 && c <= 8;
+    const int cs = pad8 ? 8 : c;
+    Feat frames_in, frame_fb;            // [t_in] frames / the fed-back frame
+    if (pad8) {
+      frames_in.a = arena.alloc(px1 * 8 * 2 * t_in);
+      frames_in.lo = arena.alloc(px1 * 8 * 2 * t_in);
+      frame_fb.a = arena.alloc(px1 * 8 * 2);
+      frame_fb.lo = arena.alloc(px1 * 8 * 2);
+    } else {
+      frames_in.a = arena.alloc(px1 * c * 4 * t_in);
+      frame_fb.a = arena.alloc(px1 * c * 4);
+    }
     float* out_stage = static_cast<float*>(arena.alloc(px1 * c * 4 * pred));
-    float* frame_fb = static_cast<float*>(arena.alloc(px1 * c * 4));          // fed-back frame, NHWC
     float* raw = static_cast<float*>(arena.alloc(std::max(px2 * 32, px4 * 64) * 4));   // pre-GroupNorm conv output
     Feat e1 = feat(px2 * 32), e2 = feat(px2 * 32), e3 = feat(px4 * 64), mid = feat(px4 * 64);
     void* ep = arena.alloc(px4 * 64 * esz_c);
@@ -192,7 +204,7 @@ class PhyDNetModel : public Model {
     // DCGANConv / DCGANConvTranspose: conv -> GroupNorm(16) -> LeakyReLU(0.2)   (model_blocks/conv.py:58-95)
     // `in_f32`: the input is a plain fp32 tensor (image frames: CUDA-core kernel), otherwise a feature map
     auto dcgan = [&](const std::string& p, bool transpose, Feat in, bool in_f32, int H, int W, int Cin, int Cout,
-                     int stride, OutKind kind, Feat out, const float* add) {
+                     int stride, OutKind kind, Feat out, const float* add, int cin_w = -1) {
       int oh, ow;
       const bool sp = split && !in_f32;
       const ActInfo& ai = sp ? sa : f32a;
@@ -202,6 +214,7 @@ class PhyDNetModel : public Model {
         a.out_f32_dense = true;
         a.split = sp;
         a.x_lo = in.lo;
+        a.cin_w = cin_w;
         add_conv(prog, conv_spec(a, ai, &oh, &ow), measure, stream, ai.dtype);
       } else {
         DeconvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, stride == 2 ? 1 : 0, in.a, hp(p + "main.0.weight"),
@@ -225,7 +238,11 @@ class PhyDNetModel : public Model {
       Op pre;
       pre.name = "frames_to_nhwc";
       pre.fn = [=](cudaStream_t s, const RunCtx& rc) {
-        launch_frames_to_nhwc(rc.x, frames_in, DT_F32, B, t_in, c, h, w, ns, s);
+        if (pad8)
+          launch_frames_to_nhwc8(rc.x, static_cast<long long>(t_in) * c * h * w, frames_in.a, frames_in.lo, B, t_in, c, h,
+                                 w, ns, s);
+        else
+          launch_frames_to_nhwc(rc.x, frames_in.a, DT_F32, B, t_in, c, h, w, ns, s);
       };
       prog.pre.push_back(std::move(pre));
       if (!branch_only) {
@@ -246,10 +263,14 @@ class PhyDNetModel : public Model {
     for (int st = 0; st < n_steps; ++st) {
       const bool decode = st >= t_in - 1;                        // produces a predicted frame
       const int di = st - (t_in - 1);
-      Feat frame;
-      frame.a = (st < t_in) ? frames_in + static_cast<size_t>(st) * px1 * c : frame_fb;
+      Feat frame = frame_fb;
+      if (st < t_in) {
+        const size_t off = static_cast<size_t>(st) * px1 * cs * (pad8 ? 2 : 4);
+        frame.a = static_cast<char*>(frames_in.a) + off;
+        frame.lo = pad8 ? static_cast<char*>(frames_in.lo) + off : nullptr;
+      }
       // ---- encoders ----
-      dcgan("encoder_E.c1.", false, frame, true, h, w, c, 32, 2, OUT_FEAT, e1, nullptr);
+      dcgan("encoder_E.c1.", false, frame, !pad8, h, w, cs, 32, 2, OUT_FEAT, e1, nullptr, c);
       dcgan("encoder_E.c2.", false, e1, false, h2, w2, 32, 32, 1, OUT_FEAT, e2, nullptr);
       dcgan("encoder_E.c3.", false, e2, false, h2, w2, 32, 64, 2, OUT_FEAT, e3, nullptr);
       if (!branch_only) {
@@ -348,7 +369,8 @@ class PhyDNetModel : public Model {
         Op op;
         op.name = "feedback_frame";
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_frames_to_nhwc_strided(src, bs, frame_fb, DT_F32, B, 1, c, h, w, ns, s);
+          if (pad8) launch_frames_to_nhwc8(src, bs, frame_fb.a, frame_fb.lo, B, 1, c, h, w, ns, s);
+          else launch_frames_to_nhwc_strided(src, bs, frame_fb.a, DT_F32, B, 1, c, h, w, ns, s);
         };
         prog.body.push_back(std::move(op));
       }
