@@ -345,10 +345,10 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       // Measured on the B200 (profiles/): with tileN >= 192 the per-tap CTA-pair kernel's mainloop is ~25 % faster than
       // the halo kernel's (weight tiles dominate the traffic there and its single ring pipelines better); for narrower N
       // the activation tile dominates and the halo kernel wins by up to 2x.
-      // ... except for the ConvLSTM gate GEMM at tileN = 256, where the halo kernel's whole-tile operand prefetch
-      // (conv_halo.cu, MODE 2) more than makes up for it.
+      // ... except for the ConvLSTM gate GEMMs, where the halo kernel's whole-tile operand prefetch (conv_halo.cu,
+      // MODE 2) and two taps per weight slot more than make up for it.
       const bool wide = L.Cn * L.G >= 192;
-      const bool lstm256 = L.epi.kind == EPI_LSTM && L.Cn * L.G == 256 && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr);
+      const bool lstm256 = L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr);
       bool prefer_halo = !wide || lstm256 || L.epi.proj_n > 0;
       if (const char* env = getenv("VPK_TC_HALO")) prefer_halo = atoi(env) != 0;
       bc.use_halo = !bc.use_direct && (backend == 0) && prefer_halo &&
