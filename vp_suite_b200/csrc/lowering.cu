@@ -342,14 +342,11 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       // the CUDA-core direct kernel is for what the tensor-core path cannot address (image-channel stems) and for
       // single-K-chunk heads; anything larger runs ~4x faster through tcgen05 even at N = 16 (profiles/)
       bc.use_direct = direct_eligible(L) && !(backend == 0 && tc_eligible(L, dtype) && L.K_pad > 64);
-      // Measured on the B200 (profiles/): with tileN >= 192 the per-tap CTA-pair kernel's mainloop is ~25 % faster than
-      // the halo kernel's (weight tiles dominate the traffic there and its single ring pipelines better); for narrower N
-      // the activation tile dominates and the halo kernel wins by up to 2x.
-      // ... except for the ConvLSTM gate GEMMs, where the halo kernel's whole-tile operand prefetch (conv_halo.cu,
-      // MODE 2) and two taps per weight slot more than make up for it.
-      const bool wide = L.Cn * L.G >= 192;
-      const bool lstm256 = L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr);
-      bool prefer_halo = !wide || lstm256 || L.epi.proj_n > 0;
+      // The halo-reuse kernel is the default for everything it can address.  (Early in the round the per-tap CTA-pair
+      // kernel was ~25 % faster at tile N >= 192; with the flat single-thread issue loop, two taps per weight slot and
+      // the whole-tile operand prefetch the halo kernel wins everywhere: cfg 3 gate GEMMs 1.51 -> 1.63 PFLOP/s, cfg 5
+      // N = 192 layers 1.02 -> 1.16.)  VPK_TC_HALO=0 forces the per-tap kernels (tests, A/B runs).
+      bool prefer_halo = true;
       if (const char* env = getenv("VPK_TC_HALO")) prefer_halo = atoi(env) != 0;
       bc.use_halo = !bc.use_direct && (backend == 0) && prefer_halo &&
                     halo_eligible(L, dtype, q.radius, q.nblocks, q.ntaps);
