@@ -36,6 +36,7 @@ constexpr int kEpiThreads = 256;
 constexpr int kTW = 8, kTH = 16;
 constexpr unsigned kMaxSmem = 232448;
 constexpr uint32_t kTapFirstOfBlock = 1, kTapLastOfBlock = 2, kTapFirstOfGroup = 4, kTapLastOfGroup = 8;
+constexpr uint32_t kTapFuseNext = 16;   // the next tap needs no hand-off in between and both are full (4 K-slices): one asm block
 
 __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   HaloTap* s_taps = reinterpret_cast<HaloTap*>(s_blocks + P.nblocks);
   // per tap, for the MMA thread: x = offset of the shifted activation view in descriptor units (16 B), y = K=16 slices
   uint2* s_tapmma = reinterpret_cast<uint2*>((reinterpret_cast<uintptr_t>(s_taps + P.ntaps) + 15) & ~uintptr_t(15));
-  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapmma + P.ntaps + 1) + 15) & ~uintptr_t(15));
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(s_tapmma + P.ntaps + 2) + 15) & ~uintptr_t(15));
 
   float* s_proj = s_bias + P.L.N_pad;      // MODE 3: [4][N_pad] projection weights, then 4 projection biases
   const int warp = threadIdx.x >> 5;
@@ -111,6 +112,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int hwp = kTW + 2 * P.P;
     const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
     const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk);
+    // fuse with the next tap: same block, no group boundary in between, both with 4 K-slices
+    if (q + 1 < blk.ntaps && !(flags & (kTapLastOfGroup | kTapLastOfBlock)) && nk == 4 && P.taps[i + 1].nk == 4 &&
+        (P.resident || (g + 1) % P.bgroup != 0))
+      flags |= kTapFuseNext;
     s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24),
                              static_cast<uint32_t>(P.resident ? i : g) * (P.b_tap_stride >> 4));
   }
@@ -127,7 +132,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       s_proj[i] = v;
     }
   }
-  if (threadIdx.x == 0) s_tapmma[P.ntaps] = make_uint2(0u, 0u);
+  if (threadIdx.x < 2) s_tapmma[P.ntaps + threadIdx.x] = make_uint2(0u, 0u);
   for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
 
   if (warp == 0 && ptx::elect_one()) {
@@ -296,10 +301,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               b_d = bdesc0 + static_cast<uint32_t>(sb) * b_slot_u;
             }
           }
-          if constexpr (PAIR) ptx::mma_bf16_ss_tap_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, cur.x >> 24);
-          else ptx::mma_bf16_ss_tap(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, cur.x >> 24);
+          uint32_t lflags = flags;
+          if (flags & kTapFuseNext) {
+            const uint2 nx = ti;              // the table entry after `cur` is consumed by the same asm block
+            tab += 8;
+            ti = ptx::lds_u2(tab);
+            ++i;
+            if constexpr (PAIR)
+              ptx::mma_bf16_ss_tap2_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
+            else
+              ptx::mma_bf16_ss_tap2(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
+            lflags = nx.x >> 16;
+          } else {
+            if constexpr (PAIR) ptx::mma_bf16_ss_tap_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, (cur.x >> 24) & 0xFFu);
+            else ptx::mma_bf16_ss_tap(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, (cur.x >> 24) & 0xFFu);
+          }
           accum = 1u;
-          if (flags & (kTapLastOfGroup | kTapLastOfBlock)) {
+          if (lflags & (kTapLastOfGroup | kTapLastOfBlock)) {
+            const uint32_t flags = lflags;
             if (flags & kTapLastOfGroup) {
               if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, 3);
               else ptx::mma_commit(bempty + 8 * sb);

@@ -353,6 +353,71 @@ __device__ __forceinline__ void mma_bf16_ss_tap_pair(uint32_t tmem_d, uint64_t a
   }
 }
 
+// two full taps (2 x 4 K-slices) from one asm block
+__device__ __forceinline__ void mma_bf16_ss_tap2(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1,
+                                                 uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pacc;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 pacc, %6, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %5, pacc;\n"
+      "add.s64 da, %1, 2;\n"
+      "add.s64 db, %2, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %1, 4;\n"
+      "add.s64 db, %2, 4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %1, 6;\n"
+      "add.s64 db, %2, 6;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %3, %4, %5, 1;\n"
+      "add.s64 da, %3, 2;\n"
+      "add.s64 db, %4, 2;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %3, 4;\n"
+      "add.s64 db, %4, 4;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %3, 6;\n"
+      "add.s64 db, %4, 6;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, 1;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a0), "l"(b0), "l"(a1), "l"(b1), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two full taps (2 x 4 K-slices) from one asm block
+__device__ __forceinline__ void mma_bf16_ss_tap2_pair(uint32_t tmem_d, uint64_t a0, uint64_t b0, uint64_t a1, uint64_t b1,
+                                                      uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred pacc;\n"
+      ".reg .b64 da, db;\n"
+      "setp.ne.b32 pacc, %6, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %5, pacc;\n"
+      "add.s64 da, %1, 2;\n"
+      "add.s64 db, %2, 2;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %1, 4;\n"
+      "add.s64 db, %2, 4;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %1, 6;\n"
+      "add.s64 db, %2, 6;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %3, %4, %5, 1;\n"
+      "add.s64 da, %3, 2;\n"
+      "add.s64 db, %4, 2;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %3, 4;\n"
+      "add.s64 db, %4, 4;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n"
+      "add.s64 da, %3, 6;\n"
+      "add.s64 db, %4, 6;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %5, 1;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(a0), "l"(b0), "l"(a1), "l"(b1), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major operand tile stored as rows of 128 B with the 128-byte swizzle
 // (what TMA writes for a {64 x bf16, rows...} box with CU_TENSOR_MAP_SWIZZLE_128B): 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
