@@ -2,11 +2,14 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 namespace vpk {
 
@@ -28,7 +31,9 @@ struct Error : std::runtime_error {
                        std::to_string(__LINE__) + ")");                                                  \
   } while (0)
 
-enum DType : int { DT_F32 = 0, DT_BF16 = 1 };
+// DT_F16: fp16 conv OPERANDS (11 mantissa bits; PhyDNet's GroupNorm-fed encoder/decoder convs, whose feature maps are
+// O(1) after GroupNorm + LeakyReLU).  Such launches read fp16 activations / packed weights and write fp32 only.
+enum DType : int { DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2 };
 __host__ __device__ inline size_t dtype_size(int dt) { return dt == DT_F32 ? 4 : 2; }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -123,8 +128,37 @@ struct ConvLaunch {
   int Cn;                 // channels per N tile for the tensor-core kernel (tile N = Cn*G)
   EpiParams epi;
   // bookkeeping
+  int op_f16;             // 16-bit operands are fp16 instead of bf16 (tensor-core kernels: instruction descriptor)
   double flops;           // 2*M*N*K of the real (unpadded) contraction
   int is_gate_gemm;       // counted in the gate-GEMM roofline figure
 };
+
+// VPK_PDL=0 turns programmatic dependent launch off (A/B runs).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* env = getenv("VPK_PDL");
+    return env == nullptr || atoi(env) != 0;
+  }();
+  return on;
+}
+
+#ifdef __CUDACC__
+// Launch of a kernel that starts with ptx::pdl_launch_dependents() / ptx::pdl_wait() (see ptx.cuh): with PDL enabled its
+// CTAs may become resident (and run whatever precedes their pdl_wait) while the previous kernel of the stream drains.
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  VPK_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+}
+#endif
 
 }  // namespace vpk

@@ -84,6 +84,7 @@ void launch_conv_direct(const ConvLaunch& L, int dtype, int num_sms, cudaStream_
   const long long blocks = (M + kDirectThreads - 1) / kDirectThreads;
   const int grid = static_cast<int>(std::max<long long>(1, std::min<long long>(blocks, static_cast<long long>(num_sms) * 8)));
   if (dtype == DT_F32) launch_n<float>(L, grid, stream);
+  else if (dtype == DT_F16) launch_n<__half>(L, grid, stream);
   else launch_n<__nv_bfloat16>(L, grid, stream);
   VPK_CUDA(cudaGetLastError());
 }

@@ -34,7 +34,11 @@ namespace {
 constexpr int kHaloThreads = 352;   // warps 0..2: activation TMA, weight TMA, MMA issue (+ TMEM alloc); warps 3..10: epilogue
 constexpr int kEpiThreads = 256;
 constexpr int kTW = 8, kTH = 16;
+#ifdef VPK_TRACE
+constexpr unsigned kMaxSmem = 232448 - 1024;   // room for the static trace slots
+#else
 constexpr unsigned kMaxSmem = 232448;
+#endif
 constexpr uint32_t kTapFirstOfBlock = 1, kTapLastOfBlock = 2, kTapFirstOfGroup = 4, kTapLastOfGroup = 8;
 constexpr uint32_t kTapFuseNext = 16;   // the next tap needs no hand-off in between and both are full (4 K-slices): one asm block
 
@@ -62,6 +66,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  // PDL: the next kernel of the stream may become resident as soon as every CTA of this grid is (it then waits in its
+  // own pdl_wait); everything up to our pdl_wait below reads only plan tables, biases and packed weights' descriptors
+  ptx::pdl_launch_dependents();
+  // Built with -DVPK_TRACE and run with VPK_TC_DEBUG & 128: CTA 0 prints a timeline of its phases (globaltimer, ns) --
+  // developer aid for the fixed cost of short launches; compiled out of the product build
+#ifdef VPK_TRACE
+  __shared__ unsigned long long s_trace[8];
+  const bool trace = (P.debug & 128) && blockIdx.x == 0;
+  auto stamp = [&](int i) {
+    if (trace) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      s_trace[i] = t;
+    }
+  };
+#else
+  auto stamp = [](int) {};
+#endif
+  if (threadIdx.x == 0) stamp(0);
 
   const int SA = P.SA, SB = P.SB;
   const int tileN = P.tileN;
@@ -168,6 +191,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) stamp(1);
+  ptx::pdl_wait();           // the previous kernel has completed: activations / cell state may be read from here on
+  if (threadIdx.x == 0) stamp(2);
 
   const int m_tiles = P.L.B * P.tiles_y * P.tiles_x;
   const int units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
@@ -266,7 +292,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // idles whenever this thread falls behind (ncu: 73 % tensor-active with the previous ~60-instruction tap).
     // Descriptors move by their low word only (start address in 16-byte units; shared memory < 256 KB: no carry).
     if (leader && ptx::elect_one()) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(PAIR ? 256 : 128, tileN);
+      const uint32_t idesc = ptx::idesc_bf16_f32(PAIR ? 256 : 128, tileN, P.L.op_f16 != 0);
       const uint32_t sbo = (P.debug & 64) ? 1024u : static_cast<uint32_t>(HWp * 128);
       const uint64_t adesc0 = smem_desc_sw128_sbo(ptx::smem_u32(smem_a), sbo);
       const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
@@ -295,6 +321,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             if (flags & kTapFirstOfBlock) {
               ptx::mbar_wait_spin(afull + 8 * sa, pha);
               a_d = adesc0 + static_cast<uint32_t>(sa) * a_slot_u;
+              if (iter == 0 && i == 0) stamp(3);
             }
             if (flags & kTapFirstOfGroup) {
               ptx::mbar_wait_spin(bfull + 8 * sb, phb);
@@ -333,7 +360,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
         if constexpr (PAIR) ptx::mma_commit_pair(tfull + 8 * acc, 3);
         else ptx::mma_commit(tfull + 8 * acc);
+        if (iter == 0) stamp(4);
       }
+      stamp(5);
     }
     __syncwarp();
   } else if (warp >= 3) {
@@ -572,6 +601,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   }
 
+  if (threadIdx.x == kHaloThreads - 1) stamp(6);      // last epilogue warp has finished its tiles
   ptx::tc_fence_before();
   if constexpr (PAIR) ptx::cluster_sync_all();
   else __syncthreads();
@@ -579,6 +609,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if constexpr (PAIR) ptx::tmem_dealloc_pair(tmem_base, static_cast<uint32_t>(P.tmem_cols));
     else ptx::tmem_dealloc(tmem_base, static_cast<uint32_t>(P.tmem_cols));
   }
+#ifdef VPK_TRACE
+  if (trace && threadIdx.x == 0) {
+    stamp(7);
+    const unsigned long long t0 = s_trace[0];
+    printf("halo trace N=%d taps=%d tiles/cta=%d: setup %llu  pdl_wait %llu  first_A %llu  tile0_issued %llu  all_issued %llu  "
+           "epi_done %llu  exit %llu (ns since entry)\n",
+           P.tileN, P.ntaps, (total + nunits - 1) / nunits, s_trace[1] - t0, s_trace[2] - t0, s_trace[3] - t0,
+           s_trace[4] - t0, s_trace[5] - t0, s_trace[6] - t0, s_trace[7] - t0);
+  }
+#endif
 #endif
 }
 
@@ -628,13 +668,15 @@ template <int KIND, bool PAIR, int MODE> void launch_one(const HaloPlan& P, cuda
   cfg.blockDim = dim3(kHaloThreads);
   cfg.dynamicSmemBytes = P.smem_bytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = PAIR ? 2 : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   VPK_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<KIND, PAIR, MODE>, P));
 }
 
@@ -696,7 +738,19 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   // Ring depths by bytes: ~60 % of shared memory for weight tiles (4..24 slots), the rest for activation halo tiles
   // (2..8).  What matters is the number of TMA operations in flight against their ~2 us latency: small-N layers have
   // small weight tiles and get deep rings, the N = 256 gate GEMMs get 7-8 x 16 KB.
-  const unsigned avail = kMaxSmem - fixed;
+  // Experiment kept behind VPK_HALO_SMEM_CAP=<bytes> (default off): capping short low-register launches at half of the
+  // SM's shared memory lets the next kernel's CTAs become resident under PDL and overlap their set-up -- measured on
+  // cfg 4 / cfg 2 it is SLOWER (10.37 vs 9.70 ms, 10.45 vs 10.02 ms): the shallower activation ring costs more than the
+  // hidden set-up saves.
+  unsigned budget = kMaxSmem;
+  if (const char* env = getenv("VPK_HALO_SMEM_CAP")) {
+    const unsigned cap = static_cast<unsigned>(atoi(env));
+    const bool low_reg = (L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0) || L.epi.kind == EPI_PHY_GATE;
+    if (cap > 0 && cap <= kMaxSmem && low_reg && P.fast_epi && m_tiles * P.n_tiles <= 8ll * num_sms &&
+        fixed + (P.resident ? 1u : 2u) * P.b_slot_bytes + 2u * P.a_slot_bytes <= cap)
+      budget = cap;
+  }
+  const unsigned avail = budget - fixed;
   int sb = static_cast<int>(avail * 6 / 10 / P.b_slot_bytes);
   sb = std::max(4, std::min(24, sb));
   while (sb > 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes > avail) --sb;
@@ -707,7 +761,7 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   P.SA = std::max(2, std::min<int>(8, static_cast<int>((avail - P.SB * P.b_slot_bytes) / P.a_slot_bytes)));
   if (const char* env = getenv("VPK_HALO_SA")) {
     const int sa = atoi(env);
-    if (!P.resident && sa >= 2 && fixed + sa * P.a_slot_bytes + 2 * P.b_slot_bytes <= kMaxSmem) {
+    if (!P.resident && sa >= 2 && fixed + sa * P.a_slot_bytes + 2 * P.b_slot_bytes <= budget) {
       P.SA = sa;
       P.SB = std::min<int>(24, static_cast<int>((avail - P.SA * P.a_slot_bytes) / P.b_slot_bytes));
     }

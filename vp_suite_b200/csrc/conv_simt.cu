@@ -141,6 +141,7 @@ template <typename T> void launch_g(const ConvLaunch& L, cudaStream_t stream) {
 void launch_conv_simt(const ConvLaunch& L, int dtype, cudaStream_t stream) {
   VPK_REQUIRE(L.nsteps > 0 && L.nsteps <= kMaxSteps, "conv_simt: bad step count");
   if (dtype == DT_F32) launch_g<float>(L, stream);
+  else if (dtype == DT_F16) launch_t<__half, 1, 8>(L, stream);     // fp16 operands exist for plain convs only (G = 1)
   else launch_g<__nv_bfloat16>(L, stream);
   VPK_CUDA(cudaGetLastError());
 }

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================================
-    const uint32_t idesc = ptx::idesc_bf16_f32(128, tileN);
+    const uint32_t idesc = ptx::idesc_bf16_f32(128, tileN, P.L.op_f16 != 0);
     int stage = 0;
     uint32_t phase = 0;
     int iter = 0;
@@ -248,7 +248,9 @@ template <int G> void set_smem_attr() {
 }  // namespace
 
 bool tc_eligible(const ConvLaunch& L, int dtype) {
-  if (dtype != DT_BF16) return false;
+  if (dtype != DT_BF16 && dtype != DT_F16) return false;
+  // fp16 operands: the tensor-core epilogues store activation-type outputs as bf16, so fp16 launches are fp32-out only
+  if (dtype == DT_F16 && (L.epi.kind != EPI_BIAS_ACT || !L.epi.out_f32)) return false;
   if (L.G < 1 || L.G > 4) return false;
   const int tileN = L.Cn * L.G;
   if (L.Cn % 8 != 0 || tileN % 16 != 0 || tileN > 256 || L.N_pad % tileN != 0) return false;

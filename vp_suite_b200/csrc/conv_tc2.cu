@@ -134,7 +134,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kTcThreads, 1)
     // ===================================== MMA issuer (leader CTA only) =====================================
     // ONE thread runs the whole loop; descriptors advance arithmetically (16-byte units, no carry out of the field).
     if (leader && ptx::elect_one()) {
-      const uint32_t idesc = ptx::idesc_bf16_f32(256, tileN);
+      const uint32_t idesc = ptx::idesc_bf16_f32(256, tileN, P.L.op_f16 != 0);
       const uint64_t adesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_a));
       const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
       const uint32_t a_u = kAStageBytes >> 4, b_u = b_stage_bytes >> 4;

@@ -6,6 +6,7 @@
 #include "common.h"
 #include "elementwise.h"
 #include "epilogue.cuh"
+#include "ptx.cuh"
 
 namespace vpk {
 
@@ -21,6 +22,8 @@ inline int grid_for(long long n, int threads, int num_sms) {
 template <typename T>
 __global__ void frames_to_nhwc_kernel(const float* __restrict__ x, long long bstride, T* __restrict__ out, int B,
                                       int Tn, int C, int H, int W) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long total = static_cast<long long>(B) * Tn * HW;   // one thread per (b, t, pixel); loops channels
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -38,8 +41,12 @@ __global__ void frames_to_nhwc_kernel(const float* __restrict__ x, long long bst
 // x fp32 [B, T, C, H, W] -> bf16 [T][B][H][W][8] with channels C..7 zero: one 16-byte store per pixel, and the frame
 // becomes TMA-addressable (16-byte pixel stride), so the image-channel stem convs run on the tensor-core kernel.
 // `lo` != nullptr: split-bf16, hi = bf16(v) and lo = bf16(v - hi) in two tensors of the same layout.
+// F16: `hi` receives fp16 values instead (single tensor, no low parts).
+template <bool F16>
 __global__ void frames_to_nhwc8_kernel(const float* __restrict__ x, long long bstride, __nv_bfloat16* __restrict__ hi,
                                        __nv_bfloat16* __restrict__ lo, int B, int Tn, int C, int H, int W) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long total = static_cast<long long>(B) * Tn * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -57,6 +64,13 @@ __global__ void frames_to_nhwc8_kernel(const float* __restrict__ x, long long bs
       vl[c] = __float2bfloat16_rn(v - __bfloat162float(vh[c]));
     }
     const long long o = ((static_cast<long long>(t) * B + b) * HW + p);
+    if (F16) {
+      __align__(16) __half vf[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) vf[c] = __float2half_rn((c < C) ? src[c * HW] : 0.f);
+      reinterpret_cast<uint4*>(hi)[o] = *reinterpret_cast<const uint4*>(vf);
+      continue;
+    }
     reinterpret_cast<uint4*>(hi)[o] = *reinterpret_cast<const uint4*>(vh);
     if (lo != nullptr) reinterpret_cast<uint4*>(lo)[o] = *reinterpret_cast<const uint4*>(vl);
   }
@@ -67,6 +81,8 @@ __global__ void frames_to_nhwc8_kernel(const float* __restrict__ x, long long bs
 template <typename T>
 __global__ void patchify_kernel(const float* __restrict__ x, long long bstride, T* __restrict__ out, int B, int Tn,
                                 int C, int H, int W, int p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int hp = H / p, wp = W / p, cp = p * p * C;
   const long long total = static_cast<long long>(B) * Tn * hp * wp * cp;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -90,6 +106,8 @@ __global__ void patchify_kernel(const float* __restrict__ x, long long bstride, 
 template <typename T>
 __global__ void unpatchify_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int P, int t, int C, int H,
                                   int W, int p) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int hp = H / p, wp = W / p, cp = p * p * C;
   const long long total = static_cast<long long>(B) * C * H * W;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -108,6 +126,8 @@ __global__ void unpatchify_kernel(const T* __restrict__ in, float* __restrict__ 
 // in T [B][H][W][C] -> out fp32 [B][C][H][W]
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int B, int C, int H, int W) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long HW = static_cast<long long>(H) * W;
   const long long total = static_cast<long long>(B) * C * HW;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -120,6 +140,8 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict_
 }
 
 __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const long long n2 = n / 2;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n2;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -129,6 +151,21 @@ __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = __float2bfloat16_rn(in[n - 1]);
 }
 
+// fp32 -> fp16, n % 4 == 0
+__global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n4) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    uint2 hv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+    hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    reinterpret_cast<uint2*>(out)[i] = hv;
+  }
+}
+
 // PredRNN-V2 decoupling loss term (models/predrnn_v2.py:197-211): ad = adapter(delta) as fp32 [2B][HW][C] with
 // delta_c in the first B samples and delta_m in the last B.  Per (b, ch): |cos| between the two HW-vectors, each
 // L2-normalised first (F.normalize eps 1e-12).  Adds sum over (b, ch) to *acc.
@@ -136,6 +173,8 @@ __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
 // slices are combined through shared memory, then one warp finishes |cos| and the block adds one fp64 atomic.
 __global__ void __launch_bounds__(256) decouple_reduce_kernel(const float* __restrict__ ad, int B, int HW, int C,
                                                               double* acc) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   __shared__ float s_part[8][3][128];
   const int b = blockIdx.x;
   const int q = threadIdx.x & 31;            // channel quad inside this block's 128-channel range
@@ -192,6 +231,8 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict
                                                             int Cs_out, int groups, int TC,
                                                             const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, float eps, int act) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   __shared__ float s_acc[64], s_mean[64], s_rstd[64];
   const int b = blockIdx.x;
   const int tx = threadIdx.x % TC, ty = threadIdx.x / TC, rows = 256 / TC;
@@ -271,6 +312,8 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
                                                                     const float* __restrict__ add, int HW, int C,
                                                                     int groups, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, float eps, int act) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   extern __shared__ float4 gn_stage[];
   __shared__ float s_acc[64], s_mean[64], s_rstd[64];
   const int b = blockIdx.x;
@@ -330,6 +373,12 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
     }
     if (OUT == 0) {
       reinterpret_cast<float4*>(out)[obase + i] = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (OUT == 3) {
+      const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+      uint2 hv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+      hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(out)[obase + i] = hv;
     } else {
       const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
       uint2 hv;
@@ -352,6 +401,8 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
 // fp32 -> split-bf16 (hi, lo); n % 4 == 0
 __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n4) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const float4 v = reinterpret_cast<const float4*>(in)[i];
@@ -370,6 +421,8 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* _
 }
 
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   aux[0] = static_cast<float>(acc[0] * scale);
 }
 
@@ -379,8 +432,8 @@ void launch_nhwc_to_nchw(const void* in, int dtype, float* out, int B, int C, in
                          cudaStream_t stream) {
   const long long total = static_cast<long long>(B) * C * H * W;
   const int g = grid_for(total, 256, num_sms);
-  if (dtype == DT_F32) nhwc_to_nchw_kernel<float><<<g, 256, 0, stream>>>(static_cast<const float*>(in), out, B, C, H, W);
-  else nhwc_to_nchw_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, B, C, H, W);
+  if (dtype == DT_F32) launch_pdl(nhwc_to_nchw_kernel<float>, dim3(g), dim3(256), 0, stream, static_cast<const float*>(in), out, B, C, H, W);
+  else launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(in), out, B, C, H, W);
   VPK_CUDA(cudaGetLastError());
 }
 
@@ -389,19 +442,23 @@ void launch_frames_to_nhwc_strided(const float* x, long long bstride, void* out,
   const long long total = static_cast<long long>(B) * T * H * W;
   const int g = grid_for(total, 256, num_sms);
   if (dtype == DT_F32)
-    frames_to_nhwc_kernel<float><<<g, 256, 0, stream>>>(x, bstride, static_cast<float*>(out), B, T, C, H, W);
+    launch_pdl(frames_to_nhwc_kernel<float>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<float*>(out), B, T, C, H, W);
   else
-    frames_to_nhwc_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C,
+    launch_pdl(frames_to_nhwc_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C,
                                                                H, W);
   VPK_CUDA(cudaGetLastError());
 }
 
-void launch_frames_to_nhwc8(const float* x, long long bstride, void* hi, void* lo, int B, int T, int C, int H, int W,
-                            int num_sms, cudaStream_t stream) {
+void launch_frames_to_nhwc8(const float* x, long long bstride, void* hi, void* lo, int out_dtype, int B, int T, int C,
+                            int H, int W, int num_sms, cudaStream_t stream) {
   VPK_REQUIRE(C >= 1 && C <= 8, "frames_to_nhwc8: 1..8 image channels");
   const long long total = static_cast<long long>(B) * T * H * W;
-  frames_to_nhwc8_kernel<<<grid_for(total, 256, num_sms), 256, 0, stream>>>(
-      x, bstride, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, T, C, H, W);
+  if (out_dtype == DT_F16)
+    launch_pdl(frames_to_nhwc8_kernel<true>, dim3(grid_for(total, 256, num_sms)), dim3(256), 0, stream, 
+        x, bstride, static_cast<__nv_bfloat16*>(hi), nullptr, B, T, C, H, W);
+  else
+    launch_pdl(frames_to_nhwc8_kernel<false>, dim3(grid_for(total, 256, num_sms)), dim3(256), 0, stream, 
+        x, bstride, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), B, T, C, H, W);
   VPK_CUDA(cudaGetLastError());
 }
 
@@ -411,14 +468,20 @@ void launch_frames_to_nhwc(const float* x, void* out, int dtype, int B, int T, i
 }
 
 void launch_cast_f32_to_bf16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream) {
-  cast_kernel<<<grid_for((n + 1) / 2, 256, num_sms), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(out), n);
+  launch_pdl(cast_kernel, dim3(grid_for((n + 1) / 2, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__nv_bfloat16*>(out), n);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream) {
+  VPK_REQUIRE(n % 4 == 0, "cast_f32_to_f16: element count must be a multiple of 4");
+  launch_pdl(cast_f16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__half*>(out), n / 4);
   VPK_CUDA(cudaGetLastError());
 }
 
 void launch_decouple_reduce(const float* ad, int B, int HW, int C, double* acc, cudaStream_t stream) {
   VPK_REQUIRE(C % 4 == 0, "decouple_reduce: channel count must be a multiple of 4");
   dim3 grid(static_cast<unsigned>(B), static_cast<unsigned>((C + 127) / 128));
-  decouple_reduce_kernel<<<grid, 256, 0, stream>>>(ad, B, HW, C, acc);
+  launch_pdl(decouple_reduce_kernel, dim3(grid), dim3(256), 0, stream, ad, B, HW, C, acc);
   VPK_CUDA(cudaGetLastError());
 }
 
@@ -429,11 +492,12 @@ void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype
   int TC = 1;
   while (TC < C) TC <<= 1;
 #define VPK_GN(TI, TO)                                                                                          \
-  groupnorm_act_kernel<TI, TO><<<B, 256, 0, stream>>>(static_cast<const TI*>(in), static_cast<TO*>(out),           \
+  launch_pdl(groupnorm_act_kernel<TI, TO>, dim3(B), dim3(256), 0, stream, static_cast<const TI*>(in), static_cast<TO*>(out),           \
                                                       static_cast<const TO*>(add), HW, C, Cs_in, Cs_out, groups, TC, \
                                                       gamma, beta, eps, act)
   if (in_dtype == DT_F32 && out_dtype == DT_F32) VPK_GN(float, float);
   else if (in_dtype == DT_F32 && out_dtype == DT_BF16) VPK_GN(float, __nv_bfloat16);
+  else if (in_dtype == DT_F32 && out_dtype == DT_F16) VPK_GN(float, __half);
   else if (in_dtype == DT_BF16 && out_dtype == DT_BF16) VPK_GN(__nv_bfloat16, __nv_bfloat16);
   else VPK_THROW(1, "groupnorm: unsupported dtype combination");
 #undef VPK_GN
@@ -448,7 +512,7 @@ void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kin
                            int C, int groups, const float* gamma, const float* beta, float eps, int act,
                            cudaStream_t stream) {
   VPK_REQUIRE(groupnorm_smem_supported(HW, C, groups), "groupnorm_smem: unsupported shape");
-  VPK_REQUIRE(out_kind >= 0 && out_kind <= 2 && (out_kind != 2 || out_lo != nullptr), "groupnorm_smem: bad output kind");
+  VPK_REQUIRE(out_kind >= 0 && out_kind <= 3 && (out_kind != 2 || out_lo != nullptr), "groupnorm_smem: bad output kind");
   const size_t bytes = static_cast<size_t>(HW) * C * sizeof(float);
   const bool staged = bytes <= 200 * 1024;
 #define VPK_GNS(OUT, ST)                                                                                           \
@@ -457,16 +521,18 @@ void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kin
     std::call_once(once, [] {                                                                                      \
       cudaFuncSetAttribute(groupnorm_smem_kernel<OUT, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
     });                                                                                                            \
-    groupnorm_smem_kernel<OUT, ST><<<B, kGnThreads, (ST) ? bytes : 0, stream>>>(in, out, out_lo, add, HW, C, groups, \
+    launch_pdl(groupnorm_smem_kernel<OUT, ST>, dim3(B), dim3(kGnThreads), (ST) ? bytes : 0, stream, in, out, out_lo, add, HW, C, groups, \
                                                                                 gamma, beta, eps, act);            \
   } while (0)
   if (staged) {
     if (out_kind == 0) VPK_GNS(0, true);
     else if (out_kind == 1) VPK_GNS(1, true);
+    else if (out_kind == 3) VPK_GNS(3, true);
     else VPK_GNS(2, true);
   } else {
     if (out_kind == 0) VPK_GNS(0, false);
     else if (out_kind == 1) VPK_GNS(1, false);
+    else if (out_kind == 3) VPK_GNS(3, false);
     else VPK_GNS(2, false);
   }
 #undef VPK_GNS
@@ -475,13 +541,13 @@ void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kin
 
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream) {
   VPK_REQUIRE(n % 4 == 0, "split_bf16: element count must be a multiple of 4");
-  split_bf16_kernel<<<grid_for(n / 4, 256, num_sms), 256, 0, stream>>>(in, static_cast<__nv_bfloat16*>(hi),
+  launch_pdl(split_bf16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__nv_bfloat16*>(hi),
                                                                        static_cast<__nv_bfloat16*>(lo), n / 4);
   VPK_CUDA(cudaGetLastError());
 }
 
 void launch_decouple_finalize(const double* acc, float* aux, double scale, cudaStream_t stream) {
-  decouple_finalize_kernel<<<1, 1, 0, stream>>>(acc, aux, scale);
+  launch_pdl(decouple_finalize_kernel, dim3(1), dim3(1), 0, stream, acc, aux, scale);
   VPK_CUDA(cudaGetLastError());
 }
 
@@ -490,9 +556,9 @@ void launch_patchify_strided(const float* x, long long bstride, void* out, int d
   const long long total = static_cast<long long>(B) * T * C * H * W;
   const int g = grid_for(total, 256, num_sms);
   if (dtype == DT_F32)
-    patchify_kernel<float><<<g, 256, 0, stream>>>(x, bstride, static_cast<float*>(out), B, T, C, H, W, p);
+    launch_pdl(patchify_kernel<float>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<float*>(out), B, T, C, H, W, p);
   else
-    patchify_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C, H, W,
+    launch_pdl(patchify_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C, H, W,
                                                          p);
   VPK_CUDA(cudaGetLastError());
 }
@@ -502,9 +568,9 @@ void launch_unpatchify(const void* in, float* out, int dtype, int B, int P, int 
   const long long total = static_cast<long long>(B) * C * H * W;
   const int g = grid_for(total, 256, num_sms);
   if (dtype == DT_F32)
-    unpatchify_kernel<float><<<g, 256, 0, stream>>>(static_cast<const float*>(in), out, B, P, t, C, H, W, p);
+    launch_pdl(unpatchify_kernel<float>, dim3(g), dim3(256), 0, stream, static_cast<const float*>(in), out, B, P, t, C, H, W, p);
   else
-    unpatchify_kernel<__nv_bfloat16><<<g, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(in), out, B, P, t, C, H,
+    launch_pdl(unpatchify_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(in), out, B, P, t, C, H,
                                                            W, p);
   VPK_CUDA(cudaGetLastError());
 }

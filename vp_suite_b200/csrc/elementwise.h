@@ -10,9 +10,9 @@ namespace vpk {
 void launch_frames_to_nhwc(const float* x, void* out, int dtype, int B, int T, int C, int H, int W, int num_sms,
                            cudaStream_t stream);
 // x fp32 [B, *, C, H, W] (sequence stride `bstride` elements), first T frames -> bf16 [T][B][H][W][8], channels C..7
-// zero (TMA-addressable frames); lo != nullptr: split-bf16 (hi, lo) pair
-void launch_frames_to_nhwc8(const float* x, long long bstride, void* hi, void* lo, int B, int T, int C, int H, int W,
-                            int num_sms, cudaStream_t stream);
+// zero (TMA-addressable frames); lo != nullptr: split-bf16 (hi, lo) pair; out_dtype == DT_F16: `hi` receives fp16 values
+void launch_frames_to_nhwc8(const float* x, long long bstride, void* hi, void* lo, int out_dtype, int B, int T, int C,
+                            int H, int W, int num_sms, cudaStream_t stream);
 // PredRNN patchify: the first T frames of x fp32 [B, *, c, H, W] (sequence stride `bstride` elements)
 // -> out [T][B][H/p][W/p][p*p*c]
 void launch_patchify_strided(const float* x, long long bstride, void* out, int dtype, int B, int T, int C, int H, int W,
@@ -40,13 +40,15 @@ void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype
                           int act, cudaStream_t stream);
 
 // Same operation with the sample staged in shared memory (one HBM read + one write).  in: fp32 dense [B][HW][C];
-// out_kind 0: fp32 out; 1: bf16 out; 2: split-bf16 (out = high parts, out_lo = low parts); add: optional fp32 dense
+// out_kind 0: fp32 out; 1: bf16 out; 2: split-bf16 (out = high parts, out_lo = low parts); 3: fp16 out;
+// add: optional fp32 dense
 // residual added after the activation.
 bool groupnorm_smem_supported(int HW, int C, int groups);
 void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kind, const float* add, int B, int HW,
                            int C, int groups, const float* gamma, const float* beta, float eps, int act,
                            cudaStream_t stream);
 // fp32 -> split-bf16: hi = bf16(v), lo = bf16(v - hi)
+void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);   // n % 4 == 0
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
 
 }  // namespace vpk

@@ -8,7 +8,9 @@ namespace vpk {
 
 __device__ __forceinline__ float to_f32(float v) { return v; }
 __device__ __forceinline__ float to_f32(__nv_bfloat16 v) { return __bfloat162float(v); }
+__device__ __forceinline__ float to_f32(__half v) { return __half2float(v); }
 template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ __half from_f32<__half>(float v) { return __float2half_rn(v); }
 template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
 template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
 
@@ -79,6 +81,15 @@ template <int N> __device__ __forceinline__ void load_act(const __nv_bfloat16* p
 #pragma unroll
     for (int i = 0; i < N; ++i) v[i] = (i < nvalid) ? __bfloat162float(p[i]) : 0.f;
   }
+}
+template <int N> __device__ __forceinline__ void load_act(const __half* p, float (&v)[N], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) v[i] = (i < nvalid) ? __half2float(p[i]) : 0.f;
+}
+template <int N> __device__ __forceinline__ void store_act(__half* p, const float (&v)[N], int nvalid) {
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i < nvalid) p[i] = __float2half_rn(v[i]);
 }
 template <int N> __device__ __forceinline__ void store_act(float* p, const float (&v)[N], int nvalid) {
   store_f32<N>(p, v, nvalid);

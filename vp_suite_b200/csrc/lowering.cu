@@ -269,6 +269,10 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         q.bias = d_bias;
         if (dtype == DT_F32) {
           q.w = store.upload(wf.data(), wf.size() * sizeof(float), stream);
+        } else if (dtype == DT_F16) {
+          std::vector<__half> wh(wf.size());
+          for (size_t i = 0; i < wf.size(); ++i) wh[i] = __float2half_rn(wf[i]);
+          q.w = store.upload(wh.data(), wh.size() * sizeof(__half), stream);
         } else {
           std::vector<__nv_bfloat16> wb(wf.size());
           for (size_t i = 0; i < wf.size(); ++i) wb[i] = __float2bfloat16_rn(wf[i]);
@@ -330,6 +334,8 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi = ph.epi;
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
+    L.op_f16 = (dtype == DT_F16) ? 1 : 0;
+    VPK_REQUIRE(dtype != DT_F16 || G == 1, "fp16 operands are for plain convs only: " + spec.name);
     double kreal = 0;
     for (const HostStep& h : ph.steps) kreal += h.kw_valid;   // split-bf16 layers count their three products
     L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;

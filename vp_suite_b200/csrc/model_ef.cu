@@ -10,6 +10,7 @@
 #include <cstring>
 
 #include "builders.h"
+#include "conv_stem.h"
 #include "elementwise.h"
 #include "model.h"
 
@@ -177,7 +178,7 @@ class EfConvLstm : public Model {
       pre.name = "frames_to_nhwc";
       pre.fn = [=](cudaStream_t s, const RunCtx& ctx) {
         if (pad8)
-          launch_frames_to_nhwc8(ctx.x, static_cast<long long>(t_in) * c * h * w, frames_in, nullptr, B, t_in, c, h, w, ns, s);
+          launch_frames_to_nhwc8(ctx.x, static_cast<long long>(t_in) * c * h * w, frames_in, nullptr, DT_BF16, B, t_in, c, h, w, ns, s);
         else
           launch_frames_to_nhwc(ctx.x, frames_in, dt, B, t_in, c, h, w, ns, s);
       };
@@ -206,6 +207,26 @@ class EfConvLstm : public Model {
         ConvArgs ca{st, B, in_h, in_w, in_c, mid, d.enc_conv_k[n], d.enc_conv_s[n], d.enc_conv_p[n], in,
                     hp(st + "weight"), hp(st + "bias"), d.ef_act, xin[n]};
         if (n == 0) ca.cin_w = c;
+        // image-channel stem (K = 9 * c): HBM-bound, direct CUDA-core kernel instead of a tensor-core tile
+        const bool stem = n == 0 && pad8 && dtype == DT_BF16 && backend == 0 && getenv("VPK_NO_STEM") == nullptr &&
+                          (d.ef_act == ACT_LEAKY || d.ef_act == ACT_NONE || d.ef_act == ACT_RELU) &&
+                          conv_stem_supported(d.enc_conv_k[0], d.enc_conv_s[0], d.enc_conv_p[0], c, mid, in_h, in_w);
+        if (stem) {
+          oh = (in_h + 2 - 3) / d.enc_conv_s[0] + 1;
+          ow = (in_w + 2 - 3) / d.enc_conv_s[0] + 1;
+          if (!measure) {
+            std::vector<float> hb(hp(st + "bias"), hp(st + "bias") + mid);
+            StemArgs sa{in, 0, B, in_h, in_w, c, d.enc_conv_s[0],
+                        dev_f32(st + "stem.w", conv_stem_pack(hp(st + "weight"), mid, c, DT_BF16), stream),
+                        dev_f32(st + "stem.b", hb, stream), mid, d.ef_act, xin[n], 0};
+            const int ns = num_sms;
+            Op op;
+            op.name = st + "stem";
+            op.flops = 2.0 * static_cast<double>(B) * oh * ow * mid * 9 * c;
+            op.fn = [=](cudaStream_t s, const RunCtx&) { launch_conv_stem(sa, ns, s); };
+            prog.body.push_back(std::move(op));
+          }
+        } else
         add_conv(prog, conv_spec(ca, act, &oh, &ow), measure, stream);
         VPK_REQUIRE(oh == eh[n] && ow == ew[n], "encoder stage size mismatch");
         LstmArgs la{rn, B, eh[n], ew[n], mid, outc, d.enc_rnn_k[n], xin[n], hbuf[n][par[n]], hbuf[n][par[n] ^ 1],

@@ -10,14 +10,17 @@
 // the decoders are skipped there; of the three decoder_D passes per step only `output_image` (:87-88) is computed.
 //
 // Precision in bf16 mode: the recurrent cells (85 % of the FLOPs) run bf16 on the tensor cores.  The DCGAN encoder /
-// decoder convs feed GroupNorm, which amplifies operand rounding past the 5e-3 single-step bound,
-// so they need ~fp32 operands: their feature maps are kept as SPLIT bf16 (hi + lo, 16 mantissa bits) and each conv is
-// three bf16 tensor-core products (A_hi W_hi + A_hi W_lo + A_lo W_hi, fp32 accumulation in TMEM) through the same
-// tcgen05 kernel -- the dropped A_lo W_lo term is ~2^-18 relative.  Only encoder_E.c1 (image frames, 1 or 3 input
-// channels: not TMA-addressable) stays on the CUDA-core fp32 kernel.
+// decoder convs feed GroupNorm, which amplifies operand rounding past the 5e-3 single-step bound with bf16 operands
+// (tools/precision_probe.py: 4.3e-3 .. 8.1e-3 per frame), so they need more mantissa bits.
+// Default: FP16 operands (11 bits; the feature maps are O(1) after GroupNorm + LeakyReLU, the frames lie in [0, 1] and
+// the accumulators stay fp32 in TMEM) -- one tcgen05 product per conv, 2-byte feature maps, first-frame error 1.1e-3
+// (fp32 convs next to bf16 cells: 1.0e-3, the cells dominate).  VPK_FEAT_SPLIT=1 selects the earlier SPLIT-bf16 form
+// instead (hi + lo, 16 mantissa bits, three bf16 products A_hi W_hi + A_hi W_lo + A_lo W_hi per conv), kept for A/B runs.
 #include <cmath>
+#include <cstdlib>
 
 #include "builders.h"
+#include "conv_stem.h"
 #include "elementwise.h"
 #include "model.h"
 #include "phycell.h"
@@ -35,6 +38,7 @@ int group_norm_divisor(int x) {   // model_blocks/phydnet.py:348-362
 class PhyDNetModel : public Model {
  public:
   PhyDNetModel(const vpk_model_desc& d, bool branch) : Model(d), branch_only(branch) {
+    if (const char* env = getenv("VPK_FEAT_SPLIT")) feat_split = atoi(env) != 0;
     VPK_REQUIRE(d.img_c > 0 && d.img_h % 4 == 0 && d.img_w % 4 == 0 && d.img_h > 0 && d.img_w > 0,
                 "img size must be a multiple of 4 (other sizes need the reference's Resize)");
     n_phy = d.phycell_n_layers;
@@ -109,8 +113,10 @@ class PhyDNetModel : public Model {
   void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) override {
     const vpk_model_desc& d = desc;
     const int cdt = dtype;                // recurrent-cell operand type
-    const bool split = (cdt == DT_BF16);  // encoder / decoder convs: three bf16 products on the tensor cores
-    const ActInfo f32a{DT_F32, 4}, sa{DT_BF16, 2}, ca{cdt, esize()};
+    const bool split = (cdt == DT_BF16) && feat_split;   // encoder / decoder convs: three bf16 products
+    const bool f16 = (cdt == DT_BF16) && !feat_split;    // encoder / decoder convs: one fp16 product
+    const bool tcfeat = split || f16;                     // feature maps are 16-bit tensor-core operands
+    const ActInfo f32a{DT_F32, 4}, sa{f16 ? DT_F16 : DT_BF16, 2}, ca{cdt, esize()};
     const int esz_c = esize();
     const int c = d.img_c, h = d.img_h, w = d.img_w;
     const int h2 = h / 2, w2 = w / 2, h4 = h / 4, w4 = w / 4;
@@ -124,6 +130,8 @@ class PhyDNetModel : public Model {
       if (split) {
         f.a = arena.alloc(elems * 2);
         f.lo = arena.alloc(elems * 2);
+      } else if (f16) {
+        f.a = arena.alloc(elems * 2);
       } else {
         f.a = arena.alloc(elems * 4);
       }
@@ -131,14 +139,19 @@ class PhyDNetModel : public Model {
     };
     // split mode: frames as split-bf16 with 8 channels per pixel (zero padded): TMA-addressable, so encoder_E.c1 runs on
     // the tensor cores like every other conv; fp32 mode: plain fp32 NHWC frames for the CUDA-core kernel
-    const bool pad8 = split && backend == 0 && c <= 8;
+    const bool pad8 = tcfeat && backend == 0 && c <= 8;
     const int cs = pad8 ? 8 : c;
+    const bool direct_ok = f16 && pad8 && getenv("VPK_NO_STEM") == nullptr;
+    const bool stem_direct = direct_ok && conv_stem_supported(3, 2, 1, c, 32, h, w);
+    const bool tail_direct = direct_ok && deconv_tail_supported(3, 2, 1, 1, 32, c, h2, w2);
     Feat frames_in, frame_fb;            // [t_in] frames / the fed-back frame
     if (pad8) {
       frames_in.a = arena.alloc(px1 * 8 * 2 * t_in);
-      frames_in.lo = arena.alloc(px1 * 8 * 2 * t_in);
       frame_fb.a = arena.alloc(px1 * 8 * 2);
-      frame_fb.lo = arena.alloc(px1 * 8 * 2);
+      if (split) {
+        frames_in.lo = arena.alloc(px1 * 8 * 2 * t_in);
+        frame_fb.lo = arena.alloc(px1 * 8 * 2);
+      }
     } else {
       frames_in.a = arena.alloc(px1 * c * 4 * t_in);
       frame_fb.a = arena.alloc(px1 * c * 4);
@@ -173,7 +186,7 @@ class PhyDNetModel : public Model {
     float* dp = static_cast<float*>(arena.alloc(px4 * 64 * 4));
     Feat dsum = feat(px4 * 64), d1 = feat(px2 * 32), d2 = feat(px2 * 32);
     Feat dec_p, dec_r;                   // decoder inputs: PhyCell h and top ConvLSTM h as feature maps
-    if (split) {
+    if (tcfeat) {
       dec_p = feat(px4 * 64);
       dec_r = feat(px4 * 64);
     }
@@ -184,12 +197,12 @@ class PhyDNetModel : public Model {
       if (measure) return;
       const float* g = dev_f32(key + "weight", vec(key + "weight"), stream);
       const float* bta = dev_f32(key + "bias", vec(key + "bias"), stream);
-      const int out_dt = (kind == OUT_F32) ? DT_F32 : (kind == OUT_CELL) ? cdt : (split ? DT_BF16 : DT_F32);
+      const int out_dt = (kind == OUT_F32) ? DT_F32 : (kind == OUT_CELL) ? cdt : (split ? DT_BF16 : f16 ? DT_F16 : DT_F32);
       const bool two = (kind == OUT_FEAT) && split;
       Op op;
       op.name = "groupnorm " + key;
       if (groupnorm_smem_supported(HW, C, groups)) {
-        const int ok = two ? 2 : (out_dt == DT_BF16 ? 1 : 0);
+        const int ok = two ? 2 : (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
         op.fn = [=](cudaStream_t s, const RunCtx&) {
           launch_groupnorm_smem(in, out.a, out.lo, ok, add, B, HW, C, groups, g, bta, 1e-5f, actk, s);
         };
@@ -207,7 +220,7 @@ class PhyDNetModel : public Model {
                      int stride, OutKind kind, Feat out, const float* add, int cin_w = -1) {
       int oh, ow;
       const bool sp = split && !in_f32;
-      const ActInfo& ai = sp ? sa : f32a;
+      const ActInfo& ai = (tcfeat && !in_f32) ? sa : f32a;
       if (!transpose) {
         ConvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, in.a, hp(p + "main.0.weight"), hp(p + "main.0.bias"),
                    ACT_NONE, raw};
@@ -230,7 +243,10 @@ class PhyDNetModel : public Model {
       if (measure) return;
       Op op;
       op.name = name;
-      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_split_bf16(src, dst.a, dst.lo, static_cast<long long>(n), ns, s); };
+      op.fn = [=](cudaStream_t s, const RunCtx&) {
+        if (f16) launch_cast_f32_to_f16(src, dst.a, static_cast<long long>(n), ns, s);
+        else launch_split_bf16(src, dst.a, dst.lo, static_cast<long long>(n), ns, s);
+      };
       prog.body.push_back(std::move(op));
     };
 
@@ -239,8 +255,8 @@ class PhyDNetModel : public Model {
       pre.name = "frames_to_nhwc";
       pre.fn = [=](cudaStream_t s, const RunCtx& rc) {
         if (pad8)
-          launch_frames_to_nhwc8(rc.x, static_cast<long long>(t_in) * c * h * w, frames_in.a, frames_in.lo, B, t_in, c, h,
-                                 w, ns, s);
+          launch_frames_to_nhwc8(rc.x, static_cast<long long>(t_in) * c * h * w, frames_in.a, frames_in.lo, sa.dtype, B,
+                                 t_in, c, h, w, ns, s);
         else
           launch_frames_to_nhwc(rc.x, frames_in.a, DT_F32, B, t_in, c, h, w, ns, s);
       };
@@ -270,7 +286,21 @@ class PhyDNetModel : public Model {
         frame.lo = pad8 ? static_cast<char*>(frames_in.lo) + off : nullptr;
       }
       // ---- encoders ----
-      dcgan("encoder_E.c1.", false, frame, !pad8, h, w, cs, 32, 2, OUT_FEAT, e1, nullptr, c);
+      if (stem_direct) {   // image-channel stem: direct CUDA-core kernel (HBM-bound), then the usual GroupNorm pass
+        if (!measure) {
+          const std::string p = "encoder_E.c1.";
+          StemArgs sa_{frame.a, 1, B, h, w, c, 2, dev_f32(p + "stem.w", conv_stem_pack(hp(p + "main.0.weight"), 32, c, DT_F16), stream),
+                       dev_f32(p + "stem.b", vec(p + "main.0.bias"), stream), 32, ACT_NONE, raw, 1};
+          Op op;
+          op.name = p + "main.0.stem";
+          op.flops = 2.0 * static_cast<double>(px2) * 32 * 9 * c;
+          op.fn = [=](cudaStream_t s, const RunCtx&) { launch_conv_stem(sa_, ns, s); };
+          prog.body.push_back(std::move(op));
+        }
+        gn_op("encoder_E.c1.main.1.", raw, OUT_FEAT, e1, nullptr, h2 * w2, 32, 16, ACT_LEAKY);
+      } else {
+        dcgan("encoder_E.c1.", false, frame, !pad8, h, w, cs, 32, 2, OUT_FEAT, e1, nullptr, c);
+      }
       dcgan("encoder_E.c2.", false, e1, false, h2, w2, 32, 32, 1, OUT_FEAT, e2, nullptr);
       dcgan("encoder_E.c3.", false, e2, false, h2, w2, 32, 64, 2, OUT_FEAT, e3, nullptr);
       if (!branch_only) {
@@ -333,7 +363,7 @@ class PhyDNetModel : public Model {
       if (!decode) continue;
       // ---- decoders ----
       Feat in_p, in_r;
-      if (split) {
+      if (tcfeat) {
         if (!branch_only) split_op(hp_master[n_phy - 1], dec_p, px4 * 64, "split_phy_h");
         split_op(h_top32, dec_r, px4 * 64, "split_lstm_h");
         in_p = dec_p;
@@ -351,6 +381,21 @@ class PhyDNetModel : public Model {
       dcgan("decoder_Dr.upc2.", true, mid, false, h4, w4, 64, 64, 1, OUT_FEAT, dsum, branch_only ? nullptr : dp);
       dcgan("decoder_D.upc1.", true, dsum, false, h4, w4, 64, 32, 2, OUT_FEAT, d1, nullptr);
       dcgan("decoder_D.upc2.", true, d1, false, h2, w2, 32, 32, 1, OUT_FEAT, d2, nullptr);
+      if (tail_direct) {   // all four output parities + sigmoid + the fed-back 8-channel frame in one direct kernel
+        if (!measure) {
+          const std::string p = "decoder_D.upc3.";
+          TailArgs ta{d2.a, B, h2, w2, 32, c, dev_f32(p + "tail.w", deconv_tail_pack(hp(p + "weight"), 32, c, DT_F16), stream),
+                      dev_f32(p + "tail.b", vec(p + "bias"), stream), ACT_SIGMOID,
+                      out_stage + static_cast<size_t>(di) * c * h * w, static_cast<long long>(pred) * c * h * w,
+                      (di + 1 < pred) ? frame_fb.a : nullptr};
+          Op op;
+          op.name = p + "tail";
+          op.flops = 2.0 * static_cast<double>(px2) * 32 * 9 * c;
+          op.fn = [=](cudaStream_t s, const RunCtx&) { launch_deconv_tail(ta, ns, s); };
+          prog.body.push_back(std::move(op));
+        }
+        continue;
+      }
       {
         int oh, ow;
         DeconvArgs a{"decoder_D.upc3.", B, h2, w2, 32, c, 3, 2, 1, 1, d2.a, hp("decoder_D.upc3.weight"),
@@ -359,7 +404,7 @@ class PhyDNetModel : public Model {
         a.oB_nchw = static_cast<long long>(pred) * c * h * w;
         a.split = split;
         a.x_lo = d2.lo;
-        const ActInfo& ai = split ? sa : f32a;
+        const ActInfo& ai = tcfeat ? sa : f32a;
         add_conv(prog, deconv_spec(a, ai, &oh, &ow), measure, stream, ai.dtype);
         VPK_REQUIRE(oh == h && ow == w, "decoder output size mismatch");
       }
@@ -369,7 +414,7 @@ class PhyDNetModel : public Model {
         Op op;
         op.name = "feedback_frame";
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          if (pad8) launch_frames_to_nhwc8(src, bs, frame_fb.a, frame_fb.lo, B, 1, c, h, w, ns, s);
+          if (pad8) launch_frames_to_nhwc8(src, bs, frame_fb.a, frame_fb.lo, sa.dtype, B, 1, c, h, w, ns, s);
           else launch_frames_to_nhwc_strided(src, bs, frame_fb.a, DT_F32, B, 1, c, h, w, ns, s);
         };
         prog.body.push_back(std::move(op));
@@ -389,6 +434,7 @@ class PhyDNetModel : public Model {
 
  private:
   bool branch_only;
+  bool feat_split = false;     // VPK_FEAT_SPLIT=1: split-bf16 feature maps instead of fp16
   int n_phy = 1, hid = 49, kp = 7, n_lstm = 3, kl = 3;
 };
 

@@ -6,6 +6,14 @@
 namespace vpk {
 namespace ptx {
 
+// Programmatic dependent launch (PDL): a kernel launched with the programmatic-stream-serialization attribute may become
+// resident while its predecessor in the stream is still draining.  `pdl_launch_dependents` lets the NEXT kernel's CTAs be
+// scheduled as soon as every CTA of this grid has issued it (or exited); `pdl_wait` blocks until the PREVIOUS grid has
+// completed and its memory is visible -- everything before it may only touch data no earlier kernel writes (plans,
+// packed weights, biases, barrier / TMEM setup).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -430,12 +438,12 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-// Instruction descriptor for kind::f16 with bf16 A/B (both K-major), fp32 accumulate, M x N tile.
-__device__ __host__ __forceinline__ uint32_t idesc_bf16_f32(int M, int N) {
+// Instruction descriptor for kind::f16 with bf16 (or, f16 = true, fp16) A/B (both K-major), fp32 accumulate, M x N tile.
+__device__ __host__ __forceinline__ uint32_t idesc_bf16_f32(int M, int N, bool f16 = false) {
   uint32_t d = 0;
   d |= 1u << 4;                                   // D format  = F32
-  d |= 1u << 7;                                   // A format  = BF16
-  d |= 1u << 10;                                  // B format  = BF16
+  d |= (f16 ? 0u : 1u) << 7;                      // A format  = BF16 (1) / F16 (0)
+  d |= (f16 ? 0u : 1u) << 10;                     // B format  = BF16 (1) / F16 (0)
   d |= static_cast<uint32_t>(N >> 3) << 17;       // N / 8
   d |= static_cast<uint32_t>(M >> 4) << 24;       // M / 16
   return d;
