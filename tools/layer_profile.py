@@ -18,6 +18,9 @@ def main():
     t_in = ctx + (pred if key == "predrnn-pp" else 0)
     torch.manual_seed(0)
     m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+    if os.environ.get("PROFILE_NO_PEEPHOLES"):      # experiment: ConvLSTM without the Wci/Wcf/Wco terms
+        sd = {k: v for k, v in m.state_dict().items() if k.rsplit(".", 1)[-1] not in ("Wci", "Wcf", "Wco")}
+        m.load_state_dict(sd)
     x = torch.rand(B, t_in, *img, device="cuda")
     with torch.no_grad():
         for _ in range(2):

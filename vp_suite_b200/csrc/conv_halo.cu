@@ -563,6 +563,45 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             epi_tc_finish<KIND, G>(P.L.epi, et, ch_base + ch, bias, a, cur);
           }
         };
+        bool stats = false;
+        if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr;
+        if (stats) {
+          // conv feeding a GroupNorm: per-(sample, group) sum / sum of squares of the stored values, reduced over the
+          // 32 positions of the warp and added to gn_sums[b][group][2] (the plan guarantees Cn <= 64, Cn / gs <= 16,
+          // no residual); positions outside the image contribute zeros
+          if constexpr (KIND == EPI_BIAS_ACT) {
+            float gs16[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) gs16[i] = 0.f;
+            const int gsz = P.L.epi.gn_group_size;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int ch = half * 8 + 16 * k;
+              if (ch < Cn) {
+                uint32_t r[8 * G];
+                tmem_chunk(ch, r);
+                ptx::tmem_ld_wait();
+                float a[G][8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[0][j] = 0.f;
+                if (valid && ch_base + ch < C) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) a[0][j] = __uint_as_float(r[j]);
+                  epi_tc_finish<KIND, G>(P.L.epi, et, ch_base + ch, bias, a, ops0);
+                }
+                if (gsz == 2) gn_accum<2>(gs16, k, a[0]);
+                else if (gsz == 4) gn_accum<4>(gs16, k, a[0]);
+                else gn_accum<8>(gs16, k, a[0]);
+              }
+            }
+            const float tot = gn_warp_reduce16(gs16, lane);
+            const int vi = gn_lane_value(lane), pairi = vi >> 1, gpc = 8 / gsz;
+            const int kk = pairi / gpc, jj = pairi - kk * gpc;
+            const int chg = ch_base + half * 8 + 16 * kk;       // first channel of that chunk
+            if ((lane & 1) == 0 && b < P.L.B && half * 8 + 16 * kk < Cn && chg < C)
+              atomicAdd(P.L.epi.gn_sums + (static_cast<long long>(b) * (C / gsz) + chg / gsz + jj) * 2 + (vi & 1), tot);
+          }
+        } else
         for (int ch = half * 8; ch < Cn; ch += 32) {
           do_chunk(ch, ops0, ops1);
           if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
@@ -711,6 +750,12 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
   P.roll = (P.fast_epi && L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) ? 1 : 0;
   if (const char* env = getenv("VPK_EPI_ROLL")) P.roll = P.roll && atoi(env) != 0;
+  if (L.epi.gn_sums != nullptr) {
+    const int gs = L.epi.gn_group_size;
+    VPK_REQUIRE(P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0 && L.epi.res == nullptr &&
+                    (gs == 2 || gs == 4 || gs == 8) && L.Cn <= 64 && L.Cn / gs <= 16 && L.epi.C % gs == 0,
+                "halo plan: fused GroupNorm statistics need the lean BIAS_ACT epilogue, <= 64 channels per tile and groups of 2/4/8");
+  }
   P.tmem_cols = std::max(32, pow2_at_least(2 * P.tileN));
   VPK_REQUIRE(P.tmem_cols <= 512, "halo plan: accumulators exceed TMEM");
   const int HWp = kTW + 2 * radius, HHp = kTH + 2 * radius;

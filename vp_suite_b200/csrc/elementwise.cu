@@ -398,6 +398,66 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
   }
 }
 
+// GroupNorm apply pass for convs whose epilogue already accumulated the statistics (sums[b][group][2] = sum, sum of
+// squares over the group's channels x HW positions): y = (x - mean) * rstd * gamma + beta, LeakyReLU, optional fp32 add.
+// One block = one slice of ONE sample (blockIdx.y = sample), so scale / shift per channel are computed once per block.
+// OUT as in groupnorm_smem_kernel (0 fp32, 1 bf16, 3 fp16).  var = E[x^2] - mean^2 in fp32 (n <= a few thousand).
+template <int OUT>
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ in, void* __restrict__ out,
+                                                              const float* __restrict__ add,
+                                                              const float* __restrict__ sums, int HW, int C, int groups,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float eps, int act) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ float s_sc[256], s_sh[256];
+  const int b = blockIdx.y;
+  const int cg = C / groups;
+  if (threadIdx.x < C) {
+    const float n = static_cast<float>(cg) * HW;
+    const float* sp = sums + (static_cast<size_t>(b) * groups + threadIdx.x / cg) * 2;
+    const float mean = sp[0] / n;
+    const float var = fmaxf(sp[1] / n - mean * mean, 0.f);
+    const float sc = rsqrtf(var + eps) * gamma[threadIdx.x];
+    s_sc[threadIdx.x] = sc;
+    s_sh[threadIdx.x] = beta[threadIdx.x] - mean * sc;
+  }
+  __syncthreads();
+  const int n4 = HW * C / 4;
+  const size_t obase = static_cast<size_t>(b) * n4;
+  const float4* src = reinterpret_cast<const float4*>(in) + obase;
+  const float4* addp = add ? reinterpret_cast<const float4*>(add) + obase : nullptr;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
+    const int c0 = (i * 4) % C;
+    const float4 x = src[i];
+    float v[4] = {fmaf(x.x, s_sc[c0], s_sh[c0]), fmaf(x.y, s_sc[c0 + 1], s_sh[c0 + 1]), fmaf(x.z, s_sc[c0 + 2], s_sh[c0 + 2]),
+                  fmaf(x.w, s_sc[c0 + 3], s_sh[c0 + 3])};
+    if (act == ACT_LEAKY) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
+    }
+    if (addp) {
+      const float4 r = addp[i];
+      v[0] += r.x; v[1] += r.y; v[2] += r.z; v[3] += r.w;
+    }
+    if (OUT == 0) {
+      reinterpret_cast<float4*>(out)[obase + i] = make_float4(v[0], v[1], v[2], v[3]);
+    } else if (OUT == 3) {
+      const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);
+      uint2 hv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+      hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(out)[obase + i] = hv;
+    } else {
+      const __nv_bfloat162 h01 = __floats2bfloat162_rn(v[0], v[1]), h23 = __floats2bfloat162_rn(v[2], v[3]);
+      uint2 hv;
+      hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+      hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+      reinterpret_cast<uint2*>(out)[obase + i] = hv;
+    }
+  }
+}
+
 // fp32 -> split-bf16 (hi, lo); n % 4 == 0
 __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ hi,
                                   __nv_bfloat16* __restrict__ lo, long long n4) {
@@ -537,6 +597,27 @@ void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kin
   }
 #undef VPK_GNS
   VPK_CUDA(cudaGetLastError());
+}
+
+bool groupnorm_apply_supported(int HW, int C, int groups) {
+  return C % 4 == 0 && C <= 256 && C % groups == 0 && (HW * C) % 4 == 0;
+}
+
+void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int B, int HW,
+                            int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
+                            cudaStream_t stream) {
+  VPK_REQUIRE(groupnorm_apply_supported(HW, C, groups), "groupnorm_apply: unsupported shape");
+  VPK_REQUIRE(out_kind == 0 || out_kind == 1 || out_kind == 3, "groupnorm_apply: bad output kind");
+  const int n4 = HW * C / 4;
+  // ~2 waves of blocks over the whole batch, at least one block per sample
+  const int per = std::max(1, std::min((n4 + 1023) / 1024, std::max(1, 2 * num_sms * 8 / std::max(1, B))));
+  const dim3 grid(per, B);
+  if (out_kind == 0)
+    launch_pdl(groupnorm_apply_kernel<0>, grid, dim3(256), 0, stream, in, out, add, sums, HW, C, groups, gamma, beta, eps, act);
+  else if (out_kind == 1)
+    launch_pdl(groupnorm_apply_kernel<1>, grid, dim3(256), 0, stream, in, out, add, sums, HW, C, groups, gamma, beta, eps, act);
+  else
+    launch_pdl(groupnorm_apply_kernel<3>, grid, dim3(256), 0, stream, in, out, add, sums, HW, C, groups, gamma, beta, eps, act);
 }
 
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream) {

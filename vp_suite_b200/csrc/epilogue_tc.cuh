@@ -77,6 +77,42 @@ __device__ __forceinline__ void ld_f32x8(const float* p, float (&v)[8]) {
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 }
 
+// ---- GroupNorm statistics of a conv output, accumulated by the conv's own epilogue ---------------------------------
+// A thread owns up to four 8-channel chunks (k = 0..3) of one output position; s[(k * (8/GS) + j) * 2 + {0, 1}] holds the
+// sum / sum of squares of group j of chunk k (GS = channels per group, 8 % GS == 0): at most 16 values per thread.
+template <int GS>
+__device__ __forceinline__ void gn_accum(float (&s)[16], int k, const float (&v)[8]) {
+  constexpr int GPC = 8 / GS;
+#pragma unroll
+  for (int j = 0; j < GPC; ++j) {
+    const int idx = (k * GPC + j) * 2;
+    if (idx < 16) {
+#pragma unroll
+      for (int c = 0; c < GS; ++c) {
+        const float x = v[j * GS + c];
+        s[idx] += x;
+        s[idx + 1] = fmaf(x, x, s[idx + 1]);
+      }
+    }
+  }
+}
+// Sums the 16 per-thread values over the 32 lanes of a warp with 8 + 4 + 2 + 1 + 1 shuffles (each step halves the values a
+// lane keeps).  Returns the total of value gn_lane_value(lane) -- the same in lanes 2i and 2i + 1.
+__device__ __forceinline__ float gn_warp_reduce16(float (&s)[16], int lane) {
+#pragma unroll
+  for (int w = 8, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? s[i] : s[i + w];
+      const float keep = up ? s[i + w] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return s[0] + __shfl_xor_sync(0xffffffffu, s[0], 1);
+}
+__device__ __forceinline__ int gn_lane_value(int lane) { return lane >> 1; }   // bits 4..1 of the lane = value index
+
 // Whether the fast path may be used for this launch: whole 8-channel chunks, 16-byte aligned rows.
 __host__ __device__ inline bool epi_tc_fast_ok(const EpiParams& E) {
   if (E.C % 8 != 0) return false;
@@ -146,6 +182,8 @@ __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile&
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = acc[0][j];
     }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[0][j] = v[j];      // the activated values, for callers that accumulate statistics
     if (E.res != nullptr) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) v[j] += o.a[j];

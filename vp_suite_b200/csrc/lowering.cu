@@ -347,7 +347,9 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       L.epi.bias = q.bias;
       // the CUDA-core direct kernel is for what the tensor-core path cannot address (image-channel stems) and for
       // single-K-chunk heads; anything larger runs ~4x faster through tcgen05 even at N = 16 (profiles/)
-      bc.use_direct = direct_eligible(L) && !(backend == 0 && tc_eligible(L, dtype) && L.K_pad > 64);
+      // (a one-tap transposed-conv parity with 32 output channels: 39 us direct vs 15 us through the halo kernel)
+      bc.use_direct = direct_eligible(L) && !(backend == 0 && tc_eligible(L, dtype) &&
+                                              (L.K_pad > 64 || L.N_pad >= 32 || L.epi.gn_sums != nullptr));
       // The halo-reuse kernel is the default for everything it can address.  (Early in the round the per-tap CTA-pair
       // kernel was ~25 % faster at tile N >= 192; with the flat single-thread issue loop, two taps per weight slot and
       // the whole-tile operand prefetch the halo kernel wins everywhere: cfg 3 gate GEMMs 1.51 -> 1.63 PFLOP/s, cfg 5
@@ -363,6 +365,8 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         bc.use_tc = false;
         VPK_REQUIRE(bc.use_halo, "fused projection epilogue needs the tcgen05 halo kernel for " + spec.name);
       }
+      VPK_REQUIRE(L.epi.gn_sums == nullptr || bc.use_halo,
+                  "fused GroupNorm statistics need the tcgen05 halo kernel for " + spec.name);
       if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);
       if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);
     }
