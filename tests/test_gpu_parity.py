@@ -94,8 +94,8 @@ def test_tcgen05_agrees_with_cuda_core_kernel(manifest, name):
             outs.append(m(x, pred_frames=meta["pred"])[0].cpu().numpy())
     errs = _frame_errs(outs[0], outs[1])
     # PhyDNet-family programs are not operand-identical between the two backends: the CUDA-core program reads fp32 image
-    # frames in encoder_E.c1 and uses the two-pass GroupNorm, the tcgen05 program fp16 frames and statistics accumulated
-    # in the conv epilogue (atomics: summation order varies run to run) -- both sit ~1e-3 from the reference
+    # frames in encoder_E.c1 and uses the two-pass GroupNorm, the tcgen05 program fp16 frames and one-pass statistics
+    # from the conv epilogue -- both sit ~1e-3 from the reference
     tol = 4e-3 if meta["key"] in ("phy", "convlstm-branch") else 2e-3
     assert max(errs) <= tol, f"{name}: tcgen05 vs CUDA-core per-frame diff {errs}"
 
@@ -253,4 +253,5 @@ def test_every_tcgen05_kernel_variant_agrees_with_cuda_cores(manifest, name, pai
     with torch.no_grad():
         ref = ref_m(x, pred_frames=meta["pred"])[0].cpu().numpy()
     errs = _frame_errs(got, ref)
-    assert max(errs) <= 2e-3, f"{name} pair={pair} halo={halo}: {errs}"
+    tol = 4e-3 if meta["key"] in ("phy", "convlstm-branch") else 2e-3     # see test_tcgen05_agrees_with_cuda_core_kernel
+    assert max(errs) <= tol, f"{name} pair={pair} halo={halo}: {errs}"

@@ -110,9 +110,13 @@ struct EpiParams {
   const float* proj_w;    // device fp32 [proj_n][C]
   const float* proj_b;    // device fp32 [proj_n] or nullptr
   int proj_n;
-  // optional per-(b, group) statistics for a following GroupNorm: sums[b][g][2] (sum, sum of squares)
+  // optional statistics for a following GroupNorm, written by the tcgen05 halo kernel's BIAS_ACT epilogue:
+  // gn_sums[b][slot][group][2] = (sum, sum of squares) of one warp's 32 positions; slot = gn_slot0 + (tile index inside
+  // the image) * 4 + TMEM lane quadrant.  Every slot is written exactly once per launch (plain stores, no atomics), so
+  // the apply pass adds them in a fixed order: results do not depend on the schedule.
   float* gn_sums;
   int gn_group_size;      // channels per group (0 = disabled)
+  int gn_slot0, gn_nslots;
 };
 
 struct ConvLaunch {

@@ -566,9 +566,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         bool stats = false;
         if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr;
         if (stats) {
-          // conv feeding a GroupNorm: per-(sample, group) sum / sum of squares of the stored values, reduced over the
-          // 32 positions of the warp and added to gn_sums[b][group][2] (the plan guarantees Cn <= 64, Cn / gs <= 16,
-          // no residual); positions outside the image contribute zeros
+          // conv feeding a GroupNorm: per-group sum / sum of squares of the stored values, reduced over the 32 positions
+          // of the warp and stored to this warp's slot of gn_sums (the plan guarantees Cn <= 64, Cn / gs <= 16, no
+          // residual); positions outside the image contribute zeros
           if constexpr (KIND == EPI_BIAS_ACT) {
             float gs16[16];
 #pragma unroll
@@ -598,8 +598,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const int vi = gn_lane_value(lane), pairi = vi >> 1, gpc = 8 / gsz;
             const int kk = pairi / gpc, jj = pairi - kk * gpc;
             const int chg = ch_base + half * 8 + 16 * kk;       // first channel of that chunk
-            if ((lane & 1) == 0 && b < P.L.B && half * 8 + 16 * kk < Cn && chg < C)
-              atomicAdd(P.L.epi.gn_sums + (static_cast<long long>(b) * (C / gsz) + chg / gsz + jj) * 2 + (vi & 1), tot);
+            if ((lane & 1) == 0 && b < P.L.B && half * 8 + 16 * kk < Cn && chg < C) {
+              const int slot = P.L.epi.gn_slot0 + (mt % (P.tiles_x * P.tiles_y)) * 4 + quad;
+              P.L.epi.gn_sums[((static_cast<long long>(b) * P.L.epi.gn_nslots + slot) * (C / gsz) + chg / gsz + jj) * 2 +
+                              (vi & 1)] = tot;
+            }
           }
         } else
         for (int ch = half * 8; ch < Cn; ch += 32) {

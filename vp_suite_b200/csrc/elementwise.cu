@@ -233,7 +233,9 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict
                                                             const float* __restrict__ beta, float eps, int act) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
-  __shared__ float s_acc[64], s_mean[64], s_rstd[64];
+  // per-thread partial sums go to s_part[thread] and are added in a fixed order: no atomics, results do not depend on
+  // the warp schedule
+  __shared__ float s_part[256], s_mean[64], s_rstd[64];
   const int b = blockIdx.x;
   const int tx = threadIdx.x % TC, ty = threadIdx.x / TC, rows = 256 / TC;
   const int cg = C / groups;
@@ -241,17 +243,18 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict
   const int g = live ? tx / cg : 0;
   const TI* ip = in + static_cast<size_t>(b) * HW * Cs_in + tx;
   const float n = static_cast<float>(cg) * HW;
-  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.f;
-  __syncthreads();
+  auto group_total = [&](int grp) {           // sum of the partials of group grp: rows x cg entries, fixed order
+    float t = 0.f;
+    for (int r = 0; r < rows; ++r)
+      for (int c = 0; c < cg; ++c) t += s_part[r * TC + grp * cg + c];
+    return t;
+  };
   float a = 0.f;
   if (live)
     for (int p = ty; p < HW; p += rows) a += to_f32(ip[static_cast<size_t>(p) * Cs_in]);
-  if (live) atomicAdd(&s_acc[g], a);
+  s_part[threadIdx.x] = a;
   __syncthreads();
-  if (threadIdx.x < groups) {
-    s_mean[threadIdx.x] = s_acc[threadIdx.x] / n;
-    s_acc[threadIdx.x] = 0.f;
-  }
+  if (threadIdx.x < groups) s_mean[threadIdx.x] = group_total(threadIdx.x) / n;
   __syncthreads();
   const float mean = s_mean[g];
   a = 0.f;
@@ -260,9 +263,9 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict
       const float d = to_f32(ip[static_cast<size_t>(p) * Cs_in]) - mean;
       a = fmaf(d, d, a);
     }
-  if (live) atomicAdd(&s_acc[g], a);
+  s_part[threadIdx.x] = a;
   __syncthreads();
-  if (threadIdx.x < groups) s_rstd[threadIdx.x] = rsqrtf(s_acc[threadIdx.x] / n + eps);
+  if (threadIdx.x < groups) s_rstd[threadIdx.x] = rsqrtf(group_total(threadIdx.x) / n + eps);
   __syncthreads();
   if (!live) return;
   const float sc = s_rstd[g] * gamma[tx];
@@ -285,8 +288,11 @@ __global__ void __launch_bounds__(256) groupnorm_act_kernel(const TI* __restrict
 // three-product tensor-core convs that replace fp32 convs).  STAGED = false re-reads global memory instead (samples
 // larger than shared memory).
 // lanes of a warp that own the same four channels (4 * lane distance is a multiple of C) are summed by shuffles first,
-// then one lane per channel quad adds to the per-group accumulators in shared memory
-__device__ __forceinline__ void gn_commit(float* s_acc, int C, int cg, int c0, float a0, float a1, float a2, float a3) {
+// then one lane per channel quad stores the warp's partial to s_part[warp][channel]; gn_total() adds the partials of a
+// group in a fixed order (no atomics: results do not depend on the warp schedule).  s_part must be zero where a warp
+// owns no lanes of a channel, so it is cleared before each pass.
+constexpr int kGnMaxC = 256;
+__device__ __forceinline__ void gn_commit(float (*s_part)[kGnMaxC], int C, int c0, float a0, float a1, float a2, float a3) {
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
     if ((o * 4) % C == 0) {
@@ -296,13 +302,19 @@ __device__ __forceinline__ void gn_commit(float* s_acc, int C, int cg, int c0, f
       a3 += __shfl_xor_sync(0xffffffffu, a3, o);
     }
   }
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (lane * 4 < C) {
-    atomicAdd(&s_acc[(c0 + 0) / cg], a0);
-    atomicAdd(&s_acc[(c0 + 1) / cg], a1);
-    atomicAdd(&s_acc[(c0 + 2) / cg], a2);
-    atomicAdd(&s_acc[(c0 + 3) / cg], a3);
+    s_part[warp][c0 + 0] = a0;
+    s_part[warp][c0 + 1] = a1;
+    s_part[warp][c0 + 2] = a2;
+    s_part[warp][c0 + 3] = a3;
   }
+}
+__device__ __forceinline__ float gn_total(float (*s_part)[kGnMaxC], int nwarps, int grp, int cg) {
+  float t = 0.f;
+  for (int w = 0; w < nwarps; ++w)
+    for (int c = 0; c < cg; ++c) t += s_part[w][grp * cg + c];
+  return t;
 }
 
 constexpr int kGnThreads = 512;
@@ -315,14 +327,18 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   extern __shared__ float4 gn_stage[];
-  __shared__ float s_acc[64], s_mean[64], s_rstd[64];
+  __shared__ float s_part[kGnThreads / 32][kGnMaxC];
+  __shared__ float s_mean[64], s_rstd[64];
   const int b = blockIdx.x;
   const int n4 = HW * C / 4;
   const float4* src = reinterpret_cast<const float4*>(in + static_cast<size_t>(b) * HW * C);
   const int c0 = (threadIdx.x * 4) % C;
   const int cg = C / groups;
   const float n = static_cast<float>(cg) * HW;
-  if (threadIdx.x < 64) s_acc[threadIdx.x] = 0.f;
+  auto clear_part = [&]() {
+    for (int i = threadIdx.x; i < (kGnThreads / 32) * C; i += kGnThreads) s_part[i / C][i % C] = 0.f;
+  };
+  clear_part();
   __syncthreads();
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   for (int i = threadIdx.x; i < n4; i += kGnThreads) {
@@ -330,12 +346,11 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
     if (STAGED) gn_stage[i] = v;
     a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
   }
-  gn_commit(s_acc, C, cg, c0, a0, a1, a2, a3);
+  gn_commit(s_part, C, c0, a0, a1, a2, a3);
   __syncthreads();
-  if (threadIdx.x < groups) {
-    s_mean[threadIdx.x] = s_acc[threadIdx.x] / n;
-    s_acc[threadIdx.x] = 0.f;
-  }
+  if (threadIdx.x < groups) s_mean[threadIdx.x] = gn_total(s_part, kGnThreads / 32, threadIdx.x, cg) / n;
+  __syncthreads();
+  clear_part();
   __syncthreads();
   const float m0 = s_mean[(c0 + 0) / cg], m1 = s_mean[(c0 + 1) / cg], m2 = s_mean[(c0 + 2) / cg],
               m3 = s_mean[(c0 + 3) / cg];
@@ -347,9 +362,9 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
     a2 = fmaf(v.z - m2, v.z - m2, a2);
     a3 = fmaf(v.w - m3, v.w - m3, a3);
   }
-  gn_commit(s_acc, C, cg, c0, a0, a1, a2, a3);
+  gn_commit(s_part, C, c0, a0, a1, a2, a3);
   __syncthreads();
-  if (threadIdx.x < groups) s_rstd[threadIdx.x] = rsqrtf(s_acc[threadIdx.x] / n + eps);
+  if (threadIdx.x < groups) s_rstd[threadIdx.x] = rsqrtf(gn_total(s_part, kGnThreads / 32, threadIdx.x, cg) / n + eps);
   __syncthreads();
   float sc[4], sh[4];
   const float mm[4] = {m0, m1, m2, m3};
@@ -398,14 +413,16 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
   }
 }
 
-// GroupNorm apply pass for convs whose epilogue already accumulated the statistics (sums[b][group][2] = sum, sum of
-// squares over the group's channels x HW positions): y = (x - mean) * rstd * gamma + beta, LeakyReLU, optional fp32 add.
+// GroupNorm apply pass for convs whose epilogue already produced partial statistics (sums[b][slot][group][2] = sum, sum
+// of squares of one warp's positions; nslots slots, added here in slot order -- deterministic):
+// y = (x - mean) * rstd * gamma + beta, LeakyReLU, optional fp32 add.
 // One block = one slice of ONE sample (blockIdx.y = sample), so scale / shift per channel are computed once per block.
 // OUT as in groupnorm_smem_kernel (0 fp32, 1 bf16, 3 fp16).  var = E[x^2] - mean^2 in fp32 (n <= a few thousand).
 template <int OUT>
 __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ in, void* __restrict__ out,
                                                               const float* __restrict__ add,
-                                                              const float* __restrict__ sums, int HW, int C, int groups,
+                                                              const float* __restrict__ sums, int nslots, int HW, int C,
+                                                              int groups,
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float eps, int act) {
   ptx::pdl_launch_dependents();
@@ -415,9 +432,16 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
   const int cg = C / groups;
   if (threadIdx.x < C) {
     const float n = static_cast<float>(cg) * HW;
-    const float* sp = sums + (static_cast<size_t>(b) * groups + threadIdx.x / cg) * 2;
-    const float mean = sp[0] / n;
-    const float var = fmaxf(sp[1] / n - mean * mean, 0.f);
+    const float2* sp = reinterpret_cast<const float2*>(sums) + static_cast<size_t>(b) * nslots * groups + threadIdx.x / cg;
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll 8
+    for (int sl = 0; sl < nslots; ++sl) {
+      const float2 v = sp[static_cast<size_t>(sl) * groups];
+      s0 += v.x;
+      s1 += v.y;
+    }
+    const float mean = s0 / n;
+    const float var = fmaxf(s1 / n - mean * mean, 0.f);
     const float sc = rsqrtf(var + eps) * gamma[threadIdx.x];
     s_sc[threadIdx.x] = sc;
     s_sh[threadIdx.x] = beta[threadIdx.x] - mean * sc;
@@ -565,7 +589,7 @@ void launch_groupnorm_act(const void* in, int in_dtype, void* out, int out_dtype
 }
 
 bool groupnorm_smem_supported(int HW, int C, int groups) {
-  return C >= 4 && (kGnThreads * 4) % C == 0 && groups <= 64 && C % groups == 0 && (HW * C) % 4 == 0;
+  return C >= 4 && C <= kGnMaxC && (kGnThreads * 4) % C == 0 && groups <= 64 && C % groups == 0 && (HW * C) % 4 == 0;
 }
 
 void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kind, const float* add, int B, int HW,
@@ -603,8 +627,8 @@ bool groupnorm_apply_supported(int HW, int C, int groups) {
   return C % 4 == 0 && C <= 256 && C % groups == 0 && (HW * C) % 4 == 0;
 }
 
-void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int B, int HW,
-                            int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
+void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int nslots,
+                            int B, int HW, int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
                             cudaStream_t stream) {
   VPK_REQUIRE(groupnorm_apply_supported(HW, C, groups), "groupnorm_apply: unsupported shape");
   VPK_REQUIRE(out_kind == 0 || out_kind == 1 || out_kind == 3, "groupnorm_apply: bad output kind");
@@ -613,11 +637,11 @@ void launch_groupnorm_apply(const float* in, void* out, int out_kind, const floa
   const int per = std::max(1, std::min((n4 + 1023) / 1024, std::max(1, 2 * num_sms * 8 / std::max(1, B))));
   const dim3 grid(per, B);
   if (out_kind == 0)
-    launch_pdl(groupnorm_apply_kernel<0>, grid, dim3(256), 0, stream, in, out, add, sums, HW, C, groups, gamma, beta, eps, act);
+    launch_pdl(groupnorm_apply_kernel<0>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act);
   else if (out_kind == 1)
-    launch_pdl(groupnorm_apply_kernel<1>, grid, dim3(256), 0, stream, in, out, add, sums, HW, C, groups, gamma, beta, eps, act);
+    launch_pdl(groupnorm_apply_kernel<1>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act);
   else
-    launch_pdl(groupnorm_apply_kernel<3>, grid, dim3(256), 0, stream, in, out, add, sums, HW, C, groups, gamma, beta, eps, act);
+    launch_pdl(groupnorm_apply_kernel<3>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act);
 }
 
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream) {

@@ -48,10 +48,10 @@ void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kin
                            int C, int groups, const float* gamma, const float* beta, float eps, int act,
                            cudaStream_t stream);
 // fp32 -> split-bf16: hi = bf16(v), lo = bf16(v - hi)
-// GroupNorm whose statistics the producing conv's epilogue accumulated: sums[b][group][2] (sum, sum of squares)
+// GroupNorm whose partial statistics the producing conv's epilogue wrote: sums[b][slot][group][2] (sum, sum of squares)
 bool groupnorm_apply_supported(int HW, int C, int groups);
-void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int B, int HW,
-                            int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
+void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int nslots,
+                            int B, int HW, int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
                             cudaStream_t stream);
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);   // n % 4 == 0
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);

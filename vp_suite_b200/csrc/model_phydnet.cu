@@ -191,17 +191,17 @@ class PhyDNetModel : public Model {
       dec_r = feat(px4 * 64);
     }
 
-    // GroupNorm statistics accumulated by the producing conv's epilogue (tcgen05 path, fp16 feature maps): one
-    // [B][16][2] fp32 slice per DCGAN block and step, all zeroed by one memset at the start of the rollout
+    // GroupNorm partial statistics written by the producing conv's epilogue (tcgen05 path, fp16 feature maps): one
+    // region [B][slots][16][2] fp32 reused by every DCGAN block (stream order separates producer / consumer pairs);
+    // slots = (phases) x (8x16 tiles per image) x 4 warps, at most 4 x 8 x 4 for the 32 x 32 maps of a 64 x 64 image
     const char* halo_env = getenv("VPK_TC_HALO");          // tests force the per-tap kernels with VPK_TC_HALO=0
     const bool fuse_gn = f16 && backend == 0 && getenv("VPK_NO_FUSED_GN") == nullptr && (halo_env == nullptr || atoi(halo_env) != 0);
-    const size_t gn_slice = static_cast<size_t>(B) * 16 * 2;
-    const size_t gn_slices = static_cast<size_t>((t_in - 1) + pred) * 14;
-    float* gn_region = static_cast<float*>(arena.alloc(gn_slices * gn_slice * sizeof(float)));
-    size_t gn_used = 0;
+    auto gn_tiles = [](int H, int W) { return ((H + 15) / 16) * ((W + 7) / 8); };
+    const int gn_max_slots = 4 * 4 * std::max(gn_tiles(h2, w2), gn_tiles(h4, w4));
+    float* gn_region = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * gn_max_slots * 16 * 2 * sizeof(float)));
     // GroupNorm (+ LeakyReLU) of the fp32 conv output `in` into a feature map / cell operand / fp32 tensor
     auto gn_op = [&](const std::string& key, const float* in, OutKind kind, Feat out, const float* add, int HW, int C,
-                     int groups, int actk, const float* sums = nullptr) {
+                     int groups, int actk, const float* sums = nullptr, int nslots = 0) {
       if (measure) return;
       const float* g = dev_f32(key + "weight", vec(key + "weight"), stream);
       const float* bta = dev_f32(key + "bias", vec(key + "bias"), stream);
@@ -212,7 +212,7 @@ class PhyDNetModel : public Model {
       if (sums != nullptr) {
         const int ok = (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_groupnorm_apply(in, out.a, ok, add, sums, B, HW, C, groups, g, bta, 1e-5f, actk, ns, s);
+          launch_groupnorm_apply(in, out.a, ok, add, sums, nslots, B, HW, C, groups, g, bta, 1e-5f, actk, ns, s);
         };
       } else if (groupnorm_smem_supported(HW, C, groups)) {
         const int ok = two ? 2 : (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
@@ -236,16 +236,21 @@ class PhyDNetModel : public Model {
       const ActInfo& ai = (tcfeat && !in_f32) ? sa : f32a;
       const int gsz = Cout / 16;
       float* sums = nullptr;
-      if (fuse_gn && !in_f32 && Cout % 16 == 0 && (gsz == 2 || gsz == 4 || gsz == 8) && Cout <= 64 ) {
-        VPK_REQUIRE(gn_used < gn_slices, "GroupNorm statistics region exhausted");
-        sums = gn_region + gn_used++ * gn_slice;
-      }
+      if (fuse_gn && !in_f32 && Cout % 16 == 0 && (gsz == 2 || gsz == 4 || gsz == 8) && Cout <= 64) sums = gn_region;
+      int nslots = 0;
       auto with_stats = [&](ConvSpec sp_) {
-        if (sums != nullptr)
+        if (sums != nullptr) {
+          int slot0 = 0;
           for (PhaseSpec& ph : sp_.phases) {
             ph.epi.gn_sums = sums;
             ph.epi.gn_group_size = gsz;
+            ph.epi.gn_slot0 = slot0;
+            slot0 += 4 * gn_tiles(ph.H, ph.W);
           }
+          nslots = slot0;
+          VPK_REQUIRE(nslots <= gn_max_slots, "GroupNorm statistics region too small");
+          for (PhaseSpec& ph : sp_.phases) ph.epi.gn_nslots = nslots;
+        }
         return sp_;
       };
       if (!transpose) {
@@ -265,7 +270,7 @@ class PhyDNetModel : public Model {
         add_conv(prog, with_stats(deconv_spec(a, ai, &oh, &ow)), measure, stream, ai.dtype);
       }
       if (sums != nullptr && !groupnorm_apply_supported(oh * ow, Cout, 16)) VPK_THROW(1, "groupnorm_apply: unsupported shape");
-      gn_op(p + "main.1.", raw, kind, out, add, oh * ow, Cout, 16, ACT_LEAKY, sums);
+      gn_op(p + "main.1.", raw, kind, out, add, oh * ow, Cout, 16, ACT_LEAKY, sums, nslots);
     };
     auto split_op = [&](const float* src, Feat dst, size_t n, const char* name) {
       if (measure) return;
@@ -289,7 +294,6 @@ class PhyDNetModel : public Model {
           launch_frames_to_nhwc(rc.x, frames_in.a, DT_F32, B, t_in, c, h, w, ns, s);
       };
       prog.pre.push_back(std::move(pre));
-      if (fuse_gn) add_memset(prog, gn_region, gn_slices * gn_slice * sizeof(float), "zero_gn_sums");
       if (!branch_only) {
         for (int j = 0; j < n_phy; ++j) {
           add_memset(prog, hp_master[j], px4 * 64 * 4, "zero_hp");
