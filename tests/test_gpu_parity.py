@@ -255,3 +255,21 @@ def test_every_tcgen05_kernel_variant_agrees_with_cuda_cores(manifest, name, pai
     errs = _frame_errs(got, ref)
     tol = 4e-3 if meta["key"] in ("phy", "convlstm-branch") else 2e-3     # see test_tcgen05_agrees_with_cuda_core_kernel
     assert max(errs) <= tol, f"{name} pair={pair} halo={halo}: {errs}"
+
+
+@pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "phy_1x64"])
+def test_weight_multicast_clusters_reproduce_the_pair_kernel(manifest, name, monkeypatch):
+    """VPK_HALO_MC=2 forces the four-CTA-cluster form of the halo kernel (two CTA pairs sharing every streamed weight
+    tile through TMA multicast; picked by size otherwise).  Same tiles, same MMA order: the frames must be identical."""
+    meta = manifest["models"][name]
+    x = _input(meta).cuda()
+    monkeypatch.setenv("VPK_TC_PAIR", "1")
+    monkeypatch.setenv("VPK_HALO_MC", "0")
+    m0, _ = _build(meta["key"], meta, precision="bf16")
+    with torch.no_grad():
+        ref = m0(x, pred_frames=meta["pred"])[0].clone()
+    monkeypatch.setenv("VPK_HALO_MC", "2")
+    m1, _ = _build(meta["key"], meta, precision="bf16")
+    with torch.no_grad():
+        got = m1(x, pred_frames=meta["pred"])[0].clone()
+    assert torch.equal(got, ref)

@@ -108,10 +108,23 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   float* s_proj = s_bias + P.L.N_pad;      // MODE 3: [4][N_pad] projection weights, then 4 projection biases
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = PAIR ? ptx::cluster_ctarank() : 0u;
+  // PAIR: clusters of 2 (one CTA pair) or, P.mc, of 4 = two pairs (ranks 0,1 and 2,3) that walk the SAME sequence of
+  // (N tile, tap) steps on different M tiles and share every weight tile through TMA multicast
+  const bool MC = PAIR && P.mc != 0;
+  const uint32_t crank = PAIR ? ptx::cluster_ctarank() : 0u;     // rank in the cluster
+  const uint32_t rank = crank & 1u;                               // rank in the CTA pair
+  const uint32_t prank = crank >> 1;                              // pair in the cluster (0 unless MC)
+  const uint32_t lead = crank & ~1u;                              // cluster rank of this pair's leader CTA
   const bool leader = rank == 0;
-  const int unit0 = PAIR ? (blockIdx.x >> 1) : blockIdx.x;
-  const int nunits = PAIR ? (gridDim.x >> 1) : gridDim.x;
+  const int csize = MC ? 4 : (PAIR ? 2 : 1);
+  const int unit0 = blockIdx.x / csize;
+  const int nunits = gridDim.x / csize;
+  const uint16_t pair_mask = static_cast<uint16_t>(3u << lead);  // both CTAs of this pair
+  // M tile of iteration t for this CTA (t / n_tiles = M unit of the cluster)
+  auto m_tile_of = [&](int t) {
+    const int mu = t / P.n_tiles;
+    return MC ? ((mu * 2 + static_cast<int>(prank)) * 2 + static_cast<int>(rank)) : (mu * (PAIR ? 2 : 1) + static_cast<int>(rank));
+  };
   const int nblocks = P.nblocks;
 
   for (int i = threadIdx.x; i < nblocks; i += kHaloThreads) s_blocks[i] = P.blocks[i];
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
     for (int i = 0; i < SB; ++i) {
       ptx::mbar_init(bfull + 8 * i, prod);
-      ptx::mbar_init(bempty + 8 * i, 1);
+      ptx::mbar_init(bempty + 8 * i, MC ? 2 : 1);      // MC: a slot is free once BOTH pairs' MMAs have consumed it
     }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(tfull + 8 * i, 1);
@@ -196,7 +209,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   if (threadIdx.x == 0) stamp(2);
 
   const int m_tiles = P.L.B * P.tiles_y * P.tiles_x;
-  const int units = PAIR ? (m_tiles + 1) / 2 : m_tiles;
+  const int units = MC ? ((m_tiles + 1) / 2 + 1) / 2 : (PAIR ? (m_tiles + 1) / 2 : m_tiles);   // M units per cluster
   const int total = units * P.n_tiles;
   const int rad = P.P;
   const int HWp = kTW + 2 * rad;
@@ -210,7 +223,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       int sa = 0;
       uint32_t ph = 0;
       for (int t = unit0; t < total; t += nunits) {
-        const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+        const int mt = m_tile_of(t);
         const int x0 = (mt % P.tiles_x) * kTW;
         const int y0 = ((mt / P.tiles_x) % P.tiles_y) * kTH;
         const int b0 = mt / (P.tiles_x * P.tiles_y);            // odd tail of a pair: b0 == B -> zero fill
@@ -220,9 +233,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const uint32_t fb = afull + 8 * sa;
           const uint32_t dst = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
           if (P.debug & 4) {
-            if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, 0);
+            if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, lead);
           } else if constexpr (PAIR) {
-            if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * a_box_bytes); else ptx::mbar_arrive_cluster(fb, 0);
+            if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * a_box_bytes); else ptx::mbar_arrive_cluster(fb, lead);
             ptx::tma_load_4d_pair(&P.amap[blk.src], fb, dst, blk.c0, x0 - rad, y0 - rad, b0);
           } else {
             ptx::mbar_arrive_expect_tx(fb, a_box_bytes);
@@ -240,10 +253,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int n0 = static_cast<int>(rank) * (PAIR ? rowsB : 0);
         const uint32_t dst = ptx::smem_u32(smem_b);
         if (P.debug & 4) {
-          if (leader) ptx::mbar_arrive(bfull); else ptx::mbar_arrive_cluster(bfull, 0);
+          if (leader) ptx::mbar_arrive(bfull); else ptx::mbar_arrive_cluster(bfull, lead);
         } else {
           if constexpr (PAIR) {
-            if (leader) ptx::mbar_arrive_expect_tx(bfull, ncta * b_box_bytes * P.ntaps); else ptx::mbar_arrive_cluster(bfull, 0);
+            if (leader) ptx::mbar_arrive_expect_tx(bfull, ncta * b_box_bytes * P.ntaps); else ptx::mbar_arrive_cluster(bfull, lead);
           } else {
             ptx::mbar_arrive_expect_tx(bfull, b_box_bytes * P.ntaps);
           }
@@ -266,17 +279,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const uint32_t fb = bfull + 8 * sb;
             const uint32_t dst = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
             if (P.debug & 4) {
-              if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, 0);
+              if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, lead);
             } else {
               if constexpr (PAIR) {
-                if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * b_box_bytes * gn); else ptx::mbar_arrive_cluster(fb, 0);
+                if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * b_box_bytes * gn); else ptx::mbar_arrive_cluster(fb, lead);
               } else {
                 ptx::mbar_arrive_expect_tx(fb, b_box_bytes * gn);
               }
               for (int q = 0; q < gn; ++q) {
                 const int wk = s_taps[blk.first_tap + q0 + q].wk;
-                if constexpr (PAIR) ptx::tma_load_2d_pair(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0);
-                else ptx::tma_load_2d(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0);
+                if constexpr (PAIR) {
+                  if (MC) {    // taps alternate between the two pairs' producers; each load feeds the same-half CTA of both
+                    if ((q & 1) == static_cast<int>(prank))
+                      ptx::tma_load_2d_pair_mc(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0,
+                                               static_cast<uint16_t>((1u << rank) | (4u << rank)));
+                  } else {
+                    ptx::tma_load_2d_pair(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0);
+                  }
+                } else {
+                  ptx::tma_load_2d(&P.bmap, fb, dst + q * P.b_tap_stride, wk, n0);
+                }
               }
             }
             if (++sb == SB) { sb = 0; ph ^= 1u; }
@@ -303,10 +325,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       uint32_t pha = 0, phb = 0;
       uint64_t a_d = adesc0, b_d = bdesc0;
       int iter = 0;
+#ifdef VPK_TRACE
+      long long w_acc = 0, w_a = 0, w_b = 0, t_begin = clock64();     // cycles the MMA thread spent waiting, by cause
+#define VPK_TIMED(counter, stmt) do { const long long c0_ = clock64(); stmt; counter += clock64() - c0_; } while (0)
+#else
+#define VPK_TIMED(counter, stmt) stmt
+#endif
       if (P.resident && unit0 < total) ptx::mbar_wait_spin(bfull, 0);
       for (int t = unit0; t < total; t += nunits, ++iter) {
         const int acc = iter & 1;
-        ptx::mbar_wait_spin(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u);
+        VPK_TIMED(w_acc, ptx::mbar_wait_spin(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u));
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
         uint32_t accum = 0;
@@ -319,12 +347,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const uint32_t flags = cur.x >> 16;
           if (flags & (kTapFirstOfBlock | kTapFirstOfGroup)) {
             if (flags & kTapFirstOfBlock) {
-              ptx::mbar_wait_spin(afull + 8 * sa, pha);
+              VPK_TIMED(w_a, ptx::mbar_wait_spin(afull + 8 * sa, pha));
               a_d = adesc0 + static_cast<uint32_t>(sa) * a_slot_u;
               if (iter == 0 && i == 0) stamp(3);
             }
             if (flags & kTapFirstOfGroup) {
-              ptx::mbar_wait_spin(bfull + 8 * sb, phb);
+              VPK_TIMED(w_b, ptx::mbar_wait_spin(bfull + 8 * sb, phb));
               b_d = bdesc0 + static_cast<uint32_t>(sb) * b_slot_u;
             }
           }
@@ -347,22 +375,28 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if (lflags & (kTapLastOfGroup | kTapLastOfBlock)) {
             const uint32_t flags = lflags;
             if (flags & kTapLastOfGroup) {
-              if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, 3);
+              if constexpr (PAIR) ptx::mma_commit_pair(bempty + 8 * sb, MC ? static_cast<uint16_t>(0xF) : pair_mask);
               else ptx::mma_commit(bempty + 8 * sb);
               if (++sb == SB) { sb = 0; phb ^= 1u; }
             }
             if (flags & kTapLastOfBlock) {
-              if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, 3);
+              if constexpr (PAIR) ptx::mma_commit_pair(aempty + 8 * sa, pair_mask);
               else ptx::mma_commit(aempty + 8 * sa);
               if (++sa == SA) { sa = 0; pha ^= 1u; }
             }
           }
         }
-        if constexpr (PAIR) ptx::mma_commit_pair(tfull + 8 * acc, 3);
+        if constexpr (PAIR) ptx::mma_commit_pair(tfull + 8 * acc, pair_mask);
         else ptx::mma_commit(tfull + 8 * acc);
         if (iter == 0) stamp(4);
       }
       stamp(5);
+#ifdef VPK_TRACE
+      if (trace)
+        printf("halo trace N=%d taps=%d: MMA thread %lld cycles for %d tiles: waiting for accumulator %lld, activations %lld, "
+               "weights %lld\n", tileN, ntaps, clock64() - t_begin, iter, w_acc, w_a, w_b);
+#endif
+#undef VPK_TIMED
     }
     __syncwarp();
   } else if (warp >= 3) {
@@ -389,7 +423,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           LstmPeep pps[PPD];
           auto locate = [&](int t, LstmTile& et, int& chb) -> bool {
             const int nt = t % P.n_tiles;
-            const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+            const int mt = m_tile_of(t);
             const int x = (mt % P.tiles_x) * kTW + rx;
             const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
             const int b = mt / (P.tiles_x * P.tiles_y);
@@ -453,7 +487,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             ptx::tc_fence_before();
             __syncwarp();            // every lane's tcgen05.ld has completed (wait::ld) and is fenced: one arrival per warp
             if (lane == 0) {
-              if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+              if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
               else ptx::mbar_arrive(tempty + 8 * acc);
             }
             et = etn;
@@ -479,7 +513,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const EpiParams& E = P.L.epi;
       const int np = P.L.N_pad;
       for (int t = unit0; t < total; t += nunits, ++iter) {
-        const int mt = t * (PAIR ? 2 : 1) + static_cast<int>(rank);          // n_tiles == 1
+        const int mt = m_tile_of(t);                                         // n_tiles == 1
         const int x = (mt % P.tiles_x) * kTW + rx;
         const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
         const int b = mt / (P.tiles_x * P.tiles_y);
@@ -515,7 +549,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         ptx::tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+          if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
           else ptx::mbar_arrive(tempty + 8 * acc);
         }
       }
@@ -523,7 +557,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if constexpr (!rolled && MODE != 3)
     for (int t = unit0; t < total; t += nunits, ++iter) {
       const int nt = t % P.n_tiles;
-      const int mt = (t / P.n_tiles) * (PAIR ? 2 : 1) + static_cast<int>(rank);
+      const int mt = m_tile_of(t);
       const int x = (mt % P.tiles_x) * kTW + rx;
       const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
       const int b = mt / (P.tiles_x * P.tiles_y);
@@ -637,7 +671,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       ptx::tc_fence_before();
       __syncwarp();              // one arrival per warp (512 per-thread remote arrivals per tile serialised on the barrier)
       if (lane == 0) {
-        if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, 0);
+        if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
         else ptx::mbar_arrive(tempty + 8 * acc);
       }
     }
@@ -706,13 +740,38 @@ template <int KIND, bool PAIR, int MODE> void launch_one(const HaloPlan& P, cuda
                          static_cast<int>(kMaxSmem));
   });
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(static_cast<unsigned>(P.grid));
+  int grid = P.grid;
+  if (PAIR && P.mc) {
+    // four-CTA clusters must sit inside one GPC: ask how many fit at once and keep the persistent grid to that
+    static int max_clusters = -1;
+    static unsigned max_for_smem = 0;
+    if (max_clusters < 0 || P.smem_bytes > max_for_smem) {
+      cudaLaunchConfig_t q{};
+      q.gridDim = dim3(static_cast<unsigned>(P.grid));
+      q.blockDim = dim3(kHaloThreads);
+      q.dynamicSmemBytes = P.smem_bytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 4;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      VPK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_halo_kernel<KIND, PAIR, MODE>, &q));
+      max_clusters = std::max(1, n);
+      max_for_smem = P.smem_bytes;
+      if (getenv("VPK_VERBOSE")) fprintf(stderr, "conv_halo: %d clusters of 4 CTAs fit (%u bytes of shared memory)\n", n, P.smem_bytes);
+    }
+    grid = std::min(grid, 4 * max_clusters);
+  }
+  cfg.gridDim = dim3(static_cast<unsigned>(grid));
   cfg.blockDim = dim3(kHaloThreads);
   cfg.dynamicSmemBytes = P.smem_bytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = PAIR ? 2 : 1;
+  attr[0].val.clusterDim.x = PAIR ? (P.mc ? 4 : 2) : 1;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -815,6 +874,21 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
     }
   }
   P.smem_bytes = fixed + P.SA * P.a_slot_bytes + P.SB * P.b_slot_bytes;
+  // Streamed weights are the largest L2 -> SM stream of the gate GEMMs (27 taps x 32 KB per 256 x 256 tile against
+  // 69 KB of activations; the MMA thread waits for weight tiles 25-34 % of its time, phase timeline in profiles/).
+  // VPK_HALO_MC=1 (size rule) / 2 (always) runs clusters of four CTAs that fetch every weight tile once for two CTA
+  // pairs (TMA multicast).  Measured on the B200: +6.7 % per SM on the N = 256 gate GEMM, but only 33 four-CTA
+  // clusters are co-resident (132 of 148 SMs; a cluster must sit inside one GPC), so the whole launch is 4.5 % SLOWER
+  // (cfg 5: 285.7 vs 277.0 ms) -- off by default; the pair kernel keeps all 148 SMs busy.
+  P.mc = 0;
+  if (const char* env = getenv("VPK_HALO_MC")) {
+    const int v = atoi(env);
+    P.mc = (P.pair && !P.resident && (v > 1 || (v == 1 && (m_tiles + 1) / 2 * P.n_tiles >= 4ll * num_sms))) ? 1 : 0;
+  }
+  if (P.mc) {
+    const long long cl_units = ((m_tiles + 1) / 2 + 1) / 2 * P.n_tiles;
+    P.grid = 4 * static_cast<int>(std::min<long long>(cl_units, num_sms / 4));
+  } else
   if (P.pair) {
     const long long units = (m_tiles + 1) / 2 * P.n_tiles;
     P.grid = 2 * static_cast<int>(std::min<long long>(units, num_sms / 2));

@@ -51,6 +51,8 @@ struct alignas(64) HaloPlan {
   unsigned smem_bytes;
   int grid;
   int pair;                    // cta_group::2
+  int mc;                      // 1: clusters of FOUR CTAs = two CTA pairs that run the same weight-tile sequence on different
+                               //    M tiles; every weight tile is fetched from L2 once per cluster (TMA multicast)
   int fast_epi;                // lean compile-time-specialised epilogue (epilogue_tc.cuh) usable for this launch
   int roll;                    // ConvLSTM epilogue with a whole tile of operands in flight (lstm_ops_load / lstm_finish)
   int debug;

@@ -237,6 +237,16 @@ __device__ __forceinline__ void tma_load_2d_pair(const void* desc, uint32_t bar,
       ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
       : "memory");
 }
+// the same, multicast: the box lands at the same shared-memory offset of every CTA in `cta_mask`, and each copy signals
+// the barrier at this offset in ITS pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair_mc(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1), "h"(cta_mask)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_4d_pair(const void* desc, uint32_t bar, uint32_t dst, int c0, int c1, int c2,
                                                  int c3) {
   asm volatile(
