@@ -269,7 +269,7 @@ def main():
         mb = model.microbatch_size(B)
         traffic = tj["dram_bytes_in_capture"] / tj["sequences_in_capture"] * mb
         traffic_note = (f"DRAM bytes per launch of {tj['kernel']} at this run's microbatch of {mb} sequences, scaled from the "
-                        f"ncu capture at {tj['sequences_in_capture']} sequences (profiles/r01_ncu_halo_rnn1_deconv3_cfg5_b64.md); "
+                        f"ncu capture at {tj['sequences_in_capture']} sequences ({tj.get('profile', 'profiles/')}); "
                         f"algorithmic bytes of that launch = {tj['algorithmic_bytes_per_position'] * tj['positions_per_sequence'] * mb:.3e}")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,

@@ -828,7 +828,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   // several taps share one weight slot (one barrier round trip) when the tiles are small: per-tap barrier latency,
   // not bytes, bounds the small-N layers
   // (measured, cfg 5: two taps per 16 KB-tile slot instead of one = -8 % on the N = 256 gate GEMM, -12 % at N = 192)
-  P.bgroup = std::max(1, std::min<int>(9, static_cast<int>(32768u / P.b_tap_stride)));
+  // (40 KB slots: three 12 KB taps at N = 192 -- forecaster.rnn2 760 -> 719 us, encoder.rnn2 589 -> 573 us -- two 16 KB taps at 256)
+  P.bgroup = std::max(1, std::min<int>(9, static_cast<int>(40960u / P.b_tap_stride)));
   if (const char* env = getenv("VPK_HALO_BGROUP")) P.bgroup = std::max(1, atoi(env));
   P.b_slot_bytes = P.bgroup * P.b_tap_stride;
   // Resident weights: with one N tile and <= 96 KB of weight tiles the ring (and its per-group wait + commit in the
