@@ -246,7 +246,7 @@ def main():
         sampler.start()
     dev_ms, _, metric_vec = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    launches = model.last_launch_count() * args.steps
+    launches = (model.last_launch_count() + 2) * args.steps       # rollout kernels + the two metric-reduction kernels
     ms_per_step = dev_ms / args.steps
     frames = B * pred * world
     value = frames / (ms_per_step * 1e-3)

@@ -162,6 +162,15 @@ int vpk_phycell_cell_step(vpk_cell* cell, int32_t batch, const float* x, const f
 
 void vpk_cell_destroy(vpk_cell* cell);
 
+/* ---- evaluation metrics (replaces the per-measure torch reductions + .item() syncs of
+ *      vp_suite/measure/metric_provider.py:34-73 for MSE / PSNR) ----------------------
+ * pred, target: device fp32 [batch, frames, chw] (contiguous [b, p, c, h, w] tensors).  Writes the fp64 device vector
+ * out[2 * frames + 1] = [ sum_b sum_chw (p - y)^2 per frame | sum_b 10 * log10(mean_chw (p - y)^2) per frame | batch ]
+ * (vp_suite/measure/image_wise.py:19-31, 53-75 before the means): the partial sums one NCCL all-reduce then adds over
+ * ranks.  scratch: device fp64 [batch * frames].  Deterministic (fixed-order reductions).  Enqueued on `stream`. */
+int vpk_metric_partial_sums(const float* pred, const float* target, int32_t batch, int32_t frames, int64_t chw,
+                            double* scratch, double* out, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------------------------ */
 const char* vpk_last_error(void);
 const char* vpk_version(void);

@@ -273,3 +273,22 @@ def test_weight_multicast_clusters_reproduce_the_pair_kernel(manifest, name, mon
     with torch.no_grad():
         got = m1(x, pred_frames=meta["pred"])[0].clone()
     assert torch.equal(got, ref)
+
+
+def test_metric_partial_sums_kernel_matches_the_torch_definition():
+    """vpk_metric_partial_sums (per-horizon MSE / PSNR partial sums on the device) against the torch expression that
+    defines them (vp_suite/measure/image_wise.py:19-31, 53-75), incl. an odd frame size (scalar path) and B > 256."""
+    from vp_suite_b200 import evaluation as E
+    dev = _cuda()
+    g = torch.Generator().manual_seed(5)
+    for shape in ((300, 4, 3, 16, 16), (5, 7, 1, 9, 7)):
+        pred = torch.rand(shape, generator=g)
+        tgt = torch.rand(shape, generator=g)
+        ref = E.metric_partial_sums(pred, tgt)                      # CPU tensors: the torch definition
+        got = E.metric_partial_sums(pred.to(dev), tgt.to(dev)).cpu()
+        assert got.shape == ref.shape
+        assert torch.allclose(got, ref, rtol=1e-6, atol=1e-9), (got - ref).abs().max()
+        again = E.metric_partial_sums(pred.to(dev), tgt.to(dev)).cpu()
+        assert torch.equal(got, again)                               # fixed-order reductions
+        m = E.finalize_metrics(got)
+        assert len(m["mse"]) == shape[1] and m["sequences"] == shape[0]

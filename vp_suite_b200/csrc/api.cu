@@ -5,6 +5,7 @@
 
 #include "../../include/vpk.h"
 #include "cells.h"
+#include "elementwise.h"
 #include "model.h"
 
 namespace {
@@ -37,6 +38,19 @@ struct vpk_cell {
 };
 
 extern "C" {
+
+int vpk_metric_partial_sums(const float* pred, const float* target, int32_t batch, int32_t frames, int64_t chw,
+                            double* scratch, double* out, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(pred && target && scratch && out, "vpk_metric_partial_sums: null pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      VPK_THROW(VPK_ERR_CUDA, "no CUDA device: libvpk has no CPU fallback");
+    }
+    vpk::launch_metric_partial_sums(pred, target, batch, frames, chw, scratch, out, static_cast<cudaStream_t>(stream));
+  });
+}
 
 const char* vpk_last_error(void) { return g_last_error.c_str(); }
 const char* vpk_version(void) { return "libvpk 0.1 (sm_100a)"; }

@@ -151,6 +151,70 @@ __global__ void cast_kernel(const float* __restrict__ in, __nv_bfloat16* __restr
   if ((n & 1) && blockIdx.x == 0 && threadIdx.x == 0) out[n - 1] = __float2bfloat16_rn(in[n - 1]);
 }
 
+// Evaluation metrics, stage 1: one block per (sample, frame) sums (p - y)^2 over the frame: fp32 products, fp64
+// accumulation per thread, warp shuffles, then the 8 warp totals in order (deterministic).
+__global__ void __launch_bounds__(256) metric_sse_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                         long long chw, double* __restrict__ sse) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ double s_w[8];
+  const float* p = pred + static_cast<long long>(blockIdx.x) * chw;
+  const float* y = tgt + static_cast<long long>(blockIdx.x) * chw;
+  double acc = 0.0;
+  if ((chw & 3) == 0 && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(y)) & 15) == 0) {
+    const long long n4 = chw >> 2;
+    for (long long i = threadIdx.x; i < n4; i += 256) {
+      const float4 a = reinterpret_cast<const float4*>(p)[i], b = reinterpret_cast<const float4*>(y)[i];
+      const float d0 = a.x - b.x, d1 = a.y - b.y, d2 = a.z - b.z, d3 = a.w - b.w;
+      acc += static_cast<double>(d0 * d0) + static_cast<double>(d1 * d1) + static_cast<double>(d2 * d2) +
+             static_cast<double>(d3 * d3);
+    }
+  } else {
+    for (long long i = threadIdx.x; i < chw; i += 256) {
+      const float d = p[i] - y[i];
+      acc += static_cast<double>(d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    sse[blockIdx.x] = t;
+  }
+}
+// stage 2: one block per frame adds the batch in a fixed order (thread-strided partials, then a tree in shared memory)
+__global__ void __launch_bounds__(256) metric_frame_sums_kernel(const double* __restrict__ sse, int B, int P, long long chw,
+                                                                double* __restrict__ out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ double s_a[256], s_b[256];
+  const int t = blockIdx.x;
+  double a = 0.0, b = 0.0;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const double v = sse[static_cast<long long>(i) * P + t];
+    a += v;
+    b += 10.0 * log10(v / static_cast<double>(chw));
+  }
+  s_a[threadIdx.x] = a;
+  s_b[threadIdx.x] = b;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) {
+      s_a[threadIdx.x] += s_a[threadIdx.x + o];
+      s_b[threadIdx.x] += s_b[threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[t] = s_a[0];
+    out[P + t] = s_b[0];
+    if (t == 0) out[2 * P] = static_cast<double>(B);
+  }
+}
+
 // fp32 -> fp16, n % 4 == 0
 __global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n4) {
   ptx::pdl_launch_dependents();
@@ -554,6 +618,13 @@ void launch_frames_to_nhwc(const float* x, void* out, int dtype, int B, int T, i
 void launch_cast_f32_to_bf16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream) {
   launch_pdl(cast_kernel, dim3(grid_for((n + 1) / 2, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__nv_bfloat16*>(out), n);
   VPK_CUDA(cudaGetLastError());
+}
+
+void launch_metric_partial_sums(const float* pred, const float* target, int B, int P, long long chw, double* scratch,
+                                double* out, cudaStream_t stream) {
+  VPK_REQUIRE(B > 0 && P > 0 && chw > 0, "metric_partial_sums: empty input");
+  launch_pdl(metric_sse_kernel, dim3(static_cast<unsigned>(B) * P), dim3(256), 0, stream, pred, target, chw, scratch);
+  launch_pdl(metric_frame_sums_kernel, dim3(P), dim3(256), 0, stream, static_cast<const double*>(scratch), B, P, chw, out);
 }
 
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream) {

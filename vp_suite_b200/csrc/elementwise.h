@@ -53,6 +53,10 @@ bool groupnorm_apply_supported(int HW, int C, int groups);
 void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int nslots,
                             int B, int HW, int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
                             cudaStream_t stream);
+// per-(sample, frame) sum of squared errors (fp64), then per-frame sums over the batch of the SSE and of
+// 10 * log10(SSE / chw); out = [frames SSE sums | frames log sums | batch]
+void launch_metric_partial_sums(const float* pred, const float* target, int B, int P, long long chw, double* scratch,
+                                double* out, cudaStream_t stream);
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);   // n % 4 == 0
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
 

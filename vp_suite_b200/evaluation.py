@@ -26,13 +26,34 @@ def shard_bounds(batch: int, rank: int, world: int):
 
 def metric_partial_sums(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """fp64 vector [P mse sums | P psnr sums | count] for this rank's sequences; entry t is the sum over the rank's
-    batch of the per-frame value at predicted frame t (horizon means are prefix means of these, see finalize)."""
+    batch of the per-frame value at predicted frame t (horizon means are prefix means of these, see finalize).
+    CUDA tensors go through libvpk's two reduction kernels (``vpk_metric_partial_sums``: no intermediate tensors, no
+    host sync, deterministic); the torch expression below is the definition and serves CPU tensors (gloo tests)."""
+    if pred.is_cuda:
+        return _native_partial_sums(pred, target)
     se = (pred - target).pow(2).flatten(2)                              # [b, P, chw]
     per_frame = se.sum(-1, dtype=torch.float64)                         # [b, P] sum_chw, fp64 accumulation
     mse_t = per_frame.sum(0)                                            # sum_b sum_chw
     psnr_t = (10.0 * torch.log10(per_frame / se.shape[-1])).sum(0)      # sum_b 10 log10(mean_chw)
     n = torch.tensor([float(pred.shape[0])], dtype=torch.float64, device=pred.device)
     return torch.cat([mse_t, psnr_t, n])
+
+
+def _native_partial_sums(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    from . import _native as N
+    if pred.shape != target.shape or pred.dim() < 3:
+        raise ValueError(f"metric_partial_sums: shapes {tuple(pred.shape)} / {tuple(target.shape)}")
+    b, p = pred.shape[:2]
+    chw = pred[0, 0].numel()
+    pred = pred.contiguous().float()
+    target = target.to(pred.device).contiguous().float()
+    scratch = torch.empty(b * p, dtype=torch.float64, device=pred.device)
+    out = torch.empty(2 * p + 1, dtype=torch.float64, device=pred.device)
+    stream = torch.cuda.current_stream(pred.device).cuda_stream
+    with torch.cuda.device(pred.device):
+        N.check(N.lib().vpk_metric_partial_sums(N.ptr(pred), N.ptr(target), b, p, chw, N.ptr(scratch), N.ptr(out),
+                                                stream))
+    return out
 
 
 def all_reduce_sums(vec: torch.Tensor, group=None) -> torch.Tensor:
