@@ -34,9 +34,13 @@ WORKLOADS = {
     "cfg3": ("predrnn-pp", (1, 64, 64), 10, 10, 256, "predrnn-pp 1x64x64 10+10"),
     "cfg4": ("phy", (3, 64, 64), 2, 10, 256, "phy 3x64x64 2+10"),
     "cfg5": ("convlstm-shi", (3, 128, 128), 10, 20, 512, "convlstm-shi 3x128x128 10+20"),
+    # ST-LSTM with layer_norm=True, same shape as cfg3
+    "cfg3ln": ("predrnn-pp", (1, 64, 64), 10, 10, 256, "predrnn-pp layer_norm=True 1x64x64 10+10"),
 }
+WORKLOAD_KW = {"cfg3ln": {"layer_norm": True}}          # extra model kwargs of a workload
 # "required" GFLOP per sequence of the whole rollout; informational
-REQUIRED_GFLOP_PER_SEQ = {"cfg1": 81.03, "cfg2": 26.319, "cfg3": 168.787, "cfg4": 17.74, "cfg5": 524.31}
+REQUIRED_GFLOP_PER_SEQ = {"cfg1": 81.03, "cfg2": 26.319, "cfg3": 168.787, "cfg4": 17.74, "cfg5": 524.31,
+                          "cfg3ln": 168.787}
 
 
 def parse():
@@ -125,7 +129,8 @@ def cpu_reference_throughput(workload, seconds_budget=20.0, threads=None):
     key, img, ctx, pred, _, _ = WORKLOADS[workload]
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sd = synth_state_dict(SHAPES[key](img), 0, 1.0)
+    kw = WORKLOAD_KW.get(workload)
+    sd = synth_state_dict(SHAPES[key](img, kw) if kw else SHAPES[key](img), 0, 1.0)
     b = 2 if workload == "cfg5" else 8
     t_in = ctx + (pred if key == "predrnn-pp" else 0)
     x = synth_frames(b, t_in, *img, seed=1234)
@@ -193,7 +198,7 @@ def main():
     torch.manual_seed(0)      # random-init weights of the named architecture (torch default init, as the reference)
     model = V.MODEL_CLASSES[key](f"cuda:{local}", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
                                  precision=args.precision, max_microbatch=args.microbatch,
-                                 use_cuda_graph=bool(use_graph)).eval()
+                                 use_cuda_graph=bool(use_graph), **WORKLOAD_KW.get(args.workload, {})).eval()
 
     g = torch.Generator(device="cpu").manual_seed(1234 + rank)
     x_host = torch.rand((B, t_in, *img), generator=g, dtype=torch.float32).pin_memory()

@@ -67,6 +67,7 @@ typedef struct vpk_model_desc {
   /* predrnn-pp (predrnn_v2.py:34-43) */
   int32_t patch_size, num_layers, num_hidden[8], filter_size;
   float decoupling_loss_scale;
+  int32_t layer_norm;        /* 1: nn.LayerNorm([k*C, H/p, W/p]) after conv_x/h/m/o (model_blocks/predrnn.py:24-40)  */
   /* phy / convlstm-branch (models/phydnet.py:28-33) */
   int32_t phycell_n_layers, phycell_channels, phycell_kernel_size;
   int32_t convlstm_n_layers, convlstm_hidden_dims[8], convlstm_kernel_size;

@@ -65,15 +65,24 @@ def convlstm_cell_step(x, h, c, w, b):
 # --------------------------------------------------------------------------------------------------
 # ST-LSTM v2 cell, layer_norm=False             (vp_suite/model_blocks/predrnn.py:57-83)
 # --------------------------------------------------------------------------------------------------
-def stlstm_step(x, h, c, m, w_x, w_h, w_m, w_o, w_last, forget_bias=1.0):
+def stlstm_step(x, h, c, m, w_x, w_h, w_m, w_o, w_last, forget_bias=1.0, ln=None):
     """conv_x/conv_h/conv_m are bias-free 'same' convs (:58-60); split orders (:61-63); gate math
     (:65-76); o uses conv_o over cat(c', m') (:78-79); h' = o * tanh(conv_last(mem)) (:80).
-    Returns (h', c', m', delta_c, delta_m) (:82)."""
+    Returns (h', c', m', delta_c, delta_m) (:82).
+    ``ln`` (layer_norm=True, :24-40): dict with 'x', 'h', 'm', 'o' -> (weight, bias) of the nn.LayerNorm([C', H, W])
+    that follows conv_x / conv_h / conv_m / conv_o (eps 1e-5, statistics over C', H, W of each sample)."""
     C = w_h.shape[0] // 4
     pad = w_x.shape[-1] // 2
-    X = F.conv2d(x, w_x, None, padding=pad)
-    H = F.conv2d(h, w_h, None, padding=pad)
-    M = F.conv2d(m, w_m, None, padding=pad)
+
+    def norm(t, key):
+        if ln is None:
+            return t
+        w, b = ln[key]
+        return F.layer_norm(t, tuple(w.shape), w, b, eps=1e-5)
+
+    X = norm(F.conv2d(x, w_x, None, padding=pad), "x")
+    H = norm(F.conv2d(h, w_h, None, padding=pad), "h")
+    M = norm(F.conv2d(m, w_m, None, padding=pad), "m")
     i_x, f_x, g_x, ip_x, fp_x, gp_x, o_x = torch.split(X, C, dim=1)
     i_h, f_h, g_h, o_h = torch.split(H, C, dim=1)
     i_m, f_m, g_m = torch.split(M, C, dim=1)
@@ -88,7 +97,7 @@ def stlstm_step(x, h, c, m, w_x, w_h, w_m, w_o, w_last, forget_bias=1.0):
     delta_m = ip * gp
     m_new = fp * m + delta_m
     mem = torch.cat([c_new, m_new], dim=1)
-    o_t = torch.sigmoid(o_x + o_h + F.conv2d(mem, w_o, None, padding=pad))
+    o_t = torch.sigmoid(o_x + o_h + norm(F.conv2d(mem, w_o, None, padding=pad), "o"))
     h_new = o_t * torch.tanh(F.conv2d(mem, w_last, None))
     return h_new, c_new, m_new, delta_c, delta_m
 

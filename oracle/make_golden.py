@@ -32,7 +32,11 @@ MODEL_CASES = [
     ("predrnn_3x32",  "predrnn-pp",   (3, 32, 32), 1, 2,     2,    3,     5,     1.5),
     ("phy_3x64",      "phy",          (3, 64, 64), 2, 2,     3,    4,     42,    1.5),
     ("phy_1x64",      "phy",          (1, 64, 64), 1, 3,     2,    5,     43,    1.5),
+    ("predrnn_ln_1x64", "predrnn-pp", (1, 64, 64), 2, 3,     3,    7,     101,   1.5),
+    ("predrnn_ln_3x32", "predrnn-pp", (3, 32, 32), 1, 2,     2,    8,     6,     1.5),
 ]
+# extra constructor kwargs of a case (the manifest records them as `model_kwargs`)
+MODEL_KW = {"predrnn_ln_1x64": {"layer_norm": True}, "predrnn_ln_3x32": {"layer_norm": True}}
 
 
 def shapes_of(module):
@@ -42,7 +46,8 @@ def shapes_of(module):
 def run_models(classes, manifest):
     for name, key, img, b, t, p, wseed, xseed, gain in MODEL_CASES:
         torch.manual_seed(0)
-        m = classes[key]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+        kw = MODEL_KW.get(name, {})
+        m = classes[key]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0], **kw).eval()
         shp = shapes_of(m)
         m.load_state_dict(synth_state_dict(shp, wseed, gain))
         total_t = t + p if key == "predrnn-pp" else t          # NEEDS_COMPLETE_INPUT (predrnn_v2.py:32)
@@ -55,7 +60,7 @@ def run_models(classes, manifest):
             arrays["loss"] = np.asarray(float(lv), dtype=np.float64)
         np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
         manifest["models"][name] = dict(key=key, img_shape=list(img), batch=b, context=t, pred=p,
-                                        wseed=wseed, xseed=xseed, gain=gain, shapes=shp,
+                                        wseed=wseed, xseed=xseed, gain=gain, shapes=shp, model_kwargs=kw,
                                         pred_std=float(pred.std()), pred_mean=float(pred.mean()))
         print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
 

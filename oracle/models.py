@@ -126,9 +126,12 @@ def predrnn_v2_forward(sd, x, pred_frames, cfg=None, return_states=False):
         for i in range(L):
             inp = net if i == 0 else h_t[i - 1]
             pre = f"cell_list.{i}."
+            ln = None
+            if pre + "conv_x.1.weight" in sd:       # layer_norm=True (model_blocks/predrnn.py:24-40)
+                ln = {k: (sd[f"{pre}conv_{k}.1.weight"], sd[f"{pre}conv_{k}.1.bias"]) for k in "xhmo"}
             h_t[i], c_t[i], memory, dc, dm = B.stlstm_step(
                 inp, h_t[i], c_t[i], memory, sd[pre + "conv_x.0.weight"], sd[pre + "conv_h.0.weight"],
-                sd[pre + "conv_m.0.weight"], sd[pre + "conv_o.0.weight"], sd[pre + "conv_last.weight"])
+                sd[pre + "conv_m.0.weight"], sd[pre + "conv_o.0.weight"], sd[pre + "conv_last.weight"], ln=ln)
             dcn = F.normalize(F.conv2d(dc, w_adapter).flatten(2), dim=2)
             dmn = F.normalize(F.conv2d(dm, w_adapter).flatten(2), dim=2)
             dec.append(torch.mean(torch.abs(F.cosine_similarity(dcn, dmn, dim=2))))

@@ -64,6 +64,11 @@ def predrnn_shapes(img_shape, cfg=None):
         out[f"cell_list.{i}.conv_m.0.weight"] = (3 * C, C, k, k)
         out[f"cell_list.{i}.conv_o.0.weight"] = (C, 2 * C, k, k)
         out[f"cell_list.{i}.conv_last.weight"] = (C, 2 * C, 1, 1)
+        if cfg.get("layer_norm"):                       # nn.LayerNorm([k * C, H / p, W / p]) after conv_x/h/m/o
+            hp, wp = img_shape[1] // p, img_shape[2] // p
+            for name, mult in (("x", 7), ("h", 4), ("m", 3), ("o", 1)):
+                out[f"cell_list.{i}.conv_{name}.1.weight"] = (mult * C, hp, wp)
+                out[f"cell_list.{i}.conv_{name}.1.bias"] = (mult * C, hp, wp)
     out["conv_last.weight"] = (p * p * c, hid[L - 1], 1, 1)
     out["adapter.weight"] = (hid[0], hid[0], 1, 1)
     return out

@@ -30,7 +30,7 @@ def synth_tensor(key, shape, seed=0, gain=1.5):
             fan_in = shape[0] * shape[2] * shape[3]
         a = gain / math.sqrt(fan_in)
         return (torch.rand(shape, generator=g) * 2 - 1) * a
-    if leaf == "weight" and len(shape) == 1:           # norm scale
+    if leaf == "weight" and len(shape) in (1, 3):      # norm scale (GroupNorm [C]; LayerNorm [C, H, W])
         return 1.0 + (torch.rand(shape, generator=g) * 2 - 1) * 0.2
     return (torch.rand(shape, generator=g) * 2 - 1) * 0.1
 

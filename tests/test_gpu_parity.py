@@ -27,6 +27,7 @@ def _cuda():
 def _build(key, meta, **kw):
     import vp_suite_b200 as V
     dev = _cuda()
+    kw = {**(meta.get("model_kwargs") or {}), **kw}          # e.g. layer_norm=True for the predrnn_ln_* cases
     m = V.MODEL_CLASSES[key](dev, img_shape=tuple(meta["img_shape"]), action_size=0, tensor_value_range=[0.0, 1.0],
                              **kw).eval()
     sd = synth_state_dict(meta["shapes"], meta["wseed"], meta["gain"])
@@ -44,7 +45,8 @@ def _frame_errs(a, b):
     return [float(d[:, t].max()) for t in range(d.shape[1])]
 
 
-EF_CASES = ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64", "branch_1x64"]
+EF_CASES = ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64", "branch_1x64",
+            "predrnn_ln_1x64", "predrnn_ln_3x32"]
 
 
 @pytest.mark.parametrize("name", EF_CASES)

@@ -20,7 +20,7 @@ def _case(manifest, name):
 
 
 @pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64",
-                                  "branch_1x64"])
+                                  "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32"])
 def test_model_rollout_matches_reference(manifest, name):
     meta, sd, x = _case(manifest, name)
     gold = load_golden(name)
@@ -104,5 +104,6 @@ def test_shape_listing_matches_reference(manifest):
     from oracle.shapes import SHAPES
     for name, meta in manifest["models"].items():
         want = {k: tuple(v) for k, v in meta["shapes"].items()}
-        got = SHAPES[meta["key"]](tuple(meta["img_shape"]))
+        kw = meta.get("model_kwargs") or {}
+        got = SHAPES[meta["key"]](tuple(meta["img_shape"]), kw) if kw else SHAPES[meta["key"]](tuple(meta["img_shape"]))
         assert got == want, (name, set(got.items()) ^ set(want.items()))

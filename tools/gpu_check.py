@@ -28,7 +28,8 @@ def main():
         for precision, backend in (("fp32", "auto"), ("bf16", "simt"), ("bf16", "auto")):
             try:
                 m = V.MODEL_CLASSES[meta["key"]]("cuda:0", img_shape=tuple(meta["img_shape"]), action_size=0,
-                                                 tensor_value_range=[0.0, 1.0], precision=precision, backend=backend)
+                                                 tensor_value_range=[0.0, 1.0], precision=precision, backend=backend,
+                                                 **(meta.get("model_kwargs") or {}))
                 m.load_state_dict(sd)
                 with torch.no_grad():
                     pred, aux = m(x, pred_frames=meta["pred"])

@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import vp_suite_b200 as V          # noqa: E402
-from bench import WORKLOADS        # noqa: E402
+from bench import WORKLOADS, WORKLOAD_KW        # noqa: E402
 
 
 def main():
@@ -17,7 +17,8 @@ def main():
     B = int(sys.argv[2]) if len(sys.argv) > 2 else default_b
     t_in = ctx + (pred if key == "predrnn-pp" else 0)
     torch.manual_seed(0)
-    m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+    m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
+                             **WORKLOAD_KW.get(wl, {})).eval()
     if os.environ.get("PROFILE_NO_PEEPHOLES"):      # experiment: ConvLSTM without the Wci/Wcf/Wco terms
         sd = {k: v for k, v in m.state_dict().items() if k.rsplit(".", 1)[-1] not in ("Wci", "Wcf", "Wco")}
         m.load_state_dict(sd)

@@ -30,7 +30,7 @@ class ModelDesc(C.Structure):
         ("enc_rnn_k", C.c_int32 * 3), ("dec_rnn_k", C.c_int32 * 3),
         ("final_conv_c", C.c_int32), ("ef_act", C.c_int32),
         ("patch_size", C.c_int32), ("num_layers", C.c_int32), ("num_hidden", C.c_int32 * 8),
-        ("filter_size", C.c_int32), ("decoupling_loss_scale", C.c_float),
+        ("filter_size", C.c_int32), ("decoupling_loss_scale", C.c_float), ("layer_norm", C.c_int32),
         ("phycell_n_layers", C.c_int32), ("phycell_channels", C.c_int32), ("phycell_kernel_size", C.c_int32),
         ("convlstm_n_layers", C.c_int32), ("convlstm_hidden_dims", C.c_int32 * 8),
         ("convlstm_kernel_size", C.c_int32),

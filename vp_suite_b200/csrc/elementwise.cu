@@ -733,6 +733,8 @@ void launch_patchify_strided(const float* x, long long bstride, void* out, int d
   const int g = grid_for(total, 256, num_sms);
   if (dtype == DT_F32)
     launch_pdl(patchify_kernel<float>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<float*>(out), B, T, C, H, W, p);
+  else if (dtype == DT_F16)
+    launch_pdl(patchify_kernel<__half>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<__half*>(out), B, T, C, H, W, p);
   else
     launch_pdl(patchify_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C, H, W,
                                                          p);

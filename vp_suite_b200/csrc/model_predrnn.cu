@@ -1,5 +1,6 @@
-// predrnn-pp: PredRNN-V2 rollout, non action-conditional, layer_norm=False, eval mode
-// (reference: models/predrnn_v2.py:131-230; cell: model_blocks/predrnn.py:57-83).
+// predrnn-pp: PredRNN-V2 rollout, non action-conditional, eval mode (reference: models/predrnn_v2.py:131-230; cell:
+// model_blocks/predrnn.py:57-83).  layer_norm=False: three fused tcgen05 launches per cell step (stlstm.h);
+// layer_norm=True (model_blocks/predrnn.py:24-40): raw convs + per-sample statistics + fused gate kernels (stlstm_ln.h).
 //
 // Per step t (total_frames - 1 steps): layer 0 reads the patchified frame x_t (t < context) or the model's own
 // x_gen (eval mask is all zero, predrnn_v2.py:172-176, 300-309); the spatio-temporal memory m zig-zags through the
@@ -9,6 +10,7 @@
 #include "elementwise.h"
 #include "model.h"
 #include "stlstm.h"
+#include "stlstm_ln.h"
 
 namespace vpk {
 
@@ -37,6 +39,13 @@ class PredRnnV2 : public Model {
       declare(pre + "conv_m.0.weight", {3 * C, C, k, k});
       declare(pre + "conv_o.0.weight", {C, 2 * C, k, k});
       declare(pre + "conv_last.weight", {C, 2 * C, 1, 1});
+      if (d.layer_norm) {
+        const std::pair<const char*, int> lns[4] = {{"conv_x", 7}, {"conv_h", 4}, {"conv_m", 3}, {"conv_o", 1}};
+        for (const auto& ln : lns) {
+          declare(pre + ln.first + ".1.weight", {ln.second * C, hp_, wp_});
+          declare(pre + ln.first + ".1.bias", {ln.second * C, hp_, wp_});
+        }
+      }
     }
     declare("conv_last.weight", {cp, C, 1, 1});
     declare("adapter.weight", {C, C, 1, 1});
@@ -66,7 +75,12 @@ class PredRnnV2 : public Model {
 
   void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) override {
     const vpk_model_desc& d = desc;
-    const ActInfo act{dtype, esize()};
+    // layer_norm=True in bf16 mode: LayerNorm rescales every conv output to unit variance, which amplifies operand
+    // rounding -- bf16 operands give 1.3e-2 on the first frame of the golden case (bound 5e-3).  The LN variant therefore
+    // runs its convs on FP16 operands (11 mantissa bits; h in (-1, 1), frames in [0, 1], c / m O(1)), like PhyDNet's
+    // GroupNorm-fed convs: all of them write fp32 (raw conv outputs, head, adapter), which is what DT_F16 launches do.
+    const int adt = (d.layer_norm != 0 && dtype == DT_BF16) ? DT_F16 : dtype;
+    const ActInfo act{adt, esize()};
     const int esz = esize();
     const int c = d.img_c, h = d.img_h, w = d.img_w;
     const int ctx = t_in - pred;
@@ -90,11 +104,24 @@ class PredRnnV2 : public Model {
     float* opart = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     char* dcdm = static_cast<char*>(arena.alloc(2 * px * C * esz));          // [delta_c ; delta_m] stacked on batch
     float* adapt = static_cast<float*>(arena.alloc(2 * px * C * sizeof(float)));
+    // layer_norm=True: raw conv outputs (fp32), a dense copy of m for conv_m, statistics slots
+    const bool ln = d.layer_norm != 0;
+    float *xraw = nullptr, *hraw = nullptr, *mraw = nullptr, *oraw = nullptr, *lraw = nullptr, *lnpart = nullptr;
+    void* m_act = nullptr;
+    if (ln) {
+      xraw = static_cast<float*>(arena.alloc(px * 7 * C * sizeof(float)));
+      hraw = static_cast<float*>(arena.alloc(px * 4 * C * sizeof(float)));
+      mraw = static_cast<float*>(arena.alloc(px * 3 * C * sizeof(float)));
+      oraw = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
+      lraw = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
+      lnpart = static_cast<float*>(arena.alloc(static_cast<size_t>(3) * B * kLnSlices * 2 * sizeof(float)));
+      m_act = arena.alloc(px * C * esz);
+    }
     float* xgen32 = static_cast<float*>(arena.alloc(px * cp * sizeof(float)));
     void* xgen_act = (dtype == DT_F32) ? static_cast<void*>(xgen32) : arena.alloc(px * cp * esz);
 
     if (!measure) {
-      const int ns = num_sms, dt = dtype, pp = p;
+      const int ns = num_sms, dt = adt, pp = p;
       Op pre;
       pre.name = "patchify";
       // x holds t_in frames per sequence; frames >= ctx are ignored
@@ -108,6 +135,7 @@ class PredRnnV2 : public Model {
       }
       add_memset(prog, mstate, px * C * sizeof(float), "zero_m");
       add_memset(prog, memb[2 * (L - 1) + 1], px * 2 * C * esz, "zero_mem");   // m seen by layer 0 at t = 0
+      if (ln) add_memset(prog, m_act, px * C * esz, "zero_m_act");
     }
 
     std::vector<int> par(L, 0);
@@ -125,7 +153,13 @@ class PredRnnV2 : public Model {
                      hp(pre + "conv_x.0.weight"), hp(pre + "conv_h.0.weight"), hp(pre + "conv_m.0.weight"),
                      hp(pre + "conv_o.0.weight"), hp(pre + "conv_last.weight")};
         a.c4 = true;
-        for (const ConvSpec& sp : stlstm_specs(a, act)) add_conv(prog, sp, measure, stream);
+        if (!ln) {
+          for (const ConvSpec& sp : stlstm_specs(a, act)) add_conv(prog, sp, measure, stream, adt);
+        } else {
+          add_ln_cell(prog, pre, B, cin, inp, hb[2 * i + par[i]], hb[2 * i + (par[i] ^ 1)], cb[i], mstate, opart,
+                      memb[2 * i + (t & 1)], m_act, dcdm, dcdm + px * C * esz, xraw, hraw, mraw, oraw, lraw, lnpart, act,
+                      measure, stream);
+        }
         par[i] ^= 1;
         // decoupling-loss term: adapter (1x1, no bias) over [delta_c ; delta_m], then the per-(b, ch) cosine
         int oh, ow;
@@ -135,7 +169,7 @@ class PredRnnV2 : public Model {
         ad.oY = static_cast<long long>(wp_) * C;
         ad.oX = C;
         ad.oC = 1;
-        add_conv(prog, conv_spec(ad, act, &oh, &ow), measure, stream);
+        add_conv(prog, conv_spec(ad, act, &oh, &ow), measure, stream, adt);
         if (!measure) {
           const int HW = hp_ * wp_, CC = C;
           double* acc = d_loss;
@@ -154,14 +188,17 @@ class PredRnnV2 : public Model {
       hd.oY = static_cast<long long>(wp_) * cp;
       hd.oX = cp;
       hd.oC = 1;
-      add_conv(prog, conv_spec(hd, act, &oh, &ow), measure, stream);
+      add_conv(prog, conv_spec(hd, act, &oh, &ow), measure, stream, adt);
       if (!measure) {
         const int ns = num_sms;
         if (dtype != DT_F32 && t + 1 >= ctx && t + 1 < t_in - 1) {
           const long long n = static_cast<long long>(px) * cp;
           Op op;
           op.name = "cast_xgen";
-          op.fn = [=](cudaStream_t s, const RunCtx&) { launch_cast_f32_to_bf16(xgen32, xgen_act, n, ns, s); };
+          op.fn = [=](cudaStream_t s, const RunCtx&) {
+            if (adt == DT_F16) launch_cast_f32_to_f16(xgen32, xgen_act, n, ns, s);
+            else launch_cast_f32_to_bf16(xgen32, xgen_act, n, ns, s);
+          };
           prog.body.push_back(std::move(op));
         }
         const int first_out = t_in - 1 - pred;
@@ -185,6 +222,66 @@ class PredRnnV2 : public Model {
         VPK_CUDA(cudaMemcpyAsync(rc.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s));
       };
       prog.post.push_back(std::move(post));
+    }
+  }
+
+  // LayerNorm affine of `key` ([kC, H, W] in the reference) repacked to the NHWC order of the raw conv outputs
+  const float* ln_param(const std::string& key, int kc, cudaStream_t stream) {
+    const float* src = hp(key);
+    const int HW = hp_ * wp_;
+    std::vector<float> v(static_cast<size_t>(kc) * HW);
+    for (int ch = 0; ch < kc; ++ch)
+      for (int q = 0; q < HW; ++q) v[static_cast<size_t>(q) * kc + ch] = src[static_cast<size_t>(ch) * HW + q];
+    return dev_f32(key + ".nhwc", v, stream);
+  }
+
+  // One ST-LSTM step with layer_norm=True (stlstm_ln.h): 5 raw convs, 2 statistics launches, 2 fused gate kernels.
+  void add_ln_cell(Program& prog, const std::string& pre, int B, int cin, const void* x, const void* h_in, void* h_out,
+                   float* c, float* m, float* opart, void* mem, void* m_act, void* dc, void* dm, float* xraw, float* hraw,
+                   float* mraw, float* oraw, float* lraw, float* part, const ActInfo& act, bool measure,
+                   cudaStream_t stream) {
+    int oh, ow;
+    auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& wkey, float* out) {
+      ConvArgs a{pre + name, B, hp_, wp_, ci, co, kk, 1, kk / 2, in, hp(pre + wkey), nullptr, ACT_NONE, out};
+      a.out_f32_dense = true;
+      ConvSpec sp = conv_spec(a, act, &oh, &ow);
+      sp.is_gate_gemm = true;
+      add_conv(prog, sp, measure, stream, act.dtype);
+    };
+    raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw);
+    raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw);
+    raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw);
+    const int HW = hp_ * wp_, CC = C, ns = num_sms, dt = act.dtype;
+    if (!measure) {
+      LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
+      Op op;
+      op.name = pre + "ln_stats_xhm";
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(sa, s); };
+      prog.body.push_back(std::move(op));
+      StLnGatesArgs ga{xraw, hraw, mraw, part,
+                       ln_param(pre + "conv_x.1.weight", 7 * C, stream), ln_param(pre + "conv_x.1.bias", 7 * C, stream),
+                       ln_param(pre + "conv_h.1.weight", 4 * C, stream), ln_param(pre + "conv_h.1.bias", 4 * C, stream),
+                       ln_param(pre + "conv_m.1.weight", 3 * C, stream), ln_param(pre + "conv_m.1.bias", 3 * C, stream),
+                       c, m, mem, m_act, dc, dm, opart, B, HW, CC, dt, 1.0f};
+      Op og;
+      og.name = pre + "ln_gates";
+      og.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_gates(ga, ns, s); };
+      prog.body.push_back(std::move(og));
+    }
+    raw_conv("conv_o.ln.", mem, 2 * C, C, k, "conv_o.0.weight", oraw);
+    raw_conv("conv_last.ln.", mem, 2 * C, C, 1, "conv_last.weight", lraw);
+    if (!measure) {
+      LnStatsArgs so{{oraw, nullptr, nullptr}, {1ll * C * HW, 0, 0}, 1, B, part};
+      Op op;
+      op.name = pre + "ln_stats_o";
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(so, s); };
+      prog.body.push_back(std::move(op));
+      StLnOutArgs oa{oraw, lraw, part, ln_param(pre + "conv_o.1.weight", C, stream),
+                     ln_param(pre + "conv_o.1.bias", C, stream), opart, h_out, B, HW, CC, dt};
+      Op oo;
+      oo.name = pre + "ln_out";
+      oo.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_out(oa, ns, s); };
+      prog.body.push_back(std::move(oo));
     }
   }
 

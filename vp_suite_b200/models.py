@@ -245,8 +245,6 @@ class PredRNN_V2(VPModel, NativeRollout):
         self._native_init()
         if self.action_conditional:
             raise NotImplementedError("the native rollout covers the non action-conditional PredRNN-V2 (SURVEY 8(f))")
-        if self.layer_norm:
-            raise NotImplementedError("the native rollout covers layer_norm=False (SURVEY 8(f))")
         if self.stride != 1:
             raise AttributeError("ST-LSTM stride must be 1")
         self.patch_c = self.patch_size * self.patch_size * self.img_c          # predrnn_v2.py:59-62
@@ -262,7 +260,10 @@ class PredRNN_V2(VPModel, NativeRollout):
             cell = _Params()
             for name, (o, ci) in (("conv_x", (7 * C, cin)), ("conv_h", (4 * C, C)), ("conv_m", (3 * C, C)),
                                   ("conv_o", (C, 2 * C))):
-                setattr(cell, name, nn.Sequential(nn.Conv2d(ci, o, k, 1, k // 2, bias=False)))
+                layers = [nn.Conv2d(ci, o, k, 1, k // 2, bias=False)]
+                if self.layer_norm:                                            # model_blocks/predrnn.py:24-40
+                    layers.append(nn.LayerNorm([o, self.rnn_h, self.rnn_w]))
+                setattr(cell, name, nn.Sequential(*layers))
             cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
             cells.append(cell)
         self.cell_list = nn.ModuleList(cells)
@@ -280,6 +281,7 @@ class PredRNN_V2(VPModel, NativeRollout):
         for i, v in enumerate(self.num_hidden[:8]):
             d.num_hidden[i] = int(v)
         d.decoupling_loss_scale = float(self.decoupling_loss_scale)
+        d.layer_norm = int(bool(self.layer_norm))
         return d
 
     def _native_key(self, key):
