@@ -11,10 +11,10 @@ KW = dict(action_size=0, tensor_value_range=[0.0, 1.0])
 
 
 @pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64",
-                                  "branch_1x64"])
+                                  "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32"])
 def test_state_dict_layout_matches_reference(manifest, name):
     meta = manifest["models"][name]
-    m = V.MODEL_CLASSES[meta["key"]]("cpu", img_shape=tuple(meta["img_shape"]), **KW)
+    m = V.MODEL_CLASSES[meta["key"]]("cpu", img_shape=tuple(meta["img_shape"]), **KW, **(meta.get("model_kwargs") or {}))
     got = {k: list(v.shape) for k, v in m.state_dict().items()}
     assert got == meta["shapes"]
     # and the native library expects exactly these tensors
