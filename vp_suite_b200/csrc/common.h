@@ -69,6 +69,9 @@ enum EpiKind : int {
   EPI_ST_M = 3,           // G=3  (i',f',g') ST-LSTM spatio-temporal-memory update
   EPI_ST_O = 4,           // G=2  (conv_o, conv_last) ST-LSTM output gate
   EPI_PHY_GATE = 5,       // G=1  PhyCell Kalman-style blend
+  EPI_DECOUPLE = 6,       // G=2  (adapter(delta_c), adapter(delta_m)): per-(sample, channel) dot product and squared norms
+                          //      over the positions (PredRNN-V2 decoupling loss); nothing else is stored.  tcgen05 halo
+                          //      kernel only: s1[b][slot][C][3] gets one warp's 32 positions per slot (slot as gn_slot0 / gn_nslots)
 };
 enum ActKind : int { ACT_NONE = 0, ACT_LEAKY = 1, ACT_SIGMOID = 2, ACT_RELU = 3 };
 

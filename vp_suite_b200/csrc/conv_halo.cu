@@ -52,7 +52,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint
 }
 
 __host__ __device__ constexpr int gates_of(int kind) {
-  return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O) ? 2 : 1;
+  return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O || kind == EPI_DECOUPLE) ? 2 : 1;
 }
 
 // MODE: 0 generic epilogue, 1 lean compile-time epilogue, 2 ConvLSTM epilogue with a whole tile of operands in flight,
@@ -599,6 +599,31 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         };
         bool stats = false;
         if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr;
+        if constexpr (KIND == EPI_DECOUPLE) {
+          // PredRNN-V2 decoupling loss: acc = (adapter(delta_c), adapter(delta_m)) of 8 channels at this position; the
+          // warp's 32 positions are reduced to dot / |c|^2 / |m|^2 per channel (32-value butterfly) and stored to this
+          // warp's slot -- the adapter outputs never reach memory
+          stats = false;
+          const EpiParams& E = P.L.epi;
+          const int slot = E.gn_slot0 + (mt % (P.tiles_x * P.tiles_y)) * 4 + quad;
+          for (int ch = half * 8; ch < Cn; ch += 16) {
+            uint32_t r[8 * G];
+            tmem_chunk(ch, r);
+            ptx::tmem_ld_wait();
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float ac = valid ? __uint_as_float(r[2 * j]) : 0.f, am = valid ? __uint_as_float(r[2 * j + 1]) : 0.f;
+              v[j] = ac * am;
+              v[8 + j] = ac * ac;
+              v[16 + j] = am * am;
+              v[24 + j] = 0.f;
+            }
+            const float tot = warp_reduce32(v, lane);
+            if (lane < 24 && b < P.L.B && ch_base + ch < C)
+              E.s1[((static_cast<long long>(b) * E.gn_nslots + slot) * C + ch_base + ch + (lane & 7)) * 3 + (lane >> 3)] = tot;
+          }
+        } else
         if (stats) {
           // conv feeding a GroupNorm: per-group sum / sum of squares of the stored values, reduced over the 32 positions
           // of the warp and stored to this warp's slot of gn_sums (the plan guarantees Cn <= 64, Cn / gs <= 16, no
@@ -938,6 +963,11 @@ void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
     case EPI_ST_M: VPK_HALO(EPI_ST_M);
     case EPI_ST_O: VPK_HALO(EPI_ST_O);
     case EPI_PHY_GATE: VPK_HALO(EPI_PHY_GATE);
+    case EPI_DECOUPLE:
+      VPK_REQUIRE(P.fast_epi, "conv_halo: the decoupling-loss epilogue needs whole 8-channel chunks");
+      if (P.pair) launch_one<EPI_DECOUPLE, true, 1>(P, stream);
+      else launch_one<EPI_DECOUPLE, false, 1>(P, stream);
+      break;
     default: VPK_THROW(1, "conv_halo: unsupported epilogue kind");
   }
 #undef VPK_HALO

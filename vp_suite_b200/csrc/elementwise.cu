@@ -285,6 +285,51 @@ __global__ void __launch_bounds__(256) decouple_reduce_kernel(const float* __res
   }
 }
 
+// Decoupling-loss term from the partial sums the EPI_DECOUPLE conv epilogue left (slots[b][slot][C][3] = dot, |c|^2,
+// |m|^2 over one warp's positions): per (b, ch) |cos| as above, summed over the channels of sample b in a fixed order
+// into term[b].  One block per sample, one thread per channel.
+__global__ void __launch_bounds__(256) decouple_cos_kernel(const float* __restrict__ slots, int nslots, int C,
+                                                           float* __restrict__ term) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ float s_v[256];
+  const int b = blockIdx.x, c = threadIdx.x;
+  float v = 0.f;
+  if (c < C) {
+    float d = 0.f, a = 0.f, m = 0.f;
+    const float* p = slots + (static_cast<size_t>(b) * nslots * C + c) * 3;
+    for (int s = 0; s < nslots; ++s) {
+      d += p[0];
+      a += p[1];
+      m += p[2];
+      p += static_cast<size_t>(C) * 3;
+    }
+    v = fabsf(d) / (fmaxf(sqrtf(a), 1e-12f) * fmaxf(sqrtf(m), 1e-12f));
+  }
+  s_v[c] = v;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (c < o) s_v[c] += s_v[c + o];
+    __syncthreads();
+  }
+  if (c == 0) term[b] = s_v[0];
+}
+// *acc += sum of terms[0 .. n) in index order (one thread per 1/256th, fixed tree): the rollout's loss accumulator
+__global__ void __launch_bounds__(256) decouple_sum_kernel(const float* __restrict__ terms, long long n, double* acc) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ double s_v[256];
+  double v = 0.0;
+  for (long long i = threadIdx.x; i < n; i += 256) v += static_cast<double>(terms[i]);
+  s_v[threadIdx.x] = v;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) s_v[threadIdx.x] += s_v[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *acc += s_v[0];
+}
+
 // GroupNorm (+ optional LeakyReLU(0.2), + optional residual add) over one sample per CTA, NHWC.
 //   in  [B][HW][Cs_in]  (first C channels are real), out [B][HW][Cs_out]; statistics per (sample, group) over
 //   (C/groups) channels x HW positions, two-pass (mean, then centred variance) like ATen's kernel; eps inside the
@@ -720,6 +765,14 @@ void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num
   launch_pdl(split_bf16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__nv_bfloat16*>(hi),
                                                                        static_cast<__nv_bfloat16*>(lo), n / 4);
   VPK_CUDA(cudaGetLastError());
+}
+
+void launch_decouple_cos(const float* slots, int nslots, int B, int C, float* term, cudaStream_t stream) {
+  VPK_REQUIRE(C >= 1 && C <= 256, "decouple_cos: at most 256 channels");
+  launch_pdl(decouple_cos_kernel, dim3(B), dim3(256), 0, stream, slots, nslots, C, term);
+}
+void launch_decouple_sum(const float* terms, long long n, double* acc, cudaStream_t stream) {
+  launch_pdl(decouple_sum_kernel, dim3(1), dim3(256), 0, stream, terms, n, acc);
 }
 
 void launch_decouple_finalize(const double* acc, float* aux, double scale, cudaStream_t stream) {

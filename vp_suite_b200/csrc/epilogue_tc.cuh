@@ -112,6 +112,20 @@ __device__ __forceinline__ float gn_warp_reduce16(float (&s)[16], int lane) {
   return s[0] + __shfl_xor_sync(0xffffffffu, s[0], 1);
 }
 __device__ __forceinline__ int gn_lane_value(int lane) { return lane >> 1; }   // bits 4..1 of the lane = value index
+// The same for 32 values (16 + 8 + 4 + 2 + 1 shuffles): lane i ends up with the warp total of value i.
+__device__ __forceinline__ float warp_reduce32(float (&s)[32], int lane) {
+#pragma unroll
+  for (int w = 16, bit = 16; w >= 1; w >>= 1, bit >>= 1) {
+    const bool up = (lane & bit) != 0;
+#pragma unroll
+    for (int i = 0; i < w; ++i) {
+      const float send = up ? s[i] : s[i + w];
+      const float keep = up ? s[i + w] : s[i];
+      s[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+    }
+  }
+  return s[0];
+}
 
 // Whether the fast path may be used for this launch: whole 8-channel chunks, 16-byte aligned rows.
 __host__ __device__ inline bool epi_tc_fast_ok(const EpiParams& E) {
@@ -128,6 +142,7 @@ __host__ __device__ inline bool epi_tc_fast_ok(const EpiParams& E) {
 template <int KIND>
 __device__ __forceinline__ void epi_tc_prefetch(const EpiParams& E, const EpiTile& t, int ch, EpiOperands<8>& o) {
   using bf16 = __nv_bfloat16;
+  if constexpr (KIND == EPI_DECOUPLE) return;      // handled inside the halo kernel (cross-lane reduction)
   if constexpr (KIND == EPI_LSTM) {
     ld_state8(E.s0, t.st_off, t.st_g, ch, o.a);
     if (E.p0 != nullptr) {
@@ -150,6 +165,7 @@ template <int KIND, int G>
 __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile& t, int ch, const float* s_bias,
                                               float (&acc)[G][8], EpiOperands<8>& o) {
   using bf16 = __nv_bfloat16;
+  if constexpr (KIND == EPI_DECOUPLE) return;      // handled inside the halo kernel (cross-lane reduction)
   if (s_bias != nullptr) {   // packed order (ch + j) * G + g: 8*G consecutive floats
     const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * G);
 #pragma unroll

@@ -335,7 +335,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
     L.op_f16 = (dtype == DT_F16) ? 1 : 0;
-    VPK_REQUIRE(dtype != DT_F16 || G == 1, "fp16 operands are for plain convs only: " + spec.name);
+    VPK_REQUIRE(dtype != DT_F16 || G == 1 || ph.epi.kind == EPI_DECOUPLE, "fp16 operands are for plain convs only: " + spec.name);
     double kreal = 0;
     for (const HostStep& h : ph.steps) kreal += h.kw_valid;   // split-bf16 layers count their three products
     L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;
@@ -365,6 +365,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         bc.use_tc = false;
         VPK_REQUIRE(bc.use_halo, "fused projection epilogue needs the tcgen05 halo kernel for " + spec.name);
       }
+      VPK_REQUIRE(L.epi.kind != EPI_DECOUPLE || bc.use_halo, "the decoupling-loss epilogue needs the tcgen05 halo kernel");
       VPK_REQUIRE(L.epi.gn_sums == nullptr || bc.use_halo,
                   "fused GroupNorm statistics need the tcgen05 halo kernel for " + spec.name);
       if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);

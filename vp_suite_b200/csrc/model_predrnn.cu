@@ -6,6 +6,8 @@
 // x_gen (eval mask is all zero, predrnn_v2.py:172-176, 300-309); the spatio-temporal memory m zig-zags through the
 // layers (:196-204); every (t, layer) contributes a decoupling-loss term over adapter(delta_c), adapter(delta_m)
 // (:197-211); the 1x1 head gives x_gen (:223); the last `pred` x_gen are un-patchified (:227-228).
+#include <cstdlib>
+
 #include "builders.h"
 #include "elementwise.h"
 #include "model.h"
@@ -117,6 +119,13 @@ class PredRnnV2 : public Model {
       lnpart = static_cast<float*>(arena.alloc(static_cast<size_t>(3) * B * kLnSlices * 2 * sizeof(float)));
       m_act = arena.alloc(px * C * esz);
     }
+    // fused decoupling loss (tcgen05 path): per-warp partial slots + one term per (step, layer, sample)
+    const char* halo_env = getenv("VPK_TC_HALO");
+    const bool fuse_dec = adt != DT_F32 && backend == 0 && C % 8 == 0 && C <= 128 && getenv("VPK_NO_FUSED_DECOUPLE") == nullptr &&
+                          (halo_env == nullptr || atoi(halo_env) != 0);
+    const int dec_nslots = 4 * ((hp_ + 15) / 16) * ((wp_ + 7) / 8);
+    float* dec_slots = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * dec_nslots * C * 3 * sizeof(float)));
+    float* dec_terms = static_cast<float*>(arena.alloc(static_cast<size_t>(t_in - 1) * L * B * sizeof(float)));
     float* xgen32 = static_cast<float*>(arena.alloc(px * cp * sizeof(float)));
     void* xgen_act = (dtype == DT_F32) ? static_cast<void*>(xgen32) : arena.alloc(px * cp * esz);
 
@@ -161,7 +170,46 @@ class PredRnnV2 : public Model {
                       measure, stream);
         }
         par[i] ^= 1;
-        // decoupling-loss term: adapter (1x1, no bias) over [delta_c ; delta_m], then the per-(b, ch) cosine
+        // decoupling-loss term: adapter (1x1, no bias) over delta_c and delta_m, then the per-(b, ch) cosine.
+        // tcgen05 path: ONE conv with two gate columns per channel (adapter(delta_c), adapter(delta_m)) whose epilogue
+        // reduces dot / norms over the positions -- the adapter outputs (2 x px x C fp32) never reach memory.
+        if (fuse_dec) {
+          ConvSpec sp;
+          sp.name = "adapter.decouple";
+          sp.B = B;
+          sp.G = 2;
+          sp.C = C;
+          for (int g = 0; g < 2; ++g) {
+            WeightRef wr;
+            wr.w = hp("adapter.weight");
+            wr.O = C;
+            wr.I = C;
+            wr.KH = wr.KW = 1;
+            for (int q = 0; q < 4; ++q) wr.gate_block[q] = -1;
+            wr.gate_block[g] = 0;
+            sp.wrefs.push_back(wr);
+          }
+          int oh2, ow2;
+          std::vector<ConvInput> ins;
+          ins.push_back(ConvInput{dense_view(dcdm, hp_, wp_, C), 0, 0});
+          ins.push_back(ConvInput{dense_view(dcdm + px * C * esz, hp_, wp_, C), 1, 0});
+          lower_conv(sp, 1, 1, 0, ins, hp_, wp_, esz, &oh2, &ow2);
+          EpiParams& e = sp.phases[0].epi;
+          e.kind = EPI_DECOUPLE;
+          e.s1 = dec_slots;
+          e.gn_slot0 = 0;
+          e.gn_nslots = dec_nslots;
+          add_conv(prog, sp, measure, stream, adt);
+          if (!measure) {
+            const int CC = C, nsl = dec_nslots;
+            float* term = dec_terms + static_cast<size_t>(t * L + i) * B;
+            Op op;
+            op.name = "decouple_cos";
+            op.fn = [=](cudaStream_t s, const RunCtx&) { launch_decouple_cos(dec_slots, nsl, B, CC, term, s); };
+            prog.body.push_back(std::move(op));
+          }
+          continue;
+        }
         int oh, ow;
         ConvArgs ad{"adapter.", 2 * B, hp_, wp_, C, C, 1, 1, 0, dcdm, hp("adapter.weight"), nullptr, ACT_NONE, adapt};
         ad.f32_strided = true;
@@ -212,6 +260,14 @@ class PredRnnV2 : public Model {
           prog.body.push_back(std::move(op));
         }
       }
+    }
+    if (!measure && fuse_dec) {
+      const long long n = static_cast<long long>(t_in - 1) * L * B;
+      double* acc = d_loss;
+      Op op;
+      op.name = "decouple_sum";
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_decouple_sum(dec_terms, n, acc, s); };
+      prog.body.push_back(std::move(op));
     }
     if (!measure) {
       const size_t bytes = static_cast<size_t>(B) * pred * c * h * w * sizeof(float);
