@@ -118,7 +118,8 @@ struct EpiParams {
   // the image) * 4 + TMEM lane quadrant.  Every slot is written exactly once per launch (plain stores, no atomics), so
   // the apply pass adds them in a fixed order: results do not depend on the schedule.
   float* gn_sums;
-  int gn_group_size;      // channels per group (0 = disabled)
+  int gn_group_size;      // channels per group (0 = disabled); -1 = ONE group = the whole sample (LayerNorm over C, H, W):
+                          //   gn_sums[b][slot][2] with slot = gn_slot0 + ((tile in image) * n_tiles + N tile) * 8 + quadrant * 2 + half
   int gn_slot0, gn_nslots;
 };
 

@@ -583,6 +583,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         if (valid && ch_base + half * 8 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + half * 8, ops0);
         ptx::mbar_wait_fast(tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
+        const bool ln_stats = (KIND == EPI_BIAS_ACT) && P.L.epi.gn_sums != nullptr && P.L.epi.gn_group_size < 0;
+        float ln_s = 0.f, ln_q = 0.f;
         auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
           uint32_t r[8 * G];
           tmem_chunk(ch, r);
@@ -595,10 +597,19 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
               for (int g = 0; g < G; ++g) a[g][j] = __uint_as_float(r[j * G + g]);
             epi_tc_finish<KIND, G>(P.L.epi, et, ch_base + ch, bias, a, cur);
+            if constexpr (KIND == EPI_BIAS_ACT) {
+              if (ln_stats) {          // whole-sample statistics (a following LayerNorm): the values just stored
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  ln_s += a[0][j];
+                  ln_q = fmaf(a[0][j], a[0][j], ln_q);
+                }
+              }
+            }
           }
         };
         bool stats = false;
-        if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr;
+        if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr && P.L.epi.gn_group_size > 0;
         if constexpr (KIND == EPI_DECOUPLE) {
           // PredRNN-V2 decoupling loss: acc = (adapter(delta_c), adapter(delta_m)) of 8 channels at this position; the
           // warp's 32 positions are reduced to dot / |c|^2 / |m|^2 per channel (32-value butterfly) and stored to this
@@ -663,10 +674,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                               (vi & 1)] = tot;
             }
           }
-        } else
-        for (int ch = half * 8; ch < Cn; ch += 32) {
-          do_chunk(ch, ops0, ops1);
-          if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+        } else {
+          for (int ch = half * 8; ch < Cn; ch += 32) {
+            do_chunk(ch, ops0, ops1);
+            if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+          }
+          if (ln_stats) {      // one (sum, sum of squares) pair per warp and tile, in this warp's own slot: deterministic
+#pragma unroll
+            for (int o = 16; o >= 1; o >>= 1) {
+              ln_s += __shfl_xor_sync(0xffffffffu, ln_s, o);
+              ln_q += __shfl_xor_sync(0xffffffffu, ln_q, o);
+            }
+            if (lane == 0 && b < P.L.B) {
+              const int slot = P.L.epi.gn_slot0 + ((mt % (P.tiles_x * P.tiles_y)) * P.n_tiles + nt) * 8 + quad * 2 + half;
+              float* o = P.L.epi.gn_sums + (static_cast<long long>(b) * P.L.epi.gn_nslots + slot) * 2;
+              o[0] = ln_s;
+              o[1] = ln_q;
+            }
+          }
         }
       } else {
         // ---- generic path (ragged channel counts, channel-strided outputs) ----
@@ -837,7 +862,10 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
   P.roll = (P.fast_epi && L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) ? 1 : 0;
   if (const char* env = getenv("VPK_EPI_ROLL")) P.roll = P.roll && atoi(env) != 0;
-  if (L.epi.gn_sums != nullptr) {
+  if (L.epi.gn_sums != nullptr && L.epi.gn_group_size < 0) {
+    VPK_REQUIRE(P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0 && L.epi.res == nullptr,
+                "halo plan: fused LayerNorm statistics need the lean BIAS_ACT epilogue");
+  } else if (L.epi.gn_sums != nullptr) {
     const int gs = L.epi.gn_group_size;
     VPK_REQUIRE(P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0 && L.epi.res == nullptr &&
                     (gs == 2 || gs == 4 || gs == 8) && L.Cn <= 64 && L.Cn / gs <= 16 && L.epi.C % gs == 0,

@@ -116,7 +116,10 @@ class PredRnnV2 : public Model {
       mraw = static_cast<float*>(arena.alloc(px * 3 * C * sizeof(float)));
       oraw = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
       lraw = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
-      lnpart = static_cast<float*>(arena.alloc(static_cast<size_t>(3) * B * kLnSlices * 2 * sizeof(float)));
+      // statistics partials: up to (tiles per image) x (N tiles <= 4) x 8 slots per tensor and sample when the conv
+      // epilogues write them, kLnSlices otherwise
+      const size_t max_slots = std::max<size_t>(kLnSlices, static_cast<size_t>(((hp_ + 15) / 16) * ((wp_ + 7) / 8)) * 4 * 8);
+      lnpart = static_cast<float*>(arena.alloc(static_cast<size_t>(3) * B * max_slots * 2 * sizeof(float)));
       m_act = arena.alloc(px * C * esz);
     }
     // fused decoupling loss (tcgen05 path): per-warp partial slots + one term per (step, layer, sample)
@@ -297,24 +300,51 @@ class PredRnnV2 : public Model {
                    float* mraw, float* oraw, float* lraw, float* part, const ActInfo& act, bool measure,
                    cudaStream_t stream) {
     int oh, ow;
-    auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& wkey, float* out) {
+    // tcgen05 path: the conv epilogues leave the per-sample (sum, sum of squares) partials themselves (one slot per
+    // warp, tile and N tile); otherwise a separate statistics launch reads the raw tensors once more
+    const char* halo_env = getenv("VPK_TC_HALO");
+    const bool fuse_stats = act.dtype != DT_F32 && backend == 0 && getenv("VPK_NO_FUSED_LN_STATS") == nullptr &&
+                            (halo_env == nullptr || atoi(halo_env) != 0);
+    const int tiles_img = ((hp_ + 15) / 16) * ((wp_ + 7) / 8);
+    auto slots_of = [&](int co) {       // as lowering.cu's choose_cn for G = 1: N tiles of <= 256 columns, multiples of 16
+      int nt = std::max(1, (co + 255) / 256);
+      while (((co + nt - 1) / nt + 15) / 16 * 16 > 256) ++nt;
+      return tiles_img * nt * 8;
+    };
+    auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& wkey, float* out,
+                        float* stat, int nslots) {
       ConvArgs a{pre + name, B, hp_, wp_, ci, co, kk, 1, kk / 2, in, hp(pre + wkey), nullptr, ACT_NONE, out};
       a.out_f32_dense = true;
       ConvSpec sp = conv_spec(a, act, &oh, &ow);
       sp.is_gate_gemm = true;
+      if (stat != nullptr) {
+        EpiParams& e = sp.phases[0].epi;
+        e.gn_sums = stat;
+        e.gn_group_size = -1;
+        e.gn_slot0 = 0;
+        e.gn_nslots = nslots;
+      }
       add_conv(prog, sp, measure, stream, act.dtype);
     };
-    raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw);
-    raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw);
-    raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw);
+    // statistics regions inside `part`: X, H, M (and O reuses X's)
+    const int nsx = fuse_stats ? slots_of(7 * C) : kLnSlices, nsh = fuse_stats ? slots_of(4 * C) : kLnSlices,
+              nsm = fuse_stats ? slots_of(3 * C) : kLnSlices, nso = fuse_stats ? slots_of(C) : kLnSlices;
+    float* px_ = part;
+    float* ph_ = px_ + static_cast<size_t>(B) * nsx * 2;
+    float* pm_ = ph_ + static_cast<size_t>(B) * nsh * 2;
+    raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw, fuse_stats ? px_ : nullptr, nsx);
+    raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw, fuse_stats ? ph_ : nullptr, nsh);
+    raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw, fuse_stats ? pm_ : nullptr, nsm);
     const int HW = hp_ * wp_, CC = C, ns = num_sms, dt = act.dtype;
     if (!measure) {
-      LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
-      Op op;
-      op.name = pre + "ln_stats_xhm";
-      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(sa, s); };
-      prog.body.push_back(std::move(op));
-      StLnGatesArgs ga{xraw, hraw, mraw, part,
+      if (!fuse_stats) {
+        LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
+        Op op;
+        op.name = pre + "ln_stats_xhm";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(sa, s); };
+        prog.body.push_back(std::move(op));
+      }
+      StLnGatesArgs ga{xraw, hraw, mraw, {px_, ph_, pm_}, {nsx, nsh, nsm},
                        ln_param(pre + "conv_x.1.weight", 7 * C, stream), ln_param(pre + "conv_x.1.bias", 7 * C, stream),
                        ln_param(pre + "conv_h.1.weight", 4 * C, stream), ln_param(pre + "conv_h.1.bias", 4 * C, stream),
                        ln_param(pre + "conv_m.1.weight", 3 * C, stream), ln_param(pre + "conv_m.1.bias", 3 * C, stream),
@@ -324,15 +354,17 @@ class PredRnnV2 : public Model {
       og.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_gates(ga, ns, s); };
       prog.body.push_back(std::move(og));
     }
-    raw_conv("conv_o.ln.", mem, 2 * C, C, k, "conv_o.0.weight", oraw);
-    raw_conv("conv_last.ln.", mem, 2 * C, C, 1, "conv_last.weight", lraw);
+    raw_conv("conv_o.ln.", mem, 2 * C, C, k, "conv_o.0.weight", oraw, fuse_stats ? px_ : nullptr, nso);
+    raw_conv("conv_last.ln.", mem, 2 * C, C, 1, "conv_last.weight", lraw, nullptr, 0);
     if (!measure) {
-      LnStatsArgs so{{oraw, nullptr, nullptr}, {1ll * C * HW, 0, 0}, 1, B, part};
-      Op op;
-      op.name = pre + "ln_stats_o";
-      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(so, s); };
-      prog.body.push_back(std::move(op));
-      StLnOutArgs oa{oraw, lraw, part, ln_param(pre + "conv_o.1.weight", C, stream),
+      if (!fuse_stats) {
+        LnStatsArgs so{{oraw, nullptr, nullptr}, {1ll * C * HW, 0, 0}, 1, B, part};
+        Op op;
+        op.name = pre + "ln_stats_o";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(so, s); };
+        prog.body.push_back(std::move(op));
+      }
+      StLnOutArgs oa{oraw, lraw, px_, nso, ln_param(pre + "conv_o.1.weight", C, stream),
                      ln_param(pre + "conv_o.1.bias", C, stream), opart, h_out, B, HW, CC, dt};
       Op oo;
       oo.name = pre + "ln_out";

@@ -48,10 +48,10 @@ __global__ void __launch_bounds__(256) ln_stats_kernel(const LnStatsArgs a) {
 }
 
 // mean / rstd of tensor z of sample b from its partial slots (double accumulation, fixed order)
-__device__ __forceinline__ void ln_finalize(const float* part, int z, int B, int b, double n, float* mean, float* rstd) {
-  const float* p = part + ((static_cast<long long>(z) * B + b) * kLnSlices) * 2;
+__device__ __forceinline__ void ln_finalize(const float* part, int nslots, int b, double n, float* mean, float* rstd) {
+  const float* p = part + static_cast<long long>(b) * nslots * 2;
   double s = 0.0, q = 0.0;
-  for (int i = 0; i < kLnSlices; ++i) {
+  for (int i = 0; i < nslots; ++i) {
     s += static_cast<double>(p[2 * i]);
     q += static_cast<double>(p[2 * i + 1]);
   }
@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(256) stlstm_ln_gates_kernel(const StLnGatesArg
   if (threadIdx.x < 3 * nb) {
     const int j = threadIdx.x / 3, z = threadIdx.x - 3 * j;
     const double n = static_cast<double>(HW) * C * (z == 0 ? 7 : z == 1 ? 4 : 3);
-    ln_finalize(a.part, z, a.B, b0 + j, n, &s_mean[j][z], &s_rstd[j][z]);
+    ln_finalize(a.part[z], a.nslots[z], b0 + j, n, &s_mean[j][z], &s_rstd[j][z]);
   }
   __syncthreads();
   const int it = blockIdx.x * 256 + threadIdx.x;
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(256) stlstm_ln_out_kernel(const StLnOutArgs a)
   __shared__ float s_mean, s_rstd;
   const int b = blockIdx.y;
   const int C = a.C, HW = a.HW, cq = C >> 2;
-  if (threadIdx.x == 0) ln_finalize(a.part, 0, a.B, b, static_cast<double>(HW) * C, &s_mean, &s_rstd);
+  if (threadIdx.x == 0) ln_finalize(a.part, a.nslots, b, static_cast<double>(HW) * C, &s_mean, &s_rstd);
   __syncthreads();
   const float mo = s_mean, ro = s_rstd;
   const int items = HW * cq;

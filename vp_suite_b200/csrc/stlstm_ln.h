@@ -22,7 +22,10 @@ void launch_ln_stats(const LnStatsArgs& a, cudaStream_t stream);
 
 struct StLnGatesArgs {
   const float *X, *H, *M;                      // raw conv outputs, NHWC [B*HW][7C] / [4C] / [3C]
-  const float* part;                           // statistics of X, H, M from launch_ln_stats
+  // partial statistics of X, H, M: part[z][b][nslots[z]][2] (sum, sum of squares), written either by launch_ln_stats
+  // (kLnSlices slots) or by the conv epilogues themselves (EpiParams::gn_group_size = -1)
+  const float* part[3];
+  int nslots[3];
   const float *gx, *bx, *gh, *bh, *gm, *bm;    // LayerNorm affine, repacked [HW][k*C]
   float *c, *m;                                // fp32 state [B*HW][C], updated in place
   void* mem;                                   // activation type [B*HW][2C]: c' | m'
@@ -36,7 +39,8 @@ void launch_stlstm_ln_gates(const StLnGatesArgs& a, int num_sms, cudaStream_t st
 
 struct StLnOutArgs {
   const float *O, *Lraw;                       // raw conv_o / conv_last outputs [B*HW][C]
-  const float* part;                           // statistics of O (one tensor)
+  const float* part;                           // partial statistics of O: [b][nslots][2]
+  int nslots;
   const float *go, *bo;                        // LayerNorm affine of conv_o, [HW][C]
   const float* opart;
   void* h;                                     // activation type [B*HW][C]
