@@ -285,6 +285,103 @@ __global__ void __launch_bounds__(256) decouple_reduce_kernel(const float* __res
   }
 }
 
+// PhyCell F tail (model_blocks/phydnet.py:33-39, 60): h~ = h + conv2(GroupNorm(f1)) in ONE kernel.  f1 = F.conv1(h)
+// is fp32 [B][HW][Cs] (hid real channels, channel-padded); GroupNorm(groups, hid) has no activation; conv2 is 1 x 1
+// (hid -> C) with bias.  One block per sample: the sample is staged in shared memory (rows padded to an odd word count:
+// conflict-free), statistics are two-pass over the staged copy with fixed-order sums, the normalised values overwrite it,
+// and every thread then does the hid x C matrix-vector product of its positions against the shared-memory weights
+// (broadcast LDS.128) in fp32.  Replaces a GroupNorm launch + a tensor-core 1x1 conv launch (K = 49: one MMA slice).
+constexpr int kPhyTailThreads = 256;
+__global__ void __launch_bounds__(kPhyTailThreads) phy_f_tail_kernel(const float* __restrict__ f1, const float* __restrict__ h,
+                                                                    float* __restrict__ htilde, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta, const float* __restrict__ w2,
+                                                                    const float* __restrict__ b2, int HW, int hid, int Cs,
+                                                                    int groups, int C, float eps) {
+  ptx::pdl_launch_dependents();
+  extern __shared__ __align__(16) float s_dyn[];
+  const int rs = Cs | 1;                                   // row stride in words (odd)
+  float* s_x = s_dyn;                                      // [HW][rs]
+  float* s_w = s_x + ((HW * rs + 3) & ~3);                 // [hid][C]  (w2 transposed: input-channel major)
+  float* s_b = s_w + hid * C;                              // [C]
+  __shared__ float s_part[kPhyTailThreads / 32][64], s_mean[64], s_rstd[64];
+  for (int i = threadIdx.x; i < hid * C; i += kPhyTailThreads) {
+    const int k = i / C, o = i - k * C;
+    s_w[i] = w2[o * hid + k];                              // reference layout [C][hid][1][1]
+  }
+  for (int i = threadIdx.x; i < C; i += kPhyTailThreads) s_b[i] = b2 ? b2[i] : 0.f;
+  ptx::pdl_wait();
+  const int b = blockIdx.x;
+  const float* src = f1 + static_cast<size_t>(b) * HW * Cs;
+  for (int i = threadIdx.x; i < HW * Cs; i += kPhyTailThreads) {
+    const int p = i / Cs, k = i - p * Cs;
+    s_x[p * rs + k] = src[i];
+  }
+  __syncthreads();
+  const int cg = hid / groups;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = kPhyTailThreads / 32;
+  const float n = static_cast<float>(cg) * HW;
+  // statistics: warp w sums positions w, w + nw, ...; lane = channel (two rounds cover hid <= 64)
+  auto group_pass = [&](bool centred) {
+    for (int c0 = 0; c0 < hid; c0 += 32) {
+      const int c = c0 + lane;
+      float a = 0.f;
+      if (c < hid) {
+        const float mu = centred ? s_mean[c / cg] : 0.f;
+        for (int p = warp; p < HW; p += nw) {
+          const float d = s_x[p * rs + c] - mu;
+          a = centred ? fmaf(d, d, a) : a + d;
+        }
+      }
+      s_part[warp][c0 + lane] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+      float t = 0.f;
+      for (int w = 0; w < nw; ++w)
+        for (int c = 0; c < cg; ++c) t += s_part[w][threadIdx.x * cg + c];
+      if (centred) s_rstd[threadIdx.x] = rsqrtf(t / n + eps);
+      else s_mean[threadIdx.x] = t / n;
+    }
+    __syncthreads();
+  };
+  group_pass(false);
+  group_pass(true);
+  for (int i = threadIdx.x; i < HW * hid; i += kPhyTailThreads) {
+    const int p = i / hid, k = i - p * hid;
+    const float sc = s_rstd[k / cg] * gamma[k];
+    s_x[p * rs + k] = fmaf(s_x[p * rs + k] - s_mean[k / cg], sc, beta[k]);
+  }
+  __syncthreads();
+  // 1x1 conv + bias + residual: one position per thread, 16 output channels at a time
+  for (int p = threadIdx.x; p < HW; p += kPhyTailThreads) {
+    const float* hp_ = h + (static_cast<size_t>(b) * HW + p) * C;
+    float* op = htilde + (static_cast<size_t>(b) * HW + p) * C;
+    for (int o0 = 0; o0 < C; o0 += 16) {
+      float acc[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[j] = s_b[o0 + j];
+      for (int k = 0; k < hid; ++k) {
+        const float xv = s_x[p * rs + k];
+        const float4* wr = reinterpret_cast<const float4*>(s_w + k * C + o0);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wv = wr[q];
+          acc[4 * q + 0] = fmaf(xv, wv.x, acc[4 * q + 0]);
+          acc[4 * q + 1] = fmaf(xv, wv.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(xv, wv.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(xv, wv.w, acc[4 * q + 3]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 hv = *reinterpret_cast<const float4*>(hp_ + o0 + 4 * q);
+        *reinterpret_cast<float4*>(op + o0 + 4 * q) =
+            make_float4(acc[4 * q] + hv.x, acc[4 * q + 1] + hv.y, acc[4 * q + 2] + hv.z, acc[4 * q + 3] + hv.w);
+      }
+    }
+  }
+}
+
 // Decoupling-loss term from the partial sums the EPI_DECOUPLE conv epilogue left (slots[b][slot][C][3] = dot, |c|^2,
 // |m|^2 over one warp's positions): per (b, ch) |cos| as above, summed over the channels of sample b in a fixed order
 // into term[b].  One block per sample, one thread per channel.
@@ -765,6 +862,24 @@ void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num
   launch_pdl(split_bf16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__nv_bfloat16*>(hi),
                                                                        static_cast<__nv_bfloat16*>(lo), n / 4);
   VPK_CUDA(cudaGetLastError());
+}
+
+size_t phy_f_tail_smem(int HW, int hid, int Cs, int C) {
+  return (static_cast<size_t>((HW * (Cs | 1) + 3) & ~3) + static_cast<size_t>(hid) * C + C) * sizeof(float);
+}
+bool phy_f_tail_supported(int HW, int hid, int Cs, int groups, int C) {
+  return hid <= 64 && groups <= 64 && hid % groups == 0 && C % 16 == 0 && Cs >= hid && phy_f_tail_smem(HW, hid, Cs, C) <= 200 * 1024;
+}
+void launch_phy_f_tail(const float* f1, const float* h, float* htilde, const float* gamma, const float* beta,
+                       const float* w2, const float* b2, int B, int HW, int hid, int Cs, int groups, int C, float eps,
+                       cudaStream_t stream) {
+  VPK_REQUIRE(phy_f_tail_supported(HW, hid, Cs, groups, C), "phy_f_tail: unsupported shape");
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(phy_f_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  });
+  launch_pdl(phy_f_tail_kernel, dim3(B), dim3(kPhyTailThreads), phy_f_tail_smem(HW, hid, Cs, C), stream, f1, h, htilde, gamma,
+             beta, w2, b2, HW, hid, Cs, groups, C, eps);
 }
 
 void launch_decouple_cos(const float* slots, int nslots, int B, int C, float* term, cudaStream_t stream) {

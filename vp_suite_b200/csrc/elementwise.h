@@ -31,6 +31,11 @@ void launch_frames_to_nhwc_strided(const float* x, long long bstride, void* out,
 void launch_cast_f32_to_bf16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);
 // PredRNN-V2 decouple loss: ad fp32 [2B][HW][C] (adapter(delta_c) then adapter(delta_m)); *acc += sum_{b,ch} |cos|
 void launch_decouple_reduce(const float* ad, int B, int HW, int C, double* acc, cudaStream_t stream);
+// PhyCell: h~ = h + conv2(GroupNorm(f1)), one block per sample (f1 fp32 [B][HW][Cs], hid real channels; w2 [C][hid], b2 [C])
+bool phy_f_tail_supported(int HW, int hid, int Cs, int groups, int C);
+void launch_phy_f_tail(const float* f1, const float* h, float* htilde, const float* gamma, const float* beta,
+                       const float* w2, const float* b2, int B, int HW, int hid, int Cs, int groups, int C, float eps,
+                       cudaStream_t stream);
 // fused form: the EPI_DECOUPLE conv epilogue leaves slots[b][slot][C][3]; term[b] = sum_ch |cos|; then *acc += sum(terms)
 void launch_decouple_cos(const float* slots, int nslots, int B, int C, float* term, cudaStream_t stream);
 void launch_decouple_sum(const float* terms, long long n, double* acc, cudaStream_t stream);

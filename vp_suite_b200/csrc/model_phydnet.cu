@@ -355,6 +355,30 @@ class PhyDNetModel : public Model {
                          hp(p + "F.conv2.bias"), hp(p + "convgate.weight"), hp(p + "convgate.bias")};
           std::vector<ConvSpec> specs = phycell_specs(pa, ca);
           add_conv(prog, specs[0], measure, stream, cdt);
+          // tcgen05 path: GroupNorm + 1x1 conv2 + residual in one kernel (phy_f_tail_kernel), then the gate conv
+          const int f_groups = group_norm_divisor(hid);
+          if (backend == 0 && getenv("VPK_NO_PHY_TAIL") == nullptr && phy_f_tail_supported(h4 * w4, hid, Cp, f_groups, 64)) {
+            if (!measure) {
+              const float* g = dev_f32(p + "F.bn1.weight", vec(p + "F.bn1.weight"), stream);
+              const float* bta = dev_f32(p + "F.bn1.bias", vec(p + "F.bn1.bias"), stream);
+              const float* w2 = dev_f32(p + "F.conv2.weight", vec(p + "F.conv2.weight"), stream);
+              const float* b2 = dev_f32(p + "F.conv2.bias", vec(p + "F.conv2.bias"), stream);
+              const int HW = h4 * w4, hid_ = hid;
+              float* hm = hp_master[j];
+              float* ht = htilde[j];
+              Op op;
+              op.name = p + "F.tail (GroupNorm + conv2 + h)";
+              op.flops = 2.0 * static_cast<double>(px4) * hid * 64;
+              op.fn = [=](cudaStream_t s, const RunCtx&) {
+                launch_phy_f_tail(f1raw, hm, ht, g, bta, w2, b2, B, HW, hid_, Cp, f_groups, 64, 1e-5f, s);
+              };
+              prog.body.push_back(std::move(op));
+            }
+            add_conv(prog, specs[2], measure, stream, cdt);
+            ppar[j] ^= 1;
+            xin = h_act_new;
+            continue;
+          }
           // F.bn1 = GroupNorm(find_divisor(hid), hid), no activation
           if (!measure) {
             const std::string key = p + "F.bn1.";
