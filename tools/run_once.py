@@ -8,7 +8,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import vp_suite_b200 as V          # noqa: E402
-from bench import WORKLOADS        # noqa: E402
+from bench import WORKLOADS, WORKLOAD_KW        # noqa: E402
 
 
 def main():
@@ -18,7 +18,8 @@ def main():
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
     t_in = ctx + (pred if key == "predrnn-pp" else 0)
     torch.manual_seed(0)
-    m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+    m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
+                             **WORKLOAD_KW.get(wl, {})).eval()
     x = torch.rand(B, t_in, *img, device="cuda")
     with torch.no_grad():
         for _ in range(reps):
