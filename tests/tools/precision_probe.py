@@ -1,7 +1,7 @@
 """Developer aid (CPU): emulates operand rounding of the PhyDNet path in the oracle to choose operand formats.
 Cells (ConvLSTM / PhyCell convs) get bf16-rounded conv inputs and weights; the DCGAN encoder/decoder convs get the
 format under test (fp32 / bf16 / fp16).  Accumulation stays fp32.  Prints per-frame max-abs error against the golden
-vectors of the reference.      python tools/precision_probe.py [phy_3x64 ...]"""
+vectors of the reference.      python tests/tools/precision_probe.py [phy_3x64 ...]"""
 import json
 import os
 import sys
@@ -10,7 +10,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from oracle import blocks as OB, models as OM            # noqa: E402
 from oracle.weights import synth_state_dict, synth_frames  # noqa: E402

@@ -1,11 +1,11 @@
 """Developer aid (GPU): does sequence i's result depend on its batch position / on the run?  Repeats 3 sequences to a
-batch, compares every copy with the first, and the same call twice.   python tools/repl_check.py phy 48 [frames]"""
+batch, compares every copy with the first, and the same call twice.   python tests/tools/repl_check.py phy 48 [frames]"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import vp_suite_b200 as V                                     # noqa: E402
 from oracle.shapes import SHAPES                               # noqa: E402

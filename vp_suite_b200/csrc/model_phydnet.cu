@@ -11,7 +11,7 @@
 //
 // Precision in bf16 mode: the recurrent cells (85 % of the FLOPs) run bf16 on the tensor cores.  The DCGAN encoder /
 // decoder convs feed GroupNorm, which amplifies operand rounding past the 5e-3 single-step bound with bf16 operands
-// (tools/precision_probe.py: 4.3e-3 .. 8.1e-3 per frame), so they need more mantissa bits.
+// (tests/tools/precision_probe.py: 4.3e-3 .. 8.1e-3 per frame), so they need more mantissa bits.
 // Default: FP16 operands (11 bits; the feature maps are O(1) after GroupNorm + LeakyReLU, the frames lie in [0, 1] and
 // the accumulators stay fp32 in TMEM) -- one tcgen05 product per conv, 2-byte feature maps, first-frame error 1.1e-3
 // (fp32 convs next to bf16 cells: 1.0e-3, the cells dominate).  VPK_FEAT_SPLIT=1 selects the earlier SPLIT-bf16 form
