@@ -189,7 +189,19 @@ def main():
     dev = torch.device("cuda", local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the communicator is created; stdout must carry exactly one JSON
+        # line, so file descriptor 1 points at stderr while the process group comes up (init + first collective)
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     key, img, ctx, pred, default_b, desc = WORKLOADS[args.workload]
     B = args.seqs_per_gpu or default_b
