@@ -314,7 +314,7 @@ __global__ void __launch_bounds__(kPhyTailThreads) phy_f_tail_kernel(const float
   const float* src = f1 + static_cast<size_t>(b) * HW * Cs;
   for (int i = threadIdx.x; i < HW * Cs; i += kPhyTailThreads) {
     const int p = i / Cs, k = i - p * Cs;
-    s_x[p * rs + k] = src[i];
+    s_x[p * rs + k] = (k < hid) ? src[i] : 0.f;      // padding channels of f1 are never written by conv1: do not read them
   }
   __syncthreads();
   const int cg = hid / groups;
