@@ -157,10 +157,17 @@ class PhyDNetModel : public Model {
       frame_fb.a = arena.alloc(px1 * c * 4);
     }
     float* out_stage = static_cast<float*>(arena.alloc(px1 * c * 4 * pred));
-    float* raw = static_cast<float*>(arena.alloc(std::max(px2 * 32, px4 * 64) * 4));   // pre-GroupNorm conv output
-    Feat e1 = feat(px2 * 32), e2 = feat(px2 * 32), e3 = feat(px4 * 64), mid = feat(px4 * 64);
-    void* ep = arena.alloc(px4 * 64 * esz_c);
-    void* er = arena.alloc(px4 * 64 * esz_c);
+    // The encoders of the CONTEXT frames do not depend on the recurrence: they run once, time-batched over all t_in
+    // frames (batch t_in * B -- GroupNorm is per sample, so the frames are just more samples), instead of t_in times on
+    // B sequences; the step loop then only consumes their outputs.  Fed-back frames are encoded per step as before.
+    // (tcgen05 / fp16-feature path; ~100 short launches fewer per cfg-2 rollout.)
+    const bool batch_ctx = f16 && pad8 && t_in >= 2 && getenv("VPK_NO_CTX_BATCH") == nullptr;
+    const size_t tb = batch_ctx ? static_cast<size_t>(t_in) : 1;     // buffers shared by both uses are sized for t_in * B
+    float* raw = static_cast<float*>(arena.alloc(std::max(px2 * 32, px4 * 64) * 4 * tb));   // pre-GroupNorm conv output
+    Feat e1 = feat(px2 * 32 * tb), e2 = feat(px2 * 32 * tb), e3 = feat(px4 * 64 * tb), mid = feat(px4 * 64 * tb);
+    void* ep = arena.alloc(px4 * 64 * esz_c * tb);     // batch_ctx: [t_in][B, h4, w4, 64], slice st = step st's cell input
+    void* er = arena.alloc(px4 * 64 * esz_c * tb);
+    int Bcur = B;                                       // batch the dcgan / gn_op / stem builders below emit launches for
     // PhyCell state
     std::vector<float*> hp_master(n_phy), htilde(n_phy);
     std::vector<void*> hp_act(2 * n_phy);
@@ -198,13 +205,14 @@ class PhyDNetModel : public Model {
     const bool fuse_gn = f16 && backend == 0 && getenv("VPK_NO_FUSED_GN") == nullptr && (halo_env == nullptr || atoi(halo_env) != 0);
     auto gn_tiles = [](int H, int W) { return ((H + 15) / 16) * ((W + 7) / 8); };
     const int gn_max_slots = 4 * 4 * std::max(gn_tiles(h2, w2), gn_tiles(h4, w4));
-    float* gn_region = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * gn_max_slots * 16 * 2 * sizeof(float)));
+    float* gn_region = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * tb * gn_max_slots * 16 * 2 * sizeof(float)));
     // GroupNorm (+ LeakyReLU) of the fp32 conv output `in` into a feature map / cell operand / fp32 tensor
     auto gn_op = [&](const std::string& key, const float* in, OutKind kind, Feat out, const float* add, int HW, int C,
                      int groups, int actk, const float* sums = nullptr, int nslots = 0) {
       if (measure) return;
       const float* g = dev_f32(key + "weight", vec(key + "weight"), stream);
       const float* bta = dev_f32(key + "bias", vec(key + "bias"), stream);
+      const int Bx = Bcur;
       const int out_dt = (kind == OUT_F32) ? DT_F32 : (kind == OUT_CELL) ? cdt : (split ? DT_BF16 : f16 ? DT_F16 : DT_F32);
       const bool two = (kind == OUT_FEAT) && split;
       Op op;
@@ -212,17 +220,17 @@ class PhyDNetModel : public Model {
       if (sums != nullptr) {
         const int ok = (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_groupnorm_apply(in, out.a, ok, add, sums, nslots, B, HW, C, groups, g, bta, 1e-5f, actk, ns, s);
+          launch_groupnorm_apply(in, out.a, ok, add, sums, nslots, Bx, HW, C, groups, g, bta, 1e-5f, actk, ns, s);
         };
       } else if (groupnorm_smem_supported(HW, C, groups)) {
         const int ok = two ? 2 : (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_groupnorm_smem(in, out.a, out.lo, ok, add, B, HW, C, groups, g, bta, 1e-5f, actk, s);
+          launch_groupnorm_smem(in, out.a, out.lo, ok, add, Bx, HW, C, groups, g, bta, 1e-5f, actk, s);
         };
       } else {
         VPK_REQUIRE(!two && (add == nullptr || out_dt == DT_F32), "groupnorm: shape needs the shared-memory kernel");
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_groupnorm_act(in, DT_F32, out.a, out_dt, add, B, HW, C, C, C, groups, g, bta, 1e-5f, actk, s);
+          launch_groupnorm_act(in, DT_F32, out.a, out_dt, add, Bx, HW, C, C, C, groups, g, bta, 1e-5f, actk, s);
         };
       }
       prog.body.push_back(std::move(op));
@@ -254,7 +262,7 @@ class PhyDNetModel : public Model {
         return sp_;
       };
       if (!transpose) {
-        ConvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, in.a, hp(p + "main.0.weight"), hp(p + "main.0.bias"),
+        ConvArgs a{p + "main.0.", Bcur, H, W, Cin, Cout, 3, stride, 1, in.a, hp(p + "main.0.weight"), hp(p + "main.0.bias"),
                    ACT_NONE, raw};
         a.out_f32_dense = true;
         a.split = sp;
@@ -262,7 +270,7 @@ class PhyDNetModel : public Model {
         a.cin_w = cin_w;
         add_conv(prog, with_stats(conv_spec(a, ai, &oh, &ow)), measure, stream, ai.dtype);
       } else {
-        DeconvArgs a{p + "main.0.", B, H, W, Cin, Cout, 3, stride, 1, stride == 2 ? 1 : 0, in.a, hp(p + "main.0.weight"),
+        DeconvArgs a{p + "main.0.", Bcur, H, W, Cin, Cout, 3, stride, 1, stride == 2 ? 1 : 0, in.a, hp(p + "main.0.weight"),
                      hp(p + "main.0.bias"), ACT_NONE, raw};
         a.out_f32 = true;
         a.split = sp;
@@ -307,6 +315,39 @@ class PhyDNetModel : public Model {
       }
     }
 
+    // encoder_E -> encoder_Ep / encoder_Er of `Bcur` frames `fr`; cell inputs go to ep_out / er_out
+    auto encoders = [&](Feat fr, void* ep_out, void* er_out) {
+      if (stem_direct) {   // image-channel stem: direct CUDA-core kernel (HBM-bound), then the usual GroupNorm pass
+        if (!measure) {
+          const std::string p = "encoder_E.c1.";
+          StemArgs sa_{fr.a, 1, Bcur, h, w, c, 2, dev_f32(p + "stem.w", conv_stem_pack(hp(p + "main.0.weight"), 32, c, DT_F16), stream),
+                       dev_f32(p + "stem.b", vec(p + "main.0.bias"), stream), 32, ACT_NONE, raw, 1};
+          Op op;
+          op.name = p + "main.0.stem";
+          op.flops = 2.0 * static_cast<double>(px2) * (Bcur / B) * 32 * 9 * c;
+          op.fn = [=](cudaStream_t s, const RunCtx&) { launch_conv_stem(sa_, ns, s); };
+          prog.body.push_back(std::move(op));
+        }
+        gn_op("encoder_E.c1.main.1.", raw, OUT_FEAT, e1, nullptr, h2 * w2, 32, 16, ACT_LEAKY);
+      } else {
+        dcgan("encoder_E.c1.", false, fr, !pad8, h, w, cs, 32, 2, OUT_FEAT, e1, nullptr, c);
+      }
+      dcgan("encoder_E.c2.", false, e1, false, h2, w2, 32, 32, 1, OUT_FEAT, e2, nullptr);
+      dcgan("encoder_E.c3.", false, e2, false, h2, w2, 32, 64, 2, OUT_FEAT, e3, nullptr);
+      if (!branch_only) {
+        dcgan("encoder_Ep.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
+        dcgan("encoder_Ep.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{ep_out, nullptr}, nullptr);
+      }
+      dcgan("encoder_Er.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
+      dcgan("encoder_Er.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{er_out, nullptr}, nullptr);
+
+    };
+    if (batch_ctx) {
+      Bcur = B * t_in;
+      encoders(frames_in, ep, er);
+      Bcur = B;
+    }
+
     std::vector<int> ppar(n_phy, 0), lpar(n_lstm, 0);
     const int n_steps = (t_in - 1) + pred;
     for (int st = 0; st < n_steps; ++st) {
@@ -319,33 +360,18 @@ class PhyDNetModel : public Model {
         frame.lo = pad8 ? static_cast<char*>(frames_in.lo) + off : nullptr;
       }
       // ---- encoders ----
-      if (stem_direct) {   // image-channel stem: direct CUDA-core kernel (HBM-bound), then the usual GroupNorm pass
-        if (!measure) {
-          const std::string p = "encoder_E.c1.";
-          StemArgs sa_{frame.a, 1, B, h, w, c, 2, dev_f32(p + "stem.w", conv_stem_pack(hp(p + "main.0.weight"), 32, c, DT_F16), stream),
-                       dev_f32(p + "stem.b", vec(p + "main.0.bias"), stream), 32, ACT_NONE, raw, 1};
-          Op op;
-          op.name = p + "main.0.stem";
-          op.flops = 2.0 * static_cast<double>(px2) * 32 * 9 * c;
-          op.fn = [=](cudaStream_t s, const RunCtx&) { launch_conv_stem(sa_, ns, s); };
-          prog.body.push_back(std::move(op));
-        }
-        gn_op("encoder_E.c1.main.1.", raw, OUT_FEAT, e1, nullptr, h2 * w2, 32, 16, ACT_LEAKY);
+      const void* ep_in = ep;
+      const void* er_in = er;
+      if (batch_ctx && st < t_in) {       // context frame: encoded by the time-batched pass before the loop
+        ep_in = static_cast<const char*>(ep) + static_cast<size_t>(st) * px4 * 64 * esz_c;
+        er_in = static_cast<const char*>(er) + static_cast<size_t>(st) * px4 * 64 * esz_c;
       } else {
-        dcgan("encoder_E.c1.", false, frame, !pad8, h, w, cs, 32, 2, OUT_FEAT, e1, nullptr, c);
+        encoders(frame, ep, er);
       }
-      dcgan("encoder_E.c2.", false, e1, false, h2, w2, 32, 32, 1, OUT_FEAT, e2, nullptr);
-      dcgan("encoder_E.c3.", false, e2, false, h2, w2, 32, 64, 2, OUT_FEAT, e3, nullptr);
-      if (!branch_only) {
-        dcgan("encoder_Ep.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
-        dcgan("encoder_Ep.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{ep, nullptr}, nullptr);
-      }
-      dcgan("encoder_Er.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
-      dcgan("encoder_Er.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{er, nullptr}, nullptr);
 
       // ---- PhyCell stack (model_blocks/phydnet.py:95-105) ----
       if (!branch_only) {
-        const void* xin = ep;
+        const void* xin = ep_in;
         for (int j = 0; j < n_phy; ++j) {
           const std::string p = "phycell.cell_list." + std::to_string(j) + ".";
           const void* h_act = hp_act[2 * j + ppar[j]];
@@ -401,7 +427,7 @@ class PhyDNetModel : public Model {
       }
       // ---- ConvLSTM stack (model_blocks/phydnet.py:147-163) ----
       {
-        const void* xin = er;
+        const void* xin = er_in;
         int cin = 64;
         for (int j = 0; j < n_lstm; ++j) {
           const int hd = d.convlstm_hidden_dims[j];
