@@ -294,3 +294,41 @@ def test_metric_partial_sums_kernel_matches_the_torch_definition():
         assert torch.equal(got, again)                               # fixed-order reductions
         m = E.finalize_metrics(got)
         assert len(m["mse"]) == shape[1] and m["sequences"] == shape[0]
+
+
+SWITCHES = [
+    # (environment switch, golden case, exact): every A/B switch of INTEGRATION.md sec. 5 selects an alternative code path
+    # that must stay correct; `exact` = the alternative performs the same arithmetic in the same order
+    ("VPK_PDL=0", "ef_3x32", True),
+    ("VPK_PDL=0", "phy_1x64", True),
+    ("VPK_NO_CTX_BATCH=1", "phy_3x64", True),
+    ("VPK_NO_CTX_BATCH=1", "branch_1x64", True),
+    ("VPK_NO_FUSED_GN=1", "phy_1x64", False),
+    ("VPK_NO_STEM=1", "phy_1x64", False),
+    ("VPK_NO_STEM=1", "ef_3x32", False),
+    ("VPK_NO_PHY_TAIL=1", "phy_1x64", False),
+    ("VPK_FEAT_SPLIT=1", "phy_1x64", False),
+    ("VPK_EF_NO_FUSE=1", "ef_3x32", False),
+    ("VPK_NO_FUSED_LN_STATS=1", "predrnn_ln_3x32", False),
+    ("VPK_NO_FUSED_DECOUPLE=1", "predrnn_3x32", True),
+    ("VPK_HALO_RESIDENT=0", "phy_1x64", True),
+]
+
+
+@pytest.mark.parametrize("switch,name,exact", SWITCHES)
+def test_ab_switches_select_correct_alternative_paths(manifest, switch, name, exact, monkeypatch):
+    meta = manifest["models"][name]
+    x = _input(meta).cuda()
+    gold = load_golden(name)["pred"]
+    m0, _ = _build(meta["key"], meta, precision="bf16")
+    with torch.no_grad():
+        ref = m0(x, pred_frames=meta["pred"])[0].clone()
+    var, val = switch.split("=")
+    monkeypatch.setenv(var, val)
+    m1, _ = _build(meta["key"], meta, precision="bf16")
+    with torch.no_grad():
+        got = m1(x, pred_frames=meta["pred"])[0].clone()
+    if exact:
+        assert torch.equal(got, ref), f"{switch}: max abs diff {(got - ref).abs().max().item()}"
+    errs = _frame_errs(got.cpu().numpy(), gold)
+    assert errs[0] <= BF16_TOL_FIRST and max(errs) <= BF16_TOL_LAST, f"{switch} on {name}: {errs}"
