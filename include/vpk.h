@@ -148,6 +148,11 @@ int vpk_convlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const 
 int vpk_stlstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w,
                            int32_t k, const float* w_x, const float* w_h, const float* w_m, const float* w_o,
                            const float* w_last, vpk_cell** out);
+/* layer_norm=True (model_blocks/predrnn.py:24-40): the affine parameters of the nn.LayerNorm([k*ch, h, w]) that follows
+ * conv_x (k = 7), conv_h (4), conv_m (3), conv_o (1); host fp32 in the reference layout [k*ch, h, w].  Call once after
+ * vpk_stlstm_cell_create; the cell then normalises the four conv outputs per sample (eps 1e-5). */
+int vpk_stlstm_cell_set_layer_norm(vpk_cell* cell, const float* gx, const float* bx, const float* gh, const float* bh,
+                                   const float* gm, const float* bm, const float* go, const float* bo);
 int vpk_stlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
                          const float* m, float* h_out, float* c_out, float* m_out, float* dc_out, float* dm_out,
                          void* stream);

@@ -134,6 +134,18 @@ def run_blocks(manifest):
         arrays[nm] = v.numpy()
     manifest["blocks"]["stlstm"] = dict(shapes=shp, wseed=23, xseed=7)
 
+    stl = SpatioTemporalLSTMCell(16, 32, 8, 8, 5, 1, True).eval()        # layer_norm=True (predrnn.py:24-40)
+    shp = shapes_of(stl)
+    stl.load_state_dict(synth_state_dict(shp, 25))
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+    h, c, mm = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(3)]
+    with torch.no_grad():
+        res = stl(x, h, c, mm)
+    for nm, v in zip(("stln_h", "stln_c", "stln_m", "stln_dc", "stln_dm"), res):
+        arrays[nm] = v.numpy()
+    manifest["blocks"]["stlstm_ln"] = dict(shapes=shp, wseed=25, xseed=9)
+
     pc = PhyCell_Cell(input_dim=16, action_conditional=False, action_size=0, hidden_dim=49, kernel_size=(7, 7)).eval()
     shp = shapes_of(pc)
     pc.load_state_dict(synth_state_dict(shp, 24))

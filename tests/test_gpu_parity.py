@@ -209,6 +209,16 @@ def test_blocks_match_reference_golden(manifest, precision, tol):
         for t, k in zip(res, ("st_h", "st_c", "st_m", "st_dc", "st_dm")):
             close(t, k)
 
+        stl = MB.SpatioTemporalLSTMCell(16, 32, 8, 8, 5, 1, True).to(dev)       # layer_norm=True
+        stl.precision = precision
+        stl.load_state_dict(synth_state_dict(mb["stlstm_ln"]["shapes"], mb["stlstm_ln"]["wseed"]))
+        g = torch.Generator().manual_seed(9)
+        x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+        h, c, m = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(3)]
+        res = stl(x.to(dev), h.to(dev), c.to(dev), m.to(dev))
+        for t, k in zip(res, ("stln_h", "stln_c", "stln_m", "stln_dc", "stln_dm")):
+            close(t, k)
+
         pc = MB.PhyCell_Cell(input_dim=16, action_conditional=False, action_size=0, hidden_dim=49,
                              kernel_size=(7, 7)).to(dev)
         pc.precision = precision

@@ -81,6 +81,17 @@ def test_blocks_match_reference(manifest):
         for nm, v in zip(("st_h", "st_c", "st_m", "st_dc", "st_dm"), res):
             assert np.abs(v.numpy() - gold[nm]).max() <= ATOL, nm
 
+        # ST-LSTM cell with layer_norm=True
+        sd = synth_state_dict(mb["stlstm_ln"]["shapes"], mb["stlstm_ln"]["wseed"])
+        g = torch.Generator().manual_seed(9)
+        x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+        h, c, m = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(3)]
+        ln = {k: (sd[f"conv_{k}.1.weight"], sd[f"conv_{k}.1.bias"]) for k in "xhmo"}
+        res = OB.stlstm_step(x, h, c, m, sd["conv_x.0.weight"], sd["conv_h.0.weight"], sd["conv_m.0.weight"],
+                             sd["conv_o.0.weight"], sd["conv_last.weight"], ln=ln)
+        for nm, v in zip(("stln_h", "stln_c", "stln_m", "stln_dc", "stln_dm"), res):
+            assert np.abs(v.numpy() - gold[nm]).max() <= ATOL, nm
+
         # PhyCell cell
         sd = synth_state_dict(mb["phycell"]["shapes"], mb["phycell"]["wseed"])
         g = torch.Generator().manual_seed(8)

@@ -215,6 +215,15 @@ int vpk_stlstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int3
   });
 }
 
+int vpk_stlstm_cell_set_layer_norm(vpk_cell* cell, const float* gx, const float* bx, const float* gh, const float* bh,
+                                   const float* gm, const float* bm, const float* go, const float* bo) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && gx && bx && gh && bh && gm && bm && go && bo, "null argument");
+    const float* p[8] = {gx, bx, gh, bh, gm, bm, go, bo};
+    cell->impl->set_layer_norm(p);
+  });
+}
+
 int vpk_stlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
                          const float* m, float* h_out, float* c_out, float* m_out, float* dc_out, float* dm_out,
                          void* stream) {

@@ -11,6 +11,7 @@
 #include "elementwise.h"
 #include "phycell.h"
 #include "stlstm.h"
+#include "stlstm_ln.h"
 
 namespace vpk {
 
@@ -139,8 +140,97 @@ class StLstmCell : public CellBase {
     wo.assign(w_o, w_o + static_cast<size_t>(ch) * 2 * ch * kk);
     wl.assign(w_last, w_last + static_cast<size_t>(ch) * 2 * ch);
   }
+  void set_layer_norm(const float* const* params) override {
+    const int mult[4] = {7, 4, 3, 1};
+    const int HW = h * w;
+    for (int i = 0; i < 8; ++i) {          // reference [kC, H, W] -> NHWC [HW][kC], the order of the raw conv outputs
+      const int kc = mult[i / 2] * ch;
+      ln[i].resize(static_cast<size_t>(kc) * HW);
+      for (int c = 0; c < kc; ++c)
+        for (int q = 0; q < HW; ++q) ln[i][static_cast<size_t>(q) * kc + c] = params[i][static_cast<size_t>(c) * HW + q];
+    }
+    has_ln = true;
+    built_batch = -1;
+  }
+  // layer_norm=True: the pipeline of stlstm_ln.h with a separate statistics launch (this boundary converts NCHW <-> NHWC
+  // around every call anyway; the fused-statistics form lives in the rollout)
+  void step_ln(int B, const float* const* in, float* const* out, cudaStream_t s) {
+    // fp16 operands in 16-bit mode, as in the rollout (LayerNorm amplifies bf16 operand rounding past the tolerance)
+    const int adt = (dtype == DT_BF16) ? DT_F16 : dtype;
+    const ActInfo a16{adt, esize()};
+    const size_t px = static_cast<size_t>(B) * h * w;
+    const int HW = h * w;
+    void* xb = buf("x", px * cin * esize());
+    void* hi = buf("h_in", px * ch * esize());
+    void* mi = buf("m_in", px * ch * esize());
+    void* ho = buf("h_out", px * ch * esize());
+    void* mem = buf("mem", px * 2 * ch * esize());
+    void* mact = buf("m_act", px * ch * esize());
+    void* dc = buf("dc", px * ch * esize());
+    void* dm = buf("dm", px * ch * esize());
+    float* cb = static_cast<float*>(buf("c", px * ch * sizeof(float)));
+    float* mb = static_cast<float*>(buf("m", px * ch * sizeof(float)));
+    float* op = static_cast<float*>(buf("o_part", px * ch * sizeof(float)));
+    float* xr = static_cast<float*>(buf("x_raw", px * 7 * ch * sizeof(float)));
+    float* hr = static_cast<float*>(buf("h_raw", px * 4 * ch * sizeof(float)));
+    float* mr = static_cast<float*>(buf("m_raw", px * 3 * ch * sizeof(float)));
+    float* orw = static_cast<float*>(buf("o_raw", px * ch * sizeof(float)));
+    float* lr = static_cast<float*>(buf("l_raw", px * ch * sizeof(float)));
+    float* part = static_cast<float*>(buf("ln_part", static_cast<size_t>(3) * B * kLnSlices * 2 * sizeof(float)));
+    if (d_ln[0] == nullptr)
+      for (int i = 0; i < 8; ++i) d_ln[i] = static_cast<float*>(store.upload(ln[i].data(), ln[i].size() * sizeof(float), s));
+    if (built_batch != B) {
+      convs.clear();
+      int oh, ow;
+      auto raw_conv = [&](const char* name, const void* src, int ci, int co, int kk, const float* wt, float* dst) {
+        ConvArgs a{std::string("cell.ln.") + name, B, h, w, ci, co, kk, 1, kk / 2, src, wt, nullptr, ACT_NONE, dst};
+        a.out_f32_dense = true;
+        for (BuiltConv& bc : build_conv(conv_spec(a, a16, &oh, &ow), adt, backend, store, cache, s, num_sms, false))
+          convs.push_back(bc);
+      };
+      raw_conv("x", xb, cin, 7 * ch, k, wx.data(), xr);
+      raw_conv("h", hi, ch, 4 * ch, k, wh.data(), hr);
+      raw_conv("m", mi, ch, 3 * ch, k, wm.data(), mr);
+      raw_conv("o", mem, 2 * ch, ch, k, wo.data(), orw);
+      raw_conv("last", mem, 2 * ch, ch, 1, wl.data(), lr);
+      finish_build(s);
+      built_batch = B;
+    }
+    to_nhwc(in[0], xb, adt, B, cin, h, w, s);
+    to_nhwc(in[1], hi, adt, B, ch, h, w, s);
+    to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
+    to_nhwc(in[3], mi, adt, B, ch, h, w, s);
+    to_nhwc(in[3], mb, DT_F32, B, ch, h, w, s);
+    auto run16 = [&](const BuiltConv& bc) {
+      if (bc.use_halo) launch_conv_halo(bc.halo, s);
+      else if (bc.use_tc) launch_conv_tc(bc.tc, s);
+      else if (bc.use_direct) launch_conv_direct(bc.L, adt, num_sms, s);
+      else launch_conv_simt(bc.L, adt, s);
+    };
+    for (int i = 0; i < 3; ++i) run16(convs[i]);
+    LnStatsArgs sa{{xr, hr, mr}, {7ll * ch * HW, 4ll * ch * HW, 3ll * ch * HW}, 3, B, part};
+    launch_ln_stats(sa, s);
+    float* px_ = part;
+    float* ph_ = part + static_cast<size_t>(B) * kLnSlices * 2;
+    float* pm_ = ph_ + static_cast<size_t>(B) * kLnSlices * 2;
+    StLnGatesArgs ga{xr, hr, mr, {px_, ph_, pm_}, {kLnSlices, kLnSlices, kLnSlices},
+                     d_ln[0], d_ln[1], d_ln[2], d_ln[3], d_ln[4], d_ln[5], cb, mb, mem, mact, dc, dm, op, B, HW, ch, adt, 1.0f};
+    launch_stlstm_ln_gates(ga, num_sms, s);
+    run16(convs[3]);
+    run16(convs[4]);
+    LnStatsArgs so{{orw, nullptr, nullptr}, {1ll * ch * HW, 0, 0}, 1, B, part};
+    launch_ln_stats(so, s);
+    StLnOutArgs oa{orw, lr, part, kLnSlices, d_ln[6], d_ln[7], op, ho, B, HW, ch, adt};
+    launch_stlstm_ln_out(oa, num_sms, s);
+    launch_nhwc_to_nchw(ho, adt, out[0], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(cb, DT_F32, out[1], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(mb, DT_F32, out[2], B, ch, h, w, num_sms, s);
+    if (out[3]) launch_nhwc_to_nchw(dc, adt, out[3], B, ch, h, w, num_sms, s);
+    if (out[4]) launch_nhwc_to_nchw(dm, adt, out[4], B, ch, h, w, num_sms, s);
+  }
   // in: x, h, c, m    out: h', c', m', delta_c, delta_m
   void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    if (has_ln) return step_ln(B, in, out, s);
     const size_t px = static_cast<size_t>(B) * h * w;
     void* xb = buf("x", px * cin * esize());
     void* hi = buf("h_in", px * ch * esize());
@@ -176,6 +266,9 @@ class StLstmCell : public CellBase {
  private:
   int cin, ch, h, w, k;
   std::vector<float> wx, wh, wm, wo, wl;
+  bool has_ln = false;
+  std::vector<float> ln[8];
+  float* d_ln[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 // ------------------------------------------------------------------------------------------------------------------

@@ -9,6 +9,8 @@ class Cell {
   virtual ~Cell() {}
   // in / out: up to 8 device pointers each, meaning defined per cell kind (see api.cu)
   virtual void step(int batch, const float* const* in, float* const* out, cudaStream_t stream) = 0;
+  // ST-LSTM only: LayerNorm affine parameters (gamma, beta) x (conv_x, conv_h, conv_m, conv_o), host, [k*C, H, W]
+  virtual void set_layer_norm(const float* const* params) { VPK_THROW(1, "this cell kind has no LayerNorm variant"); }
 };
 
 Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, int gate_order,

@@ -723,6 +723,7 @@ void launch_nhwc_to_nchw(const void* in, int dtype, float* out, int B, int C, in
   const long long total = static_cast<long long>(B) * C * H * W;
   const int g = grid_for(total, 256, num_sms);
   if (dtype == DT_F32) launch_pdl(nhwc_to_nchw_kernel<float>, dim3(g), dim3(256), 0, stream, static_cast<const float*>(in), out, B, C, H, W);
+  else if (dtype == DT_F16) launch_pdl(nhwc_to_nchw_kernel<__half>, dim3(g), dim3(256), 0, stream, static_cast<const __half*>(in), out, B, C, H, W);
   else launch_pdl(nhwc_to_nchw_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(in), out, B, C, H, W);
   VPK_CUDA(cudaGetLastError());
 }
@@ -733,6 +734,8 @@ void launch_frames_to_nhwc_strided(const float* x, long long bstride, void* out,
   const int g = grid_for(total, 256, num_sms);
   if (dtype == DT_F32)
     launch_pdl(frames_to_nhwc_kernel<float>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<float*>(out), B, T, C, H, W);
+  else if (dtype == DT_F16)
+    launch_pdl(frames_to_nhwc_kernel<__half>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<__half*>(out), B, T, C, H, W);
   else
     launch_pdl(frames_to_nhwc_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, x, bstride, static_cast<__nv_bfloat16*>(out), B, T, C,
                                                                H, W);

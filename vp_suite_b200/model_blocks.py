@@ -7,7 +7,7 @@ the arithmetic happens in libvpk's single-step cell entry points (include/vpk.h)
     ConvLSTM                <- vp_suite/model_blocks/conv_lstm_hzzone.py:7-70     (Shi et al., peepholes)
     ConvLSTMCell            <- vp_suite/model_blocks/conv_lstm_ndrplz.py:7-48     (ndrplz cell)
     SingleStepConvLSTM      <- vp_suite/model_blocks/phydnet.py:117-175
-    SpatioTemporalLSTMCell  <- vp_suite/model_blocks/predrnn.py:7-83              (layer_norm=False)
+    SpatioTemporalLSTMCell  <- vp_suite/model_blocks/predrnn.py:7-83
     PhyCell_Cell / PhyCell  <- vp_suite/model_blocks/phydnet.py:13-114            (action_conditional=False)
 """
 import ctypes as C
@@ -197,7 +197,7 @@ class SingleStepConvLSTM(nn.Module):
 
 
 class SpatioTemporalLSTMCell(VPModelBlock, _NativeCell):
-    """model_blocks/predrnn.py:7-83 with layer_norm=False."""
+    """model_blocks/predrnn.py:7-83, layer_norm False or True."""
     NAME = "Spatio-Temporal LSTM Cell"
     PAPER_REFERENCE = "https://arxiv.org/abs/2103.09504"
     CODE_REFERENCE = "https://github.com/thuml/predrnn-pytorch"
@@ -206,15 +206,17 @@ class SpatioTemporalLSTMCell(VPModelBlock, _NativeCell):
     def __init__(self, in_channel, num_hidden, height, width, filter_size, stride, layer_norm):
         super().__init__()
         self._cell_init()
-        if layer_norm:
-            raise NotImplementedError("layer_norm=True: SURVEY 8(f)")
         if stride != 1 or filter_size % 2 == 0:
             raise ValueError("stride 1 and odd filter sizes only")
         self.num_hidden, self.padding, self._forget_bias = num_hidden, filter_size // 2, 1.0
         self._shape = (in_channel, height, width, filter_size)
+        self._layer_norm = bool(layer_norm)
 
         def conv(ci, co):
-            return nn.Sequential(nn.Conv2d(ci, co, filter_size, stride, self.padding, bias=False))
+            layers = [nn.Conv2d(ci, co, filter_size, stride, self.padding, bias=False)]
+            if layer_norm:                                               # model_blocks/predrnn.py:24-40
+                layers.append(nn.LayerNorm([co, height, width]))
+            return nn.Sequential(*layers)
         self.conv_x = conv(in_channel, num_hidden * 7)
         self.conv_h = conv(num_hidden, num_hidden * 4)
         self.conv_m = conv(num_hidden, num_hidden * 3)
@@ -228,6 +230,10 @@ class SpatioTemporalLSTMCell(VPModelBlock, _NativeCell):
                                       self.conv_o[0].weight, self.conv_last.weight)]
         N.check(N.lib().vpk_stlstm_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], cin,
                                                self.num_hidden, h, w, k, *[N.ptr(t) for t in ws], C.byref(cell)))
+        if self._layer_norm:
+            ln = [self._host(t) for seq in (self.conv_x, self.conv_h, self.conv_m, self.conv_o)
+                  for t in (seq[1].weight, seq[1].bias)]
+            N.check(N.lib().vpk_stlstm_cell_set_layer_norm(cell, *[N.ptr(t) for t in ln]))
         return cell
 
     def forward(self, x_t, h_t, c_t, m_t):
