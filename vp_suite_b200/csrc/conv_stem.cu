@@ -40,7 +40,7 @@ template <bool F16> __device__ __forceinline__ void unpack8(const uint4& q, floa
 
 // x: [B][H][W][8] 16-bit (fp16 if F16IN, else bf16); wsm layout [ky][kx][ci][N] fp32; out: [B][OH][OW][N] fp32 (F32OUT)
 // or bf16.  One thread = kStemPX consecutive output positions of one output row.
-template <int CIN, int N, int STRIDE, bool F16IN, bool F32OUT>
+template <int CIN, int N, int STRIDE, bool F16IN, bool F32OUT, int PX>
 __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __restrict__ x, const float* __restrict__ wpk,
                                                                 const float* __restrict__ bias, void* __restrict__ out,
                                                                 int B, int H, int W, int OH, int OW, int act) {
@@ -52,8 +52,8 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
   __syncthreads();
   ptx::pdl_wait();
 
-  constexpr int NCOL = STRIDE * (kStemPX - 1) + 3;
-  const int gx = OW / kStemPX;
+  constexpr int NCOL = STRIDE * (PX - 1) + 3;
+  const int gx = OW / PX;
   const long long total = static_cast<long long>(B) * OH * gx;
   for (long long g = blockIdx.x * static_cast<long long>(kStemThreads) + threadIdx.x; g < total;
        g += static_cast<long long>(gridDim.x) * kStemThreads) {
@@ -61,10 +61,10 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
     const long long r = g / gx;
     const int oy = static_cast<int>(r % OH);
     const int b = static_cast<int>(r / OH);
-    const int ox0 = xg * kStemPX;
-    float acc[kStemPX][N];
+    const int ox0 = xg * PX;
+    float acc[PX][N];
 #pragma unroll
-    for (int p = 0; p < kStemPX; ++p)
+    for (int p = 0; p < PX; ++p)
 #pragma unroll
       for (int n = 0; n < N; ++n) acc[p][n] = 0.f;
     const int ix0 = ox0 * STRIDE - 1;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
           for (int n4 = 0; n4 < N / 4; ++n4) {
             const float4 wv = wr[n4];
 #pragma unroll
-            for (int p = 0; p < kStemPX; ++p) {
+            for (int p = 0; p < PX; ++p) {
               const float a = v[p * STRIDE + kx][ci];
               acc[p][4 * n4 + 0] = fmaf(a, wv.x, acc[p][4 * n4 + 0]);
               acc[p][4 * n4 + 1] = fmaf(a, wv.y, acc[p][4 * n4 + 1]);
@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
     }
     const long long obase = ((static_cast<long long>(b) * OH + oy) * OW + ox0) * N;
 #pragma unroll
-    for (int p = 0; p < kStemPX; ++p) {
+    for (int p = 0; p < PX; ++p) {
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         float y = acc[p][n] + s_b[n];
@@ -250,15 +250,18 @@ inline int grid_for_stem(long long n, int num_sms) {
   return static_cast<int>(std::max<long long>(1, std::min<long long>(blocks, static_cast<long long>(num_sms) * 16)));
 }
 
+// positions per thread: 4 at N = 16 (64 accumulators); 2 at N = 32 (4 x 32 accumulators need 255 registers: 11 % occupancy)
+template <int N> constexpr int stem_px() { return N >= 32 ? 2 : 4; }
 template <int CIN, int N, int STRIDE> void launch_stem_t(const StemArgs& a, int OH, int OW, int num_sms, cudaStream_t s) {
-  const long long groups = static_cast<long long>(a.B) * OH * (OW / kStemPX);
+  constexpr int PX = stem_px<N>();
+  const long long groups = static_cast<long long>(a.B) * OH * (OW / PX);
   const int grid = grid_for_stem(groups, num_sms);
   const uint4* x = static_cast<const uint4*>(a.x);
   if (a.x_f16)
-    launch_pdl(conv_stem_kernel<CIN, N, STRIDE, true, true>, dim3(grid), dim3(kStemThreads), 0, s, x, a.w, a.bias, a.out,
+    launch_pdl(conv_stem_kernel<CIN, N, STRIDE, true, true, PX>, dim3(grid), dim3(kStemThreads), 0, s, x, a.w, a.bias, a.out,
                a.B, a.H, a.W, OH, OW, a.act);
   else
-    launch_pdl(conv_stem_kernel<CIN, N, STRIDE, false, false>, dim3(grid), dim3(kStemThreads), 0, s, x, a.w, a.bias, a.out,
+    launch_pdl(conv_stem_kernel<CIN, N, STRIDE, false, false, PX>, dim3(grid), dim3(kStemThreads), 0, s, x, a.w, a.bias, a.out,
                a.B, a.H, a.W, OH, OW, a.act);
 }
 template <int CIN, int N> void launch_stem_s(const StemArgs& a, int OH, int OW, int num_sms, cudaStream_t s) {
