@@ -312,9 +312,22 @@ __global__ void __launch_bounds__(kPhyTailThreads) phy_f_tail_kernel(const float
   ptx::pdl_wait();
   const int b = blockIdx.x;
   const float* src = f1 + static_cast<size_t>(b) * HW * Cs;
-  for (int i = threadIdx.x; i < HW * Cs; i += kPhyTailThreads) {
-    const int p = i / Cs, k = i - p * Cs;
-    s_x[p * rs + k] = (k < hid) ? src[i] : 0.f;      // padding channels of f1 are never written by conv1: do not read them
+  // 16-byte global loads (Cs % 4 == 0); padding channels of f1 (k >= hid) are never written by conv1: only whole quads
+  // below hid are read, the ragged last quad element by element
+  const int q4 = Cs >> 2;
+  for (int i = threadIdx.x; i < HW * q4; i += kPhyTailThreads) {
+    const int p = i / q4, k = (i - p * q4) * 4;
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    if (k + 4 <= hid) {
+      const float4 t = *reinterpret_cast<const float4*>(src + static_cast<size_t>(p) * Cs + k);
+      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (k + j < hid) v[j] = src[static_cast<size_t>(p) * Cs + k + j];
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s_x[p * rs + k + j] = v[j];
   }
   __syncthreads();
   const int cg = hid / groups;
@@ -360,6 +373,7 @@ __global__ void __launch_bounds__(kPhyTailThreads) phy_f_tail_kernel(const float
       float acc[16];
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = s_b[o0 + j];
+#pragma unroll 7
       for (int k = 0; k < hid; ++k) {
         const float xv = s_x[p * rs + k];
         const float4* wr = reinterpret_cast<const float4*>(s_w + k * C + o0);
@@ -871,7 +885,8 @@ size_t phy_f_tail_smem(int HW, int hid, int Cs, int C) {
   return (static_cast<size_t>((HW * (Cs | 1) + 3) & ~3) + static_cast<size_t>(hid) * C + C) * sizeof(float);
 }
 bool phy_f_tail_supported(int HW, int hid, int Cs, int groups, int C) {
-  return hid <= 64 && groups <= 64 && hid % groups == 0 && C % 16 == 0 && Cs >= hid && phy_f_tail_smem(HW, hid, Cs, C) <= 200 * 1024;
+  return hid <= 64 && groups <= 64 && hid % groups == 0 && C % 16 == 0 && Cs >= hid && Cs % 4 == 0 &&
+         phy_f_tail_smem(HW, hid, Cs, C) <= 200 * 1024;
 }
 void launch_phy_f_tail(const float* f1, const float* h, float* htilde, const float* gamma, const float* beta,
                        const float* w2, const float* b2, int B, int HW, int hid, int Cs, int groups, int C, float eps,
