@@ -135,6 +135,23 @@ def test_ef_microbatching_and_graph_are_invisible(manifest):
     assert torch.equal(a, c) and torch.equal(c, c2)
 
 
+@pytest.mark.parametrize("name", ["ef_3x32", "predrnn_3x32", "phy_1x64", "branch_1x64"])
+def test_forward_host_matches_device_path(manifest, name, monkeypatch):
+    """Host-buffer entry (pinned H2D -> rollout -> per-frame D2H streaming, double-buffered microbatches) against the
+    device-tensor entry, with a ragged last microbatch; and the same without frame streaming."""
+    meta = dict(manifest["models"][name])
+    meta.update(batch=3)
+    x = _input(meta)
+    m, _ = _build(meta["key"], meta, precision="bf16", max_microbatch=2)
+    p = meta["pred"]
+    with torch.no_grad():
+        a = m(x.cuda(), pred_frames=p)[0].cpu()
+        b = m.forward_host(x.pin_memory(), pred_frames=p)[0].clone()     # the result buffer is reused across calls
+        monkeypatch.setenv("VPK_NO_FRAME_STREAM", "1")
+        c = m.forward_host(x.pin_memory(), pred_frames=p)[0].clone()
+    assert torch.equal(a, b) and torch.equal(a, c)
+
+
 def test_ef_forward_host_matches_device_path(manifest):
     meta = dict(manifest["models"]["ef_3x32"])
     meta.update(batch=3)

@@ -1,5 +1,7 @@
 #include "model.h"
 
+#include <cstdlib>
+
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
@@ -26,6 +28,7 @@ struct Model::HostPipe {
   size_t x_bytes = 0, out_bytes = 0, ws_bytes = 0;
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
+  std::vector<cudaEvent_t> ev_frame;       // one per predicted frame (frame streaming)
   bool init = false;
   ~HostPipe() {
     for (int i = 0; i < 2; ++i) {
@@ -34,6 +37,7 @@ struct Model::HostPipe {
     }
     if (ws) cudaFree(ws);
     if (d_aux) cudaFree(d_aux);
+    for (cudaEvent_t e : ev_frame) cudaEventDestroy(e);
     if (init) {
       for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(ev_in[i]);
@@ -227,6 +231,7 @@ void Model::run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx
       gate_flags.push_back(op.gate);
     }
     if (op.is_kernel) ++last_launches;
+    if (op.frame >= 0 && ctx.on_frame != nullptr) (*ctx.on_frame)(op, stream);
   }
 }
 
@@ -362,8 +367,34 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_in[buf], 0));
     if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_out[buf], 0));
     Program* prog = get_program(nb, t_in, pred, hpipe.ws, hpipe.ws_bytes, hpipe.s_comp);
+    // Frame streaming: as soon as the op that completes predicted frame p is enqueued, the frame is copied into this
+    // microbatch's output buffer and from there to the host on the copy stream, so that only the LAST frame's transfer
+    // (1 / pred of the output) is left when the rollout ends, not the whole microbatch's.
+    int frames_streamed = 0;
+    float* dout = static_cast<float*>(hpipe.d_out[buf]);
+    float* hout = out + mb0 * out_stride;
+    const std::function<void(const Op&, cudaStream_t)> on_frame = [&](const Op& op, cudaStream_t s) {
+      const size_t width = static_cast<size_t>(op.frame_elems) * sizeof(float);
+      const size_t pitch = out_stride * sizeof(float);
+      float* d_frame = dout + static_cast<size_t>(op.frame) * op.frame_elems;
+      VPK_CUDA(cudaMemcpy2DAsync(d_frame, pitch, op.frame_src, static_cast<size_t>(op.frame_pitch) * sizeof(float), width, nb,
+                                 cudaMemcpyDeviceToDevice, s));
+      while (hpipe.ev_frame.size() <= static_cast<size_t>(op.frame)) {
+        cudaEvent_t e;
+        VPK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        hpipe.ev_frame.push_back(e);
+      }
+      cudaEvent_t e = hpipe.ev_frame[op.frame];
+      VPK_CUDA(cudaEventRecord(e, s));
+      VPK_CUDA(cudaStreamWaitEvent(hpipe.s_out, e, 0));
+      VPK_CUDA(cudaMemcpy2DAsync(hout + static_cast<size_t>(op.frame) * op.frame_elems, pitch, d_frame, pitch, width, nb,
+                                 cudaMemcpyDeviceToHost, hpipe.s_out));
+      ++frames_streamed;
+    };
     RunCtx ctx{static_cast<const float*>(hpipe.d_x[buf]), static_cast<float*>(hpipe.d_out[buf]), hpipe.d_aux, mb0, nb,
                batch};
+    // (a CUDA-graph replay enqueues the whole body at once: no per-op hook, the whole-microbatch copy below is used)
+    if (getenv("VPK_NO_FRAME_STREAM") == nullptr && !(prog->graph != nullptr && timing == 0)) ctx.on_frame = &on_frame;
     run_ops(prog->pre, hpipe.s_comp, ctx);
     if (prog->graph != nullptr && timing == 0) {
       VPK_CUDA(cudaGraphLaunch(prog->graph, hpipe.s_comp));
@@ -374,10 +405,12 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     }
     run_ops(prog->post, hpipe.s_comp, ctx);
     VPK_CUDA(cudaEventRecord(hpipe.ev_comp[buf], hpipe.s_comp));
-    // D2H
+    VPK_REQUIRE(frames_streamed == 0 || frames_streamed == pred, "frame streaming: a rollout must mark every predicted frame");
+    // D2H (whole microbatch unless every frame has already been streamed)
     VPK_CUDA(cudaStreamWaitEvent(hpipe.s_out, hpipe.ev_comp[buf], 0));
-    VPK_CUDA(cudaMemcpyAsync(out + mb0 * out_stride, hpipe.d_out[buf], nb * out_stride * sizeof(float),
-                             cudaMemcpyDeviceToHost, hpipe.s_out));
+    if (frames_streamed != pred)
+      VPK_CUDA(cudaMemcpyAsync(out + mb0 * out_stride, hpipe.d_out[buf], nb * out_stride * sizeof(float),
+                               cudaMemcpyDeviceToHost, hpipe.s_out));
     VPK_CUDA(cudaEventRecord(hpipe.ev_out[buf], hpipe.s_out));
   }
   end_call(batch, hpipe.d_aux, hpipe.s_comp);

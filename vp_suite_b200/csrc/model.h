@@ -20,6 +20,7 @@ struct HostParam {
   bool provided = false;
 };
 
+struct Op;
 struct RunCtx {          // pointers of the current microbatch (already offset)
   const float* x;
   float* out;
@@ -27,6 +28,9 @@ struct RunCtx {          // pointers of the current microbatch (already offset)
   int mb0;               // first sequence of the microbatch
   int nb;                // sequences in it
   int batch;             // sequences of the whole call
+  // host-buffer entry only: called right after an op that completes a predicted frame (Op::frame >= 0) was enqueued,
+  // so that the frame's device-to-host copy can start while the rollout continues
+  const std::function<void(const Op&, cudaStream_t)>* on_frame = nullptr;
 };
 
 struct Op {
@@ -35,6 +39,11 @@ struct Op {
   double flops = 0;
   bool gate = false;     // counted in the gate-GEMM roofline figure
   bool is_kernel = true; // false for memsets / copies
+  // >= 0: this op writes the last bytes of predicted frame `frame` of every sequence of the microbatch, at
+  // frame_src + b * frame_pitch (fp32, frame_elems values each)
+  int frame = -1;
+  const float* frame_src = nullptr;
+  long long frame_pitch = 0, frame_elems = 0;
 };
 
 struct Program {

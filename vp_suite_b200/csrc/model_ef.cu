@@ -281,7 +281,18 @@ class EfConvLstm : public Model {
         VPK_REQUIRE(oh == dh[n + 1] && ow == dw[n + 1], "forecaster stage size mismatch");
         in = ybuf[n];
       }
-      if (fuse_final) continue;
+      auto mark_frame = [&]() {      // the op just added completes predicted frame t (host entry: starts its D2H)
+        if (measure || prog.body.empty()) return;
+        Op& o = prog.body.back();
+        o.frame = t;
+        o.frame_src = out_stage + static_cast<size_t>(t) * c * h * w;
+        o.frame_pitch = static_cast<long long>(pred) * c * h * w;
+        o.frame_elems = static_cast<long long>(c) * h * w;
+      };
+      if (fuse_final) {
+        mark_frame();
+        continue;
+      }
       // identity + final 1x1 conv (ef_conv_lstm.py:99-104), written as fp32 NCHW frame t of the staging tensor
       int oh, ow;
       ConvArgs fa{"forecaster.stage1.final.", B, h, w, d.final_conv_c, c, 1, 1, 0, ybuf[2],
@@ -293,6 +304,7 @@ class EfConvLstm : public Model {
       fa.oY = w;
       fa.oX = 1;
       add_conv(prog, conv_spec(fa, act, &oh, &ow), measure, stream);
+      mark_frame();
     }
     if (!measure) {
       const size_t bytes = frame_px * c * sizeof(float) * pred;
@@ -300,6 +312,7 @@ class EfConvLstm : public Model {
       post.name = "copy_out";
       post.is_kernel = false;
       post.fn = [=](cudaStream_t s, const RunCtx& ctx) {
+        if (ctx.on_frame != nullptr) return;     // host entry with frame streaming: every frame has been copied already
         VPK_CUDA(cudaMemcpyAsync(ctx.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s));
       };
       prog.post.push_back(std::move(post));

@@ -348,6 +348,14 @@ class PhyDNetModel : public Model {
       Bcur = B;
     }
 
+    auto mark_frame = [&](int di) {   // the op just added completes predicted frame di (host entry: starts its D2H)
+      if (measure || prog.body.empty()) return;
+      Op& o = prog.body.back();
+      o.frame = di;
+      o.frame_src = out_stage + static_cast<size_t>(di) * c * h * w;
+      o.frame_pitch = static_cast<long long>(pred) * c * h * w;
+      o.frame_elems = static_cast<long long>(c) * h * w;
+    };
     std::vector<int> ppar(n_phy, 0), lpar(n_lstm, 0);
     const int n_steps = (t_in - 1) + pred;
     for (int st = 0; st < n_steps; ++st) {
@@ -476,6 +484,7 @@ class PhyDNetModel : public Model {
           op.flops = 2.0 * static_cast<double>(px2) * 32 * 9 * c;
           op.fn = [=](cudaStream_t s, const RunCtx&) { launch_deconv_tail(ta, ns, s); };
           prog.body.push_back(std::move(op));
+          mark_frame(di);
         }
         continue;
       }
@@ -490,6 +499,7 @@ class PhyDNetModel : public Model {
         const ActInfo& ai = tcfeat ? sa : f32a;
         add_conv(prog, deconv_spec(a, ai, &oh, &ow), measure, stream, ai.dtype);
         VPK_REQUIRE(oh == h && ow == w, "decoder output size mismatch");
+        mark_frame(di);
       }
       if (!measure && di + 1 < pred) {   // next decoder input = output_image (models/phydnet.py:121)
         const float* src = out_stage + static_cast<size_t>(di) * c * h * w;
@@ -509,6 +519,7 @@ class PhyDNetModel : public Model {
       post.name = "copy_out";
       post.is_kernel = false;
       post.fn = [=](cudaStream_t s, const RunCtx& rc) {
+        if (rc.on_frame != nullptr) return;      // host entry with frame streaming: every frame has been copied already
         VPK_CUDA(cudaMemcpyAsync(rc.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s));
       };
       prog.post.push_back(std::move(post));

@@ -260,6 +260,10 @@ class PredRnnV2 : public Model {
           op.fn = [=](cudaStream_t s, const RunCtx&) {
             launch_unpatchify(xgen32, out_stage, DT_F32, B, pred, fo, c, h, w, pp, ns, s);
           };
+          op.frame = fo;       // completes predicted frame fo (host entry: its D2H starts here)
+          op.frame_src = out_stage + static_cast<size_t>(fo) * c * h * w;
+          op.frame_pitch = static_cast<long long>(pred) * c * h * w;
+          op.frame_elems = static_cast<long long>(c) * h * w;
           prog.body.push_back(std::move(op));
         }
       }
@@ -278,6 +282,7 @@ class PredRnnV2 : public Model {
       post.name = "copy_out";
       post.is_kernel = false;
       post.fn = [=](cudaStream_t s, const RunCtx& rc) {
+        if (rc.on_frame != nullptr) return;      // host entry with frame streaming: every frame has been copied already
         VPK_CUDA(cudaMemcpyAsync(rc.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s));
       };
       prog.post.push_back(std::move(post));
