@@ -217,7 +217,8 @@ def main():
     tgt_host = torch.rand((B, pred, *img), generator=g, dtype=torch.float32)
     x_dev = x_host.to(dev)
     tgt_dev = tgt_host.to(dev)
-    in_bytes = x_host.numel() * 4
+    # bytes the host entry really copies: predrnn-pp reads only the context frames of its context + target input
+    in_bytes = B * ctx * img[0] * img[1] * img[2] * 4 if key == "predrnn-pp" else x_host.numel() * 4
     out_bytes = B * pred * img[0] * img[1] * img[2] * 4
 
     def metrics_reduce(pred_frames):

@@ -360,8 +360,15 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     const int buf = it & 1;
     // H2D of this microbatch; d_x[buf] was last read by the compute of iteration it-2
     if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_in, hpipe.ev_comp[buf], 0));
-    VPK_CUDA(cudaMemcpyAsync(hpipe.d_x[buf], x + mb0 * in_stride, nb * in_stride * sizeof(float),
-                             cudaMemcpyHostToDevice, hpipe.s_in));
+    {
+      const size_t used = static_cast<size_t>(used_in_frames(t_in, pred)) * desc.img_c * desc.img_h * desc.img_w;
+      if (used == in_stride)
+        VPK_CUDA(cudaMemcpyAsync(hpipe.d_x[buf], x + mb0 * in_stride, nb * in_stride * sizeof(float),
+                                 cudaMemcpyHostToDevice, hpipe.s_in));
+      else      // only the frames the rollout reads, same device layout (sequence pitch unchanged)
+        VPK_CUDA(cudaMemcpy2DAsync(hpipe.d_x[buf], in_stride * sizeof(float), x + mb0 * in_stride, in_stride * sizeof(float),
+                                   used * sizeof(float), nb, cudaMemcpyHostToDevice, hpipe.s_in));
+    }
     VPK_CUDA(cudaEventRecord(hpipe.ev_in[buf], hpipe.s_in));
     // compute; d_out[buf] was last read by the D2H of iteration it-2
     VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_in[buf], 0));

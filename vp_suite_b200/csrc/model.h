@@ -85,6 +85,8 @@ class Model {
   virtual void validate(int t_in, int pred) const {}
   virtual int default_microbatch() const { return 64; }
   virtual int in_frames(int t_in, int pred) const { return t_in; }
+  // frames of each input sequence the rollout really reads (the host entry copies only these to the device)
+  virtual int used_in_frames(int t_in, int pred) const { return in_frames(t_in, pred); }
   virtual void begin_call(int batch, float* aux, cudaStream_t stream) {}
   virtual void end_call(int batch, float* aux, cudaStream_t stream) {}
 

@@ -62,6 +62,9 @@ class PredRnnV2 : public Model {
     if (t_in - pred < 1) VPK_THROW(1, "predrnn-pp needs input sequences that also include the target frames");
   }
   int default_microbatch() const override { return 256; }
+  // eval mode reads the context frames only (the mask is all zero, predrnn_v2.py:300-309): the target frames that
+  // NEEDS_COMPLETE_INPUT puts behind them never have to reach the device
+  int used_in_frames(int t_in, int pred) const override { return t_in - pred; }
 
   void begin_call(int, float*, cudaStream_t stream) override {
     if (!d_loss) VPK_CUDA(cudaMalloc(&d_loss, sizeof(double)));
