@@ -29,6 +29,7 @@ struct Model::HostPipe {
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
   std::vector<cudaEvent_t> ev_frame;       // one per predicted frame (frame streaming)
+  std::vector<cudaEvent_t> ev_in_frame;    // [2 buffers][input frames] (input frame streaming)
   bool init = false;
   ~HostPipe() {
     for (int i = 0; i < 2; ++i) {
@@ -38,6 +39,7 @@ struct Model::HostPipe {
     if (ws) cudaFree(ws);
     if (d_aux) cudaFree(d_aux);
     for (cudaEvent_t e : ev_frame) cudaEventDestroy(e);
+    for (cudaEvent_t e : ev_in_frame) cudaEventDestroy(e);
     if (init) {
       for (int i = 0; i < 2; ++i) {
         cudaEventDestroy(ev_in[i]);
@@ -219,6 +221,7 @@ void Model::run_ops(std::vector<Op>& ops, cudaStream_t stream, const RunCtx& ctx
       }
       VPK_CUDA(cudaEventRecord(ev_pool[ev_used], stream));
     }
+    if (op.needs_input >= 0 && ctx.on_input != nullptr) (*ctx.on_input)(op.needs_input, stream);
     op.fn(stream, ctx);
     if (t) {
       VPK_CUDA(cudaEventRecord(ev_pool[ev_used + 1], stream));
@@ -360,7 +363,24 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     const int buf = it & 1;
     // H2D of this microbatch; d_x[buf] was last read by the compute of iteration it-2
     if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_in, hpipe.ev_comp[buf], 0));
-    {
+    const bool frame_in = streams_input() && getenv("VPK_NO_FRAME_STREAM") == nullptr;
+    const size_t chw = static_cast<size_t>(desc.img_c) * desc.img_h * desc.img_w;
+    if (frame_in) {
+      // one 2-D copy per input frame (all sequences of the microbatch), each with its own event: the rollout's step t
+      // waits for frame t only, so compute starts after 1 / t_in of the microbatch's input has arrived
+      const int nf = used_in_frames(t_in, pred);
+      while (hpipe.ev_in_frame.size() < static_cast<size_t>(2 * nf)) {
+        cudaEvent_t e;
+        VPK_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        hpipe.ev_in_frame.push_back(e);
+      }
+      for (int f = 0; f < nf; ++f) {
+        VPK_CUDA(cudaMemcpy2DAsync(static_cast<float*>(hpipe.d_x[buf]) + f * chw, in_stride * sizeof(float),
+                                   x + mb0 * in_stride + f * chw, in_stride * sizeof(float), chw * sizeof(float), nb,
+                                   cudaMemcpyHostToDevice, hpipe.s_in));
+        VPK_CUDA(cudaEventRecord(hpipe.ev_in_frame[buf * nf + f], hpipe.s_in));
+      }
+    } else {
       const size_t used = static_cast<size_t>(used_in_frames(t_in, pred)) * desc.img_c * desc.img_h * desc.img_w;
       if (used == in_stride)
         VPK_CUDA(cudaMemcpyAsync(hpipe.d_x[buf], x + mb0 * in_stride, nb * in_stride * sizeof(float),
@@ -371,7 +391,7 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     }
     VPK_CUDA(cudaEventRecord(hpipe.ev_in[buf], hpipe.s_in));
     // compute; d_out[buf] was last read by the D2H of iteration it-2
-    VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_in[buf], 0));
+    if (!frame_in) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_in[buf], 0));
     if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_out[buf], 0));
     Program* prog = get_program(nb, t_in, pred, hpipe.ws, hpipe.ws_bytes, hpipe.s_comp);
     // Frame streaming: as soon as the op that completes predicted frame p is enqueued, the frame is copied into this
@@ -400,6 +420,11 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     };
     RunCtx ctx{static_cast<const float*>(hpipe.d_x[buf]), static_cast<float*>(hpipe.d_out[buf]), hpipe.d_aux, mb0, nb,
                batch};
+    const int nf_in = used_in_frames(t_in, pred);
+    const std::function<void(int, cudaStream_t)> on_input = [&](int f, cudaStream_t s) {
+      VPK_CUDA(cudaStreamWaitEvent(s, hpipe.ev_in_frame[buf * nf_in + f], 0));
+    };
+    if (frame_in) ctx.on_input = &on_input;
     // (a CUDA-graph replay enqueues the whole body at once: no per-op hook, the whole-microbatch copy below is used)
     if (getenv("VPK_NO_FRAME_STREAM") == nullptr && !(prog->graph != nullptr && timing == 0)) ctx.on_frame = &on_frame;
     run_ops(prog->pre, hpipe.s_comp, ctx);

@@ -31,6 +31,9 @@ struct RunCtx {          // pointers of the current microbatch (already offset)
   // host-buffer entry only: called right after an op that completes a predicted frame (Op::frame >= 0) was enqueued,
   // so that the frame's device-to-host copy can start while the rollout continues
   const std::function<void(const Op&, cudaStream_t)>* on_frame = nullptr;
+  // host-buffer entry only: called right BEFORE an op that is the first to read input frame Op::needs_input, so that
+  // the compute stream waits for that frame's host-to-device copy only (the frames arrive one by one)
+  const std::function<void(int frame, cudaStream_t)>* on_input = nullptr;
 };
 
 struct Op {
@@ -42,6 +45,7 @@ struct Op {
   // >= 0: this op writes the last bytes of predicted frame `frame` of every sequence of the microbatch, at
   // frame_src + b * frame_pitch (fp32, frame_elems values each)
   int frame = -1;
+  int needs_input = -1;  // >= 0: the first op that reads input frame `needs_input` of the microbatch
   const float* frame_src = nullptr;
   long long frame_pitch = 0, frame_elems = 0;
 };
@@ -87,6 +91,9 @@ class Model {
   virtual int in_frames(int t_in, int pred) const { return t_in; }
   // frames of each input sequence the rollout really reads (the host entry copies only these to the device)
   virtual int used_in_frames(int t_in, int pred) const { return in_frames(t_in, pred); }
+  // true: the program converts input frame t in its own op (marked Op::needs_input = t) instead of converting all frames
+  // up front, so the host entry may deliver the frames one by one
+  virtual bool streams_input() const { return false; }
   virtual void begin_call(int batch, float* aux, cudaStream_t stream) {}
   virtual void end_call(int batch, float* aux, cudaStream_t stream) {}
 

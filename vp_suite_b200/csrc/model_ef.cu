@@ -175,15 +175,17 @@ class EfConvLstm : public Model {
 
     if (!measure) {
       const int ns = num_sms, dt = dtype;
-      Op pre;
-      pre.name = "frames_to_nhwc";
-      pre.fn = [=](cudaStream_t s, const RunCtx& ctx) {
-        if (pad8)
-          launch_frames_to_nhwc8(ctx.x, static_cast<long long>(t_in) * c * h * w, frames_in, nullptr, DT_BF16, B, t_in, c, h, w, ns, s);
-        else
-          launch_frames_to_nhwc(ctx.x, frames_in, dt, B, t_in, c, h, w, ns, s);
-      };
-      prog.pre.push_back(std::move(pre));
+      if (!streams_input()) {       // CUDA-graph replay: the conversion reads the call's input pointer, so it stays outside
+        Op pre;
+        pre.name = "frames_to_nhwc";
+        pre.fn = [=](cudaStream_t s, const RunCtx& ctx) {
+          if (pad8)
+            launch_frames_to_nhwc8(ctx.x, static_cast<long long>(t_in) * c * h * w, frames_in, nullptr, DT_BF16, B, t_in, c, h, w, ns, s);
+          else
+            launch_frames_to_nhwc(ctx.x, frames_in, dt, B, t_in, c, h, w, ns, s);
+        };
+        prog.pre.push_back(std::move(pre));
+      }
       for (int n = 0; n < 3; ++n) {
         const size_t px = static_cast<size_t>(B) * eh[n] * ew[n];
         add_memset(prog, hbuf[n][0], px * d.enc_c[2 * n + 1] * esz, "zero_h");
@@ -199,6 +201,21 @@ class EfConvLstm : public Model {
     // ------------------------------------------ encoder (ef_blocks.py:67-82) ---------------------------------
     for (int t = 0; t < t_in; ++t) {
       const void* in = frames_in + static_cast<size_t>(t) * frame_px * cs * esz;
+      if (!measure && streams_input()) {
+        // input frame t is converted right before the step that reads it; under the host entry this op waits for the
+        // frame's own host-to-device copy only
+        const int ns = num_sms, dt = dtype;
+        char* dst = frames_in + static_cast<size_t>(t) * frame_px * cs * esz;
+        const long long bstride = static_cast<long long>(t_in) * c * h * w, foff = static_cast<long long>(t) * c * h * w;
+        Op cv;
+        cv.name = "frames_to_nhwc";
+        cv.needs_input = t;
+        cv.fn = [=](cudaStream_t s, const RunCtx& ctx) {
+          if (pad8) launch_frames_to_nhwc8(ctx.x + foff, bstride, dst, nullptr, DT_BF16, B, 1, c, h, w, ns, s);
+          else launch_frames_to_nhwc_strided(ctx.x + foff, bstride, dst, dt, B, 1, c, h, w, ns, s);
+        };
+        prog.body.push_back(std::move(cv));
+      }
       int in_h = h, in_w = w, in_c = cs;
       for (int n = 0; n < 3; ++n) {
         const std::string st = "encoder.stage" + std::to_string(n + 1) + ".conv.";
@@ -318,6 +335,8 @@ class EfConvLstm : public Model {
       prog.post.push_back(std::move(post));
     }
   }
+
+  bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_EF_NO_INPUT_STREAM") == nullptr; }
 
  private:
   int eh[3], ew[3], dh[4], dw[4], dec_in_c[3];
