@@ -339,6 +339,9 @@ SWITCHES = [
     ("VPK_NO_FUSED_LN_STATS=1", "predrnn_ln_3x32", False),
     ("VPK_NO_FUSED_DECOUPLE=1", "predrnn_3x32", True),
     ("VPK_HALO_RESIDENT=0", "phy_1x64", True),
+    # small batches use the sub-pixel deconv by default: the per-parity form adds the same products in the same order
+    ("VPK_SUBPIX=0", "ef_3x32", True),
+    ("VPK_SUBPIX=0", "ef_1x64", True),
 ]
 
 

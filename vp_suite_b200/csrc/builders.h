@@ -159,6 +159,46 @@ struct DeconvArgs {
   const float* proj_b = nullptr;   // device fp32 [proj_n]
   int proj_n = 0;
 };
+// The same stride-2 transposed conv in sub-pixel form (lowering.h): one launch, dense NHWC output (activation type or fp32).
+inline ConvSpec deconv_subpix_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
+  ConvSpec s;
+  s.name = a.name + "subpix.";
+  s.B = a.B;
+  s.G = 4;
+  s.C = a.Cout;
+  WeightRef w;
+  w.w = a.weight;
+  w.O = a.Cout;
+  w.I = a.Cin;
+  w.KH = w.KW = a.k;
+  w.transposed = true;
+  for (int g = 0; g < 4; ++g) w.gate_block[g] = 0;
+  s.wrefs.push_back(w);
+  if (a.bias) {
+    BiasRef b;
+    b.b = a.bias;
+    for (int g = 0; g < 4; ++g) b.gate_block[g] = 0;
+    s.biases.push_back(b);
+  }
+  ConvInput cin{make_view(a.x, a.H, a.W, a.Cin), 0, 0};
+  lower_conv_transpose_subpixel(s, a.k, a.pad, a.out_pad, cin, a.H, a.W, oh, ow);
+  EpiParams& e = s.phases[0].epi;
+  e.kind = EPI_SUBPIX;
+  e.act = a.act;
+  e.out = a.out;
+  e.out_f32 = a.out_f32 ? 1 : 0;
+  const long long C = a.Cout, OW = *ow, OH = *oh;
+  e.oB = OH * OW * C;
+  e.oY = 2 * OW * C;
+  e.oX = 2 * C;
+  e.oC = 1;
+  e.ps_row = OW * C;
+  return s;
+}
+inline bool deconv_subpix_ok(const DeconvArgs& a) {
+  if (a.stride != 2 || a.split || a.nchw || a.proj_n > 0 || a.Cout % 8 != 0 || a.Cin % 8 != 0) return false;
+  return (a.H - 1) * 2 - 2 * a.pad + a.k + a.out_pad == 2 * a.H;
+}
 inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
   s.name = a.name;

@@ -69,6 +69,8 @@ enum EpiKind : int {
   EPI_ST_M = 3,           // G=3  (i',f',g') ST-LSTM spatio-temporal-memory update
   EPI_ST_O = 4,           // G=2  (conv_o, conv_last) ST-LSTM output gate
   EPI_PHY_GATE = 5,       // G=1  PhyCell Kalman-style blend
+  EPI_SUBPIX = 7,         // G=4  sub-pixel transposed conv: gate (ry, rx) of a position is output pixel (2y + ry, 2x + rx);
+                          //      y = act(acc + bias) stored as activation type at out + b*oB + y*oY + x*oX + ry*ps_row + rx*C + ch
   EPI_DECOUPLE = 6,       // G=2  (adapter(delta_c), adapter(delta_m)): per-(sample, channel) dot product and squared norms
                           //      over the positions (PredRNN-V2 decoupling loss); nothing else is stored.  tcgen05 halo
                           //      kernel only: s1[b][slot][C][3] gets one warp's 32 positions per slot (slot as gn_slot0 / gn_nslots)
@@ -121,6 +123,7 @@ struct EpiParams {
   int gn_group_size;      // channels per group (0 = disabled); -1 = ONE group = the whole sample (LayerNorm over C, H, W):
                           //   gn_sums[b][slot][2] with slot = gn_slot0 + ((tile in image) * n_tiles + N tile) * 8 + quadrant * 2 + half
   int gn_slot0, gn_nslots;
+  long long ps_row;       // EPI_SUBPIX: elements between two output rows (OW * C)
 };
 
 struct ConvLaunch {

@@ -52,7 +52,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint
 }
 
 __host__ __device__ constexpr int gates_of(int kind) {
-  return (kind == EPI_LSTM || kind == EPI_ST_C) ? 4 : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O || kind == EPI_DECOUPLE) ? 2 : 1;
+  return (kind == EPI_LSTM || kind == EPI_ST_C || kind == EPI_SUBPIX) ? 4
+         : (kind == EPI_ST_M) ? 3 : (kind == EPI_ST_O || kind == EPI_DECOUPLE) ? 2 : 1;
 }
 
 // MODE: 0 generic epilogue, 1 lean compile-time epilogue, 2 ConvLSTM epilogue with a whole tile of operands in flight,
@@ -610,6 +611,61 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         };
         bool stats = false;
         if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr && P.L.epi.gn_group_size > 0;
+        if constexpr (KIND == EPI_SUBPIX) {
+          // sub-pixel transposed conv: the four gates of a channel are the four output pixels of this input position;
+          // optional GroupNorm statistics of the stored values (all four pixels feed the channel's group), as in BIAS_ACT
+          stats = false;
+          const EpiParams& E = P.L.epi;
+          const bool gstats = E.gn_sums != nullptr;
+          const int gsz = E.gn_group_size;
+          float gs16[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) gs16[i] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int ch = half * 8 + 16 * k;
+            if (ch < Cn) {
+              uint32_t r[8 * G];
+              tmem_chunk(ch, r);
+              ptx::tmem_ld_wait();
+              const bool live = valid && ch_base + ch < C;
+              const float4* bp = reinterpret_cast<const float4*>(bias + (ch_base + ch) * 4);
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const float4 bv = bp[j];
+                  const float bj = g == 0 ? bv.x : g == 1 ? bv.y : g == 2 ? bv.z : bv.w;
+                  float t = __uint_as_float(r[j * 4 + g]) + bj;
+                  if (E.act == ACT_LEAKY) t = t > 0.f ? t : 0.2f * t;
+                  else if (E.act == ACT_RELU) t = fmaxf(t, 0.f);
+                  v[j] = live ? t : 0.f;
+                }
+                if (live) {
+                  const long long off = et.out_off + (g >> 1) * E.ps_row + (g & 1) * C + ch_base + ch;
+                  if (E.out_f32) st_f32x8(static_cast<float*>(E.out) + off, v);
+                  else st_bf16x8(static_cast<bf16*>(E.out) + off, v);
+                }
+                if (gstats && k < 4) {
+                  if (gsz == 2) gn_accum<2>(gs16, k, v);
+                  else if (gsz == 4) gn_accum<4>(gs16, k, v);
+                  else gn_accum<8>(gs16, k, v);
+                }
+              }
+            }
+          }
+          if (gstats) {
+            const float tot = gn_warp_reduce16(gs16, lane);
+            const int vi = gn_lane_value(lane), pairi = vi >> 1, gpc = 8 / gsz;
+            const int kk = pairi / gpc, jj = pairi - kk * gpc;
+            const int chg = ch_base + half * 8 + 16 * kk;
+            if ((lane & 1) == 0 && b < P.L.B && half * 8 + 16 * kk < Cn && chg < C) {
+              const int slot = E.gn_slot0 + (mt % (P.tiles_x * P.tiles_y)) * 4 + quad;
+              E.gn_sums[((static_cast<long long>(b) * E.gn_nslots + slot) * (C / gsz) + chg / gsz + jj) * 2 + (vi & 1)] = tot;
+            }
+          }
+        } else
         if constexpr (KIND == EPI_DECOUPLE) {
           // PredRNN-V2 decoupling loss: acc = (adapter(delta_c), adapter(delta_m)) of 8 channels at this position; the
           // warp's 32 positions are reduced to dot / |c|^2 / |m|^2 per channel (32-value butterfly) and stored to this
@@ -867,8 +923,9 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
                 "halo plan: fused LayerNorm statistics need the lean BIAS_ACT epilogue");
   } else if (L.epi.gn_sums != nullptr) {
     const int gs = L.epi.gn_group_size;
-    VPK_REQUIRE(P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0 && L.epi.res == nullptr &&
-                    (gs == 2 || gs == 4 || gs == 8) && L.Cn <= 64 && L.Cn / gs <= 16 && L.epi.C % gs == 0,
+    VPK_REQUIRE(P.fast_epi && (L.epi.kind == EPI_BIAS_ACT || L.epi.kind == EPI_SUBPIX) && L.epi.proj_n == 0 &&
+                    L.epi.res == nullptr && (gs == 2 || gs == 4 || gs == 8) && L.Cn <= 64 && L.Cn / gs <= 16 &&
+                    L.epi.C % gs == 0,
                 "halo plan: fused GroupNorm statistics need the lean BIAS_ACT epilogue, <= 64 channels per tile and groups of 2/4/8");
   }
   P.tmem_cols = std::max(32, pow2_at_least(2 * P.tileN));
@@ -991,6 +1048,11 @@ void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
     case EPI_ST_M: VPK_HALO(EPI_ST_M);
     case EPI_ST_O: VPK_HALO(EPI_ST_O);
     case EPI_PHY_GATE: VPK_HALO(EPI_PHY_GATE);
+    case EPI_SUBPIX:
+      VPK_REQUIRE(P.fast_epi, "conv_halo: the sub-pixel epilogue needs whole 8-channel chunks");
+      if (P.pair) launch_one<EPI_SUBPIX, true, 1>(P, stream);
+      else launch_one<EPI_SUBPIX, false, 1>(P, stream);
+      break;
     case EPI_DECOUPLE:
       VPK_REQUIRE(P.fast_epi, "conv_halo: the decoupling-loss epilogue needs whole 8-channel chunks");
       if (P.pair) launch_one<EPI_DECOUPLE, true, 1>(P, stream);

@@ -142,7 +142,7 @@ __host__ __device__ inline bool epi_tc_fast_ok(const EpiParams& E) {
 template <int KIND>
 __device__ __forceinline__ void epi_tc_prefetch(const EpiParams& E, const EpiTile& t, int ch, EpiOperands<8>& o) {
   using bf16 = __nv_bfloat16;
-  if constexpr (KIND == EPI_DECOUPLE) return;      // handled inside the halo kernel (cross-lane reduction)
+  if constexpr (KIND == EPI_DECOUPLE || KIND == EPI_SUBPIX) return;      // handled inside the halo kernel itself
   if constexpr (KIND == EPI_LSTM) {
     ld_state8(E.s0, t.st_off, t.st_g, ch, o.a);
     if (E.p0 != nullptr) {
@@ -165,7 +165,7 @@ template <int KIND, int G>
 __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile& t, int ch, const float* s_bias,
                                               float (&acc)[G][8], EpiOperands<8>& o) {
   using bf16 = __nv_bfloat16;
-  if constexpr (KIND == EPI_DECOUPLE) return;      // handled inside the halo kernel (cross-lane reduction)
+  if constexpr (KIND == EPI_DECOUPLE || KIND == EPI_SUBPIX) return;      // handled inside the halo kernel itself
   if (s_bias != nullptr) {   // packed order (ch + j) * G + g: 8*G consecutive floats
     const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * G);
 #pragma unroll

@@ -142,11 +142,14 @@ void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pa
       ph.H = (OH - ry + stride - 1) / stride;
       ph.W = (OW - rx + stride - 1) / stride;
       // y = stride*iy - pad + ky  with  y = stride*q + ry   =>   iy = q + (ry + pad - ky) / stride
+      // taps in ascending (dy, dx) order = descending (ky, kx): the same order in which the sub-pixel form
+      // (lower_conv_transpose_subpixel) meets them, so that both forms add a pixel's products in the same sequence and
+      // agree bit for bit (which form runs depends on the problem size)
       auto emit = [&](int s_idx, int wsplit, int c0) {
-        for (int ky = 0; ky < k; ++ky) {
+        for (int ky = k - 1; ky >= 0; --ky) {
           if (((ry + pad - ky) % stride + stride) % stride != 0) continue;
           const int dy = floordiv(ry + pad - ky, stride);
-          for (int kx = 0; kx < k; ++kx) {
+          for (int kx = k - 1; kx >= 0; --kx) {
             if (((rx + pad - kx) % stride + stride) % stride != 0) continue;
             const int dx = floordiv(rx + pad - kx, stride);
             add_step(ph.steps, s_idx, dy, dx, input.view.C, c0, input.wref, ky, kx, input.wc0, input.wc_count, wsplit);
@@ -166,6 +169,52 @@ void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pa
       ph.epi = epi_for_phase(ry, rx, stride, OH, OW);
       spec.phases.push_back(ph);
     }
+  *oh = OH;
+  *ow = OW;
+}
+
+void lower_conv_transpose_subpixel(ConvSpec& spec, int k, int pad, int out_pad, const ConvInput& input, int in_h, int in_w,
+                                   int* oh, int* ow) {
+  const int OH = (in_h - 1) * 2 - 2 * pad + k + out_pad;
+  const int OW = (in_w - 1) * 2 - 2 * pad + k + out_pad;
+  VPK_REQUIRE(OH == 2 * in_h && OW == 2 * in_w, "sub-pixel transposed conv needs an output of exactly twice the input size");
+  VPK_REQUIRE(input.lo_view.base == nullptr && input.lo_view.C == 0, "sub-pixel transposed conv: no split operands");
+  const int src = static_cast<int>(spec.srcs.size());
+  spec.srcs.push_back(input.view);
+  // per axis and parity r: y = 2 i - pad + kk with y = 2 q + r  =>  i = q + (r + pad - kk) / 2 for kk = r + pad (mod 2)
+  auto tap_of = [&](int r, int d) {          // kernel index that parity r reads at input offset d, or -1
+    const int kk = r + pad - 2 * d;
+    return (kk >= 0 && kk < k) ? kk : -1;
+  };
+  int dmin = 0, dmax = 0;
+  for (int r = 0; r < 2; ++r)
+    for (int kk = 0; kk < k; ++kk)
+      if (((r + pad - kk) % 2 + 2) % 2 == 0) {
+        const int d = floordiv(r + pad - kk, 2);
+        dmin = std::min(dmin, d);
+        dmax = std::max(dmax, d);
+      }
+  PhaseSpec ph;
+  ph.H = in_h;
+  ph.W = in_w;
+  for (int c0 = 0; c0 < input.view.C; c0 += 64)
+    for (int dy = dmin; dy <= dmax; ++dy)
+      for (int dx = dmin; dx <= dmax; ++dx) {
+        add_step(ph.steps, src, dy, dx, input.view.C, c0, input.wref, 0, 0, input.wc0, input.wc_count, 0);
+        HostStep& h = ph.steps.back();
+        h.per_gate = true;
+        bool any = false;
+        for (int g = 0; g < 4; ++g) {
+          const int ky = tap_of(g >> 1, dy), kx = tap_of(g & 1, dx);
+          if (ky >= 0 && kx >= 0) {
+            h.gky[g] = static_cast<signed char>(ky);
+            h.gkx[g] = static_cast<signed char>(kx);
+            any = true;
+          }
+        }
+        if (!any) ph.steps.pop_back();
+      }
+  spec.phases.push_back(ph);
   *oh = OH;
   *ow = OW;
 }
@@ -252,8 +301,10 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
               if (w.gate_block[g] < 0) continue;
               const int oc = w.gate_block[g] * C + ch;
               float* row = wf.data() + static_cast<size_t>(ch * G + g) * K_pad + h.s.wk;
+              if (h.per_gate && h.gky[g] < 0) continue;       // this parity does not read this input offset
+              const int ky = h.per_gate ? h.gky[g] : h.ky, kx = h.per_gate ? h.gkx[g] : h.kx;
               for (int j = 0; j < h.kw_valid; ++j) {
-                float v = weight_at(w, oc, h.wc0 + h.s.c0 + j, h.ky, h.kx);
+                float v = weight_at(w, oc, h.wc0 + h.s.c0 + j, ky, kx);
                 if (h.wsplit != 0) {   // split-bf16: high part, or what the high part misses
                   const float hi = __bfloat162float(__float2bfloat16_rn(v));
                   v = (h.wsplit == 1) ? hi : v - hi;
@@ -335,9 +386,18 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
     L.op_f16 = (dtype == DT_F16) ? 1 : 0;
-    VPK_REQUIRE(dtype != DT_F16 || G == 1 || ph.epi.kind == EPI_DECOUPLE, "fp16 operands are for plain convs only: " + spec.name);
+    VPK_REQUIRE(dtype != DT_F16 || G == 1 || ph.epi.kind == EPI_DECOUPLE || ph.epi.kind == EPI_SUBPIX,
+                "fp16 operands are for plain convs only: " + spec.name);
     double kreal = 0;
-    for (const HostStep& h : ph.steps) kreal += h.kw_valid;   // split-bf16 layers count their three products
+    for (const HostStep& h : ph.steps) {                      // split-bf16 layers count their three products
+      double used = 1.0;
+      if (h.per_gate) {                                       // sub-pixel form: only the parities that read this offset
+        int nv = 0;
+        for (int g = 0; g < G; ++g) nv += h.gky[g] >= 0 ? 1 : 0;
+        used = static_cast<double>(nv) / G;
+      }
+      kreal += h.kw_valid * used;
+    }
     L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;
     if (!measure_only) {
       const PackedWeights& q = (*packed)[p];
@@ -366,6 +426,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         VPK_REQUIRE(bc.use_halo, "fused projection epilogue needs the tcgen05 halo kernel for " + spec.name);
       }
       VPK_REQUIRE(L.epi.kind != EPI_DECOUPLE || bc.use_halo, "the decoupling-loss epilogue needs the tcgen05 halo kernel");
+      VPK_REQUIRE(L.epi.kind != EPI_SUBPIX || bc.use_halo, "the sub-pixel epilogue needs the tcgen05 halo kernel");
       VPK_REQUIRE(L.epi.gn_sums == nullptr || bc.use_halo,
                   "fused GroupNorm statistics need the tcgen05 halo kernel for " + spec.name);
       if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);

@@ -32,6 +32,10 @@ struct HostStep {
   int wref;      // index into ConvSpec::wrefs
   int ky, kx;    // tap of that weight tensor
   int wc0;       // input-channel index of that weight tensor that corresponds to channel 0 of the source
+  // sub-pixel transposed convs: the G = 4 "gates" are the four output parities, and each reads its OWN tap of the
+  // weight tensor at this input offset (or none: -1)
+  bool per_gate = false;
+  signed char gky[4] = {-1, -1, -1, -1}, gkx[4] = {-1, -1, -1, -1};
 };
 
 struct PhaseSpec {
@@ -71,6 +75,15 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
 void lower_conv_transpose(ConvSpec& spec, int k, int stride, int pad, int out_pad, const ConvInput& input, int in_h,
                           int in_w, int* oh, int* ow,
                           const std::function<EpiParams(int ry, int rx, int stride, int OH, int OW)>& epi_for_phase);
+
+// Stride-2 transposed conv as ONE stride-1 conv over the input grid with four gate columns per channel = the four
+// output parities ("sub-pixel" form): gate (ry, rx) of input position (q_y, q_x) is output pixel (2 q_y + ry, 2 q_x + rx).
+// Every input offset of the union neighbourhood is one K-step whose weight rows are zero for the parities that do not
+// use it, so the contraction is denser than the four per-parity launches (k4: 36 vs 16 tap-parity pairs, k3: 16 vs 9) --
+// worth it only when the launches are latency-bound (small batches): one launch and one activation tile instead of four.
+// Requires OH = 2 * in_h, OW = 2 * in_w (k4 p1, k3 p1 op1).
+void lower_conv_transpose_subpixel(ConvSpec& spec, int k, int pad, int out_pad, const ConvInput& input, int in_h, int in_w,
+                                   int* oh, int* ow);
 
 // Simple bump allocator over a caller-provided (or library-owned) device range; base == nullptr only measures.
 struct Arena {

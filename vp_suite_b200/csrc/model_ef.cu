@@ -294,7 +294,15 @@ class EfConvLstm : public Model {
             da.proj_b = dev_f32("forecaster.stage1.final.bias", fb.data, stream);
           }
         }
-        add_conv(prog, deconv_spec(da, act, &oh, &ow), measure, stream);
+        // small batches: the four per-parity launches of a stride-2 deconv are pure launch latency -- one sub-pixel
+        // launch instead (denser contraction, so only while there are fewer tiles than ~2 per SM)
+        const long long tiles = static_cast<long long>(B) * ((dh[n] + 15) / 16) * ((dw[n] + 7) / 8);
+        const char* sp_env = getenv("VPK_SUBPIX");
+        const char* halo_env = getenv("VPK_TC_HALO");     // tests force the per-tap kernels with VPK_TC_HALO=0
+        const bool subpix = dtype == DT_BF16 && backend == 0 && deconv_subpix_ok(da) && (halo_env == nullptr || atoi(halo_env) != 0) &&
+                            (sp_env ? atoi(sp_env) != 0 : tiles <= 2ll * num_sms);
+        if (subpix) add_conv(prog, deconv_subpix_spec(da, act, &oh, &ow), measure, stream);
+        else add_conv(prog, deconv_spec(da, act, &oh, &ow), measure, stream);
         VPK_REQUIRE(oh == dh[n + 1] && ow == dw[n + 1], "forecaster stage size mismatch");
         in = ybuf[n];
       }
