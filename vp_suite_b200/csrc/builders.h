@@ -159,7 +159,7 @@ struct DeconvArgs {
   const float* proj_b = nullptr;   // device fp32 [proj_n]
   int proj_n = 0;
 };
-// The same stride-2 transposed conv in sub-pixel form (lowering.h): one launch, dense NHWC output (activation type or fp32).
+// The same stride-2 transposed conv in sub-pixel form (lowering.h): one launch, dense bf16 NHWC output only.
 inline ConvSpec deconv_subpix_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
   s.name = a.name + "subpix.";
@@ -186,7 +186,7 @@ inline ConvSpec deconv_subpix_spec(const DeconvArgs& a, const ActInfo& act, int*
   e.kind = EPI_SUBPIX;
   e.act = a.act;
   e.out = a.out;
-  e.out_f32 = a.out_f32 ? 1 : 0;
+  e.out_f32 = 0;
   const long long C = a.Cout, OW = *ow, OH = *oh;
   e.oB = OH * OW * C;
   e.oY = 2 * OW * C;
@@ -196,7 +196,7 @@ inline ConvSpec deconv_subpix_spec(const DeconvArgs& a, const ActInfo& act, int*
   return s;
 }
 inline bool deconv_subpix_ok(const DeconvArgs& a) {
-  if (a.stride != 2 || a.split || a.nchw || a.proj_n > 0 || a.Cout % 8 != 0 || a.Cin % 8 != 0) return false;
+  if (a.stride != 2 || a.split || a.nchw || a.out_f32 || a.proj_n > 0 || a.Cout % 8 != 0 || a.Cin % 8 != 0) return false;
   return (a.H - 1) * 2 - 2 * a.pad + a.k + a.out_pad == 2 * a.H;
 }
 inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, int* ow) {

@@ -612,23 +612,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         bool stats = false;
         if constexpr (KIND == EPI_BIAS_ACT) stats = P.L.epi.gn_sums != nullptr && P.L.epi.gn_group_size > 0;
         if constexpr (KIND == EPI_SUBPIX) {
-          // sub-pixel transposed conv: the four gates of a channel are the four output pixels of this input position;
-          // optional GroupNorm statistics of the stored values (all four pixels feed the channel's group), as in BIAS_ACT
+          // sub-pixel transposed conv: the four gates of a channel are the four output pixels of this input position
           stats = false;
           const EpiParams& E = P.L.epi;
-          const bool gstats = E.gn_sums != nullptr;
-          const int gsz = E.gn_group_size;
-          float gs16[16];
-#pragma unroll
-          for (int i = 0; i < 16; ++i) gs16[i] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const int ch = half * 8 + 16 * k;
-            if (ch < Cn) {
-              uint32_t r[8 * G];
-              tmem_chunk(ch, r);
-              ptx::tmem_ld_wait();
-              const bool live = valid && ch_base + ch < C;
+          for (int ch = half * 8; ch < Cn; ch += 16) {
+            uint32_t r[8 * G];
+            tmem_chunk(ch, r);
+            ptx::tmem_ld_wait();
+            if (valid && ch_base + ch < C) {
               const float4* bp = reinterpret_cast<const float4*>(bias + (ch_base + ch) * 4);
 #pragma unroll
               for (int g = 0; g < 4; ++g) {
@@ -640,29 +631,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                   float t = __uint_as_float(r[j * 4 + g]) + bj;
                   if (E.act == ACT_LEAKY) t = t > 0.f ? t : 0.2f * t;
                   else if (E.act == ACT_RELU) t = fmaxf(t, 0.f);
-                  v[j] = live ? t : 0.f;
+                  v[j] = t;
                 }
-                if (live) {
-                  const long long off = et.out_off + (g >> 1) * E.ps_row + (g & 1) * C + ch_base + ch;
-                  if (E.out_f32) st_f32x8(static_cast<float*>(E.out) + off, v);
-                  else st_bf16x8(static_cast<bf16*>(E.out) + off, v);
-                }
-                if (gstats && k < 4) {
-                  if (gsz == 2) gn_accum<2>(gs16, k, v);
-                  else if (gsz == 4) gn_accum<4>(gs16, k, v);
-                  else gn_accum<8>(gs16, k, v);
-                }
+                st_bf16x8(static_cast<bf16*>(E.out) + et.out_off + (g >> 1) * E.ps_row + (g & 1) * C + ch_base + ch, v);
               }
-            }
-          }
-          if (gstats) {
-            const float tot = gn_warp_reduce16(gs16, lane);
-            const int vi = gn_lane_value(lane), pairi = vi >> 1, gpc = 8 / gsz;
-            const int kk = pairi / gpc, jj = pairi - kk * gpc;
-            const int chg = ch_base + half * 8 + 16 * kk;
-            if ((lane & 1) == 0 && b < P.L.B && half * 8 + 16 * kk < Cn && chg < C) {
-              const int slot = E.gn_slot0 + (mt % (P.tiles_x * P.tiles_y)) * 4 + quad;
-              E.gn_sums[((static_cast<long long>(b) * E.gn_nslots + slot) * (C / gsz) + chg / gsz + jj) * 2 + (vi & 1)] = tot;
             }
           }
         } else
@@ -923,9 +895,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
                 "halo plan: fused LayerNorm statistics need the lean BIAS_ACT epilogue");
   } else if (L.epi.gn_sums != nullptr) {
     const int gs = L.epi.gn_group_size;
-    VPK_REQUIRE(P.fast_epi && (L.epi.kind == EPI_BIAS_ACT || L.epi.kind == EPI_SUBPIX) && L.epi.proj_n == 0 &&
-                    L.epi.res == nullptr && (gs == 2 || gs == 4 || gs == 8) && L.Cn <= 64 && L.Cn / gs <= 16 &&
-                    L.epi.C % gs == 0,
+    VPK_REQUIRE(P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0 && L.epi.res == nullptr &&
+                    (gs == 2 || gs == 4 || gs == 8) && L.Cn <= 64 && L.Cn / gs <= 16 && L.epi.C % gs == 0,
                 "halo plan: fused GroupNorm statistics need the lean BIAS_ACT epilogue, <= 64 channels per tile and groups of 2/4/8");
   }
   P.tmem_cols = std::max(32, pow2_at_least(2 * P.tileN));

@@ -386,8 +386,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
     L.op_f16 = (dtype == DT_F16) ? 1 : 0;
-    VPK_REQUIRE(dtype != DT_F16 || G == 1 || ph.epi.kind == EPI_DECOUPLE || ph.epi.kind == EPI_SUBPIX,
-                "fp16 operands are for plain convs only: " + spec.name);
+    VPK_REQUIRE(dtype != DT_F16 || G == 1 || ph.epi.kind == EPI_DECOUPLE, "fp16 operands are for plain convs only: " + spec.name);
     double kreal = 0;
     for (const HostStep& h : ph.steps) {                      // split-bf16 layers count their three products
       double used = 1.0;
