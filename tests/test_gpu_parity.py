@@ -138,7 +138,7 @@ def test_ef_microbatching_and_graph_are_invisible(manifest):
 @pytest.mark.parametrize("name", ["ef_3x32", "predrnn_3x32", "phy_1x64", "branch_1x64"])
 def test_forward_host_matches_device_path(manifest, name, monkeypatch):
     """Host-buffer entry (pinned H2D -> rollout -> per-frame D2H streaming, double-buffered microbatches) against the
-    device-tensor entry, with a ragged last microbatch; and the same without frame streaming."""
+    device-tensor entry, with a ragged last microbatch; and the same without per-frame output / input streaming."""
     meta = dict(manifest["models"][name])
     meta.update(batch=3)
     x = _input(meta)
@@ -148,7 +148,9 @@ def test_forward_host_matches_device_path(manifest, name, monkeypatch):
         a = m(x.cuda(), pred_frames=p)[0].cpu()
         b = m.forward_host(x.pin_memory(), pred_frames=p)[0].clone()     # the result buffer is reused across calls
         monkeypatch.setenv("VPK_NO_FRAME_STREAM", "1")
-        c = m.forward_host(x.pin_memory(), pred_frames=p)[0].clone()
+        monkeypatch.setenv("VPK_NO_INPUT_STREAM", "1")      # read when the program is built: use a fresh model
+        m2, _ = _build(meta["key"], meta, precision="bf16", max_microbatch=2)
+        c = m2.forward_host(x.pin_memory(), pred_frames=p)[0].clone()
     assert torch.equal(a, b) and torch.equal(a, c)
 
 

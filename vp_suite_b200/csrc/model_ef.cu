@@ -344,7 +344,7 @@ class EfConvLstm : public Model {
     }
   }
 
-  bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_EF_NO_INPUT_STREAM") == nullptr; }
+  bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_NO_INPUT_STREAM") == nullptr; }
 
  private:
   int eh[3], ew[3], dh[4], dw[4], dec_in_c[3];

@@ -65,6 +65,7 @@ class PredRnnV2 : public Model {
   // eval mode reads the context frames only (the mask is all zero, predrnn_v2.py:300-309): the target frames that
   // NEEDS_COMPLETE_INPUT puts behind them never have to reach the device
   int used_in_frames(int t_in, int pred) const override { return t_in - pred; }
+  bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_NO_INPUT_STREAM") == nullptr; }
 
   void begin_call(int, float*, cudaStream_t stream) override {
     if (!d_loss) VPK_CUDA(cudaMalloc(&d_loss, sizeof(double)));
@@ -137,13 +138,15 @@ class PredRnnV2 : public Model {
 
     if (!measure) {
       const int ns = num_sms, dt = adt, pp = p;
-      Op pre;
-      pre.name = "patchify";
-      // x holds t_in frames per sequence; frames >= ctx are ignored
-      pre.fn = [=](cudaStream_t s, const RunCtx& rc) {
-        launch_patchify_strided(rc.x, static_cast<long long>(t_in) * c * h * w, xp, dt, B, ctx, c, h, w, pp, ns, s);
-      };
-      prog.pre.push_back(std::move(pre));
+      if (!streams_input()) {     // CUDA-graph replay: the conversion reads the call's input pointer, so it stays outside
+        Op pre;
+        pre.name = "patchify";
+        // x holds t_in frames per sequence; frames >= ctx are ignored
+        pre.fn = [=](cudaStream_t s, const RunCtx& rc) {
+          launch_patchify_strided(rc.x, static_cast<long long>(t_in) * c * h * w, xp, dt, B, ctx, c, h, w, pp, ns, s);
+        };
+        prog.pre.push_back(std::move(pre));
+      }
       for (int i = 0; i < L; ++i) {
         add_memset(prog, hb[2 * i], px * C * esz, "zero_h");
         add_memset(prog, cb[i], px * C * sizeof(float), "zero_c");
@@ -156,6 +159,20 @@ class PredRnnV2 : public Model {
     std::vector<int> par(L, 0);
     for (int t = 0; t < t_in - 1; ++t) {
       const void* net = (t < ctx) ? static_cast<const void*>(xp + static_cast<size_t>(t) * px * cp * esz) : xgen_act;
+      if (!measure && t < ctx && streams_input()) {
+        // context frame t is patchified right before the step that reads it; under the host entry this op waits for
+        // the frame's own host-to-device copy only
+        const int ns = num_sms, dt = adt, pp = p;
+        char* dst = xp + static_cast<size_t>(t) * px * cp * esz;
+        const long long bstride = static_cast<long long>(t_in) * c * h * w, foff = static_cast<long long>(t) * c * h * w;
+        Op cv;
+        cv.name = "patchify";
+        cv.needs_input = t;
+        cv.fn = [=](cudaStream_t s, const RunCtx& rc) {
+          launch_patchify_strided(rc.x + foff, bstride, dst, dt, B, 1, c, h, w, pp, ns, s);
+        };
+        prog.body.push_back(std::move(cv));
+      }
       for (int i = 0; i < L; ++i) {
         const std::string pre = "cell_list." + std::to_string(i) + ".";
         const void* inp = (i == 0) ? net : hb[2 * (i - 1) + par[i - 1]];
