@@ -393,7 +393,9 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     // compute; d_out[buf] was last read by the D2H of iteration it-2
     if (!frame_in) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_in[buf], 0));
     if (it >= 2) VPK_CUDA(cudaStreamWaitEvent(hpipe.s_comp, hpipe.ev_out[buf], 0));
+    host_build = true;
     Program* prog = get_program(nb, t_in, pred, hpipe.ws, hpipe.ws_bytes, hpipe.s_comp);
+    host_build = false;
     // Frame streaming: as soon as the op that completes predicted frame p is enqueued, the frame is copied into this
     // microbatch's output buffer and from there to the host on the copy stream, so that only the LAST frame's transfer
     // (1 / pred of the output) is left when the rollout ends, not the whole microbatch's.

@@ -94,6 +94,9 @@ class Model {
   // true: the program converts input frame t in its own op (marked Op::needs_input = t) instead of converting all frames
   // up front, so the host entry may deliver the frames one by one
   virtual bool streams_input() const { return false; }
+  // true while forward_host() builds a program: a rollout may lay its ops out differently for the host pipeline
+  // (PhyDNet encodes the context frames in growing groups so that compute starts after the first frame's copy)
+  bool host_build = false;
   virtual void begin_call(int batch, float* aux, cudaStream_t stream) {}
   virtual void end_call(int batch, float* aux, cudaStream_t stream) {}
 

@@ -96,6 +96,7 @@ class PhyDNetModel : public Model {
 
  protected:
   int default_microbatch() const override { return 256; }
+  bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_NO_INPUT_STREAM") == nullptr; }
 
   std::vector<float> vec(const std::string& key) const {
     const HostParam& p = params.at(key);
@@ -291,17 +292,30 @@ class PhyDNetModel : public Model {
       prog.body.push_back(std::move(op));
     };
 
-    if (!measure) {
-      Op pre;
-      pre.name = "frames_to_nhwc";
-      pre.fn = [=](cudaStream_t s, const RunCtx& rc) {
+    // Input frames [f0, f0 + n) -> channels-last.  Device entry: one pre op over all frames.  Host entry
+    // (streams_input()): one body op per group of frames, marked with the last frame it reads, so that the op waits for
+    // that frame's host-to-device copy only.
+    const bool stream_in = host_build && streams_input();
+    auto convert_frames = [&](std::vector<Op>& dst, int f0, int n, bool mark) {
+      if (measure) return;
+      const long long chw = static_cast<long long>(c) * h * w;
+      const size_t off = static_cast<size_t>(f0) * px1 * cs * (pad8 ? 2 : 4);
+      void* oa = static_cast<char*>(frames_in.a) + off;
+      void* olo = frames_in.lo != nullptr ? static_cast<char*>(frames_in.lo) + off : nullptr;
+      const int sdt = sa.dtype;
+      Op cv;
+      cv.name = "frames_to_nhwc";
+      if (mark) cv.needs_input = f0 + n - 1;
+      cv.fn = [=](cudaStream_t s, const RunCtx& rc) {
         if (pad8)
-          launch_frames_to_nhwc8(rc.x, static_cast<long long>(t_in) * c * h * w, frames_in.a, frames_in.lo, sa.dtype, B,
-                                 t_in, c, h, w, ns, s);
+          launch_frames_to_nhwc8(rc.x + f0 * chw, t_in * chw, oa, olo, sdt, B, n, c, h, w, ns, s);
         else
-          launch_frames_to_nhwc(rc.x, frames_in.a, DT_F32, B, t_in, c, h, w, ns, s);
+          launch_frames_to_nhwc_strided(rc.x + f0 * chw, t_in * chw, oa, DT_F32, B, n, c, h, w, ns, s);
       };
-      prog.pre.push_back(std::move(pre));
+      dst.push_back(std::move(cv));
+    };
+    if (!measure) {
+      if (!stream_in) convert_frames(prog.pre, 0, t_in, false);
       if (!branch_only) {
         for (int j = 0; j < n_phy; ++j) {
           add_memset(prog, hp_master[j], px4 * 64 * 4, "zero_hp");
@@ -342,10 +356,15 @@ class PhyDNetModel : public Model {
       dcgan("encoder_Er.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{er_out, nullptr}, nullptr);
 
     };
-    if (batch_ctx) {
-      Bcur = B * t_in;
-      encoders(frames_in, ep, er);
-      Bcur = B;
+    // group_at[st] = number of context frames converted (and, with batch_ctx, encoded) right before step st.  Host
+    // entry: groups of 1, 2, 4, ... frames -- the copy engine delivers frames several times faster than the steps consume
+    // them, so only the first frame's copy is exposed and later groups keep most of the time-batching.
+    std::vector<int> group_at(t_in, 0);
+    if (stream_in) {
+      for (int s0 = 0, g = 1; s0 < t_in; s0 += g, g *= 2) group_at[s0] = batch_ctx ? std::min(g, t_in - s0) : 1;
+      if (!batch_ctx) std::fill(group_at.begin(), group_at.end(), 1);
+    } else if (batch_ctx) {
+      group_at[0] = t_in;
     }
 
     auto mark_frame = [&](int di) {   // the op just added completes predicted frame di (host entry: starts its D2H)
@@ -370,9 +389,16 @@ class PhyDNetModel : public Model {
       // ---- encoders ----
       const void* ep_in = ep;
       const void* er_in = er;
-      if (batch_ctx && st < t_in) {       // context frame: encoded by the time-batched pass before the loop
-        ep_in = static_cast<const char*>(ep) + static_cast<size_t>(st) * px4 * 64 * esz_c;
-        er_in = static_cast<const char*>(er) + static_cast<size_t>(st) * px4 * 64 * esz_c;
+      if (stream_in && st < t_in && group_at[st] > 0) convert_frames(prog.body, st, group_at[st], true);
+      if (batch_ctx && st < t_in) {       // context frame: encoded by a time-batched pass over its group
+        const size_t slot = static_cast<size_t>(st) * px4 * 64 * esz_c;
+        if (group_at[st] > 0) {
+          Bcur = B * group_at[st];
+          encoders(frame, static_cast<char*>(ep) + slot, static_cast<char*>(er) + slot);
+          Bcur = B;
+        }
+        ep_in = static_cast<const char*>(ep) + slot;
+        er_in = static_cast<const char*>(er) + slot;
       } else {
         encoders(frame, ep, er);
       }
