@@ -154,6 +154,23 @@ def test_forward_host_matches_device_path(manifest, name, monkeypatch):
     assert torch.equal(a, b) and torch.equal(a, c)
 
 
+@pytest.mark.parametrize("name", ["ef_3x32", "predrnn_3x32", "phy_1x64"])
+@pytest.mark.parametrize("variant", ["fp32", "graph"])
+def test_forward_host_other_programs(manifest, name, variant):
+    """The host entry lays its program out differently per mode: fp32 (PhyDNet: per-frame conversion, no time-batched
+    context encoders) and CUDA-graph replay (conversion stays a pre op, whole-microbatch copies)."""
+    meta = dict(manifest["models"][name])
+    meta.update(batch=3)
+    x = _input(meta)
+    kw = dict(precision="fp32") if variant == "fp32" else dict(precision="bf16", use_cuda_graph=True)
+    m, _ = _build(meta["key"], meta, max_microbatch=2, **kw)
+    p = meta["pred"]
+    with torch.no_grad():
+        a = m(x.cuda(), pred_frames=p)[0].cpu()
+        b = m.forward_host(x.pin_memory(), pred_frames=p)[0].clone()
+    assert torch.equal(a, b)
+
+
 def test_ef_forward_host_matches_device_path(manifest):
     meta = dict(manifest["models"]["ef_3x32"])
     meta.update(batch=3)
