@@ -5,7 +5,8 @@ The CPU oracle cannot run a 256-sequence batch in test time, so each case is che
      bf16 mode <= 5e-3 on the first predicted frame, <= 2e-2 at the end of the rollout);
   2. the full batch, built by repeating those three sequences, against the three-sequence result -- a size-independent
      property of the path (sequences are independent: output i depends on input i only), which exercises every tile /
-     microbatch / CTA-pair position of the full-size launch.
+     microbatch / CTA-pair position of the full-size launch;
+  3. the same full batch through the host-buffer entry (vpk_model_forward_host), bit for bit.
 """
 import numpy as np
 import pytest
@@ -26,7 +27,16 @@ CASES = {
     "cfg3": ("predrnn-pp", (1, 64, 64), 10, 10, 256, 1.5, {}, 0.0),
     "cfg2": ("convlstm-branch", (1, 64, 64), 10, 10, 256, 1.5, {}, 0.0),
     "cfg4": ("phy", (3, 64, 64), 2, 10, 256, 1.5, {}, 0.0),
+    # cfg 3's shape with LayerNorm in the ST-LSTM cells (statistics in per-warp slots, fixed order)
+    "cfg3ln": ("predrnn-pp", (1, 64, 64), 10, 10, 256, 1.5, {"layer_norm": True}, 0.0),
 }
+
+
+# End-of-rollout bound.  north_star states 2e-2 after 10 predicted frames for the five BASELINE configs.  The LayerNorm
+# variant is outside those five: LayerNorm renormalises every gate pre-activation to unit variance, the
+# 16-bit operand rounding (fp16 here) is amplified more per step, and the full-length 10 + 10 rollout with random weights
+# measures 2.5e-2 on the tenth frame (4.4e-3 on the first; fp32-operand mode: 6e-6).  Written as measured, not as 2e-2.
+END_TOL = {"cfg3ln": 3e-2}
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -36,7 +46,8 @@ def test_full_shape_parity_and_batch_independence(name):
     import vp_suite_b200 as V
     key, img, ctx, pred, full_b, gain, kw, rep_tol = CASES[name]
     t_in = ctx + (pred if key == "predrnn-pp" else 0)
-    sd = synth_state_dict(SHAPES[key](img), seed=11, gain=gain)
+    shape_kw = {k: v for k, v in kw.items() if k == "layer_norm"}
+    sd = synth_state_dict(SHAPES[key](img, shape_kw) if shape_kw else SHAPES[key](img), seed=11, gain=gain)
     x3 = synth_frames(3, t_in, *img, seed=321)
     m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
                              precision="bf16", **kw).eval()
@@ -46,7 +57,7 @@ def test_full_shape_parity_and_batch_independence(name):
         small, small_aux = m(x3.cuda(), pred_frames=pred)
     d = (small.cpu() - ref).abs()
     errs = [float(d[:, t].max()) for t in range(pred)]
-    assert errs[0] <= 5e-3 and max(errs) <= 2e-2, f"{name}: per-frame max abs error vs the oracle {errs}"
+    assert errs[0] <= 5e-3 and max(errs) <= END_TOL.get(name, 2e-2), f"{name}: per-frame max abs error vs the oracle {errs}"
 
     idx = torch.arange(full_b) % 3
     with torch.no_grad():
@@ -54,6 +65,10 @@ def test_full_shape_parity_and_batch_independence(name):
     assert full.shape == (full_b, pred, *img)
     diff = float((full - small[idx.cuda()]).abs().max())
     assert diff <= rep_tol, f"{name}: sequence results depend on the batch they ran in (max abs diff {diff})"
+    # the host-buffer entry at the full batch (per-frame copies in and out, double-buffered microbatches): same bits
+    with torch.no_grad():
+        host, _ = m.forward_host(x3[idx].pin_memory(), pred_frames=pred)
+    assert torch.equal(host, full.cpu()), f"{name}: host entry differs from the device entry"
     if ref_aux is not None:       # PredRNN decoupling loss: a batch mean, so repetition leaves it (nearly) unchanged
         (k, v), = full_aux.items()
         (_, rv), = ref_aux.items()
