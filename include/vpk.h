@@ -177,6 +177,19 @@ void vpk_cell_destroy(vpk_cell* cell);
 int vpk_metric_partial_sums(const float* pred, const float* target, int32_t batch, int32_t frames, int64_t chw,
                             double* scratch, double* out, void* stream);
 
+/* SSIM partial sums (vp_suite/measure/image_wise.py:100-121: `1 - piqa.ssim.SSIM()(pred, target)` after
+ * base_measure.py:59-75's reshape_clamp).  piqa 1.1.7 is a third-party dependency absent from the reference checkout and
+ * from this image: its published algorithm is restated (11-tap Gaussian window, sigma 1.5, valid region, K1 = 0.01,
+ * K2 = 0.03, value range 1, mean over channels and positions per image) -- VALUE PARITY UNPINNED; checked against the
+ * reference's own SSIM tests' axioms (tests/test_measure.py:26-50) and the oracle's torch restatement.
+ * pred, target: device fp32 [batch, frames, c, h, w] in the model's [-1, 1]-mapped convention of reshape_clamp
+ * ((v + 1) / 2, clamped to [0, 1]).  out[frames] (device fp64) = sum over the batch of SSIM(pred[b, t], target[b, t]);
+ * the reference's measure is 1 - mean of these.  scratch: device fp64 [vpk_metric_ssim_scratch_elems(...)]
+ * (-1: image smaller than the 11 x 11 window or too wide).  Deterministic.  Enqueued on `stream`. */
+int64_t vpk_metric_ssim_scratch_elems(int32_t batch, int32_t frames, int32_t c, int32_t h, int32_t w);
+int vpk_metric_ssim_sums(const float* pred, const float* target, int32_t batch, int32_t frames, int32_t c, int32_t h,
+                         int32_t w, double* scratch, double* out, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------------------------------ */
 const char* vpk_last_error(void);
 const char* vpk_version(void);

@@ -7,6 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
+from oracle import measure as OM
 from vp_suite_b200 import evaluation as E
 
 
@@ -24,17 +25,21 @@ def _worker(rank, world, port, pred, target, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     lo, hi = E.shard_bounds(pred.shape[0], rank, world)
     vec = E.metric_partial_sums(pred[lo:hi], target[lo:hi])
-    vec = E.all_reduce_sums(vec)
+    ssim = E.ssim_partial_sums(pred[lo:hi], target[lo:hi])   # travels in the same all-reduce as the MSE / PSNR sums
+    vec = E.all_reduce_sums(torch.cat([vec, ssim]))
     if rank == 0:
-        out.put(E.finalize_metrics(vec))
+        n_frames = pred.shape[1]
+        res = E.finalize_metrics(vec[:-n_frames])
+        res["ssim"] = E.finalize_ssim(vec[-n_frames:], res["sequences"])
+        out.put(res)
     dist.barrier()
     dist.destroy_process_group()
 
 
 def test_sharded_metric_reduction_matches_single_process():
     g = torch.Generator().manual_seed(0)
-    pred = torch.rand((5, 4, 3, 8, 8), generator=g)          # 5 sequences over 2 ranks: ragged shards (3 + 2)
-    target = torch.rand((5, 4, 3, 8, 8), generator=g)
+    pred = torch.rand((5, 4, 3, 12, 14), generator=g)        # 5 sequences over 2 ranks: ragged shards (3 + 2)
+    target = torch.rand((5, 4, 3, 12, 14), generator=g)
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
@@ -52,6 +57,8 @@ def test_sharded_metric_reduction_matches_single_process():
         mse, psnr = _reference_metrics(pred[:, :k], target[:, :k])
         assert abs(got["mse"][k - 1] - mse) <= 1e-6 * max(1.0, abs(mse))      # fp32 elementwise, fp64 accumulation
         assert abs(got["psnr"][k - 1] - psnr) <= 1e-6 * max(1.0, abs(psnr))
+        ssim = float(OM.ssim_images(pred[:, :k].numpy(), target[:, :k].numpy()).mean())   # to_display(1 - mean)
+        assert abs(got["ssim"][k - 1] - ssim) <= 1e-5
 
 
 def test_shard_bounds_cover_batch_without_overlap():

@@ -58,6 +58,8 @@ SYMBOLS = {
     "vpk_model_profile": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "vpk_model_destroy": (None, [_vp]),
     "vpk_metric_partial_sums": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int64, _vp, _vp, _vp]),
+    "vpk_metric_ssim_scratch_elems": (C.c_int64, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "vpk_metric_ssim_sums": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "vpk_convlstm_cell_create": (C.c_int, [C.c_int32] * 8 + [_vp, _vp, C.POINTER(_vp)]),
     "vpk_convlstm_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 9),
     "vpk_stlstm_cell_create": (C.c_int, [C.c_int32] * 7 + [_vp] * 5 + [C.POINTER(_vp)]),

@@ -52,6 +52,23 @@ int vpk_metric_partial_sums(const float* pred, const float* target, int32_t batc
   });
 }
 
+int64_t vpk_metric_ssim_scratch_elems(int32_t batch, int32_t frames, int32_t c, int32_t h, int32_t w) {
+  return vpk::metric_ssim_scratch_elems(batch, frames, c, h, w);
+}
+
+int vpk_metric_ssim_sums(const float* pred, const float* target, int32_t batch, int32_t frames, int32_t c, int32_t h,
+                         int32_t w, double* scratch, double* out, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(pred && target && scratch && out, "vpk_metric_ssim_sums: null pointer");
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+      cudaGetLastError();
+      VPK_THROW(VPK_ERR_CUDA, "no CUDA device: libvpk has no CPU fallback");
+    }
+    vpk::launch_metric_ssim_sums(pred, target, batch, frames, c, h, w, scratch, out, static_cast<cudaStream_t>(stream));
+  });
+}
+
 const char* vpk_last_error(void) { return g_last_error.c_str(); }
 const char* vpk_version(void) { return "libvpk 0.1 (sm_100a)"; }
 

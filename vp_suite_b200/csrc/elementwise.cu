@@ -215,6 +215,150 @@ __global__ void __launch_bounds__(256) metric_frame_sums_kernel(const double* __
   }
 }
 
+// SSIM (vp_suite/measure/image_wise.py:100-121 = piqa 1.1.7 SSIM with its defaults, restated: 11-tap Gaussian window,
+// sigma 1.5, valid region only, K1 = 0.01, K2 = 0.03, value range 1; inputs mapped (v + 1) / 2 and clamped to [0, 1]
+// as base_measure.py:59-75 does).  Stage 1: one block per (image plane, strip of R output rows).  The strip (+10 halo
+// rows) of both images goes to shared memory once.  Pass 1 filters vertically: a thread owns one column and four
+// output rows, so 14 loaded (x, y) pairs feed 4 x 5 filtered moments (x, y, xx, yy, xy); the moments are stored
+// transposed ([moment][column][row], odd row pitch).  Pass 2 filters horizontally: a thread owns one row and four output
+// columns (14 x 5 loads for four SSIM values; consecutive lanes = consecutive rows of the transposed store).  fp64
+// block sum in a fixed order.  ~25 shared-memory loads and ~110 FMAs per output position: issue-bound, not HBM-bound.
+struct SsimWin {
+  float w[11];
+};
+__global__ void __launch_bounds__(256) metric_ssim_kernel(const float* __restrict__ pred, const float* __restrict__ tgt,
+                                                          int H, int W, int R, SsimWin win, double* __restrict__ part) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  extern __shared__ float ssim_sm[];
+  __shared__ double s_w[8];
+  const int Ho = H - 10, Wo = W - 10, RS = R + 1;
+  const int r0 = blockIdx.y * R;
+  const int rows_out = min(R, Ho - r0), rows_in = rows_out + 10;
+  float* sx = ssim_sm;
+  float* sy = sx + (R + 10) * W;
+  float* vq = sy + (R + 10) * W;            // [5][W][RS]
+  const int plane = W * RS;
+  const long long base = (static_cast<long long>(blockIdx.x) * H + r0) * W;
+  for (int i = threadIdx.x; i < rows_in * W; i += 256) {
+    sx[i] = fminf(fmaxf((pred[base + i] + 1.f) * 0.5f, 0.f), 1.f);
+    sy[i] = fminf(fmaxf((tgt[base + i] + 1.f) * 0.5f, 0.f), 1.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < (R / 4) * W; i += 256) {
+    const int rb = i / W, c = i - rb * W, rr = rb * 4;
+    if (rr >= rows_out) continue;
+    float a[4] = {0.f, 0.f, 0.f, 0.f}, b[4] = {0.f, 0.f, 0.f, 0.f}, aa[4] = {0.f, 0.f, 0.f, 0.f},
+          bb[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int row = rr + k;
+      float xv = 0.f, yv = 0.f;
+      if (row < rows_in) {
+        xv = sx[row * W + c];
+        yv = sy[row * W + c];
+      }
+      const float xx = xv * xv, yy = yv * yv, xy = xv * yv;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k - j;
+        if (kk >= 0 && kk <= 10) {
+          const float wk = win.w[kk];
+          a[j] += wk * xv;
+          b[j] += wk * yv;
+          aa[j] += wk * xx;
+          bb[j] += wk * yy;
+          ab[j] += wk * xy;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (rr + j < rows_out) {
+        const int o = c * RS + rr + j;
+        vq[o] = a[j];
+        vq[plane + o] = b[j];
+        vq[2 * plane + o] = aa[j];
+        vq[3 * plane + o] = bb[j];
+        vq[4 * plane + o] = ab[j];
+      }
+    }
+  }
+  __syncthreads();
+  const float c1 = 1e-4f, c2 = 9e-4f;       // (K1 * range)^2, (K2 * range)^2
+  const int ncb = (Wo + 3) / 4;
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < R * ncb; i += 256) {
+    const int r = i & (R - 1), c0 = (i / R) * 4;
+    if (r >= rows_out) continue;
+    float m[5][4];
+#pragma unroll
+    for (int q = 0; q < 5; ++q)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) m[q][j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      const int col = c0 + k;
+      float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+      if (col < W) {
+        const int o = col * RS + r;
+#pragma unroll
+        for (int q = 0; q < 5; ++q) v[q] = vq[q * plane + o];
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int kk = k - j;
+        if (kk >= 0 && kk <= 10) {
+          const float wk = win.w[kk];
+#pragma unroll
+          for (int q = 0; q < 5; ++q) m[q][j] += wk * v[q];
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (c0 + j < Wo) {
+        const float mx = m[0][j], my = m[1][j];
+        const float mxx = mx * mx, myy = my * my, mxy = mx * my;
+        const float cs = (2.f * (m[4][j] - mxy) + c2) / ((m[2][j] - mxx) + (m[3][j] - myy) + c2);
+        acc += static_cast<double>((2.f * mxy + c1) / (mxx + myy + c1) * cs);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += s_w[w];
+    part[static_cast<long long>(blockIdx.x) * gridDim.y + blockIdx.y] = t;
+  }
+}
+// stage 2: one block per frame; out[t] = sum over the batch of the image's SSIM (mean of the map over channels and the
+// valid region); fixed order: per sample the C * S strip sums in index order, thread-strided over the batch, smem tree
+__global__ void __launch_bounds__(256) metric_ssim_sums_kernel(const double* __restrict__ part, int B, int P, int CS,
+                                                               double inv_count, double* __restrict__ out) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ double s_a[256];
+  const int t = blockIdx.x;
+  double a = 0.0;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const double* q = part + (static_cast<long long>(i) * P + t) * CS;
+    double v = 0.0;
+    for (int j = 0; j < CS; ++j) v += q[j];
+    a += v * inv_count;
+  }
+  s_a[threadIdx.x] = a;
+  __syncthreads();
+  for (int o = 128; o >= 1; o >>= 1) {
+    if (threadIdx.x < o) s_a[threadIdx.x] += s_a[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[t] = s_a[0];
+}
+
 // fp32 -> fp16, n % 4 == 0
 __global__ void cast_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, long long n4) {
   ptx::pdl_launch_dependents();
@@ -784,6 +928,46 @@ void launch_metric_partial_sums(const float* pred, const float* target, int B, i
   VPK_REQUIRE(B > 0 && P > 0 && chw > 0, "metric_partial_sums: empty input");
   launch_pdl(metric_sse_kernel, dim3(static_cast<unsigned>(B) * P), dim3(256), 0, stream, pred, target, chw, scratch);
   launch_pdl(metric_frame_sums_kernel, dim3(P), dim3(256), 0, stream, static_cast<const double*>(scratch), B, P, chw, out);
+}
+
+namespace {
+size_t ssim_smem_bytes(int R, int W) {     // both strips with halo rows + five transposed moment planes
+  return (static_cast<size_t>(R + 10) * 2 * W + static_cast<size_t>(5) * W * (R + 1)) * sizeof(float);
+}
+}  // namespace
+
+int metric_ssim_strip_rows(int H, int W) {
+  if (H < 11 || W < 11) return 0;
+  int R = 16;
+  while (R > 4 && ssim_smem_bytes(R, W) > 200 * 1024) R /= 2;      // a power of two >= 4 (row blocks of 4)
+  return ssim_smem_bytes(R, W) <= 200 * 1024 ? R : 0;
+}
+
+long long metric_ssim_scratch_elems(int B, int P, int C, int H, int W) {
+  const int R = metric_ssim_strip_rows(H, W);
+  if (R == 0 || B <= 0 || P <= 0 || C <= 0) return -1;
+  return static_cast<long long>(B) * P * C * ((H - 10 + R - 1) / R);
+}
+
+void launch_metric_ssim_sums(const float* pred, const float* target, int B, int P, int C, int H, int W, double* scratch,
+                             double* out, cudaStream_t stream) {
+  const int R = metric_ssim_strip_rows(H, W);
+  VPK_REQUIRE(B > 0 && P > 0 && C > 0 && R > 0, "metric_ssim_sums: images must be at least 11 x 11 (and at most ~4000 wide)");
+  SsimWin win;                              // piqa's gaussian_kernel(11, 1.5), fp32 like torch
+  float sum = 0.f;
+  for (int k = 0; k < 11; ++k) {
+    const float d = static_cast<float>(k) - 5.f;
+    win.w[k] = expf(-(d * d) / (2.f * 1.5f * 1.5f));
+    sum += win.w[k];
+  }
+  for (int k = 0; k < 11; ++k) win.w[k] /= sum;
+  const int S = (H - 10 + R - 1) / R;
+  const size_t smem = ssim_smem_bytes(R, W);
+  VPK_CUDA(cudaFuncSetAttribute(metric_ssim_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  launch_pdl(metric_ssim_kernel, dim3(static_cast<unsigned>(B) * P * C, S), dim3(256), smem, stream, pred, target, H, W, R, win,
+             scratch);
+  const double inv = 1.0 / (static_cast<double>(C) * (H - 10) * (W - 10));
+  launch_pdl(metric_ssim_sums_kernel, dim3(P), dim3(256), 0, stream, static_cast<const double*>(scratch), B, P, C * S, inv, out);
 }
 
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream) {

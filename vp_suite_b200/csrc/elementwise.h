@@ -65,6 +65,11 @@ void launch_groupnorm_apply(const float* in, void* out, int out_kind, const floa
 // 10 * log10(SSE / chw); out = [frames SSE sums | frames log sums | batch]
 void launch_metric_partial_sums(const float* pred, const float* target, int B, int P, long long chw, double* scratch,
                                 double* out, cudaStream_t stream);
+// SSIM (piqa defaults, restated): out[t] = sum over the batch of SSIM(pred[b, t], target[b, t]); scratch holds
+// metric_ssim_scratch_elems() fp64 strip sums (-1: unsupported image size)
+long long metric_ssim_scratch_elems(int B, int P, int C, int H, int W);
+void launch_metric_ssim_sums(const float* pred, const float* target, int B, int P, int C, int H, int W, double* scratch,
+                             double* out, cudaStream_t stream);
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);   // n % 4 == 0
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
 

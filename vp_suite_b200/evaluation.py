@@ -10,6 +10,9 @@ means over the batch of per-sample values:
           mean over frames, mean over batch
     PSNR  vp_suite/measure/image_wise.py:53-75: forward() = mean_{b,t} 10*log10(mean_chw (p-y)^2)  (lower is
           better); to_display() negates it
+    SSIM  vp_suite/measure/image_wise.py:100-121: forward() = 1 - piqa.ssim.SSIM()(reshape_clamp(pred, target)), the
+          mean over all (b, t) images of the per-image SSIM; 3-channel images only.  piqa is absent from the reference
+          checkout and this image: its algorithm is restated (value parity unpinned, see include/vpk.h)
 The per-horizon listing follows PredictionMetricProvider.get_metrics(all_frame_cnts=True)
 (vp_suite/measure/metric_provider.py:56-71): horizon k uses the first k predicted frames.
 """
@@ -54,6 +57,63 @@ def _native_partial_sums(pred: torch.Tensor, target: torch.Tensor) -> torch.Tens
         N.check(N.lib().vpk_metric_partial_sums(N.ptr(pred), N.ptr(target), b, p, chw, N.ptr(scratch), N.ptr(out),
                                                 stream))
     return out
+
+
+def _ssim_images_torch(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """Per-image SSIM [b, P] (definition for CPU tensors / gloo tests): piqa's defaults restated -- 11-tap Gaussian
+    window (sigma 1.5), valid region, K1 = 0.01, K2 = 0.03, value range 1, after reshape_clamp's (v + 1) / 2 clamp."""
+    import torch.nn.functional as F
+    b, p, c = pred.shape[:3]
+    x = ((pred.float() + 1) / 2).clamp(0.0, 1.0).flatten(0, 1)
+    y = ((target.float() + 1) / 2).clamp(0.0, 1.0).flatten(0, 1)
+    k = torch.arange(11, dtype=torch.float32, device=pred.device) - 5.0
+    k = torch.exp(-(k ** 2) / (2 * 1.5 ** 2))
+    k = k / k.sum()
+
+    def filt(v):
+        v = F.conv2d(v, k.view(1, 1, 11, 1).expand(c, 1, 11, 1), groups=c)
+        return F.conv2d(v, k.view(1, 1, 1, 11).expand(c, 1, 1, 11), groups=c)
+
+    mx, my = filt(x), filt(y)
+    mxx, myy, mxy = mx * mx, my * my, mx * my
+    sxx, syy, sxy = filt(x * x) - mxx, filt(y * y) - myy, filt(x * y) - mxy
+    cs = (2 * sxy + 0.03 ** 2) / (sxx + syy + 0.03 ** 2)
+    ss = (2 * mxy + 0.01 ** 2) / (mxx + myy + 0.01 ** 2) * cs
+    return ss.flatten(1).mean(-1, dtype=torch.float64).view(b, p)
+
+
+def ssim_partial_sums(pred: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    """fp64 vector [P]: entry t = sum over this rank's sequences of SSIM(pred[b, t], target[b, t]).  Like the
+    reference's measure (image_wise.py:112-113) it takes 3-channel frames only.  CUDA tensors go through libvpk
+    (``vpk_metric_ssim_sums``); CPU tensors use the torch definition above (gloo tests)."""
+    if pred.shape != target.shape or pred.dim() != 5:
+        raise ValueError(f"ssim_partial_sums: shapes {tuple(pred.shape)} / {tuple(target.shape)}")
+    if pred.shape[2] != 3:
+        raise ValueError("Structural Similarity (SSIM) needs 3-channel images with the channels at dim 2")
+    if not pred.is_cuda:
+        return _ssim_images_torch(pred, target).sum(0)
+    from . import _native as N
+    b, p, c, h, w = pred.shape
+    n = N.lib().vpk_metric_ssim_scratch_elems(b, p, c, h, w)
+    if n < 0:
+        raise ValueError(f"ssim_partial_sums: unsupported image size {h} x {w} (the window is 11 x 11)")
+    pred = pred.contiguous().float()
+    target = target.to(pred.device).contiguous().float()
+    scratch = torch.empty(n, dtype=torch.float64, device=pred.device)
+    out = torch.empty(p, dtype=torch.float64, device=pred.device)
+    stream = torch.cuda.current_stream(pred.device).cuda_stream
+    with torch.cuda.device(pred.device):
+        N.check(N.lib().vpk_metric_ssim_sums(N.ptr(pred), N.ptr(target), b, p, c, h, w, N.ptr(scratch), N.ptr(out),
+                                             stream))
+    return out
+
+
+def finalize_ssim(ssim_vec: torch.Tensor, sequences: float) -> list:
+    """Per-horizon SSIM as the reference displays it (to_display(1 - mean) = mean over the first k frames and the
+    batch of the per-image SSIM; image_wise.py:119-121)."""
+    P = ssim_vec.numel()
+    frames = torch.arange(1, P + 1, dtype=torch.float64, device=ssim_vec.device)
+    return (torch.cumsum(ssim_vec, 0) / (frames * float(sequences))).tolist()
 
 
 def all_reduce_sums(vec: torch.Tensor, group=None) -> torch.Tensor:
