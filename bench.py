@@ -7,7 +7,7 @@ bench.py -- predicted frames/s of the recurrent-rollout hot path on B200 (BASELI
 One "step" = one rollout (VPModel.forward) over this rank's shard of synthetic sequences.  Default workload is
 BASELINE config 5 (convlstm-shi, 3x128x128, 10 context + 20 predicted frames), sharded by independent sequences:
 every rank processes `--seqs-per-gpu` sequences (weak scaling; 512/GPU = the named global batch 4096 at 8 GPUs).
-The rollout has no inter-GPU traffic; NCCL only sums the evaluation metrics (MSE / PSNR partial sums).
+The rollout has no inter-GPU traffic; NCCL only sums the evaluation metrics (MSE / PSNR / SSIM partial sums).
 
 Printed JSON (rank 0, one line): metric/value/unit, ms_per_step, e2e (host buffers through the C ABI, H2D/D2H
 inside the timed region), roofline (gate-GEMM kernels: algorithmic FLOPs / CUDA-event time vs the measured bf16
@@ -299,6 +299,15 @@ def main():
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json "
                                f"({'sustained' if ms_per_step > 50 else 'burst'} bf16 cuBLAS)"}
 
+    # ---- SSIM sums of one (untimed) rollout, 3-channel workloads: the third metric the evaluation all-reduces ----
+    ssim_disp = None
+    if img[0] == 3:
+        with torch.no_grad():
+            out, _ = model(x_dev, pred_frames=pred)
+            ssim_vec = E.all_reduce_sums(E.ssim_partial_sums(out, tgt_dev))
+        ssim_disp = E.finalize_ssim(ssim_vec, B * world)
+        del out
+
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -331,7 +340,10 @@ def main():
             "clocks": clocks,
             "eval_metrics": {"mse_h1": ev["mse"][0], "psnr_h1": ev["psnr"][0], "mse_hP": ev["mse"][-1],
                              "psnr_hP": ev["psnr"][-1], "sequences": ev["sequences"],
-                             "note": "synthetic random targets; exercises the NCCL metric reduction only"},
+                             "ssim_h1": ssim_disp[0] if ssim_disp else None,
+                             "ssim_hP": ssim_disp[-1] if ssim_disp else None,
+                             "note": "synthetic random targets; exercises the NCCL metric reduction only (MSE / PSNR sums inside "
+                                     "the timed step; SSIM sums, 3-channel workloads, once outside it)"},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
