@@ -103,6 +103,43 @@ def stlstm_step(x, h, c, m, w_x, w_h, w_m, w_o, w_last, forget_bias=1.0, ln=None
 
 
 # --------------------------------------------------------------------------------------------------
+# Action-conditional ST-LSTM v2 cell            (vp_suite/model_blocks/predrnn.py:86-169)
+# --------------------------------------------------------------------------------------------------
+def stlstm_ac_step(x, h, c, m, a, sd, forget_bias=1.0):
+    """ActionConditionalSpatioTemporalLSTMCell.forward (:142-169) from the block's own state dict ``sd``.
+    Differences to ``stlstm_step``: every conv has a bias (:104-139); a fifth conv ``conv_a`` (4C outputs) runs on the
+    action tensor ``a`` [b, C, H, W] and MULTIPLIES conv_h's output before the (i, f, g, o) split (:145,149); with
+    layer_norm=True each of conv_x / conv_h / conv_a / conv_m / conv_o is followed by its own LayerNorm([C', H, W]).
+    Oracle only so far: libvpk has no kernel path for this cell yet (second half)."""
+    C = sd["conv_h.0.weight"].shape[0] // 4
+    pad = sd["conv_x.0.weight"].shape[-1] // 2
+
+    def conv(t, key):
+        out = F.conv2d(t, sd[f"conv_{key}.0.weight"], sd[f"conv_{key}.0.bias"], padding=pad)
+        w = sd.get(f"conv_{key}.1.weight")
+        return out if w is None else F.layer_norm(out, tuple(w.shape), w, sd[f"conv_{key}.1.bias"], eps=1e-5)
+
+    X, H, A, M = conv(x, "x"), conv(h, "h"), conv(a, "a"), conv(m, "m")
+    i_x, f_x, g_x, ip_x, fp_x, gp_x, o_x = torch.split(X, C, dim=1)
+    i_h, f_h, g_h, o_h = torch.split(H * A, C, dim=1)
+    i_m, f_m, g_m = torch.split(M, C, dim=1)
+    i_t = torch.sigmoid(i_x + i_h)
+    f_t = torch.sigmoid(f_x + f_h + forget_bias)
+    g_t = torch.tanh(g_x + g_h)
+    delta_c = i_t * g_t
+    c_new = f_t * c + delta_c
+    ip = torch.sigmoid(ip_x + i_m)
+    fp = torch.sigmoid(fp_x + f_m + forget_bias)
+    gp = torch.tanh(gp_x + g_m)
+    delta_m = ip * gp
+    m_new = fp * m + delta_m
+    mem = torch.cat([c_new, m_new], dim=1)
+    o_t = torch.sigmoid(o_x + o_h + conv(mem, "o"))
+    h_new = o_t * torch.tanh(F.conv2d(mem, sd["conv_last.weight"], sd["conv_last.bias"]))
+    return h_new, c_new, m_new, delta_c, delta_m
+
+
+# --------------------------------------------------------------------------------------------------
 # PhyCell cell, action_conditional=False        (vp_suite/model_blocks/phydnet.py:49-62)
 # --------------------------------------------------------------------------------------------------
 def find_divisor_for_group_norm(x):

@@ -160,8 +160,38 @@ def run_blocks(manifest):
     print("blocks:", sorted(arrays))
 
 
+def run_blocks_ac(manifest):
+    """Action-conditional ST-LSTM cell (predrnn.py:86-169), both layer_norm settings -> blocks_ac.npz.  Kept in its own
+    file so that adding it does not rewrite the other fixtures: ``python -m oracle.make_golden blocks_ac``."""
+    from vp_suite.model_blocks.predrnn import ActionConditionalSpatioTemporalLSTMCell as ACCell
+    arrays = {}
+    for tag, ln, wseed, xseed in (("stac", False, 26, 10), ("stacln", True, 27, 11)):
+        cell = ACCell(16, 32, 8, 8, 5, 1, ln).eval()
+        shp = shapes_of(cell)
+        cell.load_state_dict(synth_state_dict(shp, wseed))
+        g = torch.Generator().manual_seed(xseed)
+        x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+        h, c, mm, a = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(4)]
+        with torch.no_grad():
+            res = cell(x, h, c, mm, a)
+        for nm, v in zip(("h", "c", "m", "dc", "dm"), res):
+            arrays[f"{tag}_{nm}"] = v.numpy()
+        manifest["blocks"][f"stlstm_{tag[2:]}"] = dict(shapes=shp, wseed=wseed, xseed=xseed)
+    np.savez_compressed(os.path.join(OUT, "blocks_ac.npz"), **arrays)
+    print("blocks_ac:", sorted(arrays))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if sys.argv[1:] == ["blocks_ac"]:            # add the action-conditional block fixtures to an existing manifest
+        ref_shim.load_reference()
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
+        with open(os.path.join(OUT, "manifest.json")) as f:
+            manifest = json.load(f)
+        run_blocks_ac(manifest)
+        with open(os.path.join(OUT, "manifest.json"), "w") as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     classes = ref_shim.load_reference()
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     manifest = {"generator": "oracle/make_golden.py", "reference": "AIS-Bonn/vp-suite v0.0.9 (/root/reference)",
@@ -169,6 +199,7 @@ def main():
     run_models(classes, manifest)
     run_branch(classes, manifest)
     run_blocks(manifest)
+    run_blocks_ac(manifest)
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

@@ -100,6 +100,22 @@ def test_blocks_match_reference(manifest):
         assert np.abs(hn.numpy() - gold["phy_h"]).max() <= ATOL
 
 
+@pytest.mark.parametrize("tag, key, xseed", [("stac", "stlstm_ac", 10), ("stacln", "stlstm_acln", 11)])
+def test_action_conditional_stlstm_cell_matches_reference(manifest, tag, key, xseed):
+    """ActionConditionalSpatioTemporalLSTMCell (predrnn.py:86-169), layer_norm off / on: the oracle restatement against
+    vectors the reference produced (oracle/make_golden.py run_blocks_ac).  Oracle only: no kernel path yet."""
+    gold = load_golden("blocks_ac")
+    mb = manifest["blocks"][key]
+    sd = synth_state_dict(mb["shapes"], mb["wseed"])
+    g = torch.Generator().manual_seed(xseed)
+    x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+    h, c, m, a = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(4)]
+    with torch.no_grad():
+        res = OB.stlstm_ac_step(x, h, c, m, a, sd)
+    for nm, v in zip(("h", "c", "m", "dc", "dm"), res):
+        assert np.abs(v.numpy() - gold[f"{tag}_{nm}"]).max() <= ATOL, nm
+
+
 def test_group_norm_divisor():
     # phydnet.py:348-362: 49 -> 7 groups, 64 -> 8
     assert OB.find_divisor_for_group_norm(49) == 7
