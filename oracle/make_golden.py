@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim                      # noqa: E402
-from oracle.weights import synth_state_dict, synth_frames   # noqa: E402
+from oracle.weights import synth_state_dict, synth_frames, measure_inputs   # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -181,14 +181,45 @@ def run_blocks_ac(manifest):
     print("blocks_ac:", sorted(arrays))
 
 
+def run_measures(manifest):
+    """MSE / PSNR per prediction horizon from the reference's OWN measure classes, through its PredictionMetricProvider
+    (measure/metric_provider.py:34-73, measure/image_wise.py:19-31,53-75) -> measures.npz.  SSIM is not included: the
+    reference delegates it to piqa, which is absent (value parity unpinned)."""
+    from vp_suite.measure.metric_provider import PredictionMetricProvider
+    from vp_suite.measure.image_wise import MSE, PSNR
+    arrays = {}
+    manifest["measures"] = {}
+    for name, shape, seed in (("m3", (3, 5, 3, 24, 20), 31), ("m1", (2, 4, 1, 16, 16), 32)):
+        pred, target = measure_inputs(shape, seed)
+        # (a 1-channel config must list "fvd": metric_provider.py:29-31 pops it unconditionally when img_c is not 2 or 3)
+        metrics = ["mse", "psnr"] + (["fvd"] if shape[2] not in (2, 3) else [])
+        prov = PredictionMetricProvider({"device": "cpu", "metrics": metrics, "img_c": shape[2]})
+        rows = prov.get_metrics(pred, target, all_frame_cnts=True)
+        keys = sorted(rows[0])
+        assert keys == ["mse (↓)", "psnr (↑)"], keys
+        arrays[f"{name}_mse"] = np.asarray([r["mse (↓)"] for r in rows], dtype=np.float64)
+        arrays[f"{name}_psnr"] = np.asarray([r["psnr (↑)"] for r in rows], dtype=np.float64)
+        # the raw (lower-is-better) forward values over all frames, as loss providers see them
+        arrays[f"{name}_mse_fwd"] = np.asarray(float(MSE("cpu")(pred, target)), dtype=np.float64)
+        arrays[f"{name}_psnr_fwd"] = np.asarray(float(PSNR("cpu")(pred, target)), dtype=np.float64)
+        manifest["measures"][name] = dict(shape=list(shape), seed=seed, keys=keys)
+    np.savez_compressed(os.path.join(OUT, "measures.npz"), **arrays)
+    print("measures:", {k: np.round(v, 4).tolist() for k, v in arrays.items()})
+
+
+INCREMENTAL = {"blocks_ac": run_blocks_ac, "measures": run_measures}
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
-    if sys.argv[1:] == ["blocks_ac"]:            # add the action-conditional block fixtures to an existing manifest
+    if sys.argv[1:] and all(a in INCREMENTAL for a in sys.argv[1:]):
+        # add fixtures to an existing manifest without rewriting the others: python -m oracle.make_golden measures ...
         ref_shim.load_reference()
         torch.set_num_threads(max(1, os.cpu_count() or 1))
         with open(os.path.join(OUT, "manifest.json")) as f:
             manifest = json.load(f)
-        run_blocks_ac(manifest)
+        for a in sys.argv[1:]:
+            INCREMENTAL[a](manifest)
         with open(os.path.join(OUT, "manifest.json"), "w") as f:
             json.dump(manifest, f, indent=1, sort_keys=True)
         return
@@ -200,6 +231,7 @@ def main():
     run_branch(classes, manifest)
     run_blocks(manifest)
     run_blocks_ac(manifest)
+    run_measures(manifest)
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

@@ -49,3 +49,20 @@ def ssim_measure(pred, target):
     if np.shape(pred)[2] != 3 or np.shape(target)[2] != 3:
         raise ValueError("Structural Similarity (SSIM) needs 3-channel images with the channels at dim 2")
     return 1.0 - float(ssim_images(pred, target).mean())
+
+
+# ---- MSE / PSNR (fully in the reference; pinned by tests/golden/measures.npz, made by the reference's own classes) ----
+def mse_per_horizon(pred, target):
+    """vp_suite/measure/image_wise.py:19-31 + base/base_measure.py:54-57: squared error summed over (c, h, w), mean over the
+    first k frames, mean over the batch -- for every horizon k = 1..P (metric_provider.py:56-71).  fp64 numpy."""
+    se = (np.asarray(pred, dtype=np.float64) - np.asarray(target, dtype=np.float64)) ** 2
+    per_frame = se.sum(axis=(2, 3, 4))                                     # [b, P]
+    return np.asarray([per_frame[:, :k].mean(axis=1).mean(axis=0) for k in range(1, per_frame.shape[1] + 1)])
+
+
+def psnr_per_horizon(pred, target):
+    """vp_suite/measure/image_wise.py:65-75: 10 * log10(mean_chw squared error) per frame, mean over frames then batch,
+    negated for display (to_display)."""
+    se = (np.asarray(pred, dtype=np.float64) - np.asarray(target, dtype=np.float64)) ** 2
+    per_frame = 10.0 * np.log10(se.mean(axis=(2, 3, 4)))
+    return np.asarray([-per_frame[:, :k].mean(axis=1).mean(axis=0) for k in range(1, per_frame.shape[1] + 1)])

@@ -1,10 +1,12 @@
 """
-Import shim for the real vp-suite reference (test infrastructure; authoring container only).
+Import shim for the real vp-suite reference (test infrastructure).
 
-``/root/reference`` is a read-only mount that exists only where the golden vectors are generated; it does not
-exist on the GPU box, so nothing at test / bench time may call this.  Recipe from SURVEY.md App. A.1:
-register a bare ``vp_suite`` namespace (skips ``vp_suite/__init__.py`` and its dataset imports), polyfill
-``torch._utils._accumulate`` and stub ``piqa``.
+The unmodified reference is looked for in ``baseline/_ref`` first (``pip install --no-deps --target baseline/_ref`` of
+the checkout; git-ignored, but it travels to the GPU box with the repo snapshot) and then in the
+authoring container's read-only mount ``/root/reference``.  Recipe from SURVEY.md App. A.1: register a bare
+``vp_suite`` namespace (skips ``vp_suite/__init__.py`` and its dataset imports, which need packages this image lacks),
+polyfill ``torch._utils._accumulate`` and stub ``piqa``.  Users: ``oracle/make_golden.py``, the tests that compare
+against the real reference, and ``bench.py --impl reference`` -- never the product path.
 """
 import importlib
 import itertools
@@ -13,7 +15,17 @@ import sys
 import types
 from unittest.mock import MagicMock
 
-REFERENCE_ROOT = os.environ.get("VPK_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_root():
+    for cand in (os.environ.get("VPK_REFERENCE_ROOT"), os.path.join(_REPO, "baseline", "_ref"), "/root/reference"):
+        if cand and os.path.isdir(os.path.join(cand, "vp_suite", "models")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def available():

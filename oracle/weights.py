@@ -49,3 +49,12 @@ def synth_frames(b, t, c, h, w, seed=1234):
     up = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=False)
     x = 0.8 * up + 0.2 * torch.rand(b * t, c, h, w, generator=g)
     return x.reshape(b, t, c, h, w).clamp_(0.0, 1.0 - 1e-6).contiguous()
+
+
+def measure_inputs(shape, seed):
+    """Deterministic (pred, target) pair in [0, 1] for the measure fixtures (tests regenerate them from the seed)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    target = torch.rand(shape, generator=g)
+    pred = (target + 0.15 * torch.randn(shape, generator=g)).clamp(0.0, 1.0)
+    return pred, target

@@ -32,11 +32,9 @@ CASES = {
 }
 
 
-# End-of-rollout bound.  north_star states 2e-2 after 10 predicted frames for the five BASELINE configs.  The LayerNorm
-# variant is outside those five: LayerNorm renormalises every gate pre-activation to unit variance, the
-# 16-bit operand rounding (fp16 here) is amplified more per step, and the full-length 10 + 10 rollout with random weights
-# measures 2.5e-2 on the tenth frame (4.4e-3 on the first; fp32-operand mode: 6e-6).  Written as measured, not as 2e-2.
-END_TOL = {"cfg3ln": 3e-2}
+# End-of-rollout bound: north_star's 2e-2 after 10 predicted frames, for every case incl. the LayerNorm variant (whose
+# conv_x / conv_h / conv_m run with split fp16 weights for exactly this reason, model_predrnn.cu: add_ln_cell).
+END_TOL = 2e-2
 
 
 @pytest.mark.parametrize("name", sorted(CASES))
@@ -57,7 +55,8 @@ def test_full_shape_parity_and_batch_independence(name):
         small, small_aux = m(x3.cuda(), pred_frames=pred)
     d = (small.cpu() - ref).abs()
     errs = [float(d[:, t].max()) for t in range(pred)]
-    assert errs[0] <= 5e-3 and max(errs) <= END_TOL.get(name, 2e-2), f"{name}: per-frame max abs error vs the oracle {errs}"
+    print(f"{name}: per-frame max abs error vs the oracle {['%.1e' % e for e in errs]}")
+    assert errs[0] <= 5e-3 and max(errs) <= END_TOL, f"{name}: per-frame max abs error vs the oracle {errs}"
 
     idx = torch.arange(full_b) % 3
     with torch.no_grad():
@@ -73,3 +72,24 @@ def test_full_shape_parity_and_batch_independence(name):
         (k, v), = full_aux.items()
         (_, rv), = ref_aux.items()
         assert abs(float(v) - float(rv)) <= 0.05 * abs(float(rv)) + 1e-2
+
+
+def test_layer_norm_statistics_buffer_for_wide_models():
+    """num_hidden >= 152 makes conv_x's 7C outputs span more than four N tiles: the per-sample statistics regions of
+    conv_x / conv_h / conv_m (sized from the real slot counts) must not overlap each other or the next buffer."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import vp_suite_b200 as V
+    img, ctx, pred = (1, 32, 32), 2, 2
+    kw = {"layer_norm": True, "num_hidden": [160, 160, 160, 160], "num_layers": 2}
+    m = V.MODEL_CLASSES["predrnn-pp"]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
+                                      precision="bf16", **kw).eval()
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=5, gain=1.5)
+    m.load_state_dict(sd)
+    x = synth_frames(3, ctx + pred, *img, seed=8)
+    with torch.no_grad():
+        ref, _ = OM.predrnn_v2_forward(sd, x, pred, cfg={"num_hidden": kw["num_hidden"], "num_layers": 2})
+        got, _ = m(x.cuda(), pred_frames=pred)
+    d = (got.cpu() - ref).abs()
+    errs = [float(d[:, t].max()) for t in range(pred)]
+    assert errs[0] <= 5e-3 and max(errs) <= 2e-2, errs

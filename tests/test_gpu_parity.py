@@ -203,15 +203,20 @@ def test_ef_pred_1_and_missing_peepholes(manifest):
 # ------------------------------------------------------------------------------------------------------------------
 # VPModelBlock boundary: single-step cells through vpk_*_cell_step against the reference's block golden vectors
 # ------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+# single-step bound of north_star (5e-3) for the 16-bit mode; the measured per-tensor errors are printed (pytest -s) and
+# recorded in DESIGN.md
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-3)])
 def test_blocks_match_reference_golden(manifest, precision, tol):
     from vp_suite_b200 import model_blocks as MB
     dev = _cuda()
     gold = load_golden("blocks")
     mb = manifest["blocks"]
 
+    measured = {}
+
     def close(a, key):
         err = np.abs(a.detach().cpu().numpy() - gold[key]).max()
+        measured[key] = float(err)
         assert err <= tol, f"{key} ({precision}): max abs err {err}"
 
     with torch.no_grad():
@@ -262,6 +267,7 @@ def test_blocks_match_reference_golden(manifest, precision, tol):
         g = torch.Generator().manual_seed(8)
         x, h = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1, torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
         close(pc(x.to(dev), None, h.to(dev)), "phy_h")
+    print(f"single-step blocks, {precision}: " + ", ".join(f"{k} {v:.1e}" for k, v in measured.items()))
 
 
 def test_stateful_blocks_reset_on_first_timestep():

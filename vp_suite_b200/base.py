@@ -1,14 +1,20 @@
 """
-Host-side mirror of the reference's model contract.
+Host side of the reference's model contract.
 
-``VPModel`` follows vp_suite/base/base_model.py:11-146 (constructor ``(device, **model_kwargs)``, ``REQUIRED_ARGS``,
-kwargs -> type-checked attributes, ``config`` property, ``forward`` / ``pred_1``); ``VPModelBlock`` follows
-vp_suite/base/base_model_block.py:4-13.  ``NativeRollout`` is the glue to libvpk: it mirrors the module's
-``state_dict`` into the native handle and runs ``forward`` through the C ABI.  Nothing here computes frames in
-Python -- without the CUDA library the calls raise.
+When the reference package is importable (``import vp_suite`` works, e.g. it is installed, or the tests' import shim
+registered it), ``VPModel`` / ``VPModelBlock`` here ARE subclasses of ``vp_suite.base.VPModel`` /
+``vp_suite.base.VPModelBlock``: constructor, ``config``, ``unpack_data``, ``eval_iter`` are the reference's own code and
+``isinstance(model, vp_suite.base.VPModel)`` holds, so ``VPSuite.test()`` (vp_suite/vpsuite.py:536-550) drives a
+registered drop-in unchanged.  Otherwise a faithful mirror of vp_suite/base/base_model.py:11-216 is used (constructor
+``(device, **model_kwargs)``, ``REQUIRED_ARGS``, kwargs -> type-checked attributes, ``config``, ``unpack_data``,
+``eval_iter``).  In both cases ``train_iter`` refuses: the native rollout is inference-only (``TRAINABLE = False``, which
+``VPSuite.train`` honours, vpsuite.py:312).  ``NativeRollout`` is the glue to libvpk: it mirrors the module's
+``state_dict`` into the native handle and runs ``forward`` through the C ABI.  Nothing here computes frames in Python --
+without the CUDA library the calls raise.
 """
 import ctypes as C
 import inspect
+import os
 
 import torch
 import torch.nn as nn
@@ -16,12 +22,21 @@ import torch.nn as nn
 from . import _native as N
 
 
-class VPModelBlock(nn.Module):
-    """Marker base of the model blocks (vp_suite/base/base_model_block.py:4-13)."""
-    NAME: str = __name__
-    PAPER_REFERENCE = None
-    CODE_REFERENCE = None
-    MATCHES_REFERENCE: str = None
+def _reference_bases():
+    """(vp_suite.base.VPModel, vp_suite.base.VPModelBlock) when the reference package imports, else (None, None).
+    VPK_NO_REFERENCE=1 forces the mirror (tests)."""
+    if os.environ.get("VPK_NO_REFERENCE"):
+        return None, None
+    try:
+        from vp_suite.base.base_model import VPModel as ref_model
+        from vp_suite.base.base_model_block import VPModelBlock as ref_block
+        return ref_model, ref_block
+    except Exception:          # not installed, or its own imports (datasets, piqa, ...) fail in this environment
+        return None, None
+
+
+_RefVPModel, _RefVPModelBlock = _reference_bases()
+REFERENCE_BASE = _RefVPModel is not None          #: True: the drop-ins subclass the real vp_suite.base.VPModel
 
 
 def _set_from_kwarg(obj, kwargs, name, required=False):
@@ -36,8 +51,17 @@ def _set_from_kwarg(obj, kwargs, name, required=False):
     setattr(obj, name, val)
 
 
-class VPModel(nn.Module):
-    # vp_suite/base/base_model.py:18-36
+class _MirrorVPModelBlock(nn.Module):
+    """Marker base of the model blocks (vp_suite/base/base_model_block.py:4-13)."""
+    NAME: str = __name__
+    PAPER_REFERENCE = None
+    CODE_REFERENCE = None
+    MATCHES_REFERENCE: str = None
+
+
+class _MirrorVPModel(nn.Module):
+    """vp_suite/base/base_model.py:11-216 restated (used only when the reference package is not importable)."""
+    # base_model.py:18-36
     NON_CONFIG_VARS = ["functions", "model_dir", "dump_patches", "training"]
     NAME = None
     PAPER_REFERENCE = None
@@ -87,11 +111,61 @@ class VPModel(nn.Module):
         out.update({"img_h": h, "img_w": w, "img_c": c, "NAME": self.NAME})
         return out
 
+    def unpack_data(self, data, config, reverse=False, complete=False):
+        """base_model.py:87-114: frames / actions of a VPData blob to the run's device, optional time reversal, split
+        into context and target frames (or context + target as the input when the model NEEDS_COMPLETE_INPUT)."""
+        img_data = data["frames"].to(config["device"])                   # [b, T, c, h, w]
+        actions = data["actions"].to(config["device"])                   # [b, T-1, a]
+        if img_data.ndim == 4:                                           # no batch dimension
+            img_data = img_data.unsqueeze(0)
+            actions = actions.unsqueeze(0)
+        if reverse:
+            img_data = torch.flip(img_data, dims=[1])
+            actions = torch.flip(actions, dims=[1])
+        t_in, t_pred = config["context_frames"], config["pred_frames"]
+        if self.NEEDS_COMPLETE_INPUT or complete:
+            input_frames = img_data[:, :t_in + t_pred]
+            target_frames = input_frames[:, t_in:].clone()
+        else:
+            input_frames, target_frames = torch.split(img_data[:, :t_in + t_pred], [t_in, t_pred], dim=1)
+        return input_frames, target_frames, actions
+
     def pred_1(self, x, **kwargs):
         raise NotImplementedError
 
     def forward(self, x, pred_frames=1, **kwargs):
         raise NotImplementedError
+
+    def eval_iter(self, config, loader, loss_provider):
+        """base_model.py:181-216: one pass over the validation loader; returns ({loss name: mean}, indicator loss)."""
+        self.eval()
+        all_losses, indicator_losses = [], []
+        with torch.no_grad():
+            for data in loader:
+                inp, targets, actions = self.unpack_data(data, config)
+                predictions, _ = self(inp, pred_frames=config["pred_frames"], actions=actions)
+                loss_values, _ = loss_provider.get_losses(predictions, targets)
+                all_losses.append(loss_values)
+                indicator_losses.append(loss_values[config["val_rec_criterion"]])
+        indicator_loss = torch.stack(indicator_losses).mean()
+        all_losses = {k: torch.stack([lv[k] for lv in all_losses]).mean().item() for k in all_losses[0].keys()}
+        self.train()
+        return all_losses, indicator_loss
+
+
+class VPModelBlock(_RefVPModelBlock or _MirrorVPModelBlock):
+    """Base of the drop-in blocks: the reference's marker class when importable (base_model_block.py:4-13)."""
+
+
+class VPModel(_RefVPModel or _MirrorVPModel):
+    """Base of the drop-in models: the reference's own VPModel when importable, else its mirror above."""
+    TRAINABLE = False        # vpsuite.py:312 skips training for such models; the native rollout has no backward pass
+
+    def train_iter(self, config, loader, optimizer, loss_provider, epoch):
+        """base_model.py:148-179 needs gradients through forward(); libvpk is inference-only."""
+        raise NotImplementedError(f"{type(self).__name__} (vp_suite_b200) is an inference-only drop-in: forward() runs in "
+                                  f"libvpk without autograd, so train_iter() is not available (TRAINABLE = False); train "
+                                  f"with the reference class and load its state_dict / checkpoint here")
 
 
 class NativeRollout:
@@ -108,17 +182,47 @@ class NativeRollout:
 
     def _native_init(self):
         self._handle = None
+        self._handle_device = None
         self._versions = None
         self._workspaces = {}
 
+    # -- pickling (torch.save(model) / torch.load, vpsuite.py:394,135): the native handle is dropped and rebuilt ----------
+    _NATIVE_STATE = ("_handle", "_handle_device", "_versions", "_workspaces", "_host_out")
+
+    def __getstate__(self):
+        state = dict(self.__dict__)
+        for k in self._NATIVE_STATE:
+            state.pop(k, None)
+        return state
+
+    def __setstate__(self, state):
+        nn.Module.__setstate__(self, state)
+        self._native_init()
+
     # -- handle lifecycle ---------------------------------------------------------------------------------------
-    def _native_handle(self):
-        lib = N.lib()
-        self._create_handle()
-        versions = tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items())
-        if versions != self._versions:
-            self._push_weights()
-            self._versions = versions
+    def _native_device(self):
+        """CUDA device the handle lives on: the device of the module's parameters (the constructor moves them to
+        ``self.device``; a later ``.to()`` is followed)."""
+        p = next(iter(self.parameters()), None)
+        if p is None or not p.is_cuda:
+            raise N.NativeError("vp_suite_b200 models run on a CUDA device only (there is no CPU path); construct the "
+                                "model with device='cuda[:i]'")
+        return p.device
+
+    def _native_handle(self, device=None):
+        """The libvpk handle with current weights.  libvpk allocates on, and launches on, the calling thread's current
+        device: every native call is made with the model's device current."""
+        device = torch.device(device) if device is not None else self._native_device()
+        N.lib()
+        with torch.cuda.device(device):
+            if self._handle is not None and self._handle_device != device:
+                self._native_release()                 # the module moved: packed weights / programs live on the old device
+            self._create_handle()
+            self._handle_device = device
+            versions = tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items())
+            if versions != self._versions:
+                self._push_weights()
+                self._versions = versions
         return self._handle
 
     def _create_handle(self):
@@ -175,7 +279,7 @@ class NativeRollout:
             raise N.NativeError("vp_suite_b200 models run on CUDA tensors only (there is no CPU path); "
                                 "use forward_host() for host buffers")
         lib = N.lib()
-        h = self._native_handle()
+        h = self._native_handle(x.device)
         x = x.detach().to(torch.float32).contiguous()
         b = x.shape[0]
         out = torch.empty((b, pred_frames, self.img_c, self.img_h, self.img_w), dtype=torch.float32, device=x.device)
@@ -189,8 +293,9 @@ class NativeRollout:
             ws = torch.empty(nbytes.value, dtype=torch.uint8, device=x.device)
             self._workspaces[key] = ws
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        N.check(lib.vpk_model_forward(h, N.ptr(x), b, t_in, pred_frames, N.ptr(out), N.ptr(aux), N.ptr(ws),
-                                      ws.numel(), C.c_void_p(stream)))
+        with torch.cuda.device(x.device):
+            N.check(lib.vpk_model_forward(h, N.ptr(x), b, t_in, pred_frames, N.ptr(out), N.ptr(aux), N.ptr(ws),
+                                          ws.numel(), C.c_void_p(stream)))
         return out, aux
 
     def forward_host(self, x, pred_frames=1, out=None):
@@ -212,8 +317,9 @@ class NativeRollout:
         elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.is_cuda:
             raise ValueError("out must be a contiguous host fp32 tensor of shape %s" % (shape,))
         aux = torch.zeros(1, dtype=torch.float32)
-        N.check(lib.vpk_model_forward_host(h, N.ptr(x), b, self._native_t_in(t_in, pred_frames), pred_frames,
-                                           N.ptr(out), N.ptr(aux)))
+        with torch.cuda.device(self._handle_device):
+            N.check(lib.vpk_model_forward_host(h, N.ptr(x), b, self._native_t_in(t_in, pred_frames), pred_frames,
+                                               N.ptr(out), N.ptr(aux)))
         return out, aux
 
     def _native_t_in(self, t_total, pred_frames):

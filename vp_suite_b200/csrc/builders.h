@@ -100,6 +100,7 @@ struct ConvArgs {
   bool split = false;           // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
   const void* x_lo = nullptr;
   int cin_w = -1;               // input channels the weight tensor really has (-1: Cin); x may carry zero padding channels
+  bool w_split = false;         // weights as high + low 16-bit parts over the same activations (lowering.h: ConvInput::w_split)
 };
 inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -120,6 +121,7 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
   }
   ConvInput in{make_view(a.x, a.H, a.W, a.Cin), 0, 0};
   in.wc_count = a.cin_w;
+  in.w_split = a.w_split && a.stride == 1;
   if (a.split) in.lo_view = make_view(a.x_lo, a.H, a.W, a.Cin);
   lower_conv(s, a.k, a.stride, a.pad, {in}, a.H, a.W, act.esize, oh, ow);
   EpiParams& e = s.phases[0].epi;

@@ -182,15 +182,20 @@ class StLstmCell : public CellBase {
     if (built_batch != B) {
       convs.clear();
       int oh, ow;
-      auto raw_conv = [&](const char* name, const void* src, int ci, int co, int kk, const float* wt, float* dst) {
+      // 16-bit mode: split fp16 weights for conv_x / conv_h / conv_m, as in the rollout (model_predrnn.cu: add_ln_cell)
+      const char* ws_env = getenv("VPK_LN_WSPLIT");
+      const bool w_split_on = adt == DT_F16 && (ws_env == nullptr || atoi(ws_env) != 0);
+      auto raw_conv = [&](const char* name, const void* src, int ci, int co, int kk, const float* wt, float* dst,
+                          bool wsplit = false) {
         ConvArgs a{std::string("cell.ln.") + name, B, h, w, ci, co, kk, 1, kk / 2, src, wt, nullptr, ACT_NONE, dst};
         a.out_f32_dense = true;
+        a.w_split = wsplit && w_split_on && ((ci + 63) / 64) * 2 * kk * kk <= kMaxSteps;
         for (BuiltConv& bc : build_conv(conv_spec(a, a16, &oh, &ow), adt, backend, store, cache, s, num_sms, false))
           convs.push_back(bc);
       };
-      raw_conv("x", xb, cin, 7 * ch, k, wx.data(), xr);
-      raw_conv("h", hi, ch, 4 * ch, k, wh.data(), hr);
-      raw_conv("m", mi, ch, 3 * ch, k, wm.data(), mr);
+      raw_conv("x", xb, cin, 7 * ch, k, wx.data(), xr, true);
+      raw_conv("h", hi, ch, 4 * ch, k, wh.data(), hr, true);
+      raw_conv("m", mi, ch, 3 * ch, k, wm.data(), mr, true);
       raw_conv("o", mem, 2 * ch, ch, k, wo.data(), orw);
       raw_conv("last", mem, 2 * ch, ch, 1, wl.data(), lr);
       finish_build(s);

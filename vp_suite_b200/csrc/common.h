@@ -144,6 +144,19 @@ struct ConvLaunch {
   int is_gate_gemm;       // counted in the gate-GEMM roofline figure
 };
 
+// Environment switches.  Everything the shipping library reads with getenv() selects between code paths that compute
+// the same frames (A/B runs; each alternative has a GPU test).  Switches that CHANGE results or skip work -- perf
+// experiments (VPK_EXP_NO_PEEPHOLES, VPK_TC_DEBUG) -- exist only in developer builds (make EXTRA_FLAGS=-DVPK_DEV): in the
+// product build dev_env() is constant nullptr, so a stray export on a box cannot silently void a number.
+inline const char* dev_env(const char* name) {
+#ifdef VPK_DEV
+  return getenv(name);
+#else
+  (void)name;
+  return nullptr;
+#endif
+}
+
 // VPK_PDL=0 turns programmatic dependent launch off (A/B runs).
 inline bool pdl_enabled() {
   static const bool on = [] {

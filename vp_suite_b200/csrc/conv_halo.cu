@@ -884,7 +884,7 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   P.pair = (P.tileN % 16 == 0 && m_tiles * P.n_tiles >= num_sms) ? 1 : 0;
   if (const char* env = getenv("VPK_TC_PAIR")) P.pair = (atoi(env) != 0 && P.tileN % 16 == 0) ? 1 : 0;
   P.debug = 0;
-  if (const char* env = getenv("VPK_TC_DEBUG")) P.debug = atoi(env);
+  if (const char* env = dev_env("VPK_TC_DEBUG")) P.debug = atoi(env);
   P.L.epi.debug = P.debug;
   P.fast_epi = (epi_tc_fast_ok(L.epi) && gates_of(L.epi.kind) == L.G) ? 1 : 0;
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;

@@ -281,7 +281,7 @@ void tc_make_plan(const ConvLaunch& L, TcPlan* plan, int num_sms) {
   // CTA pairs pay off once every SM pair has at least one 256-position tile; VPK_TC_PAIR=0/1 overrides (testing)
   P.cta2 = (P.tileN % 16 == 0 && m_tiles_total * P.n_tiles >= num_sms) ? 1 : 0;
   P.debug = 0;
-  if (const char* env = getenv("VPK_TC_DEBUG")) P.debug = atoi(env);
+  if (const char* env = dev_env("VPK_TC_DEBUG")) P.debug = atoi(env);
   P.L.epi.debug = P.debug;
   const int gk = (L.epi.kind == EPI_LSTM || L.epi.kind == EPI_ST_C) ? 4 : (L.epi.kind == EPI_ST_M) ? 3 : (L.epi.kind == EPI_ST_O) ? 2 : 1;
   P.fast_epi = (epi_tc_fast_ok(L.epi) && gk == L.G) ? 1 : 0;

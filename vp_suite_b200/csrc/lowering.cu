@@ -51,6 +51,8 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
     for (const ConvInput& in : inputs) {
       VPK_REQUIRE(in.view.H == in_h && in.view.W == in_w, "conv input size mismatch");
       const bool split = in.lo_view.base != nullptr || in.lo_view.C > 0;
+      VPK_REQUIRE(!(split && in.w_split), "conv input: either split activations + weights or split weights only");
+      const bool parts = split || in.w_split;
       const int hi = static_cast<int>(spec.srcs.size());
       spec.srcs.push_back(in.view);
       int lo = -1;
@@ -59,10 +61,12 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
         spec.srcs.push_back(in.lo_view);
       }
       for (int c0 = 0; c0 < in.view.C; c0 += 64) {
-        for (int part = split ? 1 : 0; part <= (split ? 2 : 0); ++part)
+        for (int part = parts ? 1 : 0; part <= (parts ? 2 : 0); ++part)
           for (int ky = 0; ky < k; ++ky)
-            for (int kx = 0; kx < k; ++kx)
+            for (int kx = 0; kx < k; ++kx) {
               add_step(ph.steps, hi, ky - pad, kx - pad, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count, part);
+              if (in.w_split && part == 2) ph.steps.back().count_flops = false;
+            }
         if (split)
           for (int ky = 0; ky < k; ++ky)
             for (int kx = 0; kx < k; ++kx)
@@ -253,6 +257,15 @@ int choose_cn(int C, int G) {
   }
 }
 
+}  // namespace
+
+int conv_n_tiles(int C, int G) {
+  const int cn = choose_cn(C, G);
+  return (C + cn - 1) / cn;
+}
+
+namespace {
+
 float weight_at(const WeightRef& w, int oc, int ic, int ky, int kx) {
   if (!w.transposed) return w.w[((static_cast<size_t>(oc) * w.I + ic) * w.KH + ky) * w.KW + kx];
   return w.w[((static_cast<size_t>(ic) * w.O + oc) * w.KH + ky) * w.KW + kx];
@@ -305,8 +318,8 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
               const int ky = h.per_gate ? h.gky[g] : h.ky, kx = h.per_gate ? h.gkx[g] : h.kx;
               for (int j = 0; j < h.kw_valid; ++j) {
                 float v = weight_at(w, oc, h.wc0 + h.s.c0 + j, ky, kx);
-                if (h.wsplit != 0) {   // split-bf16: high part, or what the high part misses
-                  const float hi = __bfloat162float(__float2bfloat16_rn(v));
+                if (h.wsplit != 0) {   // split operand: high 16-bit part, or what the high part misses
+                  const float hi = (dtype == DT_F16) ? __half2float(__float2half_rn(v)) : __bfloat162float(__float2bfloat16_rn(v));
                   v = (h.wsplit == 1) ? hi : v - hi;
                 }
                 row[j] = v;
@@ -395,7 +408,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         for (int g = 0; g < G; ++g) nv += h.gky[g] >= 0 ? 1 : 0;
         used = static_cast<double>(nv) / G;
       }
-      kreal += h.kw_valid * used;
+      if (h.count_flops) kreal += h.kw_valid * used;
     }
     L.flops = 2.0 * static_cast<double>(spec.B) * ph.H * ph.W * (static_cast<double>(G) * C) * kreal;
     if (!measure_only) {

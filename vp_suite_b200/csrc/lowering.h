@@ -28,7 +28,8 @@ struct BiasRef {
 struct HostStep {
   ConvStep s;
   int kw_valid;  // channels of this step that exist in the weight tensor (<= s.kc; the rest is zero padding)
-  int wsplit;    // 0: weight value as is; 1 / 2: high / low bf16 part of it (split-bf16 operands)
+  int wsplit;    // 0: weight value as is; 1 / 2: high / low 16-bit part of it (split operands)
+  bool count_flops = true;   // false: an extra product of a split weight (not part of the algorithmic FLOP count)
   int wref;      // index into ConvSpec::wrefs
   int ky, kx;    // tap of that weight tensor
   int wc0;       // input-channel index of that weight tensor that corresponds to channel 0 of the source
@@ -63,6 +64,9 @@ struct ConvInput {                  // one logical input tensor of a conv (full-
   SrcView lo_view{nullptr, 0, 0, 0, 0, 0, 0};   // split-bf16 operand: `view` holds the high parts, `lo_view` the low parts
   int wc_count = -1;                // channels the weight really has for this input (-1: view.C); a view may carry
                                     // zero-padded extra channels (e.g. 49 -> 56 so that TMA strides are 16-byte)
+  // weights only are split into a high and a low 16-bit part: A * W_hi + A * W_lo, two taps per weight tap over the SAME
+  // activation tile (~22 weight mantissa bits; stride-1 convs; LayerNorm-fed ST-LSTM convs, see model_predrnn.cu)
+  bool w_split = false;
 };
 
 // Appends the K-steps of a k x k conv with the given stride (1 or 2) and padding over `inputs` to spec.phases[0]
@@ -132,6 +136,9 @@ struct PackedWeights {
   HaloTap* taps = nullptr;
   int nblocks = 0, ntaps = 0, radius = 0;
 };
+
+// N tiles the tensor-core kernels split `C` output channels with `G` gates per channel into (the tile rule of build_conv).
+int conv_n_tiles(int C, int G);
 
 // Packs the weights of every phase of `spec` for activation type `dtype` and returns one BuiltConv per phase (device
 // pointers of the sources / outputs inside spec must already be final unless `measure_only`).

@@ -294,7 +294,7 @@ void Model::forward(const float* x, int batch, int t_in, int pred, float* out, f
   const int mb = microbatch(batch);
   const size_t in_stride = static_cast<size_t>(in_frames(t_in, pred)) * desc.img_c * desc.img_h * desc.img_w;
   const size_t out_stride = static_cast<size_t>(pred) * desc.img_c * desc.img_h * desc.img_w;
-  begin_call(batch, aux, stream);
+  begin_call(batch, t_in, pred, aux, stream);
   for (int mb0 = 0; mb0 < batch; mb0 += mb) {
     const int nb = std::min(mb, batch - mb0);
     Program* prog = get_program(nb, t_in, pred, ws, ws_bytes, stream);
@@ -356,7 +356,7 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
   gate_flags.clear();
   timed_flops = 0;
   timed_launches = 0;
-  begin_call(batch, hpipe.d_aux, hpipe.s_comp);
+  begin_call(batch, t_in, pred, hpipe.d_aux, hpipe.s_comp);
   int it = 0;
   for (int mb0 = 0; mb0 < batch; mb0 += mb, ++it) {
     const int nb = std::min(mb, batch - mb0);

@@ -97,7 +97,7 @@ class Model {
   // true while forward_host() builds a program: a rollout may lay its ops out differently for the host pipeline
   // (PhyDNet encodes the context frames in growing groups so that compute starts after the first frame's copy)
   bool host_build = false;
-  virtual void begin_call(int batch, float* aux, cudaStream_t stream) {}
+  virtual void begin_call(int batch, int t_in, int pred, float* aux, cudaStream_t stream) {}
   virtual void end_call(int batch, float* aux, cudaStream_t stream) {}
 
   // ---- helpers for build() ----

@@ -164,7 +164,7 @@ class EfConvLstm : public Model {
           const std::string rn = std::string(side == 0 ? "encoder.rnn" : "forecaster.rnn") + std::to_string(n + 1) + ".";
           const int C = d.enc_c[2 * n + 1];
           if (!has(rn + "Wci") && !has(rn + "Wcf") && !has(rn + "Wco")) continue;
-          if (getenv("VPK_EXP_NO_PEEPHOLES") != nullptr) continue;   // perf experiments only: changes the results
+          if (dev_env("VPK_EXP_NO_PEEPHOLES") != nullptr) continue;   // perf experiments only: changes the results
           const char* names[3] = {"Wci", "Wcf", "Wco"};
           for (int k = 0; k < 3; ++k)
             peep[side][n][k] = dev_f32(rn + names[k], peephole_packed(rn + names[k], C, eh[n], ew[n]), stream);

@@ -67,7 +67,8 @@ class PredRnnV2 : public Model {
   int used_in_frames(int t_in, int pred) const override { return t_in - pred; }
   bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_NO_INPUT_STREAM") == nullptr; }
 
-  void begin_call(int, float*, cudaStream_t stream) override {
+  void begin_call(int, int t_in, int, float*, cudaStream_t stream) override {
+    call_terms = (t_in - 1) * L;      // decoupling-loss terms of THIS call (a cached program may serve other lengths)
     if (!d_loss) VPK_CUDA(cudaMalloc(&d_loss, sizeof(double)));
     VPK_CUDA(cudaMemsetAsync(d_loss, 0, sizeof(double), stream));
   }
@@ -75,7 +76,7 @@ class PredRnnV2 : public Model {
     if (aux == nullptr) return;
     // 100 * mean over (t, layer) of mean over (b, ch)   (predrnn_v2.py:209-211, 229-230)
     const double scale = static_cast<double>(desc.decoupling_loss_scale) /
-                         (static_cast<double>(n_terms) * batch * C);
+                         (static_cast<double>(call_terms) * batch * C);
     launch_decouple_finalize(d_loss, aux, scale, stream);
   }
 
@@ -91,7 +92,6 @@ class PredRnnV2 : public Model {
     const int c = d.img_c, h = d.img_h, w = d.img_w;
     const int ctx = t_in - pred;
     const size_t px = static_cast<size_t>(B) * hp_ * wp_;
-    n_terms = (t_in - 1) * L;
     if (!measure && !d_loss) VPK_CUDA(cudaMalloc(&d_loss, sizeof(double)));
 
     // only the context frames are ever read (eval mask = 0): patchify those
@@ -120,10 +120,11 @@ class PredRnnV2 : public Model {
       mraw = static_cast<float*>(arena.alloc(px * 3 * C * sizeof(float)));
       oraw = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
       lraw = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
-      // statistics partials: up to (tiles per image) x (N tiles <= 4) x 8 slots per tensor and sample when the conv
-      // epilogues write them, kLnSlices otherwise
-      const size_t max_slots = std::max<size_t>(kLnSlices, static_cast<size_t>(((hp_ + 15) / 16) * ((wp_ + 7) / 8)) * 4 * 8);
-      lnpart = static_cast<float*>(arena.alloc(static_cast<size_t>(3) * B * max_slots * 2 * sizeof(float)));
+      // statistics partials: (tiles per image) x (N tiles) x 8 slots per tensor and sample when the conv epilogues write
+      // them (three regions: conv_x, conv_h, conv_m; conv_o reuses conv_x's), kLnSlices per tensor otherwise
+      const size_t slots = std::max<size_t>(3 * kLnSlices, static_cast<size_t>(ln_slots(7 * C)) + ln_slots(4 * C) + ln_slots(3 * C));
+      lnpart_floats = static_cast<size_t>(B) * slots * 2;
+      lnpart = static_cast<float*>(arena.alloc(lnpart_floats * sizeof(float)));
       m_act = arena.alloc(px * C * esz);
     }
     // fused decoupling loss (tcgen05 path): per-warp partial slots + one term per (step, layer, sample)
@@ -309,6 +310,10 @@ class PredRnnV2 : public Model {
     }
   }
 
+  // statistics slots per sample the tcgen05 epilogue of a G = 1 conv with `co` output channels writes (epilogue slot rule
+  // in common.h: ((tile in image) * n_tiles + N tile) * 8 + quadrant * 2 + half)
+  int ln_slots(int co) const { return ((hp_ + 15) / 16) * ((wp_ + 7) / 8) * conv_n_tiles(co, 1) * 8; }
+
   // LayerNorm affine of `key` ([kC, H, W] in the reference) repacked to the NHWC order of the raw conv outputs
   const float* ln_param(const std::string& key, int kc, cudaStream_t stream) {
     const float* src = hp(key);
@@ -330,16 +335,20 @@ class PredRnnV2 : public Model {
     const char* halo_env = getenv("VPK_TC_HALO");
     const bool fuse_stats = act.dtype != DT_F32 && backend == 0 && getenv("VPK_NO_FUSED_LN_STATS") == nullptr &&
                             (halo_env == nullptr || atoi(halo_env) != 0);
-    const int tiles_img = ((hp_ + 15) / 16) * ((wp_ + 7) / 8);
-    auto slots_of = [&](int co) {       // as lowering.cu's choose_cn for G = 1: N tiles of <= 256 columns, multiples of 16
-      int nt = std::max(1, (co + 255) / 256);
-      while (((co + nt - 1) / nt + 15) / 16 * 16 > 256) ++nt;
-      return tiles_img * nt * 8;
-    };
+    auto slots_of = [&](int co) { return ln_slots(co); };
+    // 16-bit mode: the weights of conv_x / conv_h / conv_m are split into a high and a low fp16 part (two products per tap
+    // over the same activation tile).  LayerNorm renormalises every conv output, and the rounding of the WEIGHTS -- a
+    // systematic perturbation repeated at every step -- is what drives the rollout error: with plain fp16 weights the
+    // tenth predicted frame of cfg 3's shape is 2.4e-2 off (bound 2e-2), with split weights 1.4e-2 (CPU emulation,
+    // tests/tools/ln_precision_probe.py; splitting the activations instead only gives 2.2e-2).  VPK_LN_WSPLIT=0: plain fp16.
+    const char* ws_env = getenv("VPK_LN_WSPLIT");
+    const bool w_split_on = act.dtype == DT_F16 && (ws_env == nullptr || atoi(ws_env) != 0);
     auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& wkey, float* out,
-                        float* stat, int nslots) {
+                        float* stat, int nslots, bool wsplit = false) {
       ConvArgs a{pre + name, B, hp_, wp_, ci, co, kk, 1, kk / 2, in, hp(pre + wkey), nullptr, ACT_NONE, out};
       a.out_f32_dense = true;
+      // (the step table holds at most kMaxSteps taps)
+      a.w_split = wsplit && w_split_on && ((ci + 63) / 64) * 2 * kk * kk <= kMaxSteps;
       ConvSpec sp = conv_spec(a, act, &oh, &ow);
       sp.is_gate_gemm = true;
       if (stat != nullptr) {
@@ -357,9 +366,11 @@ class PredRnnV2 : public Model {
     float* px_ = part;
     float* ph_ = px_ + static_cast<size_t>(B) * nsx * 2;
     float* pm_ = ph_ + static_cast<size_t>(B) * nsh * 2;
-    raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw, fuse_stats ? px_ : nullptr, nsx);
-    raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw, fuse_stats ? ph_ : nullptr, nsh);
-    raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw, fuse_stats ? pm_ : nullptr, nsm);
+    VPK_REQUIRE(static_cast<size_t>(B) * (static_cast<size_t>(nsx) + nsh + nsm) * 2 <= lnpart_floats && nso <= nsx,
+                "LayerNorm statistics regions exceed their buffer");
+    raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw, fuse_stats ? px_ : nullptr, nsx, true);
+    raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw, fuse_stats ? ph_ : nullptr, nsh, true);
+    raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw, fuse_stats ? pm_ : nullptr, nsm, true);
     const int HW = hp_ * wp_, CC = C, ns = num_sms, dt = act.dtype;
     if (!measure) {
       if (!fuse_stats) {
@@ -400,7 +411,8 @@ class PredRnnV2 : public Model {
 
  private:
   int p = 4, L = 3, k = 5, C = 128, cp = 16, hp_ = 16, wp_ = 16;
-  int n_terms = 1;
+  size_t lnpart_floats = 0;
+  int call_terms = 1;
   double* d_loss = nullptr;
 };
 

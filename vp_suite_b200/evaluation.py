@@ -131,3 +131,85 @@ def finalize_metrics(vec: torch.Tensor) -> dict:
     mse = torch.cumsum(vec[:P], 0) / (frames * n)
     psnr = -torch.cumsum(vec[P:2 * P], 0) / (frames * n)                # to_display(): higher is better
     return {"mse": mse.tolist(), "psnr": psnr.tolist(), "sequences": n}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Evaluation caller: the reference's per-metric, per-horizon loop with one `.item()` sync each
+# (vp_suite/measure/metric_provider.py:56-71, called per datapoint from vp_suite/vpsuite.py:536-550) replaced by ONE pass
+# of the on-device reduction kernels over (pred, target) and ONE device-to-host read per call.
+# ----------------------------------------------------------------------------------------------------------------------
+NATIVE_METRICS = ("mse", "psnr", "ssim")      #: metric ids this provider computes; "lpips" / "fvd" need pretrained networks
+
+
+class NativeMetricProvider:
+    """Drop-in for ``vp_suite.measure.metric_provider.PredictionMetricProvider`` (same constructor config keys --
+    ``device``, ``metrics``, ``img_c`` -- same ``get_metrics`` signature and return format: a list, one dict per
+    prediction horizon, ``"<id> (↑|↓)" -> displayed value``).
+
+    All horizons come from one set of per-frame partial sums (``metric_partial_sums`` / ``ssim_partial_sums``): horizon k
+    is the prefix mean over the first k frames, which is exactly what the reference computes by re-running every measure
+    on ``pred[:, :k]`` (MSE image_wise.py:19-31 + base_measure.py:54-57, PSNR image_wise.py:65-75 are means over frames of
+    per-frame values).  SSIM: piqa's algorithm restated, value parity unpinned (see include/vpk.h); as in the reference it
+    is only produced for 3-channel frames.  With a process group initialised and ``reduce=True`` the sums are
+    all-reduced first, so every rank gets the metrics of the GLOBAL batch."""
+    ARROWS = {"mse": "↓", "psnr": "↑", "ssim": "↑"}
+
+    def __init__(self, config: dict):
+        self.device = config["device"]
+        wanted = NATIVE_METRICS if config["metrics"] == "all" else tuple(config["metrics"])
+        unsupported = [k for k in wanted if k not in NATIVE_METRICS and k not in ("fvd", "lpips", "l1", "smooth_l1")]
+        if unsupported:
+            raise KeyError(f"unknown metric ids {unsupported}")
+        self.metric_ids = [k for k in wanted if k in NATIVE_METRICS]
+        self.skipped = [k for k in wanted if k not in NATIVE_METRICS]     # left to the reference's own provider
+        self.img_c = config.get("img_c")
+
+    def get_metrics(self, pred, target, frames=None, all_frame_cnts=False, reduce=False):
+        if pred.ndim != 5 or target.ndim != 5:
+            raise ValueError("Input tensors expected to be 5-dimensional!")           # metric_provider.py:50-53
+        if pred.shape != target.shape:
+            raise ValueError("Output images and target images are of different shape!")
+        frames = frames or pred.shape[1]
+        pred, target = pred[:, :frames], target[:, :frames]
+        vec = metric_partial_sums(pred, target)
+        want_ssim = "ssim" in self.metric_ids
+        if want_ssim and pred.shape[2] != 3:                                           # image_wise.py:114-115
+            raise ValueError("Structural Similarity (SSIM) needs 3-channel images with the channels at dim 2")
+        if want_ssim:
+            vec = torch.cat([vec, ssim_partial_sums(pred, target)])
+        if reduce:
+            vec = all_reduce_sums(vec)
+        host = vec.cpu()                                                               # the one device-to-host read
+        P = frames
+        res = finalize_metrics(host[:2 * P + 1])
+        if want_ssim:
+            res["ssim"] = finalize_ssim(host[2 * P + 1:], res["sequences"])
+        horizons = range(1, P + 1) if all_frame_cnts else [P]
+        return [{f"{k} ({self.ARROWS[k]})": res[k][h - 1] for k in self.metric_ids} for h in horizons]
+
+
+def evaluate_loader(model, loader, config, metric_provider=None, max_datapoints=None):
+    """The reference's test loop for one model (vp_suite/vpsuite.py:533-550): per datapoint
+    ``unpack_data -> model.eval() -> model(input, pred_frames) -> get_metrics(all_frame_cnts=True)``, then the
+    per-horizon means over the datapoints (vpsuite.py:574-585).  Returns (mean metric dict per horizon, per-datapoint list).
+    ``metric_provider`` defaults to the on-device ``NativeMetricProvider``; the reference's ``PredictionMetricProvider``
+    can be passed instead."""
+    provider = metric_provider or NativeMetricProvider(config)
+    per_dp = []
+    with torch.no_grad():
+        for i, data in enumerate(loader):
+            if max_datapoints is not None and i >= max_datapoints:
+                break
+            inp, target, actions = model.unpack_data(data, config)
+            model.eval()
+            if getattr(model, "use_actions", False):
+                pred, _ = model(inp, pred_frames=config["pred_frames"], actions=actions)
+            else:
+                pred, _ = model(inp, pred_frames=config["pred_frames"])
+            model.train()
+            per_dp.append(provider.get_metrics(pred, target, all_frame_cnts=True))
+    if not per_dp:
+        raise RuntimeError("loaded dataset does not contain any data (len < 1)")          # vpsuite.py:520-521
+    keys = per_dp[0][0].keys()
+    means = [{k: sum(dp[f][k] for dp in per_dp) / len(per_dp) for k in keys} for f in range(len(per_dp[0]))]
+    return means, per_dp

@@ -29,14 +29,32 @@ class _NativeCell:
         self._cell = None
         self._cell_versions = None
 
-    def _cell_handle(self):
+    def __getstate__(self):                       # pickling drops the native handle; it is rebuilt on the next call
+        state = dict(self.__dict__)
+        state.pop("_cell", None)
+        state.pop("_cell_versions", None)
+        return state
+
+    def __setstate__(self, state):
+        nn.Module.__setstate__(self, state)
+        self._cell_init()
+
+    def _cell_handle(self, device):
+        """Handle with current weights, living on ``device`` (libvpk allocates on the calling thread's current device)."""
         versions = tuple((k, v._version, v.data_ptr()) for k, v in self.state_dict().items()) + (self.precision,
-                                                                                               self.backend)
+                                                                                               self.backend, str(device))
         if self._cell is None or versions != self._cell_versions:
             self._cell_release()
-            self._cell = self._cell_create()
+            with torch.cuda.device(device):
+                self._cell = self._cell_create()
             self._cell_versions = versions
         return self._cell
+
+    @staticmethod
+    def _step(device, fn, *args):
+        """One native cell step with the tensors' device current."""
+        with torch.cuda.device(device):
+            N.check(fn(*args))
 
     def _cell_release(self):
         if getattr(self, "_cell", None) is not None:
@@ -64,7 +82,7 @@ class _NativeCell:
         return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
-class ConvLSTMCell(nn.Module, _NativeCell):
+class ConvLSTMCell(_NativeCell, nn.Module):
     """conv_lstm_ndrplz.py:7-48: gate conv over cat(x, h), split order (i, f, o, g), no peepholes."""
 
     def __init__(self, input_dim, hidden_dim, kernel_size, bias):
@@ -93,10 +111,10 @@ class ConvLSTMCell(nn.Module, _NativeCell):
         if self._hw != tuple(x.shape[-2:]):
             self._hw = tuple(x.shape[-2:])
             self._cell_release()
-        cell = self._cell_handle()
+        cell = self._cell_handle(x.device)
         h_next, c_next = torch.empty_like(h), torch.empty_like(c)
-        N.check(N.lib().vpk_convlstm_cell_step(cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), None, None, None,
-                                               N.ptr(h_next), N.ptr(c_next), self._stream(x)))
+        self._step(x.device, N.lib().vpk_convlstm_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), None, None,
+                   None, N.ptr(h_next), N.ptr(c_next), self._stream(x))
         return h_next, c_next
 
     def init_hidden(self, batch_size, image_size):                       # conv_lstm_ndrplz.py:45-48
@@ -106,7 +124,7 @@ class ConvLSTMCell(nn.Module, _NativeCell):
                 torch.zeros(batch_size, self.hidden_dim, height, width, device=dev))
 
 
-class ConvLSTM(VPModelBlock, _NativeCell):
+class ConvLSTM(_NativeCell, VPModelBlock):
     """conv_lstm_hzzone.py:7-70: whole-sequence driver of the Shi-et-al. ConvLSTM with peepholes."""
     NAME = "ConvLSTM (Shi et al.)"
     PAPER_REFERENCE = "https://arxiv.org/abs/1506.04214"
@@ -146,15 +164,14 @@ class ConvLSTM(VPModelBlock, _NativeCell):
             h, c = states
             b = h.shape[0]
         h, c = self._dev(h), self._dev(c)
-        cell = self._cell_handle()
+        cell = self._cell_handle(h.device)
         peep = [self._dev(p)[0] for p in (self.Wci, self.Wcf, self.Wco)]
         outputs = []
         for t in range(seq_len):                                         # conv_lstm_hzzone.py:52-69
             x = None if inputs is None else self._dev(inputs[:, t])      # None = all-zero input (:54-56)
             h_new, c_new = torch.empty_like(h), torch.empty_like(c)
-            N.check(N.lib().vpk_convlstm_cell_step(cell, b, N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(peep[0]),
-                                                   N.ptr(peep[1]), N.ptr(peep[2]), N.ptr(h_new), N.ptr(c_new),
-                                                   self._stream(h)))
+            self._step(h.device, N.lib().vpk_convlstm_cell_step, cell, b, N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(peep[0]),
+                       N.ptr(peep[1]), N.ptr(peep[2]), N.ptr(h_new), N.ptr(c_new), self._stream(h))
             h, c = h_new, c_new
             outputs.append(h)
         return torch.stack(outputs, dim=1), (h, c)
@@ -196,7 +213,7 @@ class SingleStepConvLSTM(nn.Module):
         self.H, self.C = hidden
 
 
-class SpatioTemporalLSTMCell(VPModelBlock, _NativeCell):
+class SpatioTemporalLSTMCell(_NativeCell, VPModelBlock):
     """model_blocks/predrnn.py:7-83, layer_norm False or True."""
     NAME = "Spatio-Temporal LSTM Cell"
     PAPER_REFERENCE = "https://arxiv.org/abs/2103.09504"
@@ -238,14 +255,14 @@ class SpatioTemporalLSTMCell(VPModelBlock, _NativeCell):
 
     def forward(self, x_t, h_t, c_t, m_t):
         x, h, c, m = (self._dev(t) for t in (x_t, h_t, c_t, m_t))
-        cell = self._cell_handle()
+        cell = self._cell_handle(x.device)
         outs = [torch.empty_like(h) for _ in range(5)]
-        N.check(N.lib().vpk_stlstm_cell_step(cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(m),
-                                             *[N.ptr(o) for o in outs], self._stream(x)))
+        self._step(x.device, N.lib().vpk_stlstm_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(m),
+                   *[N.ptr(o) for o in outs], self._stream(x))
         return tuple(outs)                                               # h', c', m', delta_c, delta_m (predrnn.py:82)
 
 
-class PhyCell_Cell(VPModelBlock, _NativeCell):
+class PhyCell_Cell(_NativeCell, VPModelBlock):
     """model_blocks/phydnet.py:13-62 with action_conditional=False."""
     NAME = "PhyCell - Cell"
     PAPER_REFERENCE = "https://arxiv.org/abs/2003.01460"
@@ -284,9 +301,9 @@ class PhyCell_Cell(VPModelBlock, _NativeCell):
         if self._hw != tuple(x.shape[-2:]):
             self._hw = tuple(x.shape[-2:])
             self._cell_release()
-        cell = self._cell_handle()
+        cell = self._cell_handle(x.device)
         out = torch.empty_like(h)
-        N.check(N.lib().vpk_phycell_cell_step(cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(out), self._stream(x)))
+        self._step(x.device, N.lib().vpk_phycell_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(out), self._stream(x))
         return out
 
 

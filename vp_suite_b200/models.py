@@ -38,14 +38,15 @@ def _stage(layers):
 
 
 def _act_code(name):
-    if "leaky" in name:
-        return 1
+    """ef_blocks.py:32-46 tests 'relu' BEFORE 'leaky': a layer called '*leaky_relu*' is a plain ReLU there."""
     if "relu" in name:
         return 3
+    if "leaky" in name:
+        return 1
     return 0
 
 
-class EF_ConvLSTM(VPModel, NativeRollout):
+class EF_ConvLSTM(NativeRollout, VPModel):
     NAME = "EF-ConvLSTM (Shi et al.)"
     PAPER_REFERENCE = "https://arxiv.org/abs/1506.04214"
     CODE_REFERENCE = "https://github.com/Hzzone/Precipitation-Nowcasting"
@@ -210,7 +211,7 @@ class EF_ConvLSTM(VPModel, NativeRollout):
         return pred, None                                                # ef_blocks.py:184-187
 
 
-class PredRNN_V2(VPModel, NativeRollout):
+class PredRNN_V2(NativeRollout, VPModel):
     NAME = "PredRNN++"
     PAPER_REFERENCE = "https://arxiv.org/abs/2103.09504"
     CODE_REFERENCE = "https://github.com/thuml/predrnn-pytorch"
@@ -323,7 +324,7 @@ def _gn_divisor(x):
     return x // sq
 
 
-class PhyDNet(VPModel, NativeRollout):
+class PhyDNet(NativeRollout, VPModel):
     NAME = "PhyDNet"
     PAPER_REFERENCE = "https://arxiv.org/abs/2003.01460"
     CODE_REFERENCE = "https://github.com/vincent-leguen/PhyDNet"
