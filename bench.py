@@ -9,15 +9,22 @@ BASELINE config 5 (convlstm-shi, 3x128x128, 10 context + 20 predicted frames), s
 every rank processes `--seqs-per-gpu` sequences (weak scaling; 512/GPU = the named global batch 4096 at 8 GPUs).
 The rollout has no inter-GPU traffic; NCCL only sums the evaluation metrics (MSE / PSNR / SSIM partial sums).
 
-Printed JSON (rank 0, one line): metric/value/unit, ms_per_step, e2e (host buffers through the C ABI, H2D/D2H
-inside the timed region), roofline (gate-GEMM kernels: algorithmic FLOPs / CUDA-event time vs the measured bf16
-peak), cpu_baseline (the oracle's CPU port on a bounded sample), clocks, gpu_launches.
+Printed JSON (rank 0, ONE line): metric/value/unit, ms_per_step, e2e (host buffers through the C ABI, H2D/D2H inside
+the timed region), roofline (gate-GEMM kernels: algorithmic FLOPs / CUDA-event time vs the measured bf16 peak, plus the
+burst fraction and the WHOLE-step fraction), cpu_baseline, clocks, gpu_launches, env (every VPK_* switch that is set),
+and at 1 GPU also
+  per_config          the other BASELINE configs (cfg1-4, and the LayerNorm widening cfg3ln) measured the same way in the
+                      same process: ms, frames/s, whole-model and gate-GEMM fractions, e2e, >= 20 clock samples each
+  gpu_eager_baseline  the UNMODIFIED reference (baseline/_ref) on the same GPU in PyTorch eager mode (cuDNN / cuBLAS),
+                      fp32 / TF32 / bf16 autocast, bounded batch -- the real bar on the box
 
-`--impl reference` times the reference's CPU implementation of the same path -- the oracle port (oracle/), since
-the Python reference checkout does not travel to the GPU box -- on the host cores, on the same workload/metric.
+`--impl reference` times the reference's own CPU implementation of the same path -- the unmodified reference from
+baseline/_ref when present (kind "reference"), else the oracle port (kind "port") -- on the host cores, with all threads,
+W warm-up + K timed forwards of a bounded batch of the same workload.
 """
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -38,9 +45,12 @@ WORKLOADS = {
     "cfg3ln": ("predrnn-pp", (1, 64, 64), 10, 10, 256, "predrnn-pp layer_norm=True 1x64x64 10+10"),
 }
 WORKLOAD_KW = {"cfg3ln": {"layer_norm": True}}          # extra model kwargs of a workload
-# "required" GFLOP per sequence of the whole rollout; informational
+# "required" GFLOP per sequence of the whole rollout
 REQUIRED_GFLOP_PER_SEQ = {"cfg1": 81.03, "cfg2": 26.319, "cfg3": 168.787, "cfg4": 17.74, "cfg5": 524.31,
                           "cfg3ln": 168.787}
+# bounded batch of the CPU reference arm / cpu_baseline and of the same-GPU eager baseline
+CPU_BATCH = {"cfg5": 2}
+EAGER_BATCH = {"cfg1": 8, "cfg2": 64, "cfg3": 64, "cfg3ln": 64, "cfg4": 64, "cfg5": 16}
 
 
 def parse():
@@ -56,6 +66,7 @@ def parse():
     p.add_argument("--graph", type=int, default=-1, help="CUDA-graph replay (default: on for small batches)")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-per-config", action="store_true", help="skip the per_config / gpu_eager_baseline blocks")
     return p.parse_args()
 
 
@@ -68,30 +79,41 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
+def vpk_env():
+    """Every VPK_* switch set in the environment (the library reads some of them; a stray one must be visible)."""
+    return {k: v for k, v in sorted(os.environ.items()) if k.startswith("VPK_")}
+
+
 class ClockSampler:
     """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=100):
         self.index = index
+        self.period_ms = period_ms
         self.lines = []
         self.proc = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self):
+        """Samples taken so far are discarded (they belong to whatever ran before the timed region)."""
+        self.t_mark = time.perf_counter()
 
     def stop(self):
         if self.proc is None:
@@ -101,9 +123,12 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
+        t0 = getattr(self, "t_mark", 0.0)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in self.lines:
+            if ts < t0:
+                continue
             parts = [p.strip() for p in ln.split(",")]
             if len(parts) < 7:
                 continue
@@ -120,33 +145,74 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_reference_throughput(workload, seconds_budget=20.0, threads=None):
-    """Times the oracle's CPU port of the rollout on a bounded sample; returns (frames/s, sample description, cores)."""
+# ----------------------------------------------------------------------------------------------------------------------
+# reference implementations (CPU arm, cpu_baseline, same-GPU eager baseline)
+# ----------------------------------------------------------------------------------------------------------------------
+def _reference_forward(workload, device):
+    """(forward(x, pred) -> frames, kind, batch-first input builder): the unmodified reference from baseline/_ref when it
+    is present (kind "reference"), else the oracle's port of the same rollout (kind "port").  cfg2 is OUR composition of
+    reference blocks (the reference registers no such model): it is driven through the reference PhyDNet's own
+    sub-modules when the reference is present."""
     import torch
-    from oracle import models as OM
-    from oracle.weights import synth_state_dict, synth_frames
-    from oracle.shapes import SHAPES
+    from oracle import ref_shim
+    from oracle.weights import synth_state_dict
     key, img, ctx, pred, _, _ = WORKLOADS[workload]
+    kw = WORKLOAD_KW.get(workload, {})
+    if ref_shim.available():
+        classes = ref_shim.load_reference()
+        torch.manual_seed(0)
+        ref_key = "phy" if key == "convlstm-branch" else key
+        m = classes[ref_key](device, img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0], **kw).to(device).eval()
+        if key == "convlstm-branch":
+            def fwd(x, p):                     # oracle/make_golden.py: run_branch, on the reference's sub-modules
+                t = x.shape[1]
+
+                def step(frame, first):
+                    er = m.encoder_Er(m.encoder_E(frame))
+                    _, out = m.convcell(er, None, first)
+                    return torch.sigmoid(m.decoder_D(m.decoder_Dr(out[-1])))
+                for ei in range(t - 1):
+                    step(x[:, ei], ei == 0)
+                frame, outs = x[:, t - 1], []
+                for di in range(p):
+                    frame = step(frame, t == 1 and di == 0)
+                    outs.append(frame)
+                return torch.stack(outs, 1)
+        else:
+            def fwd(x, p):
+                return m(x, pred_frames=p)[0]
+        return fwd, "reference"
+    from oracle import models as OM
+    from oracle.shapes import SHAPES
+    sd = synth_state_dict(SHAPES[key](img, kw) if kw else SHAPES[key](img), 0, 1.0)
+    sd = {k: v.to(device) for k, v in sd.items()}
+    f = OM.FORWARDS[key]
+    return (lambda x, p: f(sd, x, p)[0]), "port"
+
+
+def cpu_reference_run(workload, warmup, steps, threads=None):
+    """The reference's CPU path on a bounded batch: `warmup` untimed + `steps` timed forwards; returns a dict."""
+    import torch
+    from oracle.weights import synth_frames
+    key, img, ctx, pred, _, desc = WORKLOADS[workload]
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
-    kw = WORKLOAD_KW.get(workload)
-    sd = synth_state_dict(SHAPES[key](img, kw) if kw else SHAPES[key](img), 0, 1.0)
-    b = 2 if workload == "cfg5" else 8
+    b = CPU_BATCH.get(workload, 8)
     t_in = ctx + (pred if key == "predrnn-pp" else 0)
     x = synth_frames(b, t_in, *img, seed=1234)
-    fwd = OM.FORWARDS[key]
+    fwd, kind = _reference_forward(workload, "cpu")
+    times = []
     with torch.no_grad():
-        t0 = time.perf_counter()
-        fwd(sd, x, pred)
-        first = time.perf_counter() - t0
-        reps = max(1, min(5, int(seconds_budget / max(first, 1e-3)) - 1))
-        best = first
-        for _ in range(reps):
+        for i in range(warmup + steps):
             t0 = time.perf_counter()
-            fwd(sd, x, pred)
-            best = min(best, time.perf_counter() - t0)
-    sample = f"{WORKLOADS[workload][5]} at batch {b}, best of {reps + 1} forwards, torch CPU fp32"
-    return b * pred / best, sample, threads, best
+            fwd(x, pred)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    mean = sum(times) / len(times)
+    what = "unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port"
+    return {"fps": b * pred / mean, "sec_per_step": mean, "best_sec": min(times), "batch": b, "cores": threads, "kind": kind,
+            "sample": f"{desc} at batch {b}: {warmup} warm-up + {steps} timed forwards (mean), {what}, torch CPU fp32, "
+                      f"{threads} threads"}
 
 
 def run_reference(args):
@@ -154,19 +220,186 @@ def run_reference(args):
     if rank != 0:
         return
     key, img, ctx, pred, _, desc = WORKLOADS[args.workload]
-    # each "step" is one bounded-sample forward; warm-up + K steps stay within a few minutes
-    fps, sample, cores, sec = cpu_reference_throughput(args.workload, seconds_budget=8.0 * max(1, args.steps))
+    r = cpu_reference_run(args.workload, args.warmup, args.steps)
     line = {
-        "impl": "reference", "metric": "predicted frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": "predicted frames/sec", "value": r["fps"], "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["sec_per_step"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": desc, "note": "reference CPU path = oracle port (the Python reference checkout does "
-                                             "not travel to the GPU box); throughput is batch-linear on CPU"},
-        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "config": {"workload": desc, "context": ctx, "pred": pred, "seqs_per_step": r["batch"],
+                   "note": "each step = one forward of the reference's CPU path over a bounded batch of the same workload "
+                           "(CPU throughput is batch-linear; the GPU arm runs 512 sequences per step)"},
+        "cpu_baseline": {"value": r["fps"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["fps"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "env": vpk_env(),
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_baseline(workload, reps=2):
+    """The reference on the SAME GPU in PyTorch eager mode (one cuDNN / cuBLAS / ATen kernel per torch op), inputs and
+    weights resident, CUDA events, cudnn.benchmark on: fp32 (TF32 off), TF32, bf16 autocast.  Bounded batch."""
+    import torch
+    from oracle.weights import synth_frames
+    key, img, ctx, pred, _, desc = WORKLOADS[workload]
+    b = EAGER_BATCH[workload]
+    x = synth_frames(b, ctx + (pred if key == "predrnn-pp" else 0), *img, seed=1234).cuda()
+    out = {"batch": b, "unit": "frames/s"}
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
+    try:
+        fwd, kind = _reference_forward(workload, "cuda")
+        out["impl"] = ("unmodified reference (baseline/_ref)" if kind == "reference" else "oracle port") + \
+            ", torch eager on the same GPU (cuDNN / cuBLAS), best of %d after 2 warm-ups" % reps
+        for mode in ("fp32", "tf32", "bf16_autocast"):
+            tf32 = mode != "fp32"
+            torch.backends.cudnn.allow_tf32 = tf32
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.benchmark = True
+            times = []
+            with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=(mode == "bf16_autocast")):
+                for i in range(2 + reps):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    torch.cuda.synchronize()
+                    e0.record()
+                    fwd(x, pred)
+                    e1.record()
+                    torch.cuda.synchronize()
+                    if i >= 2:
+                        times.append(e0.elapsed_time(e1))
+            out[mode] = round(b * pred / (min(times) * 1e-3), 1)
+    except Exception as e:  # noqa: BLE001  (a reported baseline: never takes the bench line down)
+        out["error"] = repr(e)[:200]
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark = saved
+        torch.cuda.empty_cache()
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+class Runner:
+    """One workload on this rank: model, resident and host inputs, timed device / host-entry steps."""
+
+    def __init__(self, workload, args, dev, rank, world, seqs=0):
+        import torch
+        import vp_suite_b200 as V
+        self.torch, self.world, self.dev = torch, world, dev
+        key, img, ctx, pred, default_b, desc = WORKLOADS[workload]
+        self.workload, self.key, self.img, self.ctx, self.pred, self.desc = workload, key, img, ctx, pred, desc
+        self.B = seqs or default_b
+        self.t_in = ctx + (pred if key == "predrnn-pp" else 0)
+        self.use_graph = args.graph if args.graph >= 0 else int(self.B <= 32)
+        torch.manual_seed(0)      # random-init weights of the named architecture (torch default init, as the reference)
+        self.model = V.MODEL_CLASSES[key](str(dev), img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
+                                          precision=args.precision, max_microbatch=args.microbatch,
+                                          use_cuda_graph=bool(self.use_graph), **WORKLOAD_KW.get(workload, {})).eval()
+        g = torch.Generator(device="cpu").manual_seed(1234 + rank)
+        self.x_host = torch.rand((self.B, self.t_in, *img), generator=g, dtype=torch.float32).pin_memory()
+        tgt_host = torch.rand((self.B, pred, *img), generator=g, dtype=torch.float32)
+        self.x_dev = self.x_host.to(dev)
+        self.tgt_dev = tgt_host.to(dev)
+        chw = img[0] * img[1] * img[2]
+        # bytes the host entry really copies: predrnn-pp reads only the context frames of its context + target input
+        self.in_bytes = self.B * ctx * chw * 4 if key == "predrnn-pp" else self.x_host.numel() * 4
+        self.out_bytes = self.B * pred * chw * 4
+
+    def step_device(self):
+        """One rollout + the evaluation's metric reduction (per-horizon MSE / PSNR partial sums, one NCCL all-reduce)."""
+        from vp_suite_b200 import evaluation as E
+        with self.torch.no_grad():
+            out, _ = self.model(self.x_dev, pred_frames=self.pred)
+        return E.all_reduce_sums(E.metric_partial_sums(out, self.tgt_dev))
+
+    def step_host(self):
+        out, _ = self.model.forward_host(self.x_host, pred_frames=self.pred)
+        return out
+
+    def barrier(self):
+        import torch.distributed as dist
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed(self, fn, steps):
+        import torch.distributed as dist
+        torch = self.torch
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        wall = (time.perf_counter() - t0) * 1e3
+        dev_ms = e0.elapsed_time(e1)
+        self.barrier()
+        t = torch.tensor([dev_ms, wall], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0]), float(t[1]), r
+
+    def gemm_stats(self):
+        torch = self.torch
+        self.model.set_timing(True)
+        with torch.no_grad():
+            self.model(self.x_dev, pred_frames=self.pred)
+            torch.cuda.synchronize()
+            gs = self.model.last_gemm_stats()
+        self.model.set_timing(False)
+        return gs
+
+    def fractions(self, ms_per_step, gs, peaks):
+        """Whole-step and gate-GEMM TFLOP/s against the measured burst and sustained bf16 peaks."""
+        burst, sus = peaks.get("bf16_tflops", 1590.0), peaks.get("bf16_tflops_sustained", 1400.0)
+        whole = REQUIRED_GFLOP_PER_SEQ[self.workload] * self.B / ms_per_step                  # GFLOP / ms = TFLOP/s
+        gemm = gs["flops"] / max(gs["ms"], 1e-9) * 1e-9 if gs["launches"] else 0.0
+        return {"whole_step_tflops": whole, "whole_step_frac_burst": whole / burst, "whole_step_frac_sustained": whole / sus,
+                "gate_gemm_tflops": gemm, "gate_gemm_frac_burst": gemm / burst, "gate_gemm_frac_sustained": gemm / sus,
+                "gate_gemm_share_of_step": gs["ms"] / ms_per_step if ms_per_step else None}
+
+
+def per_config_block(args, dev, rank, peaks, min_seconds=2.4):
+    """cfg1-4 (+ cfg3ln) in the same process, each timed for >= `min_seconds` on the device so that >= 20 nvidia-smi
+    samples (100 ms period) fall inside its timed region."""
+    import torch
+    out = {}
+    for w in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg3ln"):
+        if w == args.workload:
+            continue
+        try:
+            r = Runner(w, args, dev, rank, 1)
+            for _ in range(3):
+                r.step_device()
+            ms1, _, _ = r.timed(r.step_device, 2)
+            steps = max(5, int(math.ceil(min_seconds * 1e3 / max(ms1 / 2, 1e-3))))
+            sampler = ClockSampler(dev.index, 50).start()
+            time.sleep(0.15)
+            sampler.mark()
+            dev_ms, _, _ = r.timed(r.step_device, steps)
+            clocks = sampler.stop()
+            ms = dev_ms / steps
+            gs = r.gemm_stats()
+            for _ in range(2):
+                r.step_host()
+            _, wall_ms, _ = r.timed(r.step_host, max(3, steps // 4))
+            e2e_ms = wall_ms / max(3, steps // 4)
+            entry = {"workload": r.desc, "seqs": r.B, "steps": steps, "ms_per_step": ms, "value": r.B * r.pred / (ms * 1e-3),
+                     "unit": "frames/s", "cuda_graph": bool(r.use_graph),
+                     "e2e": {"value": r.B * r.pred / (e2e_ms * 1e-3), "ms_per_step": e2e_ms,
+                             "h2d_bytes_per_step": r.in_bytes, "d2h_bytes_per_step": r.out_bytes},
+                     "gpu_launches_per_step": int(r.model.last_launch_count()) + 2,
+                     "required_gflop_per_seq": REQUIRED_GFLOP_PER_SEQ[w], **r.fractions(ms, gs, peaks), "clocks": clocks}
+            del r
+            torch.cuda.empty_cache()
+            if not args.no_cpu_baseline:
+                entry["gpu_eager_baseline"] = gpu_eager_baseline(w)
+            out[w] = entry
+        except Exception as e:  # noqa: BLE001  (the main line must survive a failing side config -- and show the failure)
+            out[w] = {"error": repr(e)[:300]}
+            torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -177,7 +410,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    import vp_suite_b200 as V
     from vp_suite_b200 import evaluation as E
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -203,66 +435,18 @@ def main():
             os.dup2(saved, 1)
             os.close(saved)
 
-    key, img, ctx, pred, default_b, desc = WORKLOADS[args.workload]
-    B = args.seqs_per_gpu or default_b
-    t_in = ctx + (pred if key == "predrnn-pp" else 0)
-    use_graph = args.graph if args.graph >= 0 else int(B <= 32)
-    torch.manual_seed(0)      # random-init weights of the named architecture (torch default init, as the reference)
-    model = V.MODEL_CLASSES[key](f"cuda:{local}", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
-                                 precision=args.precision, max_microbatch=args.microbatch,
-                                 use_cuda_graph=bool(use_graph), **WORKLOAD_KW.get(args.workload, {})).eval()
-
-    g = torch.Generator(device="cpu").manual_seed(1234 + rank)
-    x_host = torch.rand((B, t_in, *img), generator=g, dtype=torch.float32).pin_memory()
-    tgt_host = torch.rand((B, pred, *img), generator=g, dtype=torch.float32)
-    x_dev = x_host.to(dev)
-    tgt_dev = tgt_host.to(dev)
-    # bytes the host entry really copies: predrnn-pp reads only the context frames of its context + target input
-    in_bytes = B * ctx * img[0] * img[1] * img[2] * 4 if key == "predrnn-pp" else x_host.numel() * 4
-    out_bytes = B * pred * img[0] * img[1] * img[2] * 4
-
-    def metrics_reduce(pred_frames):
-        """Per-horizon MSE / PSNR partial sums, summed over ranks with one NCCL all-reduce (vp_suite_b200.evaluation)."""
-        return E.all_reduce_sums(E.metric_partial_sums(pred_frames, tgt_dev))
-
-    def step_device():
-        with torch.no_grad():
-            out, _ = model(x_dev, pred_frames=pred)
-        return metrics_reduce(out)
-
-    def step_host():
-        out, _ = model.forward_host(x_host, pred_frames=pred)
-        return out
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps):
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            r = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        wall = (time.perf_counter() - t0) * 1e3
-        dev_ms = e0.elapsed_time(e1)
-        barrier()
-        t = torch.tensor([dev_ms, wall], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t[0]), float(t[1]), r
+    peaks, peak_kind = load_peaks()
+    r = Runner(args.workload, args, dev, rank, world, args.seqs_per_gpu)
+    key, img, ctx, pred, B, t_in, desc = r.key, r.img, r.ctx, r.pred, r.B, r.t_in, r.desc
+    model = r.model
 
     for _ in range(args.warmup):
-        step_device()
+        r.step_device()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    dev_ms, _, metric_vec = timed(step_device, args.steps)
+        sampler.mark()
+    dev_ms, _, metric_vec = r.timed(r.step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     launches = (model.last_launch_count() + 2) * args.steps       # rollout kernels + the two metric-reduction kernels
     ms_per_step = dev_ms / args.steps
@@ -270,15 +454,11 @@ def main():
     value = frames / (ms_per_step * 1e-3)
 
     # ---- roofline of the dominant kernel (gate GEMMs): events around every launch, same steps ----
-    model.set_timing(True)
-    with torch.no_grad():
-        model(x_dev, pred_frames=pred)
-        torch.cuda.synchronize()
-        gs = model.last_gemm_stats()
-    model.set_timing(False)
-    peaks, peak_kind = load_peaks()
-    peak = peaks.get("bf16_tflops_sustained" if ms_per_step > 50 else "bf16_tflops", 1590.0)
-    achieved = gs["flops"] / max(gs["ms"], 1e-9) * 1e-9 if gs["launches"] else 0.0     # TFLOP/s
+    gs = r.gemm_stats()
+    fr = r.fractions(ms_per_step, gs, peaks)
+    sustained = ms_per_step > 50            # a kernel timed inside a long step runs at the power-capped (sustained) clocks
+    peak = peaks.get("bf16_tflops_sustained" if sustained else "bf16_tflops", 1590.0)
+    achieved = fr["gate_gemm_tflops"]
     traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if os.path.exists(tpath) and args.workload == "cfg5":
@@ -291,20 +471,26 @@ def main():
                         f"algorithmic bytes of that launch = {tj['algorithmic_bytes_per_position'] * tj['positions_per_sequence'] * mb:.3e}")
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
-                "kernel": "conv_halo_kernel / conv_tc2_kernel <EPI_LSTM> (tcgen05 ConvLSTM gate GEMMs + fused state update)"
-                if key != "predrnn-pp" else "conv_tc2_kernel / conv_halo_kernel <EPI_ST_*> (tcgen05 ST-LSTM gate GEMMs + fused update)",
+                "kernel": "conv_halo_kernel <EPI_LSTM> (tcgen05 ConvLSTM gate GEMMs + fused state update)"
+                if key != "predrnn-pp" else "conv_halo_kernel <EPI_ST_*> (tcgen05 ST-LSTM gate GEMMs + fused update)",
                 "gemm_launches_per_step": gs["launches"], "gemm_ms_per_step": gs["ms"],
-                "gemm_share_of_step": gs["ms"] / ms_per_step if ms_per_step else None,
+                "gemm_share_of_step": fr["gate_gemm_share_of_step"],
                 "algorithmic_gflop_per_step": gs["flops"] * 1e-9,
+                "frac_note": "`frac` is the GATE-GEMM kernels only; the whole rollout (stage convs, deconvs, conversions "
+                             "included) is whole_step_*",
+                "frac_burst": fr["gate_gemm_frac_burst"], "frac_sustained": fr["gate_gemm_frac_sustained"],
+                "whole_step_tflops": fr["whole_step_tflops"], "whole_step_frac_burst": fr["whole_step_frac_burst"],
+                "whole_step_frac_sustained": fr["whole_step_frac_sustained"],
+                "peak_burst": peaks.get("bf16_tflops"), "peak_sustained": peaks.get("bf16_tflops_sustained"),
                 "peak_source": f"{peak_kind} MEASURED_PEAKS.json "
-                               f"({'sustained' if ms_per_step > 50 else 'burst'} bf16 cuBLAS)"}
+                               f"({'sustained' if sustained else 'burst'} bf16 cuBLAS)"}
 
     # ---- SSIM sums of one (untimed) rollout, 3-channel workloads: the third metric the evaluation all-reduces ----
     ssim_disp = None
     if img[0] == 3:
         with torch.no_grad():
-            out, _ = model(x_dev, pred_frames=pred)
-            ssim_vec = E.all_reduce_sums(E.ssim_partial_sums(out, tgt_dev))
+            out, _ = model(r.x_dev, pred_frames=pred)
+            ssim_vec = E.all_reduce_sums(E.ssim_partial_sums(out, r.tgt_dev))
         ssim_disp = E.finalize_ssim(ssim_vec, B * world)
         del out
 
@@ -312,38 +498,51 @@ def main():
     e2e = None
     if not args.no_e2e:
         for _ in range(min(args.warmup, 2)):
-            step_host()
-        _, wall_ms, _ = timed(step_host, args.steps)
+            r.step_host()
+        _, wall_ms, _ = r.timed(r.step_host, args.steps)
         e2e = {"value": frames / (wall_ms / args.steps * 1e-3), "unit": "frames/s",
-               "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": out_bytes,
+               "h2d_bytes_per_step": r.in_bytes, "d2h_bytes_per_step": r.out_bytes,
                "ms_per_step": wall_ms / args.steps,
                "path": "vpk_model_forward_host: pinned host x -> H2D -> rollout -> D2H host frames, per microbatch"}
 
-    cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        fps, sample, cores, _ = cpu_reference_throughput(args.workload)
-        cpu_baseline = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample}
+    ev = E.finalize_metrics(metric_vec) if rank == 0 else None
+    small = B * t_in * img[0] * img[1] * img[2] * 4 <= 2.6e8
+    use_graph = r.use_graph
+    del r, model
+    torch.cuda.empty_cache()
+
+    per_config, eager, cpu_baseline = None, None, None
+    if rank == 0 and world == 1:
+        if not args.no_per_config:
+            per_config = per_config_block(args, dev, rank, peaks)
+            if not args.no_cpu_baseline:
+                eager = gpu_eager_baseline(args.workload)
+        if not args.no_cpu_baseline:
+            c = cpu_reference_run(args.workload, 1, 3)
+            cpu_baseline = {"value": c["fps"], "unit": "frames/s", "cores": c["cores"], "kind": c["kind"], "sample": c["sample"]}
 
     if rank == 0:
-        ev = E.finalize_metrics(metric_vec)
         line = {
             "metric": "predicted frames/sec", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
             "config": {"workload": desc, "seqs_per_gpu": B, "global_batch": B * world, "context": ctx, "pred": pred,
                        "sharding": f"independent sequences, {world} rank(s), no data-path collective",
-                       "l2": "inputs/activations per step far exceed the 126 MB L2 (no flush needed)"
-                       if B * t_in * img[0] * img[1] * img[2] * 4 > 2.6e8 else "small working set: latency-bound case",
+                       "scaling_note": "weak: fixed sequences per GPU; 512 per GPU at 8 GPUs IS BASELINE's fixed batch of 4096 "
+                                       "(the library microbatches internally, so per-GPU time depends on the shard only)",
+                       "l2": "small working set: latency-bound case" if small else
+                             "inputs/activations per step far exceed the 126 MB L2 (no flush needed)",
                        "cuda_graph": bool(use_graph),
                        "required_gflop_per_seq": REQUIRED_GFLOP_PER_SEQ.get(args.workload)},
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "clocks": clocks,
+            "clocks": clocks, "env": vpk_env(),
             "eval_metrics": {"mse_h1": ev["mse"][0], "psnr_h1": ev["psnr"][0], "mse_hP": ev["mse"][-1],
                              "psnr_hP": ev["psnr"][-1], "sequences": ev["sequences"],
                              "ssim_h1": ssim_disp[0] if ssim_disp else None,
                              "ssim_hP": ssim_disp[-1] if ssim_disp else None,
                              "note": "synthetic random targets; exercises the NCCL metric reduction only (MSE / PSNR sums inside "
                                      "the timed step; SSIM sums, 3-channel workloads, once outside it)"},
+            "gpu_eager_baseline": eager, "per_config": per_config,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

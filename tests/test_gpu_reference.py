@@ -59,7 +59,11 @@ def test_full_batch_against_the_real_reference_on_cuda(name):
     ours32.load_state_dict(sd)
     x = synth_frames(B, t_in, *img, seed=777).cuda()
     ref = _reference_on_cuda(key, img, sd, kw)
-    with torch.no_grad():
+    # PredRNN's 5 x 5 convs: cuDNN's fp32 algorithm choice there (FFT / Winograd family) is itself 3e-4 away from the CPU
+    # reference after 19 steps (2.6e-2 with LayerNorm), i.e. not an fp32 reference at the 1e-4 level; ATen's native
+    # convolution (im2col + fp32 SGEMM, TF32 off) is.  The 3 x 3 models agree with cuDNN to 3e-7 and keep it.
+    # (cudnn.flags() resets allow_tf32 to its default True unless told otherwise)
+    with torch.no_grad(), torch.backends.cudnn.flags(enabled=(key != "predrnn-pp"), allow_tf32=False):
         want, want_aux = ref(x, pred_frames=pred)
     del ref
     torch.cuda.empty_cache()

@@ -22,20 +22,24 @@ struct PhyCellArgs {
   float* f1raw;             // fp32 [B,H,W,Cp]
   const void* f1n;          // activation type [B,H,W,Cp], padded channels zero
   const float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *gate_w, *gate_b;   // host, reference layouts
+  // optional: a separate copy of h for F.conv1 in the operand type of the F path (see phycell_specs' f_act); nullptr: h_act
+  const void* h_f = nullptr;
 };
 
 inline int phycell_padded_channels(int hid) { return (hid + 7) / 8 * 8; }
 
-inline std::vector<ConvSpec> phycell_specs(const PhyCellArgs& a, const ActInfo& act) {
+// act: operand type of the gate conv (and of x / h_act / h_act_out); f_act: operand type of F.conv1 / F.conv2 (h_f, f1n).
+// The caller builds specs [0], [1] with f_act.dtype and [2] with act.dtype.
+inline std::vector<ConvSpec> phycell_specs(const PhyCellArgs& a, const ActInfo& act, const ActInfo& f_act) {
   std::vector<ConvSpec> out;
   const int Cp = phycell_padded_channels(a.hid);
   int oh, ow;
   {
-    ConvArgs c1{a.name + "F.conv1.", a.B, a.H, a.W, a.C, a.hid, a.k, 1, a.k / 2, a.h_act, a.conv1_w, a.conv1_b, ACT_NONE,
-                a.f1raw};
+    ConvArgs c1{a.name + "F.conv1.", a.B, a.H, a.W, a.C, a.hid, a.k, 1, a.k / 2, a.h_f ? a.h_f : a.h_act, a.conv1_w,
+                a.conv1_b, ACT_NONE, a.f1raw};
     c1.out_f32_dense = true;
     c1.out_pix = Cp;
-    out.push_back(conv_spec(c1, act, &oh, &ow));
+    out.push_back(conv_spec(c1, f_act, &oh, &ow));
   }
   {
     ConvSpec s;
@@ -54,7 +58,7 @@ inline std::vector<ConvSpec> phycell_specs(const PhyCellArgs& a, const ActInfo& 
     s.biases.push_back(br);
     ConvInput in{make_view(a.f1n, a.H, a.W, Cp), 0, 0};
     in.wc_count = a.hid;
-    lower_conv(s, 1, 1, 0, {in}, a.H, a.W, act.esize, &oh, &ow);
+    lower_conv(s, 1, 1, 0, {in}, a.H, a.W, f_act.esize, &oh, &ow);
     EpiParams& e = s.phases[0].epi;
     e.kind = EPI_BIAS_ACT;
     e.act = ACT_NONE;
@@ -92,5 +96,6 @@ inline std::vector<ConvSpec> phycell_specs(const PhyCellArgs& a, const ActInfo& 
   }
   return out;
 }
+inline std::vector<ConvSpec> phycell_specs(const PhyCellArgs& a, const ActInfo& act) { return phycell_specs(a, act, act); }
 
 }  // namespace vpk
