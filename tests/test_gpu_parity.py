@@ -365,6 +365,9 @@ SWITCHES = [
     ("VPK_EF_NO_FUSE=1", "ef_3x32", False),
     ("VPK_NO_FUSED_LN_STATS=1", "predrnn_ln_3x32", False),
     ("VPK_NO_FUSED_DECOUPLE=1", "predrnn_3x32", True),
+    # LayerNorm ST-LSTM: fp16 products per conv_x / conv_h / conv_m tap (default 3 = split weights and activations)
+    ("VPK_LN_PRODUCTS=2", "predrnn_ln_3x32", False),
+    ("VPK_LN_PRODUCTS=1", "predrnn_ln_1x64", False),
     ("VPK_HALO_RESIDENT=0", "phy_1x64", True),
     # small batches use the sub-pixel deconv by default: the per-parity form adds the same products in the same order
     ("VPK_SUBPIX=0", "ef_3x32", True),

@@ -101,6 +101,7 @@ struct ConvArgs {
   const void* x_lo = nullptr;
   int cin_w = -1;               // input channels the weight tensor really has (-1: Cin); x may carry zero padding channels
   bool w_split = false;         // weights as high + low 16-bit parts over the same activations (lowering.h: ConvInput::w_split)
+  bool split_uncounted = false; // `split` is for precision: the two extra products are not algorithmic FLOPs
 };
 inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* ow) {
   ConvSpec s;
@@ -123,6 +124,7 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
   in.wc_count = a.cin_w;
   in.w_split = a.w_split && a.stride == 1;
   if (a.split) in.lo_view = make_view(a.x_lo, a.H, a.W, a.Cin);
+  in.extra_uncounted = a.split && a.split_uncounted;
   lower_conv(s, a.k, a.stride, a.pad, {in}, a.H, a.W, act.esize, oh, ow);
   EpiParams& e = s.phases[0].epi;
   e.kind = EPI_BIAS_ACT;

@@ -868,6 +868,26 @@ __global__ void split_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* _
   }
 }
 
+// fp32 -> split-fp16 (hi, lo); n % 4 == 0
+__global__ void split_f16_kernel(const float* __restrict__ in, __half* __restrict__ hi, __half* __restrict__ lo, long long n4) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(in)[i];
+    const __half2 h01 = __floats2half2_rn(v.x, v.y), h23 = __floats2half2_rn(v.z, v.w);
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn(v.x - f01.x, v.y - f01.y), l23 = __floats2half2_rn(v.z - f23.x, v.w - f23.y);
+    uint2 hv, lv;
+    hv.x = *reinterpret_cast<const uint32_t*>(&h01);
+    hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+    lv.x = *reinterpret_cast<const uint32_t*>(&l01);
+    lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+    reinterpret_cast<uint2*>(hi)[i] = hv;
+    reinterpret_cast<uint2*>(lo)[i] = lv;
+  }
+}
+
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
@@ -1062,6 +1082,13 @@ void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num
   VPK_REQUIRE(n % 4 == 0, "split_bf16: element count must be a multiple of 4");
   launch_pdl(split_bf16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__nv_bfloat16*>(hi),
                                                                        static_cast<__nv_bfloat16*>(lo), n / 4);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_split_f16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream) {
+  VPK_REQUIRE(n % 4 == 0, "split_f16: element count must be a multiple of 4");
+  launch_pdl(split_f16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__half*>(hi),
+             static_cast<__half*>(lo), n / 4);
   VPK_CUDA(cudaGetLastError());
 }
 

@@ -72,5 +72,7 @@ void launch_metric_ssim_sums(const float* pred, const float* target, int B, int 
                              double* out, cudaStream_t stream);
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);   // n % 4 == 0
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
+// fp32 -> split-fp16: hi = fp16(v), lo = fp16(v - hi)   (n % 4 == 0)
+void launch_split_f16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
 
 }  // namespace vpk

@@ -65,12 +65,15 @@ void lower_conv(ConvSpec& spec, int k, int stride, int pad, const std::vector<Co
           for (int ky = 0; ky < k; ++ky)
             for (int kx = 0; kx < k; ++kx) {
               add_step(ph.steps, hi, ky - pad, kx - pad, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count, part);
-              if (in.w_split && part == 2) ph.steps.back().count_flops = false;
+              if ((in.w_split || in.extra_uncounted) && part == 2) ph.steps.back().count_flops = false;
             }
         if (split)
           for (int ky = 0; ky < k; ++ky)
             for (int kx = 0; kx < k; ++kx)
+            {
               add_step(ph.steps, lo, ky - pad, kx - pad, in.view.C, c0, in.wref, ky, kx, in.wc0, in.wc_count, 1);
+              if (in.extra_uncounted) ph.steps.back().count_flops = false;
+            }
       }
     }
   } else {

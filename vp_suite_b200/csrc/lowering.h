@@ -67,6 +67,8 @@ struct ConvInput {                  // one logical input tensor of a conv (full-
   // weights only are split into a high and a low 16-bit part: A * W_hi + A * W_lo, two taps per weight tap over the SAME
   // activation tile (~22 weight mantissa bits; stride-1 convs; LayerNorm-fed ST-LSTM convs, see model_predrnn.cu)
   bool w_split = false;
+  // split activations + weights used for PRECISION only (lo_view set): count the algorithmic FLOPs once, not three times
+  bool extra_uncounted = false;
 };
 
 // Appends the K-steps of a k x k conv with the given stride (1 or 2) and padding over `inputs` to spec.phases[0]

@@ -84,6 +84,18 @@ template <> __device__ __forceinline__ void st_act4<__half>(__half* p, float4 v)
   *reinterpret_cast<uint2*>(p) = t;
 }
 
+// what the activation-type copy of v misses: v - float(T(v)), rounded to T (split operands: hi + lo ~ 22 mantissa bits)
+template <typename T> __device__ __forceinline__ float4 lo_part4(float4 v);
+template <> __device__ __forceinline__ float4 lo_part4<float>(float4) { return make_float4(0.f, 0.f, 0.f, 0.f); }
+template <> __device__ __forceinline__ float4 lo_part4<__half>(float4 v) {
+  return make_float4(v.x - __half2float(__float2half_rn(v.x)), v.y - __half2float(__float2half_rn(v.y)),
+                     v.z - __half2float(__float2half_rn(v.z)), v.w - __half2float(__float2half_rn(v.w)));
+}
+template <> __device__ __forceinline__ float4 lo_part4<__nv_bfloat16>(float4 v) {
+  return make_float4(v.x - __bfloat162float(__float2bfloat16_rn(v.x)), v.y - __bfloat162float(__float2bfloat16_rn(v.y)),
+                     v.z - __bfloat162float(__float2bfloat16_rn(v.z)), v.w - __bfloat162float(__float2bfloat16_rn(v.w)));
+}
+
 // grid (item blocks, sample chunks): one thread = one (position, four channels) for kGateNB consecutive samples.  The
 // LayerNorm affine parameters depend on (position, channel) only, so they are read once per gate group and reused for
 // the whole chunk of samples (they would otherwise be two thirds of the kernel's L2 -> SM traffic: 28 parameter
@@ -158,6 +170,7 @@ __global__ void __launch_bounds__(256) stlstm_ln_gates_kernel(const StLnGatesArg
       *reinterpret_cast<float4*>(a.m + pos * C + ch) = mv;
       st_act4<T>(static_cast<T*>(a.mem) + pos * 2 * C + C + ch, mv);
       st_act4<T>(static_cast<T*>(a.m_act) + pos * C + ch, mv);
+      if (a.m_act_lo != nullptr) st_act4<T>(static_cast<T*>(a.m_act_lo) + pos * C + ch, lo_part4<T>(mv));
       st_act4<T>(static_cast<T*>(a.dm) + pos * C + ch, dm);
     }
   }
@@ -193,6 +206,7 @@ __global__ void __launch_bounds__(256) stlstm_ln_out_kernel(const StLnOutArgs a)
     const float4 h = make_float4(sigmoid_f(p.x + o.x) * tanh_f(l.x), sigmoid_f(p.y + o.y) * tanh_f(l.y),
                                  sigmoid_f(p.z + o.z) * tanh_f(l.z), sigmoid_f(p.w + o.w) * tanh_f(l.w));
     st_act4<T>(static_cast<T*>(a.h) + pos * C + ch, h);
+    if (a.h_lo != nullptr) st_act4<T>(static_cast<T*>(a.h_lo) + pos * C + ch, lo_part4<T>(h));
   }
 }
 

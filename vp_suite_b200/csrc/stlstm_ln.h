@@ -34,6 +34,7 @@ struct StLnGatesArgs {
   float* opart;                                // fp32 [B*HW][C]: LN(conv_x)_o + LN(conv_h)_o
   int B, HW, C, dtype;
   float forget_bias;
+  void* m_act_lo = nullptr;                    // optional: low part of m' (m' - m_act), activation type [B*HW][C]
 };
 void launch_stlstm_ln_gates(const StLnGatesArgs& a, int num_sms, cudaStream_t stream);
 
@@ -45,6 +46,7 @@ struct StLnOutArgs {
   const float* opart;
   void* h;                                     // activation type [B*HW][C]
   int B, HW, C, dtype;
+  void* h_lo = nullptr;                        // optional: low part of h' (h' - h), activation type [B*HW][C]
 };
 void launch_stlstm_ln_out(const StLnOutArgs& a, int num_sms, cudaStream_t stream);
 
