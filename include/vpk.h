@@ -74,6 +74,12 @@ typedef struct vpk_model_desc {
   /* execution */
   int32_t max_microbatch;    /* sequences processed per pass over the layers (0 = library default)             */
   int32_t use_cuda_graph;    /* 1: capture the per-microbatch launch program into a CUDA graph and replay it   */
+  /* action-conditional variants (VPModel.action_conditional / action_size, base_model.py:33-34): predrnn-pp
+   * (predrnn_v2.py:65-90: stride-2 input / action convs, ActionConditionalSpatioTemporalLSTMCell, output deconvs) and phy
+   * (model_blocks/phydnet.py:44-55, 153-155: frame / hidden action convs in PhyCell, action channels into the ConvLSTM) */
+  int32_t action_conditional;
+  int32_t action_size;
+  int32_t residual_on_action_conv;   /* predrnn-pp (predrnn_v2.py:46, 213-218) */
 } vpk_model_desc;
 
 /* Replaces: MODEL_CLASSES[key](device, **model_kwargs)  (vp_suite/vpsuite.py:170; base_model.py:38-69). */
@@ -104,11 +110,23 @@ int vpk_model_workspace_bytes(vpk_model* m, int32_t batch, int32_t t_in, int32_t
 int vpk_model_forward(vpk_model* m, const float* x, int32_t batch, int32_t t_in, int32_t pred_frames, float* out,
                       float* aux, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Replaces: VPModel.forward(x, pred_frames, actions=a) of an action-conditional model (predrnn_v2.py:147-152, 181-191;
+ * models/phydnet.py:100-105).  actions: DEVICE fp32 [batch, action_steps, action_size]; step t of the rollout reads
+ * actions[:, t]; action_steps must cover the rollout (context + pred_frames - 1).  A model created without
+ * action_conditional ignores them (pass NULL / use vpk_model_forward); an action-conditional model given NULL actions or
+ * too few steps fails with VPK_ERR_INVALID ("Given actions are None or of the wrong size!"). */
+int vpk_model_forward_actions(vpk_model* m, const float* x, const float* actions, int32_t action_steps, int32_t batch,
+                              int32_t t_in, int32_t pred_frames, float* out, float* aux, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* Same call with HOST buffers (x, out, aux on the host; pinned memory recommended): the library stages
  * microbatches through the device, overlapping copies with compute, and returns when `out` is complete.
  * The library allocates its own device workspace for this entry. */
 int vpk_model_forward_host(vpk_model* m, const float* x_host, int32_t batch, int32_t t_in, int32_t pred_frames,
                            float* out_host, float* aux_host);
+/* Host-buffer entry of an action-conditional model: actions_host fp32 [batch, action_steps, action_size] on the host. */
+int vpk_model_forward_host_actions(vpk_model* m, const float* x_host, const float* actions_host, int32_t action_steps,
+                                   int32_t batch, int32_t t_in, int32_t pred_frames, float* out_host, float* aux_host);
 
 /* Sequences the library processes per pass over the layers (its microbatch) for a call with `batch` sequences. */
 int vpk_model_microbatch(vpk_model* m, int32_t batch, int32_t* sequences);

@@ -150,10 +150,16 @@ def find_divisor_for_group_norm(x):
     return x // sq
 
 
-def phycell_step(x, h, p):
+def phycell_step(x, h, p, action=None):
     """``p`` holds F.conv1.{weight,bias}, F.bn1.{weight,bias}, F.conv2.{weight,bias}, convgate.{weight,bias}.
     K = sigmoid(convgate(cat[x, h])) (:57-59); h~ = h + F(h) with F = conv1 -> GroupNorm -> conv2 (:33-39, :60);
-    h' = h~ + K * (x - h~) (:61)."""
+    h' = h~ + K * (x - h~) (:61).  action_conditional=True (``p`` also holds frame_action_conv / hidden_action_conv,
+    :44-48): the action vector [b, a] is inflated to the frame size, concatenated to frame and to hidden, and each goes
+    through its own 1x1 conv first (:50-55); everything after uses the convolved frame / hidden."""
+    if "frame_action_conv.weight" in p:
+        infl = action[:, :, None, None].expand(-1, -1, *x.shape[-2:])
+        x = F.conv2d(torch.cat([x, infl], dim=1), p["frame_action_conv.weight"], p["frame_action_conv.bias"])
+        h = F.conv2d(torch.cat([h, infl], dim=1), p["hidden_action_conv.weight"], p["hidden_action_conv.bias"])
     k1 = p["F.conv1.weight"]
     hid = k1.shape[0]
     groups = find_divisor_for_group_norm(hid)

@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle import ref_shim                      # noqa: E402
-from oracle.weights import synth_state_dict, synth_frames, measure_inputs   # noqa: E402
+from oracle.weights import synth_state_dict, synth_frames, measure_inputs, synth_actions   # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden")
 
@@ -207,7 +207,42 @@ def run_measures(manifest):
     print("measures:", {k: np.round(v, 4).tolist() for k, v in arrays.items()})
 
 
-INCREMENTAL = {"blocks_ac": run_blocks_ac, "measures": run_measures}
+AC_CASES = [
+    # name,              key,          img_shape,   b, ctx, pred, wseed, xseed, gain, action_size, extra kwargs
+    ("predrnn_ac_1x64",  "predrnn-pp", (1, 64, 64), 2, 3,   3,    31,    201,   1.5,  3,           {}),
+    ("predrnn_acln_3x32", "predrnn-pp", (3, 32, 32), 2, 2,   2,    32,    202,   1.5,  4,           {"layer_norm": True}),
+    ("phy_ac_3x64",      "phy",        (3, 64, 64), 2, 2,   3,    33,    203,   1.5,  3,           {}),
+]
+
+
+def run_models_ac(manifest):
+    """Action-conditional rollouts of the reference (predrnn_v2.py:73-90,181-221; models/phydnet.py:94-122 with
+    model_blocks/phydnet.py:44-55,153-155): ``model(x, pred_frames, actions=a)`` -> <name>.npz."""
+    classes = ref_shim.load_reference()
+    for name, key, img, b, t, p, wseed, xseed, gain, a_size, kw in AC_CASES:
+        torch.manual_seed(0)
+        m = classes[key]("cpu", img_shape=img, action_size=a_size, tensor_value_range=[0.0, 1.0], action_conditional=True,
+                         **kw).eval()
+        shp = shapes_of(m)
+        m.load_state_dict(synth_state_dict(shp, wseed, gain))
+        total_t = t + p if key == "predrnn-pp" else t
+        x = synth_frames(b, total_t, *img, seed=xseed)
+        actions = synth_actions(b, t + p - 1, a_size, seed=xseed + 1)
+        with torch.no_grad():
+            pred, aux = m(x, pred_frames=p, actions=actions)
+        arrays = {"pred": pred.numpy()}
+        if aux is not None:
+            (lk, lv), = aux.items()
+            arrays["loss"] = np.asarray(float(lv), dtype=np.float64)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **arrays)
+        manifest["models"][name] = dict(key=key, img_shape=list(img), batch=b, context=t, pred=p, wseed=wseed, xseed=xseed,
+                                        gain=gain, shapes=shp, action_size=a_size, aseed=xseed + 1,
+                                        model_kwargs={**kw, "action_conditional": True, "action_size": a_size},
+                                        pred_std=float(pred.std()), pred_mean=float(pred.mean()))
+        print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
+
+
+INCREMENTAL = {"blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac}
 
 
 def main():
@@ -232,6 +267,7 @@ def main():
     run_blocks(manifest)
     run_blocks_ac(manifest)
     run_measures(manifest)
+    run_models_ac(manifest)
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

@@ -103,10 +103,65 @@ def reshape_patch_back(xp, p):
     return xp.reshape(b, t, c, hp * p, wp * p)
 
 
-def predrnn_v2_forward(sd, x, pred_frames, cfg=None, return_states=False):
+def predrnn_v2_ac_forward(sd, x, pred_frames, actions, cfg=None):
+    """PredRNN_V2.forward in eval mode with action_conditional=True (predrnn_v2.py:131-230).  The constructor then forces
+    conv_actions_on_input and reverse_scheduled_sampling (:65-67): frames and the spatially inflated actions each pass two
+    stride-2 k x k convs (no bias, no activation, :74-81, :178-188) down to a (patch_h / 4) x (patch_w / 4) latent, the
+    cells are ActionConditionalSpatioTemporalLSTMCell (:94, blocks.stlstm_ac_step), every layer sees the SAME convolved
+    action (:191, :200), and x_gen comes back through two transposed convs with the input-side residuals
+    (residual_on_action_conv, :213-218).  The reverse-sampling eval mask is 1 for t < context (:306-308), so real frames feed
+    the context steps and x_gen the rest, as in the non action-conditional rollout.  ``actions``: [b, >= total - 1, a]."""
+    cfg = {**PREDRNN_DEFAULTS, "residual_on_action_conv": True, **(cfg or {})}
+    p, L, hid = cfg["patch_size"], cfg["num_layers"], cfg["num_hidden"]
+    b, total = x.shape[:2]
+    ctx = total - pred_frames
+    if ctx < 1:
+        raise ValueError("input must hold context and target frames")
+    a_size = sd["action_conv_input1.weight"].shape[1]
+    if actions is None or actions.shape[-1] != a_size:
+        raise ValueError("Given actions are None or of the wrong size!")
+    xp = reshape_patch(x, p)
+    hp, wp = xp.shape[-2:]
+    pad = sd["conv_input1.weight"].shape[-1] // 2
+    rh, rw = hp // 4, wp // 4
+    h_t = [torch.zeros(b, hid[i], rh, rw) for i in range(L)]
+    c_t = [torch.zeros(b, hid[i], rh, rw) for i in range(L)]
+    memory = torch.zeros(b, hid[0], rh, rw)
+    w_adapter = sd["adapter.weight"]
+    x_gen = None
+    frames, dec = [], []
+    for t in range(total - 1):
+        net = xp[:, t] if t < ctx else x_gen
+        action = actions[:, t, :, None, None].expand(-1, -1, hp, wp)
+        net1 = F.conv2d(net, sd["conv_input1.weight"], stride=2, padding=pad)
+        net2 = F.conv2d(net1, sd["conv_input2.weight"], stride=2, padding=pad)
+        action = F.conv2d(F.conv2d(action, sd["action_conv_input1.weight"], stride=2, padding=pad),
+                          sd["action_conv_input2.weight"], stride=2, padding=pad)
+        for i in range(L):
+            inp = net2 if i == 0 else h_t[i - 1]
+            h_t[i], c_t[i], memory, dc, dm = B.stlstm_ac_step(inp, h_t[i], c_t[i], memory, action, B._sub(sd, f"cell_list.{i}."))
+            dcn = F.normalize(F.conv2d(dc, w_adapter).flatten(2), dim=2)
+            dmn = F.normalize(F.conv2d(dm, w_adapter).flatten(2), dim=2)
+            dec.append(torch.mean(torch.abs(F.cosine_similarity(dcn, dmn, dim=2))))
+        top = h_t[L - 1]
+        if cfg["residual_on_action_conv"]:
+            g = F.conv_transpose2d(top + net2, sd["deconv_output1.weight"], stride=2, padding=pad, output_padding=1)
+            x_gen = F.conv_transpose2d(g + net1, sd["deconv_output2.weight"], stride=2, padding=pad, output_padding=1)
+        else:
+            g = F.conv_transpose2d(top, sd["deconv_output1.weight"], stride=2, padding=pad, output_padding=1)
+            x_gen = F.conv_transpose2d(g, sd["deconv_output2.weight"], stride=2, padding=pad, output_padding=1)
+        frames.append(x_gen)
+    pred = reshape_patch_back(torch.stack(frames[-pred_frames:], dim=1), p)
+    loss = cfg["decoupling_loss_scale"] * torch.mean(torch.stack(dec))
+    return pred, {"ST-LSTM decouple loss": loss}
+
+
+def predrnn_v2_forward(sd, x, pred_frames, cfg=None, return_states=False, actions=None):
     """PredRNN_V2.forward in eval mode (predrnn_v2.py:131-230).  ``x`` holds context + target frames (:134-137);
     the eval mask is all zeros (:300-309) so from t >= context_frames the model's own x_gen is the input
     (:172-176); zig-zag ``memory`` (:196-204); decouple loss over all (t, layer) (:197-211, :229)."""
+    if "conv_input1.weight" in sd:              # action-conditional checkpoint layout
+        return predrnn_v2_ac_forward(sd, x, pred_frames, actions, cfg)
     cfg = {**PREDRNN_DEFAULTS, **(cfg or {})}
     p, L, hid = cfg["patch_size"], cfg["num_layers"], cfg["num_hidden"]
     b, total = x.shape[:2]
@@ -148,9 +203,12 @@ def predrnn_v2_forward(sd, x, pred_frames, cfg=None, return_states=False):
 # --------------------------------------------------------------------------------------------------
 # phy  (PhyDNet, non action-conditional, eval)  and the cfg-2 composition (its residual branch alone)
 # --------------------------------------------------------------------------------------------------
-def _convcell_stack(sd, prefix, frame, H, C, n_layers):
-    """SingleStepConvLSTM.forward (model_blocks/phydnet.py:147-163) for one frame; H, C are lists (mutated)."""
+def _convcell_stack(sd, prefix, frame, H, C, n_layers, action=None):
+    """SingleStepConvLSTM.forward (model_blocks/phydnet.py:147-163) for one frame; H, C are lists (mutated).
+    action_conditional: the inflated action is concatenated to the bottom layer's input (:153-155)."""
     inp = frame
+    if action is not None:
+        inp = torch.cat([inp, action[:, :, None, None].expand(-1, -1, *frame.shape[-2:])], dim=1)
     for j in range(n_layers):
         H[j], C[j] = B.convlstm_cell_step(inp, H[j], C[j], sd[f"{prefix}cell_list.{j}.conv.weight"],
                                           sd[f"{prefix}cell_list.{j}.conv.bias"])
@@ -158,7 +216,7 @@ def _convcell_stack(sd, prefix, frame, H, C, n_layers):
     return H[-1]
 
 
-def phydnet_forward(sd, x, pred_frames, cfg=None):
+def phydnet_forward(sd, x, pred_frames, cfg=None, actions=None):
     """PhyDNet.forward in eval mode (models/phydnet.py:94-137) with encoder_fwd (:73-89): T_in-1 warm-up steps
     on context frames, then autoregression from the last context frame.  Only ``output_image`` (:87-88) is
     computed -- the two visualisation-only decoder passes (:84-85) do not influence the result."""
@@ -168,8 +226,13 @@ def phydnet_forward(sd, x, pred_frames, cfg=None):
     nl = cfg["convlstm_n_layers"]
     n_phy = cfg["phycell_n_layers"]
     state = {}
+    ac = "phycell.cell_list.0.frame_action_conv.weight" in sd          # action-conditional checkpoint layout
+    if ac:
+        a_size = sd["phycell.cell_list.0.frame_action_conv.weight"].shape[1] - sd["phycell.cell_list.0.convgate.weight"].shape[0]
+        if actions is None or actions.shape[-1] != a_size:              # models/phydnet.py:103-105
+            raise ValueError("Given actions are None or of the wrong size!")
 
-    def step(frame, first):
+    def step(frame, first, action=None):
         e = B.dcgan_encoder(frame, sd, "encoder_E.")
         ep = B.encoder_split(e, sd, "encoder_Ep.")
         er = B.encoder_split(e, sd, "encoder_Er.")
@@ -179,21 +242,21 @@ def phydnet_forward(sd, x, pred_frames, cfg=None):
             state["C"] = [torch.zeros(b, hd[j], *er.shape[-2:]) for j in range(nl)]
         inp = ep
         for j in range(n_phy):                                           # PhyCell.forward :95-105
-            state["Hp"][j] = B.phycell_step(inp, state["Hp"][j], B._sub(sd, f"phycell.cell_list.{j}."))
+            state["Hp"][j] = B.phycell_step(inp, state["Hp"][j], B._sub(sd, f"phycell.cell_list.{j}."), action)
             inp = state["Hp"][j]
-        out_r = _convcell_stack(sd, "convcell.", er, state["H"], state["C"], nl)
+        out_r = _convcell_stack(sd, "convcell.", er, state["H"], state["C"], nl, action)
         dp = B.decoder_split(state["Hp"][-1], sd, "decoder_Dp.")
         dr = B.decoder_split(out_r, sd, "decoder_Dr.")
         return torch.sigmoid(B.dcgan_decoder(dp + dr, sd, "decoder_D."))
 
-    idx = 0
+    idx = 0                                                             # ac_index (models/phydnet.py:108-122)
     for ei in range(t_in - 1):
-        step(x[:, ei], idx == 0)
+        step(x[:, ei], idx == 0, actions[:, idx] if ac else None)
         idx += 1
     frame = x[:, t_in - 1]
     outs = []
     for _ in range(pred_frames):
-        frame = step(frame, idx == 0)
+        frame = step(frame, idx == 0, actions[:, idx] if ac else None)
         outs.append(frame)
         idx += 1
     return torch.stack(outs, dim=1), None

@@ -56,21 +56,35 @@ def predrnn_shapes(img_shape, cfg=None):
     c = img_shape[0]
     p, L, hid, k = cfg["patch_size"], cfg["num_layers"], cfg["num_hidden"], cfg["filter_size"]
     out = {}
+    ac = bool(cfg.get("action_conditional"))            # predrnn_v2.py:65-90 and model_blocks/predrnn.py:97-139
+    hp, wp = img_shape[1] // p, img_shape[2] // p
+    if ac:
+        a, C0, CL = cfg["action_size"], hid[0], hid[L - 1]
+        hp, wp = hp // 4, wp // 4
+        out["conv_input1.weight"] = (C0 // 2, p * p * c, k, k)
+        out["conv_input2.weight"] = (C0, C0 // 2, k, k)
+        out["action_conv_input1.weight"] = (C0 // 2, a, k, k)
+        out["action_conv_input2.weight"] = (C0, C0 // 2, k, k)
+        out["deconv_output1.weight"] = (CL, CL // 2, k, k)
+        out["deconv_output2.weight"] = (CL // 2, p * p * c, k, k)
     for i in range(L):
-        cin = p * p * c if i == 0 else hid[i - 1]
+        cin = (hid[0] if ac else p * p * c) if i == 0 else hid[i - 1]
         C = hid[i]
-        out[f"cell_list.{i}.conv_x.0.weight"] = (7 * C, cin, k, k)
-        out[f"cell_list.{i}.conv_h.0.weight"] = (4 * C, C, k, k)
-        out[f"cell_list.{i}.conv_m.0.weight"] = (3 * C, C, k, k)
-        out[f"cell_list.{i}.conv_o.0.weight"] = (C, 2 * C, k, k)
-        out[f"cell_list.{i}.conv_last.weight"] = (C, 2 * C, 1, 1)
-        if cfg.get("layer_norm"):                       # nn.LayerNorm([k * C, H / p, W / p]) after conv_x/h/m/o
-            hp, wp = img_shape[1] // p, img_shape[2] // p
-            for name, mult in (("x", 7), ("h", 4), ("m", 3), ("o", 1)):
+        convs = [("x", 7, cin), ("h", 4, C)] + ([("a", 4, C)] if ac else []) + [("m", 3, C), ("o", 1, 2 * C)]
+        for name, mult, ci in convs:
+            out[f"cell_list.{i}.conv_{name}.0.weight"] = (mult * C, ci, k, k)
+            if ac:
+                out[f"cell_list.{i}.conv_{name}.0.bias"] = (mult * C,)
+            if cfg.get("layer_norm"):                   # nn.LayerNorm([k * C, H', W']) after every conv
                 out[f"cell_list.{i}.conv_{name}.1.weight"] = (mult * C, hp, wp)
                 out[f"cell_list.{i}.conv_{name}.1.bias"] = (mult * C, hp, wp)
-    out["conv_last.weight"] = (p * p * c, hid[L - 1], 1, 1)
-    out["adapter.weight"] = (hid[0], hid[0], 1, 1)
+        out[f"cell_list.{i}.conv_last.weight"] = (C, 2 * C, 1, 1)
+        if ac:
+            out[f"cell_list.{i}.conv_last.bias"] = (C,)
+    if not ac:
+        out["conv_last.weight"] = (p * p * c, hid[L - 1], 1, 1)
+    ca = hid[L - 1] if ac else hid[0]
+    out["adapter.weight"] = (ca, ca, 1, 1)
     return out
 
 
@@ -110,7 +124,11 @@ def phydnet_shapes(img_shape, cfg=None):
         out[pre + "F.conv2.bias"] = (64,)
         out[pre + "convgate.weight"] = (64, 128, 3, 3)
         out[pre + "convgate.bias"] = (64,)
-    cin = 64
+        if cfg.get("action_conditional"):               # model_blocks/phydnet.py:44-48
+            for nm in ("frame_action_conv", "hidden_action_conv"):
+                out[pre + nm + ".weight"] = (64, 64 + cfg["action_size"], 1, 1)
+                out[pre + nm + ".bias"] = (64,)
+    cin = 64 + (cfg["action_size"] if cfg.get("action_conditional") else 0)
     kc = cfg["convlstm_kernel_size"][0]
     for j, hd in enumerate(cfg["convlstm_hidden_dims"][:cfg["convlstm_n_layers"]]):
         out[f"convcell.cell_list.{j}.conv.weight"] = (4 * hd, cin + hd, kc, kc)

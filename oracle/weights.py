@@ -58,3 +58,10 @@ def measure_inputs(shape, seed):
     target = torch.rand(shape, generator=g)
     pred = (target + 0.15 * torch.randn(shape, generator=g)).clamp(0.0, 1.0)
     return pred, target
+
+
+def synth_actions(b, t, a, seed=77):
+    """Deterministic action vectors [b, t, a] in (-1, 1) (the reference's datasets emit float actions per frame pair)."""
+    g = torch.Generator(device="cpu")
+    g.manual_seed(seed)
+    return torch.rand((b, t, a), generator=g) * 2 - 1

@@ -65,6 +65,32 @@ def test_reference_model_test_protocol(key, precision):
         assert e1 <= 5e-3 and e5[0] <= 5e-3 and max(e5) <= 2e-2, (e1, e5)
 
 
+@pytest.mark.parametrize("key", ["convlstm-shi", "predrnn-pp", "phy"])
+def test_reference_model_test_protocol_with_actions(key):
+    """tests/test_models.py:39-60 of the reference: action_conditional = CAN_HANDLE_ACTIONS, actions passed to every model
+    (models that cannot handle them ignore the keyword), shapes of pred_1 / forward -- plus values against the oracle."""
+    import vp_suite_b200 as V
+    from oracle.weights import synth_actions
+    img, b, p, a_size = (3, 64, 64), 2, 5, 3
+    cls = V.MODEL_CLASSES[key]
+    model = cls("cuda:0", img_shape=img, action_size=a_size, temporal_dim=3, action_conditional=cls.CAN_HANDLE_ACTIONS,
+                tensor_value_range=[0.0, 1.0], precision="fp32").to("cuda:0")
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in model.state_dict().items()}, seed=3, gain=GAIN.get(key, 1.5))
+    model.load_state_dict(sd)
+    t_x = p + 3 if cls.NEEDS_COMPLETE_INPUT else 3
+    x = torch.randn((b, t_x, *img), generator=torch.Generator().manual_seed(18))
+    a = synth_actions(b, p + 3 - 1, a_size, seed=19)
+    with torch.no_grad():
+        pred_1 = model.pred_1(x.cuda(), actions=a.cuda())
+        pred_5, _ = model(x.cuda(), pred_frames=p, actions=a.cuda())
+        ref_5, _ = OM.FORWARDS[key](sd, x, p, **({"actions": a} if cls.CAN_HANDLE_ACTIONS else {}))
+    assert pred_1.shape == (b, *img)
+    assert pred_5.shape == (b, 5, *img)
+    errs = _errs(pred_5.cpu(), ref_5)
+    print(f"{key} with actions (fp32): forward per-frame err {['%.1e' % e for e in errs]}")
+    assert max(errs) <= 1e-4, errs
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 @needs_ref
 @pytest.mark.parametrize("key,img,ctx,pred", [("convlstm-shi", (3, 32, 32), 4, 3), ("predrnn-pp", (1, 64, 64), 3, 3),

@@ -9,7 +9,7 @@ import torch
 
 from conftest import load_golden
 from oracle import models as OM
-from oracle.weights import synth_state_dict, synth_frames
+from oracle.weights import synth_state_dict, synth_frames, synth_actions
 
 pytestmark = pytest.mark.gpu
 
@@ -27,9 +27,9 @@ def _cuda():
 def _build(key, meta, **kw):
     import vp_suite_b200 as V
     dev = _cuda()
-    kw = {**(meta.get("model_kwargs") or {}), **kw}          # e.g. layer_norm=True for the predrnn_ln_* cases
-    m = V.MODEL_CLASSES[key](dev, img_shape=tuple(meta["img_shape"]), action_size=0, tensor_value_range=[0.0, 1.0],
-                             **kw).eval()
+    # model_kwargs: e.g. layer_norm=True for the predrnn_ln_* cases, action_conditional / action_size for the *_ac_* ones
+    kw = {"action_size": 0, **(meta.get("model_kwargs") or {}), **kw}
+    m = V.MODEL_CLASSES[key](dev, img_shape=tuple(meta["img_shape"]), tensor_value_range=[0.0, 1.0], **kw).eval()
     sd = synth_state_dict(meta["shapes"], meta["wseed"], meta["gain"])
     m.load_state_dict(sd)
     return m, sd
@@ -43,6 +43,45 @@ def _input(meta):
 def _frame_errs(a, b):
     d = np.abs(a - b)
     return [float(d[:, t].max()) for t in range(d.shape[1])]
+
+
+def _actions(meta):
+    return synth_actions(meta["batch"], meta["context"] + meta["pred"] - 1, meta["action_size"], seed=meta["aseed"])
+
+
+AC_CASES = ["predrnn_ac_1x64", "predrnn_acln_3x32", "phy_ac_3x64"]
+
+
+@pytest.mark.parametrize("name", AC_CASES)
+@pytest.mark.parametrize("precision,backend", [("fp32", "auto"), ("bf16", "auto"), ("bf16", "simt")])
+def test_action_conditional_models_match_reference_golden(manifest, name, precision, backend):
+    """model(x, pred_frames, actions=a) of the action-conditional predrnn-pp (predrnn_v2.py:65-90, 178-221; layer_norm off
+    and on) and phy (model_blocks/phydnet.py:44-55, 153-155) against vectors the reference produced; device and host
+    entries; the reference's error for missing / wrongly sized actions."""
+    meta = manifest["models"][name]
+    m, sd = _build(meta["key"], meta, precision=precision, backend=backend)
+    x, a = _input(meta), _actions(meta)
+    with torch.no_grad():
+        pred, aux = m(x.cuda(), pred_frames=meta["pred"], actions=a.cuda())
+    gold = load_golden(name)
+    errs = _frame_errs(pred.cpu().numpy(), gold["pred"])
+    print(f"{name} {precision}/{backend}: per-frame max abs err {['%.1e' % e for e in errs]}")
+    if precision == "fp32":
+        assert max(errs) <= FP32_TOL, errs
+    else:
+        assert errs[0] <= BF16_TOL_FIRST and max(errs) <= BF16_TOL_LAST, errs
+    if "loss" in gold:
+        rel = 1e-3 if precision == "fp32" else 5e-2
+        assert abs(float(list(aux.values())[0]) - float(gold["loss"])) <= rel * abs(float(gold["loss"])) + 1e-3
+    with torch.no_grad():
+        host, _ = m.forward_host(x.pin_memory(), pred_frames=meta["pred"], actions=a)
+    assert torch.equal(host, pred.cpu())
+    with pytest.raises(ValueError):
+        m(x.cuda(), pred_frames=meta["pred"])                                  # no actions
+    with pytest.raises(ValueError):
+        m(x.cuda(), pred_frames=meta["pred"], actions=a[..., :-1].cuda())      # wrong action size
+    with pytest.raises(ValueError):
+        m(x.cuda(), pred_frames=meta["pred"], actions=a[:, :1].cuda())         # too few steps
 
 
 EF_CASES = ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64", "branch_1x64",

@@ -11,10 +11,11 @@ KW = dict(action_size=0, tensor_value_range=[0.0, 1.0])
 
 
 @pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64",
-                                  "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32"])
+                                  "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32", "predrnn_ac_1x64",
+                                  "predrnn_acln_3x32", "phy_ac_3x64"])
 def test_state_dict_layout_matches_reference(manifest, name):
     meta = manifest["models"][name]
-    m = V.MODEL_CLASSES[meta["key"]]("cpu", img_shape=tuple(meta["img_shape"]), **KW, **(meta.get("model_kwargs") or {}))
+    m = V.MODEL_CLASSES[meta["key"]]("cpu", img_shape=tuple(meta["img_shape"]), **{**KW, **(meta.get("model_kwargs") or {})})
     got = {k: list(v.shape) for k, v in m.state_dict().items()}
     assert got == meta["shapes"]
     # and the native library expects exactly these tensors
@@ -80,13 +81,18 @@ def test_ef_loads_cuda_built_checkpoint_without_peepholes(manifest):
 
 
 @pytest.mark.skipif(not ref_shim.available(), reason="reference checkout not mounted")
-@pytest.mark.parametrize("key,img", [("convlstm-shi", (1, 64, 64)), ("predrnn-pp", (1, 64, 64)), ("phy", (3, 64, 64))])
-def test_same_seed_gives_the_reference_init_and_config(key, img):
+@pytest.mark.parametrize("key,img,extra", [
+    ("convlstm-shi", (1, 64, 64), {}), ("predrnn-pp", (1, 64, 64), {}), ("phy", (3, 64, 64), {}),
+    ("predrnn-pp", (1, 64, 64), {"action_conditional": True, "action_size": 3}),
+    ("predrnn-pp", (3, 32, 32), {"action_conditional": True, "action_size": 4, "layer_norm": True}),
+    ("phy", (3, 64, 64), {"action_conditional": True, "action_size": 3})])
+def test_same_seed_gives_the_reference_init_and_config(key, img, extra):
     ref_cls = ref_shim.load_reference()[key]
+    kw = {**KW, **extra}
     torch.manual_seed(7)
-    ref = ref_cls("cpu", img_shape=img, **KW)
+    ref = ref_cls("cpu", img_shape=img, **kw)
     torch.manual_seed(7)
-    ours = V.MODEL_CLASSES[key]("cpu", img_shape=img, **KW)
+    ours = V.MODEL_CLASSES[key]("cpu", img_shape=img, **kw)
     rsd, osd = ref.state_dict(), ours.state_dict()
     assert list(rsd) == list(osd)
     for k in rsd:

@@ -6,7 +6,7 @@ import torch
 from conftest import load_golden
 from oracle import blocks as OB
 from oracle import models as OM
-from oracle.weights import synth_state_dict, synth_frames
+from oracle.weights import synth_state_dict, synth_frames, synth_actions
 
 ATOL = 2e-5      # same arithmetic (ATen CPU fp32) in a different call structure
 
@@ -36,6 +36,22 @@ def test_model_rollout_matches_reference(manifest, name):
         assert abs(float(v) - float(gold["loss"])) <= 1e-4 * max(1.0, abs(float(gold["loss"])))
     else:
         assert aux is None
+
+
+@pytest.mark.parametrize("name", ["predrnn_ac_1x64", "predrnn_acln_3x32", "phy_ac_3x64"])
+def test_action_conditional_rollout_matches_reference(manifest, name):
+    """model(x, pred_frames, actions=a) of the reference's action-conditional predrnn-pp (incl. layer_norm) and phy."""
+    meta, sd, x = _case(manifest, name)
+    actions = synth_actions(meta["batch"], meta["context"] + meta["pred"] - 1, meta["action_size"], seed=meta["aseed"])
+    gold = load_golden(name)
+    with torch.no_grad():
+        pred, aux = OM.FORWARDS[meta["key"]](sd, x, meta["pred"], actions=actions)
+    assert np.abs(pred.numpy() - gold["pred"]).max() <= ATOL
+    assert gold["pred"].std() > 0.02
+    if "loss" in gold:
+        assert abs(float(list(aux.values())[0]) - float(gold["loss"])) <= 1e-4 * max(1.0, abs(float(gold["loss"])))
+    with pytest.raises(ValueError):                      # predrnn_v2.py:149-151, models/phydnet.py:103-105
+        OM.FORWARDS[meta["key"]](sd, x, meta["pred"], actions=actions[..., :-1])
 
 
 def test_ef_missing_peepholes_are_zero(manifest):

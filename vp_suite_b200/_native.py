@@ -35,6 +35,7 @@ class ModelDesc(C.Structure):
         ("convlstm_n_layers", C.c_int32), ("convlstm_hidden_dims", C.c_int32 * 8),
         ("convlstm_kernel_size", C.c_int32),
         ("max_microbatch", C.c_int32), ("use_cuda_graph", C.c_int32),
+        ("action_conditional", C.c_int32), ("action_size", C.c_int32), ("residual_on_action_conv", C.c_int32),
     ]
 
 
@@ -51,6 +52,9 @@ SYMBOLS = {
     "vpk_model_workspace_bytes": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_size_t)]),
     "vpk_model_forward": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, C.c_size_t, _vp]),
     "vpk_model_forward_host": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
+    "vpk_model_forward_actions": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp,
+                                            C.c_size_t, _vp]),
+    "vpk_model_forward_host_actions": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp]),
     "vpk_model_microbatch": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int32)]),
     "vpk_model_last_launch_count": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "vpk_model_set_timing": (C.c_int, [_vp, C.c_int32]),

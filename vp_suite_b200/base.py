@@ -274,7 +274,19 @@ class NativeRollout:
             pass
 
     # -- forward through the C ABI --------------------------------------------------------------------------------
-    def _native_forward(self, x, pred_frames, t_in, want_aux=False):
+    def _native_actions(self, kwargs, batch, device):
+        """The ``actions`` keyword of an action-conditional model as a contiguous fp32 [b, steps, action_size] tensor on
+        ``device`` (host tensor for device=None), validated like the reference (predrnn_v2.py:147-151, models/phydnet.py:100-105:
+        missing / all-zero-default or wrongly sized actions raise ValueError); None for other models."""
+        if not self.action_conditional:
+            return None
+        actions = kwargs.get("actions", None)
+        if actions is None or actions.dim() != 3 or actions.shape[0] != batch or actions.shape[-1] != self.action_size:
+            raise ValueError("Given actions are None or of the wrong size!")
+        actions = actions.detach().to(torch.float32)
+        return (actions.cpu() if device is None else actions.to(device)).contiguous()
+
+    def _native_forward(self, x, pred_frames, t_in, want_aux=False, actions=None):
         if not x.is_cuda:
             raise N.NativeError("vp_suite_b200 models run on CUDA tensors only (there is no CPU path); "
                                 "use forward_host() for host buffers")
@@ -294,11 +306,15 @@ class NativeRollout:
             self._workspaces[key] = ws
         stream = torch.cuda.current_stream(x.device).cuda_stream
         with torch.cuda.device(x.device):
-            N.check(lib.vpk_model_forward(h, N.ptr(x), b, t_in, pred_frames, N.ptr(out), N.ptr(aux), N.ptr(ws),
-                                          ws.numel(), C.c_void_p(stream)))
+            if actions is None:
+                N.check(lib.vpk_model_forward(h, N.ptr(x), b, t_in, pred_frames, N.ptr(out), N.ptr(aux), N.ptr(ws),
+                                              ws.numel(), C.c_void_p(stream)))
+            else:
+                N.check(lib.vpk_model_forward_actions(h, N.ptr(x), N.ptr(actions), actions.shape[1], b, t_in, pred_frames,
+                                                      N.ptr(out), N.ptr(aux), N.ptr(ws), ws.numel(), C.c_void_p(stream)))
         return out, aux
 
-    def forward_host(self, x, pred_frames=1, out=None):
+    def forward_host(self, x, pred_frames=1, out=None, **kwargs):
         """Same as ``forward`` for HOST tensors (pinned memory recommended): microbatches are staged through the
         device with copies overlapped with compute; returns host tensors.  ``out`` may be a caller-owned (pinned)
         result buffer; otherwise a pinned buffer owned by the module is reused across calls of the same shape."""
@@ -317,9 +333,15 @@ class NativeRollout:
         elif tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.is_cuda:
             raise ValueError("out must be a contiguous host fp32 tensor of shape %s" % (shape,))
         aux = torch.zeros(1, dtype=torch.float32)
+        actions = self._native_actions(kwargs, b, None)
         with torch.cuda.device(self._handle_device):
-            N.check(lib.vpk_model_forward_host(h, N.ptr(x), b, self._native_t_in(t_in, pred_frames), pred_frames,
-                                               N.ptr(out), N.ptr(aux)))
+            if actions is None:
+                N.check(lib.vpk_model_forward_host(h, N.ptr(x), b, self._native_t_in(t_in, pred_frames), pred_frames,
+                                                   N.ptr(out), N.ptr(aux)))
+            else:
+                N.check(lib.vpk_model_forward_host_actions(h, N.ptr(x), N.ptr(actions), actions.shape[1], b,
+                                                           self._native_t_in(t_in, pred_frames), pred_frames,
+                                                           N.ptr(out), N.ptr(aux)))
         return out, aux
 
     def _native_t_in(self, t_total, pred_frames):

@@ -156,6 +156,24 @@ int vpk_model_forward_host(vpk_model* m, const float* x_host, int32_t batch, int
   });
 }
 
+int vpk_model_forward_actions(vpk_model* m, const float* x, const float* actions, int32_t action_steps, int32_t batch,
+                              int32_t t_in, int32_t pred_frames, float* out, float* aux, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(m, "null argument");
+    m->impl->forward(x, batch, t_in, pred_frames, out, aux, workspace, workspace_bytes, static_cast<cudaStream_t>(stream),
+                     actions, action_steps);
+  });
+}
+
+int vpk_model_forward_host_actions(vpk_model* m, const float* x_host, const float* actions_host, int32_t action_steps,
+                                   int32_t batch, int32_t t_in, int32_t pred_frames, float* out_host, float* aux_host) {
+  return guarded([&] {
+    VPK_REQUIRE(m, "null argument");
+    m->impl->forward_host(x_host, batch, t_in, pred_frames, out_host, aux_host, actions_host, action_steps);
+  });
+}
+
 int vpk_model_microbatch(vpk_model* m, int32_t batch, int32_t* sequences) {
   return guarded([&] {
     VPK_REQUIRE(m && sequences && batch > 0, "bad argument");

@@ -44,6 +44,10 @@ struct LstmArgs {
   const float *wci, *wcf, *wco;   // device fp32 [H,W,C] (or [C/4,H,W,4] when c4) or nullptr
   bool c4 = false;          // c and the peepholes use the channel-quad layout [.., C/4, H, W, 4] (needs C % 4 == 0)
   const void* pp16 = nullptr;   // device: the three peepholes as packed bf16 [C/8][H][W][3][8] (tcgen05 epilogue), optional
+  // optional second input tensor concatenated BEHIND x (action-conditional SingleStepConvLSTM: the inflated action,
+  // model_blocks/phydnet.py:153-155): [B,H,W,C2p] with C2 real channels (C2p - C2 zero padding channels)
+  const void* x2 = nullptr;
+  int C2 = 0, C2p = 0;
 };
 inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   ConvSpec s;
@@ -55,7 +59,7 @@ inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   WeightRef w;
   w.w = a.weight;
   w.O = 4 * a.C;
-  w.I = a.Cin + a.C;
+  w.I = a.Cin + a.C2 + a.C;
   w.KH = w.KW = a.k;
   const int hz[4] = {0, 1, 2, 3}, nd[4] = {0, 1, 3, 2};   // packed gates are always (i, f, g, o)
   for (int g = 0; g < 4; ++g) w.gate_block[g] = a.order_ifog ? nd[g] : hz[g];
@@ -68,7 +72,12 @@ inline ConvSpec lstm_spec(const LstmArgs& a, const ActInfo& act) {
   }
   std::vector<ConvInput> in;
   if (a.x) in.push_back(ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0});
-  in.push_back(ConvInput{make_view(a.h_in, a.H, a.W, a.C), 0, a.Cin});
+  if (a.x2) {
+    ConvInput i2{make_view(a.x2, a.H, a.W, a.C2p), 0, a.Cin};
+    i2.wc_count = a.C2;
+    in.push_back(i2);
+  }
+  in.push_back(ConvInput{make_view(a.h_in, a.H, a.W, a.C), 0, a.Cin + a.C2});
   int oh, ow;
   lower_conv(s, a.k, 1, a.k / 2, in, a.H, a.W, act.esize, &oh, &ow);
   EpiParams& e = s.phases[0].epi;

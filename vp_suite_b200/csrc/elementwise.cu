@@ -888,6 +888,41 @@ __global__ void split_f16_kernel(const float* __restrict__ in, __half* __restric
   }
 }
 
+// ---- action-conditional helpers ----
+template <typename T> __device__ __forceinline__ T to_act(float v);
+template <> __device__ __forceinline__ float to_act<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half to_act<__half>(float v) { return __float2half_rn(v); }
+template <> __device__ __forceinline__ __nv_bfloat16 to_act<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+__device__ __forceinline__ float from_act(float v) { return v; }
+__device__ __forceinline__ float from_act(__half v) { return __half2float(v); }
+__device__ __forceinline__ float from_act(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// out[t][b][hw][ch] = ch < a ? actions[b * bstride + t * a + ch] : 0   (the action vector of step t, inflated spatially)
+template <typename T>
+__global__ void inflate_actions_kernel(const float* __restrict__ actions, long long bstride, int a, T* __restrict__ out, int B,
+                                       int Tn, int HW, int a_pad) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const long long total = static_cast<long long>(Tn) * B * HW * a_pad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int ch = static_cast<int>(i % a_pad);
+    const long long tb = i / (static_cast<long long>(a_pad) * HW);
+    const int b = static_cast<int>(tb % B), t = static_cast<int>(tb / B);
+    out[i] = to_act<T>(ch < a ? actions[b * bstride + static_cast<long long>(t) * a + ch] : 0.f);
+  }
+}
+
+// out = T(x + y) elementwise; x of type TX, y fp32 (or absent)
+template <typename TX, typename T>
+__global__ void add_to_act_kernel(const TX* __restrict__ x, const float* __restrict__ y, T* __restrict__ out, long long n) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = to_act<T>(from_act(x[i]) + (y != nullptr ? y[i] : 0.f));
+}
+
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
@@ -1089,6 +1124,30 @@ void launch_split_f16(const float* in, void* hi, void* lo, long long n, int num_
   VPK_REQUIRE(n % 4 == 0, "split_f16: element count must be a multiple of 4");
   launch_pdl(split_f16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__half*>(hi),
              static_cast<__half*>(lo), n / 4);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_inflate_actions(const float* actions, long long bstride, int a, void* out, int dtype, int B, int T, int HW,
+                            int a_pad, int num_sms, cudaStream_t stream) {
+  VPK_REQUIRE(a >= 1 && a <= a_pad && B > 0 && T > 0 && HW > 0, "inflate_actions: bad shape");
+  const int g = grid_for(static_cast<long long>(T) * B * HW * a_pad, 256, num_sms);
+  if (dtype == DT_F32) launch_pdl(inflate_actions_kernel<float>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<float*>(out), B, T, HW, a_pad);
+  else if (dtype == DT_F16) launch_pdl(inflate_actions_kernel<__half>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<__half*>(out), B, T, HW, a_pad);
+  else launch_pdl(inflate_actions_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<__nv_bfloat16*>(out), B, T, HW, a_pad);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_add_to_act(const void* x, int x_dtype, const float* y, void* out, int out_dtype, long long n, int num_sms,
+                       cudaStream_t stream) {
+  const int g = grid_for(n, 256, num_sms);
+#define VPK_ADD(TX, TO) launch_pdl(add_to_act_kernel<TX, TO>, dim3(g), dim3(256), 0, stream, static_cast<const TX*>(x), y, static_cast<TO*>(out), n)
+  if (x_dtype == DT_F32 && out_dtype == DT_F32) VPK_ADD(float, float);
+  else if (x_dtype == DT_F32 && out_dtype == DT_F16) VPK_ADD(float, __half);
+  else if (x_dtype == DT_F32 && out_dtype == DT_BF16) VPK_ADD(float, __nv_bfloat16);
+  else if (x_dtype == DT_F16 && out_dtype == DT_F16) VPK_ADD(__half, __half);
+  else if (x_dtype == DT_BF16 && out_dtype == DT_BF16) VPK_ADD(__nv_bfloat16, __nv_bfloat16);
+  else VPK_THROW(1, "add_to_act: unsupported dtype combination");
+#undef VPK_ADD
   VPK_CUDA(cudaGetLastError());
 }
 

@@ -72,6 +72,13 @@ void launch_metric_ssim_sums(const float* pred, const float* target, int B, int 
                              double* out, cudaStream_t stream);
 void launch_cast_f32_to_f16(const float* in, void* out, long long n, int num_sms, cudaStream_t stream);   // n % 4 == 0
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
+// action-conditional models: actions fp32 [B, *, a] (sequence stride `bstride` elements), steps 0..T-1 ->
+// out (activation type) [T][B][HW][a_pad], channels a..a_pad-1 zero (the action vector inflated to the frame size)
+void launch_inflate_actions(const float* actions, long long bstride, int a, void* out, int dtype, int B, int T, int HW,
+                            int a_pad, int num_sms, cudaStream_t stream);
+// out = x + y (y fp32 or nullptr: a plain conversion), x of x_dtype, out of out_dtype
+void launch_add_to_act(const void* x, int x_dtype, const float* y, void* out, int out_dtype, long long n, int num_sms,
+                       cudaStream_t stream);
 // fp32 -> split-fp16: hi = fp16(v), lo = fp16(v - hi)   (n % 4 == 0)
 void launch_split_f16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream);
 

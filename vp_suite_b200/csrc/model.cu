@@ -25,6 +25,8 @@ struct Model::HostPipe {
   void* d_out[2] = {nullptr, nullptr};
   void* ws = nullptr;
   float* d_aux = nullptr;
+  float* d_actions = nullptr;
+  size_t act_bytes = 0;
   size_t x_bytes = 0, out_bytes = 0, ws_bytes = 0;
   cudaStream_t s_in = nullptr, s_comp = nullptr, s_out = nullptr;
   cudaEvent_t ev_in[2], ev_comp[2], ev_out[2];
@@ -38,6 +40,7 @@ struct Model::HostPipe {
     }
     if (ws) cudaFree(ws);
     if (d_aux) cudaFree(d_aux);
+    if (d_actions) cudaFree(d_actions);
     for (cudaEvent_t e : ev_frame) cudaEventDestroy(e);
     for (cudaEvent_t e : ev_in_frame) cudaEventDestroy(e);
     if (init) {
@@ -114,7 +117,8 @@ float* Model::dev_f32(const std::string& name, const std::vector<float>& host, c
   return d;
 }
 
-void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream, int dt_override) {
+void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream, int dt_override,
+                     std::vector<Op>* dst) {
   const int dt = dt_override >= 0 ? dt_override : dtype;
   std::vector<BuiltConv> built = build_conv(spec, dt, backend, store, packed_cache, stream, num_sms, measure);
   if (measure) return;
@@ -137,7 +141,7 @@ void Model::add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStre
       ConvLaunch L = bc.L;
       op.fn = [L, dt](cudaStream_t s, const RunCtx&) { launch_conv_simt(L, dt, s); };
     }
-    prog.body.push_back(std::move(op));
+    (dst != nullptr ? *dst : prog.body).push_back(std::move(op));
   }
 }
 
@@ -279,12 +283,22 @@ void Model::gemm_stats(float* ms, int64_t* launches, double* flops) {
   *flops = timed_flops;
 }
 
+void Model::check_actions(const float* actions, int action_steps, int t_in, int pred) const {
+  const int need = action_steps_needed(t_in, pred);
+  // the reference raises ValueError (predrnn_v2.py:149-151, models/phydnet.py:103-105)
+  if (need > 0 && (actions == nullptr || action_steps < need))
+    VPK_THROW(1, "Given actions are None or of the wrong size! (an action-conditional model needs actions[:, 0:" +
+                     std::to_string(need) + "])");
+}
+
 void Model::forward(const float* x, int batch, int t_in, int pred, float* out, float* aux, void* ws, size_t ws_bytes,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const float* actions, int action_steps) {
   VPK_REQUIRE(finalized, "forward before finalize");
   VPK_REQUIRE(x != nullptr && out != nullptr && ws != nullptr, "null buffer");
   VPK_REQUIRE(batch > 0 && pred > 0 && t_in > 0, "bad batch / frame counts");
   validate(t_in, pred);
+  check_actions(actions, action_steps, t_in, pred);
+  const size_t act_stride = static_cast<size_t>(action_steps) * std::max(0, desc.action_size);
   last_launches = 0;
   ev_used = 0;
   ev_names.clear();
@@ -299,6 +313,10 @@ void Model::forward(const float* x, int batch, int t_in, int pred, float* out, f
     const int nb = std::min(mb, batch - mb0);
     Program* prog = get_program(nb, t_in, pred, ws, ws_bytes, stream);
     RunCtx ctx{x + mb0 * in_stride, out + mb0 * out_stride, aux, mb0, nb, batch};
+    if (actions != nullptr) {
+      ctx.actions = actions + mb0 * act_stride;
+      ctx.action_steps = action_steps;
+    }
     run_ops(prog->pre, stream, ctx);
     if (prog->graph != nullptr && timing == 0) {
       VPK_CUDA(cudaGraphLaunch(prog->graph, stream));
@@ -312,10 +330,12 @@ void Model::forward(const float* x, int batch, int t_in, int pred, float* out, f
   end_call(batch, aux, stream);
 }
 
-void Model::forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux) {
+void Model::forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux, const float* actions,
+                         int action_steps) {
   VPK_REQUIRE(finalized, "forward before finalize");
   VPK_REQUIRE(x != nullptr && out != nullptr, "null buffer");
   validate(t_in, pred);
+  check_actions(actions, action_steps, t_in, pred);
   const int mb = microbatch(batch);
   const size_t in_stride = static_cast<size_t>(in_frames(t_in, pred)) * desc.img_c * desc.img_h * desc.img_w;
   const size_t out_stride = static_cast<size_t>(pred) * desc.img_c * desc.img_h * desc.img_w;
@@ -357,6 +377,17 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
   timed_flops = 0;
   timed_launches = 0;
   begin_call(batch, t_in, pred, hpipe.d_aux, hpipe.s_comp);
+  // actions of the whole call (a few KB): one copy ahead of the first microbatch, on the compute stream
+  const size_t act_stride = static_cast<size_t>(action_steps) * std::max(0, desc.action_size);
+  if (actions != nullptr && act_stride > 0) {
+    const size_t ab = static_cast<size_t>(batch) * act_stride * sizeof(float);
+    if (ab > hpipe.act_bytes) {
+      if (hpipe.d_actions) cudaFree(hpipe.d_actions);
+      VPK_CUDA(cudaMalloc(&hpipe.d_actions, ab));
+      hpipe.act_bytes = ab;
+    }
+    VPK_CUDA(cudaMemcpyAsync(hpipe.d_actions, actions, ab, cudaMemcpyHostToDevice, hpipe.s_comp));
+  }
   int it = 0;
   for (int mb0 = 0; mb0 < batch; mb0 += mb, ++it) {
     const int nb = std::min(mb, batch - mb0);
@@ -422,6 +453,10 @@ void Model::forward_host(const float* x, int batch, int t_in, int pred, float* o
     };
     RunCtx ctx{static_cast<const float*>(hpipe.d_x[buf]), static_cast<float*>(hpipe.d_out[buf]), hpipe.d_aux, mb0, nb,
                batch};
+    if (actions != nullptr && act_stride > 0) {
+      ctx.actions = hpipe.d_actions + mb0 * act_stride;
+      ctx.action_steps = action_steps;
+    }
     const int nf_in = used_in_frames(t_in, pred);
     const std::function<void(int, cudaStream_t)> on_input = [&](int f, cudaStream_t s) {
       VPK_CUDA(cudaStreamWaitEvent(s, hpipe.ev_in_frame[buf * nf_in + f], 0));

@@ -34,6 +34,9 @@ struct RunCtx {          // pointers of the current microbatch (already offset)
   // host-buffer entry only: called right BEFORE an op that is the first to read input frame Op::needs_input, so that
   // the compute stream waits for that frame's host-to-device copy only (the frames arrive one by one)
   const std::function<void(int frame, cudaStream_t)>* on_input = nullptr;
+  // action-conditional models: DEVICE fp32 [nb, action_steps, action_size] of this microbatch (nullptr otherwise)
+  const float* actions = nullptr;
+  int action_steps = 0;
 };
 
 struct Op {
@@ -70,8 +73,9 @@ class Model {
   void finalize(cudaStream_t stream);
   size_t workspace_bytes(int batch, int t_in, int pred);
   void forward(const float* x, int batch, int t_in, int pred, float* out, float* aux, void* ws, size_t ws_bytes,
-               cudaStream_t stream);
-  void forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux);
+               cudaStream_t stream, const float* actions = nullptr, int action_steps = 0);
+  void forward_host(const float* x, int batch, int t_in, int pred, float* out, float* aux, const float* actions = nullptr,
+                    int action_steps = 0);
 
   int microbatch(int batch) const;
 
@@ -87,6 +91,9 @@ class Model {
   // ---- implemented by the concrete rollouts ----
   virtual void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) = 0;
   virtual void validate(int t_in, int pred) const {}
+  // rollout steps that read an action vector (0: the model is not action-conditional)
+  virtual int action_steps_needed(int t_in, int pred) const { return 0; }
+  void check_actions(const float* actions, int action_steps, int t_in, int pred) const;
   virtual int default_microbatch() const { return 64; }
   virtual int in_frames(int t_in, int pred) const { return t_in; }
   // frames of each input sequence the rollout really reads (the host entry copies only these to the device)
@@ -106,7 +113,10 @@ class Model {
   bool has(const std::string& key) const;
   float* dev_f32(const std::string& name, const std::vector<float>& host, cudaStream_t stream);  // cached upload
   // dt: operand type of this launch (-1: the model's precision); lets one program mix bf16 cells with fp32 convs
-  void add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream, int dt = -1);
+  // dst: op list the launches are appended to (nullptr: prog.body); ops that read RunCtx pointers of the CALL (input
+  // frames, actions) and everything feeding only on them may go to prog.pre, which is never part of a captured graph
+  void add_conv(Program& prog, const ConvSpec& spec, bool measure, cudaStream_t stream, int dt = -1,
+                std::vector<Op>* dst = nullptr);
   void add_memset(Program& prog, void* p, size_t bytes, const char* name);
   int esize() const { return static_cast<int>(dtype_size(dtype)); }
   SrcView dense_view(void* p, int H, int W, int C) const {

@@ -46,6 +46,9 @@ class PhyDNetModel : public Model {
     kp = d.phycell_kernel_size;
     n_lstm = d.convlstm_n_layers;
     kl = d.convlstm_kernel_size;
+    ac = d.action_conditional != 0 && !branch;
+    a_sz = ac ? d.action_size : 0;
+    VPK_REQUIRE(!ac || a_sz > 0, "action-conditional phy needs action_size > 0");
     VPK_REQUIRE(n_phy >= 1 && n_phy <= 4 && hid > 0 && kp % 2 == 1, "bad PhyCell hyper-parameters");
     VPK_REQUIRE(n_lstm >= 1 && n_lstm <= 8 && kl % 2 == 1, "bad ConvLSTM hyper-parameters");
     const int c = d.img_c;
@@ -80,8 +83,14 @@ class PhyDNetModel : public Model {
       declare(p + "F.conv2.bias", {64});
       declare(p + "convgate.weight", {64, 128, 3, 3});
       declare(p + "convgate.bias", {64});
+      if (ac) {                 // model_blocks/phydnet.py:44-48
+        declare(p + "frame_action_conv.weight", {64, 64 + a_sz, 1, 1});
+        declare(p + "frame_action_conv.bias", {64});
+        declare(p + "hidden_action_conv.weight", {64, 64 + a_sz, 1, 1});
+        declare(p + "hidden_action_conv.bias", {64});
+      }
     }
-    int cin = 64;
+    int cin = 64 + (ac ? a_sz : 0);    // SingleStepConvLSTM: the inflated action joins the bottom layer's input (:137, 153-155)
     for (int j = 0; j < n_lstm; ++j) {
       const int hd = d.convlstm_hidden_dims[j];
       VPK_REQUIRE(hd > 0, "bad convlstm_hidden_dims");
@@ -97,6 +106,8 @@ class PhyDNetModel : public Model {
  protected:
   int default_microbatch() const override { return 256; }
   bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_NO_INPUT_STREAM") == nullptr; }
+  // one action per encoder_fwd call: ac_index runs over the context and the predicted steps (models/phydnet.py:108-122)
+  int action_steps_needed(int t_in, int pred) const override { return ac ? t_in - 1 + pred : 0; }
 
   std::vector<float> vec(const std::string& key) const {
     const HostParam& p = params.at(key);
@@ -162,7 +173,8 @@ class PhyDNetModel : public Model {
     // frames (batch t_in * B -- GroupNorm is per sample, so the frames are just more samples), instead of t_in times on
     // B sequences; the step loop then only consumes their outputs.  Fed-back frames are encoded per step as before.
     // (tcgen05 / fp16-feature path; ~100 short launches fewer per cfg-2 rollout.)
-    const bool batch_ctx = f16 && pad8 && t_in >= 2 && getenv("VPK_NO_CTX_BATCH") == nullptr;
+    // (action-conditional: PhyCell's frame input is needed in fp32 per step -- kept per step for simplicity)
+    const bool batch_ctx = f16 && pad8 && t_in >= 2 && !ac && getenv("VPK_NO_CTX_BATCH") == nullptr;
     const size_t tb = batch_ctx ? static_cast<size_t>(t_in) : 1;     // buffers shared by both uses are sized for t_in * B
     float* raw = static_cast<float*>(arena.alloc(std::max(px2 * 32, px4 * 64) * 4 * tb));   // pre-GroupNorm conv output
     Feat e1 = feat(px2 * 32 * tb), e2 = feat(px2 * 32 * tb), e3 = feat(px4 * 64 * tb), mid = feat(px4 * 64 * tb);
@@ -189,6 +201,24 @@ class PhyDNetModel : public Model {
       hb[2 * j] = arena.alloc(px4 * hd * esz_c);
       hb[2 * j + 1] = arena.alloc(px4 * hd * esz_c);
       cb[j] = static_cast<float*>(arena.alloc(px4 * hd * 4));
+    }
+    // action-conditional: inflated actions of every step (fp32 for PhyCell's 1x1 action convs, cell type for the ConvLSTM
+    // gate conv), PhyCell's fp32 frame input and the convolved frame / hidden (fp32 + cell-type copies)
+    const int n_steps_all = (t_in - 1) + pred;
+    const int a_pad = 8;
+    float* act32 = nullptr;
+    char* act16 = nullptr;
+    float *ep32 = nullptr, *fa32 = nullptr, *ha32 = nullptr;
+    void *fa_act = nullptr, *ha_act = nullptr;
+    if (ac) {
+      VPK_REQUIRE(a_sz <= a_pad, "action_size above 8 is not supported by the action-conditional phy rollout");
+      act32 = static_cast<float*>(arena.alloc(px4 * a_pad * 4 * n_steps_all));
+      act16 = (cdt == DT_F32) ? reinterpret_cast<char*>(act32) : static_cast<char*>(arena.alloc(px4 * a_pad * esz_c * n_steps_all));
+      ep32 = static_cast<float*>(arena.alloc(px4 * 64 * 4));
+      fa32 = static_cast<float*>(arena.alloc(px4 * 64 * 4));
+      ha32 = static_cast<float*>(arena.alloc(px4 * 64 * 4));
+      fa_act = (cdt == DT_F32) ? static_cast<void*>(fa32) : arena.alloc(px4 * 64 * esz_c);
+      ha_act = (cdt == DT_F32) ? static_cast<void*>(ha32) : arena.alloc(px4 * 64 * esz_c);
     }
     float* h_top32 = static_cast<float*>(arena.alloc(px4 * 64 * 4));
     float* dp = static_cast<float*>(arena.alloc(px4 * 64 * 4));
@@ -314,6 +344,18 @@ class PhyDNetModel : public Model {
       };
       dst.push_back(std::move(cv));
     };
+    if (!measure && ac) {
+      const int HW4 = h4 * w4, steps = n_steps_all, asz = a_sz;
+      Op inf;
+      inf.name = "inflate_actions";
+      inf.fn = [=](cudaStream_t s, const RunCtx& rc) {
+        VPK_REQUIRE(rc.actions != nullptr && rc.action_steps >= steps, "Given actions are None or of the wrong size!");
+        const long long bs = static_cast<long long>(rc.action_steps) * asz;
+        launch_inflate_actions(rc.actions, bs, asz, act32, DT_F32, B, steps, HW4, a_pad, ns, s);
+        if (cdt != DT_F32) launch_inflate_actions(rc.actions, bs, asz, act16, cdt, B, steps, HW4, a_pad, ns, s);
+      };
+      prog.pre.push_back(std::move(inf));
+    }
     if (!measure) {
       if (!stream_in) convert_frames(prog.pre, 0, t_in, false);
       if (!branch_only) {
@@ -350,7 +392,8 @@ class PhyDNetModel : public Model {
       dcgan("encoder_E.c3.", false, e2, false, h2, w2, 32, 64, 2, OUT_FEAT, e3, nullptr);
       if (!branch_only) {
         dcgan("encoder_Ep.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
-        dcgan("encoder_Ep.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{ep_out, nullptr}, nullptr);
+        if (ac) dcgan("encoder_Ep.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_F32, Feat{ep32, nullptr}, nullptr);
+        else dcgan("encoder_Ep.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{ep_out, nullptr}, nullptr);
       }
       dcgan("encoder_Er.c1.", false, e3, false, h4, w4, 64, 64, 1, OUT_FEAT, mid, nullptr);
       dcgan("encoder_Er.c2.", false, mid, false, h4, w4, 64, 64, 1, OUT_CELL, Feat{er_out, nullptr}, nullptr);
@@ -410,9 +453,57 @@ class PhyDNetModel : public Model {
           const std::string p = "phycell.cell_list." + std::to_string(j) + ".";
           const void* h_act = hp_act[2 * j + ppar[j]];
           void* h_act_new = hp_act[2 * j + (ppar[j] ^ 1)];
+          const float* h_res = nullptr;
+          if (ac) {
+            // frame = frame_action_conv(cat[frame, action]), hidden = hidden_action_conv(cat[hidden, action]) (1x1 convs,
+            // model_blocks/phydnet.py:50-55): fp32 operands on the CUDA cores straight from the fp32 frame / state (K = 64 +
+            // a: negligible work; rounding the carried state to 16 bits here would enter h' directly)
+            const float* frame32 = (j == 0) ? ep32 : hp_master[j - 1];
+            const float* a32 = act32 + static_cast<size_t>(st) * px4 * a_pad;
+            auto action_conv = [&](const std::string& key, const float* src, float* out32, void* out_act) {
+              ConvSpec s1;
+              s1.name = p + key + ".";
+              s1.B = B;
+              s1.G = 1;
+              s1.C = 64;
+              WeightRef wr;
+              wr.w = hp(p + key + ".weight");
+              wr.O = 64;
+              wr.I = 64 + a_sz;
+              wr.KH = wr.KW = 1;
+              s1.wrefs.push_back(wr);
+              BiasRef br;
+              br.b = hp(p + key + ".bias");
+              s1.biases.push_back(br);
+              ConvInput i0{make_view(src, h4, w4, 64), 0, 0};
+              ConvInput i1{make_view(a32, h4, w4, a_pad), 0, 64};
+              i1.wc_count = a_sz;
+              int oh_, ow_;
+              lower_conv(s1, 1, 1, 0, {i0, i1}, h4, w4, 4, &oh_, &ow_);
+              EpiParams& e = s1.phases[0].epi;
+              e.kind = EPI_BIAS_ACT;
+              e.act = ACT_NONE;
+              e.out_f32 = 1;
+              dense_out(e, out32, h4, w4, 64);
+              add_conv(prog, s1, measure, stream, DT_F32);
+              if (!measure && cdt != DT_F32) {
+                const long long n = static_cast<long long>(px4) * 64;
+                Op op;
+                op.name = p + key + ".cast";
+                op.fn = [=](cudaStream_t s, const RunCtx&) { launch_add_to_act(out32, DT_F32, nullptr, out_act, cdt, n, ns, s); };
+                prog.body.push_back(std::move(op));
+              }
+            };
+            action_conv("frame_action_conv", frame32, fa32, fa_act);
+            action_conv("hidden_action_conv", hp_master[j], ha32, ha_act);
+            xin = fa_act;
+            h_act = ha_act;
+            h_res = ha32;
+          }
           PhyCellArgs pa{p, B, h4, w4, 64, hid, kp, xin, h_act, h_act_new, hp_master[j], htilde[j], f1raw, f1n,
                          hp(p + "F.conv1.weight"), hp(p + "F.conv1.bias"), hp(p + "F.conv2.weight"),
                          hp(p + "F.conv2.bias"), hp(p + "convgate.weight"), hp(p + "convgate.bias")};
+          pa.h_res = h_res;
           std::vector<ConvSpec> specs = phycell_specs(pa, ca);
           add_conv(prog, specs[0], measure, stream, cdt);
           // tcgen05 path: GroupNorm + 1x1 conv2 + residual in one kernel (phy_f_tail_kernel), then the gate conv
@@ -424,7 +515,7 @@ class PhyDNetModel : public Model {
               const float* w2 = dev_f32(p + "F.conv2.weight", vec(p + "F.conv2.weight"), stream);
               const float* b2 = dev_f32(p + "F.conv2.bias", vec(p + "F.conv2.bias"), stream);
               const int HW = h4 * w4, hid_ = hid;
-              float* hm = hp_master[j];
+              const float* hm = h_res ? h_res : hp_master[j];
               float* ht = htilde[j];
               Op op;
               op.name = p + "F.tail (GroupNorm + conv2 + h)";
@@ -469,6 +560,11 @@ class PhyDNetModel : public Model {
           LstmArgs la{p, B, h4, w4, cin, hd, kl, xin, hb[2 * j + lpar[j]], hb[2 * j + (lpar[j] ^ 1)], cb[j],
                       hp(p + "weight"), hp(p + "bias"), true, nullptr, nullptr, nullptr};
           la.c4 = true;
+          if (ac && j == 0) {
+            la.x2 = act16 + static_cast<size_t>(st) * px4 * a_pad * esz_c;
+            la.C2 = a_sz;
+            la.C2p = a_pad;
+          }
           ConvSpec s = lstm_spec(la, ca);
           if (j == n_lstm - 1) s.phases[0].epi.h32 = h_top32;
           add_conv(prog, s, measure, stream, cdt);
@@ -555,6 +651,8 @@ class PhyDNetModel : public Model {
  private:
   bool branch_only;
   bool feat_split = false;     // VPK_FEAT_SPLIT=1: split-bf16 feature maps instead of fp16
+  bool ac = false;             // action_conditional (models/phydnet.py; model_blocks/phydnet.py:44-55, 153-155)
+  int a_sz = 0;
   int n_phy = 1, hid = 49, kp = 7, n_lstm = 3, kl = 3;
 };
 

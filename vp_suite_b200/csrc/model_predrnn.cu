@@ -33,23 +33,45 @@ class PredRnnV2 : public Model {
     cp = p * p * d.img_c;
     hp_ = d.img_h / p;
     wp_ = d.img_w / p;
+    ac = d.action_conditional != 0;
+    if (ac) {
+      // action_conditional forces conv_actions_on_input (predrnn_v2.py:65-67): the cells run on a latent a quarter of the
+      // patch grid's size (:73-75), reached by two stride-2 convs and left by two stride-2 transposed convs (:76-90)
+      VPK_REQUIRE(d.action_size > 0, "action-conditional predrnn-pp needs action_size > 0");
+      VPK_REQUIRE(hp_ % 4 == 0 && wp_ % 4 == 0, "action-conditional predrnn-pp needs a patch grid that is a multiple of 4");
+      VPK_REQUIRE(C % 2 == 0, "num_hidden must be even");
+      rh = hp_ / 4;
+      rw = wp_ / 4;
+      declare("conv_input1.weight", {C / 2, cp, k, k});
+      declare("conv_input2.weight", {C, C / 2, k, k});
+      declare("action_conv_input1.weight", {C / 2, d.action_size, k, k});
+      declare("action_conv_input2.weight", {C, C / 2, k, k});
+      declare("deconv_output1.weight", {C, C / 2, k, k});            // ConvTranspose2d: [Cin, Cout, k, k]
+      declare("deconv_output2.weight", {C / 2, cp, k, k});
+    } else {
+      rh = hp_;
+      rw = wp_;
+    }
     for (int i = 0; i < L; ++i) {
       const std::string pre = "cell_list." + std::to_string(i) + ".";
-      const int cin = (i == 0) ? cp : C;
-      declare(pre + "conv_x.0.weight", {7 * C, cin, k, k});
-      declare(pre + "conv_h.0.weight", {4 * C, C, k, k});
-      declare(pre + "conv_m.0.weight", {3 * C, C, k, k});
-      declare(pre + "conv_o.0.weight", {C, 2 * C, k, k});
-      declare(pre + "conv_last.weight", {C, 2 * C, 1, 1});
-      if (d.layer_norm) {
-        const std::pair<const char*, int> lns[4] = {{"conv_x", 7}, {"conv_h", 4}, {"conv_m", 3}, {"conv_o", 1}};
-        for (const auto& ln : lns) {
-          declare(pre + ln.first + ".1.weight", {ln.second * C, hp_, wp_});
-          declare(pre + ln.first + ".1.bias", {ln.second * C, hp_, wp_});
+      const int cin = (i == 0 && !ac) ? cp : C;
+      // ActionConditionalSpatioTemporalLSTMCell's convs have biases and a fifth conv, conv_a (model_blocks/predrnn.py:104-139)
+      std::vector<std::pair<std::string, std::pair<int, int>>> convs = {{"conv_x", {7, cin}}, {"conv_h", {4, C}}};
+      if (ac) convs.push_back({"conv_a", {4, C}});
+      convs.push_back({"conv_m", {3, C}});
+      convs.push_back({"conv_o", {1, 2 * C}});
+      for (const auto& cv : convs) {
+        declare(pre + cv.first + ".0.weight", {cv.second.first * C, cv.second.second, k, k});
+        if (ac) declare(pre + cv.first + ".0.bias", {cv.second.first * C});
+        if (d.layer_norm) {
+          declare(pre + cv.first + ".1.weight", {cv.second.first * C, rh, rw});
+          declare(pre + cv.first + ".1.bias", {cv.second.first * C, rh, rw});
         }
       }
+      declare(pre + "conv_last.weight", {C, 2 * C, 1, 1});
+      if (ac) declare(pre + "conv_last.bias", {C});
     }
-    declare("conv_last.weight", {cp, C, 1, 1});
+    if (!ac) declare("conv_last.weight", {cp, C, 1, 1});             // (non-existent with conv_actions_on_input, :110-116)
     declare("adapter.weight", {C, C, 1, 1});
   }
   ~PredRnnV2() override {
@@ -65,6 +87,7 @@ class PredRnnV2 : public Model {
   // eval mode reads the context frames only (the mask is all zero, predrnn_v2.py:300-309): the target frames that
   // NEEDS_COMPLETE_INPUT puts behind them never have to reach the device
   int used_in_frames(int t_in, int pred) const override { return t_in - pred; }
+  int action_steps_needed(int t_in, int) const override { return ac ? t_in - 1 : 0; }
   bool streams_input() const override { return !desc.use_cuda_graph && getenv("VPK_NO_INPUT_STREAM") == nullptr; }
 
   void begin_call(int, int t_in, int, float*, cudaStream_t stream) override {
@@ -93,6 +116,10 @@ class PredRnnV2 : public Model {
     const int ctx = t_in - pred;
     const size_t px = static_cast<size_t>(B) * hp_ * wp_;
     if (!measure && !d_loss) VPK_CUDA(cudaMalloc(&d_loss, sizeof(double)));
+    if (ac) {
+      build_ac(prog, arena, B, t_in, pred, measure, stream);
+      return;
+    }
 
     // only the context frames are ever read (eval mask = 0): patchify those
     char* xp = static_cast<char*>(arena.alloc(px * cp * esz * ctx));
@@ -366,12 +393,12 @@ class PredRnnV2 : public Model {
 
   // statistics slots per sample the tcgen05 epilogue of a G = 1 conv with `co` output channels writes (epilogue slot rule
   // in common.h: ((tile in image) * n_tiles + N tile) * 8 + quadrant * 2 + half)
-  int ln_slots(int co) const { return ((hp_ + 15) / 16) * ((wp_ + 7) / 8) * conv_n_tiles(co, 1) * 8; }
+  int ln_slots(int co) const { return ((rh + 15) / 16) * ((rw + 7) / 8) * conv_n_tiles(co, 1) * 8; }
 
   // LayerNorm affine of `key` ([kC, H, W] in the reference) repacked to the NHWC order of the raw conv outputs
   const float* ln_param(const std::string& key, int kc, cudaStream_t stream) {
     const float* src = hp(key);
-    const int HW = hp_ * wp_;
+    const int HW = rh * rw;
     std::vector<float> v(static_cast<size_t>(kc) * HW);
     for (int ch = 0; ch < kc; ++ch)
       for (int q = 0; q < HW; ++q) v[static_cast<size_t>(q) * kc + ch] = src[static_cast<size_t>(ch) * HW + q];
@@ -402,7 +429,7 @@ class PredRnnV2 : public Model {
     // same activation tile, 3 = split weights and activations), counted once in the algorithmic FLOPs.
     auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& wkey, float* out,
                         float* stat, int nslots, const void* in_lo = nullptr, bool precise = false) {
-      ConvArgs a{pre + name, B, hp_, wp_, ci, co, kk, 1, kk / 2, in, hp(pre + wkey), nullptr, ACT_NONE, out};
+      ConvArgs a{pre + name, B, rh, rw, ci, co, kk, 1, kk / 2, in, hp(pre + wkey), nullptr, ACT_NONE, out};
       a.out_f32_dense = true;
       if (precise && products == 2) a.w_split = true;
       if (precise && products == 3) {
@@ -432,7 +459,7 @@ class PredRnnV2 : public Model {
     raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw, fuse_stats ? px_ : nullptr, nsx, lo.x, true);
     raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw, fuse_stats ? ph_ : nullptr, nsh, lo.h_in, true);
     raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw, fuse_stats ? pm_ : nullptr, nsm, lo.m_act, true);
-    const int HW = hp_ * wp_, CC = C, ns = num_sms, dt = act.dtype;
+    const int HW = rh * rw, CC = C, ns = num_sms, dt = act.dtype;
     if (!measure) {
       if (!fuse_stats) {
         LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
@@ -472,8 +499,387 @@ class PredRnnV2 : public Model {
     }
   }
 
+
+  // ==================================================================================================================
+  // action_conditional=True (predrnn_v2.py:65-90, 147-152, 178-221; cell: model_blocks/predrnn.py:86-169).
+  //
+  // Per step t: the patch frame (real for t < context, the model's x_gen afterwards -- the reverse-sampling eval mask is 1
+  // exactly on the context steps, :306-308) goes through conv_input1 / conv_input2 (k x k, stride 2, no bias, no
+  // activation) down to the (patch_h / 4) x (patch_w / 4) latent; the action vector, inflated to the patch grid (:151),
+  // through action_conv_input1 / 2 likewise -- all steps' actions are known up front, so those two convs run ONCE, time-
+  // batched over (t_in - 1) * B samples, in the program's pre ops.  Cells: raw convs (bias in the epilogue; fp32 outputs,
+  // per-sample LayerNorm statistics from the epilogue when layer_norm) + the action-conditional gate kernel + conv_o /
+  // conv_last + the output kernel.  x_gen = deconv_output2(deconv_output1(h_top + net2) + net1) (:213-215, residuals
+  // optional).  16-bit mode uses FP16 operands throughout (raw fp32 conv outputs, like the LayerNorm rollout).
+  // ==================================================================================================================
+  void build_ac(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) {
+    const vpk_model_desc& d = desc;
+    const bool ln = d.layer_norm != 0;
+    const bool resid = d.residual_on_action_conv != 0;
+    const int adt = (dtype == DT_BF16) ? DT_F16 : dtype;
+    const ActInfo act{adt, esize()};
+    const int esz = esize();
+    const int c = d.img_c, h = d.img_h, w = d.img_w, a_sz = d.action_size;
+    const int ctx = t_in - pred, steps = t_in - 1;
+    const int h2 = hp_ / 2, w2 = wp_ / 2;
+    const int a_pad = (a_sz + 7) / 8 * 8;
+    const size_t px = static_cast<size_t>(B) * hp_ * wp_, px2 = static_cast<size_t>(B) * h2 * w2,
+                 px4 = static_cast<size_t>(B) * rh * rw;
+    const int ns = num_sms;
+    const bool f32 = adt == DT_F32;
+    // two fp16 products (split weights) for the LayerNorm-fed convs in 16-bit mode, as VPK_LN_PRODUCTS=2 of the plain rollout
+    int products = (ln && !f32) ? 2 : 1;
+    if (const char* env = getenv("VPK_LN_PRODUCTS")) products = std::min(products, std::max(1, atoi(env)));
+    if (((C + 63) / 64) * products * k * k > kMaxSteps) products = 1;
+
+    char* xp = static_cast<char*>(arena.alloc(px * cp * esz * ctx));
+    float* out_stage = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * pred * c * h * w * sizeof(float)));
+    // inflated actions and their two convs, all steps at once: [steps][B][...]
+    void* a_inf = arena.alloc(px * a_pad * esz * steps);
+    float* a1_32 = static_cast<float*>(arena.alloc(px2 * (C / 2) * sizeof(float) * steps));
+    void* a1 = f32 ? static_cast<void*>(a1_32) : arena.alloc(px2 * (C / 2) * esz * steps);
+    float* a2_32 = static_cast<float*>(arena.alloc(px4 * C * sizeof(float) * steps));
+    char* a2 = f32 ? reinterpret_cast<char*>(a2_32) : static_cast<char*>(arena.alloc(px4 * C * esz * steps));
+    // per-step input path
+    float* n1_32 = static_cast<float*>(arena.alloc(px2 * (C / 2) * sizeof(float)));
+    void* n1 = f32 ? static_cast<void*>(n1_32) : arena.alloc(px2 * (C / 2) * esz);
+    float* n2_32 = static_cast<float*>(arena.alloc(px4 * C * sizeof(float)));
+    void* n2 = f32 ? static_cast<void*>(n2_32) : arena.alloc(px4 * C * esz);
+    // cells
+    std::vector<void*> hb(2 * L), memb(2 * L);
+    std::vector<float*> cb(L);
+    for (int i = 0; i < L; ++i) {
+      hb[2 * i] = arena.alloc(px4 * C * esz);
+      hb[2 * i + 1] = arena.alloc(px4 * C * esz);
+      memb[2 * i] = arena.alloc(px4 * 2 * C * esz);
+      memb[2 * i + 1] = arena.alloc(px4 * 2 * C * esz);
+      cb[i] = static_cast<float*>(arena.alloc(px4 * C * sizeof(float)));
+    }
+    float* mstate = static_cast<float*>(arena.alloc(px4 * C * sizeof(float)));
+    float* opart = static_cast<float*>(arena.alloc(px4 * C * sizeof(float)));
+    char* dcdm = static_cast<char*>(arena.alloc(2 * px4 * C * esz));
+    float* adapt = static_cast<float*>(arena.alloc(2 * px4 * C * sizeof(float)));
+    float* xraw = static_cast<float*>(arena.alloc(px4 * 7 * C * sizeof(float)));
+    float* hraw = static_cast<float*>(arena.alloc(px4 * 4 * C * sizeof(float)));
+    float* araw = static_cast<float*>(arena.alloc(px4 * 4 * C * sizeof(float)));
+    float* mraw = static_cast<float*>(arena.alloc(px4 * 3 * C * sizeof(float)));
+    float* oraw = static_cast<float*>(arena.alloc(px4 * C * sizeof(float)));
+    float* lraw = static_cast<float*>(arena.alloc(px4 * C * sizeof(float)));
+    const size_t slots = std::max<size_t>(4 * kLnSlices, static_cast<size_t>(ln_slots(7 * C)) + 2 * ln_slots(4 * C) + ln_slots(3 * C));
+    lnpart_floats = static_cast<size_t>(B) * slots * 2;
+    float* lnpart = static_cast<float*>(arena.alloc(lnpart_floats * sizeof(float)));
+    void* m_act = arena.alloc(px4 * C * esz);
+    // output path
+    void* s1 = arena.alloc(px4 * C * esz);                          // h_top (+ net2)
+    float* g32 = static_cast<float*>(arena.alloc(px2 * (C / 2) * sizeof(float)));
+    void* s2 = f32 ? static_cast<void*>(g32) : arena.alloc(px2 * (C / 2) * esz);   // deconv_output1 (+ net1)
+    float* xgen32 = static_cast<float*>(arena.alloc(px * cp * sizeof(float)));
+    void* xgen_act = f32 ? static_cast<void*>(xgen32) : arena.alloc(px * cp * esz);
+    // decoupling loss
+    const char* halo_env = getenv("VPK_TC_HALO");
+    const bool fuse_dec = !f32 && backend == 0 && C % 8 == 0 && C <= 128 && getenv("VPK_NO_FUSED_DECOUPLE") == nullptr &&
+                          (halo_env == nullptr || atoi(halo_env) != 0);
+    const int dec_nslots = 4 * ((rh + 15) / 16) * ((rw + 7) / 8);
+    float* dec_slots = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * dec_nslots * C * 3 * sizeof(float)));
+    float* dec_terms = static_cast<float*>(arena.alloc(static_cast<size_t>(steps) * L * B * sizeof(float)));
+
+    auto cast_op = [&](std::vector<Op>& dst, const float* src, void* out, size_t n, const char* name) {
+      if (measure || f32) return;
+      Op op;
+      op.name = name;
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_add_to_act(src, DT_F32, nullptr, out, adt, static_cast<long long>(n), ns, s); };
+      dst.push_back(std::move(op));
+    };
+    // a k x k stride-2 conv without bias / activation: fp32 dense output (+ its activation-type copy)
+    auto down_conv = [&](std::vector<Op>* dst, const std::string& key, int Bx, int H, int W, int ci, int co, const void* in,
+                         float* out32, void* out_act, int cin_w) {
+      int oh, ow;
+      ConvArgs a{key + ".", Bx, H, W, ci, co, k, 2, k / 2, in, hp(key + ".weight"), nullptr, ACT_NONE, out32};
+      a.out_f32_dense = true;
+      a.cin_w = cin_w;
+      add_conv(prog, conv_spec(a, act, &oh, &ow), measure, stream, adt, dst);
+      VPK_REQUIRE(oh == H / 2 && ow == W / 2, "stride-2 input conv size mismatch");
+      cast_op(dst != nullptr ? *dst : prog.body, out32, out_act, static_cast<size_t>(Bx) * oh * ow * co, "cast_down_conv");
+    };
+
+    // ---- pre ops: patchify (device entry), actions -> latent for every step ----
+    if (!measure) {
+      if (!streams_input()) {
+        Op pre;
+        pre.name = "patchify";
+        pre.fn = [=](cudaStream_t s, const RunCtx& rc) {
+          launch_patchify_strided(rc.x, static_cast<long long>(t_in) * c * h * w, xp, adt, B, ctx, c, h, w, p, ns, s);
+        };
+        prog.pre.push_back(std::move(pre));
+      }
+      Op inf;
+      inf.name = "inflate_actions";
+      const int HWp = hp_ * wp_;
+      inf.fn = [=](cudaStream_t s, const RunCtx& rc) {
+        VPK_REQUIRE(rc.actions != nullptr && rc.action_steps >= steps, "Given actions are None or of the wrong size!");
+        launch_inflate_actions(rc.actions, static_cast<long long>(rc.action_steps) * a_sz, a_sz, a_inf, adt, B, steps, HWp, a_pad, ns, s);
+      };
+      prog.pre.push_back(std::move(inf));
+    }
+    down_conv(&prog.pre, "action_conv_input1", B * steps, hp_, wp_, a_pad, C / 2, a_inf, a1_32, a1, a_sz);
+    down_conv(&prog.pre, "action_conv_input2", B * steps, h2, w2, C / 2, C, a1, a2_32, a2, -1);
+    if (!measure) {
+      for (int i = 0; i < L; ++i) {
+        add_memset(prog, hb[2 * i], px4 * C * esz, "zero_h");
+        add_memset(prog, cb[i], px4 * C * sizeof(float), "zero_c");
+      }
+      add_memset(prog, mstate, px4 * C * sizeof(float), "zero_m");
+      add_memset(prog, m_act, px4 * C * esz, "zero_m_act");
+    }
+
+    std::vector<int> par(L, 0);
+    for (int t = 0; t < steps; ++t) {
+      const void* net = (t < ctx) ? static_cast<const void*>(xp + static_cast<size_t>(t) * px * cp * esz) : xgen_act;
+      if (!measure && t < ctx && streams_input()) {
+        char* dst = xp + static_cast<size_t>(t) * px * cp * esz;
+        const long long bstride = static_cast<long long>(t_in) * c * h * w, foff = static_cast<long long>(t) * c * h * w;
+        const int pp = p;
+        Op cv;
+        cv.name = "patchify";
+        cv.needs_input = t;
+        cv.fn = [=](cudaStream_t s, const RunCtx& rc) { launch_patchify_strided(rc.x + foff, bstride, dst, adt, B, 1, c, h, w, pp, ns, s); };
+        prog.body.push_back(std::move(cv));
+      }
+      down_conv(nullptr, "conv_input1", B, hp_, wp_, cp, C / 2, net, n1_32, n1, -1);
+      down_conv(nullptr, "conv_input2", B, h2, w2, C / 2, C, n1, n2_32, n2, -1);
+      const void* action = a2 + static_cast<size_t>(t) * px4 * C * (f32 ? 4 : esz);
+      for (int i = 0; i < L; ++i) {
+        const std::string pre = "cell_list." + std::to_string(i) + ".";
+        const void* inp = (i == 0) ? static_cast<const void*>(n2) : hb[2 * (i - 1) + par[i - 1]];
+        add_ac_cell(prog, pre, B, inp, hb[2 * i + par[i]], hb[2 * i + (par[i] ^ 1)], cb[i], mstate, opart, memb[2 * i + (t & 1)],
+                    m_act, dcdm, dcdm + px4 * C * esz, action, xraw, hraw, araw, mraw, oraw, lraw, lnpart, act, measure,
+                    stream, ln, products);
+        par[i] ^= 1;
+        add_decouple(prog, B, t, i, dcdm, px4, adapt, dec_slots, dec_nslots, dec_terms, fuse_dec, act, measure, stream);
+      }
+      // ---- x_gen (predrnn_v2.py:213-218) ----
+      const void* top = hb[2 * (L - 1) + par[L - 1]];
+      const void* din = top;
+      if (resid && !measure) {
+        const long long n = static_cast<long long>(px4) * C;
+        Op op;
+        op.name = "residual_net2";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_add_to_act(top, adt, n2_32, s1, adt, n, ns, s); };
+        prog.body.push_back(std::move(op));
+      }
+      if (resid) din = s1;
+      int oh, ow;
+      DeconvArgs d1{"deconv_output1.", B, rh, rw, C, C / 2, k, 2, k / 2, 1, din, hp("deconv_output1.weight"), nullptr, ACT_NONE, g32};
+      d1.out_f32 = true;
+      add_conv(prog, deconv_spec(d1, act, &oh, &ow), measure, stream, adt);
+      VPK_REQUIRE(oh == h2 && ow == w2, "deconv_output1 size mismatch");
+      if (!measure && (resid || !f32)) {
+        const long long n = static_cast<long long>(px2) * (C / 2);
+        const float* add = resid ? n1_32 : nullptr;
+        Op op;
+        op.name = "residual_net1";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_add_to_act(g32, DT_F32, add, s2, adt, n, ns, s); };
+        prog.body.push_back(std::move(op));
+      }
+      DeconvArgs d2{"deconv_output2.", B, h2, w2, C / 2, cp, k, 2, k / 2, 1, s2, hp("deconv_output2.weight"), nullptr, ACT_NONE, xgen32};
+      d2.out_f32 = true;
+      add_conv(prog, deconv_spec(d2, act, &oh, &ow), measure, stream, adt);
+      VPK_REQUIRE(oh == hp_ && ow == wp_, "deconv_output2 size mismatch");
+      if (t + 1 >= ctx && t + 1 < steps) cast_op(prog.body, xgen32, xgen_act, px * cp, "cast_xgen");
+      if (!measure) {
+        const int first_out = steps - pred;
+        if (t >= first_out) {
+          const int fo = t - first_out, pp = p;
+          Op op;
+          op.name = "unpatchify";
+          op.fn = [=](cudaStream_t s, const RunCtx&) { launch_unpatchify(xgen32, out_stage, DT_F32, B, pred, fo, c, h, w, pp, ns, s); };
+          op.frame = fo;
+          op.frame_src = out_stage + static_cast<size_t>(fo) * c * h * w;
+          op.frame_pitch = static_cast<long long>(pred) * c * h * w;
+          op.frame_elems = static_cast<long long>(c) * h * w;
+          prog.body.push_back(std::move(op));
+        }
+      }
+    }
+    if (!measure && fuse_dec) {
+      const long long n = static_cast<long long>(steps) * L * B;
+      double* acc = d_loss;
+      Op op;
+      op.name = "decouple_sum";
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_decouple_sum(dec_terms, n, acc, s); };
+      prog.body.push_back(std::move(op));
+    }
+    if (!measure) {
+      const size_t bytes = static_cast<size_t>(B) * pred * c * h * w * sizeof(float);
+      Op post;
+      post.name = "copy_out";
+      post.is_kernel = false;
+      post.fn = [=](cudaStream_t s, const RunCtx& rc) {
+        if (rc.on_frame != nullptr) return;
+        VPK_CUDA(cudaMemcpyAsync(rc.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s));
+      };
+      prog.post.push_back(std::move(post));
+    }
+  }
+
+  // decoupling-loss term of (step t, layer i) over delta_c / delta_m (predrnn_v2.py:197-211) on the cells' latent grid
+  void add_decouple(Program& prog, int B, int t, int i, char* dcdm, size_t pxl, float* adapt, float* dec_slots, int dec_nslots,
+                    float* dec_terms, bool fuse_dec, const ActInfo& act, bool measure, cudaStream_t stream) {
+    const int esz = act.esize;
+    if (fuse_dec) {
+      ConvSpec sp;
+      sp.name = "adapter.decouple";
+      sp.B = B;
+      sp.G = 2;
+      sp.C = C;
+      for (int g = 0; g < 2; ++g) {
+        WeightRef wr;
+        wr.w = hp("adapter.weight");
+        wr.O = C;
+        wr.I = C;
+        wr.KH = wr.KW = 1;
+        for (int q = 0; q < 4; ++q) wr.gate_block[q] = -1;
+        wr.gate_block[g] = 0;
+        sp.wrefs.push_back(wr);
+      }
+      int oh2, ow2;
+      std::vector<ConvInput> ins;
+      ins.push_back(ConvInput{dense_view(dcdm, rh, rw, C), 0, 0});
+      ins.push_back(ConvInput{dense_view(dcdm + pxl * C * esz, rh, rw, C), 1, 0});
+      lower_conv(sp, 1, 1, 0, ins, rh, rw, esz, &oh2, &ow2);
+      EpiParams& e = sp.phases[0].epi;
+      e.kind = EPI_DECOUPLE;
+      e.s1 = dec_slots;
+      e.gn_slot0 = 0;
+      e.gn_nslots = dec_nslots;
+      add_conv(prog, sp, measure, stream, act.dtype);
+      if (!measure) {
+        const int CC = C, nsl = dec_nslots;
+        float* term = dec_terms + static_cast<size_t>(t * L + i) * B;
+        Op op;
+        op.name = "decouple_cos";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_decouple_cos(dec_slots, nsl, B, CC, term, s); };
+        prog.body.push_back(std::move(op));
+      }
+      return;
+    }
+    int oh, ow;
+    ConvArgs ad{"adapter.", 2 * B, rh, rw, C, C, 1, 1, 0, dcdm, hp("adapter.weight"), nullptr, ACT_NONE, adapt};
+    ad.f32_strided = true;
+    ad.oB = static_cast<long long>(rh) * rw * C;
+    ad.oY = static_cast<long long>(rw) * C;
+    ad.oX = C;
+    ad.oC = 1;
+    add_conv(prog, conv_spec(ad, act, &oh, &ow), measure, stream, act.dtype);
+    if (!measure) {
+      const int HW = rh * rw, CC = C;
+      double* acc = d_loss;
+      Op op;
+      op.name = "decouple_reduce";
+      op.fn = [=](cudaStream_t s, const RunCtx&) { launch_decouple_reduce(adapt, B, HW, CC, acc, s); };
+      prog.body.push_back(std::move(op));
+    }
+  }
+
+  // One ActionConditionalSpatioTemporalLSTMCell step (model_blocks/predrnn.py:142-169): raw convs with bias (x, h, a, m),
+  // optional per-sample LayerNorm statistics, the action-conditional gate kernel, conv_o / conv_last, the output kernel.
+  void add_ac_cell(Program& prog, const std::string& pre, int B, const void* x, const void* h_in, void* h_out, float* c,
+                   float* m, float* opart, void* mem, void* m_act, void* dc, void* dm, const void* action, float* xraw,
+                   float* hraw, float* araw, float* mraw, float* oraw, float* lraw, float* part, const ActInfo& act,
+                   bool measure, cudaStream_t stream, bool ln, int products) {
+    int oh, ow;
+    const char* halo_env = getenv("VPK_TC_HALO");
+    const bool fuse_stats = ln && act.dtype != DT_F32 && backend == 0 && getenv("VPK_NO_FUSED_LN_STATS") == nullptr &&
+                            (halo_env == nullptr || atoi(halo_env) != 0);
+    auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& key, float* out,
+                        float* stat, int nslots, bool precise) {
+      ConvArgs a{pre + name, B, rh, rw, ci, co, kk, 1, kk / 2, in, hp(pre + key + "weight"), hp(pre + key + "bias"), ACT_NONE, out};
+      a.out_f32_dense = true;
+      if (precise && products == 2) a.w_split = true;
+      ConvSpec sp = conv_spec(a, act, &oh, &ow);
+      sp.is_gate_gemm = true;
+      if (stat != nullptr) {
+        EpiParams& e = sp.phases[0].epi;
+        e.gn_sums = stat;
+        e.gn_group_size = -1;
+        e.gn_slot0 = 0;
+        e.gn_nslots = nslots;
+      }
+      add_conv(prog, sp, measure, stream, act.dtype);
+    };
+    const int nsx = fuse_stats ? ln_slots(7 * C) : kLnSlices, nsh = fuse_stats ? ln_slots(4 * C) : kLnSlices,
+              nsm = fuse_stats ? ln_slots(3 * C) : kLnSlices, nso = fuse_stats ? ln_slots(C) : kLnSlices;
+    // regions X, H, M, A in `part` (the non-fused statistics launch writes X, H, M contiguously with kLnSlices each)
+    float* px_ = part;
+    float* ph_ = px_ + static_cast<size_t>(B) * nsx * 2;
+    float* pm_ = ph_ + static_cast<size_t>(B) * nsh * 2;
+    float* pa_ = pm_ + static_cast<size_t>(B) * nsm * 2;
+    VPK_REQUIRE(static_cast<size_t>(B) * (static_cast<size_t>(nsx) + 2 * nsh + nsm) * 2 <= lnpart_floats && nso <= nsx,
+                "LayerNorm statistics regions exceed their buffer");
+    raw_conv("conv_x.ac.", x, C, 7 * C, k, "conv_x.0.", xraw, fuse_stats ? px_ : nullptr, nsx, true);
+    raw_conv("conv_h.ac.", h_in, C, 4 * C, k, "conv_h.0.", hraw, fuse_stats ? ph_ : nullptr, nsh, true);
+    raw_conv("conv_m.ac.", m_act, C, 3 * C, k, "conv_m.0.", mraw, fuse_stats ? pm_ : nullptr, nsm, true);
+    raw_conv("conv_a.ac.", action, C, 4 * C, k, "conv_a.0.", araw, fuse_stats ? pa_ : nullptr, nsh, true);
+    const int HW = rh * rw, CC = C, ns = num_sms, dt = act.dtype;
+    if (!measure) {
+      if (ln && !fuse_stats) {
+        LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
+        LnStatsArgs sb{{araw, nullptr, nullptr}, {4ll * C * HW, 0, 0}, 1, B, pa_};
+        Op op;
+        op.name = pre + "ln_stats_xhma";
+        op.fn = [=](cudaStream_t s, const RunCtx&) {
+          launch_ln_stats(sa, s);
+          launch_ln_stats(sb, s);
+        };
+        prog.body.push_back(std::move(op));
+      }
+      auto lp = [&](const std::string& key, int kc) -> const float* { return ln ? ln_param(pre + key, kc, stream) : nullptr; };
+      StLnGatesArgs ga{xraw, hraw, mraw, {px_, ph_, pm_}, {nsx, nsh, nsm},
+                       lp("conv_x.1.weight", 7 * C), lp("conv_x.1.bias", 7 * C), lp("conv_h.1.weight", 4 * C),
+                       lp("conv_h.1.bias", 4 * C), lp("conv_m.1.weight", 3 * C), lp("conv_m.1.bias", 3 * C),
+                       c, m, mem, m_act, dc, dm, opart, B, HW, CC, dt, 1.0f};
+      ga.A = araw;
+      ga.part_a = pa_;
+      ga.nslots_a = nsh;
+      ga.ga = lp("conv_a.1.weight", 4 * C);
+      ga.ba = lp("conv_a.1.bias", 4 * C);
+      ga.use_ln = ln ? 1 : 0;
+      Op og;
+      og.name = pre + "ac_gates";
+      og.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_gates(ga, ns, s); };
+      prog.body.push_back(std::move(og));
+    }
+    raw_conv("conv_o.ac.", mem, 2 * C, C, k, "conv_o.0.", oraw, fuse_stats ? px_ : nullptr, nso, false);
+    {
+      ConvArgs a{pre + "conv_last.ac.", B, rh, rw, 2 * C, C, 1, 1, 0, mem, hp(pre + "conv_last.weight"), hp(pre + "conv_last.bias"),
+                 ACT_NONE, lraw};
+      a.out_f32_dense = true;
+      ConvSpec sp = conv_spec(a, act, &oh, &ow);
+      sp.is_gate_gemm = true;
+      add_conv(prog, sp, measure, stream, act.dtype);
+    }
+    if (!measure) {
+      if (ln && !fuse_stats) {
+        LnStatsArgs so{{oraw, nullptr, nullptr}, {1ll * C * HW, 0, 0}, 1, B, part};
+        Op op;
+        op.name = pre + "ln_stats_o";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(so, s); };
+        prog.body.push_back(std::move(op));
+      }
+      StLnOutArgs oa{oraw, lraw, px_, nso, ln ? ln_param(pre + "conv_o.1.weight", C, stream) : nullptr,
+                     ln ? ln_param(pre + "conv_o.1.bias", C, stream) : nullptr, opart, h_out, B, HW, CC, dt};
+      oa.use_ln = ln ? 1 : 0;
+      Op oo;
+      oo.name = pre + "ac_out";
+      oo.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_out(oa, ns, s); };
+      prog.body.push_back(std::move(oo));
+    }
+  }
+
  private:
   int p = 4, L = 3, k = 5, C = 128, cp = 16, hp_ = 16, wp_ = 16;
+  bool ac = false;
+  int rh = 16, rw = 16;            // latent size of the cells (patch grid, or a quarter of it when action-conditional)
   size_t lnpart_floats = 0;
   int call_terms = 1;
   double* d_loss = nullptr;

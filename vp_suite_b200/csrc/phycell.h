@@ -24,6 +24,9 @@ struct PhyCellArgs {
   const float *conv1_w, *conv1_b, *conv2_w, *conv2_b, *gate_w, *gate_b;   // host, reference layouts
   // optional: a separate copy of h for F.conv1 in the operand type of the F path (see phycell_specs' f_act); nullptr: h_act
   const void* h_f = nullptr;
+  // optional: the fp32 `hidden` the prediction h~ = hidden + F(hidden) starts from when it is not the carried state
+  // (action-conditional: hidden = hidden_action_conv(cat[state, action]), model_blocks/phydnet.py:53-55); nullptr: h_master
+  const float* h_res = nullptr;
 };
 
 inline int phycell_padded_channels(int hid) { return (hid + 7) / 8 * 8; }
@@ -64,7 +67,7 @@ inline std::vector<ConvSpec> phycell_specs(const PhyCellArgs& a, const ActInfo& 
     e.act = ACT_NONE;
     e.out_f32 = 1;
     dense_out(e, a.htilde, a.H, a.W, a.C);
-    e.res = a.h_master;
+    e.res = a.h_res ? a.h_res : a.h_master;
     out.push_back(std::move(s));
   }
   {

@@ -186,6 +186,82 @@ __global__ void __launch_bounds__(256) stlstm_ln_gates_kernel(const StLnGatesArg
   }
 }
 
+// Action-conditional ST-LSTM gate kernel (model_blocks/predrnn.py:142-164), with or without LayerNorm: grid (item blocks,
+// samples), one thread = one (sample, position, four channels).  Same outputs as stlstm_ln_gates_kernel; the i, f, g, o
+// terms of conv_h are multiplied by those of conv_a (:149) after their (optional) LayerNorms.  These cells run on
+// (patch_h / 4) x (patch_w / 4) latents -- a few thousand items -- so the kernel is kept simple.
+template <typename T>
+__global__ void __launch_bounds__(256) stlstm_ac_gates_kernel(const StLnGatesArgs a) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  __shared__ float s_mean[4], s_rstd[4];
+  const int C = a.C, HW = a.HW, cq = C >> 2;
+  const int b = blockIdx.y;
+  const bool ln = a.use_ln != 0;
+  if (threadIdx.x < 4) {
+    const int z = threadIdx.x;
+    if (ln) {
+      const double n = static_cast<double>(HW) * C * (z == 0 ? 7 : z == 2 ? 3 : 4);
+      ln_finalize(z == 3 ? a.part_a : a.part[z], z == 3 ? a.nslots_a : a.nslots[z], b, n, &s_mean[z], &s_rstd[z]);
+    } else {
+      s_mean[z] = 0.f;
+      s_rstd[z] = 1.f;
+    }
+  }
+  __syncthreads();
+  const int it = blockIdx.x * 256 + threadIdx.x;
+  if (it >= HW * cq) return;
+  const int hw = it / cq, ch = (it - hw * cq) * 4;
+  const long long pos = static_cast<long long>(b) * HW + hw;
+  auto nrm = [&](const float* raw, const float* g, const float* be, int z, int k, int slice) {
+    const float4 v = ld4(raw + pos * k * C + slice * C + ch);
+    if (!ln) return v;
+    const long long ap = static_cast<long long>(hw) * k * C + slice * C + ch;
+    return ln4(v, s_mean[z], s_rstd[z], ld4(g + ap), ld4(be + ap));
+  };
+  auto mul4 = [](float4 p, float4 q) { return make_float4(p.x * q.x, p.y * q.y, p.z * q.z, p.w * q.w); };
+  const float fb = a.forget_bias;
+#define VPK_GATE3(f, i0, i1, f0, f1, g0, g1, d, s)                                                       \
+  {                                                                                                      \
+    const float i_ = sigmoid_f(i0.f + i1.f), f_ = sigmoid_f(f0.f + f1.f + fb), g_ = tanh_f(g0.f + g1.f); \
+    d.f = i_ * g_;                                                                                       \
+    s.f = fmaf(f_, s.f, d.f);                                                                            \
+  }
+  {   // temporal memory: conv_x slices 0..2, (conv_h * conv_a) slices 0..2
+    const float4 ix = nrm(a.X, a.gx, a.bx, 0, 7, 0), fx = nrm(a.X, a.gx, a.bx, 0, 7, 1), gx = nrm(a.X, a.gx, a.bx, 0, 7, 2);
+    const float4 ih = mul4(nrm(a.H, a.gh, a.bh, 1, 4, 0), nrm(a.A, a.ga, a.ba, 3, 4, 0));
+    const float4 fh = mul4(nrm(a.H, a.gh, a.bh, 1, 4, 1), nrm(a.A, a.ga, a.ba, 3, 4, 1));
+    const float4 gh = mul4(nrm(a.H, a.gh, a.bh, 1, 4, 2), nrm(a.A, a.ga, a.ba, 3, 4, 2));
+    float4 cv = ld4(a.c + pos * C + ch), dc;
+    VPK_GATE3(x, ix, ih, fx, fh, gx, gh, dc, cv)
+    VPK_GATE3(y, ix, ih, fx, fh, gx, gh, dc, cv)
+    VPK_GATE3(z, ix, ih, fx, fh, gx, gh, dc, cv)
+    VPK_GATE3(w, ix, ih, fx, fh, gx, gh, dc, cv)
+    *reinterpret_cast<float4*>(a.c + pos * C + ch) = cv;
+    st_act4<T>(static_cast<T*>(a.mem) + pos * 2 * C + ch, cv);
+    st_act4<T>(static_cast<T*>(a.dc) + pos * C + ch, dc);
+  }
+  {   // spatio-temporal memory: conv_x slices 3..5, conv_m slices 0..2
+    const float4 ix = nrm(a.X, a.gx, a.bx, 0, 7, 3), fx = nrm(a.X, a.gx, a.bx, 0, 7, 4), gx = nrm(a.X, a.gx, a.bx, 0, 7, 5);
+    const float4 im = nrm(a.M, a.gm, a.bm, 2, 3, 0), fm = nrm(a.M, a.gm, a.bm, 2, 3, 1), gm = nrm(a.M, a.gm, a.bm, 2, 3, 2);
+    float4 mv = ld4(a.m + pos * C + ch), dm;
+    VPK_GATE3(x, ix, im, fx, fm, gx, gm, dm, mv)
+    VPK_GATE3(y, ix, im, fx, fm, gx, gm, dm, mv)
+    VPK_GATE3(z, ix, im, fx, fm, gx, gm, dm, mv)
+    VPK_GATE3(w, ix, im, fx, fm, gx, gm, dm, mv)
+    *reinterpret_cast<float4*>(a.m + pos * C + ch) = mv;
+    st_act4<T>(static_cast<T*>(a.mem) + pos * 2 * C + C + ch, mv);
+    st_act4<T>(static_cast<T*>(a.m_act) + pos * C + ch, mv);
+    st_act4<T>(static_cast<T*>(a.dm) + pos * C + ch, dm);
+  }
+#undef VPK_GATE3
+  {   // output-gate part: conv_x slice 6 + (conv_h * conv_a) slice 3
+    const float4 ox = nrm(a.X, a.gx, a.bx, 0, 7, 6);
+    const float4 oh = mul4(nrm(a.H, a.gh, a.bh, 1, 4, 3), nrm(a.A, a.ga, a.ba, 3, 4, 3));
+    *reinterpret_cast<float4*>(a.opart + pos * C + ch) = make_float4(ox.x + oh.x, ox.y + oh.y, ox.z + oh.z, ox.w + oh.w);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) stlstm_ln_out_kernel(const StLnOutArgs a) {
   ptx::pdl_launch_dependents();
@@ -193,15 +269,16 @@ __global__ void __launch_bounds__(256) stlstm_ln_out_kernel(const StLnOutArgs a)
   __shared__ float s_mean, s_rstd;
   const int b = blockIdx.y;
   const int C = a.C, HW = a.HW, cq = C >> 2;
-  if (threadIdx.x == 0) ln_finalize(a.part, a.nslots, b, static_cast<double>(HW) * C, &s_mean, &s_rstd);
+  const bool ln = a.use_ln != 0;
+  if (threadIdx.x == 0 && ln) ln_finalize(a.part, a.nslots, b, static_cast<double>(HW) * C, &s_mean, &s_rstd);
   __syncthreads();
-  const float mo = s_mean, ro = s_rstd;
+  const float mo = ln ? s_mean : 0.f, ro = ln ? s_rstd : 1.f;
   const int items = HW * cq;
   for (int it = blockIdx.x * 256 + threadIdx.x; it < items; it += gridDim.x * 256) {
     const int hw = it / cq, ch = (it - hw * cq) * 4;
     const long long pos = static_cast<long long>(b) * HW + hw;
     const long long ao = static_cast<long long>(hw) * C + ch;
-    const float4 o = ln4(ld4(a.O + pos * C + ch), mo, ro, ld4(a.go + ao), ld4(a.bo + ao));
+    const float4 o = ln ? ln4(ld4(a.O + pos * C + ch), mo, ro, ld4(a.go + ao), ld4(a.bo + ao)) : ld4(a.O + pos * C + ch);
     const float4 p = ld4(a.opart + pos * C + ch), l = ld4(a.Lraw + pos * C + ch);
     const float4 h = make_float4(sigmoid_f(p.x + o.x) * tanh_f(l.x), sigmoid_f(p.y + o.y) * tanh_f(l.y),
                                  sigmoid_f(p.z + o.z) * tanh_f(l.z), sigmoid_f(p.w + o.w) * tanh_f(l.w));
@@ -225,6 +302,14 @@ void launch_ln_stats(const LnStatsArgs& a, cudaStream_t stream) {
 
 void launch_stlstm_ln_gates(const StLnGatesArgs& a, int num_sms, cudaStream_t stream) {
   VPK_REQUIRE(a.C % 4 == 0 && a.B > 0 && a.HW > 0, "stlstm_ln_gates: bad shape");
+  if (a.A != nullptr) {      // action-conditional cell (with or without LayerNorm)
+    const dim3 grid(static_cast<unsigned>((a.HW * (a.C / 4) + 255) / 256), static_cast<unsigned>(a.B));
+    if (a.dtype == DT_F32) launch_pdl(stlstm_ac_gates_kernel<float>, grid, dim3(256), 0, stream, a);
+    else if (a.dtype == DT_F16) launch_pdl(stlstm_ac_gates_kernel<__half>, grid, dim3(256), 0, stream, a);
+    else launch_pdl(stlstm_ac_gates_kernel<__nv_bfloat16>, grid, dim3(256), 0, stream, a);
+    return;
+  }
+  VPK_REQUIRE(a.use_ln != 0, "stlstm_ln_gates: the plain cell without LayerNorm runs through the fused conv epilogues");
   const dim3 grid(static_cast<unsigned>((a.HW * (a.C / 4) + 255) / 256), static_cast<unsigned>((a.B + kGateNB - 1) / kGateNB));
   if (a.dtype == DT_F32) launch_pdl(stlstm_ln_gates_kernel<float>, grid, dim3(256), 0, stream, a);
   else if (a.dtype == DT_F16) launch_pdl(stlstm_ln_gates_kernel<__half>, grid, dim3(256), 0, stream, a);

@@ -35,6 +35,13 @@ struct StLnGatesArgs {
   int B, HW, C, dtype;
   float forget_bias;
   void* m_act_lo = nullptr;                    // optional: low part of m' (m' - m_act), activation type [B*HW][C]
+  // action-conditional cell (model_blocks/predrnn.py:86-169): A = raw conv_a output [B*HW][4C]; (LN(H) * LN(A)) replaces
+  // LN(H) in the i, f, g, o sums (:149).  nullptr: the plain cell
+  const float* A = nullptr;
+  const float* part_a = nullptr;               // partial statistics of A, [b][nslots_a][2]
+  int nslots_a = 0;
+  const float *ga = nullptr, *ba = nullptr;    // LayerNorm affine of conv_a, [HW][4C]
+  int use_ln = 1;                              // 0: no LayerNorm (raw conv outputs already carry their bias): identity
 };
 void launch_stlstm_ln_gates(const StLnGatesArgs& a, int num_sms, cudaStream_t stream);
 
@@ -47,6 +54,7 @@ struct StLnOutArgs {
   void* h;                                     // activation type [B*HW][C]
   int B, HW, C, dtype;
   void* h_lo = nullptr;                        // optional: low part of h' (h' - h), activation type [B*HW][C]
+  int use_ln = 1;                              // 0: no LayerNorm on conv_o's output
 };
 void launch_stlstm_ln_out(const StLnOutArgs& a, int num_sms, cudaStream_t stream);
 

@@ -244,32 +244,50 @@ class PredRNN_V2(NativeRollout, VPModel):
     def __init__(self, device, **model_kwargs):
         super().__init__(device, **model_kwargs)
         self._native_init()
-        if self.action_conditional:
-            raise NotImplementedError("the native rollout covers the non action-conditional PredRNN-V2 (SURVEY 8(f))")
         if self.stride != 1:
             raise AttributeError("ST-LSTM stride must be 1")
         self.patch_c = self.patch_size * self.patch_size * self.img_c          # predrnn_v2.py:59-62
         self.patch_a = self.action_size
         self.patch_h = self.rnn_h = self.img_h // self.patch_size
         self.patch_w = self.rnn_w = self.img_w // self.patch_size
-        self.conv_actions_on_input = False                                     # predrnn_v2.py:68-70
-        self.residual_on_action_conv = False
+        ac = bool(self.action_conditional)
+        k, C0 = self.filter_size, self.num_hidden[0]
+        if ac:                                                                 # predrnn_v2.py:65-67
+            self.conv_actions_on_input = True
+            self.reverse_scheduled_sampling = True
+        else:                                                                  # predrnn_v2.py:68-70
+            self.conv_actions_on_input = False
+            self.residual_on_action_conv = False
+        if self.conv_actions_on_input:                                         # predrnn_v2.py:73-90
+            self.rnn_h //= 4
+            self.rnn_w //= 4
+            CL = self.num_hidden[self.num_layers - 1]
+            self.conv_input1 = nn.Conv2d(self.patch_c, C0 // 2, k, stride=2, padding=k // 2, bias=False)
+            self.conv_input2 = nn.Conv2d(C0 // 2, C0, k, stride=2, padding=k // 2, bias=False)
+            self.action_conv_input1 = nn.Conv2d(self.patch_a, C0 // 2, k, stride=2, padding=k // 2, bias=False)
+            self.action_conv_input2 = nn.Conv2d(C0 // 2, C0, k, stride=2, padding=k // 2, bias=False)
+            self.deconv_output1 = nn.ConvTranspose2d(CL, CL // 2, k, stride=2, padding=k // 2, bias=False)
+            self.deconv_output2 = nn.ConvTranspose2d(CL // 2, self.patch_c, k, stride=2, padding=k // 2, bias=False)
         cells = []
         for i in range(self.num_layers):                                       # predrnn_v2.py:92-108
-            cin = self.patch_c if i == 0 else self.num_hidden[i - 1]
-            C, k = self.num_hidden[i], self.filter_size
+            cin = (C0 if ac else self.patch_c) if i == 0 else self.num_hidden[i - 1]
+            C = self.num_hidden[i]
             cell = _Params()
-            for name, (o, ci) in (("conv_x", (7 * C, cin)), ("conv_h", (4 * C, C)), ("conv_m", (3 * C, C)),
-                                  ("conv_o", (C, 2 * C))):
-                layers = [nn.Conv2d(ci, o, k, 1, k // 2, bias=False)]
+            # ActionConditionalSpatioTemporalLSTMCell: convs with bias, a fifth conv_a (model_blocks/predrnn.py:97-139)
+            names = (("conv_x", (7 * C, cin)), ("conv_h", (4 * C, C))) + ((("conv_a", (4 * C, C)),) if ac else ()) + \
+                    (("conv_m", (3 * C, C)), ("conv_o", (C, 2 * C)))
+            for name, (o, ci) in names:
+                layers = [nn.Conv2d(ci, o, k, 1, k // 2, bias=ac)]
                 if self.layer_norm:                                            # model_blocks/predrnn.py:24-40
                     layers.append(nn.LayerNorm([o, self.rnn_h, self.rnn_w]))
                 setattr(cell, name, nn.Sequential(*layers))
-            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
+            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=ac)
             cells.append(cell)
         self.cell_list = nn.ModuleList(cells)
-        self.conv_last = nn.Conv2d(self.num_hidden[self.num_layers - 1], self.patch_c, 1, 1, 0, bias=False)
-        self.adapter = nn.Conv2d(self.num_hidden[0], self.num_hidden[0], 1, 1, 0, bias=False)
+        if not ac:                                 # (non-existent when conv_actions_on_input is True, predrnn_v2.py:110-116)
+            self.conv_last = nn.Conv2d(self.num_hidden[self.num_layers - 1], self.patch_c, 1, 1, 0, bias=False)
+        CA = self.num_hidden[self.num_layers - 1] if ac else C0               # predrnn_v2.py:119-120
+        self.adapter = nn.Conv2d(CA, CA, 1, 1, 0, bias=False)
         self.training_iteration = 1                                            # predrnn_v2.py:124-126
         self.sampling_eta = 1.0
         self.to(device)
@@ -283,6 +301,9 @@ class PredRNN_V2(NativeRollout, VPModel):
             d.num_hidden[i] = int(v)
         d.decoupling_loss_scale = float(self.decoupling_loss_scale)
         d.layer_norm = int(bool(self.layer_norm))
+        d.action_conditional = int(bool(self.action_conditional))
+        d.action_size = int(self.action_size)
+        d.residual_on_action_conv = int(bool(self.residual_on_action_conv))
         return d
 
     def _native_key(self, key):
@@ -299,7 +320,8 @@ class PredRNN_V2(NativeRollout, VPModel):
             raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
         if kwargs.get("train", False):
             raise NotImplementedError("the native rollout is inference-only")
-        pred, aux = self._native_forward(x, int(pred_frames), total, want_aux=True)
+        actions = self._native_actions(kwargs, b, x.device)                    # predrnn_v2.py:147-152
+        pred, aux = self._native_forward(x, int(pred_frames), total, want_aux=True, actions=actions)
         return pred, {"ST-LSTM decouple loss": aux[0]}                         # predrnn_v2.py:229-230
 
 
@@ -346,8 +368,10 @@ class PhyDNet(NativeRollout, VPModel):
     def __init__(self, device, **model_kwargs):
         super().__init__(device, **model_kwargs)
         self._native_init()
-        if self.action_conditional:
-            raise NotImplementedError("the native rollout covers the non action-conditional PhyDNet (SURVEY 8(f))")
+        ac = bool(self.action_conditional) and self._KIND == N.VPK_MODEL_PHY
+        if bool(self.action_conditional) and not ac:
+            raise AttributeError("the ConvLSTM-branch composition is not action-conditional")
+        a = int(self.action_size) if ac else 0
         if self.img_h % 4 or self.img_w % 4:
             raise AttributeError("image size must be a multiple of 4 (other sizes need the reference's Resize)")
         c = self.img_c
@@ -381,10 +405,13 @@ class PhyDNet(NativeRollout, VPModel):
             cell.F.add_module("bn1", nn.GroupNorm(_gn_divisor(hid), hid))
             cell.F.add_module("conv2", nn.Conv2d(hid, 64, (1, 1)))
             cell.convgate = nn.Conv2d(128, 64, (3, 3), padding=(1, 1))
+            if ac:                                                             # model_blocks/phydnet.py:44-48
+                cell.frame_action_conv = nn.Conv2d(64 + a, 64, (1, 1))
+                cell.hidden_action_conv = nn.Conv2d(64 + a, 64, (1, 1))
             cells.append(cell)
         self.phycell.cell_list = nn.ModuleList(cells)
         self.convcell = _Params()
-        cells, cin = [], 64
+        cells, cin = [], 64 + a                                                # model_blocks/phydnet.py:137
         kc = self.convlstm_kernel_size
         for hd in self.convlstm_hidden_dims[:self.convlstm_n_layers]:
             cell = _Params()
@@ -408,6 +435,8 @@ class PhyDNet(NativeRollout, VPModel):
         for i, v in enumerate(self.convlstm_hidden_dims[:8]):
             d.convlstm_hidden_dims[i] = int(v)
         d.convlstm_kernel_size = self.convlstm_kernel_size[0]
+        d.action_conditional = int(bool(self.action_conditional))
+        d.action_size = int(self.action_size)
         return d
 
     def _native_key(self, key):
@@ -422,7 +451,8 @@ class PhyDNet(NativeRollout, VPModel):
         b, t, c, h, w = x.shape
         if (c, h, w) != (self.img_c, self.img_h, self.img_w):
             raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
-        pred, _ = self._native_forward(x, int(pred_frames), t)
+        actions = self._native_actions(kwargs, b, x.device)                    # models/phydnet.py:100-105
+        pred, _ = self._native_forward(x, int(pred_frames), t, actions=actions)
         return pred, None                                                      # models/phydnet.py:134-137 (eval)
 
 
