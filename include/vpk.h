@@ -175,6 +175,19 @@ int vpk_stlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const fl
                          const float* m, float* h_out, float* c_out, float* m_out, float* dc_out, float* dm_out,
                          void* stream);
 
+/* Replaces ActionConditionalSpatioTemporalLSTMCell.forward (model_blocks/predrnn.py:142-169).  weights / biases: HOST fp32
+ * arrays of the six convs in the order conv_x [7ch, cin, k, k], conv_h [4ch, ch, k, k], conv_a [4ch, ch, k, k],
+ * conv_m [3ch, ch, k, k], conv_o [ch, 2ch, k, k], conv_last [ch, 2ch, 1, 1] (every conv of this cell has a bias, :104-140).
+ * layer_norm=True: vpk_stlstm_ac_cell_set_layer_norm with (weight, bias) of the LayerNorms after conv_x, conv_h, conv_a,
+ * conv_m, conv_o (10 host pointers, reference layout [k*ch, h, w]).  Step: x [b, cin, h, w]; h, c, m, a [b, ch, h, w]
+ * (a = the action tensor the model convolved to the latent size); outputs h', c', m', delta_c, delta_m. */
+int vpk_stlstm_ac_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w, int32_t k,
+                              const float* const* weights, const float* const* biases, vpk_cell** out);
+int vpk_stlstm_ac_cell_set_layer_norm(vpk_cell* cell, const float* const* params);
+int vpk_stlstm_ac_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c, const float* m,
+                            const float* a, float* h_out, float* c_out, float* m_out, float* dc_out, float* dm_out,
+                            void* stream);
+
 /* Replaces PhyCell_Cell.forward with action_conditional=False (model_blocks/phydnet.py:49-62).
  *   weights HOST fp32: conv1 [hid, ch, k, k] + bias, GroupNorm(groups, hid) weight/bias, conv2 [ch, hid, 1, 1] + bias,
  *   convgate [ch, 2ch, 3, 3] + bias.  x, h [b, ch, hh, ww]; output h'. */
@@ -183,6 +196,13 @@ int vpk_phycell_cell_create(int32_t precision, int32_t backend, int32_t ch, int3
                             const float* gn_b, const float* conv2_w, const float* conv2_b, const float* gate_w,
                             const float* gate_b, vpk_cell** out);
 int vpk_phycell_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, float* h_out, void* stream);
+/* action_conditional=True (model_blocks/phydnet.py:44-55): frame_action_conv / hidden_action_conv, HOST fp32
+ * [ch, ch + action_size, 1, 1] + bias [ch] each (action_size <= 8); the step then takes the action vectors, DEVICE fp32
+ * [b, action_size], inflates them to the frame size and runs frame / hidden through those 1x1 convs first. */
+int vpk_phycell_cell_set_action_convs(vpk_cell* cell, int32_t action_size, const float* frame_w, const float* frame_b,
+                                      const float* hidden_w, const float* hidden_b);
+int vpk_phycell_cell_step_action(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* action,
+                                 float* h_out, void* stream);
 
 void vpk_cell_destroy(vpk_cell* cell);
 

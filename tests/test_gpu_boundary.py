@@ -228,3 +228,77 @@ def test_phycell_block_stack_values(precision, tol, tol_end):
     errs = [float((a - b).abs().max()) for a, b in zip(got, want)]
     print(f"PhyCell block {precision}: per-step max abs err {['%.1e' % e for e in errs]}")
     assert errs[0] <= tol and max(errs) <= tol_end, errs      # single step / end of the (three-step) rollout
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,key,xseed,ln", [("stac", "stlstm_ac", 10, False), ("stacln", "stlstm_acln", 11, True)])
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 5e-3)])
+def test_action_conditional_stlstm_block_matches_reference_golden(manifest, tag, key, xseed, ln, precision, tol):
+    """ActionConditionalSpatioTemporalLSTMCell block drop-in (model_blocks/predrnn.py:86-169) through
+    vpk_stlstm_ac_cell_step against the vectors the reference block produced (tests/golden/blocks_ac.npz)."""
+    from conftest import load_golden
+    from vp_suite_b200 import model_blocks as MB
+    gold = load_golden("blocks_ac")
+    mb = manifest["blocks"][key]
+    cell = MB.ActionConditionalSpatioTemporalLSTMCell(16, 32, 8, 8, 5, 1, ln).to("cuda:0")
+    cell.precision = precision
+    cell.load_state_dict(synth_state_dict(mb["shapes"], mb["wseed"]))
+    g = torch.Generator().manual_seed(xseed)
+    x = torch.rand((2, 16, 8, 8), generator=g) * 2 - 1
+    h, c, m, a = [torch.rand((2, 32, 8, 8), generator=g) * 2 - 1 for _ in range(4)]
+    with torch.no_grad():
+        res = cell(*[t.cuda() for t in (x, h, c, m, a)])
+    errs = {nm: float(np.abs(v.cpu().numpy() - gold[f"{tag}_{nm}"]).max()) for nm, v in zip(("h", "c", "m", "dc", "dm"), res)}
+    print(f"AC ST-LSTM block layer_norm={ln} {precision}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= tol, errs
+
+
+@pytest.mark.parametrize("precision,tol,tol_end", [("fp32", 1e-4, 1e-4), ("bf16", 5e-3, 2e-2)])
+def test_action_conditional_phydnet_blocks(precision, tol, tol_end):
+    """PhyCell (frame / hidden action convs, model_blocks/phydnet.py:44-55) and SingleStepConvLSTM (action channels,
+    :137, 153-155) block drop-ins with action_conditional=True over three timesteps, against the reference's blocks when
+    present, else the oracle's cell steps."""
+    from oracle.weights import synth_actions
+    from vp_suite_b200 import model_blocks as MB
+    dev, a_sz = "cuda:0", 3
+    phy = MB.PhyCell((8, 8), 16, [49], 1, (7, 7), True, a_sz, dev).to(dev)
+    lstm = MB.SingleStepConvLSTM((8, 8), 16, [32, 16], 2, (3, 3), True, a_sz, dev).to(dev)
+    for cell in list(phy.cell_list) + list(lstm.cell_list):
+        cell.precision = precision
+    sd_p = synth_state_dict({k: tuple(v.shape) for k, v in phy.state_dict().items()}, seed=14)
+    sd_l = synth_state_dict({k: tuple(v.shape) for k, v in lstm.state_dict().items()}, seed=15)
+    phy.load_state_dict(sd_p)
+    lstm.load_state_dict(sd_l)
+    g = torch.Generator().manual_seed(4)
+    xs = [torch.rand((2, 16, 8, 8), generator=g) * 2 - 1 for _ in range(3)]
+    acts = synth_actions(2, 3, a_sz, seed=21)
+    got_p, got_l = [], []
+    with torch.no_grad():
+        for t, x in enumerate(xs):
+            _, out = phy(x.to(dev), acts[:, t].to(dev), first_timestep=(t == 0))
+            got_p.append(out[-1].cpu().clone())
+            _, out = lstm(x.to(dev), acts[:, t].to(dev), first_timestep=(t == 0))
+            got_l.append(out[-1].cpu().clone())
+    if HAVE_REF:
+        from vp_suite.model_blocks.phydnet import PhyCell as RefPhyCell, SingleStepConvLSTM as RefLstm
+        rp = RefPhyCell((8, 8), 16, [49], 1, (7, 7), True, a_sz, "cpu")
+        rl = RefLstm((8, 8), 16, [32, 16], 2, (3, 3), True, a_sz, "cpu")
+        rp.load_state_dict(sd_p)
+        rl.load_state_dict(sd_l)
+        with torch.no_grad():
+            want_p = [rp(x, acts[:, t], first_timestep=(t == 0))[1][-1].clone() for t, x in enumerate(xs)]
+            want_l = [rl(x, acts[:, t], first_timestep=(t == 0))[1][-1].clone() for t, x in enumerate(xs)]
+    else:
+        hp = torch.zeros(2, 16, 8, 8)
+        H = [torch.zeros(2, 32, 8, 8), torch.zeros(2, 16, 8, 8)]
+        Cs = [torch.zeros(2, 32, 8, 8), torch.zeros(2, 16, 8, 8)]
+        want_p, want_l = [], []
+        with torch.no_grad():
+            for t, x in enumerate(xs):
+                hp = OB.phycell_step(x, hp, OB._sub(sd_p, "cell_list.0."), acts[:, t])
+                want_p.append(hp)
+                want_l.append(OM._convcell_stack(sd_l, "", x, H, Cs, 2, acts[:, t]).clone())
+    ep = [float((a - b).abs().max()) for a, b in zip(got_p, want_p)]
+    el = [float((a - b).abs().max()) for a, b in zip(got_l, want_l)]
+    print(f"AC PhyCell block {precision}: {['%.1e' % e for e in ep]}; AC SingleStepConvLSTM block: {['%.1e' % e for e in el]}")
+    assert ep[0] <= tol and max(ep) <= tol_end and el[0] <= tol and max(el) <= tol_end, (ep, el)

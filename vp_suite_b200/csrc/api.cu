@@ -290,6 +290,52 @@ int vpk_phycell_cell_step(vpk_cell* cell, int32_t batch, const float* x, const f
   });
 }
 
+int vpk_stlstm_ac_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w, int32_t k,
+                              const float* const* weights, const float* const* biases, vpk_cell** out) {
+  return guarded([&] {
+    VPK_REQUIRE(weights && biases && out, "null argument");
+    for (int i = 0; i < 6; ++i) VPK_REQUIRE(weights[i] && biases[i], "null weight / bias");
+    *out = new vpk_cell{vpk::make_stlstm_ac_cell(precision, backend, cin, ch, h, w, k, weights, biases)};
+  });
+}
+
+int vpk_stlstm_ac_cell_set_layer_norm(vpk_cell* cell, const float* const* params) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && params, "null argument");
+    for (int i = 0; i < 10; ++i) VPK_REQUIRE(params[i], "null LayerNorm parameter");
+    cell->impl->set_layer_norm(params);
+  });
+}
+
+int vpk_stlstm_ac_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c, const float* m,
+                            const float* a, float* h_out, float* c_out, float* m_out, float* dc_out, float* dm_out,
+                            void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && x && h && c && m && a && h_out && c_out && m_out, "null argument");
+    const float* in[8] = {x, h, c, m, a, nullptr, nullptr, nullptr};
+    float* outp[8] = {h_out, c_out, m_out, dc_out, dm_out, nullptr, nullptr, nullptr};
+    cell->impl->step(batch, in, outp, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vpk_phycell_cell_set_action_convs(vpk_cell* cell, int32_t action_size, const float* frame_w, const float* frame_b,
+                                      const float* hidden_w, const float* hidden_b) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && frame_w && frame_b && hidden_w && hidden_b, "null argument");
+    cell->impl->set_action_convs(action_size, frame_w, frame_b, hidden_w, hidden_b);
+  });
+}
+
+int vpk_phycell_cell_step_action(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* action,
+                                 float* h_out, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && x && h && action && h_out, "null argument");
+    const float* in[8] = {x, h, action, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* outp[8] = {h_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cell->impl->step(batch, in, outp, static_cast<cudaStream_t>(stream));
+  });
+}
+
 void vpk_cell_destroy(vpk_cell* cell) {
   if (cell == nullptr) return;
   try {

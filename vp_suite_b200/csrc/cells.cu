@@ -277,6 +277,141 @@ class StLstmCell : public CellBase {
   float* d_ln[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// ActionConditionalSpatioTemporalLSTMCell.forward (model_blocks/predrnn.py:142-169), layer_norm off or on: the rollout's
+// pipeline (model_predrnn.cu: add_ac_cell) behind the NCHW block boundary -- raw convs with bias (x, h, a, m), per-sample
+// statistics when layer_norm, the action-conditional gate kernel, conv_o / conv_last, the output kernel.
+class StLstmAcCell : public CellBase {
+ public:
+  StLstmAcCell(int precision, int backend_, int cin_, int ch_, int h_, int w_, int k_, const float* const* weights,
+               const float* const* biases)
+      : CellBase(precision, backend_), cin(cin_), ch(ch_), h(h_), w(w_), k(k_) {
+    VPK_REQUIRE(cin > 0 && ch > 0 && ch % 4 == 0 && h > 0 && w > 0 && k % 2 == 1, "bad action-conditional ST-LSTM cell shape");
+    const size_t kk = static_cast<size_t>(k) * k;
+    const size_t wn[6] = {7 * ch * cin * kk, 4 * ch * ch * kk, 4 * ch * ch * kk, 3 * ch * ch * kk,
+                          static_cast<size_t>(ch) * 2 * ch * kk, static_cast<size_t>(ch) * 2 * ch};
+    const size_t bn[6] = {7u * ch, 4u * ch, 4u * ch, 3u * ch, 1u * ch, 1u * ch};
+    for (int i = 0; i < 6; ++i) {
+      wts[i].assign(weights[i], weights[i] + wn[i]);
+      bs[i].assign(biases[i], biases[i] + bn[i]);
+    }
+  }
+  // params: (gamma, beta) x (conv_x, conv_h, conv_a, conv_m, conv_o), reference layout [k*C, H, W]
+  void set_layer_norm(const float* const* params) override {
+    const int mult[5] = {7, 4, 4, 3, 1};
+    const int HW = h * w;
+    for (int i = 0; i < 10; ++i) {
+      const int kc = mult[i / 2] * ch;
+      ln[i].resize(static_cast<size_t>(kc) * HW);
+      for (int c = 0; c < kc; ++c)
+        for (int q = 0; q < HW; ++q) ln[i][static_cast<size_t>(q) * kc + c] = params[i][static_cast<size_t>(c) * HW + q];
+    }
+    has_ln = true;
+  }
+  // in: x, h, c, m, a    out: h', c', m', delta_c, delta_m
+  void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    const int adt = (dtype == DT_BF16) ? DT_F16 : dtype;      // fp16 operands in 16-bit mode, as in the rollout
+    const ActInfo a16{adt, esize()};
+    const size_t px = static_cast<size_t>(B) * h * w;
+    const int HW = h * w;
+    void* xb = buf("x", px * cin * esize());
+    void* hi = buf("h_in", px * ch * esize());
+    void* ai = buf("a_in", px * ch * esize());
+    void* mi = buf("m_in", px * ch * esize());
+    void* ho = buf("h_out", px * ch * esize());
+    void* mem = buf("mem", px * 2 * ch * esize());
+    void* mact = buf("m_act", px * ch * esize());
+    void* dc = buf("dc", px * ch * esize());
+    void* dm = buf("dm", px * ch * esize());
+    float* cb = static_cast<float*>(buf("c", px * ch * sizeof(float)));
+    float* mb = static_cast<float*>(buf("m", px * ch * sizeof(float)));
+    float* op = static_cast<float*>(buf("o_part", px * ch * sizeof(float)));
+    float* xr = static_cast<float*>(buf("x_raw", px * 7 * ch * sizeof(float)));
+    float* hr = static_cast<float*>(buf("h_raw", px * 4 * ch * sizeof(float)));
+    float* ar = static_cast<float*>(buf("a_raw", px * 4 * ch * sizeof(float)));
+    float* mr = static_cast<float*>(buf("m_raw", px * 3 * ch * sizeof(float)));
+    float* orw = static_cast<float*>(buf("o_raw", px * ch * sizeof(float)));
+    float* lr = static_cast<float*>(buf("l_raw", px * ch * sizeof(float)));
+    float* part = static_cast<float*>(buf("ln_part", static_cast<size_t>(4) * B * kLnSlices * 2 * sizeof(float)));
+    if (has_ln && d_ln[0] == nullptr)
+      for (int i = 0; i < 10; ++i) d_ln[i] = static_cast<float*>(store.upload(ln[i].data(), ln[i].size() * sizeof(float), s));
+    if (built_batch != B) {
+      convs.clear();
+      int oh, ow;
+      const char* ws_env = getenv("VPK_LN_PRODUCTS");
+      const bool w_split_on = has_ln && adt == DT_F16 && (ws_env == nullptr || atoi(ws_env) >= 2);
+      auto raw_conv = [&](const char* name, const void* src, int ci, int co, int kk, int idx, float* dst, bool precise) {
+        ConvArgs a{std::string("cell.ac.") + name, B, h, w, ci, co, kk, 1, kk / 2, src, wts[idx].data(), bs[idx].data(),
+                   ACT_NONE, dst};
+        a.out_f32_dense = true;
+        a.w_split = precise && w_split_on && ((ci + 63) / 64) * 2 * kk * kk <= kMaxSteps;
+        for (BuiltConv& bc : build_conv(conv_spec(a, a16, &oh, &ow), adt, backend, store, cache, s, num_sms, false))
+          convs.push_back(bc);
+      };
+      raw_conv("x", xb, cin, 7 * ch, k, 0, xr, true);
+      raw_conv("h", hi, ch, 4 * ch, k, 1, hr, true);
+      raw_conv("a", ai, ch, 4 * ch, k, 2, ar, true);
+      raw_conv("m", mi, ch, 3 * ch, k, 3, mr, true);
+      raw_conv("o", mem, 2 * ch, ch, k, 4, orw, false);
+      raw_conv("last", mem, 2 * ch, ch, 1, 5, lr, false);
+      finish_build(s);
+      built_batch = B;
+    }
+    to_nhwc(in[0], xb, adt, B, cin, h, w, s);
+    to_nhwc(in[1], hi, adt, B, ch, h, w, s);
+    to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
+    to_nhwc(in[3], mi, adt, B, ch, h, w, s);
+    to_nhwc(in[3], mb, DT_F32, B, ch, h, w, s);
+    to_nhwc(in[4], ai, adt, B, ch, h, w, s);
+    auto run16 = [&](const BuiltConv& bc) {
+      if (bc.use_halo) launch_conv_halo(bc.halo, s);
+      else if (bc.use_tc) launch_conv_tc(bc.tc, s);
+      else if (bc.use_direct) launch_conv_direct(bc.L, adt, num_sms, s);
+      else launch_conv_simt(bc.L, adt, s);
+    };
+    for (int i = 0; i < 4; ++i) run16(convs[i]);
+    const size_t reg = static_cast<size_t>(B) * kLnSlices * 2;
+    float *px_ = part, *ph_ = part + reg, *pm_ = part + 2 * reg, *pa_ = part + 3 * reg;
+    if (has_ln) {
+      LnStatsArgs sa{{xr, hr, mr}, {7ll * ch * HW, 4ll * ch * HW, 3ll * ch * HW}, 3, B, part};
+      LnStatsArgs sb{{ar, nullptr, nullptr}, {4ll * ch * HW, 0, 0}, 1, B, pa_};
+      launch_ln_stats(sa, s);
+      launch_ln_stats(sb, s);
+    }
+    StLnGatesArgs ga{xr, hr, mr, {px_, ph_, pm_}, {kLnSlices, kLnSlices, kLnSlices},
+                     d_ln[0], d_ln[1], d_ln[2], d_ln[3], d_ln[6], d_ln[7], cb, mb, mem, mact, dc, dm, op, B, HW, ch, adt, 1.0f};
+    ga.A = ar;
+    ga.part_a = pa_;
+    ga.nslots_a = kLnSlices;
+    ga.ga = d_ln[4];
+    ga.ba = d_ln[5];
+    ga.use_ln = has_ln ? 1 : 0;
+    launch_stlstm_ln_gates(ga, num_sms, s);
+    run16(convs[4]);
+    run16(convs[5]);
+    if (has_ln) {
+      LnStatsArgs so{{orw, nullptr, nullptr}, {1ll * ch * HW, 0, 0}, 1, B, part};
+      launch_ln_stats(so, s);
+    }
+    StLnOutArgs oa{orw, lr, part, kLnSlices, d_ln[8], d_ln[9], op, ho, B, HW, ch, adt};
+    oa.use_ln = has_ln ? 1 : 0;
+    launch_stlstm_ln_out(oa, num_sms, s);
+    launch_nhwc_to_nchw(ho, adt, out[0], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(cb, DT_F32, out[1], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(mb, DT_F32, out[2], B, ch, h, w, num_sms, s);
+    if (out[3]) launch_nhwc_to_nchw(dc, adt, out[3], B, ch, h, w, num_sms, s);
+    if (out[4]) launch_nhwc_to_nchw(dm, adt, out[4], B, ch, h, w, num_sms, s);
+  }
+
+ private:
+  int cin, ch, h, w, k;
+  std::vector<float> wts[6], bs[6];
+  bool has_ln = false;
+  std::vector<float> ln[10];
+  float* d_ln[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
 // ------------------------------------------------------------------------------------------------------------------
 class PhyCellCell : public CellBase {
  public:
@@ -297,7 +432,18 @@ class PhyCellCell : public CellBase {
     while (hid % sq != 0) --sq;
     groups = hid / sq;
   }
-  // in: x, h    out: h'
+  // action_conditional=True (model_blocks/phydnet.py:44-55): frame / hidden first go through their 1x1 action convs
+  void set_action_convs(int action_size, const float* fw_, const float* fb_, const float* hw_, const float* hb_) override {
+    VPK_REQUIRE(action_size > 0 && action_size <= 8, "PhyCell action convs: action_size must be in 1..8");
+    a_sz = action_size;
+    const size_t n = static_cast<size_t>(ch) * (ch + a_sz);
+    afw.assign(fw_, fw_ + n);
+    afb.assign(fb_, fb_ + ch);
+    ahw.assign(hw_, hw_ + n);
+    ahb.assign(hb_, hb_ + ch);
+    built_batch = -1;
+  }
+  // in: x, h [, action [b, a]]    out: h'
   // 16-bit mode: F.conv1 / F.conv2 run on FP16 operands (h and the GroupNorm output are O(1); the GroupNorm between them
   // amplifies operand rounding: with bf16 operands the golden block is 6.8e-3 off after ONE step, with fp16 3e-3), the
   // gate conv and its blend epilogue on bf16.
@@ -313,15 +459,60 @@ class PhyCellCell : public CellBase {
     float* ht = static_cast<float*>(buf("htilde", px * ch * sizeof(float)));
     float* f1 = static_cast<float*>(buf("f1raw", px * Cp * sizeof(float)));
     void* f1n = buf("f1n", px * Cp * esize());
+    const bool ac = a_sz > 0;
+    VPK_REQUIRE(!ac || in[2] != nullptr, "Given actions are None or of the wrong size!");
+    // action-conditional: fp32 frame / hidden, the inflated action, and the convolved frame / hidden (fp32; `hidden` is what
+    // the prediction h~ = hidden + F(hidden) starts from)
+    float *x32 = nullptr, *h32 = nullptr, *a32 = nullptr, *fa32 = nullptr, *ha32 = nullptr;
+    if (ac) {
+      x32 = static_cast<float*>(buf("x32", px * ch * 4));
+      h32 = static_cast<float*>(buf("h32", px * ch * 4));
+      a32 = static_cast<float*>(buf("a32", px * 8 * 4));
+      fa32 = static_cast<float*>(buf("fa32", px * ch * 4));
+      ha32 = static_cast<float*>(buf("ha32", px * ch * 4));
+    }
     if (built_batch != B) {
       convs.clear();
       PhyCellArgs a{"cell.", B, h, w, ch, hid, k, xb, hi, ho, hm, ht, f1, f1n, w1.data(), b1.data(), w2.data(),
                     b2.data(), wg.data(), bg.data()};
       a.h_f = hf;
+      if (ac) a.h_res = ha32;
       const std::vector<ConvSpec> specs = phycell_specs(a, act(), ActInfo{fdt, esize()});
       for (int i = 0; i < 3; ++i)
         for (BuiltConv& bc : build_conv(specs[i], i < 2 ? fdt : dtype, backend, store, cache, s, num_sms, false))
           convs.push_back(bc);
+      if (ac) {       // two fp32-operand 1x1 convs over (tensor, inflated action): convs[3] frame, convs[4] hidden
+        auto action_conv = [&](const char* name, const float* src, const std::vector<float>& wt, const std::vector<float>& bi,
+                               float* dst) {
+          ConvSpec s1;
+          s1.name = std::string("cell.") + name;
+          s1.B = B;
+          s1.G = 1;
+          s1.C = ch;
+          WeightRef wr;
+          wr.w = wt.data();
+          wr.O = ch;
+          wr.I = ch + a_sz;
+          wr.KH = wr.KW = 1;
+          s1.wrefs.push_back(wr);
+          BiasRef br;
+          br.b = bi.data();
+          s1.biases.push_back(br);
+          ConvInput i0{make_view(src, h, w, ch), 0, 0};
+          ConvInput i1{make_view(a32, h, w, 8), 0, ch};
+          i1.wc_count = a_sz;
+          int oh_, ow_;
+          lower_conv(s1, 1, 1, 0, {i0, i1}, h, w, 4, &oh_, &ow_);
+          EpiParams& e = s1.phases[0].epi;
+          e.kind = EPI_BIAS_ACT;
+          e.act = ACT_NONE;
+          e.out_f32 = 1;
+          dense_out(e, dst, h, w, ch);
+          for (BuiltConv& bc : build_conv(s1, DT_F32, backend, store, cache, s, num_sms, false)) convs.push_back(bc);
+        };
+        action_conv("frame_action_conv", x32, afw, afb, fa32);
+        action_conv("hidden_action_conv", h32, ahw, ahb, ha32);
+      }
       d_gamma = static_cast<float*>(store.upload(gw_.data(), gw_.size() * sizeof(float), s));
       d_beta = static_cast<float*>(store.upload(gb_.data(), gb_.size() * sizeof(float), s));
       finish_build(s);
@@ -334,10 +525,22 @@ class PhyCellCell : public CellBase {
       else if (bc.use_direct) launch_conv_direct(bc.L, dt, num_sms, s);
       else launch_conv_simt(bc.L, dt, s);
     };
-    to_nhwc(in[0], xb, dtype, B, ch, h, w, s);
-    to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
-    if (hf != hi) to_nhwc(in[1], hf, fdt, B, ch, h, w, s);
-    to_nhwc(in[1], hm, DT_F32, B, ch, h, w, s);
+    if (ac) {
+      const long long n = static_cast<long long>(px) * ch;
+      to_nhwc(in[0], x32, DT_F32, B, ch, h, w, s);
+      to_nhwc(in[1], h32, DT_F32, B, ch, h, w, s);
+      launch_inflate_actions(in[2], a_sz, a_sz, a32, DT_F32, B, 1, h * w, 8, num_sms, s);
+      run_dt(convs[3], DT_F32);
+      run_dt(convs[4], DT_F32);
+      launch_add_to_act(fa32, DT_F32, nullptr, xb, dtype, n, num_sms, s);       // frame' as the gate conv's / blend's operand
+      launch_add_to_act(ha32, DT_F32, nullptr, hi, dtype, n, num_sms, s);       // hidden' for the gate conv
+      if (hf != hi) launch_add_to_act(ha32, DT_F32, nullptr, hf, fdt, n, num_sms, s);
+    } else {
+      to_nhwc(in[0], xb, dtype, B, ch, h, w, s);
+      to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
+      if (hf != hi) to_nhwc(in[1], hf, fdt, B, ch, h, w, s);
+      to_nhwc(in[1], hm, DT_F32, B, ch, h, w, s);
+    }
     run_dt(convs[0], fdt);
     launch_groupnorm_act(f1, DT_F32, f1n, fdt, nullptr, B, h * w, hid, Cp, Cp, groups, d_gamma, d_beta, 1e-5f,
                          ACT_NONE, s);
@@ -348,6 +551,8 @@ class PhyCellCell : public CellBase {
 
  private:
   int ch, hid, h, w, k, groups = 1;
+  int a_sz = 0;
+  std::vector<float> afw, afb, ahw, ahb;
   std::vector<float> w1, b1, gw_, gb_, w2, b2, wg, bg;
   float *d_gamma = nullptr, *d_beta = nullptr;
 };
@@ -359,6 +564,11 @@ Cell* make_phycell_cell(int precision, int backend, int ch, int hid, int h, int 
                         const float* conv2_b, const float* gate_w, const float* gate_b) {
   return new PhyCellCell(precision, backend, ch, hid, h, w, k, conv1_w, conv1_b, gn_w, gn_b, conv2_w, conv2_b, gate_w,
                          gate_b);
+}
+
+Cell* make_stlstm_ac_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* const* weights,
+                          const float* const* biases) {
+  return new StLstmAcCell(precision, backend, cin, ch, h, w, k, weights, biases);
 }
 
 Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, int gate_order,

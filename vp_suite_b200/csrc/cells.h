@@ -11,12 +11,19 @@ class Cell {
   virtual void step(int batch, const float* const* in, float* const* out, cudaStream_t stream) = 0;
   // ST-LSTM only: LayerNorm affine parameters (gamma, beta) x (conv_x, conv_h, conv_m, conv_o), host, [k*C, H, W]
   virtual void set_layer_norm(const float* const* params) { VPK_THROW(1, "this cell kind has no LayerNorm variant"); }
+  // PhyCell only: the two 1x1 action convs of the action-conditional cell (host; [ch, ch + a, 1, 1] + bias each)
+  virtual void set_action_convs(int action_size, const float* fw, const float* fb, const float* hw, const float* hb) {
+    VPK_THROW(1, "this cell kind has no action-conditional variant");
+  }
 };
 
 Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, int gate_order,
                          const float* weight, const float* bias);
 Cell* make_stlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* w_x,
                        const float* w_h, const float* w_m, const float* w_o, const float* w_last);
+// ActionConditionalSpatioTemporalLSTMCell: weights / biases of conv_x, conv_h, conv_a, conv_m, conv_o, conv_last (host)
+Cell* make_stlstm_ac_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* const* weights,
+                          const float* const* biases);
 Cell* make_phycell_cell(int precision, int backend, int ch, int hid, int h, int w, int k, const float* conv1_w,
                         const float* conv1_b, const float* gn_w, const float* gn_b, const float* conv2_w,
                         const float* conv2_b, const float* gate_w, const float* gate_b);

@@ -8,7 +8,8 @@ the arithmetic happens in libvpk's single-step cell entry points (include/vpk.h)
     ConvLSTMCell            <- vp_suite/model_blocks/conv_lstm_ndrplz.py:7-48     (ndrplz cell)
     SingleStepConvLSTM      <- vp_suite/model_blocks/phydnet.py:117-175
     SpatioTemporalLSTMCell  <- vp_suite/model_blocks/predrnn.py:7-83
-    PhyCell_Cell / PhyCell  <- vp_suite/model_blocks/phydnet.py:13-114            (action_conditional=False)
+    ActionConditionalSpatioTemporalLSTMCell <- vp_suite/model_blocks/predrnn.py:86-169
+    PhyCell_Cell / PhyCell  <- vp_suite/model_blocks/phydnet.py:13-114            (with and without actions)
 """
 import ctypes as C
 
@@ -183,13 +184,11 @@ class SingleStepConvLSTM(nn.Module):
     def __init__(self, input_size, input_dim, hidden_dims, n_layers, kernel_size, action_conditional, action_size,
                  device):
         super().__init__()
-        if action_conditional:
-            raise NotImplementedError("action-conditional variant: SURVEY 8(f)")
         self.input_size, self.input_dim, self.hidden_dims = input_size, input_dim, hidden_dims
         self.n_layers, self.kernel_size = n_layers, kernel_size
         self.H, self.C = [], []
         self.action_size, self.action_conditional, self.device = action_size, action_conditional, device
-        cells, cur = [], input_dim
+        cells, cur = [], input_dim + (action_size if action_conditional else 0)      # phydnet.py:137
         for i in range(n_layers):
             cells.append(ConvLSTMCell(cur, hidden_dims[i], kernel_size, True))
             cur = hidden_dims[i]
@@ -199,6 +198,9 @@ class SingleStepConvLSTM(nn.Module):
         if first_timestep:
             self.init_hidden(frame.shape[0], frame.device)
         inp = frame
+        if self.action_conditional:                                      # phydnet.py:153-155 (layout only: the inflated
+            infl = action.unsqueeze(-1).unsqueeze(-1).expand(-1, -1, *self.input_size)   # action joins the channels)
+            inp = torch.cat([inp, infl.to(inp.dtype)], dim=-3)
         for j, cell in enumerate(self.cell_list):                        # phydnet.py:157-161
             self.H[j], self.C[j] = cell(inp, (self.H[j], self.C[j]))
             inp = self.H[j]
@@ -262,8 +264,63 @@ class SpatioTemporalLSTMCell(_NativeCell, VPModelBlock):
         return tuple(outs)                                               # h', c', m', delta_c, delta_m (predrnn.py:82)
 
 
+class ActionConditionalSpatioTemporalLSTMCell(_NativeCell, VPModelBlock):
+    """model_blocks/predrnn.py:86-169, layer_norm False or True: every conv has a bias, and a fifth conv ``conv_a`` over the
+    action tensor multiplies conv_h's output before the gate split (:149)."""
+    NAME = "Spatio-Temporal LSTM Cell (Action-Conditional)"
+    PAPER_REFERENCE = "https://arxiv.org/abs/2103.09504"
+    CODE_REFERENCE = "https://github.com/thuml/predrnn-pytorch"
+    MATCHES_REFERENCE = "Yes"
+    _CONVS = ("conv_x", "conv_h", "conv_a", "conv_m", "conv_o")
+
+    def __init__(self, in_channel, num_hidden, height, width, filter_size, stride, layer_norm):
+        super().__init__()
+        self._cell_init()
+        if stride != 1 or filter_size % 2 == 0:
+            raise ValueError("stride 1 and odd filter sizes only")
+        self.num_hidden, self.padding, self._forget_bias = num_hidden, filter_size // 2, 1.0
+        self._shape = (in_channel, height, width, filter_size)
+        self._layer_norm = bool(layer_norm)
+
+        def conv(ci, co):
+            layers = [nn.Conv2d(ci, co, filter_size, stride, self.padding)]
+            if layer_norm:
+                layers.append(nn.LayerNorm([co, height, width]))
+            return nn.Sequential(*layers)
+        self.conv_x = conv(in_channel, num_hidden * 7)                   # same construction order as the reference
+        self.conv_h = conv(num_hidden, num_hidden * 4)
+        self.conv_a = conv(num_hidden, num_hidden * 4)
+        self.conv_m = conv(num_hidden, num_hidden * 3)
+        self.conv_o = conv(num_hidden * 2, num_hidden)
+        self.conv_last = nn.Conv2d(num_hidden * 2, num_hidden, 1, 1, 0)
+
+    def _cell_create(self):
+        cin, h, w, k = self._shape
+        cell = C.c_void_p()
+        mods = [getattr(self, n)[0] for n in self._CONVS] + [self.conv_last]
+        ws = [self._host(m.weight) for m in mods]
+        bs = [self._host(m.bias) for m in mods]
+        wp = (C.c_void_p * 6)(*[t.data_ptr() for t in ws])
+        bp = (C.c_void_p * 6)(*[t.data_ptr() for t in bs])
+        N.check(N.lib().vpk_stlstm_ac_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], cin,
+                                                  self.num_hidden, h, w, k, wp, bp, C.byref(cell)))
+        if self._layer_norm:
+            ln = [self._host(t) for n in self._CONVS for t in (getattr(self, n)[1].weight, getattr(self, n)[1].bias)]
+            lp = (C.c_void_p * 10)(*[t.data_ptr() for t in ln])
+            N.check(N.lib().vpk_stlstm_ac_cell_set_layer_norm(cell, lp))
+        return cell
+
+    def forward(self, x_t, h_t, c_t, m_t, a_t):
+        x, h, c, m, a = (self._dev(t) for t in (x_t, h_t, c_t, m_t, a_t))
+        cell = self._cell_handle(x.device)
+        outs = [torch.empty_like(h) for _ in range(5)]
+        self._step(x.device, N.lib().vpk_stlstm_ac_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(m),
+                   N.ptr(a), *[N.ptr(o) for o in outs], self._stream(x))
+        return tuple(outs)                                               # h', c', m', delta_c, delta_m (predrnn.py:169)
+
+
 class PhyCell_Cell(_NativeCell, VPModelBlock):
-    """model_blocks/phydnet.py:13-62 with action_conditional=False."""
+    """model_blocks/phydnet.py:13-62, with or without the two 1x1 action convs (:44-55)."""
     NAME = "PhyCell - Cell"
     PAPER_REFERENCE = "https://arxiv.org/abs/2003.01460"
     CODE_REFERENCE = "https://github.com/vincent-leguen/PhyDNet"
@@ -272,8 +329,6 @@ class PhyCell_Cell(_NativeCell, VPModelBlock):
     def __init__(self, input_dim, action_conditional, action_size, hidden_dim, kernel_size, bias=True):
         super().__init__()
         self._cell_init()
-        if action_conditional:
-            raise NotImplementedError("action-conditional variant: SURVEY 8(f)")
         if not bias or kernel_size[0] != kernel_size[1] or kernel_size[0] % 2 == 0:
             raise ValueError("bias=True and square odd kernels only")
         self.input_dim, self.action_size, self.action_conditional = input_dim, action_size, action_conditional
@@ -284,6 +339,9 @@ class PhyCell_Cell(_NativeCell, VPModelBlock):
         self.F.add_module("bn1", nn.GroupNorm(_gn_divisor(hidden_dim), hidden_dim))
         self.F.add_module("conv2", nn.Conv2d(hidden_dim, input_dim, (1, 1), (1, 1), (0, 0)))
         self.convgate = nn.Conv2d(2 * input_dim, input_dim, (3, 3), padding=(1, 1), bias=bias)
+        if action_conditional:                                           # phydnet.py:44-48
+            self.frame_action_conv = nn.Conv2d(input_dim + action_size, input_dim, (1, 1))
+            self.hidden_action_conv = nn.Conv2d(input_dim + action_size, input_dim, (1, 1))
         self._hw = None
 
     def _cell_create(self):
@@ -294,6 +352,10 @@ class PhyCell_Cell(_NativeCell, VPModelBlock):
         N.check(N.lib().vpk_phycell_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend],
                                                 self.input_dim, self.F_hidden_dim, h, w, self.kernel_size[0],
                                                 *[N.ptr(t) for t in ts], C.byref(cell)))
+        if self.action_conditional:
+            ac = [self._host(t) for t in (self.frame_action_conv.weight, self.frame_action_conv.bias,
+                                          self.hidden_action_conv.weight, self.hidden_action_conv.bias)]
+            N.check(N.lib().vpk_phycell_cell_set_action_convs(cell, int(self.action_size), *[N.ptr(t) for t in ac]))
         return cell
 
     def forward(self, frame, action, hidden):
@@ -303,7 +365,14 @@ class PhyCell_Cell(_NativeCell, VPModelBlock):
             self._cell_release()
         cell = self._cell_handle(x.device)
         out = torch.empty_like(h)
-        self._step(x.device, N.lib().vpk_phycell_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(out), self._stream(x))
+        if self.action_conditional:
+            if action is None or action.dim() != 2 or action.shape[-1] != self.action_size:
+                raise ValueError("Given actions are None or of the wrong size!")
+            a = self._dev(action)
+            self._step(x.device, N.lib().vpk_phycell_cell_step_action, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(a),
+                       N.ptr(out), self._stream(x))
+        else:
+            self._step(x.device, N.lib().vpk_phycell_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(out), self._stream(x))
         return out
 
 
@@ -338,4 +407,4 @@ class PhyCell(VPModelBlock):
         self.H = H
 
 
-MODEL_BLOCK_CLASSES = [ConvLSTM, SpatioTemporalLSTMCell, PhyCell_Cell, PhyCell]
+MODEL_BLOCK_CLASSES = [ConvLSTM, SpatioTemporalLSTMCell, ActionConditionalSpatioTemporalLSTMCell, PhyCell_Cell, PhyCell]
