@@ -431,3 +431,30 @@ def test_ab_switches_select_correct_alternative_paths(manifest, switch, name, ex
         assert torch.equal(got, ref), f"{switch}: max abs diff {(got - ref).abs().max().item()}"
     errs = _frame_errs(got.cpu().numpy(), gold)
     assert errs[0] <= BF16_TOL_FIRST and max(errs) <= BF16_TOL_LAST, f"{switch} on {name}: {errs}"
+
+
+@pytest.mark.parametrize("name,batch,ctx,pred", [("ef_1x64", 8, 10, 10), ("ef_3x32", 5, 3, 4), ("ef_1x64", 3, 2, 1)])
+def test_persistent_sequence_program_is_bit_identical(manifest, name, batch, ctx, pred):
+    """The persistent, state-resident form of the EF rollout (conv_halo.cu MODE 4: one launch per ConvLSTM layer runs all its
+    timesteps with the cell state in shared memory and a grid barrier per step; layer-major stage convs) against the
+    launch-per-step program: same arithmetic per (tile, step) in the same order, so the frames must be identical -- and far
+    fewer launches.  cfg 1's shape (8 x 10 + 10) among the cases."""
+    meta = dict(manifest["models"][name])
+    meta.update(batch=batch, context=ctx, pred=pred, xseed=11)
+    x = _input(meta).cuda()
+    steps, _ = _build(meta["key"], meta, precision="bf16")
+    seq, sd = _build(meta["key"], meta, precision="bf16", use_cuda_graph=True)
+    with torch.no_grad():
+        a = steps(x, pred_frames=pred)[0]
+        b = seq(x, pred_frames=pred)[0]
+        b2 = seq(x, pred_frames=pred)[0]                 # graph replay: the barrier counters are reset inside the graph
+    n_steps, n_seq = steps.last_launch_count(), seq.last_launch_count()
+    print(f"{name} b={batch} {ctx}+{pred}: {n_steps} launches per-step, {n_seq} persistent")
+    assert n_seq <= 20 and n_seq < n_steps, (n_steps, n_seq)
+    assert torch.equal(a, b) and torch.equal(b, b2), float((a - b).abs().max())
+    with torch.no_grad():
+        ref, _ = OM.ef_convlstm_forward(sd, x.cpu(), pred)
+        host, _ = seq.forward_host(x.cpu().pin_memory(), pred_frames=pred)
+    errs = _frame_errs(b.cpu().numpy(), ref.numpy())
+    assert errs[0] <= BF16_TOL_FIRST and max(errs) <= BF16_TOL_LAST, errs
+    assert torch.equal(host, b.cpu())

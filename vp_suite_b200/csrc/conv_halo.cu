@@ -57,16 +57,26 @@ __host__ __device__ constexpr int gates_of(int kind) {
 }
 
 // MODE: 0 generic epilogue, 1 lean compile-time epilogue, 2 ConvLSTM epilogue with a whole tile of operands in flight,
-//       3 bias + activation + fused 1x1 projection to <= 4 channels (fp32 strided output)
+//       3 bias + activation + fused 1x1 projection to <= 4 channels (fp32 strided output),
+//       4 SEQUENCE mode (EPI_LSTM only): one launch runs P.seq_T timesteps of the layer.  Every role wraps its tile loop
+//         in a timestep loop (the same (M unit, N tile) list per CTA every step), the cell state c of the CTA's tiles
+//         lives in shared memory from the first to the last step, h'_t goes to slot t of the output sequence and is
+//         read back as step t+1's recurrent input through TMA after a grid-wide barrier (release / acquire on a global
+//         counter + fence.proxy.async: the stores are generic-proxy, the loads async-proxy).  All CTAs must be
+//         co-resident (grid <= what cudaOccupancyMaxActiveClusters reports; one CTA per SM).
 template <int KIND, bool PAIR, int MODE>
 __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid_constant__ HaloPlan P) {
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
   using bf16 = __nv_bfloat16;
   constexpr int G = gates_of(KIND);
-  constexpr bool FAST = MODE == 1 || MODE == 2;
+  constexpr bool FAST = MODE == 1 || MODE == 2 || MODE == 4;
+  constexpr bool SEQ = MODE == 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = ptx::smem_u32(smem_raw);
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
+  float* s_cstate = reinterpret_cast<float*>(smem);          // SEQ: cell state of this CTA's tiles, in front of the rings
+  if constexpr (SEQ) smem += P.seq_c_bytes;
+  const int T_steps = SEQ ? P.seq_T : 1;
   // PDL: the next kernel of the stream may become resident as soon as every CTA of this grid is (it then waits in its
   // own pdl_wait); everything up to our pdl_wait below reads only plan tables, biases and packed weights' descriptors
   ptx::pdl_launch_dependents();
@@ -223,6 +233,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (ptx::elect_one()) {
       int sa = 0;
       uint32_t ph = 0;
+      for (int ts = 0; ts < T_steps; ++ts) {
+      bool synced = false;      // SEQ: this step's recurrent input has been waited for
       for (int t = unit0; t < total; t += nunits) {
         const int mt = m_tile_of(t);
         const int x0 = (mt % P.tiles_x) * kTW;
@@ -230,6 +242,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int b0 = mt / (P.tiles_x * P.tiles_y);            // odd tail of a pair: b0 == B -> zero fill
         for (int bi = 0; bi < nblocks; ++bi) {
           const HaloBlock blk = s_blocks[bi];
+          int src = blk.src, samp = b0;
+          if constexpr (SEQ) {
+            if (src == P.seq_recur_src) {
+              if (ts == 0) {
+                src = P.seq_h0_src;
+              } else if (!synced) {
+                // step ts reads what every CTA's epilogue wrote in step ts - 1: wait for all arrivals, then order the
+                // async-proxy (TMA) reads behind the acquire
+                const unsigned target = static_cast<unsigned>(ts) * gridDim.x;
+                unsigned seen;
+                do {
+                  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.seq_barrier) : "memory");
+                } while (seen < target);
+                asm volatile("fence.proxy.async;" ::: "memory");
+                synced = true;
+              }
+            }
+            samp = (b0 < P.L.B) ? b0 * P.seq_sb[src] + ts * P.seq_st[src] + P.seq_off[src] : P.seq_oob;
+          }
           ptx::mbar_wait_spin(aempty + 8 * sa, ph ^ 1u);
           const uint32_t fb = afull + 8 * sa;
           const uint32_t dst = ptx::smem_u32(smem_a + sa * P.a_slot_bytes);
@@ -237,13 +268,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             if (leader) ptx::mbar_arrive(fb); else ptx::mbar_arrive_cluster(fb, lead);
           } else if constexpr (PAIR) {
             if (leader) ptx::mbar_arrive_expect_tx(fb, ncta * a_box_bytes); else ptx::mbar_arrive_cluster(fb, lead);
-            ptx::tma_load_4d_pair(&P.amap[blk.src], fb, dst, blk.c0, x0 - rad, y0 - rad, b0);
+            ptx::tma_load_4d_pair(&P.amap[src], fb, dst, blk.c0, x0 - rad, y0 - rad, samp);
           } else {
             ptx::mbar_arrive_expect_tx(fb, a_box_bytes);
-            ptx::tma_load_4d(&P.amap[blk.src], fb, dst, blk.c0, x0 - rad, y0 - rad, b0);
+            ptx::tma_load_4d(&P.amap[src], fb, dst, blk.c0, x0 - rad, y0 - rad, samp);
           }
           if (++sa == SA) { sa = 0; ph ^= 1u; }
         }
+      }
       }
     }
   } else if (warp == 1) {
@@ -270,6 +302,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     } else if (ptx::elect_one()) {
       int sb = 0;
       uint32_t ph = 0;
+      for (int ts = 0; ts < T_steps; ++ts)
       for (int t = unit0; t < total; t += nunits) {
         const int n0 = (t % P.n_tiles) * tileN + static_cast<int>(rank) * (PAIR ? rowsB : 0);
         for (int bi = 0; bi < nblocks; ++bi) {
@@ -333,6 +366,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #define VPK_TIMED(counter, stmt) stmt
 #endif
       if (P.resident && unit0 < total) ptx::mbar_wait_spin(bfull, 0);
+      for (int ts = 0; ts < T_steps; ++ts)
       for (int t = unit0; t < total; t += nunits, ++iter) {
         const int acc = iter & 1;
         VPK_TIMED(w_acc, ptx::mbar_wait_spin(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u));
@@ -509,6 +543,102 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         else run_n(std::false_type{});
       }
     }
+    if constexpr (SEQ && KIND == EPI_LSTM) {
+      // ---- sequence mode: T_steps timesteps, cell state resident in shared memory ----
+      auto run = [&](auto peep_c, auto nch_c) {
+        constexpr bool PEEP = decltype(peep_c)::value;
+        constexpr int NCH = decltype(nch_c)::value;        // this warp's chunks: channels (half + 2k) * 8 of the tile
+        const EpiParams& E = P.L.epi;
+        const int C = E.C;
+        const long long hw = static_cast<long long>(P.L.H) * P.L.W;
+        const int chunks = Cn >> 3;
+        for (int ts = 0; ts < T_steps; ++ts) {
+          int slot = 0;
+          for (int t = unit0; t < total; t += nunits, ++iter, ++slot) {
+            const int nt = t % P.n_tiles;
+            const int mt = m_tile_of(t);
+            const int x = (mt % P.tiles_x) * kTW + rx;
+            const int y = ((mt / P.tiles_x) % P.tiles_y) * kTH + ry;
+            const int b = mt / (P.tiles_x * P.tiles_y);
+            const int chb = nt * Cn;
+            const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B);
+            LstmTile et{};
+            if (valid) {
+              et = lstm_tile(E, b, y, x, P.L.H, P.L.W);      // st_off: c_0 / c_T in global memory, indexed by the sequence b
+              const long long bo = static_cast<long long>(b) * P.seq_out_sb + static_cast<long long>(ts) * P.seq_out_st + P.seq_out_off;
+              et.out_off = bo * E.oB + y * E.oY + x * E.oX;  // h'_t: slot (b, ts) of the output sequence
+            }
+            const int acc = iter & 1;
+            ptx::mbar_wait_fast(tfull + 8 * acc, (iter >> 1) & 1u);
+            ptx::tc_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
+            LstmPeep pp[2];
+            if constexpr (PEEP)
+              if (valid && chb + half * 8 < C) lstm_peep_load(E, et, hw, chb + half * 8, pp[0]);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const int chl = (half + 2 * k) * 8;
+              uint32_t r[32];
+              ptx::tmem_ld32(taddr + static_cast<uint32_t>(chl * 4), r);
+              if constexpr (PEEP)
+                if (k + 1 < NCH && valid && chb + chl + 16 < C) lstm_peep_load(E, et, hw, chb + chl + 16, pp[(k + 1) & 1]);
+              ptx::tmem_ld_wait();
+              if (valid && chb + chl < C) {
+                float4* cp = reinterpret_cast<float4*>(s_cstate + ((static_cast<size_t>(slot) * chunks + (chl >> 3)) * 128 + row) * 8);
+                LstmOps o;
+                if (ts == 0) {
+                  if (P.seq_c_zero) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.c[j] = 0.f;
+                  } else {
+                    lstm_c_load(E, et, hw, chb + chl, o);
+                  }
+                } else {
+                  const float4 c0 = cp[0], c1 = cp[1];
+                  o.c[0] = c0.x; o.c[1] = c0.y; o.c[2] = c0.z; o.c[3] = c0.w;
+                  o.c[4] = c1.x; o.c[5] = c1.y; o.c[6] = c1.z; o.c[7] = c1.w;
+                }
+                float a[4][8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+#pragma unroll
+                  for (int g = 0; g < 4; ++g) a[g][j] = __uint_as_float(r[j * 4 + g]);
+                lstm_finish<PEEP, false>(E, et, hw, chb + chl, s_bias, a, o, pp[k & 1]);
+                cp[0] = make_float4(o.c[0], o.c[1], o.c[2], o.c[3]);
+                cp[1] = make_float4(o.c[4], o.c[5], o.c[6], o.c[7]);
+                if (ts == T_steps - 1 && E.s0 != nullptr) st_state8(E.s0, et.st_off, E.state_c4 ? hw * 4 : 0, chb + chl, o.c);
+              }
+            }
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
+              else ptx::mbar_arrive(tempty + 8 * acc);
+            }
+          }
+          if (ts + 1 < T_steps) {
+            // this CTA's h'_ts is complete: publish it (generic-proxy stores -> other CTAs' TMA reads) and arrive once
+            asm volatile("fence.proxy.async;" ::: "memory");
+            __threadfence();
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (warp == 3 && lane == 0)
+              asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.seq_barrier), "r"(1u) : "memory");
+          }
+        }
+      };
+      auto run_n = [&](auto peep_c) {
+        switch ((Cn / 8 - half + 1) / 2) {
+          case 1: run(peep_c, std::integral_constant<int, 1>{}); break;
+          case 2: run(peep_c, std::integral_constant<int, 2>{}); break;
+          case 3: run(peep_c, std::integral_constant<int, 3>{}); break;
+          case 4: run(peep_c, std::integral_constant<int, 4>{}); break;
+          default: __trap();
+        }
+      };
+      if (P.L.epi.pp16 != nullptr) run_n(std::true_type{});
+      else run_n(std::false_type{});
+    }
     if constexpr (MODE == 3) {
       // ---- bias + activation + 1x1 projection: one warp per TMEM quadrant reads all channels of its positions ----
       const EpiParams& E = P.L.epi;
@@ -555,7 +685,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
     }
-    if constexpr (!rolled && MODE != 3)
+    if constexpr (!rolled && MODE != 3 && !SEQ)
     for (int t = unit0; t < total; t += nunits, ++iter) {
       const int nt = t % P.n_tiles;
       const int mt = m_tile_of(t);
@@ -868,9 +998,12 @@ bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int 
 }
 
 void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
-                    int radius, HaloPlan* plan, int num_sms) {
+                    int radius, HaloPlan* plan, int num_sms, unsigned reserve_smem) {
   HaloPlan& P = *plan;
   P.L = L;
+  P.seq_T = 0;
+  P.seq_c_bytes = 0;
+  P.seq_barrier = nullptr;
   P.blocks = d_blocks;
   P.taps = d_taps;
   P.nblocks = nblocks;
@@ -931,7 +1064,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   // SM's shared memory lets the next kernel's CTAs become resident under PDL and overlap their set-up -- measured on
   // cfg 4 / cfg 2 it is SLOWER (10.37 vs 9.70 ms, 10.45 vs 10.02 ms): the shallower activation ring costs more than the
   // hidden set-up saves.
-  unsigned budget = kMaxSmem;
+  VPK_REQUIRE(reserve_smem % 1024 == 0 && reserve_smem + 96 * 1024 <= kMaxSmem, "halo plan: shared-memory reserve too large");
+  unsigned budget = kMaxSmem - reserve_smem;
   if (const char* env = getenv("VPK_HALO_SMEM_CAP")) {
     const unsigned cap = static_cast<unsigned>(atoi(env));
     const bool low_reg = (L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0) || L.epi.kind == EPI_PHY_GATE;
@@ -944,6 +1078,11 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   sb = std::max(4, std::min(24, sb));
   while (sb > 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes > avail) --sb;
   if (P.resident) sb = 1;
+  if (reserve_smem > 0 && !((sb >= 2 || P.resident) && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail)) {
+    P.SA = P.SB = 0;          // sequence plan that does not fit: the caller falls back to per-step launches
+    P.smem_bytes = 0;
+    return;
+  }
   VPK_REQUIRE((sb >= 2 || P.resident) && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail,
               "halo plan: shared memory budget exceeded");
   P.SB = sb;
@@ -955,7 +1094,7 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
       P.SB = std::min<int>(24, static_cast<int>((avail - P.SA * P.a_slot_bytes) / P.b_slot_bytes));
     }
   }
-  P.smem_bytes = fixed + P.SA * P.a_slot_bytes + P.SB * P.b_slot_bytes;
+  P.smem_bytes = fixed + P.SA * P.a_slot_bytes + P.SB * P.b_slot_bytes + reserve_smem;
   // Streamed weights are the largest L2 -> SM stream of the gate GEMMs (27 taps x 32 KB per 256 x 256 tile against
   // 69 KB of activations; the MMA thread waits for weight tiles 25-34 % of its time, phase timeline in profiles/).
   // VPK_HALO_MC=1 (size rule) / 2 (always) runs clusters of four CTAs that fetch every weight tile once for two CTA
@@ -992,7 +1131,96 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   encode(&P.bmap, 2, L.wpacked, dims, strides, box, "packed weights");
 }
 
+namespace {
+template <bool PAIR> int max_coresident_ctas(unsigned smem_bytes, int grid) {
+  cudaFuncSetAttribute(conv_halo_kernel<EPI_LSTM, PAIR, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kMaxSmem));
+  cudaLaunchConfig_t q{};
+  q.gridDim = dim3(static_cast<unsigned>(grid));
+  q.blockDim = dim3(kHaloThreads);
+  q.dynamicSmemBytes = smem_bytes;
+  cudaLaunchAttribute qa[1];
+  qa[0].id = cudaLaunchAttributeClusterDimension;
+  qa[0].val.clusterDim.x = PAIR ? 2 : 1;
+  qa[0].val.clusterDim.y = 1;
+  qa[0].val.clusterDim.z = 1;
+  q.attrs = qa;
+  q.numAttrs = 1;
+  int n = 0;
+  VPK_CUDA(cudaOccupancyMaxActiveClusters(&n, conv_halo_kernel<EPI_LSTM, PAIR, 4>, &q));
+  return n * (PAIR ? 2 : 1);
+}
+}  // namespace
+
+bool halo_make_seq_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
+                        int radius, const HaloSeqSpec& seq, HaloPlan* plan, int num_sms) {
+  HaloPlan& P = *plan;
+  VPK_REQUIRE(L.epi.kind == EPI_LSTM && L.G == 4 && seq.T >= 1 && seq.barrier != nullptr, "sequence plan: ConvLSTM layers only");
+  // pass 1: tiling / pairing / grid of one timestep (all of shared memory); pass 2: the same with the cell-state reserve
+  halo_make_plan(L, d_blocks, d_taps, nblocks, ntaps, radius, &P, num_sms);
+  if (!(P.fast_epi && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) || P.mc) return false;
+  const long long m_tiles = static_cast<long long>(L.B) * P.tiles_x * P.tiles_y;
+  const long long total = (P.pair ? (m_tiles + 1) / 2 : m_tiles) * P.n_tiles;
+  auto reserve_for = [&](int grid) {
+    const int nunits = grid / (P.pair ? 2 : 1);
+    const int slots = static_cast<int>((total + nunits - 1) / nunits);
+    const unsigned bytes = static_cast<unsigned>(slots) * (L.Cn / 8) * 128 * 8 * sizeof(float);
+    return std::make_pair(slots, (bytes + 1023u) / 1024u * 1024u);
+  };
+  int grid = P.grid;
+  for (int attempt = 0; attempt < 3; ++attempt) {
+    const auto rs = reserve_for(grid);
+    if (rs.second + 96u * 1024u > kMaxSmem) return false;       // leave at least ~96 KB to the operand rings
+    const int pair = P.pair;
+    halo_make_plan(L, d_blocks, d_taps, nblocks, ntaps, radius, &P, num_sms, rs.second);
+    if (P.smem_bytes == 0 || P.pair != pair) return false;
+    const int fit = pair ? max_coresident_ctas<true>(P.smem_bytes, grid) : max_coresident_ctas<false>(P.smem_bytes, grid);
+    if (fit <= 0) return false;
+    if (fit >= grid) {
+      P.grid = grid;
+      P.seq_slots = rs.first;
+      P.seq_c_bytes = rs.second;
+      break;
+    }
+    grid = fit;                 // fewer CTAs can be co-resident than the grid wants: more tiles (state slots) per CTA
+    if (attempt == 2) return false;
+  }
+  P.roll = 0;
+  P.seq_T = seq.T;
+  for (int i = 0; i < kMaxSrc; ++i) {
+    P.seq_sb[i] = seq.sb[i];
+    P.seq_st[i] = seq.st[i];
+    P.seq_off[i] = seq.off[i];
+  }
+  P.seq_recur_src = seq.recur_src;
+  P.seq_h0_src = seq.h0_src;
+  P.seq_out_sb = seq.out_sb;
+  P.seq_out_st = seq.out_st;
+  P.seq_out_off = seq.out_off;
+  P.seq_c_zero = seq.c_zero;
+  P.seq_barrier = seq.barrier;
+  int oob = 0;
+  const int HWp = kTW + 2 * radius, HHp = kTH + 2 * radius;
+  for (int i = 0; i < L.nsrc; ++i) {       // tensor maps over the WHOLE sequence buffers (4th dimension = samples)
+    const SrcView& sv = L.src[i];
+    oob = std::max(oob, seq.samples[i]);
+    cuuint64_t dims[4] = {static_cast<cuuint64_t>(sv.C), static_cast<cuuint64_t>(sv.W), static_cast<cuuint64_t>(sv.H),
+                          static_cast<cuuint64_t>(seq.samples[i])};
+    cuuint64_t strides[3] = {static_cast<cuuint64_t>(sv.sX) * 2, static_cast<cuuint64_t>(sv.sY) * 2,
+                             static_cast<cuuint64_t>(sv.sB) * 2};
+    cuuint32_t box[4] = {64, static_cast<cuuint32_t>(HWp), static_cast<cuuint32_t>(HHp), 1};
+    encode(&P.amap[i], 4, sv.base, dims, strides, box, "activation sequence view");
+  }
+  P.seq_oob = oob + 1;
+  return true;
+}
+
 void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
+  if (P.seq_T > 0) {
+    VPK_REQUIRE(P.L.epi.kind == EPI_LSTM, "conv_halo: sequence mode is a ConvLSTM mode");
+    if (P.pair) launch_one<EPI_LSTM, true, 4>(P, stream);
+    else launch_one<EPI_LSTM, false, 4>(P, stream);
+    return;
+  }
 #define VPK_HALO(KIND)                                                                   \
   if (P.pair) {                                                                          \
     if (P.fast_epi) launch_one<KIND, true, 1>(P, stream);                                \

@@ -56,10 +56,36 @@ struct alignas(64) HaloPlan {
   int fast_epi;                // lean compile-time-specialised epilogue (epilogue_tc.cuh) usable for this launch
   int roll;                    // ConvLSTM epilogue with a whole tile of operands in flight (lstm_ops_load / lstm_finish)
   int debug;
+  // ---- sequence mode (conv_halo_kernel MODE 4): ONE launch runs seq_T timesteps of a ConvLSTM layer, persistent CTAs,
+  //      the cell state c resident in shared memory across the timesteps, a grid-wide barrier between timesteps ----
+  int seq_T;                   // 0: ordinary single-step launch
+  int seq_sb[kMaxSrc], seq_st[kMaxSrc], seq_off[kMaxSrc];   // sample index source s reads at (sequence b, step t): b*sb + t*st + off
+  int seq_oob;                 // a sample index outside every source (zero fill for the odd tail of a CTA pair)
+  int seq_recur_src;           // source that is the layer's own output sequence (step t reads what step t-1 wrote: waits for
+                               // the grid barrier), or -1
+  int seq_h0_src;              // source read INSTEAD of seq_recur_src at t = 0 (the initial hidden state)
+  int seq_out_sb, seq_out_st, seq_out_off;   // sample index of h'_t in the output tensor (L.epi.out, sample stride epi.oB)
+  int seq_c_zero;              // 1: c starts at zero; 0: c_0 is read from L.epi.s0.  c_T is always stored to L.epi.s0
+  int seq_slots;               // (M unit, N tile) iterations per CTA and timestep = cell-state slots in shared memory
+  unsigned seq_c_bytes;        // shared memory reserved for the cell state (in front of the rings)
+  unsigned* seq_barrier;       // device counter, zeroed before every launch
 };
+// Sequence-mode plan of a ConvLSTM layer (see HaloPlan::seq_*).  `L` describes ONE timestep over L.B sequences; src_samples[s]
+// = number of samples (4th tensor-map dimension) of source s.  Returns false when the layer does not fit (cell state of a
+// CTA's tiles above the shared-memory reserve, or fewer co-resident CTAs than the grid needs).
+struct HaloSeqSpec {
+  int T;
+  int sb[kMaxSrc], st[kMaxSrc], off[kMaxSrc], samples[kMaxSrc];
+  int recur_src, h0_src;
+  int out_sb, out_st, out_off;
+  int c_zero;
+  unsigned* barrier;
+};
+bool halo_make_seq_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
+                        int radius, const HaloSeqSpec& seq, HaloPlan* plan, int num_sms);
 bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps);
 void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
-                    int radius, HaloPlan* plan, int num_sms);
+                    int radius, HaloPlan* plan, int num_sms, unsigned reserve_smem = 0);
 void launch_conv_halo(const HaloPlan& plan, cudaStream_t stream);
 
 // True when the launch can run on the tensor-core kernel (bf16, channel counts TMA-addressable, ...).

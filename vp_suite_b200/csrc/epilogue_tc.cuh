@@ -316,7 +316,8 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
   }
 }
 
-template <bool PEEP>
+// STORE_C = false: the new cell state only stays in o.c (sequence mode keeps it in shared memory)
+template <bool PEEP, bool STORE_C = true>
 __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& t, long long hw, int ch,
                                             const float* s_bias, float (&acc)[4][8], LstmOps& o, const LstmPeep& pp) {
   using bf16 = __nv_bfloat16;
@@ -359,7 +360,7 @@ __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& 
       h[j] = sigmoid_fast(acc[3][j]) * tanh_fast(cn);
     }
   }
-  st_state8(E.s0, t.st_off, E.state_c4 ? hw * 4 : 0, ch, o.c);
+  if constexpr (STORE_C) st_state8(E.s0, t.st_off, E.state_c4 ? hw * 4 : 0, ch, o.c);
   st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
   if (E.h32 != nullptr) st_f32x8(E.h32 + t.out_off + ch, h);
 }

@@ -128,7 +128,236 @@ class EfConvLstm : public Model {
     return out;
   }
 
+  // ================================================================================================================
+  // Persistent, state-resident form for the latency-bound small-batch case (BASELINE north_star: "a persistent-kernel
+  // variant keeps cell state resident across the context and prediction timesteps").  LAYER-MAJOR like the reference
+  // (ef_blocks.py:67-82, 100-114): every stage conv / deconv runs ONCE over all B * T frames of its layer, and every
+  // ConvLSTM layer is ONE launch of the halo kernel's sequence mode (conv_halo.cu MODE 4): T timesteps inside the kernel,
+  // the cell state of a CTA's tiles in shared memory from the first to the last step, h_t written to slot t of the
+  // layer's output sequence and read back through TMA after a grid-wide barrier.  ~14 launches per rollout instead of
+  // ~120; each (tile, step) performs exactly the per-step program's arithmetic in the same order, so the frames are
+  // bit-identical to it.  Sequence tensors are sample-major [b][t] (sample index b * T + t): the input frames and the
+  // output frames then already have the boundary's [b, t, ...] order.
+  // Returns false (nothing emitted) when a layer's cell state does not fit the shared-memory reserve.
+  // ================================================================================================================
+  bool build_seq(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) {
+    const vpk_model_desc& d = desc;
+    const ActInfo act{dtype, esize()};
+    const int esz = esize();
+    const int c = d.img_c, h = d.img_h, w = d.img_w;
+    const int cs = 8;                                   // frames are stored with 8 zero-padded channels (TMA-addressable)
+    const size_t frame_px = static_cast<size_t>(h) * w;
+    char* frames_in = static_cast<char*>(arena.alloc(frame_px * cs * esz * B * t_in));
+    float* out_stage = static_cast<float*>(arena.alloc(frame_px * c * sizeof(float) * B * pred));
+    void *xin[3], *hseq_e[3], *hseq_f[3], *yseq[3], *hzero[3];
+    float* cbuf[3];
+    for (int n = 0; n < 3; ++n) {
+      const size_t px = static_cast<size_t>(eh[n]) * ew[n];
+      xin[n] = arena.alloc(px * d.enc_c[2 * n] * esz * B * t_in);
+      hseq_e[n] = arena.alloc(px * d.enc_c[2 * n + 1] * esz * B * t_in);
+      hseq_f[n] = arena.alloc(px * d.enc_c[2 * n + 1] * esz * B * pred);      // forecaster layer continuing encoder state n
+      hzero[n] = arena.alloc(px * d.enc_c[2 * n + 1] * esz * B);
+      cbuf[n] = static_cast<float*>(arena.alloc(px * d.enc_c[2 * n + 1] * sizeof(float) * B));
+    }
+    for (int n = 0; n < 3; ++n)
+      yseq[n] = arena.alloc(static_cast<size_t>(dh[n + 1]) * dw[n + 1] * d.dec_c[2 * n + 1] * esz * B * pred);
+    unsigned* barriers = static_cast<unsigned*>(arena.alloc(6 * 128));
+    if (measure) return true;
+
+    const float* peep[2][3][3] = {};
+    const void* peep16[2][3] = {};
+    for (int side = 0; side < 2; ++side)
+      for (int n = 0; n < 3; ++n) {
+        const std::string rn = std::string(side == 0 ? "encoder.rnn" : "forecaster.rnn") + std::to_string(n + 1) + ".";
+        const int C = d.enc_c[2 * n + 1];
+        if (!has(rn + "Wci") && !has(rn + "Wcf") && !has(rn + "Wco")) continue;
+        const char* names[3] = {"Wci", "Wcf", "Wco"};
+        for (int k = 0; k < 3; ++k)
+          peep[side][n][k] = dev_f32(rn + names[k], peephole_packed(rn + names[k], C, eh[n], ew[n]), stream);
+        if (C % 8 == 0) peep16[side][n] = dev_f32(rn + "peepholes.bf16", peephole_bf16_packed(rn, C, eh[n], ew[n]), stream);
+      }
+
+    std::vector<Op> pre, body;
+    // One ConvLSTM layer over T steps: the single-step spec gives the packed weights, step tables and tiling; its sequence
+    // plan re-reads the sources / output as [b][t] sample-major sequences.
+    auto seq_layer = [&](LstmArgs la, int T, const void* x_seq, const void* h0, int h0_samples, int h0_sb, int h0_off,
+                         void* out_seq, bool c_zero, int slot) -> bool {
+      la.x = x_seq;
+      la.h_in = out_seq;
+      la.h_out = out_seq;
+      ConvSpec sp = lstm_spec(la, act);
+      std::vector<BuiltConv> built = build_conv(sp, dtype, backend, store, packed_cache, stream, num_sms, false);
+      if (built.size() != 1 || !built[0].use_halo) return false;
+      BuiltConv& bc = built[0];
+      const int n_x = x_seq ? 1 : 0;
+      HaloSeqSpec sq{};
+      sq.T = T;
+      ConvLaunch L = bc.L;
+      if (n_x) {
+        sq.sb[0] = T; sq.st[0] = 1; sq.off[0] = 0; sq.samples[0] = B * T;
+      }
+      sq.recur_src = n_x;                                              // the h source follows x in lstm_spec's input list
+      sq.sb[n_x] = T; sq.st[n_x] = 1; sq.off[n_x] = -1; sq.samples[n_x] = B * T;     // step t reads slot t - 1
+      VPK_REQUIRE(L.nsrc == n_x + 1 && L.nsrc < kMaxSrc, "sequence layer: unexpected source list");
+      L.src[L.nsrc] = make_view(h0, la.H, la.W, la.C);                 // initial hidden state (read at t = 0 only)
+      sq.h0_src = L.nsrc;
+      sq.sb[L.nsrc] = h0_sb; sq.st[L.nsrc] = 0; sq.off[L.nsrc] = h0_off; sq.samples[L.nsrc] = h0_samples;
+      L.nsrc += 1;
+      sq.out_sb = T; sq.out_st = 1; sq.out_off = 0;
+      sq.c_zero = c_zero ? 1 : 0;
+      sq.barrier = barriers + slot * 32;
+      auto plan = std::make_shared<HaloPlan>();
+      if (!halo_make_seq_plan(L, bc.halo.blocks, bc.halo.taps, bc.halo.nblocks, bc.halo.ntaps, bc.halo.P, sq, plan.get(), num_sms))
+        return false;
+      Op op;
+      op.name = la.name + "seq";
+      op.flops = bc.L.flops * T;
+      op.gate = true;
+      op.fn = [plan](cudaStream_t s, const RunCtx&) { launch_conv_halo(*plan, s); };
+      body.push_back(std::move(op));
+      return true;
+    };
+    Program tmp;                  // add_conv appends to an op list of its own program argument or to `dst`
+    auto conv_ops = [&](const ConvSpec& spec) { add_conv(tmp, spec, false, stream, -1, &body); };
+    {
+      const int ns = num_sms;
+      const size_t zb[3] = {static_cast<size_t>(eh[0]) * ew[0] * d.enc_c[1] * esz * B, static_cast<size_t>(eh[1]) * ew[1] * d.enc_c[3] * esz * B,
+                            static_cast<size_t>(eh[2]) * ew[2] * d.enc_c[5] * esz * B};
+      Op cv;
+      cv.name = "frames_to_nhwc";
+      const long long chw = static_cast<long long>(c) * h * w;
+      cv.fn = [=](cudaStream_t s, const RunCtx& ctx) {
+        launch_frames_to_nhwc8(ctx.x, chw, frames_in, nullptr, DT_BF16, B * t_in, 1, c, h, w, ns, s);
+      };
+      pre.push_back(std::move(cv));
+      Op z;
+      z.name = "zero_h0_barriers";
+      z.is_kernel = false;
+      void* hz0 = hzero[0]; void* hz1 = hzero[1]; void* hz2 = hzero[2];
+      z.fn = [=](cudaStream_t s, const RunCtx&) {
+        VPK_CUDA(cudaMemsetAsync(hz0, 0, zb[0], s));
+        VPK_CUDA(cudaMemsetAsync(hz1, 0, zb[1], s));
+        VPK_CUDA(cudaMemsetAsync(hz2, 0, zb[2], s));
+        VPK_CUDA(cudaMemsetAsync(barriers, 0, 6 * 128, s));
+      };
+      body.push_back(std::move(z));
+    }
+    // ---------------- encoder, layer-major ----------------
+    const void* in = frames_in;
+    int in_h = h, in_w = w, in_c = cs;
+    for (int n = 0; n < 3; ++n) {
+      const std::string st = "encoder.stage" + std::to_string(n + 1) + ".conv.";
+      const std::string rn = "encoder.rnn" + std::to_string(n + 1) + ".";
+      const int mid = d.enc_c[2 * n], outc = d.enc_c[2 * n + 1];
+      int oh, ow;
+      const bool stem = n == 0 && conv_stem_supported(d.enc_conv_k[0], d.enc_conv_s[0], d.enc_conv_p[0], c, mid, in_h, in_w) &&
+                        getenv("VPK_NO_STEM") == nullptr;
+      if (stem) {
+        std::vector<float> hb(hp(st + "bias"), hp(st + "bias") + mid);
+        StemArgs sa{in, 0, B * t_in, in_h, in_w, c, d.enc_conv_s[0],
+                    dev_f32(st + "stem.w", conv_stem_pack(hp(st + "weight"), mid, c, DT_BF16), stream),
+                    dev_f32(st + "stem.b", hb, stream), mid, d.ef_act, xin[n], 0};
+        const int ns = num_sms;
+        Op op;
+        op.name = st + "stem";
+        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_conv_stem(sa, ns, s); };
+        body.push_back(std::move(op));
+      } else {
+        ConvArgs ca{st, B * t_in, in_h, in_w, in_c, mid, d.enc_conv_k[n], d.enc_conv_s[n], d.enc_conv_p[n], in,
+                    hp(st + "weight"), hp(st + "bias"), d.ef_act, xin[n]};
+        if (n == 0) ca.cin_w = c;
+        conv_ops(conv_spec(ca, act, &oh, &ow));
+      }
+      LstmArgs la{rn, B, eh[n], ew[n], mid, outc, d.enc_rnn_k[n], nullptr, nullptr, nullptr, cbuf[n], hp(rn + "_conv.weight"),
+                  hp(rn + "_conv.bias"), false, peep[0][n][0], peep[0][n][1], peep[0][n][2]};
+      la.c4 = true;
+      la.pp16 = peep16[0][n];
+      if (!seq_layer(la, t_in, xin[n], hzero[n], B, 1, 0, hseq_e[n], true, n)) return false;
+      in = hseq_e[n];
+      in_h = eh[n];
+      in_w = ew[n];
+      in_c = outc;
+    }
+    // ---------------- forecaster, layer-major ----------------
+    const void* fin = nullptr;                                          // rnn3 gets inputs=None
+    for (int n = 0; n < 3; ++n) {
+      const int idx = 3 - n, e = 2 - n;
+      const std::string rn = "forecaster.rnn" + std::to_string(idx) + ".";
+      const std::string st = "forecaster.stage" + std::to_string(idx) + ".deconv.";
+      const int mid = d.dec_c[2 * n], outc = d.dec_c[2 * n + 1];
+      LstmArgs la{rn + (fin ? "" : "h_only."), B, dh[n], dw[n], dec_in_c[n], mid, d.dec_rnn_k[n], nullptr, nullptr, nullptr, cbuf[e],
+                  hp(rn + "_conv.weight"), hp(rn + "_conv.bias"), false, peep[1][idx - 1][0], peep[1][idx - 1][1], peep[1][idx - 1][2]};
+      la.c4 = true;
+      la.pp16 = peep16[1][idx - 1];
+      // initial state = the encoder layer's final (h, c): slot t_in - 1 of its output sequence; c through cbuf[e]
+      if (!seq_layer(la, pred, fin, hseq_e[e], B * t_in, t_in, t_in - 1, hseq_f[e], false, 3 + n)) return false;
+      int oh, ow;
+      DeconvArgs da{st, B * pred, dh[n], dw[n], mid, outc, d.dec_conv_k[n], d.dec_conv_s[n], d.dec_conv_p[n], 0,
+                    hseq_f[e], hp(st + "weight"), hp(st + "bias"), d.ef_act, yseq[n]};
+      if (n == 2) {
+        da.name = st + "final_fused.";
+        da.out = out_stage;
+        da.nchw = true;
+        da.oB_nchw = static_cast<long long>(c) * h * w;              // sample (b, t) = frame t of sequence b: [b, t, c, h, w]
+        da.proj_n = c;
+        const HostParam& fw = params.at("forecaster.stage1.final.weight");
+        const HostParam& fb = params.at("forecaster.stage1.final.bias");
+        da.proj_w = dev_f32("forecaster.stage1.final.weight", fw.data, stream);
+        da.proj_b = dev_f32("forecaster.stage1.final.bias", fb.data, stream);
+      }
+      const long long tiles = static_cast<long long>(B) * pred * ((dh[n] + 15) / 16) * ((dw[n] + 7) / 8);
+      const bool subpix = deconv_subpix_ok(da) && tiles <= 2ll * num_sms;
+      if (subpix) conv_ops(deconv_subpix_spec(da, act, &oh, &ow));
+      else conv_ops(deconv_spec(da, act, &oh, &ow));
+      fin = yseq[n];
+    }
+    for (Op& o : pre) prog.pre.push_back(std::move(o));
+    for (Op& o : body) prog.body.push_back(std::move(o));
+    const size_t bytes = frame_px * c * sizeof(float) * B * pred;
+    Op post;
+    post.name = "copy_out";
+    post.is_kernel = false;
+    post.fn = [=](cudaStream_t s, const RunCtx& ctx) { VPK_CUDA(cudaMemcpyAsync(ctx.out, out_stage, bytes, cudaMemcpyDeviceToDevice, s)); };
+    prog.post.push_back(std::move(post));
+    return true;
+  }
+
+  // sequence (persistent) form is for the small-batch latency mode: the CUDA-graph flag selects it (VPK_EF_SEQ=0: off)
+  bool seq_candidate() const {
+    const vpk_model_desc& d = desc;
+    const char* env = getenv("VPK_EF_SEQ");
+    const bool fused_final_ok = d.dec_conv_s[2] == 1 && d.img_c <= 4 && d.dec_c[4] % 8 == 0 && d.dec_c[5] % 8 == 0 &&
+                                d.dec_c[5] <= 64 && d.final_conv_c == d.dec_c[5];
+    bool ch8 = true;
+    for (int i = 0; i < 6; ++i) ch8 = ch8 && d.enc_c[i] % 8 == 0 && d.dec_c[i] % 8 == 0;
+    return desc.use_cuda_graph != 0 && dtype == DT_BF16 && backend == 0 && d.img_c <= 8 && fused_final_ok && ch8 &&
+           (env == nullptr || atoi(env) != 0) && getenv("VPK_TC_HALO") == nullptr;
+  }
+
   void build(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) override {
+    if (seq_candidate()) {
+      if (measure) {            // workspace: the larger of the two layouts
+        Arena a2;
+        build_seq(prog, a2, B, t_in, pred, true, stream);
+        build_steps(prog, arena, B, t_in, pred, true, stream);
+        arena.off = std::max(arena.off, a2.off);
+        return;
+      }
+      const size_t off0 = arena.off;
+      if (build_seq(prog, arena, B, t_in, pred, false, stream)) {
+        seq_built = true;
+        return;
+      }
+      arena.off = off0;         // a layer does not fit: per-step launches
+      prog.pre.clear();
+      prog.body.clear();
+      prog.post.clear();
+    }
+    seq_built = false;
+    build_steps(prog, arena, B, t_in, pred, measure, stream);
+  }
+
+  void build_steps(Program& prog, Arena& arena, int B, int t_in, int pred, bool measure, cudaStream_t stream) {
     const vpk_model_desc& d = desc;
     const ActInfo act{dtype, esize()};
     const int esz = esize();
@@ -348,6 +577,7 @@ class EfConvLstm : public Model {
 
  private:
   int eh[3], ew[3], dh[4], dw[4], dec_in_c[3];
+  bool seq_built = false;
 };
 
 }  // namespace
