@@ -160,6 +160,16 @@ int vpk_convlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const 
                            const float* wci, const float* wcf, const float* wco, float* h_out, float* c_out,
                            void* stream);
 
+/* Backward of one ConvLSTMCell step (gate_order == 1: conv_lstm_ndrplz.py:28-43), for training through the drop-in block
+ * (the reference's train_iter back-propagates through every cell step, base_model.py:148-179).
+ * Takes the step's inputs x, h, c and the upstream gradients of its outputs dh_out / dc_out (DEVICE fp32 NCHW; either may be
+ * NULL = zero), recomputes the gates, and writes dx [b, cin, h, w], dh, dc [b, ch, h, w], dw [4ch, cin + ch, k, k] and
+ * db [4ch] (NULL allowed) -- the gradients torch.autograd gives for the reference cell.  The cell keeps the weights it was
+ * created with; dw / db are per call (the caller accumulates).  Deterministic. */
+int vpk_convlstm_cell_backward(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
+                               const float* dh_out, const float* dc_out, float* dx, float* dh, float* dc, float* dw, float* db,
+                               void* stream);
+
 /* Replaces SpatioTemporalLSTMCell.forward with layer_norm=False (model_blocks/predrnn.py:57-83).
  *   weights HOST fp32: w_x [7ch, cin, k, k], w_h [4ch, ch, k, k], w_m [3ch, ch, k, k], w_o [ch, 2ch, k, k],
  *   w_last [ch, 2ch, 1, 1].  x [b, cin, h, w]; h, c, m [b, ch, h, w]; outputs h', c', m', delta_c, delta_m. */

@@ -1,0 +1,104 @@
+"""Gradients of the differentiable ConvLSTMCell drop-in (vpk_convlstm_cell_backward behind a torch.autograd.Function)
+against torch autograd on the reference cell (baseline/_ref) or, without it, on the oracle's restatement -- fp32 mode to
+1e-4 relative, 16-bit mode to a few percent; and BPTT over two chained steps of a two-layer stack."""
+import os
+
+import pytest
+import torch
+
+from oracle import blocks as OB, ref_shim
+from oracle.weights import synth_state_dict
+
+pytestmark = pytest.mark.gpu
+HAVE_REF = ref_shim.available() and not os.environ.get("VPK_NO_REFERENCE")
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+def _reference_cell(cin, ch, sd):
+    if HAVE_REF:
+        from vp_suite.model_blocks.conv_lstm_ndrplz import ConvLSTMCell as RefCell
+        ref = RefCell(input_dim=cin, hidden_dim=ch, kernel_size=(3, 3), bias=True)
+        ref.load_state_dict(sd)
+        return ref, (lambda x, h, c: ref(x, (h, c))), [ref.conv.weight, ref.conv.bias]
+    w = sd["conv.weight"].clone().requires_grad_(True)
+    b = sd["conv.bias"].clone().requires_grad_(True)
+    return None, (lambda x, h, c: OB.convlstm_cell_step(x, h, c, w, b)), [w, b]
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+@pytest.mark.parametrize("cin,ch,hw,batch", [(8, 16, (10, 10), 2), (64, 128, (16, 16), 3)])
+def test_convlstm_cell_gradients_match_autograd(precision, tol, cin, ch, hw, batch):
+    from vp_suite_b200 import model_blocks as MB
+    dev = "cuda:0"
+    cell = MB.ConvLSTMCell(input_dim=cin, hidden_dim=ch, kernel_size=(3, 3), bias=True).to(dev)
+    cell.precision = precision
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in cell.state_dict().items()}, seed=41)
+    cell.load_state_dict(sd)
+    g = torch.Generator().manual_seed(42)
+    x, h, c = (torch.rand((batch, n, *hw), generator=g) * 2 - 1 for n in (cin, ch, ch))
+    r1, r2 = (torch.rand((batch, ch, *hw), generator=g) * 2 - 1 for _ in range(2))
+    # reference gradients (CPU autograd)
+    _, ref_step, ref_params = _reference_cell(cin, ch, sd)
+    xr, hr, cr = (t.clone().requires_grad_(True) for t in (x, h, c))
+    hn, cn = ref_step(xr, hr, cr)
+    ((hn * r1).sum() + (cn * r2).sum()).backward()
+    want = [xr.grad, hr.grad, cr.grad, ref_params[0].grad, ref_params[1].grad]
+    # ours
+    xo, ho, co = (t.clone().to(dev).requires_grad_(True) for t in (x, h, c))
+    hn_o, cn_o = cell(xo, (ho, co))
+    assert hn_o.requires_grad and cn_o.requires_grad
+    ((hn_o * r1.to(dev)).sum() + (cn_o * r2.to(dev)).sum()).backward()
+    got = [xo.grad, ho.grad, co.grad, cell.conv.weight.grad, cell.conv.bias.grad]
+    errs = {n: _rel(a.cpu(), b) for n, a, b in zip(("dx", "dh", "dc", "dW", "db"), got, want)}
+    print(f"ConvLSTMCell backward {precision} cin={cin} ch={ch}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= tol, errs
+    # only dh_out upstream (dc_out absent) and no-grad inference still work
+    xo2 = x.clone().to(dev).requires_grad_(True)
+    hn2, _ = cell(xo2, (h.to(dev), c.to(dev)))
+    hn2.sum().backward()
+    assert xo2.grad is not None and torch.isfinite(xo2.grad).all()
+    with torch.no_grad():
+        hn3, _ = cell(x.to(dev), (h.to(dev), c.to(dev)))
+    assert not hn3.requires_grad and torch.equal(hn3, hn2.detach())
+
+
+def test_bptt_through_a_two_layer_stack_over_two_steps():
+    """SingleStepConvLSTM (model_blocks/phydnet.py:117-175) built from the differentiable cells: gradients flow through both
+    layers and both timesteps exactly as with the reference cells."""
+    from vp_suite_b200 import model_blocks as MB
+    dev = "cuda:0"
+    blk = MB.SingleStepConvLSTM((8, 8), 8, [16, 8], 2, (3, 3), False, 0, dev).to(dev)
+    for cell in blk.cell_list:
+        cell.precision = "fp32"
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=43)
+    blk.load_state_dict(sd)
+    g = torch.Generator().manual_seed(44)
+    xs = [torch.rand((2, 8, 8, 8), generator=g) * 2 - 1 for _ in range(2)]
+    r = torch.rand((2, 8, 8, 8), generator=g)
+    # reference: the oracle's cell step under autograd
+    ws = [sd[f"cell_list.{j}.conv.weight"].clone().requires_grad_(True) for j in range(2)]
+    bs = [sd[f"cell_list.{j}.conv.bias"].clone().requires_grad_(True) for j in range(2)]
+    xr = [x.clone().requires_grad_(True) for x in xs]
+    H = [torch.zeros(2, 16, 8, 8), torch.zeros(2, 8, 8, 8)]
+    C = [torch.zeros(2, 16, 8, 8), torch.zeros(2, 8, 8, 8)]
+    for x in xr:
+        inp = x
+        for j in range(2):
+            H[j], C[j] = OB.convlstm_cell_step(inp, H[j], C[j], ws[j], bs[j])
+            inp = H[j]
+    (H[1] * r).sum().backward()
+    # ours
+    xo = [x.clone().to(dev).requires_grad_(True) for x in xs]
+    out = None
+    for t, x in enumerate(xo):
+        _, out = blk(x, None, first_timestep=(t == 0))
+    (out[-1] * r.to(dev)).sum().backward()
+    errs = {"dx0": _rel(xo[0].grad.cpu(), xr[0].grad), "dx1": _rel(xo[1].grad.cpu(), xr[1].grad)}
+    for j in range(2):
+        errs[f"dW{j}"] = _rel(blk.cell_list[j].conv.weight.grad.cpu(), ws[j].grad)
+        errs[f"db{j}"] = _rel(blk.cell_list[j].conv.bias.grad.cpu(), bs[j].grad)
+    print("BPTT 2 layers x 2 steps (fp32): " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= 1e-4, errs

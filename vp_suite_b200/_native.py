@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libvpk.so")
+# VPK_LIB_PATH: a developer build of the library (e.g. the -DVPK_TRACE phase-timeline build); bench.py records the variable
+LIB_PATH = os.environ.get("VPK_LIB_PATH") or os.path.join(_HERE, "libvpk.so")
 
 VPK_PREC_FP32, VPK_PREC_BF16 = 0, 1
 VPK_BACKEND_AUTO, VPK_BACKEND_SIMT = 0, 1
@@ -66,6 +67,7 @@ SYMBOLS = {
     "vpk_metric_ssim_sums": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     "vpk_convlstm_cell_create": (C.c_int, [C.c_int32] * 8 + [_vp, _vp, C.POINTER(_vp)]),
     "vpk_convlstm_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 9),
+    "vpk_convlstm_cell_backward": (C.c_int, [_vp, C.c_int32] + [_vp] * 11),
     "vpk_stlstm_cell_create": (C.c_int, [C.c_int32] * 7 + [_vp] * 5 + [C.POINTER(_vp)]),
     "vpk_stlstm_cell_set_layer_norm": (C.c_int, [_vp] * 9),
     "vpk_stlstm_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 10),

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../include/vpk.h"
+#include "backward.h"
 #include "builders.h"
 #include "elementwise.h"
 #include "phycell.h"
@@ -119,11 +120,109 @@ class ConvLstmCell : public CellBase {
     launch_nhwc_to_nchw(cb, DT_F32, out[1], B, ch, h, w, num_sms, s);
   }
 
+  // Backward of one ConvLSTMCell step (conv_lstm_ndrplz.py:28-43; training through base_model.py:148-179): recomputes the
+  // gate pre-activations z (one forward conv), differentiates the gate math elementwise, then
+  //   d[x; h] = conv_transpose(dz, W)      -- the generalised conv launch (tensor cores in 16-bit mode)
+  //   dW      = sum over positions of dz (x) shifted cat(x, h), db = sum of dz      -- fp32 CUDA-core kernels
+  // in: x, h, c, dh_out, dc_out   out: dx, dh, dc, dw, db
+  void backward(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    VPK_REQUIRE(ifog, "backward is implemented for the ndrplz ConvLSTMCell (gate order i, f, o, g, no peepholes)");
+    VPK_REQUIRE(cin > 0 && in[0] && in[1] && in[2] && out[0] && out[1] && out[2] && out[3], "convlstm backward: null argument");
+    const size_t px = static_cast<size_t>(B) * h * w;
+    const int cio = cin + ch;
+    void* xb = buf("bw_x", px * cin * esize());
+    void* hi = buf("bw_h", px * ch * esize());
+    float* x32 = dtype == DT_F32 ? static_cast<float*>(xb) : static_cast<float*>(buf("bw_x32", px * cin * 4));
+    float* h32 = dtype == DT_F32 ? static_cast<float*>(hi) : static_cast<float*>(buf("bw_h32", px * ch * 4));
+    float* cb = static_cast<float*>(buf("bw_c", px * ch * 4));
+    float* gh = in[3] ? static_cast<float*>(buf("bw_dh", px * ch * 4)) : nullptr;
+    float* gc = in[4] ? static_cast<float*>(buf("bw_dc", px * ch * 4)) : nullptr;
+    float* z = static_cast<float*>(buf("bw_z", px * 4 * ch * 4));
+    float* dz = static_cast<float*>(buf("bw_dz", px * 4 * ch * 4));
+    void* dza = dtype == DT_F32 ? static_cast<void*>(dz) : buf("bw_dz_act", px * 4 * ch * esize());
+    float* dci = static_cast<float*>(buf("bw_dc_in", px * ch * 4));
+    float* dxo = static_cast<float*>(buf("bw_dx", px * cin * 4));
+    float* dho = static_cast<float*>(buf("bw_dh_in", px * ch * 4));
+    if (bw_batch != B) {
+      bw_convs.clear();
+      if (wx_t.empty()) {      // dgrad weights: the x / h input-channel slices of W, kept in W's own [4C][.][k][k] layout,
+        const size_t kk = static_cast<size_t>(k) * k;      // which IS ConvTranspose2d's [Cin_t = 4C][Cout_t][k][k]
+        wx_t.resize(static_cast<size_t>(4) * ch * cin * kk);
+        wh_t.resize(static_cast<size_t>(4) * ch * ch * kk);
+        for (int o = 0; o < 4 * ch; ++o) {
+          std::copy(hw.begin() + (static_cast<size_t>(o) * cio) * kk, hw.begin() + (static_cast<size_t>(o) * cio + cin) * kk,
+                    wx_t.begin() + static_cast<size_t>(o) * cin * kk);
+          std::copy(hw.begin() + (static_cast<size_t>(o) * cio + cin) * kk, hw.begin() + (static_cast<size_t>(o) * cio + cio) * kk,
+                    wh_t.begin() + static_cast<size_t>(o) * ch * kk);
+        }
+      }
+      int oh, ow;
+      {   // z = conv(cat(x, h)) + b, reference row order (i | f | o | g), dense fp32
+        ConvSpec sp;
+        sp.name = "cell.bw.z";
+        sp.B = B;
+        sp.G = 1;
+        sp.C = 4 * ch;
+        WeightRef wr;
+        wr.w = hw.data();
+        wr.O = 4 * ch;
+        wr.I = cio;
+        wr.KH = wr.KW = k;
+        sp.wrefs.push_back(wr);
+        if (!hb.empty()) {
+          BiasRef br;
+          br.b = hb.data();
+          sp.biases.push_back(br);
+        }
+        lower_conv(sp, k, 1, k / 2, {ConvInput{make_view(xb, h, w, cin), 0, 0}, ConvInput{make_view(hi, h, w, ch), 0, cin}}, h, w,
+                   esize(), &oh, &ow);
+        EpiParams& e = sp.phases[0].epi;
+        e.kind = EPI_BIAS_ACT;
+        e.act = ACT_NONE;
+        e.out_f32 = 1;
+        dense_out(e, z, h, w, 4 * ch);
+        for (BuiltConv& bc : build_conv(sp, dtype, backend, store, cache, s, num_sms, false)) bw_convs.push_back(bc);
+      }
+      n_z = static_cast<int>(bw_convs.size());
+      auto dgrad = [&](const char* name, const std::vector<float>& wt, int co, float* dst) {
+        DeconvArgs a{std::string("cell.bw.") + name, B, h, w, 4 * ch, co, k, 1, k / 2, 0, dza, wt.data(), nullptr, ACT_NONE, dst};
+        a.out_f32 = true;
+        for (BuiltConv& bc : build_conv(deconv_spec(a, act(), &oh, &ow), dtype, backend, store, cache, s, num_sms, false))
+          bw_convs.push_back(bc);
+      };
+      dgrad("dx", wx_t, cin, dxo);
+      dgrad("dh", wh_t, ch, dho);
+      finish_build(s);
+      bw_batch = B;
+    }
+    to_nhwc(in[0], xb, dtype, B, cin, h, w, s);
+    to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
+    if (dtype != DT_F32) {
+      to_nhwc(in[0], x32, DT_F32, B, cin, h, w, s);
+      to_nhwc(in[1], h32, DT_F32, B, ch, h, w, s);
+    }
+    to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
+    if (gh) to_nhwc(in[3], gh, DT_F32, B, ch, h, w, s);
+    if (gc) to_nhwc(in[4], gc, DT_F32, B, ch, h, w, s);
+    for (int i = 0; i < n_z; ++i) run(bw_convs[i], s);
+    launch_lstm_gate_backward(z, cb, gh, gc, dz, dtype == DT_F32 ? nullptr : dza, dtype, dci, static_cast<long long>(px), ch, num_sms, s);
+    for (size_t i = n_z; i < bw_convs.size(); ++i) run(bw_convs[i], s);
+    launch_nhwc_to_nchw(dxo, DT_F32, out[0], B, cin, h, w, num_sms, s);
+    launch_nhwc_to_nchw(dho, DT_F32, out[1], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(dci, DT_F32, out[2], B, ch, h, w, num_sms, s);
+    launch_conv_wgrad(x32, dz, out[3], B, h, w, cin, 4 * ch, k, cio, 0, s);
+    launch_conv_wgrad(h32, dz, out[3], B, h, w, ch, 4 * ch, k, cio, cin, s);
+    if (out[4]) launch_bias_grad(dz, out[4], static_cast<long long>(px), 4 * ch, s);
+  }
+
  private:
   int cin, ch, h, w, k;
   bool ifog;
   int built_variant = -1;
   std::vector<float> hw, hb;
+  std::vector<float> wx_t, wh_t;
+  std::vector<BuiltConv> bw_convs;
+  int bw_batch = -1, n_z = 0;
 };
 
 // ------------------------------------------------------------------------------------------------------------------

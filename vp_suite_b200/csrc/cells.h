@@ -11,6 +11,11 @@ class Cell {
   virtual void step(int batch, const float* const* in, float* const* out, cudaStream_t stream) = 0;
   // ST-LSTM only: LayerNorm affine parameters (gamma, beta) x (conv_x, conv_h, conv_m, conv_o), host, [k*C, H, W]
   virtual void set_layer_norm(const float* const* params) { VPK_THROW(1, "this cell kind has no LayerNorm variant"); }
+  // ConvLSTM cell (ndrplz form) only: gradients of one step.  in: x, h, c, dh_out, dc_out (either gradient may be null);
+  // out: dx, dh, dc [b, ., h, w] and dw [4ch, cin + ch, k, k], db [4ch] (all device fp32)
+  virtual void backward(int batch, const float* const* in, float* const* out, cudaStream_t stream) {
+    VPK_THROW(1, "this cell kind has no backward pass");
+  }
   // PhyCell only: the two 1x1 action convs of the action-conditional cell (host; [ch, ch + a, 1, 1] + bias each)
   virtual void set_action_convs(int action_size, const float* fw, const float* fb, const float* hw, const float* hb) {
     VPK_THROW(1, "this cell kind has no action-conditional variant");

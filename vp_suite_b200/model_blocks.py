@@ -83,8 +83,36 @@ class _NativeCell:
         return C.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
 
 
+class _ConvLSTMCellFunction(torch.autograd.Function):
+    """One ConvLSTMCell step with a native backward (vpk_convlstm_cell_backward): the first differentiable entry of the
+    drop-in.  Saves the step's inputs; the backward recomputes the gates in the library."""
+
+    @staticmethod
+    def forward(ctx, module, x, h, c, weight, bias):
+        ctx.module = module
+        ctx.save_for_backward(x, h, c)
+        return module._native_step(x, h, c)
+
+    @staticmethod
+    def backward(ctx, dh_out, dc_out):
+        module = ctx.module
+        x, h, c = ctx.saved_tensors
+        cell = module._cell_handle(x.device)
+        dx, dh, dc = torch.empty_like(x), torch.empty_like(h), torch.empty_like(c)
+        dw = torch.empty_like(module.conv.weight, dtype=torch.float32)
+        db = torch.empty_like(module.conv.bias, dtype=torch.float32) if module.conv.bias is not None else None
+        gh = None if dh_out is None else module._dev(dh_out)
+        gc = None if dc_out is None else module._dev(dc_out)
+        module._step(x.device, N.lib().vpk_convlstm_cell_backward, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(gh),
+                     N.ptr(gc), N.ptr(dx), N.ptr(dh), N.ptr(dc), N.ptr(dw), N.ptr(db), module._stream(x))
+        return None, dx, dh, dc, dw, db
+
+
 class ConvLSTMCell(_NativeCell, nn.Module):
-    """conv_lstm_ndrplz.py:7-48: gate conv over cat(x, h), split order (i, f, o, g), no peepholes."""
+    """conv_lstm_ndrplz.py:7-48: gate conv over cat(x, h), split order (i, f, o, g), no peepholes.  Differentiable: when
+    gradients are enabled and any input or parameter requires them, the step runs through an autograd.Function whose
+    backward is libvpk's (input, state, weight and bias gradients), so BPTT over a stack / sequence of these cells composes
+    as with the reference cell."""
 
     def __init__(self, input_dim, hidden_dim, kernel_size, bias):
         super().__init__()
@@ -106,9 +134,7 @@ class ConvLSTMCell(_NativeCell, nn.Module):
                                                  N.ptr(wt), N.ptr(b), C.byref(cell)))
         return cell
 
-    def forward(self, input_tensor, cur_state):
-        h_cur, c_cur = cur_state
-        x, h, c = self._dev(input_tensor), self._dev(h_cur), self._dev(c_cur)
+    def _native_step(self, x, h, c):
         if self._hw != tuple(x.shape[-2:]):
             self._hw = tuple(x.shape[-2:])
             self._cell_release()
@@ -117,6 +143,18 @@ class ConvLSTMCell(_NativeCell, nn.Module):
         self._step(x.device, N.lib().vpk_convlstm_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), None, None,
                    None, N.ptr(h_next), N.ptr(c_next), self._stream(x))
         return h_next, c_next
+
+    def forward(self, input_tensor, cur_state):
+        h_cur, c_cur = cur_state
+        needs_grad = torch.is_grad_enabled() and (
+            any(t.requires_grad for t in (input_tensor, h_cur, c_cur)) or any(p.requires_grad for p in self.parameters()))
+        if needs_grad:
+            for t in (input_tensor, h_cur, c_cur):
+                if not t.is_cuda:
+                    raise N.NativeError("vp_suite_b200 blocks run on CUDA tensors only (there is no CPU path)")
+            x, h, c = (t.to(torch.float32).contiguous() for t in (input_tensor, h_cur, c_cur))
+            return _ConvLSTMCellFunction.apply(self, x, h, c, self.conv.weight, self.conv.bias)
+        return self._native_step(self._dev(input_tensor), self._dev(h_cur), self._dev(c_cur))
 
     def init_hidden(self, batch_size, image_size):                       # conv_lstm_ndrplz.py:45-48
         height, width = image_size
