@@ -49,6 +49,8 @@ typedef struct vpk_model vpk_model;
 #define VPK_MODEL_PREDRNN_PP 1      /* PredRNN_V2       models/predrnn_v2.py:11-230 (non action-conditional)    */
 #define VPK_MODEL_PHY 2             /* PhyDNet          models/phydnet.py:12-137   (non action-conditional)     */
 #define VPK_MODEL_CONVLSTM_BRANCH 3 /* DCGANEncoder->EncoderSplit->SingleStepConvLSTM->DecoderSplit->DCGANDecoder */
+#define VPK_MODEL_ST_PHY 4          /* STPhy            models/st_phy.py:16-181    (non action-conditional); uses num_layers,
+                                       num_hidden[0] = st_cell_channels, phycell_channels, phycell_kernel_size          */
 
 /* Hyper-parameters.  Field names follow the reference's class attributes. Unused fields are ignored per kind. */
 typedef struct vpk_model_desc {

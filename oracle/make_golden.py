@@ -242,7 +242,25 @@ def run_models_ac(manifest):
         print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
 
 
-INCREMENTAL = {"blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac}
+def run_stphy(manifest):
+    """ST-Phy (models/st_phy.py), non action-conditional, eval -> stphy_3x64.npz."""
+    classes = ref_shim.load_reference()
+    name, img, b, t, p, wseed, xseed, gain = "stphy_3x64", (3, 64, 64), 2, 3, 3, 35, 205, 1.5
+    torch.manual_seed(0)
+    m = classes["st-phy"]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+    shp = shapes_of(m)
+    m.load_state_dict(synth_state_dict(shp, wseed, gain))
+    x = synth_frames(b, t, *img, seed=xseed)
+    with torch.no_grad():
+        pred, aux = m(x, pred_frames=p)
+    assert aux is None
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), pred=pred.numpy())
+    manifest["models"][name] = dict(key="st-phy", img_shape=list(img), batch=b, context=t, pred=p, wseed=wseed, xseed=xseed,
+                                    gain=gain, shapes=shp, pred_std=float(pred.std()), pred_mean=float(pred.mean()))
+    print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
+
+
+INCREMENTAL = {"blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac, "stphy": run_stphy}
 
 
 def main():
@@ -268,6 +286,7 @@ def main():
     run_blocks_ac(manifest)
     run_measures(manifest)
     run_models_ac(manifest)
+    run_stphy(manifest)
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

@@ -291,9 +291,71 @@ def convlstm_branch_forward(sd, x, pred_frames, cfg=None):
     return torch.stack(outs, dim=1), None
 
 
+# --------------------------------------------------------------------------------------------------
+# st-phy  (STPhy, non action-conditional, eval)          vp_suite/models/st_phy.py:90-181
+# --------------------------------------------------------------------------------------------------
+STPHY_DEFAULTS = dict(num_layers=3, phycell_channels=49, phycell_kernel_size=(7, 7), st_cell_channels=64)
+
+
+def autoencoder_encode(x, sd, prefix="autoencoder.encoder."):
+    """model_blocks/enc.py:64-69: three valid (unpadded) convs with ReLU -- k5 s2, k3 s2, k3 s1 -- then an L2 normalisation
+    along the LAST axis (width), eps 1e-8."""
+    x = F.relu(F.conv2d(x, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"], stride=2))
+    x = F.relu(F.conv2d(x, sd[prefix + "conv2.weight"], sd[prefix + "conv2.bias"], stride=2))
+    x = F.relu(F.conv2d(x, sd[prefix + "mean_layer.weight"], sd[prefix + "mean_layer.bias"]))
+    return F.normalize(x, p=2, dim=-1, eps=1e-8)
+
+
+def autoencoder_decode(z, sd, out_hw, prefix="autoencoder.decoder."):
+    """model_blocks/enc.py:93-98: 1x1 conv, two k6 s2 transposed convs (ReLU after each), a k5 s1 transposed conv; the final
+    torchvision Resize is the identity when the size already matches (64 x 64 images), which is the case restated here."""
+    x = F.relu(F.conv2d(z, sd[prefix + "fc1.weight"], sd[prefix + "fc1.bias"]))
+    x = F.relu(F.conv_transpose2d(x, sd[prefix + "conv1.weight"], sd[prefix + "conv1.bias"], stride=2))
+    x = F.relu(F.conv_transpose2d(x, sd[prefix + "conv2.weight"], sd[prefix + "conv2.bias"], stride=2))
+    x = F.conv_transpose2d(x, sd[prefix + "conv3.weight"], sd[prefix + "conv3.bias"])
+    if tuple(x.shape[-2:]) != tuple(out_hw):
+        raise ValueError(f"decoder output {tuple(x.shape[-2:])} != image size {tuple(out_hw)}: needs the reference's Resize")
+    return x
+
+
+def stphy_forward(sd, x, pred_frames, cfg=None, actions=None):
+    """STPhy.forward in eval mode, action_conditional=False (models/st_phy.py:90-181).  Per step: the encoded frame (context
+    steps) or the previous x_gen feeds EVERY layer (``next_input`` is not updated inside the layer loop, :139-158); layer i
+    runs its PhyCell_Cell on (next_input, phy_h[i]) and its LayerNorm ST-LSTM cell on (next_input, h[i], c[i], shared
+    st_memory), and merges them with a 1x1 conv over cat[st_h, phy_h] (:158); only the last layer's merge survives as x_gen.
+    Frames are decoded from t = context - 1 on (:160-162).  Losses are training-only: returns (frames, None)."""
+    cfg = {**STPHY_DEFAULTS, **(cfg or {})}
+    if "action_inflate.weight" in sd:
+        raise NotImplementedError("action-conditional st-phy is not restated")
+    L, Cs = cfg["num_layers"], cfg["st_cell_channels"]
+    b, ctx = x.shape[:2]
+    enc0 = autoencoder_encode(x[:, 0], sd)
+    eh, ew = enc0.shape[-2:]
+    phy_h = [torch.zeros(b, Cs, eh, ew) for _ in range(L)]
+    st_h = [torch.zeros(b, Cs, eh, ew) for _ in range(L)]
+    st_c = [torch.zeros(b, Cs, eh, ew) for _ in range(L)]
+    memory = torch.zeros(b, Cs, eh, ew)
+    x_gen, outs = None, []
+    for t in range(ctx + pred_frames - 1):
+        nxt = autoencoder_encode(x[:, t], sd) if t < ctx else x_gen
+        for i in range(L):
+            phy_h[i] = B.phycell_step(nxt, phy_h[i], B._sub(sd, f"phycell_list.{i}."))
+            pre = f"st_cell_list.{i}."
+            ln = {k: (sd[f"{pre}conv_{k}.1.weight"], sd[f"{pre}conv_{k}.1.bias"]) for k in "xhmo"}
+            st_h[i], st_c[i], memory, _, _ = B.stlstm_step(
+                nxt, st_h[i], st_c[i], memory, sd[pre + "conv_x.0.weight"], sd[pre + "conv_h.0.weight"],
+                sd[pre + "conv_m.0.weight"], sd[pre + "conv_o.0.weight"], sd[pre + "conv_last.weight"], ln=ln)
+            x_gen = F.conv2d(torch.cat([st_h[i], phy_h[i]], dim=1), sd[f"hidden_conv_list.{i}.weight"],
+                             sd.get(f"hidden_conv_list.{i}.bias"))
+        if t >= ctx - 1:
+            outs.append(autoencoder_decode(x_gen, sd, x.shape[-2:]))
+    return torch.stack(outs, dim=1), None
+
+
 FORWARDS = {
     "convlstm-shi": ef_convlstm_forward,
     "predrnn-pp": predrnn_v2_forward,
     "phy": phydnet_forward,
     "convlstm-branch": convlstm_branch_forward,
+    "st-phy": stphy_forward,
 }

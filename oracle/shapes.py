@@ -3,7 +3,7 @@
 Lets the CPU baseline build weights for any image size without importing the reference or the product package.
 Checked against the reference's own listings in tests/golden/manifest.json (tests/test_oracle_golden.py).
 """
-from .models import EF_DEFAULTS, PREDRNN_DEFAULTS, PHYDNET_DEFAULTS
+from .models import EF_DEFAULTS, PREDRNN_DEFAULTS, PHYDNET_DEFAULTS, STPHY_DEFAULTS
 
 
 def _conv_out(v, k, s, p):
@@ -137,5 +137,42 @@ def phydnet_shapes(img_shape, cfg=None):
     return out
 
 
-SHAPES = {"convlstm-shi": ef_shapes, "predrnn-pp": predrnn_shapes, "phy": phydnet_shapes,
+def stphy_shapes(img_shape, cfg=None):
+    """models/st_phy.py:38-83 (non action-conditional), model_blocks/enc.py:14-98."""
+    cfg = {**STPHY_DEFAULTS, **(cfg or {})}
+    c, h, w = img_shape
+    L, C, hid, kp = cfg["num_layers"], cfg["st_cell_channels"], cfg["phycell_channels"], cfg["phycell_kernel_size"][0]
+    eh = ((h - 5) // 2 + 1 - 3) // 2 + 1 - 2
+    ew = ((w - 5) // 2 + 1 - 3) // 2 + 1 - 2
+    out = {}
+    for name, shp in (("encoder.conv1", (32, c, 5, 5)), ("encoder.conv2", (64, 32, 3, 3)), ("encoder.mean_layer", (C, 64, 3, 3)),
+                      ("decoder.fc1", (C, C, 1, 1)), ("decoder.conv1", (C, 64, 6, 6)), ("decoder.conv2", (64, 32, 6, 6)),
+                      ("decoder.conv3", (32, c, 5, 5))):
+        out[f"autoencoder.{name}.weight"] = shp
+        out[f"autoencoder.{name}.bias"] = (shp[1],) if "decoder.conv" in name else (shp[0],)
+    for i in range(L):
+        for nm, mult, ci in (("x", 7, C), ("h", 4, C), ("m", 3, C), ("o", 1, 2 * C)):
+            out[f"st_cell_list.{i}.conv_{nm}.0.weight"] = (mult * C, ci, 5, 5)
+            out[f"st_cell_list.{i}.conv_{nm}.1.weight"] = (mult * C, eh, ew)
+            out[f"st_cell_list.{i}.conv_{nm}.1.bias"] = (mult * C, eh, ew)
+        out[f"st_cell_list.{i}.conv_last.weight"] = (C, 2 * C, 1, 1)
+    for i in range(L):
+        pre = f"phycell_list.{i}."
+        out[pre + "F.conv1.weight"] = (hid, C, kp, kp)
+        out[pre + "F.conv1.bias"] = (hid,)
+        out[pre + "F.bn1.weight"] = (hid,)
+        out[pre + "F.bn1.bias"] = (hid,)
+        out[pre + "F.conv2.weight"] = (C, hid, 1, 1)
+        out[pre + "F.conv2.bias"] = (C,)
+        out[pre + "convgate.weight"] = (C, 2 * C, 3, 3)
+        out[pre + "convgate.bias"] = (C,)
+    for i in range(L):
+        out[f"hidden_conv_list.{i}.weight"] = (C, 2 * C, 1, 1)
+        if i < L - 1:
+            out[f"hidden_conv_list.{i}.bias"] = (C,)
+    out["adapter.weight"] = (C, C, 1, 1)
+    return out
+
+
+SHAPES = {"st-phy": stphy_shapes, "convlstm-shi": ef_shapes, "predrnn-pp": predrnn_shapes, "phy": phydnet_shapes,
           "convlstm-branch": phydnet_shapes}

@@ -923,6 +923,42 @@ __global__ void add_to_act_kernel(const TX* __restrict__ x, const float* __restr
     out[i] = to_act<T>(from_act(x[i]) + (y != nullptr ? y[i] : 0.f));
 }
 
+// fp32 [B][H][W][C] -> typed copies (hi / lo of type T1, cell of type T2, fp32), optionally L2-normalised along W first
+// (F.normalize(x, p=2, dim=-1, eps): x / max(||x||_2 over W, eps), ST-Phy's encoder, model_blocks/enc.py:69).
+// One thread = one (b, y, c) row of W values.
+template <typename T1, typename T2, bool NORM>
+__global__ void fanout_kernel(const float* __restrict__ in, T1* __restrict__ hi, T1* __restrict__ lo, T2* __restrict__ cell,
+                              float* __restrict__ f32, long long rows, int W, int C, float eps) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  for (long long r = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; r < rows;
+       r += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c = static_cast<int>(r % C);
+    const long long by = r / C;
+    const long long base = by * W * C + c;
+    float scale = 1.f;
+    if (NORM) {
+      float ss = 0.f;
+      for (int x = 0; x < W; ++x) {
+        const float v = in[base + static_cast<long long>(x) * C];
+        ss = fmaf(v, v, ss);
+      }
+      scale = 1.f / fmaxf(sqrtf(ss), eps);
+    }
+    for (int x = 0; x < W; ++x) {
+      const long long i = base + static_cast<long long>(x) * C;
+      const float v = in[i] * scale;
+      if (hi != nullptr) {
+        const T1 h = to_act<T1>(v);
+        hi[i] = h;
+        if (lo != nullptr) lo[i] = to_act<T1>(v - from_act(h));
+      }
+      if (cell != nullptr) cell[i] = to_act<T2>(v);
+      if (f32 != nullptr) f32[i] = v;
+    }
+  }
+}
+
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
@@ -1134,6 +1170,24 @@ void launch_inflate_actions(const float* actions, long long bstride, int a, void
   if (dtype == DT_F32) launch_pdl(inflate_actions_kernel<float>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<float*>(out), B, T, HW, a_pad);
   else if (dtype == DT_F16) launch_pdl(inflate_actions_kernel<__half>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<__half*>(out), B, T, HW, a_pad);
   else launch_pdl(inflate_actions_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<__nv_bfloat16*>(out), B, T, HW, a_pad);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_fanout(const float* in, void* hi, void* lo, int hi_dtype, void* cell, int cell_dtype, float* f32, int B, int H,
+                   int W, int C, bool norm_w, float eps, int num_sms, cudaStream_t stream) {
+  const long long rows = static_cast<long long>(B) * H * C;
+  const int g = grid_for(rows, 256, num_sms);
+#define VPK_FAN(T1, T2)                                                                                                  \
+  do {                                                                                                                  \
+    if (norm_w) launch_pdl(fanout_kernel<T1, T2, true>, dim3(g), dim3(256), 0, stream, in, static_cast<T1*>(hi), static_cast<T1*>(lo), static_cast<T2*>(cell), f32, rows, W, C, eps); \
+    else launch_pdl(fanout_kernel<T1, T2, false>, dim3(g), dim3(256), 0, stream, in, static_cast<T1*>(hi), static_cast<T1*>(lo), static_cast<T2*>(cell), f32, rows, W, C, eps); \
+  } while (0)
+  if (hi_dtype == DT_F16 && cell_dtype == DT_BF16) VPK_FAN(__half, __nv_bfloat16);
+  else if (hi_dtype == DT_F16 && cell_dtype == DT_F16) VPK_FAN(__half, __half);
+  else if (hi_dtype == DT_BF16 && cell_dtype == DT_BF16) VPK_FAN(__nv_bfloat16, __nv_bfloat16);
+  else if (hi_dtype == DT_F32 && cell_dtype == DT_F32) VPK_FAN(float, float);
+  else VPK_THROW(1, "fanout: unsupported dtype combination");
+#undef VPK_FAN
   VPK_CUDA(cudaGetLastError());
 }
 

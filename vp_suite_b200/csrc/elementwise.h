@@ -76,6 +76,10 @@ void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num
 // out (activation type) [T][B][HW][a_pad], channels a..a_pad-1 zero (the action vector inflated to the frame size)
 void launch_inflate_actions(const float* actions, long long bstride, int a, void* out, int dtype, int B, int T, int HW,
                             int a_pad, int num_sms, cudaStream_t stream);
+// in fp32 NHWC [B][H][W][C] -> typed copies: hi / lo (split pair of hi_dtype; either may be nullptr), cell (cell_dtype,
+// nullable), f32 (nullable; may alias `in` only when norm_w is false); norm_w: L2-normalise along W first (eps clamp)
+void launch_fanout(const float* in, void* hi, void* lo, int hi_dtype, void* cell, int cell_dtype, float* f32, int B, int H,
+                   int W, int C, bool norm_w, float eps, int num_sms, cudaStream_t stream);
 // out = x + y (y fp32 or nullptr: a plain conversion), x of x_dtype, out of out_dtype
 void launch_add_to_act(const void* x, int x_dtype, const float* y, void* out, int out_dtype, long long n, int num_sms,
                        cudaStream_t stream);

@@ -150,5 +150,6 @@ class Model {
 Model* make_ef_convlstm(const vpk_model_desc& d);
 Model* make_predrnn(const vpk_model_desc& d);
 Model* make_phydnet(const vpk_model_desc& d, bool branch_only);
+Model* make_stphy(const vpk_model_desc& d);
 
 }  // namespace vpk

@@ -13,14 +13,15 @@
 #include "model.h"
 #include "stlstm.h"
 #include "stlstm_ln.h"
+#include "stlstm_model.h"
 
 namespace vpk {
 
 namespace {
 
-class PredRnnV2 : public Model {
+class PredRnnV2 : public StLstmModelBase {
  public:
-  explicit PredRnnV2(const vpk_model_desc& d) : Model(d) {
+  explicit PredRnnV2(const vpk_model_desc& d) : StLstmModelBase(d) {
     VPK_REQUIRE(d.img_c > 0 && d.img_h > 0 && d.img_w > 0, "bad img_shape");
     p = d.patch_size;
     L = d.num_layers;
@@ -390,115 +391,6 @@ class PredRnnV2 : public Model {
       prog.post.push_back(std::move(post));
     }
   }
-
-  // statistics slots per sample the tcgen05 epilogue of a G = 1 conv with `co` output channels writes (epilogue slot rule
-  // in common.h: ((tile in image) * n_tiles + N tile) * 8 + quadrant * 2 + half)
-  int ln_slots(int co) const { return ((rh + 15) / 16) * ((rw + 7) / 8) * conv_n_tiles(co, 1) * 8; }
-
-  // LayerNorm affine of `key` ([kC, H, W] in the reference) repacked to the NHWC order of the raw conv outputs
-  const float* ln_param(const std::string& key, int kc, cudaStream_t stream) {
-    const float* src = hp(key);
-    const int HW = rh * rw;
-    std::vector<float> v(static_cast<size_t>(kc) * HW);
-    for (int ch = 0; ch < kc; ++ch)
-      for (int q = 0; q < HW; ++q) v[static_cast<size_t>(q) * kc + ch] = src[static_cast<size_t>(ch) * HW + q];
-    return dev_f32(key + ".nhwc", v, stream);
-  }
-
-  // low parts of the split activations of one LayerNorm cell step (three-product mode), all nullptr otherwise
-  struct LnLo {
-    const void* x = nullptr;
-    const void* h_in = nullptr;
-    void* h_out = nullptr;
-    void* m_act = nullptr;
-  };
-
-  // One ST-LSTM step with layer_norm=True (stlstm_ln.h): 5 raw convs, 2 statistics launches, 2 fused gate kernels.
-  void add_ln_cell(Program& prog, const std::string& pre, int B, int cin, const void* x, const void* h_in, void* h_out,
-                   float* c, float* m, float* opart, void* mem, void* m_act, void* dc, void* dm, float* xraw, float* hraw,
-                   float* mraw, float* oraw, float* lraw, float* part, const ActInfo& act, bool measure,
-                   cudaStream_t stream, int products, const LnLo& lo) {
-    int oh, ow;
-    // tcgen05 path: the conv epilogues leave the per-sample (sum, sum of squares) partials themselves (one slot per
-    // warp, tile and N tile); otherwise a separate statistics launch reads the raw tensors once more
-    const char* halo_env = getenv("VPK_TC_HALO");
-    const bool fuse_stats = act.dtype != DT_F32 && backend == 0 && getenv("VPK_NO_FUSED_LN_STATS") == nullptr &&
-                            (halo_env == nullptr || atoi(halo_env) != 0);
-    auto slots_of = [&](int co) { return ln_slots(co); };
-    // 16-bit mode: conv_x / conv_h / conv_m run `products` fp16 products per tap (see build(): 2 = split weights over the
-    // same activation tile, 3 = split weights and activations), counted once in the algorithmic FLOPs.
-    auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& wkey, float* out,
-                        float* stat, int nslots, const void* in_lo = nullptr, bool precise = false) {
-      ConvArgs a{pre + name, B, rh, rw, ci, co, kk, 1, kk / 2, in, hp(pre + wkey), nullptr, ACT_NONE, out};
-      a.out_f32_dense = true;
-      if (precise && products == 2) a.w_split = true;
-      if (precise && products == 3) {
-        a.split = true;
-        a.x_lo = in_lo;
-        a.split_uncounted = true;
-      }
-      ConvSpec sp = conv_spec(a, act, &oh, &ow);
-      sp.is_gate_gemm = true;
-      if (stat != nullptr) {
-        EpiParams& e = sp.phases[0].epi;
-        e.gn_sums = stat;
-        e.gn_group_size = -1;
-        e.gn_slot0 = 0;
-        e.gn_nslots = nslots;
-      }
-      add_conv(prog, sp, measure, stream, act.dtype);
-    };
-    // statistics regions inside `part`: X, H, M (and O reuses X's)
-    const int nsx = fuse_stats ? slots_of(7 * C) : kLnSlices, nsh = fuse_stats ? slots_of(4 * C) : kLnSlices,
-              nsm = fuse_stats ? slots_of(3 * C) : kLnSlices, nso = fuse_stats ? slots_of(C) : kLnSlices;
-    float* px_ = part;
-    float* ph_ = px_ + static_cast<size_t>(B) * nsx * 2;
-    float* pm_ = ph_ + static_cast<size_t>(B) * nsh * 2;
-    VPK_REQUIRE(static_cast<size_t>(B) * (static_cast<size_t>(nsx) + nsh + nsm) * 2 <= lnpart_floats && nso <= nsx,
-                "LayerNorm statistics regions exceed their buffer");
-    raw_conv("conv_x.ln.", x, cin, 7 * C, k, "conv_x.0.weight", xraw, fuse_stats ? px_ : nullptr, nsx, lo.x, true);
-    raw_conv("conv_h.ln.", h_in, C, 4 * C, k, "conv_h.0.weight", hraw, fuse_stats ? ph_ : nullptr, nsh, lo.h_in, true);
-    raw_conv("conv_m.ln.", m_act, C, 3 * C, k, "conv_m.0.weight", mraw, fuse_stats ? pm_ : nullptr, nsm, lo.m_act, true);
-    const int HW = rh * rw, CC = C, ns = num_sms, dt = act.dtype;
-    if (!measure) {
-      if (!fuse_stats) {
-        LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
-        Op op;
-        op.name = pre + "ln_stats_xhm";
-        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(sa, s); };
-        prog.body.push_back(std::move(op));
-      }
-      StLnGatesArgs ga{xraw, hraw, mraw, {px_, ph_, pm_}, {nsx, nsh, nsm},
-                       ln_param(pre + "conv_x.1.weight", 7 * C, stream), ln_param(pre + "conv_x.1.bias", 7 * C, stream),
-                       ln_param(pre + "conv_h.1.weight", 4 * C, stream), ln_param(pre + "conv_h.1.bias", 4 * C, stream),
-                       ln_param(pre + "conv_m.1.weight", 3 * C, stream), ln_param(pre + "conv_m.1.bias", 3 * C, stream),
-                       c, m, mem, m_act, dc, dm, opart, B, HW, CC, dt, 1.0f};
-      ga.m_act_lo = lo.m_act;
-      Op og;
-      og.name = pre + "ln_gates";
-      og.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_gates(ga, ns, s); };
-      prog.body.push_back(std::move(og));
-    }
-    raw_conv("conv_o.ln.", mem, 2 * C, C, k, "conv_o.0.weight", oraw, fuse_stats ? px_ : nullptr, nso);
-    raw_conv("conv_last.ln.", mem, 2 * C, C, 1, "conv_last.weight", lraw, nullptr, 0);
-    if (!measure) {
-      if (!fuse_stats) {
-        LnStatsArgs so{{oraw, nullptr, nullptr}, {1ll * C * HW, 0, 0}, 1, B, part};
-        Op op;
-        op.name = pre + "ln_stats_o";
-        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(so, s); };
-        prog.body.push_back(std::move(op));
-      }
-      StLnOutArgs oa{oraw, lraw, px_, nso, ln_param(pre + "conv_o.1.weight", C, stream),
-                     ln_param(pre + "conv_o.1.bias", C, stream), opart, h_out, B, HW, CC, dt};
-      oa.h_lo = lo.h_out;
-      Op oo;
-      oo.name = pre + "ln_out";
-      oo.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_out(oa, ns, s); };
-      prog.body.push_back(std::move(oo));
-    }
-  }
-
 
   // ==================================================================================================================
   // action_conditional=True (predrnn_v2.py:65-90, 147-152, 178-221; cell: model_blocks/predrnn.py:86-169).
@@ -877,10 +769,8 @@ class PredRnnV2 : public Model {
   }
 
  private:
-  int p = 4, L = 3, k = 5, C = 128, cp = 16, hp_ = 16, wp_ = 16;
+  int p = 4, L = 3, cp = 16, hp_ = 16, wp_ = 16;
   bool ac = false;
-  int rh = 16, rw = 16;            // latent size of the cells (patch grid, or a quarter of it when action-conditional)
-  size_t lnpart_floats = 0;
   int call_terms = 1;
   double* d_loss = nullptr;
 };

@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(256) stlstm_ln_out_kernel(const StLnOutArgs a)
                                  sigmoid_f(p.z + o.z) * tanh_f(l.z), sigmoid_f(p.w + o.w) * tanh_f(l.w));
     st_act4<T>(static_cast<T*>(a.h) + pos * C + ch, h);
     if (a.h_lo != nullptr) st_act4<T>(static_cast<T*>(a.h_lo) + pos * C + ch, lo_part4<T>(h));
+    if (a.h32 != nullptr) *reinterpret_cast<float4*>(a.h32 + pos * C + ch) = h;
   }
 }
 

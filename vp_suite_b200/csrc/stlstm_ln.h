@@ -55,6 +55,7 @@ struct StLnOutArgs {
   int B, HW, C, dtype;
   void* h_lo = nullptr;                        // optional: low part of h' (h' - h), activation type [B*HW][C]
   int use_ln = 1;                              // 0: no LayerNorm on conv_o's output
+  float* h32 = nullptr;                        // optional fp32 copy of h' [B*HW][C]
 };
 void launch_stlstm_ln_out(const StLnOutArgs& a, int num_sms, cudaStream_t stream);
 

@@ -9,6 +9,7 @@ load unchanged:  ``ours.load_state_dict(reference_model.state_dict())``.
     PredRNN_V2       <- vp_suite/models/predrnn_v2.py:11-230                           (key "predrnn-pp")
     PhyDNet          <- vp_suite/models/phydnet.py:12-137                              (key "phy")
     ConvLSTMBranch   <- BASELINE config 2: PhyDNet's residual branch alone (our composition of reference blocks)
+    STPhy            <- vp_suite/models/st_phy.py:16-181                               (key "st-phy")
 """
 from collections import OrderedDict
 
@@ -466,9 +467,103 @@ class ConvLSTMBranch(PhyDNet):
     _KIND = N.VPK_MODEL_CONVLSTM_BRANCH
 
 
+class STPhy(NativeRollout, VPModel):
+    """models/st_phy.py:16-181: Autoencoder + per layer one PhyCell_Cell and one LayerNorm ST-LSTM cell merged by a 1x1 conv.
+    The native rollout covers the non action-conditional model in eval mode (losses are training-only there: ``forward``
+    returns ``(frames, None)``)."""
+    NAME = "ST-Phy"
+    CAN_HANDLE_ACTIONS = True
+
+    # hyper-parameters: st_phy.py:28-36
+    num_layers = 3
+    phycell_channels = 49
+    phycell_kernel_size = (7, 7)
+    st_cell_channels = 64
+    inflated_action_dim = 3
+    decoupling_loss_scale = 100.0
+    moment_loss_scale = 1.0
+    teacher_forcing_decay = 0.003
+
+    def __init__(self, device, **model_kwargs):
+        super().__init__(device, **model_kwargs)
+        self._native_init()
+        if self.action_conditional:
+            raise NotImplementedError("the native st-phy rollout covers the non action-conditional model")
+        C, c = self.st_cell_channels, self.img_c
+        self.dim_st_hidden = [C] * self.num_layers                              # st_phy.py:41-42
+        self.dim_phy_hidden = [self.phycell_channels] * self.num_layers
+        from .model_blocks import SpatioTemporalLSTMCell                       # (model_blocks imports this module)
+        self.recurrent_cell = SpatioTemporalLSTMCell                           # st_phy.py:46 (shows up in `config`)
+        # Autoencoder (model_blocks/enc.py:14-98): same construction order as the reference for same-seed init
+        self.autoencoder = _Params()
+        enc = _Params()
+        enc.conv1 = nn.Conv2d(c, 32, 5, 2)
+        enc.conv2 = nn.Conv2d(32, 64, 3, 2)
+        enc.mean_layer = nn.Conv2d(64, C, 3, 1)
+        dec = _Params()
+        dec.fc1 = nn.Conv2d(C, C, 1, 1)
+        dec.conv1 = nn.ConvTranspose2d(C, 64, 6, 2, 0)
+        dec.conv2 = nn.ConvTranspose2d(64, 32, 6, 2, 0)
+        dec.conv3 = nn.ConvTranspose2d(32, c, 5, 1, 0)
+        self.autoencoder.encoder, self.autoencoder.decoder = enc, dec
+        h1, w1 = (self.img_h - 5) // 2 + 1, (self.img_w - 5) // 2 + 1
+        self.enc_h, self.enc_w = (h1 - 3) // 2 + 1 - 2, (w1 - 3) // 2 + 1 - 2   # autoencoder.encoded_shape (st_phy.py:45)
+        if ((self.enc_h - 1) * 2 + 6 - 1) * 2 + 6 + 4 != self.img_h or ((self.enc_w - 1) * 2 + 6 - 1) * 2 + 6 + 4 != self.img_w:
+            raise AttributeError("image sizes whose decoder output needs the reference's Resize are not supported")
+        st_cells, phycells, hidden_convs = [], [], []
+        kp = self.phycell_kernel_size
+        for i in range(self.num_layers):                                        # st_phy.py:58-70
+            cell = _Params()
+            for name, (o, ci) in (("conv_x", (7 * C, C)), ("conv_h", (4 * C, C)), ("conv_m", (3 * C, C)), ("conv_o", (C, 2 * C))):
+                setattr(cell, name, nn.Sequential(nn.Conv2d(ci, o, 5, 1, 2, bias=False), nn.LayerNorm([o, self.enc_h, self.enc_w])))
+            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
+            st_cells.append(cell)
+            pc = _Params()
+            pc.F = nn.Sequential()
+            pc.F.add_module("conv1", nn.Conv2d(C, self.phycell_channels, kp, (1, 1), (kp[0] // 2, kp[1] // 2)))
+            pc.F.add_module("bn1", nn.GroupNorm(_gn_divisor(self.phycell_channels), self.phycell_channels))
+            pc.F.add_module("conv2", nn.Conv2d(self.phycell_channels, C, (1, 1)))
+            pc.convgate = nn.Conv2d(2 * C, C, (3, 3), padding=(1, 1))
+            phycells.append(pc)
+            hidden_convs.append(nn.Conv2d(2 * C, C, (1, 1), bias=(i < self.num_layers - 1)))
+        self.st_cell_list = nn.ModuleList(st_cells)
+        self.phycell_list = nn.ModuleList(phycells)
+        self.hidden_conv_list = nn.ModuleList(hidden_convs)
+        self.adapter = nn.Conv2d(C, C, 1, stride=1, padding=0, bias=False)
+        self.to(device)
+
+    def _native_desc(self):
+        d = N.ModelDesc()
+        d.kind = N.VPK_MODEL_ST_PHY
+        d.img_c, d.img_h, d.img_w = self.img_c, self.img_h, self.img_w
+        d.num_layers = self.num_layers
+        d.num_hidden[0] = int(self.st_cell_channels)
+        d.phycell_channels = self.phycell_channels
+        if self.phycell_kernel_size[0] != self.phycell_kernel_size[1]:
+            raise AttributeError("square kernels only")
+        d.phycell_kernel_size = self.phycell_kernel_size[0]
+        return d
+
+    def _native_key(self, key):
+        return key
+
+    def pred_1(self, x, **kwargs):
+        return self(x, pred_frames=1, **kwargs)[0].squeeze(dim=1)              # st_phy.py:87-88
+
+    def forward(self, x, pred_frames=1, **kwargs):
+        if kwargs.get("train", False):
+            raise NotImplementedError("the native rollout is inference-only")
+        b, t, c, h, w = x.shape
+        if (c, h, w) != (self.img_c, self.img_h, self.img_w):
+            raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        pred, _ = self._native_forward(x, int(pred_frames), t)
+        return pred, None                                                      # st_phy.py:176-181 (eval)
+
+
 MODEL_CLASSES = {
     "convlstm-shi": EF_ConvLSTM,
     "predrnn-pp": PredRNN_V2,
     "phy": PhyDNet,
     "convlstm-branch": ConvLSTMBranch,
+    "st-phy": STPhy,
 }
