@@ -49,6 +49,7 @@ typedef struct vpk_model vpk_model;
 #define VPK_MODEL_PREDRNN_PP 1      /* PredRNN_V2       models/predrnn_v2.py:11-230 (non action-conditional)    */
 #define VPK_MODEL_PHY 2             /* PhyDNet          models/phydnet.py:12-137   (non action-conditional)     */
 #define VPK_MODEL_CONVLSTM_BRANCH 3 /* DCGANEncoder->EncoderSplit->SingleStepConvLSTM->DecoderSplit->DCGANDecoder */
+#define VPK_MODEL_TRAJGRU 5         /* EF_TrajGRU       models/precipitation_nowcasting/ef_traj_gru.py:8-119                 */
 #define VPK_MODEL_ST_PHY 4          /* STPhy            models/st_phy.py:16-181    (non action-conditional); uses num_layers,
                                        num_hidden[0] = st_cell_channels, phycell_channels, phycell_kernel_size          */
 
@@ -82,6 +83,8 @@ typedef struct vpk_model_desc {
   int32_t action_conditional;
   int32_t action_size;
   int32_t residual_on_action_conv;   /* predrnn-pp (predrnn_v2.py:46, 213-218) */
+  /* trajgru (ef_traj_gru.py:47-61): flows per recurrent block; the i2h kernel sizes travel in enc_rnn_k / dec_rnn_k */
+  int32_t enc_rnn_L[3], dec_rnn_L[3];
 } vpk_model_desc;
 
 /* Replaces: MODEL_CLASSES[key](device, **model_kwargs)  (vp_suite/vpsuite.py:170; base_model.py:38-69). */

@@ -103,6 +103,56 @@ def stlstm_step(x, h, c, m, w_x, w_h, w_m, w_o, w_last, forget_bias=1.0, ln=None
 
 
 # --------------------------------------------------------------------------------------------------
+# TrajGRU                                        (vp_suite/model_blocks/traj_gru.py:134-214)
+# --------------------------------------------------------------------------------------------------
+def trajgru_warp(inp, flow):
+    """TrajGRU._warp (:150-166): bilinear sampling of ``inp`` at (x + flow_x, y + flow_y).  The reference normalises the
+    sampling grid with (W - 1) / (H - 1) but calls F.grid_sample with its default align_corners=False -- kept as is."""
+    b, c, h, w = inp.shape
+    xx = torch.arange(0, w).view(1, -1).repeat(h, 1).view(1, 1, h, w).repeat(b, 1, 1, 1)
+    yy = torch.arange(0, h).view(-1, 1).repeat(1, w).view(1, 1, h, w).repeat(b, 1, 1, 1)
+    vgrid = torch.cat((xx, yy), 1).float() + flow
+    vx = 2.0 * vgrid[:, 0] / max(w - 1, 1) - 1.0
+    vy = 2.0 * vgrid[:, 1] / max(h - 1, 1) - 1.0
+    return F.grid_sample(inp, torch.stack([vx, vy], dim=-1), mode="bilinear", padding_mode="zeros", align_corners=False)
+
+
+def trajgru_sequence(inputs, states, seq_len, p, act):
+    """TrajGRU.forward (:170-214) with zoneout 0.  ``p``: i2h, i2f_conv1, h2f_conv1, flows_conv, ret (.weight / .bias).
+    Per step: flows from leaky(i2f(x) + h2f(h)) (:137-147), L warps of h by -flow (:192-195), 1x1 ``ret`` over their concat
+    (:196-197), GRU gates (:198-206): r = sig(i2h_0 + h2h_0), u = sig(i2h_1 + h2h_1), m = act(i2h_2 + r * h2h_2),
+    h' = u * h + (1 - u) * m.  ``inputs`` None: no i2h / i2f terms (:181-182, 203-205)."""
+    C = p["ret.weight"].shape[0] // 3
+    if states is None:
+        i2h_pad = p["i2h.weight"].shape[-1] // 2
+        b, _, _, hh, ww = inputs.shape
+        states = torch.zeros(b, C, hh, ww)
+    h = states
+    outs = []
+    for t in range(seq_len):
+        f1 = F.conv2d(h, p["h2f_conv1.weight"], p["h2f_conv1.bias"], padding=2)
+        i2h = None
+        if inputs is not None:
+            x = inputs[:, t]
+            i2h = F.conv2d(x, p["i2h.weight"], p["i2h.bias"], padding=p["i2h.weight"].shape[-1] // 2)
+            f1 = F.conv2d(x, p["i2f_conv1.weight"], p["i2f_conv1.bias"], padding=2) + f1
+        flows = F.conv2d(act(f1), p["flows_conv.weight"], p["flows_conv.bias"], padding=2)
+        warped = torch.cat([trajgru_warp(h, -fl) for fl in torch.split(flows, 2, dim=1)], dim=1)
+        h2h = F.conv2d(warped, p["ret.weight"], p["ret.bias"])
+        a, bb, cc = torch.split(h2h, C, dim=1)
+        if i2h is not None:
+            ia, ib, ic = torch.split(i2h, C, dim=1)
+            r, u = torch.sigmoid(ia + a), torch.sigmoid(ib + bb)
+            m = act(ic + r * cc)
+        else:
+            r, u = torch.sigmoid(a), torch.sigmoid(bb)
+            m = act(r * cc)
+        h = u * h + (1 - u) * m
+        outs.append(h)
+    return torch.stack(outs, dim=1), h
+
+
+# --------------------------------------------------------------------------------------------------
 # Action-conditional ST-LSTM v2 cell            (vp_suite/model_blocks/predrnn.py:86-169)
 # --------------------------------------------------------------------------------------------------
 def stlstm_ac_step(x, h, c, m, a, sd, forget_bias=1.0):

@@ -260,7 +260,25 @@ def run_stphy(manifest):
     print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
 
 
-INCREMENTAL = {"blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac, "stphy": run_stphy}
+def run_trajgru(manifest):
+    """EF-TrajGRU (models/precipitation_nowcasting/ef_traj_gru.py), eval -> trajgru_1x64.npz, trajgru_3x32.npz."""
+    classes = ref_shim.load_reference()
+    for name, img, b, t, p, wseed, xseed, gain in (("trajgru_1x64", (1, 64, 64), 2, 3, 3, 36, 206, 2.0),
+                                                   ("trajgru_3x32", (3, 32, 32), 1, 2, 3, 37, 207, 2.0)):
+        torch.manual_seed(0)
+        m = classes["trajgru"]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0]).eval()
+        shp = shapes_of(m)
+        m.load_state_dict(synth_state_dict(shp, wseed, gain))
+        x = synth_frames(b, t, *img, seed=xseed)
+        with torch.no_grad():
+            pred, aux = m(x, pred_frames=p)
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), pred=pred.numpy())
+        manifest["models"][name] = dict(key="trajgru", img_shape=list(img), batch=b, context=t, pred=p, wseed=wseed,
+                                        xseed=xseed, gain=gain, shapes=shp, pred_std=float(pred.std()), pred_mean=float(pred.mean()))
+        print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
+
+
+INCREMENTAL = {"trajgru": run_trajgru, "blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac, "stphy": run_stphy}
 
 
 def main():
@@ -287,6 +305,7 @@ def main():
     run_measures(manifest)
     run_models_ac(manifest)
     run_stphy(manifest)
+    run_trajgru(manifest)
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)
 

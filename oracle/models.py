@@ -85,6 +85,39 @@ def ef_convlstm_forward(sd, x, pred_frames, cfg=None):
     return seq, None
 
 
+def ef_trajgru_forward(sd, x, pred_frames, cfg=None):
+    """EF_TrajGRU.forward (models/precipitation_nowcasting/ef_traj_gru.py + ef_blocks.py:52-187): the Encoder-Forecaster
+    skeleton of ``ef_convlstm_forward`` with TrajGRU drivers (blocks.trajgru_sequence) instead of ConvLSTMs."""
+    cfg = {**EF_DEFAULTS, **(cfg or {})}
+    L = cfg["num_layers"]
+    act = lambda v: F.leaky_relu(v, 0.2)                                # noqa: E731  (ef_traj_gru.py:31)
+    b, t = x.shape[:2]
+    seq = x
+    states = []
+    for n in range(L):
+        name = cfg["enc_conv_names"][n]
+        flat = seq.reshape(b * t, *seq.shape[2:])
+        flat = F.leaky_relu(F.conv2d(flat, sd[f"encoder.stage{n + 1}.{name}.weight"], sd[f"encoder.stage{n + 1}.{name}.bias"],
+                                     stride=cfg["enc_conv_s"][n], padding=cfg["enc_conv_p"][n]), 0.2)
+        seq = flat.reshape(b, t, *flat.shape[1:])
+        seq, st = B.trajgru_sequence(seq, None, t, B._sub(sd, f"encoder.rnn{n + 1}."), act)
+        states.append(st)
+    seq = None
+    for n in range(L):
+        idx = L - n
+        seq, _ = B.trajgru_sequence(seq, states[idx - 1], pred_frames, B._sub(sd, f"forecaster.rnn{idx}."), act)
+        name = cfg["dec_conv_names"][n]
+        flat = seq.reshape(b * pred_frames, *seq.shape[2:])
+        flat = F.leaky_relu(F.conv_transpose2d(flat, sd[f"forecaster.stage{idx}.{name}.weight"],
+                                               sd[f"forecaster.stage{idx}.{name}.bias"], stride=cfg["dec_conv_s"][n],
+                                               padding=cfg["dec_conv_p"][n]), 0.2)
+        if n == L - 1:
+            fname = cfg["final_conv_2_name"]
+            flat = F.conv2d(flat, sd[f"forecaster.stage{idx}.{fname}.weight"], sd[f"forecaster.stage{idx}.{fname}.bias"])
+        seq = flat.reshape(b, pred_frames, *flat.shape[1:])
+    return seq, None
+
+
 # --------------------------------------------------------------------------------------------------
 # predrnn-pp  (PredRNN_V2, non action-conditional, layer_norm=False, eval)
 # --------------------------------------------------------------------------------------------------
@@ -358,4 +391,5 @@ FORWARDS = {
     "phy": phydnet_forward,
     "convlstm-branch": convlstm_branch_forward,
     "st-phy": stphy_forward,
+    "trajgru": ef_trajgru_forward,
 }

@@ -174,5 +174,39 @@ def stphy_shapes(img_shape, cfg=None):
     return out
 
 
-SHAPES = {"st-phy": stphy_shapes, "convlstm-shi": ef_shapes, "predrnn-pp": predrnn_shapes, "phy": phydnet_shapes,
+def trajgru_shapes(img_shape, cfg=None):
+    """models/precipitation_nowcasting/ef_traj_gru.py:30-119 at its default hyper-parameters (L = 13 flows, i2h k3)."""
+    base = ef_shapes(img_shape, cfg)
+    cfg = {**EF_DEFAULTS, **(cfg or {})}
+    out = {}
+    for k, v in base.items():
+        parts = k.split(".")
+        if parts[1].startswith("rnn"):
+            continue
+        out[k] = v
+
+    def rnn(prefix, in_c, c, L=13, k=3):
+        out[prefix + "i2h.weight"] = (3 * c, in_c, k, k)
+        out[prefix + "i2h.bias"] = (3 * c,)
+        out[prefix + "i2f_conv1.weight"] = (32, in_c, 5, 5)
+        out[prefix + "i2f_conv1.bias"] = (32,)
+        out[prefix + "h2f_conv1.weight"] = (32, c, 5, 5)
+        out[prefix + "h2f_conv1.bias"] = (32,)
+        out[prefix + "flows_conv.weight"] = (2 * L, 32, 5, 5)
+        out[prefix + "flows_conv.bias"] = (2 * L,)
+        out[prefix + "ret.weight"] = (3 * c, c * L, 1, 1)
+        out[prefix + "ret.bias"] = (3 * c,)
+    in_c = img_shape[0]
+    for n in range(3):
+        mid, oc = cfg["enc_c"][2 * n], cfg["enc_c"][2 * n + 1]
+        rnn(f"encoder.rnn{n + 1}.", mid, oc)
+        in_c = oc
+    for n in range(3):
+        mid, oc = cfg["dec_c"][2 * n], cfg["dec_c"][2 * n + 1]
+        rnn(f"forecaster.rnn{3 - n}.", in_c, mid)
+        in_c = oc
+    return out
+
+
+SHAPES = {"trajgru": trajgru_shapes, "st-phy": stphy_shapes, "convlstm-shi": ef_shapes, "predrnn-pp": predrnn_shapes, "phy": phydnet_shapes,
           "convlstm-branch": phydnet_shapes}

@@ -37,7 +37,7 @@ def test_desc_struct_matches_header_field_order():
     fields = []
     for decl in re.findall(r"(?:int32_t|float)\s+([^;]+);", body):
         for part in decl.split(","):
-            fields.append(re.match(r"\s*([a-z_0-9]+)", part).group(1))
+            fields.append(re.match(r"\s*([A-Za-z_0-9]+)", part).group(1))
     assert fields == [f[0] for f in N.ModelDesc._fields_]
 
 

@@ -35,7 +35,7 @@ def _errs(a, b):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("key", ["convlstm-shi", "predrnn-pp", "phy", "convlstm-branch", "st-phy"])
+@pytest.mark.parametrize("key", ["convlstm-shi", "predrnn-pp", "phy", "convlstm-branch", "st-phy", "trajgru"])
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_reference_model_test_protocol(key, precision):
     """tests/test_models.py:19-35 of the reference, plus values."""

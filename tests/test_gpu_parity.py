@@ -85,7 +85,7 @@ def test_action_conditional_models_match_reference_golden(manifest, name, precis
 
 
 EF_CASES = ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64", "branch_1x64",
-            "predrnn_ln_1x64", "predrnn_ln_3x32", "stphy_3x64"]
+            "predrnn_ln_1x64", "predrnn_ln_3x32", "stphy_3x64", "trajgru_1x64", "trajgru_3x32"]
 
 
 @pytest.mark.parametrize("name", EF_CASES)

@@ -20,7 +20,7 @@ def _case(manifest, name):
 
 
 @pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64",
-                                  "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32", "stphy_3x64"])
+                                  "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32", "stphy_3x64", "trajgru_1x64", "trajgru_3x32"])
 def test_model_rollout_matches_reference(manifest, name):
     meta, sd, x = _case(manifest, name)
     gold = load_golden(name)

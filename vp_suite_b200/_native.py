@@ -14,7 +14,8 @@ LIB_PATH = os.environ.get("VPK_LIB_PATH") or os.path.join(_HERE, "libvpk.so")
 
 VPK_PREC_FP32, VPK_PREC_BF16 = 0, 1
 VPK_BACKEND_AUTO, VPK_BACKEND_SIMT = 0, 1
-VPK_MODEL_CONVLSTM_SHI, VPK_MODEL_PREDRNN_PP, VPK_MODEL_PHY, VPK_MODEL_CONVLSTM_BRANCH, VPK_MODEL_ST_PHY = 0, 1, 2, 3, 4
+(VPK_MODEL_CONVLSTM_SHI, VPK_MODEL_PREDRNN_PP, VPK_MODEL_PHY, VPK_MODEL_CONVLSTM_BRANCH, VPK_MODEL_ST_PHY,
+ VPK_MODEL_TRAJGRU) = 0, 1, 2, 3, 4, 5
 
 PRECISIONS = {"fp32": VPK_PREC_FP32, "bf16": VPK_PREC_BF16}
 BACKENDS = {"auto": VPK_BACKEND_AUTO, "simt": VPK_BACKEND_SIMT}
@@ -37,6 +38,7 @@ class ModelDesc(C.Structure):
         ("convlstm_kernel_size", C.c_int32),
         ("max_microbatch", C.c_int32), ("use_cuda_graph", C.c_int32),
         ("action_conditional", C.c_int32), ("action_size", C.c_int32), ("residual_on_action_conv", C.c_int32),
+        ("enc_rnn_L", C.c_int32 * 3), ("dec_rnn_L", C.c_int32 * 3),
     ]
 
 

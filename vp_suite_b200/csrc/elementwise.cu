@@ -959,6 +959,90 @@ __global__ void fanout_kernel(const float* __restrict__ in, T1* __restrict__ hi,
   }
 }
 
+// ---- TrajGRU (model_blocks/traj_gru.py:150-166, 198-206) ----
+// warped[b, y, x, l * C + c] = bilinear sample of h[b, :, :, c] at (x - flow_x, y - flow_y) for flow pair l, zeros outside.
+// The reference normalises with (W - 1) / (H - 1) and samples with grid_sample's default align_corners=False: pixel
+// coordinate = ((2 s / (W - 1) - 1 + 1) * W - 1) / 2.  One thread = one (position, flow, 4 channels).
+template <typename T>
+__global__ void trajgru_warp_kernel(const float* __restrict__ h, const float* __restrict__ flows, int fpix, T* __restrict__ out,
+                                    int B, int H, int W, int C, int L) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int cq = C >> 2;
+  const long long total = static_cast<long long>(B) * H * W * L * cq;
+  const float sx = static_cast<float>(W) / static_cast<float>(max(W - 1, 1)), sy = static_cast<float>(H) / static_cast<float>(max(H - 1, 1));
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int c4 = static_cast<int>(i % cq);
+    long long r = i / cq;
+    const int l = static_cast<int>(r % L);
+    const long long pos = r / L;
+    const int x = static_cast<int>(pos % W), y = static_cast<int>((pos / W) % H);
+    const long long b = pos / (static_cast<long long>(W) * H);
+    const float* fp = flows + pos * fpix + 2 * l;
+    // vgrid = grid + (-flow); normalised with (W - 1), sampled with align_corners = False
+    const float xn = 2.0f * (static_cast<float>(x) - fp[0]) / static_cast<float>(max(W - 1, 1)) - 1.0f;
+    const float yn = 2.0f * (static_cast<float>(y) - fp[1]) / static_cast<float>(max(H - 1, 1)) - 1.0f;
+    const float ix = ((xn + 1.0f) * W - 1.0f) * 0.5f, iy = ((yn + 1.0f) * H - 1.0f) * 0.5f;
+    (void)sx; (void)sy;
+    const float fx0 = floorf(ix), fy0 = floorf(iy);
+    const int x0 = static_cast<int>(fx0), y0 = static_cast<int>(fy0);
+    const float wx1 = ix - fx0, wy1 = iy - fy0, wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* hb = h + b * static_cast<long long>(H) * W * C + c4 * 4;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const int xs = x0 + dx, ys = y0 + dy;
+        if (xs >= 0 && xs < W && ys >= 0 && ys < H) {
+          const float wgt = (dx ? wx1 : wx0) * (dy ? wy1 : wy0);
+          const float4 v = *reinterpret_cast<const float4*>(hb + (static_cast<long long>(ys) * W + xs) * C);
+          acc.x = fmaf(wgt, v.x, acc.x);
+          acc.y = fmaf(wgt, v.y, acc.y);
+          acc.z = fmaf(wgt, v.z, acc.z);
+          acc.w = fmaf(wgt, v.w, acc.w);
+        }
+      }
+    T* o = out + pos * (static_cast<long long>(L) * C) + static_cast<long long>(l) * C + c4 * 4;
+    o[0] = to_act<T>(acc.x);
+    o[1] = to_act<T>(acc.y);
+    o[2] = to_act<T>(acc.z);
+    o[3] = to_act<T>(acc.w);
+  }
+}
+
+// r = sig(i2h_0 + h2h_0), u = sig(i2h_1 + h2h_1), m = act(i2h_2 + r * h2h_2), h' = u * h + (1 - u) * m   (i2h may be absent)
+template <typename T>
+__global__ void trajgru_gates_kernel(const float* __restrict__ i2h, const float* __restrict__ h2h, const float* __restrict__ h,
+                                     float* __restrict__ h_out, T* __restrict__ h_act, long long P, int C, int act) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const long long total = P * C;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long p = i / C;
+    const int c = static_cast<int>(i - p * C);
+    const float* a = h2h + p * 3 * C;
+    float ir = 0.f, iu = 0.f, im = 0.f;
+    if (i2h != nullptr) {
+      const float* q = i2h + p * 3 * C;
+      ir = q[c];
+      iu = q[C + c];
+      im = q[2 * C + c];
+    }
+    const float r = 1.f / (1.f + __expf(-(ir + a[c])));
+    const float u = 1.f / (1.f + __expf(-(iu + a[C + c])));
+    float m = im + r * a[2 * C + c];
+    if (act == ACT_LEAKY) m = m > 0.f ? m : 0.2f * m;
+    else if (act == ACT_RELU) m = fmaxf(m, 0.f);
+    else if (act == ACT_SIGMOID) m = 1.f / (1.f + __expf(-m));
+    const float hn = u * h[i] + (1.f - u) * m;
+    h_out[i] = hn;
+    if (h_act != nullptr) h_act[i] = to_act<T>(hn);
+  }
+}
+
 __global__ void decouple_finalize_kernel(const double* acc, float* aux, double scale) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
@@ -1170,6 +1254,25 @@ void launch_inflate_actions(const float* actions, long long bstride, int a, void
   if (dtype == DT_F32) launch_pdl(inflate_actions_kernel<float>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<float*>(out), B, T, HW, a_pad);
   else if (dtype == DT_F16) launch_pdl(inflate_actions_kernel<__half>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<__half*>(out), B, T, HW, a_pad);
   else launch_pdl(inflate_actions_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, actions, bstride, a, static_cast<__nv_bfloat16*>(out), B, T, HW, a_pad);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_trajgru_warp(const float* h, const float* flows, int fpix, void* out, int dtype, int B, int H, int W, int C, int L,
+                         int num_sms, cudaStream_t stream) {
+  VPK_REQUIRE(C % 4 == 0 && L >= 1 && fpix >= 2 * L, "trajgru_warp: bad shape");
+  const int g = grid_for(static_cast<long long>(B) * H * W * L * (C / 4), 256, num_sms);
+  if (dtype == DT_F32) launch_pdl(trajgru_warp_kernel<float>, dim3(g), dim3(256), 0, stream, h, flows, fpix, static_cast<float*>(out), B, H, W, C, L);
+  else if (dtype == DT_F16) launch_pdl(trajgru_warp_kernel<__half>, dim3(g), dim3(256), 0, stream, h, flows, fpix, static_cast<__half*>(out), B, H, W, C, L);
+  else launch_pdl(trajgru_warp_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, h, flows, fpix, static_cast<__nv_bfloat16*>(out), B, H, W, C, L);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_trajgru_gates(const float* i2h, const float* h2h, const float* h, float* h_out, void* h_act, int dtype, long long P,
+                          int C, int act, int num_sms, cudaStream_t stream) {
+  const int g = grid_for(P * C, 256, num_sms);
+  if (dtype == DT_F32) launch_pdl(trajgru_gates_kernel<float>, dim3(g), dim3(256), 0, stream, i2h, h2h, h, h_out, static_cast<float*>(nullptr), P, C, act);
+  else if (dtype == DT_F16) launch_pdl(trajgru_gates_kernel<__half>, dim3(g), dim3(256), 0, stream, i2h, h2h, h, h_out, static_cast<__half*>(h_act), P, C, act);
+  else launch_pdl(trajgru_gates_kernel<__nv_bfloat16>, dim3(g), dim3(256), 0, stream, i2h, h2h, h, h_out, static_cast<__nv_bfloat16*>(h_act), P, C, act);
   VPK_CUDA(cudaGetLastError());
 }
 

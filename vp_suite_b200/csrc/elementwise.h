@@ -76,6 +76,13 @@ void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num
 // out (activation type) [T][B][HW][a_pad], channels a..a_pad-1 zero (the action vector inflated to the frame size)
 void launch_inflate_actions(const float* actions, long long bstride, int a, void* out, int dtype, int B, int T, int HW,
                             int a_pad, int num_sms, cudaStream_t stream);
+// TrajGRU (model_blocks/traj_gru.py): bilinear warps of the fp32 state h [B][H][W][C] by the L flow pairs in
+// flows [B][H][W][fpix] (pair l at channels 2l, 2l + 1) -> out (activation type) [B][H][W][L * C]; and the GRU gate update
+// from the raw i2h (nullable) / h2h pre-activations [P][3C] (fp32): h_out fp32 [P][C] + an activation-type copy
+void launch_trajgru_warp(const float* h, const float* flows, int fpix, void* out, int dtype, int B, int H, int W, int C, int L,
+                         int num_sms, cudaStream_t stream);
+void launch_trajgru_gates(const float* i2h, const float* h2h, const float* h, float* h_out, void* h_act, int dtype, long long P,
+                          int C, int act, int num_sms, cudaStream_t stream);
 // in fp32 NHWC [B][H][W][C] -> typed copies: hi / lo (split pair of hi_dtype; either may be nullptr), cell (cell_dtype,
 // nullable), f32 (nullable; may alias `in` only when norm_w is false); norm_w: L2-normalise along W first (eps clamp)
 void launch_fanout(const float* in, void* hi, void* lo, int hi_dtype, void* cell, int cell_dtype, float* f32, int B, int H,

@@ -10,6 +10,7 @@ load unchanged:  ``ours.load_state_dict(reference_model.state_dict())``.
     PhyDNet          <- vp_suite/models/phydnet.py:12-137                              (key "phy")
     ConvLSTMBranch   <- BASELINE config 2: PhyDNet's residual branch alone (our composition of reference blocks)
     STPhy            <- vp_suite/models/st_phy.py:16-181                               (key "st-phy")
+    EF_TrajGRU       <- vp_suite/models/precipitation_nowcasting/ef_traj_gru.py:8-119  (key "trajgru")
 """
 from collections import OrderedDict
 
@@ -467,6 +468,175 @@ class ConvLSTMBranch(PhyDNet):
     _KIND = N.VPK_MODEL_CONVLSTM_BRANCH
 
 
+class Activation:
+    """model_blocks/traj_gru.py:8-27: the configurable activation object EF_TrajGRU keeps as its ``activation`` attribute."""
+
+    def __init__(self, act_type, negative_slope=0.2, inplace=True):
+        self._act_type, self.negative_slope, self.inplace = act_type, negative_slope, inplace
+
+    def __call__(self, input):
+        if self._act_type == "leaky":
+            return torch.nn.functional.leaky_relu(input, negative_slope=self.negative_slope)
+        if self._act_type == "relu":
+            return torch.relu(input)
+        if self._act_type == "sigmoid":
+            return torch.sigmoid(input)
+        raise NotImplementedError
+
+
+class EF_TrajGRU(NativeRollout, VPModel):
+    """models/precipitation_nowcasting/ef_traj_gru.py:8-119: the Encoder-Forecaster skeleton with TrajGRU blocks
+    (model_blocks/traj_gru.py:70-214: learned flows, bilinear warps of the hidden state, 1x1 conv, GRU gates)."""
+    NAME = "EF-TrajGRU (Shi et al.)"
+    PAPER_REFERENCE = "https://arxiv.org/abs/1706.03458"
+    CODE_REFERENCE = "https://github.com/Hzzone/Precipitation-Nowcasting"
+    MATCHES_REFERENCE: str = "Yes"
+
+    # hyper-parameters: ef_traj_gru.py:30-74
+    activation = Activation("leaky", negative_slope=0.2, inplace=True)
+    num_layers = 3
+    enc_c = [16, 64, 64, 96, 96, 96]
+    dec_c = [96, 96, 96, 96, 64, 16]
+    enc_conv_names = ["conv1_leaky_1", "conv2_leaky_1", "conv3_leaky_1"]
+    enc_conv_k = [3, 3, 3]
+    enc_conv_s = [1, 2, 2]
+    enc_conv_p = [1, 1, 1]
+    dec_conv_names = ["deconv1_leaky_1", "deconv2_leaky_1", "deconv3_leaky_1"]
+    dec_conv_k = [4, 4, 3]
+    dec_conv_s = [2, 2, 1]
+    dec_conv_p = [1, 1, 1]
+    enc_rnn_z = [0.0, 0.0, 0.0]
+    enc_rnn_L = [13, 13, 13]
+    enc_rnn_i2h_k = [(3, 3), (3, 3), (3, 3)]
+    enc_rnn_i2h_s = [(1, 1), (1, 1), (1, 1)]
+    enc_rnn_i2h_p = [(1, 1), (1, 1), (1, 1)]
+    enc_rnn_h2h_k = [(5, 5), (5, 5), (3, 3)]
+    enc_rnn_h2h_d = [(1, 1), (1, 1), (1, 1)]
+    dec_rnn_z = [0.0, 0.0, 0.0]
+    dec_rnn_L = [13, 13, 13]
+    dec_rnn_i2h_k = [(3, 3), (3, 3), (3, 3)]
+    dec_rnn_i2h_s = [(1, 1), (1, 1), (1, 1)]
+    dec_rnn_i2h_p = [(1, 1), (1, 1), (1, 1)]
+    dec_rnn_h2h_k = [(3, 3), (5, 5), (5, 5)]
+    dec_rnn_h2h_d = [(1, 1), (1, 1), (1, 1)]
+    final_conv_1_name = "identity"
+    final_conv_1_c = 16
+    final_conv_1_k = 3
+    final_conv_1_s = 1
+    final_conv_1_p = 1
+    final_conv_2_name = "conv3_3"
+    final_conv_2_k = 1
+    final_conv_2_s = 1
+    final_conv_2_p = 0
+
+    def __init__(self, device, **model_kwargs):
+        super().__init__(device, **model_kwargs)
+        self._native_init()
+        L = self.num_layers
+        if L != 3:
+            raise AttributeError("the Encoder-Forecaster structure needs num_layers == 3")
+        for name, val in [(k, v) for k, v in vars(self).items() if k.startswith(("enc_", "dec_"))]:
+            want = 2 * L if name in ("enc_c", "dec_c") else L            # ef_blocks.py:134-143
+            if isinstance(val, (list, tuple)) and len(val) != want:
+                raise AttributeError(f"Speficied {L} layers, but len of attribute '{name}' doesn't match that ({val}).")
+        if any(z != 0.0 for z in self.enc_rnn_z + self.dec_rnn_z):
+            raise AttributeError("zoneout is a training-time regulariser: the native rollout takes zoneout 0 only")
+        for ks, ss, ps in ((self.enc_rnn_i2h_k, self.enc_rnn_i2h_s, self.enc_rnn_i2h_p), (self.dec_rnn_i2h_k, self.dec_rnn_i2h_s, self.dec_rnn_i2h_p)):
+            for k, st, pd in zip(ks, ss, ps):
+                if k[0] != k[1] or k[0] % 2 == 0 or tuple(st) != (1, 1) or tuple(pd) != (k[0] // 2, k[0] // 2):
+                    raise AttributeError("i2h convs must be square, odd, stride 1, 'same' padding (anything else changes the state size)")
+        if self.final_conv_1_name != "identity" or self.final_conv_2_k != 1 or self.final_conv_2_s != 1 or self.final_conv_2_p != 0:
+            raise AttributeError("only the reference's final block (identity + 1x1 conv) is supported")
+        acts = {_act_code(n) for n in self.enc_conv_names + self.dec_conv_names}
+        rnn_act = {"leaky": 1, "relu": 3, "sigmoid": 2}.get(getattr(self.activation, "_act_type", None))
+        if len(acts) != 1 or rnn_act is None or acts != {rnn_act}:
+            raise AttributeError("stage convs and the TrajGRU activation must share one activation")
+        self._ef_act = rnn_act
+        hw = (self.img_h, self.img_w)
+        enc_hw = []
+        for n in range(L):
+            hw = _conv_out(hw, self.enc_conv_k[n], self.enc_conv_s[n], self.enc_conv_p[n])
+            enc_hw.append(hw)
+        dec_hw = [hw]
+        for n in range(L - 1):
+            hw = _convt_out(hw, self.dec_conv_k[n], self.dec_conv_s[n], self.dec_conv_p[n])
+            dec_hw.append(hw)
+        final = _convt_out(hw, self.dec_conv_k[-1], self.dec_conv_s[-1], self.dec_conv_p[-1])
+        if final != (self.img_h, self.img_w):
+            raise AttributeError(f"Model layer hyperparameters yield wrong output size: {final} "
+                                 f"(expected: {(self.img_h, self.img_w)}). All hidden sizes: {enc_hw + dec_hw}")
+        self.enc_rnn_state_h = [v[0] for v in enc_hw]
+        self.enc_rnn_state_w = [v[1] for v in enc_hw]
+        self.dec_rnn_state_h = [v[0] for v in dec_hw]
+        self.dec_rnn_state_w = [v[1] for v in dec_hw]
+
+        def rnn(in_c, c, flows, k):                                      # traj_gru.py:93-131, same creation order
+            m = _Params()
+            m.i2h = nn.Conv2d(in_c, 3 * c, k, 1, (k[0] // 2, k[1] // 2))
+            m.i2f_conv1 = nn.Conv2d(in_c, 32, (5, 5), 1, (2, 2))
+            m.h2f_conv1 = nn.Conv2d(c, 32, (5, 5), 1, (2, 2))
+            m.flows_conv = nn.Conv2d(32, flows * 2, (5, 5), 1, (2, 2))
+            m.ret = nn.Conv2d(c * flows, 3 * c, (1, 1), 1)
+            return m
+
+        self.encoder, self.forecaster = _Params(), _Params()
+        in_c = self.img_c
+        enc_rnn, enc_io, dec_rnn, dec_io = [], [], [], []
+        for n in range(L):                                               # ef_traj_gru.py:80-97
+            mid, out_c = self.enc_c[2 * n], self.enc_c[2 * n + 1]
+            enc_io.append((in_c, mid))
+            enc_rnn.append(rnn(mid, out_c, self.enc_rnn_L[n], self.enc_rnn_i2h_k[n]))
+            in_c = out_c
+        for n in range(L):                                               # ef_traj_gru.py:99-119
+            mid, out_c = self.dec_c[2 * n], self.dec_c[2 * n + 1]
+            dec_rnn.append(rnn(in_c, mid, self.dec_rnn_L[n], self.dec_rnn_i2h_k[n]))
+            dec_io.append((mid, out_c))
+            in_c = out_c
+        for n in range(L):                                               # Encoder.__init__   ef_blocks.py:63-65
+            ci, co = enc_io[n]
+            setattr(self.encoder, f"stage{n + 1}", _stage([(self.enc_conv_names[n], nn.Conv2d(ci, co, self.enc_conv_k[n],
+                                                                                                self.enc_conv_s[n], self.enc_conv_p[n]))]))
+            setattr(self.encoder, f"rnn{n + 1}", enc_rnn[n])
+        for n in range(L):                                               # Forecaster.__init__ ef_blocks.py:96-98
+            ci, co = dec_io[n]
+            layers = [(self.dec_conv_names[n], nn.ConvTranspose2d(ci, co, self.dec_conv_k[n], self.dec_conv_s[n], self.dec_conv_p[n]))]
+            if n == L - 1:
+                layers.append((self.final_conv_1_name, nn.Identity()))
+                layers.append((self.final_conv_2_name, nn.Conv2d(self.final_conv_1_c, self.img_c, 1, 1, 0)))
+            setattr(self.forecaster, f"rnn{L - n}", dec_rnn[n])
+            setattr(self.forecaster, f"stage{L - n}", _stage(layers))
+        self.NON_CONFIG_VARS = list(self.NON_CONFIG_VARS) + ["encoder", "forecaster"]
+        self.to(device)
+
+    def _native_desc(self):
+        d = N.ModelDesc()
+        d.kind = N.VPK_MODEL_TRAJGRU
+        d.img_c, d.img_h, d.img_w = self.img_c, self.img_h, self.img_w
+        for f in ("enc_c", "dec_c", "enc_conv_k", "enc_conv_s", "enc_conv_p", "dec_conv_k", "dec_conv_s", "dec_conv_p",
+                  "enc_rnn_L", "dec_rnn_L"):
+            arr = getattr(d, f)
+            for i, v in enumerate(getattr(self, f)):
+                arr[i] = int(v)
+        for i in range(3):
+            d.enc_rnn_k[i] = int(self.enc_rnn_i2h_k[i][0])
+            d.dec_rnn_k[i] = int(self.dec_rnn_i2h_k[i][0])
+        d.final_conv_c = int(self.final_conv_1_c)
+        d.ef_act = self._ef_act
+        return d
+
+    _native_key = EF_ConvLSTM._native_key
+
+    def pred_1(self, x, **kwargs):
+        return self(x, pred_frames=1, **kwargs)[0].squeeze(dim=1)        # ef_blocks.py:181-182
+
+    def forward(self, x, pred_frames: int = 1, **kwargs):
+        b, t, c, h, w = x.shape
+        if (c, h, w) != (self.img_c, self.img_h, self.img_w):
+            raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        pred, _ = self._native_forward(x, int(pred_frames), t)
+        return pred, None                                                # ef_blocks.py:184-187
+
+
 class STPhy(NativeRollout, VPModel):
     """models/st_phy.py:16-181: Autoencoder + per layer one PhyCell_Cell and one LayerNorm ST-LSTM cell merged by a 1x1 conv.
     The native rollout covers the non action-conditional model in eval mode (losses are training-only there: ``forward``
@@ -566,4 +736,5 @@ MODEL_CLASSES = {
     "phy": PhyDNet,
     "convlstm-branch": ConvLSTMBranch,
     "st-phy": STPhy,
+    "trajgru": EF_TrajGRU,
 }
