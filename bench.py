@@ -460,7 +460,7 @@ def main():
     peak = peaks.get("bf16_tflops_sustained" if sustained else "bf16_tflops", 1590.0)
     achieved = fr["gate_gemm_tflops"]
     traffic, traffic_note = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.exists(tpath) and args.workload == "cfg5":
         with open(tpath) as f:
             tj = json.load(f)["cfg5"]

@@ -656,18 +656,26 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           const uint32_t taddr =
               tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
           float z[4] = {s_proj[4 * np], s_proj[4 * np + 1], s_proj[4 * np + 2], s_proj[4 * np + 3]};
-          for (int ch = 0; ch < Cn; ch += 8) {
-            uint32_t r[8];
-            ptx::tmem_ld8(taddr + static_cast<uint32_t>(ch), r);
+          for (int ch0 = 0; ch0 < Cn; ch0 += 32) {          // up to four 8-channel chunks per tcgen05.wait::ld
+            uint32_t r4[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              if (ch0 + 8 * q < Cn) ptx::tmem_ld8(taddr + static_cast<uint32_t>(ch0 + 8 * q), r4[q]);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float v = __uint_as_float(r[j]) + s_bias[ch + j];
-              if (E.act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
-              else if (E.act == ACT_RELU) v = fmaxf(v, 0.f);
-              else if (E.act == ACT_SIGMOID) v = sigmoid_fast(v);
+            for (int q = 0; q < 4; ++q) {
+              const int ch = ch0 + 8 * q;
+              if (ch < Cn) {
 #pragma unroll
-              for (int pr = 0; pr < 4; ++pr) z[pr] = fmaf(s_proj[pr * np + ch + j], v, z[pr]);
+                for (int j = 0; j < 8; ++j) {
+                  float v = __uint_as_float(r4[q][j]) + s_bias[ch + j];
+                  if (E.act == ACT_LEAKY) v = v > 0.f ? v : 0.2f * v;
+                  else if (E.act == ACT_RELU) v = fmaxf(v, 0.f);
+                  else if (E.act == ACT_SIGMOID) v = sigmoid_fast(v);
+#pragma unroll
+                  for (int pr = 0; pr < 4; ++pr) z[pr] = fmaf(s_proj[pr * np + ch + j], v, z[pr]);
+                }
+              }
             }
           }
           if (valid) {
@@ -802,13 +810,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
             for (int i = 0; i < 16; ++i) gs16[i] = 0.f;
             const int gsz = P.L.epi.gn_group_size;
+            uint32_t r4[4][8 * G];       // all (up to four) chunks of this warp are read behind ONE tcgen05.wait::ld
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              if (half * 8 + 16 * k < Cn) tmem_chunk(half * 8 + 16 * k, r4[k]);
+            ptx::tmem_ld_wait();
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int ch = half * 8 + 16 * k;
               if (ch < Cn) {
-                uint32_t r[8 * G];
-                tmem_chunk(ch, r);
-                ptx::tmem_ld_wait();
+                const uint32_t* r = r4[k];
                 float a[G][8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) a[0][j] = 0.f;
@@ -833,9 +844,41 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
           }
         } else {
+          if constexpr (KIND == EPI_BIAS_ACT) {
+            // bias + activation (+ residual / whole-sample statistics): nothing has to be fetched from memory first, so the
+            // only latency per chunk is the TMEM read itself (~0.5 k cycles; six serial reads made the N = 96 deconv
+            // epilogue slower than its MMAs).  Up to four chunks are read per tcgen05.wait::ld.
+            const int nj = (Cn - half * 8 + 15) / 16;          // this warp's chunks: channels half * 8 + 16 j
+            for (int j0 = 0; j0 < nj; j0 += 4) {
+              uint32_t r4[4][8];
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                if (j0 + q < nj) ptx::tmem_ld8(taddr + static_cast<uint32_t>(half * 8 + 16 * (j0 + q)), r4[q]);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const int ch = half * 8 + 16 * (j0 + q);
+                if (j0 + q < nj && valid && ch_base + ch < C) {
+                  if (P.L.epi.res != nullptr) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + ch, ops0);
+                  float a[G][8];
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) a[0][j] = __uint_as_float(r4[q][j]);
+                  epi_tc_finish<KIND, G>(P.L.epi, et, ch_base + ch, bias, a, ops0);
+                  if (ln_stats) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                      ln_s += a[0][j];
+                      ln_q = fmaf(a[0][j], a[0][j], ln_q);
+                    }
+                  }
+                }
+              }
+            }
+          } else {
           for (int ch = half * 8; ch < Cn; ch += 32) {
             do_chunk(ch, ops0, ops1);
             if (ch + 16 < Cn) do_chunk(ch + 16, ops1, ops0);
+          }
           }
           if (ln_stats) {      // one (sum, sum of squares) pair per warp and tile, in this warp's own slot: deterministic
 #pragma unroll
