@@ -76,6 +76,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   uint8_t* smem = smem_raw + (((raw_addr + 1023u) & ~1023u) - raw_addr);
   float* s_cstate = reinterpret_cast<float*>(smem);          // SEQ: cell state of this CTA's tiles, in front of the rings
   if constexpr (SEQ) smem += P.seq_c_bytes;
+  const uint32_t s_stage = ptx::smem_u32(smem);              // lean_tma: two staged output tiles
+  smem += P.stage_bytes;
   const int T_steps = SEQ ? P.seq_T : 1;
   // PDL: the next kernel of the stream may become resident as soon as every CTA of this grid is (it then waits in its
   // own pdl_wait); everything up to our pdl_wait below reads only plan tables, biases and packed weights' descriptors
@@ -443,6 +445,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int ry = row / kTW;
     const int Cn = tileN / G;
     int iter = 0;
+#ifdef VPK_TRACE
+    long long e_wait = 0, e_body = 0, e_t1 = 0, e_ld = 0;
+#endif
     constexpr bool rolled = (MODE == 2 && KIND == EPI_LSTM);
     if constexpr (rolled) {
       {
@@ -693,7 +698,160 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
     }
+    bool lean_done = false;
+    if constexpr (KIND == EPI_BIAS_ACT && MODE == 1) {
+      if (P.lean) {
+        // ---- bias + slope activation + 16-bit store, nothing else (stage convs, sub-pixel deconv parities, DCGAN tails).
+        // An epilogue warp is ONE instruction stream: at ~7 cycles per dependent instruction the ~340 instructions per tile
+        // of the general loop (tile decode by division, per-chunk predicates, activation switch, 64-bit address chains) took
+        // 2.6 k cycles -- longer than the 24 MMAs of an N = 96, K = 384 tile.  Here: tile coordinates advance incrementally,
+        // the chunk count and the activation are compile-time, all TMEM reads of a tile sit behind one wait. ----
+        lean_done = true;
+        const EpiParams& E = P.L.epi;
+        const int tpi = P.tiles_x * P.tiles_y;
+        const int mstep = nunits * csize;
+        int b, ty, tx;
+        {
+          const int mt = m_tile_of(unit0);
+          b = mt / tpi;
+          const int rem = mt - b * tpi;
+          ty = rem / P.tiles_x;
+          tx = rem - ty * P.tiles_x;
+        }
+        const int db = mstep / tpi;
+        const int dty = (mstep - db * tpi) / P.tiles_x;
+        const int dtx = (mstep - db * tpi) - dty * P.tiles_x;
+        const uint32_t sb = ptx::smem_u32(s_bias) + static_cast<uint32_t>(half * 32);
+        bf16* const outp = static_cast<bf16*>(E.out) + half * 8;
+        const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * 8);
+        const float slope = E.act == ACT_LEAKY ? 0.2f : 1.f;
+        auto run = [&](auto nj_c, auto relu_c, auto tma_c) {
+          constexpr int NJ = decltype(nj_c)::value;          // this warp's 8-channel chunks: channels half * 8 + 16 j
+          constexpr bool RELU = decltype(relu_c)::value;
+          constexpr bool TMA = decltype(tma_c)::value;
+          // TMA: the tile is staged as NJ / 2 sub-tiles of [128 positions][32 channels] (64 B rows, 64B swizzle; one
+          // [128][16] sub-tile with 32 B rows and the 32B swizzle when NJ == 1) -- conflict-free 16 B st.shared
+          constexpr int SUBS = NJ == 1 ? 1 : NJ / 2;
+          constexpr uint32_t kSubBytes = NJ == 1 ? 128u * 32u : 128u * 64u;
+          const bool issuer = TMA && warp == 3 && lane == 0;
+          uint32_t srow = 0;
+          if constexpr (TMA) srow = NJ == 1 ? static_cast<uint32_t>(row * 32) : static_cast<uint32_t>(row * 64);
+          const uint32_t sxor = NJ == 1 ? static_cast<uint32_t>((row >> 2) & 1) : static_cast<uint32_t>((row >> 1) & 3);
+          for (int t = unit0; t < total; t += nunits, ++iter) {
+            const int x = tx * kTW + rx, y = ty * kTH + ry;
+            const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
+            bf16* o = outp + (b * E.oB + y * E.oY + x * E.oX);
+            const int acc = iter & 1;
+#ifdef VPK_TRACE
+            const long long l_t0 = clock64();
+#endif
+            ptx::mbar_wait_fast(tfull + 8 * acc, (iter >> 1) & 1u);
+            ptx::tc_fence_after();
+#ifdef VPK_TRACE
+            const long long l_t1 = clock64();
+            e_wait += l_t1 - l_t0;
+#endif
+            const uint32_t ta = tq + static_cast<uint32_t>(acc * tileN);
+            uint32_t r[NJ][8];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) ptx::tmem_ld8(ta + static_cast<uint32_t>(16 * j), r[j]);
+            float4 bv[NJ][2];
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              bv[j][0] = ptx::lds_f4(sb + static_cast<uint32_t>(64 * j));
+              bv[j][1] = ptx::lds_f4(sb + static_cast<uint32_t>(64 * j + 16));
+            }
+            ptx::tmem_ld_wait();
+#ifdef VPK_TRACE
+            const long long l_t2 = clock64();
+            e_ld += l_t2 - l_t1;
+#endif
+            if constexpr (TMA) {      // the accumulator is in registers: hand the TMEM buffer back before the stores
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
+                else ptx::mbar_arrive(tempty + 8 * acc);
+              }
+            }
+            const uint32_t sbuf = s_stage + static_cast<uint32_t>(iter & 1) * (SUBS * kSubBytes) + srow;
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+              const float bj[8] = {bv[j][0].x, bv[j][0].y, bv[j][0].z, bv[j][0].w, bv[j][1].x, bv[j][1].y, bv[j][1].z, bv[j][1].w};
+              float v[8];
+#pragma unroll
+              for (int k = 0; k < 8; ++k) {
+                const float a = __uint_as_float(r[j][k]) + bj[k];
+                v[k] = RELU ? fmaxf(a, 0.f) : (a > 0.f ? a : slope * a);
+              }
+              if constexpr (TMA) {
+                uint4 pk;
+                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                // channel half * 8 + 16 j: sub-tile j / 2, 16-byte chunk (half + 2 j) % 4 of its row
+                const uint32_t chunk = NJ == 1 ? static_cast<uint32_t>(half) : static_cast<uint32_t>((half + 2 * j) & 3);
+                ptx::sts_u4(sbuf + static_cast<uint32_t>(j >> 1) * kSubBytes + ((chunk ^ sxor) << 4), pk);
+              } else {
+                if (valid) st_bf16x8(o + 16 * j, v);
+              }
+            }
+            if constexpr (TMA) {
+              ptx::fence_proxy_async_smem();               // this thread's st.shared -> visible to the bulk store
+              if (issuer) ptx::bulk_wait_read0();          // the previous tile's store has read its buffer (the one the
+                                                           // NEXT tile writes, after the barrier below)
+              asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+              if (issuer && b < P.L.B && !(P.debug & 1)) {
+#pragma unroll
+                for (int u = 0; u < SUBS; ++u)
+                  ptx::tma_store_4d(&P.omap, s_stage + static_cast<uint32_t>(iter & 1) * (SUBS * kSubBytes) + u * kSubBytes,
+                                    u * 32, tx * kTW, ty * kTH, b);
+                ptx::bulk_commit();
+              }
+            } else {
+              ptx::tc_fence_before();
+              __syncwarp();
+              if (lane == 0) {
+                if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
+                else ptx::mbar_arrive(tempty + 8 * acc);
+              }
+            }
+#ifdef VPK_TRACE
+            e_body += clock64() - l_t2;
+#endif
+            tx += dtx;
+            if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
+            ty += dty;
+            if (ty >= P.tiles_y) { ty -= P.tiles_y; ++b; }
+            b += db;
+          }
+          if (issuer) ptx::bulk_wait0();                   // all staged tiles are in global memory before the CTA exits
+        };
+        auto run_r = [&](auto nj_c, auto tma_c) {
+          if (E.act == ACT_RELU) run(nj_c, std::true_type{}, tma_c);
+          else run(nj_c, std::false_type{}, tma_c);
+        };
+        if (P.lean_tma) {
+          switch (Cn >> 4) {
+            case 1: run_r(std::integral_constant<int, 1>{}, std::true_type{}); break;
+            case 2: run_r(std::integral_constant<int, 2>{}, std::true_type{}); break;
+            case 4: run_r(std::integral_constant<int, 4>{}, std::true_type{}); break;
+            case 6: run_r(std::integral_constant<int, 6>{}, std::true_type{}); break;
+            default: __trap();    // the plan sets `lean_tma` for 16 / 32 / 64 / 96 channels only
+          }
+        } else
+        switch (Cn >> 4) {
+          case 1: run_r(std::integral_constant<int, 1>{}, std::false_type{}); break;
+          case 2: run_r(std::integral_constant<int, 2>{}, std::false_type{}); break;
+          case 3: run_r(std::integral_constant<int, 3>{}, std::false_type{}); break;
+          case 4: run_r(std::integral_constant<int, 4>{}, std::false_type{}); break;
+          case 6: run_r(std::integral_constant<int, 6>{}, std::false_type{}); break;
+          default: __trap();      // the plan sets `lean` for these chunk counts only
+        }
+      }
+    }
     if constexpr (!rolled && MODE != 3 && !SEQ)
+    if (!lean_done)
     for (int t = unit0; t < total; t += nunits, ++iter) {
       const int nt = t % P.n_tiles;
       const int mt = m_tile_of(t);
@@ -720,8 +878,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         if (valid) et = epi_tile(P.L.epi, b, y, x, P.L.H, P.L.W);
         const float* bias = s_bias;
         if (valid && ch_base + half * 8 < C) epi_tc_prefetch<KIND>(P.L.epi, et, ch_base + half * 8, ops0);
+#ifdef VPK_TRACE
+        const long long e_t0 = clock64();
+#endif
         ptx::mbar_wait_fast(tfull + 8 * acc, acc_phase);
         ptx::tc_fence_after();
+#ifdef VPK_TRACE
+        e_t1 = clock64();
+        e_wait += e_t1 - e_t0;
+#endif
         const bool ln_stats = (KIND == EPI_BIAS_ACT) && P.L.epi.gn_sums != nullptr && P.L.epi.gn_group_size < 0;
         float ln_s = 0.f, ln_q = 0.f;
         auto do_chunk = [&](int ch, EpiOperands<8>& cur, EpiOperands<8>& nxt) {
@@ -925,7 +1090,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
         else ptx::mbar_arrive(tempty + 8 * acc);
       }
+#ifdef VPK_TRACE
+      if (e_t1) e_body += clock64() - e_t1;
+#endif
     }
+#ifdef VPK_TRACE
+    if (trace && warp == 3 && lane == 0 && e_body)
+      printf("halo trace N=%d taps=%d: epilogue warp, %d tiles: waiting for the accumulator %lld cycles, TMEM reads %lld, working %lld "
+             "cycles (lean %d)\n", tileN, P.ntaps, iter, e_wait, e_ld, e_body, P.lean);
+#endif
   }
 
   if (threadIdx.x == kHaloThreads - 1) stamp(6);      // last epilogue warp has finished its tiles
@@ -966,11 +1139,11 @@ EncodeTiledFn encode_fn() {
   return fn;
 }
 void encode(CUtensorMap* map, int rank, const void* base, const cuuint64_t* dims, const cuuint64_t* strides,
-            const cuuint32_t* box, const char* what) {
+            const cuuint32_t* box, const char* what, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                            const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[200];
@@ -1066,6 +1239,21 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
   P.roll = (P.fast_epi && L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) ? 1 : 0;
   if (const char* env = getenv("VPK_EPI_ROLL")) P.roll = P.roll && atoi(env) != 0;
+  {
+    const int cn = P.tileN / L.G, nj = cn / 16;
+    P.lean = (P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.G == 1 && L.epi.proj_n == 0 && L.epi.res == nullptr &&
+              L.epi.gn_sums == nullptr && !L.epi.out_f32 && P.n_tiles == 1 && cn % 16 == 0 && cn <= L.epi.C &&
+              (nj == 1 || nj == 2 || nj == 3 || nj == 4 || nj == 6) &&
+              (L.epi.act == ACT_NONE || L.epi.act == ACT_LEAKY || L.epi.act == ACT_RELU)) ? 1 : 0;
+    if (const char* env = getenv("VPK_EPI_LEAN")) P.lean = P.lean && atoi(env) != 0;
+    // staged bulk-tensor stores: 16 / 32 / 64 / 96 channels (whole 32-channel sub-tiles), 16-byte aligned strides
+    P.lean_tma = (P.lean && reserve_smem == 0 && (nj == 1 || nj == 2 || nj == 4 || nj == 6) && L.epi.oC == 1 &&
+                  L.epi.oX % 8 == 0 && L.epi.oY % 8 == 0 && L.epi.oB % 8 == 0 &&
+                  reinterpret_cast<uintptr_t>(L.epi.out) % 16 == 0) ? 1 : 0;
+    if (const char* env = getenv("VPK_EPI_TMA")) P.lean_tma = P.lean_tma && atoi(env) != 0;
+    P.stage_bytes = P.lean_tma ? 2u * 128u * static_cast<unsigned>(cn) * 2u : 0u;
+    reserve_smem += P.stage_bytes;
+  }
   if (L.epi.gn_sums != nullptr && L.epi.gn_group_size < 0) {
     VPK_REQUIRE(P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.epi.proj_n == 0 && L.epi.res == nullptr,
                 "halo plan: fused LayerNorm statistics need the lean BIAS_ACT epilogue");
@@ -1121,7 +1309,7 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   sb = std::max(4, std::min(24, sb));
   while (sb > 2 && sb * P.b_slot_bytes + 2 * P.a_slot_bytes > avail) --sb;
   if (P.resident) sb = 1;
-  if (reserve_smem > 0 && !((sb >= 2 || P.resident) && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail)) {
+  if (reserve_smem > P.stage_bytes && !((sb >= 2 || P.resident) && sb * P.b_slot_bytes + 2 * P.a_slot_bytes <= avail)) {
     P.SA = P.SB = 0;          // sequence plan that does not fit: the caller falls back to per-step launches
     P.smem_bytes = 0;
     return;
@@ -1172,6 +1360,16 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(L.K_pad) * 2};
   cuuint32_t box[2] = {64, b_rows};
   encode(&P.bmap, 2, L.wpacked, dims, strides, box, "packed weights");
+  if (P.lean_tma) {
+    const int cn = P.tileN / L.G;
+    cuuint64_t od[4] = {static_cast<cuuint64_t>(cn), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),
+                        static_cast<cuuint64_t>(L.B)};
+    cuuint64_t os[3] = {static_cast<cuuint64_t>(L.epi.oX) * 2, static_cast<cuuint64_t>(L.epi.oY) * 2,
+                        static_cast<cuuint64_t>(L.epi.oB) * 2};
+    cuuint32_t ob[4] = {static_cast<cuuint32_t>(std::min(cn, 32)), static_cast<cuuint32_t>(kTW), static_cast<cuuint32_t>(kTH), 1};
+    encode(&P.omap, 4, L.epi.out, od, os, ob, "staged output tile",
+           cn == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_64B);
+  }
 }
 
 namespace {

@@ -55,6 +55,12 @@ struct alignas(64) HaloPlan {
                                //    M tiles; every weight tile is fetched from L2 once per cluster (TMA multicast)
   int fast_epi;                // lean compile-time-specialised epilogue (epilogue_tc.cuh) usable for this launch
   int roll;                    // ConvLSTM epilogue with a whole tile of operands in flight (lstm_ops_load / lstm_finish)
+  CUtensorMap omap;            // lean_tma: (C, W, H, B) view of the output, box (min(C, 32), 8, 16, 1), 64B / 32B swizzle
+  int lean_tma;                // lean epilogue that stages the 16-bit tile in shared memory and writes it with bulk tensor
+                               // stores (one thread, full lines) instead of 32-line st.global instructions
+  unsigned stage_bytes;        // shared memory in front of the rings for two staged output tiles
+  int lean;                    // bias + (leaky) ReLU + 16-bit store only: the short straight-line epilogue loop (the per-tile
+                               // instruction stream of ONE warp, not bandwidth, bounds the epilogue of narrow layers)
   int debug;
   // ---- sequence mode (conv_halo_kernel MODE 4): ONE launch runs seq_T timesteps of a ConvLSTM layer, persistent CTAs,
   //      the cell state c resident in shared memory across the timesteps, a grid-wide barrier between timesteps ----
