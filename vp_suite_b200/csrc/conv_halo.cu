@@ -701,34 +701,25 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     bool lean_done = false;
     if constexpr (KIND == EPI_BIAS_ACT && MODE == 1) {
       if (P.lean) {
-        // ---- bias + slope activation + 16-bit store, nothing else (stage convs, sub-pixel deconv parities, DCGAN tails).
-        // An epilogue warp is ONE instruction stream: at ~7 cycles per dependent instruction the ~340 instructions per tile
-        // of the general loop (tile decode by division, per-chunk predicates, activation switch, 64-bit address chains) took
-        // 2.6 k cycles -- longer than the 24 MMAs of an N = 96, K = 384 tile.  Here: tile coordinates advance incrementally,
-        // the chunk count and the activation are compile-time, all TMEM reads of a tile sit behind one wait. ----
+        // ---- bias + slope activation + 16-bit store (+ GroupNorm partial sums), nothing else: stage convs, sub-pixel deconv
+        // parities, the DCGAN convs.  An epilogue warp is ONE instruction stream: at ~7 cycles per dependent instruction the
+        // ~340 instructions per tile of the general loop (tile decode by division, per-chunk predicates, activation switch,
+        // 64-bit address chains) took 2.6 k cycles -- longer than the 24 MMAs of an N = 96, K = 384 tile -- and its
+        // per-thread st.global (32 lines per instruction) stalled the warps another 2.3 k.  Here: tile decode by
+        // multiply-high, chunk count and activation compile-time, all TMEM reads of a tile behind one wait, and (TMA) the
+        // tile staged in shared memory and written by bulk tensor stores. ----
         lean_done = true;
         const EpiParams& E = P.L.epi;
-        const int tpi = P.tiles_x * P.tiles_y;
-        const int mstep = nunits * csize;
-        int b, ty, tx;
-        {
-          const int mt = m_tile_of(unit0);
-          b = mt / tpi;
-          const int rem = mt - b * tpi;
-          ty = rem / P.tiles_x;
-          tx = rem - ty * P.tiles_x;
-        }
-        const int db = mstep / tpi;
-        const int dty = (mstep - db * tpi) / P.tiles_x;
-        const int dtx = (mstep - db * tpi) - dty * P.tiles_x;
-        const uint32_t sb = ptx::smem_u32(s_bias) + static_cast<uint32_t>(half * 32);
+        const uint32_t tpi = static_cast<uint32_t>(P.tiles_x * P.tiles_y);
+        const uint32_t sb0 = ptx::smem_u32(s_bias) + static_cast<uint32_t>(half * 32);
         bf16* const outp = static_cast<bf16*>(E.out) + half * 8;
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * 8);
         const float slope = E.act == ACT_LEAKY ? 0.2f : 1.f;
-        auto run = [&](auto nj_c, auto relu_c, auto tma_c) {
+        auto run = [&](auto nj_c, auto relu_c, auto tma_c, auto stats_c) {
           constexpr int NJ = decltype(nj_c)::value;          // this warp's 8-channel chunks: channels half * 8 + 16 j
           constexpr bool RELU = decltype(relu_c)::value;
           constexpr bool TMA = decltype(tma_c)::value;
+          constexpr bool STATS = decltype(stats_c)::value;   // per-group sum / sum of squares for a following GroupNorm
           // TMA: the tile is staged as NJ / 2 sub-tiles of [128 positions][32 channels] (64 B rows, 64B swizzle; one
           // [128][16] sub-tile with 32 B rows and the 32B swizzle when NJ == 1) -- conflict-free 16 B st.shared
           constexpr int SUBS = NJ == 1 ? 1 : NJ / 2;
@@ -738,9 +729,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
           if constexpr (TMA) srow = NJ == 1 ? static_cast<uint32_t>(row * 32) : static_cast<uint32_t>(row * 64);
           const uint32_t sxor = NJ == 1 ? static_cast<uint32_t>((row >> 2) & 1) : static_cast<uint32_t>((row >> 1) & 3);
           for (int t = unit0; t < total; t += nunits, ++iter) {
+            // (M unit, N tile) -> (sequence, tile row, tile column, first channel): exact multiply-high divisions (plan)
+            uint32_t mu = static_cast<uint32_t>(t), nt = 0;
+            if (P.n_tiles != 1) {
+              mu = __umulhi(static_cast<uint32_t>(t), P.magic_nt);
+              nt = static_cast<uint32_t>(t) - mu * static_cast<uint32_t>(P.n_tiles);
+            }
+            const uint32_t mt = MC ? ((mu * 2 + prank) * 2 + rank) : (mu * (PAIR ? 2u : 1u) + rank);
+            const int b = static_cast<int>(__umulhi(mt, P.magic_tpi));
+            const uint32_t rem = mt - static_cast<uint32_t>(b) * tpi;
+            const int ty = static_cast<int>(__umulhi(rem, P.magic_tx));
+            const int tx = static_cast<int>(rem) - ty * P.tiles_x;
+            const int ch_base = static_cast<int>(nt) * Cn;
             const int x = tx * kTW + rx, y = ty * kTH + ry;
             const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B) && !(P.debug & 1);
-            bf16* o = outp + (b * E.oB + y * E.oY + x * E.oX);
+            bf16* o = outp + (b * E.oB + y * E.oY + x * E.oX) + ch_base;
+            const uint32_t sb = sb0 + static_cast<uint32_t>(ch_base * 4);
             const int acc = iter & 1;
 #ifdef VPK_TRACE
             const long long l_t0 = clock64();
@@ -775,6 +779,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
             }
             const uint32_t sbuf = s_stage + static_cast<uint32_t>(iter & 1) * (SUBS * kSubBytes) + srow;
+            float gs16[STATS ? 16 : 1];
+            if constexpr (STATS) {
+#pragma unroll
+              for (int q = 0; q < 16; ++q) gs16[q] = 0.f;
+            }
 #pragma unroll
             for (int j = 0; j < NJ; ++j) {
               const float bj[8] = {bv[j][0].x, bv[j][0].y, bv[j][0].z, bv[j][0].w, bv[j][1].x, bv[j][1].y, bv[j][1].z, bv[j][1].w};
@@ -795,6 +804,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               } else {
                 if (valid) st_bf16x8(o + 16 * j, v);
               }
+              if constexpr (STATS) {       // positions outside the image contribute zeros
+                if (!valid) {
+#pragma unroll
+                  for (int k = 0; k < 8; ++k) v[k] = 0.f;
+                }
+                const int gsz = E.gn_group_size;
+                if (gsz == 2) gn_accum<2>(gs16, j, v);
+                else if (gsz == 4) gn_accum<4>(gs16, j, v);
+                else gn_accum<8>(gs16, j, v);
+              }
             }
             if constexpr (TMA) {
               ptx::fence_proxy_async_smem();               // this thread's st.shared -> visible to the bulk store
@@ -805,7 +824,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
 #pragma unroll
                 for (int u = 0; u < SUBS; ++u)
                   ptx::tma_store_4d(&P.omap, s_stage + static_cast<uint32_t>(iter & 1) * (SUBS * kSubBytes) + u * kSubBytes,
-                                    u * 32, tx * kTW, ty * kTH, b);
+                                    ch_base + u * 32, tx * kTW, ty * kTH, b);
                 ptx::bulk_commit();
               }
             } else {
@@ -816,22 +835,44 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 else ptx::mbar_arrive(tempty + 8 * acc);
               }
             }
+            if constexpr (STATS) {
+              const int gsz = E.gn_group_size;
+              const float tot = gn_warp_reduce16(gs16, lane);
+              const int vi = gn_lane_value(lane), pairi = vi >> 1, gpc = 8 / gsz;
+              const int kk = pairi / gpc, jj = pairi - kk * gpc;
+              const int chg = ch_base + half * 8 + 16 * kk;       // first channel of that chunk
+              if ((lane & 1) == 0 && b < P.L.B && kk < NJ) {
+                const int slot = E.gn_slot0 + static_cast<int>(rem) * 4 + quad;
+                E.gn_sums[((static_cast<long long>(b) * E.gn_nslots + slot) * (E.C / gsz) + chg / gsz + jj) * 2 + (vi & 1)] = tot;
+              }
+            }
 #ifdef VPK_TRACE
             e_body += clock64() - l_t2;
 #endif
-            tx += dtx;
-            if (tx >= P.tiles_x) { tx -= P.tiles_x; ++ty; }
-            ty += dty;
-            if (ty >= P.tiles_y) { ty -= P.tiles_y; ++b; }
-            b += db;
           }
           if (issuer) ptx::bulk_wait0();                   // all staged tiles are in global memory before the CTA exits
         };
         auto run_r = [&](auto nj_c, auto tma_c) {
-          if (E.act == ACT_RELU) run(nj_c, std::true_type{}, tma_c);
-          else run(nj_c, std::false_type{}, tma_c);
+          if (E.act == ACT_RELU) run(nj_c, std::true_type{}, tma_c, std::false_type{});
+          else run(nj_c, std::false_type{}, tma_c, std::false_type{});
         };
-        if (P.lean_tma) {
+        const bool stats = E.gn_sums != nullptr;             // (the plan admits group statistics with <= 64 channels per tile)
+        if (stats && P.lean_tma) {
+          switch (Cn >> 4) {
+            case 1: run(std::integral_constant<int, 1>{}, std::false_type{}, std::true_type{}, std::true_type{}); break;
+            case 2: run(std::integral_constant<int, 2>{}, std::false_type{}, std::true_type{}, std::true_type{}); break;
+            case 4: run(std::integral_constant<int, 4>{}, std::false_type{}, std::true_type{}, std::true_type{}); break;
+            default: __trap();
+          }
+        } else if (stats) {
+          switch (Cn >> 4) {
+            case 1: run(std::integral_constant<int, 1>{}, std::false_type{}, std::false_type{}, std::true_type{}); break;
+            case 2: run(std::integral_constant<int, 2>{}, std::false_type{}, std::false_type{}, std::true_type{}); break;
+            case 3: run(std::integral_constant<int, 3>{}, std::false_type{}, std::false_type{}, std::true_type{}); break;
+            case 4: run(std::integral_constant<int, 4>{}, std::false_type{}, std::false_type{}, std::true_type{}); break;
+            default: __trap();
+          }
+        } else if (P.lean_tma) {
           switch (Cn >> 4) {
             case 1: run_r(std::integral_constant<int, 1>{}, std::true_type{}); break;
             case 2: run_r(std::integral_constant<int, 2>{}, std::true_type{}); break;
@@ -1241,9 +1282,19 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   if (const char* env = getenv("VPK_EPI_ROLL")) P.roll = P.roll && atoi(env) != 0;
   {
     const int cn = P.tileN / L.G, nj = cn / 16;
+    const bool gn = L.epi.gn_sums != nullptr;
+    const int gs = L.epi.gn_group_size;
+    const unsigned long long tpi = static_cast<unsigned long long>(P.tiles_x) * P.tiles_y;
+    // exact floor(n / d) = umulhi(n, ceil(2^32 / d)) needs n * d < 2^32 for every n the epilogue divides
+    const unsigned long long nmax = static_cast<unsigned long long>(m_tiles + 4) * P.n_tiles;
+    const bool magic_ok = nmax * std::max<unsigned long long>(tpi, static_cast<unsigned long long>(P.n_tiles)) < (1ull << 32);
+    auto magic = [](unsigned long long d) { return static_cast<unsigned>(((1ull << 32) + d - 1) / d); };
+    P.magic_nt = P.n_tiles > 1 ? magic(static_cast<unsigned long long>(P.n_tiles)) : 0u;
+    P.magic_tpi = tpi > 1 ? magic(tpi) : 0u;
+    P.magic_tx = P.tiles_x > 1 ? magic(static_cast<unsigned long long>(P.tiles_x)) : 0u;
     P.lean = (P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.G == 1 && L.epi.proj_n == 0 && L.epi.res == nullptr &&
-              L.epi.gn_sums == nullptr && !L.epi.out_f32 && P.n_tiles == 1 && cn % 16 == 0 && cn <= L.epi.C &&
-              (nj == 1 || nj == 2 || nj == 3 || nj == 4 || nj == 6) &&
+              !L.epi.out_f32 && cn % 16 == 0 && L.N_pad == L.epi.C && magic_ok && tpi > 1 && P.tiles_x > 1 &&
+              (gn ? (gs > 0 && nj <= 4 && L.epi.act != ACT_RELU) : (nj == 1 || nj == 2 || nj == 3 || nj == 4 || nj == 6)) &&
               (L.epi.act == ACT_NONE || L.epi.act == ACT_LEAKY || L.epi.act == ACT_RELU)) ? 1 : 0;
     if (const char* env = getenv("VPK_EPI_LEAN")) P.lean = P.lean && atoi(env) != 0;
     // staged bulk-tensor stores: 16 / 32 / 64 / 96 channels (whole 32-channel sub-tiles), 16-byte aligned strides
@@ -1295,6 +1346,22 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   // SM's shared memory lets the next kernel's CTAs become resident under PDL and overlap their set-up -- measured on
   // cfg 4 / cfg 2 it is SLOWER (10.37 vs 9.70 ms, 10.45 vs 10.02 ms): the shallower activation ring costs more than the
   // hidden set-up saves.
+  if (P.lean_tma && !P.resident) {
+    // the staging buffers come out of the ring budget: streamed-weight layers that are bound by their activation ring
+    // (stride-2 stage convs: one TMA box per tap and output row) keep the ring instead -- an activation ring of two
+    // slots cost more than the stores saved (cfg 5 encoder.stage3: 83 -> 100 us)
+    auto depth_a = [&](unsigned res) {
+      const unsigned av = kMaxSmem - res - fixed;
+      int b = std::max(4, std::min(24, static_cast<int>(av * 6 / 10 / P.b_slot_bytes)));
+      while (b > 2 && b * P.b_slot_bytes + 2 * P.a_slot_bytes > av) --b;
+      return static_cast<int>((av - b * P.b_slot_bytes) / P.a_slot_bytes);
+    };
+    if (depth_a(reserve_smem) < 3 && depth_a(reserve_smem - P.stage_bytes) >= 3) {
+      reserve_smem -= P.stage_bytes;
+      P.stage_bytes = 0;
+      P.lean_tma = 0;
+    }
+  }
   VPK_REQUIRE(reserve_smem % 1024 == 0 && reserve_smem + 96 * 1024 <= kMaxSmem, "halo plan: shared-memory reserve too large");
   unsigned budget = kMaxSmem - reserve_smem;
   if (const char* env = getenv("VPK_HALO_SMEM_CAP")) {
@@ -1362,7 +1429,7 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   encode(&P.bmap, 2, L.wpacked, dims, strides, box, "packed weights");
   if (P.lean_tma) {
     const int cn = P.tileN / L.G;
-    cuuint64_t od[4] = {static_cast<cuuint64_t>(cn), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),
+    cuuint64_t od[4] = {static_cast<cuuint64_t>(L.epi.C), static_cast<cuuint64_t>(L.W), static_cast<cuuint64_t>(L.H),
                         static_cast<cuuint64_t>(L.B)};
     cuuint64_t os[3] = {static_cast<cuuint64_t>(L.epi.oX) * 2, static_cast<cuuint64_t>(L.epi.oY) * 2,
                         static_cast<cuuint64_t>(L.epi.oB) * 2};

@@ -59,6 +59,7 @@ struct alignas(64) HaloPlan {
   int lean_tma;                // lean epilogue that stages the 16-bit tile in shared memory and writes it with bulk tensor
                                // stores (one thread, full lines) instead of 32-line st.global instructions
   unsigned stage_bytes;        // shared memory in front of the rings for two staged output tiles
+  unsigned magic_nt, magic_tpi, magic_tx;   // ceil(2^32 / d) for d = n_tiles, tiles_x * tiles_y, tiles_x (lean epilogue)
   int lean;                    // bias + (leaky) ReLU + 16-bit store only: the short straight-line epilogue loop (the per-tile
                                // instruction stream of ONE warp, not bandwidth, bounds the epilogue of narrow layers)
   int debug;
