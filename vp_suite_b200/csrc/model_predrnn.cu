@@ -160,8 +160,9 @@ class PredRnnV2 : public StLstmModelBase {
     //   2  A * W_hi + A * W_lo                     split weights: 1.5e-2 on three sequences, 2.1e-2 worst of 256
     //   3  A_hi * W_hi + A_hi * W_lo + A_lo * W_hi  split weights and activations (~22 bits each)
     // LayerNorm renormalises every conv output, so the rollout amplifies operand rounding ~100x over 19 steps (even the
-    // fp32 mode is 6e-5 from the reference at the end): only the three-product form keeps every sequence of a
-    // 256-sequence batch inside north_star's 2e-2.  The low parts of x / h / m are written by their producers.
+    // fp32 mode is 6e-5 from the reference at the end): only split weights everywhere AND split activations for conv_x
+    // keep every sequence of a 256-sequence batch inside north_star's 2e-2 (conv_h / conv_m run form 2, see
+    // stlstm_model.h).  The low parts of x / h are written by their producers.
     int ln_products = 1;
     if (ln && adt == DT_F16) {
       ln_products = 3;
@@ -172,11 +173,9 @@ class PredRnnV2 : public StLstmModelBase {
     char* xp_lo = lo3 ? static_cast<char*>(arena.alloc(px * cp * esz * ctx)) : nullptr;
     float* xp32 = lo3 ? static_cast<float*>(arena.alloc(px * cp * sizeof(float))) : nullptr;
     std::vector<void*> hb_lo(2 * L, nullptr);
-    void* m_act_lo = nullptr;
     void* xgen_lo = nullptr;
     if (lo3) {
       for (int i = 0; i < 2 * L; ++i) hb_lo[i] = arena.alloc(px * C * esz);
-      m_act_lo = arena.alloc(px * C * esz);
       xgen_lo = arena.alloc(px * cp * esz);
     }
     // fused decoupling loss (tcgen05 path): per-warp partial slots + one term per (step, layer, sample)
@@ -218,7 +217,6 @@ class PredRnnV2 : public StLstmModelBase {
       add_memset(prog, memb[2 * (L - 1) + 1], px * 2 * C * esz, "zero_mem");   // m seen by layer 0 at t = 0
       if (ln) add_memset(prog, m_act, px * C * esz, "zero_m_act");
       if (lo3) {
-        add_memset(prog, m_act_lo, px * C * esz, "zero_m_act_lo");
         for (int i = 0; i < L; ++i) add_memset(prog, hb_lo[2 * i], px * C * esz, "zero_h_lo");
       }
     }
@@ -256,7 +254,7 @@ class PredRnnV2 : public StLstmModelBase {
                           : hb_lo[2 * (i - 1) + par[i - 1]];
           lo.h_in = hb_lo[2 * i + par[i]];
           lo.h_out = hb_lo[2 * i + (par[i] ^ 1)];
-          lo.m_act = m_act_lo;
+          lo.m_act = nullptr;      // conv_m runs two products (split weights): no low part of m needed
         }
         const int cin = (i == 0) ? cp : C;
         // memory comes from the previous layer of this step, or from the top layer of the previous step

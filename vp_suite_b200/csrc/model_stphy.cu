@@ -161,7 +161,6 @@ class StPhyModel : public StLstmModelBase {
     float* opart = static_cast<float*>(arena.alloc(pxl * C * sizeof(float)));
     void* mem = arena.alloc(pxl * 2 * C * esz);
     void* m_act = arena.alloc(pxl * C * esz);
-    void* m_act_lo = lo3 ? arena.alloc(pxl * C * esz) : nullptr;
     void* dcb = arena.alloc(pxl * C * esz);
     void* dmb = arena.alloc(pxl * C * esz);
     float* xraw = static_cast<float*>(arena.alloc(pxl * 7 * C * sizeof(float)));
@@ -216,7 +215,6 @@ class StPhyModel : public StLstmModelBase {
       }
       add_memset(prog, mstate, pxl * C * sizeof(float), "zero_m");
       add_memset(prog, m_act, pxl * C * esz, "zero_m_act");
-      if (lo3) add_memset(prog, m_act_lo, pxl * C * esz, "zero_m_act_lo");
       add_memset(prog, f1n, pxl * Cp * esz, "zero_f1n_pad");
     }
     auto fanout = [&](const float* src, bool norm, const char* name) {      // fp32 -> the operand copies of next_input
@@ -309,7 +307,7 @@ class StPhyModel : public StLstmModelBase {
           lo.x = nxt_lo;
           lo.h_in = hb_lo[2 * i + spar[i]];
           lo.h_out = hb_lo[2 * i + (spar[i] ^ 1)];
-          lo.m_act = m_act_lo;
+          lo.m_act = nullptr;      // conv_m runs two products (split weights): no low part of m needed
         }
         float* h32 = f32 ? static_cast<float*>(hb[2 * i + (spar[i] ^ 1)]) : sth32[i];
         lo.h_out32 = f32 ? nullptr : sth32[i];
