@@ -408,6 +408,11 @@ SWITCHES = [
     ("VPK_LN_PRODUCTS=2", "predrnn_ln_3x32", False),
     ("VPK_LN_PRODUCTS=1", "predrnn_ln_1x64", False),
     ("VPK_HALO_RESIDENT=0", "phy_1x64", True),
+    # bias + activation convs: general epilogue loop / per-thread stores instead of the staged bulk tensor stores
+    ("VPK_EPI_LEAN=0", "ef_3x32", True),
+    ("VPK_EPI_LEAN=0", "phy_1x64", True),
+    ("VPK_EPI_TMA=0", "ef_1x64", True),
+    ("VPK_EPI_TMA=0", "phy_3x64", True),
     # small batches use the sub-pixel deconv by default: the per-parity form adds the same products in the same order
     ("VPK_SUBPIX=0", "ef_3x32", True),
     ("VPK_SUBPIX=0", "ef_1x64", True),
@@ -458,3 +463,33 @@ def test_persistent_sequence_program_is_bit_identical(manifest, name, batch, ctx
     errs = _frame_errs(b.cpu().numpy(), ref.numpy())
     assert errs[0] <= BF16_TOL_FIRST and max(errs) <= BF16_TOL_LAST, errs
     assert torch.equal(host, b.cpu())
+
+
+# image sizes whose latents do not fill whole 8 x 16 tiles (ragged tiles in x and / or y, single-tile latents): the bulk
+# tensor stores clip at the tensor-map bounds, the per-thread paths by predicate
+RAGGED = [("convlstm-shi", (1, 40, 24), 3, 3, 4, {}), ("convlstm-shi", (3, 24, 56), 2, 2, 3, {}),
+          ("phy", (3, 24, 40), 3, 2, 3, {}), ("predrnn-pp", (1, 24, 40), 2, 3, 3, {}),
+          ("predrnn-pp", (1, 40, 24), 2, 2, 2, {"layer_norm": True})]
+
+
+@pytest.mark.parametrize("key,img,batch,ctx,pred,kw", RAGGED)
+def test_ragged_image_sizes_vs_oracle(key, img, batch, ctx, pred, kw):
+    import vp_suite_b200 as V
+    dev = _cuda()
+    t_in = ctx + (pred if key == "predrnn-pp" else 0)
+    x = synth_frames(batch, t_in, *img, seed=91)
+    ref = None
+    for precision, tol_first, tol_last in (("fp32", FP32_TOL, FP32_TOL), ("bf16", BF16_TOL_FIRST, BF16_TOL_LAST)):
+        m = V.MODEL_CLASSES[key](dev, img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0], precision=precision,
+                                 **kw).eval()
+        # (the gains of the golden cases: enough signal through the stack for the comparison to mean something)
+        sd = synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=5,
+                              gain=2.5 if key == "convlstm-shi" else 1.5)
+        m.load_state_dict(sd)
+        if ref is None:
+            with torch.no_grad():
+                ref = OM.FORWARDS[key](sd, x, pred, cfg=dict(m.config))[0].numpy()
+        with torch.no_grad():
+            got = m(x.to(dev), pred_frames=pred)[0].cpu().numpy()
+        errs = _frame_errs(got, ref)
+        assert errs[0] <= tol_first and max(errs) <= tol_last, f"{key} {img} {precision}: {errs}"
