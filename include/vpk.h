@@ -79,12 +79,15 @@ typedef struct vpk_model_desc {
   int32_t use_cuda_graph;    /* 1: capture the per-microbatch launch program into a CUDA graph and replay it   */
   /* action-conditional variants (VPModel.action_conditional / action_size, base_model.py:33-34): predrnn-pp
    * (predrnn_v2.py:65-90: stride-2 input / action convs, ActionConditionalSpatioTemporalLSTMCell, output deconvs) and phy
-   * (model_blocks/phydnet.py:44-55, 153-155: frame / hidden action convs in PhyCell, action channels into the ConvLSTM) */
+   * (model_blocks/phydnet.py:44-55, 153-155: frame / hidden action convs in PhyCell, action channels into the ConvLSTM);
+   * st-phy (st_phy.py:48-56, 142-150: Linear + (5,1) / (1,5) convs to the cells' action tensor, PhyCell action convs) */
   int32_t action_conditional;
   int32_t action_size;
   int32_t residual_on_action_conv;   /* predrnn-pp (predrnn_v2.py:46, 213-218) */
   /* trajgru (ef_traj_gru.py:47-61): flows per recurrent block; the i2h kernel sizes travel in enc_rnn_k / dec_rnn_k */
   int32_t enc_rnn_L[3], dec_rnn_L[3];
+  /* st-phy, action-conditional (st_phy.py:32, 48-56): channels of the Linear-inflated action map */
+  int32_t inflated_action_dim;
 } vpk_model_desc;
 
 /* Replaces: MODEL_CLASSES[key](device, **model_kwargs)  (vp_suite/vpsuite.py:170; base_model.py:38-69). */

@@ -260,6 +260,28 @@ def run_stphy(manifest):
     print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
 
 
+def run_stphy_ac(manifest):
+    """ST-Phy with action_conditional=True (st_phy.py:48-56, 142-150; ActionConditionalSpatioTemporalLSTMCell with
+    layer_norm=True and PhyCell's action convs per layer), eval -> stphy_ac_3x64.npz."""
+    classes = ref_shim.load_reference()
+    name, img, b, t, p, wseed, xseed, gain, a_size = "stphy_ac_3x64", (3, 64, 64), 2, 3, 3, 38, 208, 1.5, 3
+    torch.manual_seed(0)
+    m = classes["st-phy"]("cpu", img_shape=img, action_size=a_size, action_conditional=True, tensor_value_range=[0.0, 1.0]).eval()
+    shp = shapes_of(m)
+    m.load_state_dict(synth_state_dict(shp, wseed, gain))
+    x = synth_frames(b, t, *img, seed=xseed)
+    actions = synth_actions(b, t + p - 1, a_size, seed=xseed + 1)
+    with torch.no_grad():
+        pred, aux = m(x, pred_frames=p, actions=actions)
+    assert aux is None
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), pred=pred.numpy())
+    manifest["models"][name] = dict(key="st-phy", img_shape=list(img), batch=b, context=t, pred=p, wseed=wseed, xseed=xseed,
+                                    gain=gain, shapes=shp, action_size=a_size, aseed=xseed + 1,
+                                    model_kwargs={"action_conditional": True, "action_size": a_size},
+                                    pred_std=float(pred.std()), pred_mean=float(pred.mean()))
+    print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
+
+
 def run_trajgru(manifest):
     """EF-TrajGRU (models/precipitation_nowcasting/ef_traj_gru.py), eval -> trajgru_1x64.npz, trajgru_3x32.npz."""
     classes = ref_shim.load_reference()
@@ -278,7 +300,8 @@ def run_trajgru(manifest):
         print(f"{name}: pred {tuple(pred.shape)} mean {pred.mean():.4f} std {pred.std():.4f}")
 
 
-INCREMENTAL = {"trajgru": run_trajgru, "blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac, "stphy": run_stphy}
+INCREMENTAL = {"trajgru": run_trajgru, "blocks_ac": run_blocks_ac, "measures": run_measures, "models_ac": run_models_ac, "stphy": run_stphy,
+               "stphy_ac": run_stphy_ac}
 
 
 def main():
@@ -305,6 +328,7 @@ def main():
     run_measures(manifest)
     run_models_ac(manifest)
     run_stphy(manifest)
+    run_stphy_ac(manifest)
     run_trajgru(manifest)
     with open(os.path.join(OUT, "manifest.json"), "w") as f:
         json.dump(manifest, f, indent=1, sort_keys=True)

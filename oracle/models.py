@@ -352,14 +352,18 @@ def autoencoder_decode(z, sd, out_hw, prefix="autoencoder.decoder."):
 
 
 def stphy_forward(sd, x, pred_frames, cfg=None, actions=None):
-    """STPhy.forward in eval mode, action_conditional=False (models/st_phy.py:90-181).  Per step: the encoded frame (context
+    """STPhy.forward in eval mode (models/st_phy.py:90-181).  Per step: the encoded frame (context
     steps) or the previous x_gen feeds EVERY layer (``next_input`` is not updated inside the layer loop, :139-158); layer i
     runs its PhyCell_Cell on (next_input, phy_h[i]) and its LayerNorm ST-LSTM cell on (next_input, h[i], c[i], shared
     st_memory), and merges them with a 1x1 conv over cat[st_h, phy_h] (:158); only the last layer's merge survives as x_gen.
-    Frames are decoded from t = context - 1 on (:160-162).  Losses are training-only: returns (frames, None)."""
+    Frames are decoded from t = context - 1 on (:160-162).  Losses are training-only: returns (frames, None).
+    action_conditional=True (``sd`` holds ``action_inflate.weight``, :48-56, 142-150): the step's action vector goes through a
+    bias-free Linear to an [inflated_action_dim, enc_h, enc_w] map and the SUM of a (5,1) and a (1,5) conv of it is the
+    action tensor of every layer's ActionConditionalSpatioTemporalLSTMCell; the PhyCells get the raw action vector."""
     cfg = {**STPHY_DEFAULTS, **(cfg or {})}
-    if "action_inflate.weight" in sd:
-        raise NotImplementedError("action-conditional st-phy is not restated")
+    ac = "action_inflate.weight" in sd
+    if ac and (actions is None or actions.shape[-1] != sd["action_inflate.weight"].shape[1]):     # st_phy.py:100-103
+        raise ValueError("Given actions are None or of the wrong size!")
     L, Cs = cfg["num_layers"], cfg["st_cell_channels"]
     b, ctx = x.shape[:2]
     enc0 = autoencoder_encode(x[:, 0], sd)
@@ -371,9 +375,18 @@ def stphy_forward(sd, x, pred_frames, cfg=None, actions=None):
     x_gen, outs = None, []
     for t in range(ctx + pred_frames - 1):
         nxt = autoencoder_encode(x[:, t], sd) if t < ctx else x_gen
+        if ac:
+            a_t = actions[:, t]
+            amap = F.linear(a_t, sd["action_inflate.weight"]).view(b, -1, eh, ew)
+            infl = F.conv2d(amap, sd["action_conv_h.weight"], padding=(2, 0)) + F.conv2d(amap, sd["action_conv_w.weight"], padding=(0, 2))
         for i in range(L):
-            phy_h[i] = B.phycell_step(nxt, phy_h[i], B._sub(sd, f"phycell_list.{i}."))
+            phy_h[i] = B.phycell_step(nxt, phy_h[i], B._sub(sd, f"phycell_list.{i}."), action=a_t if ac else None)
             pre = f"st_cell_list.{i}."
+            if ac:
+                st_h[i], st_c[i], memory, _, _ = B.stlstm_ac_step(nxt, st_h[i], st_c[i], memory, infl, B._sub(sd, pre))
+                x_gen = F.conv2d(torch.cat([st_h[i], phy_h[i]], dim=1), sd[f"hidden_conv_list.{i}.weight"],
+                                 sd.get(f"hidden_conv_list.{i}.bias"))
+                continue
             ln = {k: (sd[f"{pre}conv_{k}.1.weight"], sd[f"{pre}conv_{k}.1.bias"]) for k in "xhmo"}
             st_h[i], st_c[i], memory, _, _ = B.stlstm_step(
                 nxt, st_h[i], st_c[i], memory, sd[pre + "conv_x.0.weight"], sd[pre + "conv_h.0.weight"],

@@ -138,24 +138,39 @@ def phydnet_shapes(img_shape, cfg=None):
 
 
 def stphy_shapes(img_shape, cfg=None):
-    """models/st_phy.py:38-83 (non action-conditional), model_blocks/enc.py:14-98."""
+    """models/st_phy.py:38-83, model_blocks/enc.py:14-98; action_conditional=True adds action_inflate / action_conv_h /
+    action_conv_w (:48-56), the ActionConditionalSpatioTemporalLSTMCell layout (conv biases, conv_a;
+    model_blocks/predrnn.py:97-139) and PhyCell's two 1x1 action convs (model_blocks/phydnet.py:44-48)."""
     cfg = {**STPHY_DEFAULTS, **(cfg or {})}
     c, h, w = img_shape
     L, C, hid, kp = cfg["num_layers"], cfg["st_cell_channels"], cfg["phycell_channels"], cfg["phycell_kernel_size"][0]
     eh = ((h - 5) // 2 + 1 - 3) // 2 + 1 - 2
     ew = ((w - 5) // 2 + 1 - 3) // 2 + 1 - 2
+    ac = bool(cfg.get("action_conditional"))
+    a = cfg.get("action_size", 0)
     out = {}
     for name, shp in (("encoder.conv1", (32, c, 5, 5)), ("encoder.conv2", (64, 32, 3, 3)), ("encoder.mean_layer", (C, 64, 3, 3)),
                       ("decoder.fc1", (C, C, 1, 1)), ("decoder.conv1", (C, 64, 6, 6)), ("decoder.conv2", (64, 32, 6, 6)),
                       ("decoder.conv3", (32, c, 5, 5))):
         out[f"autoencoder.{name}.weight"] = shp
         out[f"autoencoder.{name}.bias"] = (shp[1],) if "decoder.conv" in name else (shp[0],)
+    if ac:
+        ia = cfg.get("inflated_action_dim", 3)
+        out["action_inflate.weight"] = (ia * eh * ew, a)
+        out["action_conv_h.weight"] = (C, ia, 5, 1)
+        out["action_conv_w.weight"] = (C, ia, 1, 5)
     for i in range(L):
-        for nm, mult, ci in (("x", 7, C), ("h", 4, C), ("m", 3, C), ("o", 1, 2 * C)):
+        convs = (("x", 7, C), ("h", 4, C), ("a", 4, C), ("m", 3, C), ("o", 1, 2 * C)) if ac else \
+                (("x", 7, C), ("h", 4, C), ("m", 3, C), ("o", 1, 2 * C))
+        for nm, mult, ci in convs:
             out[f"st_cell_list.{i}.conv_{nm}.0.weight"] = (mult * C, ci, 5, 5)
+            if ac:
+                out[f"st_cell_list.{i}.conv_{nm}.0.bias"] = (mult * C,)
             out[f"st_cell_list.{i}.conv_{nm}.1.weight"] = (mult * C, eh, ew)
             out[f"st_cell_list.{i}.conv_{nm}.1.bias"] = (mult * C, eh, ew)
         out[f"st_cell_list.{i}.conv_last.weight"] = (C, 2 * C, 1, 1)
+        if ac:
+            out[f"st_cell_list.{i}.conv_last.bias"] = (C,)
     for i in range(L):
         pre = f"phycell_list.{i}."
         out[pre + "F.conv1.weight"] = (hid, C, kp, kp)
@@ -166,6 +181,10 @@ def stphy_shapes(img_shape, cfg=None):
         out[pre + "F.conv2.bias"] = (C,)
         out[pre + "convgate.weight"] = (C, 2 * C, 3, 3)
         out[pre + "convgate.bias"] = (C,)
+        if ac:
+            for nm in ("frame_action_conv", "hidden_action_conv"):
+                out[pre + nm + ".weight"] = (C, C + a, 1, 1)
+                out[pre + nm + ".bias"] = (C,)
     for i in range(L):
         out[f"hidden_conv_list.{i}.weight"] = (C, 2 * C, 1, 1)
         if i < L - 1:

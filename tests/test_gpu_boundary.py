@@ -65,7 +65,7 @@ def test_reference_model_test_protocol(key, precision):
         assert e1 <= 5e-3 and e5[0] <= 5e-3 and max(e5) <= 2e-2, (e1, e5)
 
 
-@pytest.mark.parametrize("key", ["convlstm-shi", "predrnn-pp", "phy"])
+@pytest.mark.parametrize("key", ["convlstm-shi", "predrnn-pp", "phy", "st-phy"])
 def test_reference_model_test_protocol_with_actions(key):
     """tests/test_models.py:39-60 of the reference: action_conditional = CAN_HANDLE_ACTIONS, actions passed to every model
     (models that cannot handle them ignore the keyword), shapes of pred_1 / forward -- plus values against the oracle."""

@@ -49,14 +49,14 @@ def _actions(meta):
     return synth_actions(meta["batch"], meta["context"] + meta["pred"] - 1, meta["action_size"], seed=meta["aseed"])
 
 
-AC_CASES = ["predrnn_ac_1x64", "predrnn_acln_3x32", "phy_ac_3x64"]
+AC_CASES = ["predrnn_ac_1x64", "predrnn_acln_3x32", "phy_ac_3x64", "stphy_ac_3x64"]
 
 
 @pytest.mark.parametrize("name", AC_CASES)
 @pytest.mark.parametrize("precision,backend", [("fp32", "auto"), ("bf16", "auto"), ("bf16", "simt")])
 def test_action_conditional_models_match_reference_golden(manifest, name, precision, backend):
     """model(x, pred_frames, actions=a) of the action-conditional predrnn-pp (predrnn_v2.py:65-90, 178-221; layer_norm off
-    and on) and phy (model_blocks/phydnet.py:44-55, 153-155) against vectors the reference produced; device and host
+    and on) , phy (model_blocks/phydnet.py:44-55, 153-155) and st-phy (st_phy.py:48-56, 142-150) against vectors the reference produced; device and host
     entries; the reference's error for missing / wrongly sized actions."""
     meta = manifest["models"][name]
     m, sd = _build(meta["key"], meta, precision=precision, backend=backend)

@@ -12,7 +12,7 @@ KW = dict(action_size=0, tensor_value_range=[0.0, 1.0])
 
 @pytest.mark.parametrize("name", ["ef_1x64", "ef_3x32", "predrnn_1x64", "predrnn_3x32", "phy_3x64", "phy_1x64",
                                   "branch_1x64", "predrnn_ln_1x64", "predrnn_ln_3x32", "predrnn_ac_1x64",
-                                  "predrnn_acln_3x32", "phy_ac_3x64", "stphy_3x64", "trajgru_1x64", "trajgru_3x32"])
+                                  "predrnn_acln_3x32", "phy_ac_3x64", "stphy_3x64", "stphy_ac_3x64", "trajgru_1x64", "trajgru_3x32"])
 def test_state_dict_layout_matches_reference(manifest, name):
     meta = manifest["models"][name]
     m = V.MODEL_CLASSES[meta["key"]]("cpu", img_shape=tuple(meta["img_shape"]), **{**KW, **(meta.get("model_kwargs") or {})})
@@ -86,7 +86,8 @@ def test_ef_loads_cuda_built_checkpoint_without_peepholes(manifest):
     ("predrnn-pp", (1, 64, 64), {"action_conditional": True, "action_size": 3}),
     ("predrnn-pp", (3, 32, 32), {"action_conditional": True, "action_size": 4, "layer_norm": True}),
     ("phy", (3, 64, 64), {"action_conditional": True, "action_size": 3}),
-    ("st-phy", (3, 64, 64), {}), ("trajgru", (1, 64, 64), {})])
+    ("st-phy", (3, 64, 64), {}), ("st-phy", (3, 64, 64), {"action_conditional": True, "action_size": 3}),
+    ("trajgru", (1, 64, 64), {})])
 def test_same_seed_gives_the_reference_init_and_config(key, img, extra):
     ref_cls = ref_shim.load_reference()[key]
     kw = {**KW, **extra}

@@ -38,7 +38,7 @@ def test_model_rollout_matches_reference(manifest, name):
         assert aux is None
 
 
-@pytest.mark.parametrize("name", ["predrnn_ac_1x64", "predrnn_acln_3x32", "phy_ac_3x64"])
+@pytest.mark.parametrize("name", ["predrnn_ac_1x64", "predrnn_acln_3x32", "phy_ac_3x64", "stphy_ac_3x64"])
 def test_action_conditional_rollout_matches_reference(manifest, name):
     """model(x, pred_frames, actions=a) of the reference's action-conditional predrnn-pp (incl. layer_norm) and phy."""
     meta, sd, x = _case(manifest, name)

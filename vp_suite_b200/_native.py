@@ -39,6 +39,7 @@ class ModelDesc(C.Structure):
         ("max_microbatch", C.c_int32), ("use_cuda_graph", C.c_int32),
         ("action_conditional", C.c_int32), ("action_size", C.c_int32), ("residual_on_action_conv", C.c_int32),
         ("enc_rnn_L", C.c_int32 * 3), ("dec_rnn_L", C.c_int32 * 3),
+        ("inflated_action_dim", C.c_int32),
     ]
 
 

@@ -913,6 +913,45 @@ __global__ void inflate_actions_kernel(const float* __restrict__ actions, long l
   }
 }
 
+// ST-Phy's action tensor (models/st_phy.py:48-56, 146-148): amap = Linear(action_t) viewed as [IA][H][W] (bias-free, weight wl
+// [IA*H*W][a]), out = conv(5,1)(amap) + conv(1,5)(amap) (zero padding 2, weights wh [C][IA][5], ww [C][IA][5]), stored NHWC as
+// out[t][b][y][x][c].  One block per (t, b): the map is built in shared memory, then one thread per output value.  fp32
+// arithmetic in the reference's summation structure (Linear dot; each conv's taps; the sum of the two convs).
+template <typename T>
+__global__ void __launch_bounds__(256) stphy_action_tensor_kernel(const float* __restrict__ actions, long long bstride, int a,
+                                                                  const float* __restrict__ wl, const float* __restrict__ wh,
+                                                                  const float* __restrict__ ww, T* __restrict__ out, int B, int H,
+                                                                  int W, int C, int IA) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  extern __shared__ float s_map[];                     // [IA][H][W]
+  const int b = blockIdx.x % B, t = blockIdx.x / B;
+  const int HW = H * W;
+  const float* av = actions + b * bstride + static_cast<long long>(t) * a;
+  for (int i = threadIdx.x; i < IA * HW; i += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < a; ++k) acc = fmaf(wl[static_cast<long long>(i) * a + k], av[k], acc);
+    s_map[i] = acc;
+  }
+  __syncthreads();
+  T* o = out + (static_cast<long long>(t) * B + b) * HW * C;
+  for (int i = threadIdx.x; i < HW * C; i += blockDim.x) {
+    const int c = i % C, p = i / C;
+    const int y = p / W, x = p - y * W;
+    float sh = 0.f, sw = 0.f;
+    for (int ia = 0; ia < IA; ++ia) {
+      const float* m = s_map + ia * HW;
+#pragma unroll
+      for (int d = 0; d < 5; ++d) {
+        const int yy = y + d - 2, xx = x + d - 2;
+        if (yy >= 0 && yy < H) sh = fmaf(wh[(c * IA + ia) * 5 + d], m[yy * W + x], sh);
+        if (xx >= 0 && xx < W) sw = fmaf(ww[(c * IA + ia) * 5 + d], m[y * W + xx], sw);
+      }
+    }
+    o[i] = to_act<T>(sh + sw);
+  }
+}
+
 // out = T(x + y) elementwise; x of type TX, y fp32 (or absent)
 template <typename TX, typename T>
 __global__ void add_to_act_kernel(const TX* __restrict__ x, const float* __restrict__ y, T* __restrict__ out, long long n) {
@@ -1245,6 +1284,17 @@ void launch_split_f16(const float* in, void* hi, void* lo, long long n, int num_
   launch_pdl(split_f16_kernel, dim3(grid_for(n / 4, 256, num_sms)), dim3(256), 0, stream, in, static_cast<__half*>(hi),
              static_cast<__half*>(lo), n / 4);
   VPK_CUDA(cudaGetLastError());
+}
+
+void launch_stphy_action_tensor(const float* actions, long long bstride, int a, const float* wl, const float* wh, const float* ww,
+                                void* out, int dtype, int B, int T, int H, int W, int C, int IA, cudaStream_t stream) {
+  VPK_REQUIRE(a >= 1 && B > 0 && T > 0 && H > 0 && W > 0 && C > 0 && IA >= 1, "stphy_action_tensor: bad shape");
+  const size_t smem = static_cast<size_t>(IA) * H * W * sizeof(float);
+  VPK_REQUIRE(smem <= 48 * 1024, "stphy_action_tensor: encoded map too large");
+  const dim3 g(static_cast<unsigned>(B) * T);
+  if (dtype == DT_F32) launch_pdl(stphy_action_tensor_kernel<float>, g, dim3(256), smem, stream, actions, bstride, a, wl, wh, ww, static_cast<float*>(out), B, H, W, C, IA);
+  else if (dtype == DT_F16) launch_pdl(stphy_action_tensor_kernel<__half>, g, dim3(256), smem, stream, actions, bstride, a, wl, wh, ww, static_cast<__half*>(out), B, H, W, C, IA);
+  else launch_pdl(stphy_action_tensor_kernel<__nv_bfloat16>, g, dim3(256), smem, stream, actions, bstride, a, wl, wh, ww, static_cast<__nv_bfloat16*>(out), B, H, W, C, IA);
 }
 
 void launch_inflate_actions(const float* actions, long long bstride, int a, void* out, int dtype, int B, int T, int HW,

@@ -76,6 +76,10 @@ void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num
 // out (activation type) [T][B][HW][a_pad], channels a..a_pad-1 zero (the action vector inflated to the frame size)
 void launch_inflate_actions(const float* actions, long long bstride, int a, void* out, int dtype, int B, int T, int HW,
                             int a_pad, int num_sms, cudaStream_t stream);
+// ST-Phy, action-conditional (st_phy.py:48-56, 146-148): actions fp32 [B, *, a] -> out (activation type) [T][B][H][W][C] =
+// conv(5,1)(amap) + conv(1,5)(amap) with amap = Linear(action_t) as [IA][H][W]; wl [IA*H*W][a], wh / ww [C][IA][5] (device fp32)
+void launch_stphy_action_tensor(const float* actions, long long bstride, int a, const float* wl, const float* wh, const float* ww,
+                                void* out, int dtype, int B, int T, int H, int W, int C, int IA, cudaStream_t stream);
 // TrajGRU (model_blocks/traj_gru.py): bilinear warps of the fp32 state h [B][H][W][C] by the L flow pairs in
 // flows [B][H][W][fpix] (pair l at channels 2l, 2l + 1) -> out (activation type) [B][H][W][L * C]; and the GRU gate update
 // from the raw i2h (nullable) / h2h pre-activations [P][3C] (fp32): h_out fp32 [P][C] + an activation-type copy

@@ -673,98 +673,6 @@ class PredRnnV2 : public StLstmModelBase {
 
   // One ActionConditionalSpatioTemporalLSTMCell step (model_blocks/predrnn.py:142-169): raw convs with bias (x, h, a, m),
   // optional per-sample LayerNorm statistics, the action-conditional gate kernel, conv_o / conv_last, the output kernel.
-  void add_ac_cell(Program& prog, const std::string& pre, int B, const void* x, const void* h_in, void* h_out, float* c,
-                   float* m, float* opart, void* mem, void* m_act, void* dc, void* dm, const void* action, float* xraw,
-                   float* hraw, float* araw, float* mraw, float* oraw, float* lraw, float* part, const ActInfo& act,
-                   bool measure, cudaStream_t stream, bool ln, int products) {
-    int oh, ow;
-    const char* halo_env = getenv("VPK_TC_HALO");
-    const bool fuse_stats = ln && act.dtype != DT_F32 && backend == 0 && getenv("VPK_NO_FUSED_LN_STATS") == nullptr &&
-                            (halo_env == nullptr || atoi(halo_env) != 0);
-    auto raw_conv = [&](const std::string& name, const void* in, int ci, int co, int kk, const std::string& key, float* out,
-                        float* stat, int nslots, bool precise) {
-      ConvArgs a{pre + name, B, rh, rw, ci, co, kk, 1, kk / 2, in, hp(pre + key + "weight"), hp(pre + key + "bias"), ACT_NONE, out};
-      a.out_f32_dense = true;
-      if (precise && products == 2) a.w_split = true;
-      ConvSpec sp = conv_spec(a, act, &oh, &ow);
-      sp.is_gate_gemm = true;
-      if (stat != nullptr) {
-        EpiParams& e = sp.phases[0].epi;
-        e.gn_sums = stat;
-        e.gn_group_size = -1;
-        e.gn_slot0 = 0;
-        e.gn_nslots = nslots;
-      }
-      add_conv(prog, sp, measure, stream, act.dtype);
-    };
-    const int nsx = fuse_stats ? ln_slots(7 * C) : kLnSlices, nsh = fuse_stats ? ln_slots(4 * C) : kLnSlices,
-              nsm = fuse_stats ? ln_slots(3 * C) : kLnSlices, nso = fuse_stats ? ln_slots(C) : kLnSlices;
-    // regions X, H, M, A in `part` (the non-fused statistics launch writes X, H, M contiguously with kLnSlices each)
-    float* px_ = part;
-    float* ph_ = px_ + static_cast<size_t>(B) * nsx * 2;
-    float* pm_ = ph_ + static_cast<size_t>(B) * nsh * 2;
-    float* pa_ = pm_ + static_cast<size_t>(B) * nsm * 2;
-    VPK_REQUIRE(static_cast<size_t>(B) * (static_cast<size_t>(nsx) + 2 * nsh + nsm) * 2 <= lnpart_floats && nso <= nsx,
-                "LayerNorm statistics regions exceed their buffer");
-    raw_conv("conv_x.ac.", x, C, 7 * C, k, "conv_x.0.", xraw, fuse_stats ? px_ : nullptr, nsx, true);
-    raw_conv("conv_h.ac.", h_in, C, 4 * C, k, "conv_h.0.", hraw, fuse_stats ? ph_ : nullptr, nsh, true);
-    raw_conv("conv_m.ac.", m_act, C, 3 * C, k, "conv_m.0.", mraw, fuse_stats ? pm_ : nullptr, nsm, true);
-    raw_conv("conv_a.ac.", action, C, 4 * C, k, "conv_a.0.", araw, fuse_stats ? pa_ : nullptr, nsh, true);
-    const int HW = rh * rw, CC = C, ns = num_sms, dt = act.dtype;
-    if (!measure) {
-      if (ln && !fuse_stats) {
-        LnStatsArgs sa{{xraw, hraw, mraw}, {7ll * C * HW, 4ll * C * HW, 3ll * C * HW}, 3, B, part};
-        LnStatsArgs sb{{araw, nullptr, nullptr}, {4ll * C * HW, 0, 0}, 1, B, pa_};
-        Op op;
-        op.name = pre + "ln_stats_xhma";
-        op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_ln_stats(sa, s);
-          launch_ln_stats(sb, s);
-        };
-        prog.body.push_back(std::move(op));
-      }
-      auto lp = [&](const std::string& key, int kc) -> const float* { return ln ? ln_param(pre + key, kc, stream) : nullptr; };
-      StLnGatesArgs ga{xraw, hraw, mraw, {px_, ph_, pm_}, {nsx, nsh, nsm},
-                       lp("conv_x.1.weight", 7 * C), lp("conv_x.1.bias", 7 * C), lp("conv_h.1.weight", 4 * C),
-                       lp("conv_h.1.bias", 4 * C), lp("conv_m.1.weight", 3 * C), lp("conv_m.1.bias", 3 * C),
-                       c, m, mem, m_act, dc, dm, opart, B, HW, CC, dt, 1.0f};
-      ga.A = araw;
-      ga.part_a = pa_;
-      ga.nslots_a = nsh;
-      ga.ga = lp("conv_a.1.weight", 4 * C);
-      ga.ba = lp("conv_a.1.bias", 4 * C);
-      ga.use_ln = ln ? 1 : 0;
-      Op og;
-      og.name = pre + "ac_gates";
-      og.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_gates(ga, ns, s); };
-      prog.body.push_back(std::move(og));
-    }
-    raw_conv("conv_o.ac.", mem, 2 * C, C, k, "conv_o.0.", oraw, fuse_stats ? px_ : nullptr, nso, false);
-    {
-      ConvArgs a{pre + "conv_last.ac.", B, rh, rw, 2 * C, C, 1, 1, 0, mem, hp(pre + "conv_last.weight"), hp(pre + "conv_last.bias"),
-                 ACT_NONE, lraw};
-      a.out_f32_dense = true;
-      ConvSpec sp = conv_spec(a, act, &oh, &ow);
-      sp.is_gate_gemm = true;
-      add_conv(prog, sp, measure, stream, act.dtype);
-    }
-    if (!measure) {
-      if (ln && !fuse_stats) {
-        LnStatsArgs so{{oraw, nullptr, nullptr}, {1ll * C * HW, 0, 0}, 1, B, part};
-        Op op;
-        op.name = pre + "ln_stats_o";
-        op.fn = [=](cudaStream_t s, const RunCtx&) { launch_ln_stats(so, s); };
-        prog.body.push_back(std::move(op));
-      }
-      StLnOutArgs oa{oraw, lraw, px_, nso, ln ? ln_param(pre + "conv_o.1.weight", C, stream) : nullptr,
-                     ln ? ln_param(pre + "conv_o.1.bias", C, stream) : nullptr, opart, h_out, B, HW, CC, dt};
-      oa.use_ln = ln ? 1 : 0;
-      Op oo;
-      oo.name = pre + "ac_out";
-      oo.fn = [=](cudaStream_t s, const RunCtx&) { launch_stlstm_ln_out(oa, ns, s); };
-      prog.body.push_back(std::move(oo));
-    }
-  }
 
  private:
   int p = 4, L = 3, cp = 16, hp_ = 16, wp_ = 16;

@@ -1,4 +1,4 @@
-// st-phy: ST-Phy rollout, non action-conditional, eval mode (reference: models/st_phy.py:90-181).
+// st-phy: ST-Phy rollout, eval mode, with and without actions (reference: models/st_phy.py:90-181).
 // A hybrid of the two families already on the kernel path: per layer one PhyCell_Cell (model_blocks/phydnet.py:49-62,
 // phycell.h) and one SpatioTemporalLSTMCell with layer_norm=True (model_blocks/predrnn.py:24-40, 57-83; the raw-conv +
 // statistics + fused-gate pipeline of stlstm_model.h), merged by a 1x1 conv over cat[st_h, phy_h]; an Autoencoder of
@@ -8,6 +8,12 @@
 // layer reads that same next_input (the reference does not update it inside the layer loop, st_phy.py:139-158); layer i
 // advances phy_h[i] and (h[i], c[i], shared st_memory) and overwrites x_gen with its merge, so the last layer's merge is the
 // step's x_gen.  Frames are decoded from t = context - 1 on.  Losses are training-only: forward returns (frames, None).
+//
+// action_conditional (st_phy.py:48-56, 142-150): the step's action vector goes through a bias-free Linear to an
+// [inflated_action_dim, enc_h, enc_w] map; the sum of a (5,1) and a (1,5) conv of it is the action tensor of every layer's
+// ActionConditionalSpatioTemporalLSTMCell (layer_norm=True; stlstm_model.h: add_ac_cell) -- computed for all steps in one
+// pre-op launch (it depends on the call's actions only) -- and every PhyCell first sends cat[frame, action] and
+// cat[hidden, action] through its own 1x1 convs (model_blocks/phydnet.py:50-55; fp32 CUDA-core convs as in model_phydnet.cu).
 //
 // Operand types in 16-bit mode: the LayerNorm ST-LSTM convs run on fp16 (three products, stlstm_model.h), the PhyCell on
 // bf16, the autoencoder convs on FP16 with fp32 outputs (the encoder ends in an L2 normalisation along W of ReLU outputs:
@@ -36,7 +42,10 @@ class StPhyModel : public StLstmModelBase {
  public:
   explicit StPhyModel(const vpk_model_desc& d) : StLstmModelBase(d) {
     VPK_REQUIRE(d.img_c > 0 && d.img_h > 0 && d.img_w > 0, "bad img_shape");
-    VPK_REQUIRE(!d.action_conditional, "the native st-phy rollout covers the non action-conditional model");
+    ac = d.action_conditional != 0;
+    a_sz = ac ? d.action_size : 0;
+    ia = d.inflated_action_dim > 0 ? d.inflated_action_dim : 3;
+    VPK_REQUIRE(!ac || (a_sz > 0 && a_sz <= 8), "action-conditional st-phy needs 1 <= action_size <= 8");
     L = d.num_layers;
     C = d.num_hidden[0];                 // st_cell_channels
     k = 5;                               // the ST cells are built with filter_size=5 (st_phy.py:61)
@@ -75,16 +84,24 @@ class StPhyModel : public StLstmModelBase {
     declare("autoencoder.decoder.conv2.bias", {32});
     declare("autoencoder.decoder.conv3.weight", {32, c, 5, 5});
     declare("autoencoder.decoder.conv3.bias", {c});
+    if (ac) {
+      declare("action_inflate.weight", {ia * rh * rw, a_sz});
+      declare("action_conv_h.weight", {C, ia, 5, 1});
+      declare("action_conv_w.weight", {C, ia, 1, 5});
+    }
     for (int i = 0; i < L; ++i) {
       const std::string s = "st_cell_list." + std::to_string(i) + ".";
-      const std::pair<const char*, std::pair<int, int>> convs[4] = {{"conv_x", {7, C}}, {"conv_h", {4, C}}, {"conv_m", {3, C}},
-                                                                    {"conv_o", {1, 2 * C}}};
-      for (const auto& cv : convs) {
+      const std::pair<const char*, std::pair<int, int>> convs[5] = {{"conv_x", {7, C}}, {"conv_h", {4, C}}, {"conv_m", {3, C}},
+                                                                    {"conv_o", {1, 2 * C}}, {"conv_a", {4, C}}};
+      for (int q = 0; q < (ac ? 5 : 4); ++q) {
+        const auto& cv = convs[q];
         declare(s + cv.first + ".0.weight", {cv.second.first * C, cv.second.second, k, k});
+        if (ac) declare(s + cv.first + ".0.bias", {cv.second.first * C});
         declare(s + cv.first + ".1.weight", {cv.second.first * C, rh, rw});
         declare(s + cv.first + ".1.bias", {cv.second.first * C, rh, rw});
       }
       declare(s + "conv_last.weight", {C, 2 * C, 1, 1});
+      if (ac) declare(s + "conv_last.bias", {C});
       const std::string p = "phycell_list." + std::to_string(i) + ".";
       declare(p + "F.conv1.weight", {hid, C, kp, kp});
       declare(p + "F.conv1.bias", {hid});
@@ -94,6 +111,12 @@ class StPhyModel : public StLstmModelBase {
       declare(p + "F.conv2.bias", {C});
       declare(p + "convgate.weight", {C, 2 * C, 3, 3});
       declare(p + "convgate.bias", {C});
+      if (ac) {
+        declare(p + "frame_action_conv.weight", {C, C + a_sz, 1, 1});
+        declare(p + "frame_action_conv.bias", {C});
+        declare(p + "hidden_action_conv.weight", {C, C + a_sz, 1, 1});
+        declare(p + "hidden_action_conv.bias", {C});
+      }
       declare("hidden_conv_list." + std::to_string(i) + ".weight", {C, 2 * C, 1, 1});
       if (i < L - 1) declare("hidden_conv_list." + std::to_string(i) + ".bias", {C});     // st_phy.py:68-70
     }
@@ -102,6 +125,8 @@ class StPhyModel : public StLstmModelBase {
 
  protected:
   int default_microbatch() const override { return 128; }
+  // one action per step (st_phy.py:96-103, 142)
+  int action_steps_needed(int t_in, int pred) const override { return ac ? t_in + pred - 1 : 0; }
 
   std::vector<float> vec(const std::string& key) const { return params.at(key).data; }
 
@@ -124,6 +149,7 @@ class StPhyModel : public StLstmModelBase {
       if (const char* env = getenv("VPK_LN_PRODUCTS")) products = std::max(1, std::min(3, atoi(env)));
       if (((C + 63) / 64) * products * k * k > kMaxSteps) products = 1;
     }
+    if (ac) products = std::min(products, 2);       // the action-conditional cell runs split weights (as in predrnn-pp)
     const bool lo3 = products == 3;
     const bool pad8 = !f32 && backend == 0 && c <= 8;
     const int cs = pad8 ? 8 : c;
@@ -168,7 +194,8 @@ class StPhyModel : public StLstmModelBase {
     float* mraw = static_cast<float*>(arena.alloc(pxl * 3 * C * sizeof(float)));
     float* oraw = static_cast<float*>(arena.alloc(pxl * C * sizeof(float)));
     float* lraw = static_cast<float*>(arena.alloc(pxl * C * sizeof(float)));
-    const size_t slots = std::max<size_t>(3 * kLnSlices, static_cast<size_t>(ln_slots(7 * C)) + ln_slots(4 * C) + ln_slots(3 * C));
+    float* araw = ac ? static_cast<float*>(arena.alloc(pxl * 4 * C * sizeof(float))) : nullptr;
+    const size_t slots = std::max<size_t>(4 * kLnSlices, static_cast<size_t>(ln_slots(7 * C)) + 2 * ln_slots(4 * C) + ln_slots(3 * C));
     lnpart_floats = static_cast<size_t>(B) * slots * 2;
     float* lnpart = static_cast<float*>(arena.alloc(lnpart_floats * sizeof(float)));
     // PhyCell
@@ -180,6 +207,15 @@ class StPhyModel : public StLstmModelBase {
       hp_act[2 * i] = arena.alloc(pxl * C * esz);
       hp_act[2 * i + 1] = arena.alloc(pxl * C * esz);
     }
+    // action-conditional: the cells' action tensor of every step, the spatially inflated raw actions (PhyCell), and the
+    // outputs of PhyCell's two 1x1 action convs
+    const int a_pad = 8;
+    void* atens = ac ? arena.alloc(static_cast<size_t>(steps) * pxl * C * esz) : nullptr;
+    float* act32 = ac ? static_cast<float*>(arena.alloc(static_cast<size_t>(steps) * pxl * a_pad * sizeof(float))) : nullptr;
+    float* fa32 = ac ? static_cast<float*>(arena.alloc(pxl * C * 4)) : nullptr;
+    float* ha32 = ac ? static_cast<float*>(arena.alloc(pxl * C * 4)) : nullptr;
+    void* fa_act = ac ? (f32 ? static_cast<void*>(fa32) : arena.alloc(pxl * C * esz)) : nullptr;
+    void* ha_act = ac ? (f32 ? static_cast<void*>(ha32) : arena.alloc(pxl * C * esz)) : nullptr;
     float* f1raw = static_cast<float*>(arena.alloc(pxl * Cp * 4));
     void* f1n = arena.alloc(pxl * Cp * esz);
     // decoder
@@ -206,6 +242,21 @@ class StPhyModel : public StLstmModelBase {
         else launch_frames_to_nhwc(rc.x, frames, fdt, B, t_in, c, h, w, ns, s);
       };
       prog.pre.push_back(std::move(pre));
+      if (ac) {
+        const float* wl = dev_f32("action_inflate.weight", vec("action_inflate.weight"), stream);
+        const float* wh = dev_f32("action_conv_h.weight", vec("action_conv_h.weight"), stream);
+        const float* ww = dev_f32("action_conv_w.weight", vec("action_conv_w.weight"), stream);
+        const int asz = a_sz, ia_ = ia, rh_ = rh, rw_ = rw, CC = C, HW = rh * rw;
+        Op inf;
+        inf.name = "action_tensor";
+        inf.fn = [=](cudaStream_t s, const RunCtx& rc) {
+          VPK_REQUIRE(rc.actions != nullptr && rc.action_steps >= steps, "Given actions are None or of the wrong size!");
+          const long long bs = static_cast<long long>(rc.action_steps) * asz;
+          launch_stphy_action_tensor(rc.actions, bs, asz, wl, wh, ww, atens, adt, B, steps, rh_, rw_, CC, ia_, s);
+          launch_inflate_actions(rc.actions, bs, asz, act32, DT_F32, B, steps, HW, a_pad, ns, s);
+        };
+        prog.pre.push_back(std::move(inf));
+      }
       for (int i = 0; i < L; ++i) {
         add_memset(prog, hb[2 * i], pxl * C * esz, "zero_h");
         if (lo3) add_memset(prog, hb_lo[2 * i], pxl * C * esz, "zero_h_lo");
@@ -262,9 +313,56 @@ class StPhyModel : public StLstmModelBase {
         const std::string p = "phycell_list." + std::to_string(i) + ".";
         const void* h_act = hp_act[2 * i + ppar[i]];
         void* h_act_new = hp_act[2 * i + (ppar[i] ^ 1)];
-        PhyCellArgs pa{p, B, rh, rw, C, hid, kp, nxt_cell, h_act, h_act_new, hp_master[i], htilde[i], f1raw, f1n,
+        const void* xin = nxt_cell;
+        const float* h_res = nullptr;
+        if (ac) {
+          // frame = frame_action_conv(cat[frame, action]), hidden = hidden_action_conv(cat[hidden, action]): fp32 1x1 convs
+          // on the CUDA cores straight from the fp32 next_input / state (model_blocks/phydnet.py:50-55, as in model_phydnet.cu)
+          const float* a32 = act32 + static_cast<size_t>(t) * pxl * a_pad;
+          auto action_conv = [&](const std::string& key, const float* src, float* out32, void* out_act) {
+            ConvSpec s1;
+            s1.name = p + key + ".";
+            s1.B = B;
+            s1.G = 1;
+            s1.C = C;
+            WeightRef wr;
+            wr.w = hp(p + key + ".weight");
+            wr.O = C;
+            wr.I = C + a_sz;
+            wr.KH = wr.KW = 1;
+            s1.wrefs.push_back(wr);
+            BiasRef br;
+            br.b = hp(p + key + ".bias");
+            s1.biases.push_back(br);
+            ConvInput i0{make_view(src, rh, rw, C), 0, 0};
+            ConvInput i1{make_view(a32, rh, rw, a_pad), 0, C};
+            i1.wc_count = a_sz;
+            int oh_, ow_;
+            lower_conv(s1, 1, 1, 0, {i0, i1}, rh, rw, 4, &oh_, &ow_);
+            EpiParams& e = s1.phases[0].epi;
+            e.kind = EPI_BIAS_ACT;
+            e.act = ACT_NONE;
+            e.out_f32 = 1;
+            dense_out(e, out32, rh, rw, C);
+            add_conv(prog, s1, measure, stream, DT_F32);
+            if (!measure && !f32) {
+              const long long n = static_cast<long long>(pxl) * C;
+              Op op;
+              op.name = p + key + ".cast";
+              op.fn = [=](cudaStream_t s, const RunCtx&) { launch_add_to_act(out32, DT_F32, nullptr, out_act, cdt, n, ns, s); };
+              prog.body.push_back(std::move(op));
+            }
+          };
+          action_conv("frame_action_conv", nxt32, fa32, fa_act);
+          action_conv("hidden_action_conv", hp_master[i], ha32, ha_act);
+          xin = fa_act;
+          h_act = ha_act;
+          h_res = ha32;
+        }
+        PhyCellArgs pa{p, B, rh, rw, C, hid, kp, xin, h_act, h_act_new, hp_master[i], htilde[i], f1raw, f1n,
                        hp(p + "F.conv1.weight"), hp(p + "F.conv1.bias"), hp(p + "F.conv2.weight"), hp(p + "F.conv2.bias"),
                        hp(p + "convgate.weight"), hp(p + "convgate.bias")};
+        pa.h_res = h_res;
         std::vector<ConvSpec> specs = phycell_specs(pa, ca);
         add_conv(prog, specs[0], measure, stream, cdt);
         const int f_groups = stphy_group_norm_divisor(hid);
@@ -275,7 +373,7 @@ class StPhyModel : public StLstmModelBase {
             const float* w2_ = dev_f32(p + "F.conv2.weight", vec(p + "F.conv2.weight"), stream);
             const float* b2_ = dev_f32(p + "F.conv2.bias", vec(p + "F.conv2.bias"), stream);
             const int HW = rh * rw, hid_ = hid, CC = C;
-            const float* hm = hp_master[i];
+            const float* hm = h_res ? h_res : hp_master[i];
             float* ht = htilde[i];
             Op op;
             op.name = p + "F.tail (GroupNorm + conv2 + h)";
@@ -311,6 +409,11 @@ class StPhyModel : public StLstmModelBase {
         }
         float* h32 = f32 ? static_cast<float*>(hb[2 * i + (spar[i] ^ 1)]) : sth32[i];
         lo.h_out32 = f32 ? nullptr : sth32[i];
+        if (ac)
+          add_ac_cell(prog, sp, B, nxt_hi, hb[2 * i + spar[i]], hb[2 * i + (spar[i] ^ 1)], cb[i], mstate, opart, mem, m_act, dcb, dmb,
+                      static_cast<const char*>(atens) + static_cast<size_t>(t) * pxl * C * esz, xraw, hraw, araw, mraw, oraw, lraw,
+                      lnpart, aa, measure, stream, true, products, f32 ? nullptr : sth32[i]);
+        else
         add_ln_cell(prog, sp, B, C, nxt_hi, hb[2 * i + spar[i]], hb[2 * i + (spar[i] ^ 1)], cb[i], mstate, opart, mem, m_act, dcb,
                     dmb, xraw, hraw, mraw, oraw, lraw, lnpart, aa, measure, stream, products, lo);
         spar[i] ^= 1;
@@ -396,6 +499,8 @@ class StPhyModel : public StLstmModelBase {
 
  private:
   int L = 3, hid = 49, kp = 7;
+  bool ac = false;             // action_conditional (st_phy.py:48-56)
+  int a_sz = 0, ia = 3;        // action_size, inflated_action_dim
   int h1 = 0, w1 = 0, h2 = 0, w2 = 0, d1h = 0, d1w = 0, d2h = 0, d2w = 0;
 };
 

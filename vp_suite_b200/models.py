@@ -639,8 +639,9 @@ class EF_TrajGRU(NativeRollout, VPModel):
 
 class STPhy(NativeRollout, VPModel):
     """models/st_phy.py:16-181: Autoencoder + per layer one PhyCell_Cell and one LayerNorm ST-LSTM cell merged by a 1x1 conv.
-    The native rollout covers the non action-conditional model in eval mode (losses are training-only there: ``forward``
-    returns ``(frames, None)``)."""
+    With action_conditional=True (st_phy.py:48-56, 142-150) the action vector is inflated by a Linear + a (5,1) and a (1,5)
+    conv to the action tensor of the ActionConditionalSpatioTemporalLSTMCells, and the PhyCells take the raw action.
+    The native rollout covers eval mode (losses are training-only there: ``forward`` returns ``(frames, None)``)."""
     NAME = "ST-Phy"
     CAN_HANDLE_ACTIONS = True
 
@@ -657,13 +658,12 @@ class STPhy(NativeRollout, VPModel):
     def __init__(self, device, **model_kwargs):
         super().__init__(device, **model_kwargs)
         self._native_init()
-        if self.action_conditional:
-            raise NotImplementedError("the native st-phy rollout covers the non action-conditional model")
         C, c = self.st_cell_channels, self.img_c
+        ac, a = bool(self.action_conditional), int(self.action_size)
         self.dim_st_hidden = [C] * self.num_layers                              # st_phy.py:41-42
         self.dim_phy_hidden = [self.phycell_channels] * self.num_layers
-        from .model_blocks import SpatioTemporalLSTMCell                       # (model_blocks imports this module)
-        self.recurrent_cell = SpatioTemporalLSTMCell                           # st_phy.py:46 (shows up in `config`)
+        from .model_blocks import SpatioTemporalLSTMCell, ActionConditionalSpatioTemporalLSTMCell   # (model_blocks imports this module)
+        self.recurrent_cell = ActionConditionalSpatioTemporalLSTMCell if ac else SpatioTemporalLSTMCell   # st_phy.py:46-49 (in `config`)
         # Autoencoder (model_blocks/enc.py:14-98): same construction order as the reference for same-seed init
         self.autoencoder = _Params()
         enc = _Params()
@@ -680,13 +680,21 @@ class STPhy(NativeRollout, VPModel):
         self.enc_h, self.enc_w = (h1 - 3) // 2 + 1 - 2, (w1 - 3) // 2 + 1 - 2   # autoencoder.encoded_shape (st_phy.py:45)
         if ((self.enc_h - 1) * 2 + 6 - 1) * 2 + 6 + 4 != self.img_h or ((self.enc_w - 1) * 2 + 6 - 1) * 2 + 6 + 4 != self.img_w:
             raise AttributeError("image sizes whose decoder output needs the reference's Resize are not supported")
+        if ac:                                                                  # st_phy.py:48-56
+            self.action_inflate = nn.Linear(a, self.inflated_action_dim * self.enc_h * self.enc_w, bias=False)
+            self.action_conv_h = nn.Conv2d(self.inflated_action_dim, C, (5, 1), padding=(2, 0), bias=False)
+            self.action_conv_w = nn.Conv2d(self.inflated_action_dim, C, (1, 5), padding=(0, 2), bias=False)
         st_cells, phycells, hidden_convs = [], [], []
         kp = self.phycell_kernel_size
         for i in range(self.num_layers):                                        # st_phy.py:58-70
             cell = _Params()
-            for name, (o, ci) in (("conv_x", (7 * C, C)), ("conv_h", (4 * C, C)), ("conv_m", (3 * C, C)), ("conv_o", (C, 2 * C))):
-                setattr(cell, name, nn.Sequential(nn.Conv2d(ci, o, 5, 1, 2, bias=False), nn.LayerNorm([o, self.enc_h, self.enc_w])))
-            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
+            # model_blocks/predrnn.py:24-40 / :97-139 (action-conditional: conv biases, conv_a after conv_h)
+            convs = (("conv_x", (7 * C, C)), ("conv_h", (4 * C, C)), ("conv_a", (4 * C, C)), ("conv_m", (3 * C, C)),
+                     ("conv_o", (C, 2 * C))) if ac else \
+                    (("conv_x", (7 * C, C)), ("conv_h", (4 * C, C)), ("conv_m", (3 * C, C)), ("conv_o", (C, 2 * C)))
+            for name, (o, ci) in convs:
+                setattr(cell, name, nn.Sequential(nn.Conv2d(ci, o, 5, 1, 2, bias=ac), nn.LayerNorm([o, self.enc_h, self.enc_w])))
+            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=ac)
             st_cells.append(cell)
             pc = _Params()
             pc.F = nn.Sequential()
@@ -694,6 +702,9 @@ class STPhy(NativeRollout, VPModel):
             pc.F.add_module("bn1", nn.GroupNorm(_gn_divisor(self.phycell_channels), self.phycell_channels))
             pc.F.add_module("conv2", nn.Conv2d(self.phycell_channels, C, (1, 1)))
             pc.convgate = nn.Conv2d(2 * C, C, (3, 3), padding=(1, 1))
+            if ac:                                                              # model_blocks/phydnet.py:44-48
+                pc.frame_action_conv = nn.Conv2d(C + a, C, (1, 1))
+                pc.hidden_action_conv = nn.Conv2d(C + a, C, (1, 1))
             phycells.append(pc)
             hidden_convs.append(nn.Conv2d(2 * C, C, (1, 1), bias=(i < self.num_layers - 1)))
         self.st_cell_list = nn.ModuleList(st_cells)
@@ -712,6 +723,9 @@ class STPhy(NativeRollout, VPModel):
         if self.phycell_kernel_size[0] != self.phycell_kernel_size[1]:
             raise AttributeError("square kernels only")
         d.phycell_kernel_size = self.phycell_kernel_size[0]
+        d.action_conditional = int(bool(self.action_conditional))
+        d.action_size = int(self.action_size) if self.action_conditional else 0
+        d.inflated_action_dim = int(self.inflated_action_dim)
         return d
 
     def _native_key(self, key):
@@ -726,7 +740,8 @@ class STPhy(NativeRollout, VPModel):
         b, t, c, h, w = x.shape
         if (c, h, w) != (self.img_c, self.img_h, self.img_w):
             raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
-        pred, _ = self._native_forward(x, int(pred_frames), t)
+        actions = self._native_actions(kwargs, b, x.device)                    # st_phy.py:98-103
+        pred, _ = self._native_forward(x, int(pred_frames), t, actions=actions)
         return pred, None                                                      # st_phy.py:176-181 (eval)
 
 
