@@ -100,9 +100,11 @@ template <> __device__ __forceinline__ float4 lo_part4<__nv_bfloat16>(float4 v) 
 // LayerNorm affine parameters depend on (position, channel) only, so they are read once per gate group and reused for
 // the whole chunk of samples (they would otherwise be two thirds of the kernel's L2 -> SM traffic: 28 parameter
 // vectors against 14 data vectors per item).  Three passes over the chunk: c group, m group, output-gate part.
+// HBM-bound (11 KB per position and sample): four resident blocks per SM (64 registers, a few spilled words) instead of two
+// (107 registers) put enough loads in flight -- 261 -> 183 us per launch at cfg 3's shape (0.6 of the copy bandwidth).
 constexpr int kGateNB = 8;
 template <typename T>
-__global__ void __launch_bounds__(256) stlstm_ln_gates_kernel(const StLnGatesArgs a) {
+__global__ void __launch_bounds__(256, 4) stlstm_ln_gates_kernel(const StLnGatesArgs a) {
   ptx::pdl_launch_dependents();
   ptx::pdl_wait();
   __shared__ float s_mean[kGateNB][3], s_rstd[kGateNB][3];
