@@ -22,7 +22,6 @@ namespace vpk {
 namespace {
 
 constexpr int kStemThreads = 128;
-constexpr int kStemPX = 4;        // output positions per thread (consecutive x)
 
 template <bool F16> __device__ __forceinline__ void unpack8(const uint4& q, float (&v)[8]) {
   const uint32_t w[4] = {q.x, q.y, q.z, q.w};
@@ -39,7 +38,10 @@ template <bool F16> __device__ __forceinline__ void unpack8(const uint4& q, floa
 }
 
 // x: [B][H][W][8] 16-bit (fp16 if F16IN, else bf16); wsm layout [ky][kx][ci][N] fp32; out: [B][OH][OW][N] fp32 (F32OUT)
-// or bf16.  One thread = kStemPX consecutive output positions of one output row.
+// or bf16.  One thread = PX consecutive output ROWS of one output column; consecutive threads = consecutive columns, so a
+// warp's 16-byte pixel loads cover 512 contiguous bytes (4 lines; stride 2: 8) and its stores 8 lines.  (The first version
+// gave a thread PX consecutive columns -- 16 lines per load, 32 per store; the row-wise form measured 125 -> 118 us on
+// cfg 5's stem, 37 -> 31 us on PhyDNet's: the kernel is bound by FP32 issue / latency at ~0.3 of the FMA peak, not by the LSU.)
 template <int CIN, int N, int STRIDE, bool F16IN, bool F32OUT, int PX>
 __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __restrict__ x, const float* __restrict__ wpk,
                                                                 const float* __restrict__ bias, void* __restrict__ out,
@@ -52,40 +54,39 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
   __syncthreads();
   ptx::pdl_wait();
 
-  constexpr int NCOL = STRIDE * (PX - 1) + 3;
-  const int gx = OW / PX;
-  const long long total = static_cast<long long>(B) * OH * gx;
+  constexpr int NROW = STRIDE * (PX - 1) + 3;             // input rows feeding PX output rows
+  const int gy = (OH + PX - 1) / PX;
+  const long long total = static_cast<long long>(B) * gy * OW;
   for (long long g = blockIdx.x * static_cast<long long>(kStemThreads) + threadIdx.x; g < total;
        g += static_cast<long long>(gridDim.x) * kStemThreads) {
-    const int xg = static_cast<int>(g % gx);
-    const long long r = g / gx;
-    const int oy = static_cast<int>(r % OH);
-    const int b = static_cast<int>(r / OH);
-    const int ox0 = xg * PX;
+    const int ox = static_cast<int>(g % OW);
+    const long long r = g / OW;
+    const int yg = static_cast<int>(r % gy);
+    const int b = static_cast<int>(r / gy);
+    const int oy0 = yg * PX;
     float acc[PX][N];
 #pragma unroll
     for (int p = 0; p < PX; ++p)
 #pragma unroll
       for (int n = 0; n < N; ++n) acc[p][n] = 0.f;
-    const int ix0 = ox0 * STRIDE - 1;
+    const int iy0 = oy0 * STRIDE - 1, ix0 = ox * STRIDE - 1;
 #pragma unroll
-    for (int ky = 0; ky < 3; ++ky) {
-      const int iy = oy * STRIDE - 1 + ky;
-      if (iy < 0 || iy >= H) continue;
-      const uint4* row = x + (static_cast<long long>(b) * H + iy) * W;
-      float v[NCOL][CIN];
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ix = ix0 + kx;
+      const bool okx = ix >= 0 && ix < W;
+      float v[NROW][CIN];
 #pragma unroll
-      for (int c = 0; c < NCOL; ++c) {
-        const int ix = ix0 + c;
+      for (int rr = 0; rr < NROW; ++rr) {
+        const int iy = iy0 + rr;
         uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (ix >= 0 && ix < W) q = __ldg(row + ix);
+        if (okx && iy >= 0 && iy < H) q = __ldg(x + (static_cast<long long>(b) * H + iy) * W + ix);
         float f[8];
         unpack8<F16IN>(q, f);
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) v[c][ci] = f[ci];
+        for (int ci = 0; ci < CIN; ++ci) v[rr][ci] = f[ci];
       }
 #pragma unroll
-      for (int kx = 0; kx < 3; ++kx)
+      for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
         for (int ci = 0; ci < CIN; ++ci) {
           const float4* wr = reinterpret_cast<const float4*>(s_w + ((ky * 3 + kx) * CIN + ci) * N);
@@ -94,7 +95,7 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
             const float4 wv = wr[n4];
 #pragma unroll
             for (int p = 0; p < PX; ++p) {
-              const float a = v[p * STRIDE + kx][ci];
+              const float a = v[p * STRIDE + ky][ci];
               acc[p][4 * n4 + 0] = fmaf(a, wv.x, acc[p][4 * n4 + 0]);
               acc[p][4 * n4 + 1] = fmaf(a, wv.y, acc[p][4 * n4 + 1]);
               acc[p][4 * n4 + 2] = fmaf(a, wv.z, acc[p][4 * n4 + 2]);
@@ -103,9 +104,10 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
           }
         }
     }
-    const long long obase = ((static_cast<long long>(b) * OH + oy) * OW + ox0) * N;
 #pragma unroll
     for (int p = 0; p < PX; ++p) {
+      if (oy0 + p >= OH) break;
+      const long long obase = ((static_cast<long long>(b) * OH + oy0 + p) * OW + ox) * N;
 #pragma unroll
       for (int n = 0; n < N; ++n) {
         float y = acc[p][n] + s_b[n];
@@ -114,12 +116,12 @@ __global__ void __launch_bounds__(kStemThreads) conv_stem_kernel(const uint4* __
         acc[p][n] = y;
       }
       if (F32OUT) {
-        float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + obase + p * N);
+        float4* o = reinterpret_cast<float4*>(static_cast<float*>(out) + obase);
 #pragma unroll
         for (int n4 = 0; n4 < N / 4; ++n4)
           o[n4] = make_float4(acc[p][4 * n4], acc[p][4 * n4 + 1], acc[p][4 * n4 + 2], acc[p][4 * n4 + 3]);
       } else {
-        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + obase + p * N);
+        uint4* o = reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(out) + obase);
 #pragma unroll
         for (int n8 = 0; n8 < N / 8; ++n8) {
           uint4 t;
@@ -254,7 +256,7 @@ inline int grid_for_stem(long long n, int num_sms) {
 template <int N> constexpr int stem_px() { return N >= 32 ? 2 : 4; }
 template <int CIN, int N, int STRIDE> void launch_stem_t(const StemArgs& a, int OH, int OW, int num_sms, cudaStream_t s) {
   constexpr int PX = stem_px<N>();
-  const long long groups = static_cast<long long>(a.B) * OH * (OW / PX);
+  const long long groups = static_cast<long long>(a.B) * ((OH + PX - 1) / PX) * OW;
   const int grid = grid_for_stem(groups, num_sms);
   const uint4* x = static_cast<const uint4*>(a.x);
   if (a.x_f16)
@@ -280,7 +282,7 @@ int stem_cin_slots(int cin) { return cin == 1 ? 1 : (cin == 3 ? 3 : 4); }
 bool conv_stem_supported(int k, int stride, int pad, int cin, int N, int H, int W) {
   if (k != 3 || pad != 1 || (stride != 1 && stride != 2) || cin < 1 || cin > 4 || (N != 16 && N != 32)) return false;
   const int OW = (W + 2 - 3) / stride + 1;
-  return H >= 1 && W >= 1 && OW % kStemPX == 0;
+  return H >= 1 && W >= 1 && OW >= 1;
 }
 
 std::vector<float> conv_stem_pack(const float* w, int N, int cin, int round_to) {
