@@ -235,6 +235,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     if (ptx::elect_one()) {
       int sa = 0;
       uint32_t ph = 0;
+#ifdef VPK_TRACE
+      long long p_bar = 0;
+      const long long p_begin = clock64();
+#endif
       for (int ts = 0; ts < T_steps; ++ts) {
       bool synced = false;      // SEQ: this step's recurrent input has been waited for
       for (int t = unit0; t < total; t += nunits) {
@@ -254,10 +258,16 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 // async-proxy (TMA) reads behind the acquire
                 const unsigned target = static_cast<unsigned>(ts) * gridDim.x;
                 unsigned seen;
+#ifdef VPK_TRACE
+                const long long b_t0 = clock64();
+#endif
                 do {
                   asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(P.seq_barrier) : "memory");
                 } while (seen < target);
                 asm volatile("fence.proxy.async;" ::: "memory");
+#ifdef VPK_TRACE
+                p_bar += clock64() - b_t0;
+#endif
                 synced = true;
               }
             }
@@ -279,6 +289,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         }
       }
       }
+#ifdef VPK_TRACE
+      if (SEQ && trace)
+        printf("halo seq trace N=%d taps=%d T=%d: activation producer %lld cycles, of which waiting at the grid barrier %lld\n",
+               tileN, P.ntaps, T_steps, clock64() - p_begin, p_bar);
+#endif
     }
   } else if (warp == 1) {
     // ===================================== weight producer (groups of taps per slot) ========================
@@ -574,8 +589,15 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               et.out_off = bo * E.oB + y * E.oY + x * E.oX;  // h'_t: slot (b, ts) of the output sequence
             }
             const int acc = iter & 1;
+#ifdef VPK_TRACE
+            const long long q_t0 = clock64();
+#endif
             ptx::mbar_wait_fast(tfull + 8 * acc, (iter >> 1) & 1u);
             ptx::tc_fence_after();
+#ifdef VPK_TRACE
+            const long long q_t1 = clock64();
+            e_wait += q_t1 - q_t0;
+#endif
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
             LstmPeep pp[2];
@@ -621,16 +643,34 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               if constexpr (PAIR) ptx::mbar_arrive_cluster(tempty + 8 * acc, lead);
               else ptx::mbar_arrive(tempty + 8 * acc);
             }
+#ifdef VPK_TRACE
+            e_body += clock64() - q_t1;
+#endif
           }
           if (ts + 1 < T_steps) {
             // this CTA's h'_ts is complete: publish it (generic-proxy stores -> other CTAs' TMA reads) and arrive once
+#ifdef VPK_TRACE
+            const long long q_t2 = clock64();
+#endif
+            // (every thread orders its own generic-proxy stores for the async proxy; the CTA barrier orders them before the
+            // elected thread, whose gpu-scope fence + release are cumulative over them -- one fence per CTA, not 256:
+            // the publish phase was 2.3 us of every 17 us step)
             asm volatile("fence.proxy.async;" ::: "memory");
-            __threadfence();
             asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
-            if (warp == 3 && lane == 0)
+            if (warp == 3 && lane == 0) {
+              __threadfence();
               asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(P.seq_barrier), "r"(1u) : "memory");
+            }
+#ifdef VPK_TRACE
+            e_ld += clock64() - q_t2;
+#endif
           }
         }
+#ifdef VPK_TRACE
+        if (trace && warp == 3 && lane == 0)
+          printf("halo seq trace N=%d taps=%d T=%d: epilogue warp, %d tiles: waiting for the accumulator %lld cycles, fused update %lld, "
+                 "publish (fences + CTA barrier + release) %lld\n", tileN, P.ntaps, T_steps, iter, e_wait, e_body, e_ld);
+#endif
       };
       auto run_n = [&](auto peep_c) {
         switch ((Cn / 8 - half + 1) / 2) {
