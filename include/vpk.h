@@ -178,6 +178,16 @@ int vpk_convlstm_cell_backward(vpk_cell* cell, int32_t batch, const float* x, co
                                const float* dh_out, const float* dc_out, float* dx, float* dh, float* dc, float* dw, float* db,
                                void* stream);
 
+/* The same for one timestep of the Shi et al. ConvLSTM with peepholes (conv_lstm_hzzone.py:57-69; a cell created with
+ * gate_order 0): torch.autograd's gradients of (h', c') = step(x, h, c; W, b, Wci, Wcf, Wco).  wci / wcf / wco DEVICE fp32
+ * [1, ch, h, w] (NULL = zero); x may be NULL (the forecaster's all-zero input; dx is then not written).  Also writes the
+ * peephole gradients dwci / dwcf / dwco [1, ch, h, w] (sums over the batch; NULL = not wanted).  BPTT over a sequence is the
+ * caller's loop (one call per timestep, newest first), as with the reference module under autograd.  Deterministic. */
+int vpk_convlstm_cell_backward_peep(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
+                                    const float* wci, const float* wcf, const float* wco, const float* dh_out,
+                                    const float* dc_out, float* dx, float* dh, float* dc, float* dw, float* db, float* dwci,
+                                    float* dwcf, float* dwco, void* stream);
+
 /* Replaces SpatioTemporalLSTMCell.forward with layer_norm=False (model_blocks/predrnn.py:57-83).
  *   weights HOST fp32: w_x [7ch, cin, k, k], w_h [4ch, ch, k, k], w_m [3ch, ch, k, k], w_o [ch, 2ch, k, k],
  *   w_last [ch, 2ch, 1, 1].  x [b, cin, h, w]; h, c, m [b, ch, h, w]; outputs h', c', m', delta_c, delta_m. */

@@ -1,6 +1,7 @@
-"""Gradients of the differentiable ConvLSTMCell drop-in (vpk_convlstm_cell_backward behind a torch.autograd.Function)
-against torch autograd on the reference cell (baseline/_ref) or, without it, on the oracle's restatement -- fp32 mode to
-1e-4 relative, 16-bit mode to a few percent; and BPTT over two chained steps of a two-layer stack."""
+"""Gradients of the differentiable ConvLSTMCell and Shi-et-al. ConvLSTM drop-ins (vpk_convlstm_cell_backward /
+vpk_convlstm_cell_backward_peep behind torch.autograd.Functions) against torch autograd on the reference modules
+(baseline/_ref) or, without them, on the oracle's restatement -- fp32 mode to 1e-4 relative, 16-bit mode to a few percent;
+and BPTT over two chained steps of a two-layer stack / over a peephole ConvLSTM sequence."""
 import os
 
 import pytest
@@ -102,3 +103,71 @@ def test_bptt_through_a_two_layer_stack_over_two_steps():
         errs[f"db{j}"] = _rel(blk.cell_list[j].conv.bias.grad.cpu(), bs[j].grad)
     print("BPTT 2 layers x 2 steps (fp32): " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
     assert max(errs.values()) <= 1e-4, errs
+
+
+def _shi_reference(cin, ch, hw, sd, inputs, h0, c0, seq_len):
+    """Shi-et-al. ConvLSTM over a sequence under CPU autograd: the reference module when installed, else a restatement of
+    conv_lstm_hzzone.py:52-69.  Returns (outputs, (h, c), leaves)."""
+    w, b = sd["_conv.weight"].clone().requires_grad_(True), sd["_conv.bias"].clone().requires_grad_(True)
+    peep = [sd[k].clone().requires_grad_(True) for k in ("Wci", "Wcf", "Wco")]
+    if HAVE_REF:
+        from vp_suite.model_blocks.conv_lstm_hzzone import ConvLSTM as RefShi
+        ref = RefShi("cpu", in_channels=cin, enc_channels=ch, state_h=hw[0], state_w=hw[1], kernel_size=3, stride=1, padding=1)
+        ref.load_state_dict({k: sd[k] for k in ("_conv.weight", "_conv.bias", "Wci", "Wcf", "Wco")})
+        out, (h, c) = ref(inputs, (h0, c0), seq_len)
+        return out, (h, c), [ref._conv.weight, ref._conv.bias, ref.Wci, ref.Wcf, ref.Wco]
+    h, c, outs = h0, c0, []
+    for t in range(seq_len):
+        x = torch.zeros(h.shape[0], cin, *hw) if inputs is None else inputs[:, t]
+        z = torch.nn.functional.conv2d(torch.cat([x, h], dim=1), w, b, padding=1)
+        i, f, g, o = torch.chunk(z, 4, dim=1)
+        i, f = torch.sigmoid(i + peep[0] * c), torch.sigmoid(f + peep[1] * c)
+        c = f * c + i * torch.tanh(g)
+        o = torch.sigmoid(o + peep[2] * c)
+        h = o * torch.tanh(c)
+        outs.append(h)
+    return torch.stack(outs, dim=1), (h, c), [w, b] + peep
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 2e-2)])
+@pytest.mark.parametrize("with_inputs", [True, False])
+def test_shi_convlstm_sequence_gradients_match_autograd(precision, tol, with_inputs):
+    """BPTT through three timesteps of the peephole ConvLSTM block (conv_lstm_hzzone.py:38-70): gradients of the inputs, the
+    initial state, the conv weight / bias and the three peepholes; with inputs=None (the forecaster's zero input) too."""
+    from vp_suite_b200 import model_blocks as MB
+    dev = "cuda:0"
+    cin, ch, hw, batch, T = 8, 16, (12, 10), 2, 3
+    blk = MB.ConvLSTM(dev, in_channels=cin, enc_channels=ch, state_h=hw[0], state_w=hw[1], kernel_size=3)
+    blk.precision = precision
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in blk.state_dict().items()}, seed=51)
+    blk.load_state_dict(sd)
+    g = torch.Generator().manual_seed(52)
+    inputs = (torch.rand((batch, T, cin, *hw), generator=g) * 2 - 1) if with_inputs else None
+    h0, c0 = (torch.rand((batch, ch, *hw), generator=g) * 2 - 1 for _ in range(2))
+    r_out, r_h, r_c = torch.rand((batch, T, ch, *hw), generator=g), torch.rand((batch, ch, *hw), generator=g), \
+        torch.rand((batch, ch, *hw), generator=g)
+    # reference gradients (CPU autograd)
+    xi = None if inputs is None else inputs.clone().requires_grad_(True)
+    hr, cr = h0.clone().requires_grad_(True), c0.clone().requires_grad_(True)
+    out, (hT, cT), leaves = _shi_reference(cin, ch, hw, sd, xi, hr, cr, T)
+    ((out * r_out).sum() + (hT * r_h).sum() + (cT * r_c).sum()).backward()
+    want = {"dh0": hr.grad, "dc0": cr.grad, "dW": leaves[0].grad, "db": leaves[1].grad, "dWci": leaves[2].grad,
+            "dWcf": leaves[3].grad, "dWco": leaves[4].grad}
+    if xi is not None:
+        want["dx"] = xi.grad
+    # ours
+    xo = None if inputs is None else inputs.clone().to(dev).requires_grad_(True)
+    ho, co = h0.clone().to(dev).requires_grad_(True), c0.clone().to(dev).requires_grad_(True)
+    out_o, (hT_o, cT_o) = blk(xo, (ho, co), T)
+    assert out_o.requires_grad
+    ((out_o * r_out.to(dev)).sum() + (hT_o * r_h.to(dev)).sum() + (cT_o * r_c.to(dev)).sum()).backward()
+    got = {"dh0": ho.grad, "dc0": co.grad, "dW": blk._conv.weight.grad, "db": blk._conv.bias.grad, "dWci": blk.Wci.grad,
+           "dWcf": blk.Wcf.grad, "dWco": blk.Wco.grad}
+    if xo is not None:
+        got["dx"] = xo.grad
+    errs = {k: _rel(got[k].cpu(), want[k]) for k in want}
+    print(f"Shi ConvLSTM BPTT {precision} inputs={with_inputs}: " + ", ".join(f"{k} {v:.1e}" for k, v in errs.items()))
+    assert max(errs.values()) <= tol, errs
+    with torch.no_grad():                                  # the inference path is unchanged and agrees with the forward above
+        out_n, _ = blk(None if inputs is None else inputs.to(dev), (h0.to(dev), c0.to(dev)), T)
+    assert not out_n.requires_grad and torch.equal(out_n, out_o.detach())

@@ -71,6 +71,7 @@ SYMBOLS = {
     "vpk_convlstm_cell_create": (C.c_int, [C.c_int32] * 8 + [_vp, _vp, C.POINTER(_vp)]),
     "vpk_convlstm_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 9),
     "vpk_convlstm_cell_backward": (C.c_int, [_vp, C.c_int32] + [_vp] * 11),
+    "vpk_convlstm_cell_backward_peep": (C.c_int, [_vp, C.c_int32] + [_vp] * 17),
     "vpk_stlstm_cell_create": (C.c_int, [C.c_int32] * 7 + [_vp] * 5 + [C.POINTER(_vp)]),
     "vpk_stlstm_cell_set_layer_norm": (C.c_int, [_vp] * 9),
     "vpk_stlstm_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 10),

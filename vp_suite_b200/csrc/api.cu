@@ -254,6 +254,18 @@ int vpk_convlstm_cell_backward(vpk_cell* cell, int32_t batch, const float* x, co
   });
 }
 
+int vpk_convlstm_cell_backward_peep(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
+                                    const float* wci, const float* wcf, const float* wco, const float* dh_out,
+                                    const float* dc_out, float* dx, float* dh, float* dc, float* dw, float* db, float* dwci,
+                                    float* dwcf, float* dwco, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && h && c && dh && dc && dw, "null argument");
+    const float* in[8] = {x, h, c, dh_out, dc_out, wci, wcf, wco};
+    float* outp[8] = {dx, dh, dc, dw, db, dwci, dwcf, dwco};
+    cell->impl->backward(batch, in, outp, static_cast<cudaStream_t>(stream));
+  });
+}
+
 int vpk_stlstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w,
                            int32_t k, const float* w_x, const float* w_h, const float* w_m, const float* w_o,
                            const float* w_last, vpk_cell** out) {

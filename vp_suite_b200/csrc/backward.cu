@@ -50,6 +50,62 @@ __global__ void __launch_bounds__(256) lstm_gate_backward_kernel(const float* __
   }
 }
 
+// Shi et al. ConvLSTM with peepholes (conv_lstm_hzzone.py:57-69): split order (i, f, g, o);
+//   i = s(z_i + Wci c), f = s(z_f + Wcf c), c' = f c + i tanh(z_g), o = s(z_o + Wco c'), h = o tanh(c').
+// One thread = one (position of the image, channel); it walks the batch, so the peephole gradients (sums over the
+// batch) are accumulated in a fixed order without atomics.
+template <typename T>
+__global__ void __launch_bounds__(256) lstm_peep_gate_backward_kernel(const float* __restrict__ z, const float* __restrict__ c,
+                                                                      const float* __restrict__ wci, const float* __restrict__ wcf,
+                                                                      const float* __restrict__ wco, const float* __restrict__ dh,
+                                                                      const float* __restrict__ dcn, float* __restrict__ dz,
+                                                                      T* __restrict__ dz_act, float* __restrict__ dc_in,
+                                                                      float* __restrict__ dwci, float* __restrict__ dwcf,
+                                                                      float* __restrict__ dwco, int B, long long HW, int C) {
+  const long long total = HW * C;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long hw = idx / C;
+    const int ch = static_cast<int>(idx - hw * C);
+    const float pi = wci ? wci[idx] : 0.f, pf = wcf ? wcf[idx] : 0.f, po = wco ? wco[idx] : 0.f;
+    float gi = 0.f, gf = 0.f, go = 0.f;
+    for (int b = 0; b < B; ++b) {
+      const long long p = b * HW + hw;
+      const float* zp = z + p * 4 * C;
+      const float cp = c[p * C + ch];
+      const float i = sigmoid_acc(zp[ch] + pi * cp), f = sigmoid_acc(zp[C + ch] + pf * cp), g = tanhf(zp[2 * C + ch]);
+      const float cn = f * cp + i * g;
+      const float o = sigmoid_acc(zp[3 * C + ch] + po * cn);
+      const float tc = tanhf(cn);
+      const float gh = dh != nullptr ? dh[p * C + ch] : 0.f;
+      const float dzo = gh * tc * o * (1.f - o);
+      const float dct = (dcn != nullptr ? dcn[p * C + ch] : 0.f) + gh * o * (1.f - tc * tc) + dzo * po;    // dL/dc', all paths
+      const float dzi = dct * g * i * (1.f - i);
+      const float dzf = dct * cp * f * (1.f - f);
+      const float dzg = dct * i * (1.f - g * g);
+      float* dp = dz + p * 4 * C;
+      dp[ch] = dzi;
+      dp[C + ch] = dzf;
+      dp[2 * C + ch] = dzg;
+      dp[3 * C + ch] = dzo;
+      if (dz_act != nullptr) {
+        T* ap = dz_act + p * 4 * C;
+        ap[ch] = static_cast<T>(dzi);
+        ap[C + ch] = static_cast<T>(dzf);
+        ap[2 * C + ch] = static_cast<T>(dzg);
+        ap[3 * C + ch] = static_cast<T>(dzo);
+      }
+      dc_in[p * C + ch] = dct * f + dzi * pi + dzf * pf;
+      gi = fmaf(dzi, cp, gi);
+      gf = fmaf(dzf, cp, gf);
+      go = fmaf(dzo, cn, go);
+    }
+    if (dwci) dwci[idx] = gi;
+    if (dwcf) dwcf[idx] = gf;
+    if (dwco) dwco[idx] = go;
+  }
+}
+
 // grid (ceil(Co / 64), ceil(Ci / 64), k * k); 256 threads = 16 x 16, each a 4 x 4 block of (o, i) for one tap
 constexpr int kWgTile = 64, kWgPos = 16;
 __global__ void __launch_bounds__(256) conv_wgrad_kernel(const float* __restrict__ in, const float* __restrict__ dz,
@@ -137,6 +193,22 @@ void launch_lstm_gate_backward(const float* z, const float* c, const float* dh_o
     lstm_gate_backward_kernel<__half><<<grid, 256, 0, stream>>>(z, c, dh_out, dc_out, dz, static_cast<__half*>(dz_act), dc_in, P, C);
   else
     lstm_gate_backward_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(z, c, dh_out, dc_out, dz, static_cast<__nv_bfloat16*>(dz_act), dc_in, P, C);
+  VPK_CUDA(cudaGetLastError());
+}
+
+void launch_lstm_peep_gate_backward(const float* z, const float* c, const float* wci, const float* wcf, const float* wco,
+                                    const float* dh_out, const float* dc_out, float* dz, void* dz_act, int act_dtype,
+                                    float* dc_in, float* dwci, float* dwcf, float* dwco, int B, long long HW, int C, int num_sms,
+                                    cudaStream_t stream) {
+  VPK_REQUIRE(z && c && dz && dc_in && B > 0 && HW > 0 && C > 0, "lstm_peep_gate_backward: bad arguments");
+  const long long total = HW * C;
+  const int grid = static_cast<int>(std::min<long long>((total + 255) / 256, 32ll * num_sms));
+  if (dz_act == nullptr || act_dtype == DT_F32)
+    lstm_peep_gate_backward_kernel<float><<<grid, 256, 0, stream>>>(z, c, wci, wcf, wco, dh_out, dc_out, dz, nullptr, dc_in, dwci, dwcf, dwco, B, HW, C);
+  else if (act_dtype == DT_F16)
+    lstm_peep_gate_backward_kernel<__half><<<grid, 256, 0, stream>>>(z, c, wci, wcf, wco, dh_out, dc_out, dz, static_cast<__half*>(dz_act), dc_in, dwci, dwcf, dwco, B, HW, C);
+  else
+    lstm_peep_gate_backward_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(z, c, wci, wcf, wco, dh_out, dc_out, dz, static_cast<__nv_bfloat16*>(dz_act), dc_in, dwci, dwcf, dwco, B, HW, C);
   VPK_CUDA(cudaGetLastError());
 }
 

@@ -1,4 +1,4 @@
-// Backward pass of the ndrplz ConvLSTM cell (the first differentiable entry behind the C ABI).
+// Backward pass of the two ConvLSTM cells (the differentiable entries behind the C ABI).
 #pragma once
 #include "common.h"
 
@@ -10,6 +10,14 @@ namespace vpk {
 void launch_lstm_gate_backward(const float* z, const float* c, const float* dh_out, const float* dc_out, float* dz,
                                void* dz_act, int act_dtype, float* dc_in, long long P, int C, int num_sms,
                                cudaStream_t stream);
+
+// The Shi et al. ConvLSTM step with peepholes (conv_lstm_hzzone.py:57-69), split order (i, f, g, o): z [B][HW][4C], c [B][HW][C],
+// peepholes wci / wcf / wco NHWC [HW][C] (nullptr = zero); also writes the peephole gradients dwci / dwcf / dwco [HW][C]
+// (sums over the batch, fixed order; nullptr = not wanted).
+void launch_lstm_peep_gate_backward(const float* z, const float* c, const float* wci, const float* wcf, const float* wco,
+                                    const float* dh_out, const float* dc_out, float* dz, void* dz_act, int act_dtype,
+                                    float* dc_in, float* dwci, float* dwcf, float* dwco, int B, long long HW, int C, int num_sms,
+                                    cudaStream_t stream);
 
 // Weight gradient of a k x k stride-1 'same' conv: dw[o][i][ky][kx] = sum over (b, y, x) of dz[b, y, x, o] *
 // in[b, y + ky - k/2, x + kx - k/2, i] (zero outside the image); `in` NHWC fp32 [B][H][W][Ci], dz NHWC fp32 [B][H][W][Co];

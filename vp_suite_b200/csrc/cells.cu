@@ -124,10 +124,13 @@ class ConvLstmCell : public CellBase {
   // gate pre-activations z (one forward conv), differentiates the gate math elementwise, then
   //   d[x; h] = conv_transpose(dz, W)      -- the generalised conv launch (tensor cores in 16-bit mode)
   //   dW      = sum over positions of dz (x) shifted cat(x, h), db = sum of dz      -- fp32 CUDA-core kernels
-  // in: x, h, c, dh_out, dc_out   out: dx, dh, dc, dw, db
+  // in: x, h, c, dh_out, dc_out [, Wci, Wcf, Wco]   out: dx, dh, dc, dw, db [, dWci, dWcf, dWco]
+  // The Shi et al. cell (gate order i, f, g, o; conv_lstm_hzzone.py:57-69) takes its peepholes in in[5..7] (NCHW [1, C, H, W],
+  // nullptr = zero), returns their gradients in out[5..7], and accepts x == nullptr (the forecaster's all-zero input:
+  // no dx then).
   void backward(int B, const float* const* in, float* const* out, cudaStream_t s) override {
-    VPK_REQUIRE(ifog, "backward is implemented for the ndrplz ConvLSTMCell (gate order i, f, o, g, no peepholes)");
-    VPK_REQUIRE(cin > 0 && in[0] && in[1] && in[2] && out[0] && out[1] && out[2] && out[3], "convlstm backward: null argument");
+    VPK_REQUIRE(cin > 0 && in[1] && in[2] && out[1] && out[2] && out[3], "convlstm backward: null argument");
+    VPK_REQUIRE(!ifog || (in[0] && out[0]), "convlstm backward: null argument");
     const size_t px = static_cast<size_t>(B) * h * w;
     const int cio = cin + ch;
     void* xb = buf("bw_x", px * cin * esize());
@@ -157,7 +160,7 @@ class ConvLstmCell : public CellBase {
         }
       }
       int oh, ow;
-      {   // z = conv(cat(x, h)) + b, reference row order (i | f | o | g), dense fp32
+      {   // z = conv(cat(x, h)) + b, reference row order (ndrplz: i | f | o | g; Shi et al.: i | f | g | o), dense fp32
         ConvSpec sp;
         sp.name = "cell.bw.z";
         sp.B = B;
@@ -195,19 +198,41 @@ class ConvLstmCell : public CellBase {
       finish_build(s);
       bw_batch = B;
     }
-    to_nhwc(in[0], xb, dtype, B, cin, h, w, s);
+    if (in[0]) {
+      to_nhwc(in[0], xb, dtype, B, cin, h, w, s);
+    } else {
+      VPK_CUDA(cudaMemsetAsync(xb, 0, px * cin * esize(), s));
+    }
     to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
     if (dtype != DT_F32) {
-      to_nhwc(in[0], x32, DT_F32, B, cin, h, w, s);
+      if (in[0]) to_nhwc(in[0], x32, DT_F32, B, cin, h, w, s);
+      else VPK_CUDA(cudaMemsetAsync(x32, 0, px * cin * 4, s));
       to_nhwc(in[1], h32, DT_F32, B, ch, h, w, s);
     }
     to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
     if (gh) to_nhwc(in[3], gh, DT_F32, B, ch, h, w, s);
     if (gc) to_nhwc(in[4], gc, DT_F32, B, ch, h, w, s);
     for (int i = 0; i < n_z; ++i) run(bw_convs[i], s);
-    launch_lstm_gate_backward(z, cb, gh, gc, dz, dtype == DT_F32 ? nullptr : dza, dtype, dci, static_cast<long long>(px), ch, num_sms, s);
+    if (ifog) {
+      launch_lstm_gate_backward(z, cb, gh, gc, dz, dtype == DT_F32 ? nullptr : dza, dtype, dci, static_cast<long long>(px), ch, num_sms, s);
+    } else {
+      const size_t pp = static_cast<size_t>(h) * w * ch;
+      float* pk[3] = {nullptr, nullptr, nullptr};
+      float* dpk[3] = {nullptr, nullptr, nullptr};
+      for (int q = 0; q < 3; ++q) {
+        if (in[5 + q]) {
+          pk[q] = static_cast<float*>(buf(q == 0 ? "bw_wci" : q == 1 ? "bw_wcf" : "bw_wco", pp * 4));
+          to_nhwc(in[5 + q], pk[q], DT_F32, 1, ch, h, w, s);
+        }
+        if (out[5 + q]) dpk[q] = static_cast<float*>(buf(q == 0 ? "bw_dwci" : q == 1 ? "bw_dwcf" : "bw_dwco", pp * 4));
+      }
+      launch_lstm_peep_gate_backward(z, cb, pk[0], pk[1], pk[2], gh, gc, dz, dtype == DT_F32 ? nullptr : dza, dtype, dci, dpk[0],
+                                     dpk[1], dpk[2], B, static_cast<long long>(h) * w, ch, num_sms, s);
+      for (int q = 0; q < 3; ++q)
+        if (out[5 + q]) launch_nhwc_to_nchw(dpk[q], DT_F32, out[5 + q], 1, ch, h, w, num_sms, s);
+    }
     for (size_t i = n_z; i < bw_convs.size(); ++i) run(bw_convs[i], s);
-    launch_nhwc_to_nchw(dxo, DT_F32, out[0], B, cin, h, w, num_sms, s);
+    if (out[0]) launch_nhwc_to_nchw(dxo, DT_F32, out[0], B, cin, h, w, num_sms, s);
     launch_nhwc_to_nchw(dho, DT_F32, out[1], B, ch, h, w, num_sms, s);
     launch_nhwc_to_nchw(dci, DT_F32, out[2], B, ch, h, w, num_sms, s);
     launch_conv_wgrad(x32, dz, out[3], B, h, w, cin, 4 * ch, k, cio, 0, s);

@@ -163,8 +163,44 @@ class ConvLSTMCell(_NativeCell, nn.Module):
                 torch.zeros(batch_size, self.hidden_dim, height, width, device=dev))
 
 
+class _ShiConvLSTMStepFunction(torch.autograd.Function):
+    """One timestep of the Shi-et-al. ConvLSTM (peepholes; x may be None = the forecaster's zero input) with a native backward
+    (vpk_convlstm_cell_backward_peep).  Saves the step's inputs; the backward recomputes the gates in the library and returns the
+    gradients of x, h, c, the conv weight / bias and the three peepholes; BPTT over the sequence composes through autograd."""
+
+    @staticmethod
+    def forward(ctx, module, x, h, c, weight, bias, wci, wcf, wco):
+        ctx.module = module
+        ctx.has_x = x is not None
+        ctx.save_for_backward(*([x] if x is not None else []), h, c, wci, wcf, wco)
+        d = module._dev
+        return module._native_step(None if x is None else d(x), d(h), d(c), d(wci), d(wcf), d(wco))
+
+    @staticmethod
+    def backward(ctx, dh_out, dc_out):
+        module = ctx.module
+        saved = list(ctx.saved_tensors)
+        x = saved.pop(0) if ctx.has_x else None
+        h, c, wci, wcf, wco = saved
+        cell = module._cell_handle(h.device)
+        d = module._dev
+        x, h, c, wci, wcf, wco = (None if t is None else d(t) for t in (x, h, c, wci, wcf, wco))
+        dx = torch.empty_like(x) if x is not None else None
+        dh, dc = torch.empty_like(h), torch.empty_like(c)
+        dw = torch.empty_like(module._conv.weight, dtype=torch.float32)
+        db = torch.empty_like(module._conv.bias, dtype=torch.float32)
+        dp = [torch.empty_like(p, dtype=torch.float32) for p in (wci, wcf, wco)]
+        gh = None if dh_out is None else module._dev(dh_out)
+        gc = None if dc_out is None else module._dev(dc_out)
+        module._step(h.device, N.lib().vpk_convlstm_cell_backward_peep, cell, h.shape[0], N.ptr(x), N.ptr(h), N.ptr(c),
+                     N.ptr(wci), N.ptr(wcf), N.ptr(wco), N.ptr(gh), N.ptr(gc), N.ptr(dx), N.ptr(dh), N.ptr(dc), N.ptr(dw),
+                     N.ptr(db), N.ptr(dp[0]), N.ptr(dp[1]), N.ptr(dp[2]), module._stream(h))
+        return None, dx, dh, dc, dw, db, dp[0], dp[1], dp[2]
+
+
 class ConvLSTM(_NativeCell, VPModelBlock):
-    """conv_lstm_hzzone.py:7-70: whole-sequence driver of the Shi-et-al. ConvLSTM with peepholes."""
+    """conv_lstm_hzzone.py:7-70: whole-sequence driver of the Shi-et-al. ConvLSTM with peepholes.  Differentiable like
+    ConvLSTMCell: with gradients enabled every timestep runs through an autograd.Function whose backward is libvpk's."""
     NAME = "ConvLSTM (Shi et al.)"
     PAPER_REFERENCE = "https://arxiv.org/abs/1506.04214"
     CODE_REFERENCE = "https://github.com/Hzzone/Precipitation-Nowcasting"
@@ -202,18 +238,35 @@ class ConvLSTM(_NativeCell, VPModelBlock):
         else:
             h, c = states
             b = h.shape[0]
-        h, c = self._dev(h), self._dev(c)
-        cell = self._cell_handle(h.device)
-        peep = [self._dev(p)[0] for p in (self.Wci, self.Wcf, self.Wco)]
+        params = (self._conv.weight, self._conv.bias, self.Wci, self.Wcf, self.Wco)
+        grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or h.requires_grad or c.requires_grad or
+                                            (inputs is not None and inputs.requires_grad))
         outputs = []
+        if grad:
+            # differentiable path: the tensors stay attached; each timestep is one autograd node with a native backward
+            for t_ in (h, c) + (() if inputs is None else (inputs,)):
+                if not t_.is_cuda:
+                    raise N.NativeError("vp_suite_b200 blocks run on CUDA tensors only (there is no CPU path)")
+            h, c = h.to(torch.float32).contiguous(), c.to(torch.float32).contiguous()
+            for t in range(seq_len):
+                x = None if inputs is None else inputs[:, t].to(torch.float32).contiguous()
+                h, c = _ShiConvLSTMStepFunction.apply(self, x, h, c, *params)
+                outputs.append(h)
+            return torch.stack(outputs, dim=1), (h, c)
+        h, c = self._dev(h), self._dev(c)
+        peep = [self._dev(p) for p in (self.Wci, self.Wcf, self.Wco)]
         for t in range(seq_len):                                         # conv_lstm_hzzone.py:52-69
             x = None if inputs is None else self._dev(inputs[:, t])      # None = all-zero input (:54-56)
-            h_new, c_new = torch.empty_like(h), torch.empty_like(c)
-            self._step(h.device, N.lib().vpk_convlstm_cell_step, cell, b, N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(peep[0]),
-                       N.ptr(peep[1]), N.ptr(peep[2]), N.ptr(h_new), N.ptr(c_new), self._stream(h))
-            h, c = h_new, c_new
+            h, c = self._native_step(x, h, c, *peep)
             outputs.append(h)
         return torch.stack(outputs, dim=1), (h, c)
+
+    def _native_step(self, x, h, c, wci, wcf, wco):
+        cell = self._cell_handle(h.device)
+        h_new, c_new = torch.empty_like(h), torch.empty_like(c)
+        self._step(h.device, N.lib().vpk_convlstm_cell_step, cell, h.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(wci),
+                   N.ptr(wcf), N.ptr(wco), N.ptr(h_new), N.ptr(c_new), self._stream(h))
+        return h_new, c_new
 
 
 class SingleStepConvLSTM(nn.Module):
