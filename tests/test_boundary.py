@@ -62,6 +62,8 @@ def test_train_iter_refuses_clearly_and_model_is_marked_untrainable():
     assert m.TRAINABLE is False                        # VPSuite.train skips training for such models (vpsuite.py:312)
     with pytest.raises(NotImplementedError, match="inference-only"):
         m.train_iter({}, [], None, None, 0)
+    # the one trainable drop-in: EF_ConvLSTM (differentiable ConvLSTM layers; tests/test_gpu_backward.py trains it)
+    assert V.MODEL_CLASSES["convlstm-shi"].TRAINABLE is True
 
 
 @pytest.mark.parametrize("key", ["convlstm-shi", "predrnn-pp", "phy", "convlstm-branch"])

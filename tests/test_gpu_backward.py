@@ -171,3 +171,69 @@ def test_shi_convlstm_sequence_gradients_match_autograd(precision, tol, with_inp
     with torch.no_grad():                                  # the inference path is unchanged and agrees with the forward above
         out_n, _ = blk(None if inputs is None else inputs.to(dev), (h0.to(dev), c0.to(dev)), T)
     assert not out_n.requires_grad and torch.equal(out_n, out_o.detach())
+
+
+def test_ef_convlstm_trains_like_the_reference():
+    """EF_ConvLSTM in train() mode (the differentiable forward: native ConvLSTM steps forward + backward, torch convs for the
+    stages): the frames equal the native inference rollout, the parameter gradients of an MSE loss equal those of the
+    reference model under CPU autograd (fp32 mode), and base_model.py:148-179's train_iter lowers the loss."""
+    import vp_suite_b200 as V
+    from oracle import models as OM
+    from oracle.weights import synth_frames
+    dev, img, b, ctx, pred = "cuda:0", (1, 32, 32), 2, 3, 2
+    m = V.MODEL_CLASSES["convlstm-shi"](dev, img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0], precision="fp32")
+    assert m.TRAINABLE
+    sd = synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=61, gain=2.5)
+    m.load_state_dict(sd)
+    x = synth_frames(b, ctx, *img, seed=62)
+    target = synth_frames(b, pred, *img, seed=63)
+    # reference gradients: the reference model when installed, else the oracle's functional forward over leaf tensors
+    if HAVE_REF:
+        ref = ref_shim.load_reference()["convlstm-shi"]("cpu", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0])
+        ref.load_state_dict(sd)
+        ref.train()
+        out_r, _ = ref(x, pred_frames=pred)
+        torch.nn.functional.mse_loss(out_r, target).backward()
+        want = {k: p.grad for k, p in ref.named_parameters()}
+    else:
+        leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+        out_r, _ = OM.ef_convlstm_forward(leaves, x, pred)
+        torch.nn.functional.mse_loss(out_r, target).backward()
+        want = {k: v.grad for k, v in leaves.items()}
+    m.train()
+    torch.backends.cudnn.allow_tf32 = False            # the stage convs of the training forward are torch's: plain fp32 here
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out, aux = m(x.to(dev), pred_frames=pred)
+    assert aux is None and out.requires_grad
+    torch.nn.functional.mse_loss(out, target.to(dev)).backward()
+    errs = {k: _rel(p.grad.cpu(), want[k]) for k, p in m.named_parameters() if want.get(k) is not None}
+    worst = max(errs, key=errs.get)
+    print("largest relative gradient errors:", sorted(((round(v, 6), k) for k, v in errs.items()), reverse=True)[:6])
+    print(f"EF_ConvLSTM training gradients (fp32 mode): {len(errs)} tensors, worst {worst} {errs[worst]:.1e}; "
+          f"forward err {float((out.detach().cpu() - out_r.detach()).abs().max()):.1e}")
+    assert len(errs) == 44 and max(errs.values()) <= 1e-4, errs
+    m.eval()
+    with torch.no_grad():
+        infer, _ = m(x.to(dev), pred_frames=pred)
+    assert float((infer - out.detach()).abs().max()) <= 1e-5          # the training forward IS the rollout
+    # train_iter (base_model.py:148-179) with a minimal loss provider: the loss goes down
+    class _Loss:
+        def get_losses(self, p, t):
+            v = torch.nn.functional.mse_loss(p, t)
+            return {"mse": v.detach()}, v
+    m.train()
+    m.zero_grad()
+    loader = [{"frames": torch.cat([x, target], dim=1), "actions": torch.zeros(b, ctx + pred - 1, 0)}] * 6
+    cfg = {"context_frames": ctx, "pred_frames": pred, "device": dev, "use_actions": False}
+    cfg.update(m.config)
+    opt = torch.optim.Adam(m.parameters(), lr=2e-3)
+    with torch.no_grad():
+        m.eval()
+        before = float(torch.nn.functional.mse_loss(m(x.to(dev), pred_frames=pred)[0], target.to(dev)))
+        m.train()
+    m.train_iter(cfg, loader, opt, _Loss(), epoch=0)
+    m.eval()
+    with torch.no_grad():
+        after = float(torch.nn.functional.mse_loss(m(x.to(dev), pred_frames=pred)[0], target.to(dev)))
+    print(f"train_iter: mse {before:.5f} -> {after:.5f}")
+    assert after < before

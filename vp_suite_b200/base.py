@@ -7,8 +7,9 @@ registered it), ``VPModel`` / ``VPModelBlock`` here ARE subclasses of ``vp_suite
 ``isinstance(model, vp_suite.base.VPModel)`` holds, so ``VPSuite.test()`` (vp_suite/vpsuite.py:536-550) drives a
 registered drop-in unchanged.  Otherwise a faithful mirror of vp_suite/base/base_model.py:11-216 is used (constructor
 ``(device, **model_kwargs)``, ``REQUIRED_ARGS``, kwargs -> type-checked attributes, ``config``, ``unpack_data``,
-``eval_iter``).  In both cases ``train_iter`` refuses: the native rollout is inference-only (``TRAINABLE = False``, which
-``VPSuite.train`` honours, vpsuite.py:312).  ``NativeRollout`` is the glue to libvpk: it mirrors the module's
+``eval_iter``, ``train_iter``).  ``train_iter`` refuses for the drop-ins whose rollout is inference-only (``TRAINABLE =
+False``, which ``VPSuite.train`` honours, vpsuite.py:312) and is the base class's own loop for the trainable one
+(EF_ConvLSTM: differentiable ConvLSTM layers).  ``NativeRollout`` is the glue to libvpk: it mirrors the module's
 ``state_dict`` into the native handle and runs ``forward`` through the C ABI.  Nothing here computes frames in Python --
 without the CUDA library the calls raise.
 """
@@ -136,6 +137,20 @@ class _MirrorVPModel(nn.Module):
     def forward(self, x, pred_frames=1, **kwargs):
         raise NotImplementedError
 
+    def train_iter(self, config, loader, optimizer, loss_provider, epoch):
+        """base_model.py:148-179: one pass over the training loader (forward, loss incl. the model's own losses, backward,
+        optimizer step) -- used by the drop-ins that declare TRAINABLE = True."""
+        for data in loader:
+            inp, targets, actions = self.unpack_data(data, config)
+            predictions, model_losses = self(inp, pred_frames=config["pred_frames"], actions=actions)
+            _, total_loss = loss_provider.get_losses(predictions, targets)
+            if model_losses is not None:
+                for value in model_losses.values():
+                    total_loss += value
+            optimizer.zero_grad()
+            total_loss.backward()
+            optimizer.step()
+
     def eval_iter(self, config, loader, loss_provider):
         """base_model.py:181-216: one pass over the validation loader; returns ({loss name: mean}, indicator loss)."""
         self.eval()
@@ -160,9 +175,12 @@ class VPModelBlock(_RefVPModelBlock or _MirrorVPModelBlock):
 class VPModel(_RefVPModel or _MirrorVPModel):
     """Base of the drop-in models: the reference's own VPModel when importable, else its mirror above."""
     TRAINABLE = False        # vpsuite.py:312 skips training for such models; the native rollout has no backward pass
+    _BASE_TRAIN_ITER = (_RefVPModel or _MirrorVPModel).train_iter        # for the drop-ins that do train (EF_ConvLSTM)
 
     def train_iter(self, config, loader, optimizer, loss_provider, epoch):
         """base_model.py:148-179 needs gradients through forward(); libvpk is inference-only."""
+        if self.TRAINABLE:
+            return type(self)._BASE_TRAIN_ITER(self, config, loader, optimizer, loss_provider, epoch)
         raise NotImplementedError(f"{type(self).__name__} (vp_suite_b200) is an inference-only drop-in: forward() runs in "
                                   f"libvpk without autograd, so train_iter() is not available (TRAINABLE = False); train "
                                   f"with the reference class and load its state_dict / checkpoint here")
@@ -187,7 +205,7 @@ class NativeRollout:
         self._workspaces = {}
 
     # -- pickling (torch.save(model) / torch.load, vpsuite.py:394,135): the native handle is dropped and rebuilt ----------
-    _NATIVE_STATE = ("_handle", "_handle_device", "_versions", "_workspaces", "_host_out")
+    _NATIVE_STATE = ("_handle", "_handle_device", "_versions", "_workspaces", "_host_out", "_train_blocks")
 
     def __getstate__(self):
         state = dict(self.__dict__)

@@ -49,7 +49,13 @@ def _act_code(name):
 
 
 class EF_ConvLSTM(NativeRollout, VPModel):
+    """ef_conv_lstm.py:7-108 / ef_blocks.py:53-187.  Inference (``torch.no_grad`` / ``eval()``): the whole rollout is one
+    native launch program.  Training (``train()`` with gradients enabled; ``train_iter`` of the base class, so
+    ``VPSuite.train`` runs): a differentiable forward in the reference's own layer-major order whose six ConvLSTM layers are
+    the drop-in ``ConvLSTM`` blocks -- native forward AND backward per timestep (``vpk_convlstm_cell_backward_peep``),
+    BPTT composed by autograd -- and whose stage convs / deconvs / head are torch's own conv ops (cuDNN under autograd)."""
     NAME = "EF-ConvLSTM (Shi et al.)"
+    TRAINABLE = True
     PAPER_REFERENCE = "https://arxiv.org/abs/1506.04214"
     CODE_REFERENCE = "https://github.com/Hzzone/Precipitation-Nowcasting"
     MATCHES_REFERENCE = "Yes"
@@ -209,8 +215,60 @@ class EF_ConvLSTM(NativeRollout, VPModel):
         b, t, c, h, w = x.shape
         if (c, h, w) != (self.img_c, self.img_h, self.img_w):
             raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_differentiable(x, int(pred_frames)), None
         pred, _ = self._native_forward(x, int(pred_frames), t)
         return pred, None                                                # ef_blocks.py:184-187
+
+    # -- training path ----------------------------------------------------------------------------------------------
+    def _train_block(self, holder, in_c, enc_c, hw, k):
+        """A differentiable drop-in ConvLSTM block that SHARES ``holder``'s parameters (kept out of the module tree: the
+        state_dict layout must stay the reference's)."""
+        blocks = self.__dict__.setdefault("_train_blocks", {})
+        blk = blocks.get(id(holder))
+        if blk is None:
+            from .model_blocks import ConvLSTM
+            blk = ConvLSTM(self._native_device(), in_c, enc_c, hw[0], hw[1], k, 1, k // 2)
+            blk._conv, blk.Wci, blk.Wcf, blk.Wco = holder._conv, holder.Wci, holder.Wcf, holder.Wco
+            blocks[id(holder)] = blk
+        blk.precision, blk.backend = self.precision, self.backend
+        return blk
+
+    def _forward_differentiable(self, x, pred_frames):
+        import torch.nn.functional as F
+        if not x.is_cuda:
+            raise N.NativeError("vp_suite_b200 models run on CUDA tensors only (there is no CPU path)")
+        act = {0: (lambda v: v), 1: (lambda v: F.leaky_relu(v, 0.2)), 3: F.relu}[self._ef_act]
+        L = self.num_layers
+
+        def stage(mods, v):                                              # ef_blocks.py:67-73 / 100-106: time-batched convs
+            b_, t_ = v.shape[:2]
+            v = v.reshape(-1, *v.shape[2:])
+            for name, m in mods.named_children():
+                if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                    v = m(v)
+                    if _act_code(name) and name != self.final_conv_2_name:
+                        v = act(v)
+            return v.reshape(b_, t_, *v.shape[1:])
+
+        inp, states = x.to(torch.float32), []
+        for n in range(L):                                               # Encoder.forward (ef_blocks.py:76-82)
+            inp = stage(getattr(self.encoder, f"stage{n + 1}"), inp)
+            holder = getattr(self.encoder, f"rnn{n + 1}")
+            hw = (self.enc_rnn_state_h[n], self.enc_rnn_state_w[n])
+            blk = self._train_block(holder, self.enc_c[2 * n], self.enc_c[2 * n + 1], hw, self.enc_rnn_k[n])
+            inp, st = blk(inp, None, inp.shape[1])
+            states.append(st)
+        out = None
+        for n in range(L):                                               # Forecaster.forward (ef_blocks.py:108-114)
+            idx = L - n                                                  # rnn3, rnn2, rnn1
+            holder = getattr(self.forecaster, f"rnn{idx}")
+            hw = (self.dec_rnn_state_h[n], self.dec_rnn_state_w[n])
+            in_c = self.enc_c[-1] if n == 0 else self.dec_c[2 * n - 1]
+            blk = self._train_block(holder, in_c, self.dec_c[2 * n], hw, self.dec_rnn_k[n])
+            out, _ = blk(out, states[idx - 1], pred_frames)
+            out = stage(getattr(self.forecaster, f"stage{idx}"), out)
+        return out
 
 
 class PredRNN_V2(NativeRollout, VPModel):
