@@ -65,11 +65,11 @@ class StLstmModelBase : public Model {
       // conv_x (its input enters all seven gate pre-activations) needs split activations as well; for conv_h / conv_m
       // split weights are enough: worst of 256 sequences against the reference 1.62e-2 with three products everywhere,
       // 1.65e-2 with two for conv_h / conv_m (2.19e-2 with two for conv_x and conv_h).  VPK_LN_PRODUCTS_X / _H / _M
-      // override per conv (developer switch, capped by `products`).
+      // override per conv (developer builds only, capped by `products`).
       int prod = name[5] == 'x' ? products : std::min(products, 2);
       if (precise) {
         const std::string key = std::string("VPK_LN_PRODUCTS_") + static_cast<char>(std::toupper(name[5]));
-        if (const char* env = getenv(key.c_str())) prod = std::max(1, std::min(products, atoi(env)));
+        if (const char* env = dev_env(key.c_str())) prod = std::max(1, std::min(products, atoi(env)));   // -DVPK_DEV builds only
       }
       if (precise && prod == 2) a.w_split = true;
       if (precise && prod == 3) {
