@@ -182,7 +182,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
   }
   if (threadIdx.x < 2) s_tapmma[P.ntaps + threadIdx.x] = make_uint2(0u, 0u);
-  for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) s_bias[i] = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
+  for (int i = threadIdx.x; i < P.L.N_pad; i += kHaloThreads) {
+    float v = P.L.epi.bias ? P.L.epi.bias[i] : 0.f;
+    // lstm_finish (the rolled and the sequence-mode ConvLSTM epilogues) takes the sigmoid gates' biases halved: packed order
+    // ch * 4 + (i, f, g, o)
+    if constexpr (KIND == EPI_LSTM && (MODE == 2 || MODE == 4))
+      if ((i & 3) != 2) v *= 0.5f;
+    s_bias[i] = v;
+  }
 
   if (warp == 0 && ptx::elect_one()) {
     for (int i = 0; i < P.L.nsrc; ++i) ptx::prefetch_tensormap(&P.amap[i]);
@@ -460,6 +467,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const int ry = row / kTW;
     const int Cn = tileN / G;
     int iter = 0;
+    const uint32_t sb_lstm = ptx::smem_u32(s_bias);        // lstm_finish reads the staged biases through ld.shared
 #ifdef VPK_TRACE
     long long e_wait = 0, e_body = 0, e_t1 = 0, e_ld = 0;
 #endif
@@ -525,7 +533,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 for (int j = 0; j < 8; ++j)
 #pragma unroll
                   for (int g = 0; g < 4; ++g) a[g][j] = __uint_as_float(r[j * 4 + g]);
-                lstm_finish<PEEP>(E, et, hw, chb + chl, s_bias, a, ops[k], pps[k % PPD]);
+                lstm_finish<PEEP>(E, et, hw, chb + chl, sb_lstm + static_cast<uint32_t>((chb + chl) * 16), a, ops[k], pps[k % PPD]);
               }
               if (validn && chbn + chl < C) lstm_c_load(E, etn, hw, chbn + chl, ops[k]);
               if constexpr (PEEP) {
@@ -631,7 +639,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 for (int j = 0; j < 8; ++j)
 #pragma unroll
                   for (int g = 0; g < 4; ++g) a[g][j] = __uint_as_float(r[j * 4 + g]);
-                lstm_finish<PEEP, false>(E, et, hw, chb + chl, s_bias, a, o, pp[k & 1]);
+                lstm_finish<PEEP, false>(E, et, hw, chb + chl, sb_lstm + static_cast<uint32_t>((chb + chl) * 16), a, o, pp[k & 1]);
                 cp[0] = make_float4(o.c[0], o.c[1], o.c[2], o.c[3]);
                 cp[1] = make_float4(o.c[4], o.c[5], o.c[6], o.c[7]);
                 if (ts == T_steps - 1 && E.s0 != nullptr) st_state8(E.s0, et.st_off, E.state_c4 ? hw * 4 : 0, chb + chl, o.c);

@@ -3,6 +3,7 @@
 // channel chunk hoisted to once per (thread, tile): position decode, 64-bit offsets, layout selection.  The packed
 // bias lives in shared memory (every lane reads the same float4: one broadcast wavefront).  One call = 8 channels.
 #pragma once
+#include "ptx.cuh"
 #include "epilogue.cuh"
 
 namespace vpk {
@@ -317,22 +318,25 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
 }
 
 // STORE_C = false: the new cell state only stays in o.c (sequence mode keeps it in shared memory)
+// `sb` = SHARED-space address of this chunk's 32 staged bias values in the HALVED form of the kernels that use this
+// function (conv_halo.cu stages 0.5 * b for the three sigmoid gates), and the packed peepholes are halved at pack time:
+// sigmoid(z + b + w c) = 0.5 tanh(0.5 z + 0.5 b + (0.5 w) c) + 0.5 then costs FFMA, FFMA, MUFU, FFMA instead of FADD, FFMA,
+// FMUL, MUFU, FFMA -- and, scaling by 0.5 being exact, rounds exactly as the plain form does (bit-identical results).
 template <bool PEEP, bool STORE_C = true>
 __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& t, long long hw, int ch,
-                                            const float* s_bias, float (&acc)[4][8], LstmOps& o, const LstmPeep& pp) {
+                                            uint32_t sb, float (&acc)[4][8], LstmOps& o, const LstmPeep& pp) {
   using bf16 = __nv_bfloat16;
-  const float4* bp = reinterpret_cast<const float4*>(s_bias + ch * 4);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const float4 bv = bp[j];
-    acc[0][j] += bv.x;
-    acc[1][j] += bv.y;
+    const float4 bv = ptx::lds_f4(sb + static_cast<uint32_t>(16 * j));     // (0.5 b_i, 0.5 b_f, b_g, 0.5 b_o)
+    acc[0][j] = fmaf(acc[0][j], 0.5f, bv.x);
+    acc[1][j] = fmaf(acc[1][j], 0.5f, bv.y);
     acc[2][j] += bv.z;
-    acc[3][j] += bv.w;
+    acc[3][j] = fmaf(acc[3][j], 0.5f, bv.w);
   }
   float h[8];
   if constexpr (PEEP) {
-    // peepholes are decoded two channels at a time (one 32-bit word of each gate): 6 transient registers, not 24
+    // peepholes (pre-halved) are decoded two channels at a time (one 32-bit word of each gate): 6 transient registers, not 24
     const uint32_t* pi = reinterpret_cast<const uint32_t*>(&pp.p[0]);
     const uint32_t* pf = reinterpret_cast<const uint32_t*>(&pp.p[1]);
     const uint32_t* po = reinterpret_cast<const uint32_t*>(&pp.p[2]);
@@ -344,10 +348,10 @@ __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& 
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = 2 * q + e;
-        const float ig = sigmoid_fast(fmaf(wi[e], o.c[j], acc[0][j]));
-        const float fg = sigmoid_fast(fmaf(wf[e], o.c[j], acc[1][j]));
+        const float ig = fmaf(0.5f, tanh_fast(fmaf(wi[e], o.c[j], acc[0][j])), 0.5f);
+        const float fg = fmaf(0.5f, tanh_fast(fmaf(wf[e], o.c[j], acc[1][j])), 0.5f);
         const float cn = fmaf(fg, o.c[j], ig * tanh_fast(acc[2][j]));
-        const float og = sigmoid_fast(fmaf(wo[e], cn, acc[3][j]));
+        const float og = fmaf(0.5f, tanh_fast(fmaf(wo[e], cn, acc[3][j])), 0.5f);
         o.c[j] = cn;
         h[j] = og * tanh_fast(cn);
       }
@@ -355,9 +359,10 @@ __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& 
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float cn = fmaf(sigmoid_fast(acc[1][j]), o.c[j], sigmoid_fast(acc[0][j]) * tanh_fast(acc[2][j]));
+      const float ig = fmaf(0.5f, tanh_fast(acc[0][j]), 0.5f), fg = fmaf(0.5f, tanh_fast(acc[1][j]), 0.5f);
+      const float cn = fmaf(fg, o.c[j], ig * tanh_fast(acc[2][j]));
       o.c[j] = cn;
-      h[j] = sigmoid_fast(acc[3][j]) * tanh_fast(cn);
+      h[j] = fmaf(0.5f, tanh_fast(acc[3][j]), 0.5f) * tanh_fast(cn);
     }
   }
   if constexpr (STORE_C) st_state8(E.s0, t.st_off, E.state_c4 ? hw * 4 : 0, ch, o.c);

@@ -117,7 +117,9 @@ class EfConvLstm : public Model {
       for (int c = 0; c < C; ++c)
         for (int y = 0; y < H; ++y)
           for (int x = 0; x < W; ++x) {
-            const __nv_bfloat16 v = __float2bfloat16_rn(p[(static_cast<size_t>(c) * H + y) * W + x]);
+            // halved: lstm_finish folds the 0.5 of sigmoid(z) = 0.5 tanh(0.5 z) + 0.5 into the bias and the peepholes
+            // (exact: scaling by a power of two commutes with the bf16 rounding)
+            const __nv_bfloat16 v = __float2bfloat16_rn(0.5f * p[(static_cast<size_t>(c) * H + y) * W + x]);
             uint16_t u;
             std::memcpy(&u, &v, 2);
             bits[(((static_cast<size_t>(c >> 3) * H + y) * W + x) * 3 + k) * 8 + (c & 7)] = u;
