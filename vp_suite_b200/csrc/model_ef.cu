@@ -158,12 +158,19 @@ class EfConvLstm : public Model {
       xin[n] = arena.alloc(px * d.enc_c[2 * n] * esz * B * t_in);
       hseq_e[n] = arena.alloc(px * d.enc_c[2 * n + 1] * esz * B * t_in);
       hseq_f[n] = arena.alloc(px * d.enc_c[2 * n + 1] * esz * B * pred);      // forecaster layer continuing encoder state n
-      hzero[n] = arena.alloc(px * d.enc_c[2 * n + 1] * esz * B);
       cbuf[n] = static_cast<float*>(arena.alloc(px * d.enc_c[2 * n + 1] * sizeof(float) * B));
     }
     for (int n = 0; n < 3; ++n)
       yseq[n] = arena.alloc(static_cast<size_t>(dh[n + 1]) * dw[n + 1] * d.dec_c[2 * n + 1] * esz * B * pred);
-    unsigned* barriers = static_cast<unsigned*>(arena.alloc(6 * 128));
+    // the zero initial hidden states of the three encoder layers and the six grid-barrier counters: ONE block, one memset node
+    size_t zoff[4] = {0, 0, 0, 0};
+    for (int n = 0; n < 3; ++n)
+      zoff[n + 1] = zoff[n] + (static_cast<size_t>(eh[n]) * ew[n] * d.enc_c[2 * n + 1] * esz * B + 1023) / 1024 * 1024;
+    const size_t zero_bytes = zoff[3] + 6 * 128;
+    char* zero_block = static_cast<char*>(arena.alloc(zero_bytes));
+    if (zero_block != nullptr)
+      for (int n = 0; n < 3; ++n) hzero[n] = zero_block + zoff[n];
+    unsigned* barriers = zero_block ? reinterpret_cast<unsigned*>(zero_block + zoff[3]) : nullptr;
     if (measure) return true;
 
     const float* peep[2][3][3] = {};
@@ -223,8 +230,6 @@ class EfConvLstm : public Model {
     auto conv_ops = [&](const ConvSpec& spec) { add_conv(tmp, spec, false, stream, -1, &body); };
     {
       const int ns = num_sms;
-      const size_t zb[3] = {static_cast<size_t>(eh[0]) * ew[0] * d.enc_c[1] * esz * B, static_cast<size_t>(eh[1]) * ew[1] * d.enc_c[3] * esz * B,
-                            static_cast<size_t>(eh[2]) * ew[2] * d.enc_c[5] * esz * B};
       Op cv;
       cv.name = "frames_to_nhwc";
       const long long chw = static_cast<long long>(c) * h * w;
@@ -235,13 +240,7 @@ class EfConvLstm : public Model {
       Op z;
       z.name = "zero_h0_barriers";
       z.is_kernel = false;
-      void* hz0 = hzero[0]; void* hz1 = hzero[1]; void* hz2 = hzero[2];
-      z.fn = [=](cudaStream_t s, const RunCtx&) {
-        VPK_CUDA(cudaMemsetAsync(hz0, 0, zb[0], s));
-        VPK_CUDA(cudaMemsetAsync(hz1, 0, zb[1], s));
-        VPK_CUDA(cudaMemsetAsync(hz2, 0, zb[2], s));
-        VPK_CUDA(cudaMemsetAsync(barriers, 0, 6 * 128, s));
-      };
+      z.fn = [=](cudaStream_t s, const RunCtx&) { VPK_CUDA(cudaMemsetAsync(zero_block, 0, zero_bytes, s)); };
       body.push_back(std::move(z));
     }
     // ---------------- encoder, layer-major ----------------
