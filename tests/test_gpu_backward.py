@@ -237,3 +237,38 @@ def test_ef_convlstm_trains_like_the_reference():
         after = float(torch.nn.functional.mse_loss(m(x.to(dev), pred_frames=pred)[0], target.to(dev)))
     print(f"train_iter: mse {before:.5f} -> {after:.5f}")
     assert after < before
+
+
+def test_ef_convlstm_train_iter_in_16_bit_mode():
+    """The default (bf16-operand) mode trains too: finite gradients on every parameter, the loss falls over a few Adam steps,
+    and eval() afterwards is the native rollout again (weights re-mirrored into the library after the optimizer steps)."""
+    import vp_suite_b200 as V
+    from oracle.weights import synth_frames
+    dev, img, b, ctx, pred = "cuda:0", (3, 32, 32), 2, 2, 2
+    m = V.MODEL_CLASSES["convlstm-shi"](dev, img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0])
+    m.load_state_dict(synth_state_dict({k: tuple(v.shape) for k, v in m.state_dict().items()}, seed=71, gain=2.5))
+    x, target = synth_frames(b, ctx, *img, seed=72), synth_frames(b, pred, *img, seed=73)
+
+    class _Loss:
+        def get_losses(self, p, t):
+            v = torch.nn.functional.mse_loss(p, t)
+            return {"mse": v.detach()}, v
+
+    def mse():
+        m.eval()
+        with torch.no_grad():
+            v = float(torch.nn.functional.mse_loss(m(x.to(dev), pred_frames=pred)[0], target.to(dev)))
+        m.train()
+        return v
+
+    before = mse()
+    out, _ = m(x.to(dev), pred_frames=pred)
+    torch.nn.functional.mse_loss(out, target.to(dev)).backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    m.zero_grad()
+    loader = [{"frames": torch.cat([x, target], dim=1), "actions": torch.zeros(b, ctx + pred - 1, 0)}] * 8
+    cfg = {"context_frames": ctx, "pred_frames": pred, "device": dev, "use_actions": False, **m.config}
+    m.train_iter(cfg, loader, torch.optim.Adam(m.parameters(), lr=2e-3), _Loss(), epoch=0)
+    after = mse()
+    print(f"bf16-mode train_iter: mse {before:.5f} -> {after:.5f}")
+    assert after < before
