@@ -591,11 +591,22 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const int chb = nt * Cn;
             const bool valid = (x < P.L.W) && (y < P.L.H) && (b < P.L.B);
             LstmTile et{};
+            // everything the chunks address is prepared here, BEFORE the accumulator wait (this part overlaps the tile's
+            // MMAs; what follows the wait is exposed once per timestep): h' / peephole / shared-state pointers of chunk 0,
+            // chunk k = + k * constant
+            bf16* hout0 = nullptr;
+            float* h32out0 = nullptr;
+            const uint4* pp0 = nullptr;
             if (valid) {
               et = lstm_tile(E, b, y, x, P.L.H, P.L.W);      // st_off: c_0 / c_T in global memory, indexed by the sequence b
               const long long bo = static_cast<long long>(b) * P.seq_out_sb + static_cast<long long>(ts) * P.seq_out_st + P.seq_out_off;
               et.out_off = bo * E.oB + y * E.oY + x * E.oX;  // h'_t: slot (b, ts) of the output sequence
+              hout0 = static_cast<bf16*>(E.out) + et.out_off + chb + half * 8;
+              if (E.h32 != nullptr) h32out0 = E.h32 + et.out_off + chb + half * 8;
+              if constexpr (PEEP) pp0 = static_cast<const uint4*>(E.pp16) + (static_cast<long long>((chb >> 3) + half) * hw + et.pos) * 3;
             }
+            const long long pp_step = 2 * hw * 3;             // uint4 units between this warp's consecutive chunks (16 channels)
+            float4* const cp0 = reinterpret_cast<float4*>(s_cstate + ((static_cast<size_t>(slot) * chunks + half) * 128 + row) * 8);
             const int acc = iter & 1;
 #ifdef VPK_TRACE
             const long long q_t0 = clock64();
@@ -609,18 +620,24 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
             LstmPeep pp[2];
+            auto peep_ld = [&](int k, LstmPeep& dst) {
+              const uint4* q = pp0 + k * pp_step;
+              dst.p[0] = __ldg(q);
+              dst.p[1] = __ldg(q + 1);
+              dst.p[2] = __ldg(q + 2);
+            };
             if constexpr (PEEP)
-              if (valid && chb + half * 8 < C) lstm_peep_load(E, et, hw, chb + half * 8, pp[0]);
+              if (valid && chb + half * 8 < C) peep_ld(0, pp[0]);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
               const int chl = (half + 2 * k) * 8;
               uint32_t r[32];
               ptx::tmem_ld32(taddr + static_cast<uint32_t>(chl * 4), r);
               if constexpr (PEEP)
-                if (k + 1 < NCH && valid && chb + chl + 16 < C) lstm_peep_load(E, et, hw, chb + chl + 16, pp[(k + 1) & 1]);
+                if (k + 1 < NCH && valid && chb + chl + 16 < C) peep_ld(k + 1, pp[(k + 1) & 1]);
               ptx::tmem_ld_wait();
               if (valid && chb + chl < C) {
-                float4* cp = reinterpret_cast<float4*>(s_cstate + ((static_cast<size_t>(slot) * chunks + (chl >> 3)) * 128 + row) * 8);
+                float4* cp = cp0 + k * (2 * 128 * 2);          // chunk (half + 2k): 2 chunks x 128 rows x 2 float4 further
                 LstmOps o;
                 if (ts == 0) {
                   if (P.seq_c_zero) {
@@ -639,7 +656,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 for (int j = 0; j < 8; ++j)
 #pragma unroll
                   for (int g = 0; g < 4; ++g) a[g][j] = __uint_as_float(r[j * 4 + g]);
-                lstm_finish<PEEP, false>(E, et, hw, chb + chl, sb_lstm + static_cast<uint32_t>((chb + chl) * 16), a, o, pp[k & 1]);
+                lstm_finish<PEEP, false, true>(E, et, hw, chb + chl, sb_lstm + static_cast<uint32_t>((chb + chl) * 16), a, o, pp[k & 1],
+                                               hout0 + 16 * k, h32out0 != nullptr ? h32out0 + 16 * k : nullptr);
                 cp[0] = make_float4(o.c[0], o.c[1], o.c[2], o.c[3]);
                 cp[1] = make_float4(o.c[4], o.c[5], o.c[6], o.c[7]);
                 if (ts == T_steps - 1 && E.s0 != nullptr) st_state8(E.s0, et.st_off, E.state_c4 ? hw * 4 : 0, chb + chl, o.c);

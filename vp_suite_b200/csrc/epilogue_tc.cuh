@@ -322,9 +322,10 @@ __device__ __forceinline__ void bf16x8_to_f32(const uint4& v, float (&f)[8]) {
 // function (conv_halo.cu stages 0.5 * b for the three sigmoid gates), and the packed peepholes are halved at pack time:
 // sigmoid(z + b + w c) = 0.5 tanh(0.5 z + 0.5 b + (0.5 w) c) + 0.5 then costs FFMA, FFMA, MUFU, FFMA instead of FADD, FFMA,
 // FMUL, MUFU, FFMA -- and, scaling by 0.5 being exact, rounds exactly as the plain form does (bit-identical results).
-template <bool PEEP, bool STORE_C = true>
+template <bool PEEP, bool STORE_C = true, bool PTR_OUT = false>
 __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& t, long long hw, int ch,
-                                            uint32_t sb, float (&acc)[4][8], LstmOps& o, const LstmPeep& pp) {
+                                            uint32_t sb, float (&acc)[4][8], LstmOps& o, const LstmPeep& pp,
+                                            __nv_bfloat16* hout = nullptr, float* h32out = nullptr) {
   using bf16 = __nv_bfloat16;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -366,8 +367,13 @@ __device__ __forceinline__ void lstm_finish(const EpiParams& E, const LstmTile& 
     }
   }
   if constexpr (STORE_C) st_state8(E.s0, t.st_off, E.state_c4 ? hw * 4 : 0, ch, o.c);
-  st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
-  if (E.h32 != nullptr) st_f32x8(E.h32 + t.out_off + ch, h);
+  if constexpr (PTR_OUT) {      // sequence mode: the chunk's h' address was prepared before the accumulator wait
+    st_bf16x8(hout, h);
+    if (h32out != nullptr) st_f32x8(h32out, h);
+  } else {
+    st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
+    if (E.h32 != nullptr) st_f32x8(E.h32 + t.out_off + ch, h);
+  }
 }
 
 }  // namespace vpk
