@@ -307,7 +307,10 @@ class EfConvLstm : public Model {
         da.proj_b = dev_f32("forecaster.stage1.final.bias", fb.data, stream);
       }
       const long long tiles = static_cast<long long>(B) * pred * ((dh[n] + 15) / 16) * ((dw[n] + 7) / 8);
-      const bool subpix = deconv_subpix_ok(da) && tiles <= 2ll * num_sms;
+      // latency mode: one sub-pixel launch (2.25x the contraction) still beats four per-parity launches up to ~6 tiles per
+      // SM (cfg 1, stage 2: 640 tiles, 1.0015 -> 0.9990 ms per rollout)
+      bool subpix = deconv_subpix_ok(da) && tiles <= 6ll * num_sms;
+      if (const char* sp_env = getenv("VPK_SUBPIX")) subpix = deconv_subpix_ok(da) && atoi(sp_env) != 0;
       if (subpix) conv_ops(deconv_subpix_spec(da, act, &oh, &ow));
       else conv_ops(deconv_spec(da, act, &oh, &ow));
       fin = yseq[n];
