@@ -27,7 +27,7 @@ def main():
     tot = sum(r[2] for r in rows)
     print("# r02: `ncu --set full` over one timestep's tcgen05 launches of the cfg-5 rollout (64 sequences, final build)\n")
     print("Command (on the B200 box): `ncu --set full --clock-control none --import-source on -k regex:conv_halo_kernel "
-          "--launch-skip 45 --launch-count 17 -o gpurun_out/r02_ncu_cfg5_step_b64_v2 python tools/run_once.py cfg5 64` "
+          "--launch-skip 45 --launch-count 17 -o gpurun_out/r02_ncu_cfg5_step_b64_v3 python tools/run_once.py cfg5 64` "
           "(`tools/r02_evidence.sh`).")
     print("17 consecutive launches = one of every layer shape of the rollout (cold caches, serialised replays: compare "
           "shares and ratios, not absolutes).\n")
