@@ -104,6 +104,7 @@ struct ConvArgs {
   bool f32_strided = false; // out is float*, strides below
   long long oB = 0, oY = 0, oX = 0, oC = 0;
   bool out_f32_dense = false;   // out is float*, dense NHWC [B, OH, OW, out_pix] (out_pix >= Cout channels per pixel)
+  bool out_f16 = false;         // fp16 operands on the halo kernel's lean epilogue: `out` is __half* (GroupNorm-fed raw convs)
   int out_pix = 0;              // pixel stride of a dense output (0: Cout)
   const float* res = nullptr;   // fp32 dense [B, OH, OW, Cout] residual added after the activation
   bool split = false;           // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
@@ -145,6 +146,7 @@ inline ConvSpec conv_spec(const ConvArgs& a, const ActInfo& act, int* oh, int* o
   } else {
     dense_out(e, a.out, *oh, *ow, a.out_pix > 0 ? a.out_pix : a.Cout);
     e.out_f32 = a.out_f32_dense ? 1 : 0;
+    e.out_f16 = (a.out_f16 && !a.out_f32_dense) ? 1 : 0;
   }
   e.res = a.res;
   return s;
@@ -162,6 +164,7 @@ struct DeconvArgs {
   int act;
   void* out;
   bool out_f32 = false;       // element type of `out` is float regardless of the activation type
+  bool out_f16 = false;       // fp16 operands on the halo kernel's lean epilogue: `out` is __half*
   bool nchw = false;          // fp32 NCHW output (implies out_f32)
   long long oB_nchw = 0;
   bool split = false;         // split-bf16 input: x holds the high parts, x_lo the low parts (same layout)
@@ -232,6 +235,7 @@ inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, in
   }
   const int C = a.Cout, actk = a.act;
   const bool f32 = a.out_f32 || a.nchw, nchw = a.nchw;
+  const bool f16o = a.out_f16 && !f32;
   const size_t esz = f32 ? sizeof(float) : static_cast<size_t>(act.esize);
   const long long oBn = a.oB_nchw;
   void* out = a.out;
@@ -246,6 +250,7 @@ inline ConvSpec deconv_spec(const DeconvArgs& a, const ActInfo& act, int* oh, in
                          e.kind = EPI_BIAS_ACT;
                          e.act = actk;
                          e.out_f32 = f32 ? 1 : 0;
+                         e.out_f16 = f16o ? 1 : 0;
                          e.proj_w = pw;
                          e.proj_b = pb;
                          e.proj_n = pn;

@@ -82,6 +82,7 @@ struct EpiParams {
   int C;                  // real output channels per gate
   int act;
   int out_f32;            // primary output element type: 0 = activation type T, 1 = float
+  int out_f16;            // tcgen05 halo kernel, lean BIAS_ACT epilogue only: the 16-bit output is fp16, not bf16
   const float* bias;      // packed order [N_pad] or nullptr
   // primary output (BIAS_ACT: y; LSTM / ST_O / PHY_GATE: h'), address = out + b*oB + y*oY + x*oX + ch*oC
   void* out;

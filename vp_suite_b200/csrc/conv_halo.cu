@@ -781,6 +781,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         bf16* const outp = static_cast<bf16*>(E.out) + half * 8;
         const uint32_t tq = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(half * 8);
         const float slope = E.act == ACT_LEAKY ? 0.2f : 1.f;
+        const bool f16o = E.out_f16 != 0;                    // 16-bit output as fp16 (fp16-operand launches), else bf16
         auto run = [&](auto nj_c, auto relu_c, auto tma_c, auto stats_c) {
           constexpr int NJ = decltype(nj_c)::value;          // this warp's 8-channel chunks: channels half * 8 + 16 j
           constexpr bool RELU = decltype(relu_c)::value;
@@ -802,9 +803,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               nt = static_cast<uint32_t>(t) - mu * static_cast<uint32_t>(P.n_tiles);
             }
             const uint32_t mt = MC ? ((mu * 2 + prank) * 2 + rank) : (mu * (PAIR ? 2u : 1u) + rank);
-            const int b = static_cast<int>(__umulhi(mt, P.magic_tpi));
+            const int b = static_cast<int>(tpi == 1 ? mt : __umulhi(mt, P.magic_tpi));
             const uint32_t rem = mt - static_cast<uint32_t>(b) * tpi;
-            const int ty = static_cast<int>(__umulhi(rem, P.magic_tx));
+            const int ty = static_cast<int>(P.tiles_x == 1 ? rem : __umulhi(rem, P.magic_tx));
             const int tx = static_cast<int>(rem) - ty * P.tiles_x;
             const int ch_base = static_cast<int>(nt) * Cn;
             const int x = tx * kTW + rx, y = ty * kTH + ry;
@@ -861,14 +862,30 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
               }
               if constexpr (TMA) {
                 uint4 pk;
-                __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+                if (f16o) {
+                  __half2* h2 = reinterpret_cast<__half2*>(&pk);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                  for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                } else {
+                  __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+                  for (int k = 0; k < 4; ++k) h2[k] = __floats2bfloat162_rn(v[2 * k], v[2 * k + 1]);
+                }
                 // channel half * 8 + 16 j: sub-tile j / 2, 16-byte chunk (half + 2 j) % 4 of its row
                 const uint32_t chunk = NJ == 1 ? static_cast<uint32_t>(half) : static_cast<uint32_t>((half + 2 * j) & 3);
                 ptx::sts_u4(sbuf + static_cast<uint32_t>(j >> 1) * kSubBytes + ((chunk ^ sxor) << 4), pk);
               } else {
-                if (valid) st_bf16x8(o + 16 * j, v);
+                if (valid) {
+                  if (f16o) {
+                    uint4 pk;
+                    __half2* h2 = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) h2[k] = __floats2half2_rn(v[2 * k], v[2 * k + 1]);
+                    *reinterpret_cast<uint4*>(o + 16 * j) = pk;
+                  } else {
+                    st_bf16x8(o + 16 * j, v);
+                  }
+                }
               }
               if constexpr (STATS) {       // positions outside the image contribute zeros
                 if (!valid) {
@@ -1359,10 +1376,11 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
     P.magic_tpi = tpi > 1 ? magic(tpi) : 0u;
     P.magic_tx = P.tiles_x > 1 ? magic(static_cast<unsigned long long>(P.tiles_x)) : 0u;
     P.lean = (P.fast_epi && L.epi.kind == EPI_BIAS_ACT && L.G == 1 && L.epi.proj_n == 0 && L.epi.res == nullptr &&
-              !L.epi.out_f32 && cn % 16 == 0 && L.N_pad == L.epi.C && magic_ok && tpi > 1 && P.tiles_x > 1 &&
+              !L.epi.out_f32 && cn % 16 == 0 && L.N_pad == L.epi.C && magic_ok &&
               (gn ? (gs > 0 && nj <= 4 && L.epi.act != ACT_RELU) : (nj == 1 || nj == 2 || nj == 3 || nj == 4 || nj == 6)) &&
               (L.epi.act == ACT_NONE || L.epi.act == ACT_LEAKY || L.epi.act == ACT_RELU)) ? 1 : 0;
-    if (const char* env = getenv("VPK_EPI_LEAN")) P.lean = P.lean && atoi(env) != 0;
+    if (const char* env = getenv("VPK_EPI_LEAN")) P.lean = P.lean && (atoi(env) != 0 || L.epi.out_f16);
+    VPK_REQUIRE(!L.epi.out_f16 || P.lean, "halo plan: fp16 outputs need the lean BIAS_ACT epilogue");
     // staged bulk-tensor stores: 16 / 32 / 64 / 96 channels (whole 32-channel sub-tiles), 16-byte aligned strides
     P.lean_tma = (P.lean && reserve_smem == 0 && (nj == 1 || nj == 2 || nj == 4 || nj == 6) && L.epi.oC == 1 &&
                   L.epi.oX % 8 == 0 && L.epi.oY % 8 == 0 && L.epi.oB % 8 == 0 &&

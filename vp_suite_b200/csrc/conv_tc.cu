@@ -250,7 +250,8 @@ template <int G> void set_smem_attr() {
 bool tc_eligible(const ConvLaunch& L, int dtype) {
   if (dtype != DT_BF16 && dtype != DT_F16) return false;
   // fp16 operands: the tensor-core epilogues store activation-type outputs as bf16, so fp16 launches are fp32-out only
-  if (dtype == DT_F16 && !((L.epi.kind == EPI_BIAS_ACT && L.epi.out_f32) || L.epi.kind == EPI_DECOUPLE)) return false;
+  // (or fp16-out through the halo kernel's lean epilogue: out_f16, checked again by halo_make_plan)
+  if (dtype == DT_F16 && !((L.epi.kind == EPI_BIAS_ACT && (L.epi.out_f32 || L.epi.out_f16)) || L.epi.kind == EPI_DECOUPLE)) return false;
   if (L.G < 1 || L.G > 4) return false;
   const int tileN = L.Cn * L.G;
   if (L.Cn % 8 != 0 || tileN % 16 != 0 || tileN > 256 || L.N_pad % tileN != 0) return false;

@@ -782,8 +782,8 @@ __global__ void __launch_bounds__(kGnThreads) groupnorm_smem_kernel(const float*
 // y = (x - mean) * rstd * gamma + beta, LeakyReLU, optional fp32 add.
 // One block = one slice of ONE sample (blockIdx.y = sample), so scale / shift per channel are computed once per block.
 // OUT as in groupnorm_smem_kernel (0 fp32, 1 bf16, 3 fp16).  var = E[x^2] - mean^2 in fp32 (n <= a few thousand).
-template <int OUT>
-__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __restrict__ in, void* __restrict__ out,
+template <int OUT, bool IN16>
+__global__ void __launch_bounds__(256) groupnorm_apply_kernel(const void* __restrict__ in_, void* __restrict__ out,
                                                               const float* __restrict__ add,
                                                               const float* __restrict__ sums, int nslots, int HW, int C,
                                                               int groups,
@@ -813,11 +813,20 @@ __global__ void __launch_bounds__(256) groupnorm_apply_kernel(const float* __res
   __syncthreads();
   const int n4 = HW * C / 4;
   const size_t obase = static_cast<size_t>(b) * n4;
-  const float4* src = reinterpret_cast<const float4*>(in) + obase;
+  // IN16: the producing conv stored its raw output as fp16 (its statistics came from the fp32 accumulators)
+  const float4* src = reinterpret_cast<const float4*>(in_) + (IN16 ? 0 : obase);
+  const uint2* src16 = reinterpret_cast<const uint2*>(in_) + (IN16 ? obase : 0);
   const float4* addp = add ? reinterpret_cast<const float4*>(add) + obase : nullptr;
   for (int i = blockIdx.x * 256 + threadIdx.x; i < n4; i += gridDim.x * 256) {
     const int c0 = (i * 4) % C;
-    const float4 x = src[i];
+    float4 x;
+    if constexpr (IN16) {
+      const uint2 q = src16[i];
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+      x = make_float4(a.x, a.y, b.x, b.y);
+    } else {
+      x = src[i];
+    }
     float v[4] = {fmaf(x.x, s_sc[c0], s_sh[c0]), fmaf(x.y, s_sc[c0 + 1], s_sh[c0 + 1]), fmaf(x.z, s_sc[c0 + 2], s_sh[c0 + 2]),
                   fmaf(x.w, s_sc[c0 + 3], s_sh[c0 + 3])};
     if (act == ACT_LEAKY) {
@@ -1255,7 +1264,7 @@ bool groupnorm_apply_supported(int HW, int C, int groups) {
   return C % 4 == 0 && C <= 256 && C % groups == 0 && (HW * C) % 4 == 0;
 }
 
-void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int nslots,
+void launch_groupnorm_apply(const void* in, int in_f16, void* out, int out_kind, const float* add, const float* sums, int nslots,
                             int B, int HW, int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
                             cudaStream_t stream) {
   VPK_REQUIRE(groupnorm_apply_supported(HW, C, groups), "groupnorm_apply: unsupported shape");
@@ -1264,12 +1273,17 @@ void launch_groupnorm_apply(const float* in, void* out, int out_kind, const floa
   // ~2 waves of blocks over the whole batch, at least one block per sample
   const int per = std::max(1, std::min((n4 + 1023) / 1024, std::max(1, 2 * num_sms * 8 / std::max(1, B))));
   const dim3 grid(per, B);
-  if (out_kind == 0)
-    launch_pdl(groupnorm_apply_kernel<0>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act);
-  else if (out_kind == 1)
-    launch_pdl(groupnorm_apply_kernel<1>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act);
-  else
-    launch_pdl(groupnorm_apply_kernel<3>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act);
+#define VPK_GNA(OUT)                                                                                                          \
+  do {                                                                                                                        \
+    if (in_f16)                                                                                                               \
+      launch_pdl(groupnorm_apply_kernel<OUT, true>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act); \
+    else                                                                                                                      \
+      launch_pdl(groupnorm_apply_kernel<OUT, false>, grid, dim3(256), 0, stream, in, out, add, sums, nslots, HW, C, groups, gamma, beta, eps, act); \
+  } while (0)
+  if (out_kind == 0) VPK_GNA(0);
+  else if (out_kind == 1) VPK_GNA(1);
+  else VPK_GNA(3);
+#undef VPK_GNA
 }
 
 void launch_split_bf16(const float* in, void* hi, void* lo, long long n, int num_sms, cudaStream_t stream) {

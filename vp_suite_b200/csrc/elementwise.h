@@ -58,7 +58,7 @@ void launch_groupnorm_smem(const float* in, void* out, void* out_lo, int out_kin
 // fp32 -> split-bf16: hi = bf16(v), lo = bf16(v - hi)
 // GroupNorm whose partial statistics the producing conv's epilogue wrote: sums[b][slot][group][2] (sum, sum of squares)
 bool groupnorm_apply_supported(int HW, int C, int groups);
-void launch_groupnorm_apply(const float* in, void* out, int out_kind, const float* add, const float* sums, int nslots,
+void launch_groupnorm_apply(const void* in, int in_f16, void* out, int out_kind, const float* add, const float* sums, int nslots,
                             int B, int HW, int C, int groups, const float* gamma, const float* beta, float eps, int act, int num_sms,
                             cudaStream_t stream);
 // per-(sample, frame) sum of squared errors (fp64), then per-frame sums over the batch of the SSE and of

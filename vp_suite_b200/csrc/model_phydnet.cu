@@ -239,7 +239,7 @@ class PhyDNetModel : public Model {
     float* gn_region = static_cast<float*>(arena.alloc(static_cast<size_t>(B) * tb * gn_max_slots * 16 * 2 * sizeof(float)));
     // GroupNorm (+ LeakyReLU) of the fp32 conv output `in` into a feature map / cell operand / fp32 tensor
     auto gn_op = [&](const std::string& key, const float* in, OutKind kind, Feat out, const float* add, int HW, int C,
-                     int groups, int actk, const float* sums = nullptr, int nslots = 0) {
+                     int groups, int actk, const float* sums = nullptr, int nslots = 0, bool raw16 = false) {
       if (measure) return;
       const float* g = dev_f32(key + "weight", vec(key + "weight"), stream);
       const float* bta = dev_f32(key + "bias", vec(key + "bias"), stream);
@@ -250,8 +250,9 @@ class PhyDNetModel : public Model {
       op.name = "groupnorm " + key;
       if (sums != nullptr) {
         const int ok = (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
+        const int in16 = raw16 ? 1 : 0;     // the fused-statistics convs leave their raw output as fp16 (see dcgan below)
         op.fn = [=](cudaStream_t s, const RunCtx&) {
-          launch_groupnorm_apply(in, out.a, ok, add, sums, nslots, Bx, HW, C, groups, g, bta, 1e-5f, actk, ns, s);
+          launch_groupnorm_apply(in, in16, out.a, ok, add, sums, nslots, Bx, HW, C, groups, g, bta, 1e-5f, actk, ns, s);
         };
       } else if (groupnorm_smem_supported(HW, C, groups)) {
         const int ok = two ? 2 : (out_dt == DT_BF16 ? 1 : out_dt == DT_F16 ? 3 : 0);
@@ -292,10 +293,16 @@ class PhyDNetModel : public Model {
         }
         return sp_;
       };
+      // With the statistics fused into the epilogue (taken from the fp32 accumulators), the raw conv output only feeds
+      // the GroupNorm apply pass: stored as fp16 it halves that round trip, and the conv runs the lean epilogue with staged
+      // bulk stores (16-bit outputs only).  The separate-statistics paths keep fp32 raw values.
+      const char* fe_env = getenv("VPK_TC_FAST_EPI");
+      const bool raw16 = sums != nullptr && getenv("VPK_GN_RAW32") == nullptr && (fe_env == nullptr || atoi(fe_env) != 0);
       if (!transpose) {
         ConvArgs a{p + "main.0.", Bcur, H, W, Cin, Cout, 3, stride, 1, in.a, hp(p + "main.0.weight"), hp(p + "main.0.bias"),
                    ACT_NONE, raw};
-        a.out_f32_dense = true;
+        a.out_f32_dense = !raw16;
+        a.out_f16 = raw16;
         a.split = sp;
         a.x_lo = in.lo;
         a.cin_w = cin_w;
@@ -303,13 +310,14 @@ class PhyDNetModel : public Model {
       } else {
         DeconvArgs a{p + "main.0.", Bcur, H, W, Cin, Cout, 3, stride, 1, stride == 2 ? 1 : 0, in.a, hp(p + "main.0.weight"),
                      hp(p + "main.0.bias"), ACT_NONE, raw};
-        a.out_f32 = true;
+        a.out_f32 = !raw16;
+        a.out_f16 = raw16;
         a.split = sp;
         a.x_lo = in.lo;
         add_conv(prog, with_stats(deconv_spec(a, ai, &oh, &ow)), measure, stream, ai.dtype);
       }
       if (sums != nullptr && !groupnorm_apply_supported(oh * ow, Cout, 16)) VPK_THROW(1, "groupnorm_apply: unsupported shape");
-      gn_op(p + "main.1.", raw, kind, out, add, oh * ow, Cout, 16, ACT_LEAKY, sums, nslots);
+      gn_op(p + "main.1.", raw, kind, out, add, oh * ow, Cout, 16, ACT_LEAKY, sums, nslots, raw16);
     };
     auto split_op = [&](const float* src, Feat dst, size_t n, const char* name) {
       if (measure) return;
