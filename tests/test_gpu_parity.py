@@ -413,6 +413,9 @@ SWITCHES = [
     ("VPK_EPI_LEAN=0", "phy_1x64", True),
     ("VPK_EPI_TMA=0", "ef_1x64", True),
     ("VPK_EPI_TMA=0", "phy_3x64", True),
+    # GroupNorm-fed DCGAN convs: fp32 raw outputs + general epilogue instead of fp16 raw outputs + lean epilogue
+    ("VPK_GN_RAW32=1", "phy_3x64", False),
+    ("VPK_GN_RAW32=1", "branch_1x64", False),
     # small batches use the sub-pixel deconv by default: the per-parity form adds the same products in the same order
     ("VPK_SUBPIX=0", "ef_3x32", True),
     ("VPK_SUBPIX=0", "ef_1x64", True),
