@@ -50,6 +50,9 @@ typedef struct vpk_model vpk_model;
 #define VPK_MODEL_PHY 2             /* PhyDNet          models/phydnet.py:12-137   (non action-conditional)     */
 #define VPK_MODEL_CONVLSTM_BRANCH 3 /* DCGANEncoder->EncoderSplit->SingleStepConvLSTM->DecoderSplit->DCGANDecoder */
 #define VPK_MODEL_TRAJGRU 5         /* EF_TrajGRU       models/precipitation_nowcasting/ef_traj_gru.py:8-119                 */
+#define VPK_MODEL_PREDRNN_PP_CAUSAL 6 /* PredRNN++ as published (Causal LSTM stack + gradient highway unit; Wang et al., ICML 2018):
+                                       named by the north star, ABSENT from the reference checkout -> parity unpinned
+                                       (checker: oracle/causal.py); uses patch_size, num_layers >= 2, num_hidden, filter_size */
 #define VPK_MODEL_ST_PHY 4          /* STPhy            models/st_phy.py:16-181    (non action-conditional); uses num_layers,
                                        num_hidden[0] = st_cell_channels, phycell_channels, phycell_kernel_size          */
 

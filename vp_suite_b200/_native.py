@@ -15,7 +15,7 @@ LIB_PATH = os.environ.get("VPK_LIB_PATH") or os.path.join(_HERE, "libvpk.so")
 VPK_PREC_FP32, VPK_PREC_BF16 = 0, 1
 VPK_BACKEND_AUTO, VPK_BACKEND_SIMT = 0, 1
 (VPK_MODEL_CONVLSTM_SHI, VPK_MODEL_PREDRNN_PP, VPK_MODEL_PHY, VPK_MODEL_CONVLSTM_BRANCH, VPK_MODEL_ST_PHY,
- VPK_MODEL_TRAJGRU) = 0, 1, 2, 3, 4, 5
+ VPK_MODEL_TRAJGRU, VPK_MODEL_PREDRNN_PP_CAUSAL) = 0, 1, 2, 3, 4, 5, 6
 
 PRECISIONS = {"fp32": VPK_PREC_FP32, "bf16": VPK_PREC_BF16}
 BACKENDS = {"auto": VPK_BACKEND_AUTO, "simt": VPK_BACKEND_SIMT}

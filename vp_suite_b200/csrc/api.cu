@@ -95,6 +95,7 @@ int vpk_model_create(const vpk_model_desc* desc, vpk_model** out) {
       case VPK_MODEL_CONVLSTM_BRANCH: m = vpk::make_phydnet(*desc, true); break;
       case VPK_MODEL_ST_PHY: m = vpk::make_stphy(*desc); break;
       case VPK_MODEL_TRAJGRU: m = vpk::make_ef_trajgru(*desc); break;
+      case VPK_MODEL_PREDRNN_PP_CAUSAL: m = vpk::make_predrnnpp_causal(*desc); break;
       default: VPK_THROW(VPK_ERR_INVALID, "unknown model kind");
     }
     *out = new vpk_model{m};

@@ -125,6 +125,12 @@ struct EpiParams {
                           //   gn_sums[b][slot][2] with slot = gn_slot0 + ((tile in image) * n_tiles + N tile) * 8 + quadrant * 2 + half
   int gn_slot0, gn_nslots;
   long long ps_row;       // EPI_SUBPIX: elements between two output rows (OW * C)
+  // Causal LSTM / GHU (PredRNN++, causal.h) reuse the ST-LSTM epilogue instantiations with a warp-uniform variant:
+  //   EPI_ST_C, variant 1: acc = (i', f', g', m_m)   m' = sig(f' + forget_bias) tanh(m_m) + sig(i') tanh(g'); stores m' to s0
+  //                        (fp32, no read) and t0 (activation copy); s1 / t1 untouched
+  //   EPI_ST_O, variant 1: acc = (o - o_part, last)  h' = tanh(o_part + acc0) * tanh(acc1)
+  //   EPI_ST_O, variant 2: acc = (p, u), s0 = z      z' = sig(u) z + (1 - sig(u)) tanh(p); stores z' to s0 and `out`
+  int variant;
 };
 
 struct ConvLaunch {

@@ -282,6 +282,14 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y
       store_state<NCH>(E.s0, sa, o.a, nvalid);
       store_act<NCH>(static_cast<T*>(E.out) + b * E.oB + y * E.oY + x * E.oX + ch0, h, nvalid);
       if (E.h32 != nullptr) store_f32<NCH>(E.h32 + pix * C + ch0, h, nvalid);
+    } else if (E.variant == 1) {   // Causal LSTM spatial memory (causal.h): acc = (i', f', g', m_m)
+      float mn[NCH];
+#pragma unroll
+      for (int j = 0; j < NCH; ++j)
+        mn[j] = sigmoid_t<FAST>(acc[1][j] + E.forget_bias) * tanh_t<FAST>(acc[3][j]) +
+                sigmoid_t<FAST>(acc[0][j]) * tanh_t<FAST>(acc[2][j]);
+      store_state<NCH>(E.s0, sa, mn, nvalid);
+      store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, mn, nvalid);
     } else {   // EPI_ST_C: predrnn.py:65-70; acc = (i, f, g, o_x + o_h)
       float dc[NCH], op[NCH];
 #pragma unroll
@@ -295,7 +303,7 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y
       store_state<NCH>(E.s0, sa, o.a, nvalid);
       store_state<NCH>(E.s1, sa, op, nvalid);
       store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, o.a, nvalid);
-      store_act<NCH>(static_cast<T*>(E.t1) + pix * C + ch0, dc, nvalid);
+      if (E.t1 != nullptr) store_act<NCH>(static_cast<T*>(E.t1) + pix * C + ch0, dc, nvalid);
     }
   } else if constexpr (G == 3) {   // EPI_ST_M: predrnn.py:72-77; acc = (i', f', g')
     float dm[NCH];
@@ -308,11 +316,23 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y
     }
     store_state<NCH>(E.s0, state_addr(E, b, y, x, H, W, ch0, true), o.a, nvalid);
     store_act<NCH>(static_cast<T*>(E.t0) + pix * E.t0_pix + ch0, o.a, nvalid);
-    store_act<NCH>(static_cast<T*>(E.t1) + pix * C + ch0, dm, nvalid);
+    if (E.t1 != nullptr) store_act<NCH>(static_cast<T*>(E.t1) + pix * C + ch0, dm, nvalid);
   } else if constexpr (G == 2) {   // EPI_ST_O: predrnn.py:79-80; acc = (conv_o(mem), conv_last(mem))
     float h[NCH];
+    if (E.variant == 2) {   // gradient highway unit (causal.h): acc = (p, u), o.a = z
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) h[j] = sigmoid_t<FAST>(o.a[j] + acc[0][j]) * tanh_t<FAST>(acc[1][j]);
+      for (int j = 0; j < NCH; ++j) {
+        const float u = sigmoid_t<FAST>(acc[1][j]);
+        h[j] = u * o.a[j] + (1.f - u) * tanh_t<FAST>(acc[0][j]);
+      }
+      store_state<NCH>(E.s0, state_addr(E, b, y, x, H, W, ch0, true), h, nvalid);
+    } else if (E.variant == 1) {   // Causal LSTM output: tanh output gate
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) h[j] = tanh_t<FAST>(o.a[j] + acc[0][j]) * tanh_t<FAST>(acc[1][j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) h[j] = sigmoid_t<FAST>(o.a[j] + acc[0][j]) * tanh_t<FAST>(acc[1][j]);
+    }
     store_act<NCH>(static_cast<T*>(E.out) + b * E.oB + y * E.oY + x * E.oX + ch0, h, nvalid);
   }
 }

@@ -237,6 +237,15 @@ __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile&
     st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
     if (E.h32 != nullptr) st_f32x8(E.h32 + t.pix_c + ch, h);
   } else if constexpr (KIND == EPI_ST_C) {   // acc = (i, f, g, o_x + o_h)
+    if (E.variant == 1) {   // Causal LSTM spatial memory (causal.h): acc = (i', f', g', m_m)
+      float mn[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        mn[j] = fmaf(sigmoid_fast(acc[1][j] + E.forget_bias), tanh_fast(acc[3][j]), sigmoid_fast(acc[0][j]) * tanh_fast(acc[2][j]));
+      st_state8(E.s0, t.st_off, t.st_g, ch, mn);
+      st_bf16x8(static_cast<bf16*>(E.t0) + t.pix_t0 + ch, mn);
+      return;
+    }
     float dc[8], op[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -249,7 +258,7 @@ __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile&
     st_state8(E.s0, t.st_off, t.st_g, ch, o.a);
     st_state8(E.s1, t.st_off, t.st_g, ch, op);
     st_bf16x8(static_cast<bf16*>(E.t0) + t.pix_t0 + ch, o.a);
-    st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dc);
+    if (E.t1 != nullptr) st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dc);
   } else if constexpr (KIND == EPI_ST_M) {   // acc = (i', f', g')
     float dm[8];
 #pragma unroll
@@ -261,11 +270,23 @@ __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile&
     }
     st_state8(E.s0, t.st_off, t.st_g, ch, o.a);
     st_bf16x8(static_cast<bf16*>(E.t0) + t.pix_t0 + ch, o.a);
-    st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dm);
+    if (E.t1 != nullptr) st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dm);
   } else {   // EPI_ST_O: acc = (conv_o(mem), conv_last(mem))
     float h[8];
+    if (E.variant == 2) {   // gradient highway unit (causal.h): acc = (p, u), o.a = z
 #pragma unroll
-    for (int j = 0; j < 8; ++j) h[j] = sigmoid_fast(o.a[j] + acc[0][j]) * tanh_fast(acc[1][j]);
+      for (int j = 0; j < 8; ++j) {
+        const float u = sigmoid_fast(acc[1][j]);
+        h[j] = fmaf(u, o.a[j] - tanh_fast(acc[0][j]), tanh_fast(acc[0][j]));      // u z + (1 - u) tanh(p)
+      }
+      st_state8(E.s0, t.st_off, t.st_g, ch, h);
+    } else if (E.variant == 1) {   // Causal LSTM output: tanh output gate
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = tanh_fast(o.a[j] + acc[0][j]) * tanh_fast(acc[1][j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) h[j] = sigmoid_fast(o.a[j] + acc[0][j]) * tanh_fast(acc[1][j]);
+    }
     st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
   }
 }

@@ -152,5 +152,6 @@ Model* make_predrnn(const vpk_model_desc& d);
 Model* make_phydnet(const vpk_model_desc& d, bool branch_only);
 Model* make_stphy(const vpk_model_desc& d);
 Model* make_ef_trajgru(const vpk_model_desc& d);
+Model* make_predrnnpp_causal(const vpk_model_desc& d);
 
 }  // namespace vpk

@@ -385,6 +385,89 @@ class PredRNN_V2(NativeRollout, VPModel):
         return pred, {"ST-LSTM decouple loss": aux[0]}                         # predrnn_v2.py:229-230
 
 
+class PredRNNpp(NativeRollout, VPModel):
+    """PredRNN++ as published (Wang et al., ICML 2018): Causal LSTM stack with a gradient highway unit between the first and
+    the second layer -- the cells BASELINE.json's north star names.  The reference checkout has no such model (its
+    ``predrnn-pp`` key is PredRNN_V2 above), so this class has no reference twin: PARITY UNPINNED, checked against
+    oracle/causal.py only.  The VPModel contract (patches, complete input, eval rollout, ``pred_1``) is PredRNN_V2's
+    (models/predrnn_v2.py:128-137, 223-228); parameter names follow its Sequential-per-conv layout."""
+    NAME = "PredRNN++ (Causal LSTM + GHU)"
+    PAPER_REFERENCE = "https://arxiv.org/abs/1804.06300"
+    CODE_REFERENCE = "https://github.com/Yunbo426/predrnn-pp"
+    MATCHES_REFERENCE: str = "Not Yet"
+    CAN_HANDLE_ACTIONS = False
+    NEEDS_COMPLETE_INPUT = True
+    TRAINABLE = False
+
+    patch_size = 4
+    num_layers = 4
+    num_hidden = [128, 128, 128, 128]
+    filter_size = 5
+    stride = 1
+    layer_norm: bool = False
+
+    def __init__(self, device, **model_kwargs):
+        super().__init__(device, **model_kwargs)
+        self._native_init()
+        if self.stride != 1:
+            raise AttributeError("Causal LSTM stride must be 1")
+        if self.layer_norm or self.action_conditional:
+            raise NotImplementedError("PredRNN++ drop-in: layer_norm / action_conditional are not built")
+        if self.num_layers < 2:
+            raise AttributeError("PredRNN++ needs at least two layers (the GHU sits between the first two)")
+        self.patch_c = self.patch_size * self.patch_size * self.img_c
+        self.patch_h = self.rnn_h = self.img_h // self.patch_size
+        self.patch_w = self.rnn_w = self.img_w // self.patch_size
+        k, C = self.filter_size, self.num_hidden[0]
+
+        def conv(ci, co):
+            return nn.Sequential(nn.Conv2d(ci, co, k, 1, k // 2, bias=False))
+
+        cells = []
+        for i in range(self.num_layers):
+            cell = _Params()
+            cell.conv_x = conv(self.patch_c if i == 0 else C, 7 * C)
+            cell.conv_h = conv(C, 4 * C)
+            cell.conv_c = conv(C, 3 * C)
+            cell.conv_m = conv(C, 3 * C)
+            cell.conv_c2m = conv(C, 4 * C)
+            cell.conv_om = conv(C, C)
+            cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
+            cells.append(cell)
+        self.cell_list = nn.ModuleList(cells)
+        self.gradient_highway = _Params()
+        self.gradient_highway.x_concat = conv(C, 2 * C)
+        self.gradient_highway.z_concat = conv(C, 2 * C)
+        self.conv_last = nn.Conv2d(C, self.patch_c, 1, 1, 0, bias=False)
+        self.to(device)
+
+    def _native_desc(self):
+        d = N.ModelDesc()
+        d.kind = N.VPK_MODEL_PREDRNN_PP_CAUSAL
+        d.img_c, d.img_h, d.img_w = self.img_c, self.img_h, self.img_w
+        d.patch_size, d.num_layers, d.filter_size = self.patch_size, self.num_layers, self.filter_size
+        for i, v in enumerate(self.num_hidden[:8]):
+            d.num_hidden[i] = int(v)
+        return d
+
+    def _native_key(self, key):
+        return key
+
+    def pred_1(self, x, **kwargs):
+        return self(x, pred_frames=1, **kwargs)[0].squeeze(dim=1)
+
+    def forward(self, x, pred_frames: int = 1, **kwargs):
+        b, total, c, h, w = x.shape
+        if total - pred_frames < 1:
+            raise ValueError(f"Model {self.NAME} needs input sequences that also include the target frames!")
+        if (c, h, w) != (self.img_c, self.img_h, self.img_w):
+            raise ValueError(f"shape mismatch: expected {(self.img_c, self.img_h, self.img_w)}, got {(c, h, w)}")
+        if kwargs.get("train", False):
+            raise NotImplementedError("the native rollout is inference-only")
+        pred, _ = self._native_forward(x, int(pred_frames), total)
+        return pred, {}
+
+
 def _dcgan(cin, cout, stride, transpose):
     """DCGANConv / DCGANConvTranspose parameter layout (model_blocks/conv.py:58-95): main.0 conv, main.1 GroupNorm."""
     m = _Params()
@@ -810,4 +893,5 @@ MODEL_CLASSES = {
     "convlstm-branch": ConvLSTMBranch,
     "st-phy": STPhy,
     "trajgru": EF_TrajGRU,
+    "predrnn-pp-causal": PredRNNpp,      # the north star's Causal LSTM + GHU stack; no reference twin (parity unpinned)
 }
