@@ -43,14 +43,22 @@ WORKLOADS = {
     "cfg5": ("convlstm-shi", (3, 128, 128), 10, 20, 512, "convlstm-shi 3x128x128 10+20"),
     # ST-LSTM with layer_norm=True, same shape as cfg3
     "cfg3ln": ("predrnn-pp", (1, 64, 64), 10, 10, 256, "predrnn-pp layer_norm=True 1x64x64 10+10"),
+    # BASELINE config 3 as its text reads ("PredRNN++: CausalLSTMCell stack + GHU"): four Causal LSTM layers of 128 channels + the
+    # gradient highway unit.  The reference has no such model (cfg3 above is its `predrnn-pp`): parity unpinned, the
+    # "reference" columns of this row are the oracle's port (oracle/causal.py) run by torch
+    "cfg3pp": ("predrnn-pp-causal", (1, 64, 64), 10, 10, 256, "PredRNN++ (Causal LSTM x4 + GHU) 1x64x64 10+10"),
 }
-WORKLOAD_KW = {"cfg3ln": {"layer_norm": True}}          # extra model kwargs of a workload
+COMPLETE_INPUT = ("predrnn-pp", "predrnn-pp-causal")     # models whose input holds context + target frames
+WORKLOAD_KW = {"cfg3ln": {"layer_norm": True}}         # extra model kwargs of a workload
 # "required" GFLOP per sequence of the whole rollout
 REQUIRED_GFLOP_PER_SEQ = {"cfg1": 81.03, "cfg2": 26.319, "cfg3": 168.787, "cfg4": 17.74, "cfg5": 524.31,
-                          "cfg3ln": 168.787}
+                          "cfg3ln": 168.787,
+                          # 19 steps x 256 positions x 2 x (layer 0: 6 535 168 + layers 1-3: 3 x 9 043 968 + GHU 1 638 400 +
+                          # head 2 048) MACs, see DESIGN.md
+                          "cfg3pp": 343.47}
 # bounded batch of the CPU reference arm / cpu_baseline and of the same-GPU eager baseline
 CPU_BATCH = {"cfg5": 2}
-EAGER_BATCH = {"cfg1": 8, "cfg2": 64, "cfg3": 64, "cfg3ln": 64, "cfg4": 64, "cfg5": 16}
+EAGER_BATCH = {"cfg1": 8, "cfg2": 64, "cfg3": 64, "cfg3ln": 64, "cfg3pp": 64, "cfg4": 64, "cfg5": 16}
 
 
 def parse():
@@ -158,6 +166,10 @@ def _reference_forward(workload, device):
     from oracle.weights import synth_state_dict
     key, img, ctx, pred, _, _ = WORKLOADS[workload]
     kw = WORKLOAD_KW.get(workload, {})
+    if key == "predrnn-pp-causal":             # no reference twin: the oracle's restatement of the paper, run by torch
+        from oracle import causal
+        sd = {k: v.to(device) for k, v in synth_state_dict(causal.state_dict_shapes(img[0], 4, 128), 0, 1.0).items()}
+        return (lambda x, p: causal.predrnnpp_forward(sd, x, p)[0]), "port"
     if ref_shim.available():
         classes = ref_shim.load_reference()
         torch.manual_seed(0)
@@ -198,7 +210,7 @@ def cpu_reference_run(workload, warmup, steps, threads=None):
     threads = threads or os.cpu_count() or 1
     torch.set_num_threads(threads)
     b = CPU_BATCH.get(workload, 8)
-    t_in = ctx + (pred if key == "predrnn-pp" else 0)
+    t_in = ctx + (pred if key in COMPLETE_INPUT else 0)
     x = synth_frames(b, t_in, *img, seed=1234)
     fwd, kind = _reference_forward(workload, "cpu")
     times = []
@@ -242,7 +254,7 @@ def gpu_eager_baseline(workload, reps=2):
     from oracle.weights import synth_frames
     key, img, ctx, pred, _, desc = WORKLOADS[workload]
     b = EAGER_BATCH[workload]
-    x = synth_frames(b, ctx + (pred if key == "predrnn-pp" else 0), *img, seed=1234).cuda()
+    x = synth_frames(b, ctx + (pred if key in COMPLETE_INPUT else 0), *img, seed=1234).cuda()
     out = {"batch": b, "unit": "frames/s"}
     saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.benchmark)
     try:
@@ -287,7 +299,7 @@ class Runner:
         key, img, ctx, pred, default_b, desc = WORKLOADS[workload]
         self.workload, self.key, self.img, self.ctx, self.pred, self.desc = workload, key, img, ctx, pred, desc
         self.B = seqs or default_b
-        self.t_in = ctx + (pred if key == "predrnn-pp" else 0)
+        self.t_in = ctx + (pred if key in COMPLETE_INPUT else 0)
         self.use_graph = args.graph if args.graph >= 0 else int(self.B <= 32)
         torch.manual_seed(0)      # random-init weights of the named architecture (torch default init, as the reference)
         self.model = V.MODEL_CLASSES[key](str(dev), img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
@@ -300,7 +312,7 @@ class Runner:
         self.tgt_dev = tgt_host.to(dev)
         chw = img[0] * img[1] * img[2]
         # bytes the host entry really copies: predrnn-pp reads only the context frames of its context + target input
-        self.in_bytes = self.B * ctx * chw * 4 if key == "predrnn-pp" else self.x_host.numel() * 4
+        self.in_bytes = self.B * ctx * chw * 4 if key in COMPLETE_INPUT else self.x_host.numel() * 4
         self.out_bytes = self.B * pred * chw * 4
 
     def step_device(self):
@@ -365,7 +377,7 @@ def per_config_block(args, dev, rank, peaks, min_seconds=2.4):
     samples (100 ms period) fall inside its timed region."""
     import torch
     out = {}
-    for w in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg3ln"):
+    for w in ("cfg1", "cfg2", "cfg3", "cfg4", "cfg3ln", "cfg3pp"):
         if w == args.workload:
             continue
         try:
@@ -472,7 +484,7 @@ def main():
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak if peak else None, "traffic": traffic, "traffic_note": traffic_note,
                 "kernel": "conv_halo_kernel <EPI_LSTM> (tcgen05 ConvLSTM gate GEMMs + fused state update)"
-                if key != "predrnn-pp" else "conv_halo_kernel <EPI_ST_*> (tcgen05 ST-LSTM gate GEMMs + fused update)",
+                if key not in COMPLETE_INPUT else "conv_halo_kernel <EPI_ST_*> (tcgen05 ST-LSTM gate GEMMs + fused update)",
                 "gemm_launches_per_step": gs["launches"], "gemm_ms_per_step": gs["ms"],
                 "gemm_share_of_step": fr["gate_gemm_share_of_step"],
                 "algorithmic_gflop_per_step": gs["flops"] * 1e-9,

@@ -109,10 +109,10 @@ def predrnnpp_forward(sd, x, pred_frames, cfg=None, q=None):
     xp = reshape_patch(x, p)
     hp, wp = xp.shape[-2:]
     C = sd["cell_list.0.conv_h.0.weight"].shape[1]
-    h_t = [torch.zeros(b, C, hp, wp) for _ in range(L)]
-    c_t = [torch.zeros(b, C, hp, wp) for _ in range(L)]
-    memory = torch.zeros(b, C, hp, wp)
-    z_t = torch.zeros(b, C, hp, wp)
+    h_t = [torch.zeros(b, C, hp, wp, device=x.device) for _ in range(L)]
+    c_t = [torch.zeros(b, C, hp, wp, device=x.device) for _ in range(L)]
+    memory = torch.zeros(b, C, hp, wp, device=x.device)
+    z_t = torch.zeros(b, C, hp, wp, device=x.device)
     ws = [cell_weights(sd, f"cell_list.{i}.") for i in range(L)]
     x_gen, frames = None, []
     for t in range(total - 1):

@@ -410,6 +410,12 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         int nv = 0;
         for (int g = 0; g < G; ++g) nv += h.gky[g] >= 0 ? 1 : 0;
         used = static_cast<double>(nv) / G;
+      } else if (h.wref >= 0 && h.wref < static_cast<int>(spec.wrefs.size())) {
+        // multi-source gate convs: a weight tensor that does not feed gate g (gate_block -1) leaves zero rows in the packed
+        // matrix -- executed by the MMA, but not algorithmic FLOPs (ST-LSTM / Causal LSTM output launches, the decoupling adapter)
+        int nv = 0;
+        for (int g = 0; g < G && g < 4; ++g) nv += spec.wrefs[h.wref].gate_block[g] >= 0 ? 1 : 0;
+        used = static_cast<double>(nv) / std::min(G, 4);
       }
       if (h.count_flops) kreal += h.kw_valid * used;
     }
