@@ -103,3 +103,55 @@ def test_contract_errors():
         m(torch.zeros(1, 4, 1, 16, 32, device="cuda"), pred_frames=1)          # wrong image size
     with pytest.raises(NotImplementedError):
         m(torch.zeros(1, 4, 1, 32, 32, device="cuda"), pred_frames=1, train=True)
+
+
+@pytest.mark.parametrize("precision,backend", [("fp32", "auto"), ("bf16", "auto"), ("bf16", "simt")])
+@pytest.mark.parametrize("cin,C,hw,k", [(16, 64, (16, 16), 5), (24, 24, (10, 6), 3)])
+def test_single_step_blocks_match_oracle(cin, C, hw, k, precision, backend):
+    """CausalLSTMCell.forward(x, h, c, m) -> (h', c', m') and GHU.forward(x, z) as VPModelBlock drop-ins (vpk_causal_lstm_cell_* /
+    vpk_ghu_cell_*), one step from random non-zero states; 16-bit mode inside the north star's single-step bound (5e-3),
+    and within 2.5e-3 of the oracle with bf16-rounded conv operands."""
+    from vp_suite_b200.model_blocks import CausalLSTMCell, GHU
+    g = torch.Generator().manual_seed(7)
+    shapes = {f"{n}.0.weight": s for n, s in (("conv_x", (7 * C, cin, k, k)), ("conv_h", (4 * C, C, k, k)),
+                                               ("conv_c", (3 * C, C, k, k)), ("conv_m", (3 * C, C, k, k)),
+                                               ("conv_c2m", (4 * C, C, k, k)), ("conv_om", (C, C, k, k)))}
+    shapes["conv_last.weight"] = (C, 2 * C, 1, 1)
+    sd = synth_state_dict(shapes, seed=21, gain=1.5)
+    cell = CausalLSTMCell(cin, C, hw[0], hw[1], k, 1, False).cuda()
+    cell.precision, cell.backend = precision, backend
+    cell.load_state_dict(sd)
+    x = torch.rand(3, cin, *hw, generator=g)
+    h, c, m = (torch.randn(3, C, *hw, generator=g) * s for s in (0.2, 0.3, 0.3))      # states of the size a rollout reaches
+    w = {n: sd[f"{n}.0.weight"] for n in ("conv_x", "conv_h", "conv_c", "conv_m", "conv_c2m", "conv_om")}
+    w["conv_last"] = sd["conv_last.weight"]
+    want = causal.causal_lstm_step(x, h, c, m, w)
+    emu = causal.causal_lstm_step(x, h, c, m, w, q=causal.bf16_operands)
+    got = cell(x.cuda(), h.cuda(), c.cuda(), m.cuda())
+    tol = 1e-4 if precision == "fp32" else 5e-3
+    for name, a, b, e in zip(("h", "c", "m"), got, want, emu):
+        err, err_emu = float((a.cpu() - b).abs().max()), float((a.cpu() - e).abs().max())
+        print(f"causal cell {precision}/{backend} {name}: max abs err {err:.1e} (vs bf16-operand oracle {err_emu:.1e}), |ref| max {float(b.abs().max()):.2f}")
+        assert err <= tol, (name, err)
+        if precision != "fp32":
+            assert err_emu <= 2.5e-3, (name, err_emu)      # h' leaves the cell as bf16 (half an ulp at 0.5..1 = 2e-3); c' / m' are fp32
+    # GHU
+    gs = synth_state_dict({"x_concat.0.weight": (2 * C, C, k, k), "z_concat.0.weight": (2 * C, C, k, k)}, seed=22, gain=2.0)
+    ghu = GHU(C, hw[0], hw[1], k, 1, False).cuda()
+    ghu.precision, ghu.backend = precision, backend
+    ghu.load_state_dict(gs)
+    z = 0.3 * torch.randn(3, C, *hw, generator=g)
+    wantz = causal.ghu_step(h, z, gs["x_concat.0.weight"], gs["z_concat.0.weight"])
+    gotz = ghu(h.cuda(), z.cuda())
+    errz = float((gotz.cpu() - wantz).abs().max())
+    print(f"ghu {precision}/{backend}: max abs err {errz:.1e}")
+    assert errz <= tol
+    want0 = causal.ghu_step(h, torch.zeros_like(h), gs["x_concat.0.weight"], gs["z_concat.0.weight"])
+    assert float((ghu(h.cuda()).cpu() - want0).abs().max()) <= tol           # z=None: first timestep
+    # changing a weight in place rebuilds the native handle
+    with torch.no_grad():
+        cell.conv_om[0].weight.mul_(0.0)
+    w2 = dict(w, conv_om=torch.zeros_like(w["conv_om"]))
+    want2 = causal.causal_lstm_step(x, h, c, m, w2)
+    got2 = cell(x.cuda(), h.cuda(), c.cuda(), m.cuda())
+    assert float((got2[0].cpu() - want2[0]).abs().max()) <= tol

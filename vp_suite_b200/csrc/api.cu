@@ -296,6 +296,41 @@ int vpk_stlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const fl
   });
 }
 
+int vpk_causal_lstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w,
+                                int32_t k, const float* const* weights, vpk_cell** out) {
+  return guarded([&] {
+    VPK_REQUIRE(weights && out, "null argument");
+    *out = new vpk_cell{vpk::make_causal_lstm_cell(precision, backend, cin, ch, h, w, k, weights)};
+  });
+}
+
+int vpk_causal_lstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
+                              const float* m, float* h_out, float* c_out, float* m_out, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && x && h && c && m && h_out && c_out && m_out, "null argument");
+    const float* in[8] = {x, h, c, m, nullptr, nullptr, nullptr, nullptr};
+    float* outp[8] = {h_out, c_out, m_out, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cell->impl->step(batch, in, outp, static_cast<cudaStream_t>(stream));
+  });
+}
+
+int vpk_ghu_cell_create(int32_t precision, int32_t backend, int32_t ch, int32_t h, int32_t w, int32_t k, const float* w_x,
+                        const float* w_z, vpk_cell** out) {
+  return guarded([&] {
+    VPK_REQUIRE(w_x && w_z && out, "null argument");
+    *out = new vpk_cell{vpk::make_ghu_cell(precision, backend, ch, h, w, k, w_x, w_z)};
+  });
+}
+
+int vpk_ghu_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* z, float* z_out, void* stream) {
+  return guarded([&] {
+    VPK_REQUIRE(cell && x && z && z_out, "null argument");
+    const float* in[8] = {x, z, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* outp[8] = {z_out, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cell->impl->step(batch, in, outp, static_cast<cudaStream_t>(stream));
+  });
+}
+
 int vpk_phycell_cell_create(int32_t precision, int32_t backend, int32_t ch, int32_t hid, int32_t h, int32_t w,
                             int32_t k, const float* conv1_w, const float* conv1_b, const float* gn_w,
                             const float* gn_b, const float* conv2_w, const float* conv2_b, const float* gate_w,

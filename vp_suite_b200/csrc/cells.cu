@@ -9,6 +9,7 @@
 #include "../../include/vpk.h"
 #include "backward.h"
 #include "builders.h"
+#include "causal.h"
 #include "elementwise.h"
 #include "phycell.h"
 #include "stlstm.h"
@@ -403,6 +404,93 @@ class StLstmCell : public CellBase {
 
 
 // ------------------------------------------------------------------------------------------------------------------
+// Causal LSTM cell and gradient highway unit of PredRNN++ (causal.h; absent from the reference checkout: parity unpinned,
+// checked against oracle/causal.py) behind the NCHW block boundary.
+class CausalLstmCell : public CellBase {
+ public:
+  CausalLstmCell(int precision, int backend_, int cin_, int ch_, int h_, int w_, int k_, const float* const* weights)
+      : CellBase(precision, backend_), cin(cin_), ch(ch_), h(h_), w(w_), k(k_) {
+    VPK_REQUIRE(cin > 0 && ch > 0 && h > 0 && w > 0 && k % 2 == 1, "bad Causal LSTM cell shape");
+    const size_t kk = static_cast<size_t>(k) * k, cc = static_cast<size_t>(ch) * ch;
+    const size_t n[7] = {7u * ch * cin * kk, 4 * cc * kk, 3 * cc * kk, 3 * cc * kk, 4 * cc * kk, cc * kk, 2 * cc};
+    for (int i = 0; i < 7; ++i) {
+      VPK_REQUIRE(weights[i] != nullptr, "null Causal LSTM weight");
+      wt[i].assign(weights[i], weights[i] + n[i]);
+    }
+  }
+  // in: x, h, c, m    out: h', c', m'
+  void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    const size_t px = static_cast<size_t>(B) * h * w;
+    void* xb = buf("x", px * cin * esize());
+    void* hi = buf("h_in", px * ch * esize());
+    void* ci = buf("c_in", px * ch * esize());
+    void* mi = buf("m_in", px * ch * esize());
+    void* ho = buf("h_out", px * ch * esize());
+    void* mem = buf("mem", px * 2 * ch * esize());
+    float* cb = static_cast<float*>(buf("c", px * ch * sizeof(float)));
+    float* mb = static_cast<float*>(buf("m", px * ch * sizeof(float)));
+    float* op = static_cast<float*>(buf("o_part", px * ch * sizeof(float)));
+    if (built_batch != B) {
+      convs.clear();
+      CausalArgs a{"cell.", B, h, w, cin, ch, k, xb, hi, make_view(ci, h, w, ch), make_view(mi, h, w, ch), ho, cb, mb, op, mem,
+                   wt[0].data(), wt[1].data(), wt[2].data(), wt[3].data(), wt[4].data(), wt[5].data(), wt[6].data()};
+      for (const ConvSpec& sp : causal_lstm_specs(a, act())) add(sp, s);
+      finish_build(s);
+      built_batch = B;
+    }
+    to_nhwc(in[0], xb, dtype, B, cin, h, w, s);
+    to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
+    to_nhwc(in[2], ci, dtype, B, ch, h, w, s);
+    to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
+    to_nhwc(in[3], mi, dtype, B, ch, h, w, s);
+    VPK_CUDA(cudaMemsetAsync(mb, 0, px * ch * sizeof(float), s));        // write-only state (the prefetch reads it)
+    for (const BuiltConv& bc : convs) run(bc, s);
+    launch_nhwc_to_nchw(ho, dtype, out[0], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(cb, DT_F32, out[1], B, ch, h, w, num_sms, s);
+    launch_nhwc_to_nchw(mb, DT_F32, out[2], B, ch, h, w, num_sms, s);
+  }
+
+ private:
+  int cin, ch, h, w, k;
+  std::vector<float> wt[7];
+};
+
+class GhuCell : public CellBase {
+ public:
+  GhuCell(int precision, int backend_, int ch_, int h_, int w_, int k_, const float* w_x, const float* w_z)
+      : CellBase(precision, backend_), ch(ch_), h(h_), w(w_), k(k_) {
+    VPK_REQUIRE(ch > 0 && h > 0 && w > 0 && k % 2 == 1, "bad GHU shape");
+    const size_t n = 2 * static_cast<size_t>(ch) * ch * k * k;
+    wx.assign(w_x, w_x + n);
+    wz.assign(w_z, w_z + n);
+  }
+  // in: x, z    out: z'
+  void step(int B, const float* const* in, float* const* out, cudaStream_t s) override {
+    const size_t px = static_cast<size_t>(B) * h * w;
+    void* xb = buf("x", px * ch * esize());
+    void* zi = buf("z_in", px * ch * esize());
+    void* zo = buf("z_out", px * ch * esize());
+    float* zb = static_cast<float*>(buf("z", px * ch * sizeof(float)));
+    if (built_batch != B) {
+      convs.clear();
+      GhuArgs g{"ghu.", B, h, w, ch, k, xb, zi, zo, zb, wx.data(), wz.data()};
+      add(ghu_spec(g, act()), s);
+      finish_build(s);
+      built_batch = B;
+    }
+    to_nhwc(in[0], xb, dtype, B, ch, h, w, s);
+    to_nhwc(in[1], zi, dtype, B, ch, h, w, s);
+    to_nhwc(in[1], zb, DT_F32, B, ch, h, w, s);
+    for (const BuiltConv& bc : convs) run(bc, s);
+    launch_nhwc_to_nchw(zb, DT_F32, out[0], B, ch, h, w, num_sms, s);
+  }
+
+ private:
+  int ch, h, w, k;
+  std::vector<float> wx, wz;
+};
+
+// ------------------------------------------------------------------------------------------------------------------
 // ActionConditionalSpatioTemporalLSTMCell.forward (model_blocks/predrnn.py:142-169), layer_norm off or on: the rollout's
 // pipeline (model_predrnn.cu: add_ac_cell) behind the NCHW block boundary -- raw convs with bias (x, h, a, m), per-sample
 // statistics when layer_norm, the action-conditional gate kernel, conv_o / conv_last, the output kernel.
@@ -703,6 +791,14 @@ Cell* make_convlstm_cell(int precision, int backend, int cin, int ch, int h, int
 Cell* make_stlstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* w_x,
                        const float* w_h, const float* w_m, const float* w_o, const float* w_last) {
   return new StLstmCell(precision, backend, cin, ch, h, w, k, w_x, w_h, w_m, w_o, w_last);
+}
+
+Cell* make_causal_lstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* const* weights) {
+  return new CausalLstmCell(precision, backend, cin, ch, h, w, k, weights);
+}
+
+Cell* make_ghu_cell(int precision, int backend, int ch, int h, int w, int k, const float* w_x, const float* w_z) {
+  return new GhuCell(precision, backend, ch, h, w, k, w_x, w_z);
 }
 
 }  // namespace vpk

@@ -355,6 +355,92 @@ class SpatioTemporalLSTMCell(_NativeCell, VPModelBlock):
         return tuple(outs)                                               # h', c', m', delta_c, delta_m (predrnn.py:82)
 
 
+class CausalLSTMCell(_NativeCell, VPModelBlock):
+    """Causal LSTM cell of PredRNN++ (Wang et al., ICML 2018, eq. 1): the temporal memory c and the spatial memory m in
+    cascade, tanh output gate.  The north star names it; the reference checkout has no such block, so
+    it has no reference twin -- PARITY UNPINNED, checked against oracle/causal.py.  Constructor and forward signatures
+    follow SpatioTemporalLSTMCell above (model_blocks/predrnn.py:7-83); bias-free convs, forget bias 1."""
+    NAME = "Causal LSTM Cell"
+    PAPER_REFERENCE = "https://arxiv.org/abs/1804.06300"
+    CODE_REFERENCE = "https://github.com/Yunbo426/predrnn-pp"
+    MATCHES_REFERENCE = "Not Yet"
+    _CONVS = ("conv_x", "conv_h", "conv_c", "conv_m", "conv_c2m", "conv_om")
+
+    def __init__(self, in_channel, num_hidden, height, width, filter_size, stride=1, layer_norm=False):
+        super().__init__()
+        self._cell_init()
+        if stride != 1 or filter_size % 2 == 0:
+            raise ValueError("stride 1 and odd filter sizes only")
+        if layer_norm:
+            raise NotImplementedError("Causal LSTM drop-in: layer_norm is not built")
+        self.num_hidden, self.padding, self._forget_bias = num_hidden, filter_size // 2, 1.0
+        self._shape = (in_channel, height, width, filter_size)
+
+        def conv(ci, co):
+            return nn.Sequential(nn.Conv2d(ci, co, filter_size, stride, self.padding, bias=False))
+        self.conv_x = conv(in_channel, num_hidden * 7)
+        self.conv_h = conv(num_hidden, num_hidden * 4)
+        self.conv_c = conv(num_hidden, num_hidden * 3)
+        self.conv_m = conv(num_hidden, num_hidden * 3)
+        self.conv_c2m = conv(num_hidden, num_hidden * 4)
+        self.conv_om = conv(num_hidden, num_hidden)
+        self.conv_last = nn.Conv2d(num_hidden * 2, num_hidden, 1, 1, 0, bias=False)
+
+    def _cell_create(self):
+        cin, h, w, k = self._shape
+        cell = C.c_void_p()
+        ws = [self._host(getattr(self, n)[0].weight) for n in self._CONVS] + [self._host(self.conv_last.weight)]
+        wp = (C.c_void_p * 7)(*[t.data_ptr() for t in ws])
+        N.check(N.lib().vpk_causal_lstm_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], cin,
+                                                    self.num_hidden, h, w, k, wp, C.byref(cell)))
+        return cell
+
+    def forward(self, x_t, h_t, c_t, m_t):
+        x, h, c, m = (self._dev(t) for t in (x_t, h_t, c_t, m_t))
+        cell = self._cell_handle(x.device)
+        outs = [torch.empty_like(h) for _ in range(3)]
+        self._step(x.device, N.lib().vpk_causal_lstm_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(h), N.ptr(c), N.ptr(m),
+                   *[N.ptr(o) for o in outs], self._stream(x))
+        return tuple(outs)                                               # h', c', m'
+
+
+class GHU(_NativeCell, VPModelBlock):
+    """Gradient highway unit of PredRNN++ (eq. 2): z' = s z + (1 - s) tanh(p) with (p, s) from convs over x and z; ``z``
+    None means zeros (first timestep).  No reference twin (see CausalLSTMCell): PARITY UNPINNED."""
+    NAME = "Gradient Highway Unit"
+    PAPER_REFERENCE = "https://arxiv.org/abs/1804.06300"
+    CODE_REFERENCE = "https://github.com/Yunbo426/predrnn-pp"
+    MATCHES_REFERENCE = "Not Yet"
+
+    def __init__(self, num_hidden, height, width, filter_size, stride=1, layer_norm=False):
+        super().__init__()
+        self._cell_init()
+        if stride != 1 or filter_size % 2 == 0:
+            raise ValueError("stride 1 and odd filter sizes only")
+        if layer_norm:
+            raise NotImplementedError("GHU drop-in: layer_norm is not built")
+        self.num_hidden, self.padding = num_hidden, filter_size // 2
+        self._shape = (height, width, filter_size)
+        self.x_concat = nn.Sequential(nn.Conv2d(num_hidden, num_hidden * 2, filter_size, stride, self.padding, bias=False))
+        self.z_concat = nn.Sequential(nn.Conv2d(num_hidden, num_hidden * 2, filter_size, stride, self.padding, bias=False))
+
+    def _cell_create(self):
+        h, w, k = self._shape
+        cell = C.c_void_p()
+        wx, wz = self._host(self.x_concat[0].weight), self._host(self.z_concat[0].weight)
+        N.check(N.lib().vpk_ghu_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], self.num_hidden, h, w, k,
+                                            N.ptr(wx), N.ptr(wz), C.byref(cell)))
+        return cell
+
+    def forward(self, x, z=None):
+        x = self._dev(x)
+        z = torch.zeros_like(x) if z is None else self._dev(z)
+        cell = self._cell_handle(x.device)
+        out = torch.empty_like(x)
+        self._step(x.device, N.lib().vpk_ghu_cell_step, cell, x.shape[0], N.ptr(x), N.ptr(z), N.ptr(out), self._stream(x))
+        return out
+
+
 class ActionConditionalSpatioTemporalLSTMCell(_NativeCell, VPModelBlock):
     """model_blocks/predrnn.py:86-169, layer_norm False or True: every conv has a bias, and a fifth conv ``conv_a`` over the
     action tensor multiplies conv_h's output before the gate split (:149)."""
