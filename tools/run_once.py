@@ -16,7 +16,7 @@ def main():
     key, img, ctx, pred, default_b, desc = WORKLOADS[wl]
     B = int(sys.argv[2]) if len(sys.argv) > 2 else default_b
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 1
-    t_in = ctx + (pred if key == "predrnn-pp" else 0)
+    t_in = ctx + (pred if key in ("predrnn-pp", "predrnn-pp-causal") else 0)
     torch.manual_seed(0)
     m = V.MODEL_CLASSES[key]("cuda:0", img_shape=img, action_size=0, tensor_value_range=[0.0, 1.0],
                              **WORKLOAD_KW.get(wl, {})).eval()

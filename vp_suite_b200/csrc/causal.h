@@ -38,6 +38,7 @@ struct CausalArgs {
   void* mem;              // [B,H,W,2C] written here: (c', m')
   const float *w_x, *w_h, *w_c, *w_m, *w_c2m, *w_om, *w_last;   // host, layouts of the header comment
   bool c4 = false;        // c, m, o_part use the channel-quad layout
+  float* o_raw = nullptr; // optional fp32 dense [B,H,W,C] scratch: launch O as two launches (EPI_ST_O1, see stlstm.h)
 };
 
 inline WeightRef causal_wref(const float* w, int O, int I, int kk, std::initializer_list<int> blocks) {
@@ -107,7 +108,43 @@ inline std::vector<ConvSpec> causal_lstm_specs(const CausalArgs& a, const ActInf
     e.t0_pix = 2 * C;
     out.push_back(std::move(s));
   }
-  {  // ---- O: output gate over (x, h) [kept from launch C] + c' + m', and the 1 x 1 conv over cat(c', m') ----
+  if (a.o_raw != nullptr) {  // ---- O as conv_last (1 x 1, raw) + (conv_c2m[o](c') + conv_om(m')) with the output gate ----
+    {
+      ConvSpec s;
+      s.name = a.name + "O.conv_last";
+      s.B = a.B;
+      s.G = 1;
+      s.C = C;
+      s.is_gate_gemm = true;
+      s.wrefs.push_back(causal_wref(a.w_last, C, 2 * C, 1, {0}));
+      lower_conv(s, 1, 1, 0, {ConvInput{make_view(a.mem, a.H, a.W, 2 * C), 0, 0}}, a.H, a.W, act.esize, &oh, &ow);
+      EpiParams& e = s.phases[0].epi;
+      e.kind = EPI_BIAS_ACT;
+      e.act = ACT_NONE;
+      e.out_f32 = 1;
+      dense_out(e, a.o_raw, a.H, a.W, C);
+      out.push_back(std::move(s));
+    }
+    {
+      ConvSpec s;
+      s.name = a.name + "O.conv_o";
+      s.B = a.B;
+      s.G = 1;
+      s.C = C;
+      s.is_gate_gemm = true;
+      s.wrefs.push_back(causal_wref(a.w_c2m, 4 * C, C, k, {3}));
+      s.wrefs.push_back(causal_wref(a.w_om, C, C, k, {0}));
+      lower_conv(s, k, 1, pad, {ConvInput{cnew, 0, 0}, ConvInput{mnew, 1, 0}}, a.H, a.W, act.esize, &oh, &ow);
+      EpiParams& e = s.phases[0].epi;
+      e.kind = EPI_ST_O1;
+      e.variant = 3;
+      e.state_c4 = c4;
+      e.s0 = a.o_part;
+      e.res = a.o_raw;
+      dense_out(e, a.h_out, a.H, a.W, C);
+      out.push_back(std::move(s));
+    }
+  } else {  // ---- O: output gate over (x, h) [kept from launch C] + c' + m', and the 1 x 1 conv over cat(c', m') ----
     ConvSpec s;
     s.name = a.name + "O";
     s.B = a.B;

@@ -71,6 +71,13 @@ enum EpiKind : int {
   EPI_PHY_GATE = 5,       // G=1  PhyCell Kalman-style blend
   EPI_SUBPIX = 7,         // G=4  sub-pixel transposed conv: gate (ry, rx) of a position is output pixel (2y + ry, 2x + rx);
                           //      y = act(acc + bias) stored as activation type at out + b*oB + y*oY + x*oX + ry*ps_row + rx*C + ch
+  EPI_ST_O1 = 8,          // G=1  the output gate of ST-LSTM / Causal LSTM split over two launches: a plain G = 1 conv leaves one of
+                          //      (conv_o(mem), conv_last(mem)) as raw fp32 dense NHWC in `res`, this launch computes the other and
+                          //      h' = gate(o_part + conv_o) * tanh(conv_last), s0 = o_part (state layout).  variant bit 0: tanh gate
+                          //      (Causal LSTM) instead of sigmoid; bit 1: acc = conv_o and res = conv_last (the form the rollouts
+                          //      use: the memory-bound reads then hide behind the k x k MMAs), else the other way round.
+                          //      The fused EPI_ST_O launch spends half of its k x k MMAs on the zero rows of conv_last's gate
+                          //      column; worth two launches once the layer is tensor-bound.  Same sums, same order: bit-identical
   EPI_DECOUPLE = 6,       // G=2  (adapter(delta_c), adapter(delta_m)): per-(sample, channel) dot product and squared norms
                           //      over the positions (PredRNN-V2 decoupling loss); nothing else is stored.  tcgen05 halo
                           //      kernel only: s1[b][slot][C][3] gets one warp's 32 positions per slot (slot as gn_slot0 / gn_nslots)

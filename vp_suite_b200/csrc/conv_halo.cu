@@ -1638,6 +1638,7 @@ void launch_conv_halo(const HaloPlan& P, cudaStream_t stream) {
     case EPI_ST_C: VPK_HALO(EPI_ST_C);
     case EPI_ST_M: VPK_HALO(EPI_ST_M);
     case EPI_ST_O: VPK_HALO(EPI_ST_O);
+    case EPI_ST_O1: VPK_HALO(EPI_ST_O1);
     case EPI_PHY_GATE: VPK_HALO(EPI_PHY_GATE);
     case EPI_SUBPIX:
       VPK_REQUIRE(P.fast_epi, "conv_halo: the sub-pixel epilogue needs whole 8-channel chunks");

@@ -278,6 +278,7 @@ void launch_conv_tc2(const TcPlan& P, cudaStream_t stream) {
     case EPI_ST_C: launch_kind<EPI_ST_C>(P, stream); break;
     case EPI_ST_M: launch_kind<EPI_ST_M>(P, stream); break;
     case EPI_ST_O: launch_kind<EPI_ST_O>(P, stream); break;
+    case EPI_ST_O1: launch_kind<EPI_ST_O1>(P, stream); break;
     case EPI_PHY_GATE: launch_kind<EPI_PHY_GATE>(P, stream); break;
     default: VPK_THROW(1, "conv_tc2: unsupported epilogue kind");
   }

@@ -193,6 +193,9 @@ __device__ __forceinline__ void epilogue_prefetch(const EpiParams& E, int b, int
     if (E.kind == EPI_PHY_GATE) {
       load_act<NCH>(static_cast<const T*>(E.q0) + pix * C + ch0, o.a, nvalid);
       load_f32<NCH>(E.res + pix * C + ch0, o.b, nvalid);
+    } else if (E.kind == EPI_ST_O1) {
+      load_state<NCH>(E.s0, state_addr(E, b, y, x, H, W, ch0, true), o.a, nvalid);
+      load_f32<NCH>(E.res + pix * C + ch0, o.b, nvalid);
     } else if (E.res != nullptr) {
       load_f32<NCH>(E.res + pix * C + ch0, o.a, nvalid);
     }
@@ -249,6 +252,16 @@ __device__ __forceinline__ void epilogue_finish(const EpiParams& E, int b, int y
             else static_cast<T*>(E.out)[oo] = from_f32<T>(v[j]);
           }
       }
+    } else if (E.kind == EPI_ST_O1) {   // (o.a = o_part)  variant & 2: acc = conv_o(mem), o.b = conv_last(mem); else swapped
+      float h[NCH];
+      const bool swapped = (E.variant & 2) != 0;
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const float gate = o.a[j] + (swapped ? acc[0][j] : o.b[j]);
+        const float last = swapped ? o.b[j] : acc[0][j];
+        h[j] = ((E.variant & 1) ? tanh_t<FAST>(gate) : sigmoid_t<FAST>(gate)) * tanh_t<FAST>(last);
+      }
+      store_act<NCH>(static_cast<T*>(E.out) + b * E.oB + y * E.oY + x * E.oX + ch0, h, nvalid);
     } else {   // EPI_PHY_GATE: h' = h~ + sigmoid(acc) * (x - h~)      (model_blocks/phydnet.py:58-61)
       float v[NCH];
 #pragma unroll

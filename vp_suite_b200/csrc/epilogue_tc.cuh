@@ -153,6 +153,9 @@ __device__ __forceinline__ void epi_tc_prefetch(const EpiParams& E, const EpiTil
     }
   } else if constexpr (KIND == EPI_ST_C || KIND == EPI_ST_M || KIND == EPI_ST_O) {
     ld_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+  } else if constexpr (KIND == EPI_ST_O1) {
+    ld_state8(E.s0, t.st_off, t.st_g, ch, o.a);
+    ld_f32x8(E.res + t.pix_c + ch, o.b);
   } else if constexpr (KIND == EPI_PHY_GATE) {
     ld_bf16x8(static_cast<const bf16*>(E.q0) + t.pix_c + ch, o.a);
     ld_f32x8(E.res + t.pix_c + ch, o.b);
@@ -271,6 +274,16 @@ __device__ __forceinline__ void epi_tc_finish(const EpiParams& E, const EpiTile&
     st_state8(E.s0, t.st_off, t.st_g, ch, o.a);
     st_bf16x8(static_cast<bf16*>(E.t0) + t.pix_t0 + ch, o.a);
     if (E.t1 != nullptr) st_bf16x8(static_cast<bf16*>(E.t1) + t.pix_c + ch, dm);
+  } else if constexpr (KIND == EPI_ST_O1) {   // (o.a = o_part)  variant & 2: acc = conv_o(mem), o.b = conv_last(mem); else swapped
+    float h[8];
+    const bool swapped = (E.variant & 2) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float gate = o.a[j] + (swapped ? acc[0][j] : o.b[j]);
+      const float last = swapped ? o.b[j] : acc[0][j];
+      h[j] = ((E.variant & 1) ? tanh_fast(gate) : sigmoid_fast(gate)) * tanh_fast(last);
+    }
+    st_bf16x8(static_cast<bf16*>(E.out) + t.out_off + ch, h);
   } else {   // EPI_ST_O: acc = (conv_o(mem), conv_last(mem))
     float h[8];
     if (E.variant == 2) {   // gradient highway unit (causal.h): acc = (p, u), o.a = z

@@ -136,6 +136,12 @@ class PredRnnV2 : public StLstmModelBase {
     }
     float* mstate = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     float* opart = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
+    // launch O as conv_o + conv_last (stlstm.h: o_raw) once the layer is tensor-bound: two position tiles per SM and more.
+    // Bit-identical to the fused launch (tests: full batch == repeated small batch), so the size rule is invisible.
+    // VPK_SPLIT_O=0/1 overrides (A/B runs)
+    bool split_o = d.layer_norm == 0 && dtype != DT_F32 && backend == 0 && px / 128 >= 2 * static_cast<size_t>(num_sms);
+    if (const char* env = getenv("VPK_SPLIT_O")) split_o = d.layer_norm == 0 && atoi(env) != 0;
+    float* oraw_split = split_o ? static_cast<float*>(arena.alloc(px * C * sizeof(float))) : nullptr;
     char* dcdm = static_cast<char*>(arena.alloc(2 * px * C * esz));          // [delta_c ; delta_m] stacked on batch
     float* adapt = static_cast<float*>(arena.alloc(2 * px * C * sizeof(float)));
     // layer_norm=True: raw conv outputs (fp32), a dense copy of m for conv_m, statistics slots
@@ -265,6 +271,7 @@ class PredRnnV2 : public StLstmModelBase {
                      hp(pre + "conv_x.0.weight"), hp(pre + "conv_h.0.weight"), hp(pre + "conv_m.0.weight"),
                      hp(pre + "conv_o.0.weight"), hp(pre + "conv_last.weight")};
         a.c4 = true;
+        a.o_raw = oraw_split;
         if (!ln) {
           for (const ConvSpec& sp : stlstm_specs(a, act)) add_conv(prog, sp, measure, stream, adt);
         } else {

@@ -80,6 +80,10 @@ class PredRnnPP : public Model {
     }
     float* mstate = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     float* opart = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
+    // launch O as two launches once the layer is tensor-bound (stlstm.h: o_raw; bit-identical); VPK_SPLIT_O=0/1 overrides
+    bool split_o = dtype != DT_F32 && backend == 0 && px / 128 >= 2 * static_cast<size_t>(num_sms);
+    if (const char* env = getenv("VPK_SPLIT_O")) split_o = atoi(env) != 0;
+    float* oraw = split_o ? static_cast<float*>(arena.alloc(px * C * sizeof(float))) : nullptr;
     void* zb[2] = {arena.alloc(px * C * esz), arena.alloc(px * C * esz)};
     float* zstate = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     float* xgen32 = static_cast<float*>(arena.alloc(px * cp * sizeof(float)));
@@ -133,6 +137,7 @@ class PredRnnPP : public Model {
                      hp(pre + "conv_m.0.weight"), hp(pre + "conv_c2m.0.weight"), hp(pre + "conv_om.0.weight"),
                      hp(pre + "conv_last.weight")};
         a.c4 = true;
+        a.o_raw = oraw;
         for (const ConvSpec& sp : causal_lstm_specs(a, act)) add_conv(prog, sp, measure, stream, dtype);
         par[i] ^= 1;
         if (i == 0) {   // z_t = GHU(h_t^1, z_{t-1}): read zb[t & 1], write zb[(t + 1) & 1]

@@ -31,6 +31,10 @@ struct StLstmArgs {
   void* dm;               // [B,H,W,C] delta_m
   const float *w_x, *w_h, *w_m, *w_o, *w_last;   // host, reference layouts
   bool c4 = false;        // c, m, o_part use the channel-quad layout (rollouts); the NCHW-boundary cell keeps NHWC
+  // optional fp32 dense [B,H,W,C] scratch: launch O then runs as TWO launches (EPI_ST_O1, common.h) -- conv_o alone with
+  // N = C (half the MMA work of the fused form, whose conv_last gate column is zero for all k x k taps) and the 1 x 1
+  // conv_last with the output gate in its epilogue.  Bit-identical to the fused launch; pays when the layer is tensor-bound
+  float* o_raw = nullptr;
 };
 
 inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& act) {
@@ -92,7 +96,43 @@ inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& ac
     e.t1 = a.dm;
     out.push_back(std::move(s));
   }
-  {  // ---- O ----
+  if (a.o_raw != nullptr) {  // ---- O as conv_last (1 x 1, raw) + conv_o (k x k, N = C) with the output gate ----
+    const SrcView mv = make_view(a.mem, a.H, a.W, 2 * C);
+    {
+      ConvSpec s;
+      s.name = a.name + "O.conv_last";
+      s.B = a.B;
+      s.G = 1;
+      s.C = C;
+      s.is_gate_gemm = true;
+      s.wrefs.push_back(wref(a.w_last, C, 2 * C, 1, {0}));
+      lower_conv(s, 1, 1, 0, {ConvInput{mv, 0, 0}}, a.H, a.W, act.esize, &oh, &ow);
+      EpiParams& e = s.phases[0].epi;
+      e.kind = EPI_BIAS_ACT;
+      e.act = ACT_NONE;
+      e.out_f32 = 1;
+      dense_out(e, a.o_raw, a.H, a.W, C);
+      out.push_back(std::move(s));
+    }
+    {
+      ConvSpec s;
+      s.name = a.name + "O.conv_o";
+      s.B = a.B;
+      s.G = 1;
+      s.C = C;
+      s.is_gate_gemm = true;
+      s.wrefs.push_back(wref(a.w_o, C, 2 * C, k, {0}));
+      lower_conv(s, k, 1, pad, {ConvInput{mv, 0, 0}}, a.H, a.W, act.esize, &oh, &ow);
+      EpiParams& e = s.phases[0].epi;
+      e.kind = EPI_ST_O1;
+      e.variant = 2;
+      e.state_c4 = (a.c4 && C % 4 == 0) ? 1 : 0;
+      e.s0 = a.o_part;
+      e.res = a.o_raw;
+      dense_out(e, a.h_out, a.H, a.W, C);
+      out.push_back(std::move(s));
+    }
+  } else {  // ---- O ----
     ConvSpec s;
     s.name = a.name + "O";
     s.B = a.B;
