@@ -83,6 +83,7 @@ inline std::vector<ConvSpec> causal_lstm_specs(const CausalArgs& a, const ActInf
     e.t0 = a.mem;
     e.t0_pix = 2 * C;
     e.t1 = nullptr;
+    s.region_g0 = 3;        // c does not feed o_part: regions (i, f, g) | (o_x + o_h)
     out.push_back(std::move(s));
   }
   {  // ---- M: spatial memory, cascaded behind c' ----
@@ -106,6 +107,7 @@ inline std::vector<ConvSpec> causal_lstm_specs(const CausalArgs& a, const ActInf
     e.s0 = a.m;
     e.t0 = static_cast<char*>(a.mem) + static_cast<size_t>(C) * act.esize;
     e.t0_pix = 2 * C;
+    s.region_g0 = 3;        // x and c' do not feed m_m: regions (i', f', g') | (m_m)
     out.push_back(std::move(s));
   }
   if (a.o_raw != nullptr) {  // ---- O as conv_last (1 x 1, raw) + (conv_c2m[o](c') + conv_om(m')) with the output gate ----
@@ -162,6 +164,7 @@ inline std::vector<ConvSpec> causal_lstm_specs(const CausalArgs& a, const ActInf
     e.state_c4 = c4;
     e.s0 = a.o_part;
     dense_out(e, a.h_out, a.H, a.W, C);
+    s.region_g0 = 1;        // k x k taps feed the output gate only, the 1 x 1 taps conv_last only
     out.push_back(std::move(s));
   }
   return out;

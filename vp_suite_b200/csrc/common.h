@@ -156,6 +156,11 @@ struct ConvLaunch {
   int op_f16;             // 16-bit operands are fp16 instead of bf16 (tensor-core kernels: instruction descriptor)
   double flops;           // 2*M*N*K of the real (unpadded) contraction
   int is_gate_gemm;       // counted in the gate-GEMM roofline figure
+  // tcgen05 halo kernel, CTA pairs only: > 0 splits the G gate columns of a channel into two accumulator REGIONS, gates
+  // [0, region_g0) and [region_g0, G), packed region-major inside each CTA's half of an N tile; a tap then issues only the
+  // regions its weight tensor feeds (conv_halo.cu).  Multi-source gate convs whose sources feed different gates
+  // (Causal LSTM: m_m is fed by m alone; ST-LSTM output: conv_last is 1 x 1) otherwise multiply zero weight rows.
+  int region_g0;
 };
 
 // Environment switches.  Everything the shipping library reads with getenv() selects between code paths that compute

@@ -40,6 +40,7 @@ constexpr unsigned kMaxSmem = 232448 - 1024;   // room for the static trace slot
 constexpr unsigned kMaxSmem = 232448;
 #endif
 constexpr uint32_t kTapFirstOfBlock = 1, kTapLastOfBlock = 2, kTapFirstOfGroup = 4, kTapLastOfGroup = 8;
+constexpr uint32_t kTapRegionA = 32, kTapRegionB = 64;   // accumulator regions the tap feeds (ConvLaunch::region_g0)
 constexpr uint32_t kTapFuseNext = 16;   // the next tap needs no hand-off in between and both are full (4 K-slices): one asm block
 
 __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
@@ -160,10 +161,13 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     }
     const int hwp = kTW + 2 * P.P;
     const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
-    const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk);
-    // fuse with the next tap: same block, no group boundary in between, both with 4 K-slices
-    if (q + 1 < blk.ntaps && !(flags & (kTapLastOfGroup | kTapLastOfBlock)) && nk == 4 && P.taps[i + 1].nk == 4 &&
-        (P.resident || (g + 1) % P.bgroup != 0))
+    const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk & 0xFF);
+    const uint32_t regions = static_cast<uint32_t>(tp.nk >> 8) & 3u;
+    if (regions & 1u) flags |= kTapRegionA;
+    if (regions & 2u) flags |= kTapRegionB;
+    // fuse with the next tap: same block, no group boundary in between, both with 4 K-slices, feeding the same accumulator regions
+    if (q + 1 < blk.ntaps && !(flags & (kTapLastOfGroup | kTapLastOfBlock)) && nk == 4 && (P.taps[i + 1].nk & 0xFF) == 4 &&
+        (P.resident || (g + 1) % P.bgroup != 0) && (P.taps[i + 1].nk >> 8) == (tp.nk >> 8))
       flags |= kTapFuseNext;
     s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24),
                              static_cast<uint32_t>(P.resident ? i : g) * (P.b_tap_stride >> 4));
@@ -373,6 +377,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     // Descriptors move by their low word only (start address in 16-byte units; shared memory < 256 KB: no carry).
     if (leader && ptx::elect_one()) {
       const uint32_t idesc = ptx::idesc_bf16_f32(PAIR ? 256 : 128, tileN, P.L.op_f16 != 0);
+      // accumulator regions (pairs only): widths over the pair, first column of region B, first weight row of region B in a half
+      const int rg_a = P.L.region_g0, rg_cn = tileN / G;
+      const uint32_t idesc_ra = ptx::idesc_bf16_f32(256, rg_a > 0 ? rg_cn * rg_a : tileN, P.L.op_f16 != 0);
+      const uint32_t idesc_rb = ptx::idesc_bf16_f32(256, rg_a > 0 ? rg_cn * (G - rg_a) : tileN, P.L.op_f16 != 0);
+      const uint32_t region_col_b = static_cast<uint32_t>(rg_cn * rg_a);
+      const uint32_t region_row_b = static_cast<uint32_t>((rg_cn / 2) * rg_a * 128) >> 4;
       const uint32_t sbo = (P.debug & 64) ? 1024u : static_cast<uint32_t>(HWp * 128);
       const uint64_t adesc0 = smem_desc_sw128_sbo(ptx::smem_u32(smem_a), sbo);
       const uint64_t bdesc0 = ptx::smem_desc_sw128(ptx::smem_u32(smem_b));
@@ -396,7 +406,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         VPK_TIMED(w_acc, ptx::mbar_wait_spin(tempty + 8 * acc, ((iter >> 1) & 1u) ^ 1u));
         ptx::tc_fence_after();
         const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * tileN);
-        uint32_t accum = 0;
+        uint32_t accum = 0, accum_b = 0;
         uint32_t tab = tab0;
         uint2 ti = ptx::lds_u2(tab);
         for (int i = 0; i < ntaps; ++i) {
@@ -421,16 +431,44 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             tab += 8;
             ti = ptx::lds_u2(tab);
             ++i;
-            if constexpr (PAIR)
-              ptx::mma_bf16_ss_tap2_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
-            else
+            if constexpr (PAIR) {
+              if (flags & (kTapRegionA | kTapRegionB)) {      // accumulator regions (see the single-tap form below)
+                if (flags & kTapRegionA) {
+                  ptx::mma_bf16_ss_tap2_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc_ra, accum);
+                  accum = 1u;
+                }
+                if (flags & kTapRegionB) {
+                  ptx::mma_bf16_ss_tap2_pair(tmem_d + region_col_b, a_d + (cur.x & 0xFFFFu), b_d + cur.y + region_row_b,
+                                             a_d + (nx.x & 0xFFFFu), b_d + nx.y + region_row_b, idesc_rb, accum_b);
+                  accum_b = 1u;
+                }
+              } else {
+                ptx::mma_bf16_ss_tap2_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
+              }
+            } else {
               ptx::mma_bf16_ss_tap2(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
+            }
             lflags = nx.x >> 16;
+          } else if (PAIR && (flags & (kTapRegionA | kTapRegionB))) {
+            // accumulator regions: region A = columns [0, N_A) <- the first rows of each CTA's weight half, region B behind it;
+            // a tap multiplies only what its weight tensor feeds (N is constant per region, as cta_group::2's column split needs)
+            if constexpr (PAIR) {
+              if (flags & kTapRegionA) {
+                ptx::mma_bf16_ss_tap_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc_ra, accum, (cur.x >> 24) & 0xFFu);
+                accum = 1u;
+              }
+              if (flags & kTapRegionB) {
+                ptx::mma_bf16_ss_tap_pair(tmem_d + region_col_b, a_d + (cur.x & 0xFFFFu), b_d + cur.y + region_row_b, idesc_rb, accum_b,
+                                          (cur.x >> 24) & 0xFFu);
+                accum_b = 1u;
+              }
+            }
           } else {
             if constexpr (PAIR) ptx::mma_bf16_ss_tap_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, (cur.x >> 24) & 0xFFu);
             else ptx::mma_bf16_ss_tap(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, (cur.x >> 24) & 0xFFu);
+            accum = 1u;
           }
-          accum = 1u;
+          if (!(flags & (kTapRegionA | kTapRegionB))) accum = 1u;
           if (lflags & (kTapLastOfGroup | kTapLastOfBlock)) {
             const uint32_t flags = lflags;
             if (flags & kTapLastOfGroup) {
@@ -990,6 +1028,28 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const int ch_base = nt * Cn;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
       auto tmem_chunk = [&](int ch, uint32_t (&r)[8 * G]) {
+        if constexpr (PAIR && (G == 4 || G == 2)) {
+          if (P.L.region_g0 > 0) {
+            // accumulator regions: columns [0, N_A) hold gates [0, g0), CTA halves side by side inside each region
+            // (cta_group::2 takes columns [0, N/2) of an MMA from the leader's weight rows and [N/2, N) from its peer's)
+            constexpr int GA = (G == 4) ? 3 : 1, GB = 1;
+            const int hc = Cn >> 1, hf = ch >= hc ? 1 : 0, cj = ch - hf * hc;
+            const uint32_t ca = taddr + static_cast<uint32_t>(hf * hc * GA + cj * GA);
+            const uint32_t cb = taddr + static_cast<uint32_t>(Cn * GA + hf * hc * GB + cj * GB);
+            uint32_t ra[8 * GA], rb[8 * GB];
+            if constexpr (GA == 3) { ptx::tmem_ld8(ca, ra); ptx::tmem_ld8(ca + 8, ra + 8); ptx::tmem_ld8(ca + 16, ra + 16); }
+            else ptx::tmem_ld8(ca, ra);
+            ptx::tmem_ld8(cb, rb);
+            ptx::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+              for (int g = 0; g < GA; ++g) r[j * G + g] = ra[j * GA + g];
+              r[j * G + GA] = rb[j];
+            }
+            return;
+          }
+        }
         const uint32_t ta = taddr + static_cast<uint32_t>(ch * G);
         if constexpr (G == 4) ptx::tmem_ld32(ta, r);
         else if constexpr (G == 2) ptx::tmem_ld16(ta, r);
@@ -1337,6 +1397,13 @@ bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int 
   return radius >= 0 && radius <= 3 && nblocks >= 1 && nblocks <= 64 && ntaps <= kMaxSteps;
 }
 
+bool halo_will_pair(int B, int H, int W, int tileN, int n_tiles, int num_sms) {
+  const long long m_tiles = static_cast<long long>(B) * ((W + kTW - 1) / kTW) * ((H + kTH - 1) / kTH);
+  bool pair = tileN % 16 == 0 && m_tiles * n_tiles >= num_sms;
+  if (const char* env = getenv("VPK_TC_PAIR")) pair = atoi(env) != 0 && tileN % 16 == 0;
+  return pair;
+}
+
 void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
                     int radius, HaloPlan* plan, int num_sms, unsigned reserve_smem) {
   HaloPlan& P = *plan;
@@ -1354,8 +1421,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   P.tiles_x = (L.W + kTW - 1) / kTW;
   P.tiles_y = (L.H + kTH - 1) / kTH;
   const long long m_tiles = static_cast<long long>(L.B) * P.tiles_x * P.tiles_y;
-  P.pair = (P.tileN % 16 == 0 && m_tiles * P.n_tiles >= num_sms) ? 1 : 0;
-  if (const char* env = getenv("VPK_TC_PAIR")) P.pair = (atoi(env) != 0 && P.tileN % 16 == 0) ? 1 : 0;
+  P.pair = halo_will_pair(L.B, L.H, L.W, P.tileN, P.n_tiles, num_sms) ? 1 : 0;
+  VPK_REQUIRE(L.region_g0 == 0 || P.pair, "conv_halo: accumulator regions need a CTA-pair launch");
   P.debug = 0;
   if (const char* env = dev_env("VPK_TC_DEBUG")) P.debug = atoi(env);
   P.L.epi.debug = P.debug;

@@ -29,7 +29,8 @@ struct HaloBlock {             // one (source, 64-channel block): its activation
 };
 struct HaloTap {               // one tap of a block: shifted view of the halo tile x one weight tile
   signed char dy, dx;
-  short nk;                    // K=16 MMA slices (ceil(kc / 16))
+  short nk;                    // low byte: K=16 MMA slices (ceil(kc / 16)); high byte: accumulator regions this tap feeds
+                               // (1 = first, 2 = second, 0 = no regions in use; ConvLaunch::region_g0)
   int wk;                      // column offset in the packed weights
 };
 struct alignas(64) HaloPlan {
@@ -91,6 +92,8 @@ struct HaloSeqSpec {
 bool halo_make_seq_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
                         int radius, const HaloSeqSpec& seq, HaloPlan* plan, int num_sms);
 bool halo_eligible(const ConvLaunch& L, int dtype, int radius, int nblocks, int ntaps);
+// the CTA-pair rule of halo_make_plan (shared with build_conv, which packs region-major weights for pair launches only)
+bool halo_will_pair(int B, int H, int W, int tileN, int n_tiles, int num_sms);
 void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTap* d_taps, int nblocks, int ntaps,
                     int radius, HaloPlan* plan, int num_sms, unsigned reserve_smem = 0);
 void launch_conv_halo(const HaloPlan& plan, cudaStream_t stream);

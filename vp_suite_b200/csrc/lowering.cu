@@ -285,9 +285,29 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
   const int Cn = choose_cn(C, G);
   const int N_pad = (C + Cn - 1) / Cn * Cn * G;
 
+  // Accumulator regions (ConvLaunch::region_g0): only for CTA-pair launches of the tcgen05 halo kernel with whole 8-channel
+  // chunks per CTA half, no bias, and one of the two gate splits the epilogue reads ((3, 1) of G = 4, (1, 1) of G = 2).
+  // The packed copy is region-major then, so it gets its own cache entry (a small batch of the same layer runs without pairs)
+  int rg0 = 0;
+  if (spec.region_g0 > 0 && backend == 0 && dtype != DT_F32 && spec.biases.empty() && spec.phases.size() == 1 &&
+      Cn % 16 == 0 && C % Cn == 0 && ((G == 4 && spec.region_g0 == 3) || (G == 2 && spec.region_g0 == 1)) &&
+      getenv("VPK_NO_REGIONS") == nullptr) {
+    const char* halo_env = getenv("VPK_TC_HALO");
+    if ((halo_env == nullptr || atoi(halo_env) != 0) &&
+        halo_will_pair(spec.B, spec.phases[0].H, spec.phases[0].W, Cn * G, N_pad / (Cn * G), num_sms))
+      rg0 = spec.region_g0;
+  }
+  const std::string cache_key = spec.name + (rg0 ? "#regions" : "");
+  // packed row of (channel, gate): gate-interleaved, or region-major inside each CTA half of the N tile
+  auto row_of = [&](int ch, int g) {
+    if (rg0 == 0) return ch * G + g;
+    const int tile = ch / Cn, cl = ch % Cn, hc = Cn / 2, half = cl / hc, cj = cl % hc, ga = rg0, gb = G - rg0;
+    return tile * Cn * G + half * hc * G + (g < ga ? cj * ga + g : hc * ga + cj * gb + (g - ga));
+  };
+
   std::vector<PackedWeights>* packed = nullptr;
   if (!measure_only) {
-    auto it = cache.find(spec.name);
+    auto it = cache.find(cache_key);
     if (it == cache.end()) {
       std::vector<PackedWeights> pw(spec.phases.size());
       // bias (shared by the phases)
@@ -316,7 +336,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
             for (int g = 0; g < G; ++g) {
               if (w.gate_block[g] < 0) continue;
               const int oc = w.gate_block[g] * C + ch;
-              float* row = wf.data() + static_cast<size_t>(ch * G + g) * K_pad + h.s.wk;
+              float* row = wf.data() + static_cast<size_t>(row_of(ch, g)) * K_pad + h.s.wk;
               if (h.per_gate && h.gky[g] < 0) continue;       // this parity does not read this input offset
               const int ky = h.per_gate ? h.gky[g] : h.ky, kx = h.per_gate ? h.gkx[g] : h.kx;
               for (int j = 0; j < h.kw_valid; ++j) {
@@ -347,12 +367,21 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         }
         std::vector<ConvStep> cs(steps.size());
         for (size_t i = 0; i < steps.size(); ++i) cs[i] = steps[i].s;
+        std::vector<int> region_mask(steps.size(), 0);
+        if (rg0)
+          for (size_t i = 0; i < steps.size(); ++i) {
+            const WeightRef& w = spec.wrefs[steps[i].wref];
+            for (int g = 0; g < G; ++g)
+              if (w.gate_block[g] >= 0) region_mask[i] |= (g < rg0) ? 1 : 2;
+            VPK_REQUIRE(region_mask[i] != 0, "conv step feeds no gate: " + spec.name);
+          }
         q.steps = static_cast<ConvStep*>(store.upload(cs.data(), cs.size() * sizeof(ConvStep), stream));
         // halo-kernel tables: consecutive steps of one (source, channel block) form a block
         std::vector<HaloBlock> hb;
         std::vector<HaloTap> ht;
         int radius = 0;
-        for (const ConvStep& c : cs) {
+        for (size_t ci = 0; ci < cs.size(); ++ci) {
+          const ConvStep& c = cs[ci];
           if (hb.empty() || hb.back().src != c.src || hb.back().c0 != c.c0) {
             HaloBlock b{};
             b.src = c.src;
@@ -365,7 +394,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
           HaloTap t{};
           t.dy = c.dy;
           t.dx = c.dx;
-          t.nk = static_cast<short>((c.kc + 15) / 16);
+          t.nk = static_cast<short>(((c.kc + 15) / 16) | (region_mask[ci] << 8));
           t.wk = c.wk;
           ht.push_back(t);
           hb.back().ntaps++;
@@ -377,7 +406,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
         q.ntaps = static_cast<int>(ht.size());
         q.radius = radius;
       }
-      it = cache.emplace(spec.name, std::move(pw)).first;
+      it = cache.emplace(cache_key, std::move(pw)).first;
     }
     packed = &it->second;
     VPK_REQUIRE(packed->size() == spec.phases.size(), "packed-weight cache mismatch for " + spec.name);
@@ -401,6 +430,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
     L.epi = ph.epi;
     L.epi.C = C;
     L.is_gate_gemm = spec.is_gate_gemm ? 1 : 0;
+    L.region_g0 = rg0;
     L.op_f16 = (dtype == DT_F16) ? 1 : 0;
     VPK_REQUIRE(dtype != DT_F16 || G == 1 || ph.epi.kind == EPI_DECOUPLE, "fp16 operands are for plain convs only: " + spec.name);
     double kreal = 0;
@@ -450,6 +480,7 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
       VPK_REQUIRE(L.epi.kind != EPI_SUBPIX || bc.use_halo, "the sub-pixel epilogue needs the tcgen05 halo kernel");
       VPK_REQUIRE(L.epi.gn_sums == nullptr || bc.use_halo,
                   "fused GroupNorm statistics need the tcgen05 halo kernel for " + spec.name);
+      VPK_REQUIRE(rg0 == 0 || bc.use_halo, "accumulator regions need the tcgen05 halo kernel for " + spec.name);
       if (bc.use_halo) halo_make_plan(L, q.blocks, q.taps, q.nblocks, q.ntaps, q.radius, &bc.halo, num_sms);
       if (bc.use_tc) tc_make_plan(L, &bc.tc, num_sms);
     }

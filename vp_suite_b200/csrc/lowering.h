@@ -55,6 +55,8 @@ struct ConvSpec {
   std::vector<BiasRef> biases;
   std::vector<PhaseSpec> phases;
   bool is_gate_gemm = false;
+  int region_g0 = 0;                // request: accumulator regions [0, g0) / [g0, G) (ConvLaunch::region_g0); honoured when the
+                                    // launch will run on CTA pairs of the tcgen05 halo kernel, ignored otherwise
 };
 
 struct ConvInput {                  // one logical input tensor of a conv (full-resolution NHWC view)

@@ -139,7 +139,8 @@ class PredRnnV2 : public StLstmModelBase {
     // launch O as conv_o + conv_last (stlstm.h: o_raw) once the layer is tensor-bound: two position tiles per SM and more.
     // Bit-identical to the fused launch (tests: full batch == repeated small batch), so the size rule is invisible.
     // VPK_SPLIT_O=0/1 overrides (A/B runs)
-    bool split_o = d.layer_norm == 0 && dtype != DT_F32 && backend == 0 && px / 128 >= 2 * static_cast<size_t>(num_sms);
+    bool split_o = d.layer_norm == 0 && dtype != DT_F32 && backend == 0 && px / 128 >= 2 * static_cast<size_t>(num_sms) &&
+                   getenv("VPK_NO_REGIONS") != nullptr;   // superseded by accumulator regions in the fused launch (lowering.cu)
     if (const char* env = getenv("VPK_SPLIT_O")) split_o = d.layer_norm == 0 && atoi(env) != 0;
     float* oraw_split = split_o ? static_cast<float*>(arena.alloc(px * C * sizeof(float))) : nullptr;
     char* dcdm = static_cast<char*>(arena.alloc(2 * px * C * esz));          // [delta_c ; delta_m] stacked on batch

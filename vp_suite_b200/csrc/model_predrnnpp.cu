@@ -81,7 +81,8 @@ class PredRnnPP : public Model {
     float* mstate = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     float* opart = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     // launch O as two launches once the layer is tensor-bound (stlstm.h: o_raw; bit-identical); VPK_SPLIT_O=0/1 overrides
-    bool split_o = dtype != DT_F32 && backend == 0 && px / 128 >= 2 * static_cast<size_t>(num_sms);
+    bool split_o = dtype != DT_F32 && backend == 0 && px / 128 >= 2 * static_cast<size_t>(num_sms) &&
+                   getenv("VPK_NO_REGIONS") != nullptr;   // superseded by accumulator regions in the fused launch (lowering.cu)
     if (const char* env = getenv("VPK_SPLIT_O")) split_o = atoi(env) != 0;
     float* oraw = split_o ? static_cast<float*>(arena.alloc(px * C * sizeof(float))) : nullptr;
     void* zb[2] = {arena.alloc(px * C * esz), arena.alloc(px * C * esz)};

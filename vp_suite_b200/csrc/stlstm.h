@@ -149,6 +149,7 @@ inline std::vector<ConvSpec> stlstm_specs(const StLstmArgs& a, const ActInfo& ac
     e.state_c4 = (a.c4 && C % 4 == 0) ? 1 : 0;
     e.s0 = a.o_part;
     dense_out(e, a.h_out, a.H, a.W, C);
+    s.region_g0 = 1;        // k x k taps feed conv_o only, the 1 x 1 taps conv_last only (ConvLaunch::region_g0)
     out.push_back(std::move(s));
   }
   return out;
