@@ -155,3 +155,34 @@ def test_single_step_blocks_match_oracle(cin, C, hw, k, precision, backend):
     want2 = causal.causal_lstm_step(x, h, c, m, w2)
     got2 = cell(x.cuda(), h.cuda(), c.cuda(), m.cuda())
     assert float((got2[0].cpu() - want2[0]).abs().max()) <= tol
+
+
+@pytest.mark.parametrize("key", ["predrnn-pp-causal", "predrnn-pp"])
+def test_accumulator_regions_and_split_output_gate_are_bit_identical(key, monkeypatch):
+    """Three forms of the multi-source gate launches must give the same bits: accumulator regions (default once the launch
+    runs on CTA pairs: a tap multiplies only the gate columns its weight tensor feeds), the zero-padded single accumulator
+    (VPK_NO_REGIONS=1) and the output gate as two launches (VPK_SPLIT_O=1, EPI_ST_O1).  80 sequences = 160 position tiles:
+    enough for CTA pairs; 3 sequences run without pairs (no regions) and must agree as well."""
+    import vp_suite_b200 as V
+    img, L, C, k = (1, 64, 64), 2, 64, 5
+    kw = dict(img_shape=img, num_layers=L, num_hidden=[C] * L, filter_size=k, precision="bf16", **KW)
+    x = synth_frames(3, 5, *img, seed=13)
+    xb = x.repeat(27, 1, 1, 1, 1)[:80].cuda()
+    outs = {}
+    for name, env in (("regions", {}), ("padded", {"VPK_NO_REGIONS": "1"}), ("split", {"VPK_NO_REGIONS": "1", "VPK_SPLIT_O": "1"})):
+        for var in ("VPK_NO_REGIONS", "VPK_SPLIT_O"):
+            monkeypatch.delenv(var, raising=False)
+        for var, val in env.items():
+            monkeypatch.setenv(var, val)
+        m = V.MODEL_CLASSES[key]("cuda:0", **kw).eval()
+        if name == "regions":
+            sd = synth_state_dict({n: tuple(v.shape) for n, v in m.state_dict().items()}, seed=4, gain=1.8)
+        m.load_state_dict(sd)
+        with torch.no_grad():
+            outs[name] = m(xb, pred_frames=2)[0]
+            if name == "regions":
+                small = m(x.cuda(), pred_frames=2)[0]
+    assert float(outs["regions"].abs().max()) > 1e-3
+    assert torch.equal(outs["regions"], outs["padded"])
+    assert torch.equal(outs["regions"], outs["split"])
+    assert torch.equal(outs["regions"][:3], small)
