@@ -157,14 +157,15 @@ def test_single_step_blocks_match_oracle(cin, C, hw, k, precision, backend):
     assert float((got2[0].cpu() - want2[0]).abs().max()) <= tol
 
 
-@pytest.mark.parametrize("key", ["predrnn-pp-causal", "predrnn-pp"])
-def test_accumulator_regions_and_split_output_gate_are_bit_identical(key, monkeypatch):
+@pytest.mark.parametrize("key,C,k", [("predrnn-pp-causal", 64, 5), ("predrnn-pp", 64, 5), ("predrnn-pp-causal", 16, 3),
+                                     ("predrnn-pp-causal", 48, 3)])
+def test_accumulator_regions_and_split_output_gate_are_bit_identical(key, C, k, monkeypatch):
     """Three forms of the multi-source gate launches must give the same bits: accumulator regions (default once the launch
     runs on CTA pairs: a tap multiplies only the gate columns its weight tensor feeds), the zero-padded single accumulator
     (VPK_NO_REGIONS=1) and the output gate as two launches (VPK_SPLIT_O=1, EPI_ST_O1).  80 sequences = 160 position tiles:
     enough for CTA pairs; 3 sequences run without pairs (no regions) and must agree as well."""
     import vp_suite_b200 as V
-    img, L, C, k = (1, 64, 64), 2, 64, 5
+    img, L = (1, 64, 64), 2          # C = 16, k = 3: weights small enough to stay resident in shared memory; C = 48: N = 144 + 48
     kw = dict(img_shape=img, num_layers=L, num_hidden=[C] * L, filter_size=k, precision="bf16", **KW)
     x = synth_frames(3, 5, *img, seed=13)
     xb = x.repeat(27, 1, 1, 1, 1)[:80].cuda()
@@ -184,5 +185,13 @@ def test_accumulator_regions_and_split_output_gate_are_bit_identical(key, monkey
                 small = m(x.cuda(), pred_frames=2)[0]
     assert float(outs["regions"].abs().max()) > 1e-3
     assert torch.equal(outs["regions"], outs["padded"])
-    assert torch.equal(outs["regions"], outs["split"])
+    if C >= 32:
+        assert torch.equal(outs["regions"], outs["split"])
+    else:   # a 1 x 1 conv over 2C <= 64 channels is a single-K-chunk head: it runs on the CUDA-core direct kernel (exact fp32
+        # sums instead of the tensor core's accumulation), so the two-launch form is not bit-compatible there: oracle bound
+        want, _ = causal.predrnnpp_forward(sd, x, 2, {"num_layers": L})
+        for name in ("regions", "split"):
+            errs = _errs(outs[name][:3].cpu(), want)
+            print(f"C = {C} {name}: per-frame max abs err vs the oracle {['%.1e' % e for e in errs]}, |frames| max {float(want.abs().max()):.2f}")
+            assert errs[0] <= 5e-3 and max(errs) <= 2e-2, (name, errs)
     assert torch.equal(outs["regions"][:3], small)
