@@ -210,10 +210,11 @@ int vpk_stlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const fl
  * module, so these entries replace no reference file: they are what a `model_blocks/predrnn_pp.py` written
  * to the paper would bind.  PARITY UNPINNED (checker: oracle/causal.py).
  *   Causal LSTM: weights = HOST fp32 arrays conv_x [7ch, cin, k, k] (i, f, g, i', f', g', o), conv_h [4ch, ch, k, k] (i, f, g, o),
- *   conv_c [3ch, ch, k, k] (i, f, g), conv_m [3ch, ch, k, k] (i', f', m_m), conv_c2m [4ch, ch, k, k] (i', g', f', o),
- *   conv_om [ch, ch, k, k], conv_last [ch, 2ch, 1, 1]; no biases, forget bias 1.  x [b, cin, h, w]; h, c, m [b, ch, h, w]. */
-int vpk_causal_lstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w,
-                                int32_t k, const float* const* weights, vpk_cell** out);
+ *   conv_c [3ch, ch, k, k] (i, f, g), conv_m [3ch, cm, k, k] (i', f', m_m; cm = channels of the memory the cell reads,
+ *   the width of the cell that wrote it), conv_c2m [4ch, ch, k, k] (i', g', f', o),
+ *   conv_om [ch, ch, k, k], conv_last [ch, 2ch, 1, 1]; no biases, forget bias 1.  x [b, cin, h, w]; h, c [b, ch, h, w]; m [b, cm, h, w]; m' [b, ch, h, w]. */
+int vpk_causal_lstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t cm, int32_t ch, int32_t h,
+                                int32_t w, int32_t k, const float* const* weights, vpk_cell** out);
 int vpk_causal_lstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const float* h, const float* c,
                               const float* m, float* h_out, float* c_out, float* m_out, void* stream);
 /*   Gradient highway unit: w_x, w_z HOST fp32 [2ch, ch, k, k] (rows p, u); z' = sig(u) z + (1 - sig(u)) tanh(p). */

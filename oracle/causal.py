@@ -79,21 +79,24 @@ def cell_weights(sd, prefix):
 
 
 def state_dict_shapes(img_c, num_layers, num_hidden, patch_size=4, filter_size=5):
-    """Key -> shape of the drop-in's state_dict (vp_suite_b200.models.PredRNNpp)."""
-    cp, k, C = patch_size * patch_size * img_c, filter_size, num_hidden
+    """Key -> shape of the drop-in's state_dict (vp_suite_b200.models.PredRNNpp).  ``num_hidden``: one width for all layers
+    or a list (the paper's stacks are 128-64-64-64): conv_m reads the memory written by the previous layer (the top layer for
+    layer 0), conv_x the previous layer's h (the GHU's z for layer 1, the patch frame for layer 0)."""
+    cp, k, L = patch_size * patch_size * img_c, filter_size, num_layers
+    hid = [num_hidden] * L if isinstance(num_hidden, int) else list(num_hidden)[:L]
     shapes = {}
-    for i in range(num_layers):
-        pre, cin = f"cell_list.{i}.", (cp if i == 0 else C)
+    for i in range(L):
+        pre, C, cin, cm = f"cell_list.{i}.", hid[i], (cp if i == 0 else hid[i - 1]), hid[(i - 1) % L]
         shapes[pre + "conv_x.0.weight"] = (7 * C, cin, k, k)
         shapes[pre + "conv_h.0.weight"] = (4 * C, C, k, k)
         shapes[pre + "conv_c.0.weight"] = (3 * C, C, k, k)
-        shapes[pre + "conv_m.0.weight"] = (3 * C, C, k, k)
+        shapes[pre + "conv_m.0.weight"] = (3 * C, cm, k, k)
         shapes[pre + "conv_c2m.0.weight"] = (4 * C, C, k, k)
         shapes[pre + "conv_om.0.weight"] = (C, C, k, k)
         shapes[pre + "conv_last.weight"] = (C, 2 * C, 1, 1)
-    shapes["gradient_highway.x_concat.0.weight"] = (2 * C, C, k, k)
-    shapes["gradient_highway.z_concat.0.weight"] = (2 * C, C, k, k)
-    shapes["conv_last.weight"] = (cp, C, 1, 1)
+    shapes["gradient_highway.x_concat.0.weight"] = (2 * hid[0], hid[0], k, k)
+    shapes["gradient_highway.z_concat.0.weight"] = (2 * hid[0], hid[0], k, k)
+    shapes["conv_last.weight"] = (cp, hid[L - 1], 1, 1)
     return shapes
 
 
@@ -108,11 +111,11 @@ def predrnnpp_forward(sd, x, pred_frames, cfg=None, q=None):
         raise ValueError("input must hold context and target frames")
     xp = reshape_patch(x, p)
     hp, wp = xp.shape[-2:]
-    C = sd["cell_list.0.conv_h.0.weight"].shape[1]
-    h_t = [torch.zeros(b, C, hp, wp, device=x.device) for _ in range(L)]
-    c_t = [torch.zeros(b, C, hp, wp, device=x.device) for _ in range(L)]
-    memory = torch.zeros(b, C, hp, wp, device=x.device)
-    z_t = torch.zeros(b, C, hp, wp, device=x.device)
+    hid = [sd[f"cell_list.{i}.conv_h.0.weight"].shape[1] for i in range(L)]
+    h_t = [torch.zeros(b, hid[i], hp, wp, device=x.device) for i in range(L)]
+    c_t = [torch.zeros(b, hid[i], hp, wp, device=x.device) for i in range(L)]
+    memory = torch.zeros(b, hid[L - 1], hp, wp, device=x.device)         # layer 0 reads the top layer's memory
+    z_t = torch.zeros(b, hid[0], hp, wp, device=x.device)
     ws = [cell_weights(sd, f"cell_list.{i}.") for i in range(L)]
     x_gen, frames = None, []
     for t in range(total - 1):

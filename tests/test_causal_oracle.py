@@ -60,6 +60,14 @@ def test_ghu_limits():
     assert torch.allclose(causal.ghu_step(-pos, z, wu, w0), torch.zeros_like(z), atol=1e-6)
 
 
+def test_unequal_widths_rollout_runs_and_uses_the_right_memory():
+    shapes = causal.state_dict_shapes(1, 3, [8, 4, 6], 4, 3)
+    sd = synth_state_dict(shapes, seed=5, gain=2.5)
+    x = synth_frames(1, 5, 1, 16, 16, seed=2)
+    p, _ = causal.predrnnpp_forward(sd, x, 2, {"num_layers": 3})
+    assert p.shape == (1, 2, 1, 16, 16) and torch.isfinite(p).all() and float(p.abs().max()) > 0
+
+
 def test_rollout_shape_and_feedback():
     shapes = causal.state_dict_shapes(1, 2, 8, 4, 3)
     sd = synth_state_dict(shapes, seed=4, gain=2.5)
@@ -90,5 +98,12 @@ def test_dropin_layout_matches_oracle_and_native_library():
         cls("cpu", img_shape=(1, 32, 32), num_layers=1, num_hidden=[16], **KW)
     with pytest.raises(NotImplementedError):
         cls("cpu", img_shape=(1, 32, 32), layer_norm=True, **KW)
-    with pytest.raises(Exception):                        # unequal widths are rejected by the library
-        cls("cpu", img_shape=(1, 32, 32), num_layers=2, num_hidden=[16, 32], **KW).native_param_layout()
+    # unequal widths (the paper's stacks are 128-64-64-64): conv_m reads the memory of the layer that wrote it
+    u = cls("cpu", img_shape=(1, 32, 32), num_layers=3, num_hidden=[32, 16, 24], filter_size=3, **KW)
+    got = {k: tuple(v.shape) for k, v in u.state_dict().items()}
+    assert got == causal.state_dict_shapes(1, 3, [32, 16, 24], 4, 3)
+    assert got == {k: tuple(v) for k, v in u.native_param_layout().items()}
+    assert got["cell_list.0.conv_m.0.weight"] == (96, 24, 3, 3) and got["cell_list.1.conv_m.0.weight"] == (48, 32, 3, 3)
+    assert got["cell_list.1.conv_x.0.weight"] == (7 * 16, 32, 3, 3) and got["conv_last.weight"] == (16, 24, 1, 1)
+    with pytest.raises(AttributeError):
+        cls("cpu", img_shape=(1, 32, 32), num_layers=3, num_hidden=[16, 32], **KW)

@@ -21,12 +21,14 @@ CASES = [
     ("1x64_L4_C64", (1, 64, 64), 4, 64, 5, 2, 4, 6, 1.9),
     ("3x32_L2_C32_k3", (3, 32, 32), 2, 32, 3, 3, 3, 4, 1.9),
     ("1x40x24_L3_C24", (1, 40, 24), 3, 24, 5, 2, 2, 3, 2.3),      # ragged: patch grid 10 x 6, C % 8 == 0 only
+    ("1x64_unequal_64_32_32", (1, 64, 64), 3, [64, 32, 32], 5, 2, 3, 4, 1.9),     # the paper's stacks: 128-64-64-64
 ]
 
 
 def _model(img, L, C, k, precision, backend="auto", **kw):
     import vp_suite_b200 as V
-    return V.MODEL_CLASSES["predrnn-pp-causal"]("cuda:0", img_shape=img, num_layers=L, num_hidden=[C] * L, filter_size=k,
+    hid = [C] * L if isinstance(C, int) else list(C)
+    return V.MODEL_CLASSES["predrnn-pp-causal"]("cuda:0", img_shape=img, num_layers=L, num_hidden=hid, filter_size=k,
                                                 precision=precision, backend=backend, **KW, **kw).eval()
 
 

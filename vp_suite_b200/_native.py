@@ -78,7 +78,7 @@ SYMBOLS = {
     "vpk_stlstm_ac_cell_create": (C.c_int, [C.c_int32] * 7 + [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp)]),
     "vpk_stlstm_ac_cell_set_layer_norm": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vpk_stlstm_ac_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 11),
-    "vpk_causal_lstm_cell_create": (C.c_int, [C.c_int32] * 7 + [C.POINTER(_vp), C.POINTER(_vp)]),
+    "vpk_causal_lstm_cell_create": (C.c_int, [C.c_int32] * 8 + [C.POINTER(_vp), C.POINTER(_vp)]),
     "vpk_causal_lstm_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 8),
     "vpk_ghu_cell_create": (C.c_int, [C.c_int32] * 6 + [_vp, _vp, C.POINTER(_vp)]),
     "vpk_ghu_cell_step": (C.c_int, [_vp, C.c_int32] + [_vp] * 4),

@@ -296,11 +296,11 @@ int vpk_stlstm_cell_step(vpk_cell* cell, int32_t batch, const float* x, const fl
   });
 }
 
-int vpk_causal_lstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t ch, int32_t h, int32_t w,
-                                int32_t k, const float* const* weights, vpk_cell** out) {
+int vpk_causal_lstm_cell_create(int32_t precision, int32_t backend, int32_t cin, int32_t cm, int32_t ch, int32_t h,
+                                int32_t w, int32_t k, const float* const* weights, vpk_cell** out) {
   return guarded([&] {
     VPK_REQUIRE(weights && out, "null argument");
-    *out = new vpk_cell{vpk::make_causal_lstm_cell(precision, backend, cin, ch, h, w, k, weights)};
+    *out = new vpk_cell{vpk::make_causal_lstm_cell(precision, backend, cin, cm, ch, h, w, k, weights)};
   });
 }
 

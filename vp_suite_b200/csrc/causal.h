@@ -3,7 +3,8 @@
 // launches.  BASELINE.json's north star names these cells; the vp-suite checkout has neither (its `predrnn-pp` key is
 // PredRNN-V2's ST-LSTM), so there is no reference module to compare with: PARITY UNPINNED -- the checker is
 // oracle/causal.py, a restatement of the published equations in the bias-free form of the public PyTorch
-// re-implementations (conv_x 7C, conv_h 4C, conv_c 3C, conv_m 3C, conv_c2m 4C split (i, g, f, o), conv_om C, conv_last 1x1).
+// re-implementations (conv_x 7C, conv_h 4C, conv_c 3C, conv_m 3C over the previous layer's memory, conv_c2m 4C split (i, g, f, o), conv_om C,
+// conv_last 1x1).
 //
 // The cell is a cascade -- c' feeds the spatial memory's gates, c' and m' feed the output gate -- so it takes three
 // dependent launches, each a concat-free multi-source contraction with the gate math fused into the epilogue:
@@ -39,6 +40,8 @@ struct CausalArgs {
   const float *w_x, *w_h, *w_c, *w_m, *w_c2m, *w_om, *w_last;   // host, layouts of the header comment
   bool c4 = false;        // c, m, o_part use the channel-quad layout
   float* o_raw = nullptr; // optional fp32 dense [B,H,W,C] scratch: launch O as two launches (EPI_ST_O1, see stlstm.h)
+  int Cm = 0;             // channels of m_t (0: C).  The spatial memory comes from the PREVIOUS layer (the top layer for layer 0),
+                          // so in a stack of unequal widths (the paper's 128-64-64-64) conv_m is [3C, Cm, k, k]
 };
 
 inline WeightRef causal_wref(const float* w, int O, int I, int kk, std::initializer_list<int> blocks) {
@@ -94,7 +97,7 @@ inline std::vector<ConvSpec> causal_lstm_specs(const CausalArgs& a, const ActInf
     s.C = C;
     s.is_gate_gemm = true;
     s.wrefs.push_back(causal_wref(a.w_x, 7 * C, a.Cin, k, {3, 4, 5, -1}));
-    s.wrefs.push_back(causal_wref(a.w_m, 3 * C, C, k, {0, 1, -1, 2}));
+    s.wrefs.push_back(causal_wref(a.w_m, 3 * C, a.Cm > 0 ? a.Cm : C, k, {0, 1, -1, 2}));
     s.wrefs.push_back(causal_wref(a.w_c2m, 4 * C, C, k, {0, 2, 1, -1}));      // conv_c2m splits as (i, g, f, o)
     lower_conv(s, k, 1, pad,
                {ConvInput{make_view(a.x, a.H, a.W, a.Cin), 0, 0}, ConvInput{a.m_in, 1, 0}, ConvInput{cnew, 2, 0}}, a.H, a.W,

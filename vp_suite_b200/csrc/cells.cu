@@ -408,11 +408,11 @@ class StLstmCell : public CellBase {
 // checked against oracle/causal.py) behind the NCHW block boundary.
 class CausalLstmCell : public CellBase {
  public:
-  CausalLstmCell(int precision, int backend_, int cin_, int ch_, int h_, int w_, int k_, const float* const* weights)
-      : CellBase(precision, backend_), cin(cin_), ch(ch_), h(h_), w(w_), k(k_) {
-    VPK_REQUIRE(cin > 0 && ch > 0 && h > 0 && w > 0 && k % 2 == 1, "bad Causal LSTM cell shape");
+  CausalLstmCell(int precision, int backend_, int cin_, int cm_, int ch_, int h_, int w_, int k_, const float* const* weights)
+      : CellBase(precision, backend_), cin(cin_), cm(cm_), ch(ch_), h(h_), w(w_), k(k_) {
+    VPK_REQUIRE(cin > 0 && cm > 0 && ch > 0 && h > 0 && w > 0 && k % 2 == 1, "bad Causal LSTM cell shape");
     const size_t kk = static_cast<size_t>(k) * k, cc = static_cast<size_t>(ch) * ch;
-    const size_t n[7] = {7u * ch * cin * kk, 4 * cc * kk, 3 * cc * kk, 3 * cc * kk, 4 * cc * kk, cc * kk, 2 * cc};
+    const size_t n[7] = {7u * ch * cin * kk, 4 * cc * kk, 3 * cc * kk, 3u * ch * cm * kk, 4 * cc * kk, cc * kk, 2 * cc};
     for (int i = 0; i < 7; ++i) {
       VPK_REQUIRE(weights[i] != nullptr, "null Causal LSTM weight");
       wt[i].assign(weights[i], weights[i] + n[i]);
@@ -424,7 +424,7 @@ class CausalLstmCell : public CellBase {
     void* xb = buf("x", px * cin * esize());
     void* hi = buf("h_in", px * ch * esize());
     void* ci = buf("c_in", px * ch * esize());
-    void* mi = buf("m_in", px * ch * esize());
+    void* mi = buf("m_in", px * cm * esize());
     void* ho = buf("h_out", px * ch * esize());
     void* mem = buf("mem", px * 2 * ch * esize());
     float* cb = static_cast<float*>(buf("c", px * ch * sizeof(float)));
@@ -432,8 +432,9 @@ class CausalLstmCell : public CellBase {
     float* op = static_cast<float*>(buf("o_part", px * ch * sizeof(float)));
     if (built_batch != B) {
       convs.clear();
-      CausalArgs a{"cell.", B, h, w, cin, ch, k, xb, hi, make_view(ci, h, w, ch), make_view(mi, h, w, ch), ho, cb, mb, op, mem,
+      CausalArgs a{"cell.", B, h, w, cin, ch, k, xb, hi, make_view(ci, h, w, ch), make_view(mi, h, w, cm), ho, cb, mb, op, mem,
                    wt[0].data(), wt[1].data(), wt[2].data(), wt[3].data(), wt[4].data(), wt[5].data(), wt[6].data()};
+      a.Cm = cm;
       for (const ConvSpec& sp : causal_lstm_specs(a, act())) add(sp, s);
       finish_build(s);
       built_batch = B;
@@ -442,7 +443,7 @@ class CausalLstmCell : public CellBase {
     to_nhwc(in[1], hi, dtype, B, ch, h, w, s);
     to_nhwc(in[2], ci, dtype, B, ch, h, w, s);
     to_nhwc(in[2], cb, DT_F32, B, ch, h, w, s);
-    to_nhwc(in[3], mi, dtype, B, ch, h, w, s);
+    to_nhwc(in[3], mi, dtype, B, cm, h, w, s);
     VPK_CUDA(cudaMemsetAsync(mb, 0, px * ch * sizeof(float), s));        // write-only state (the prefetch reads it)
     for (const BuiltConv& bc : convs) run(bc, s);
     launch_nhwc_to_nchw(ho, dtype, out[0], B, ch, h, w, num_sms, s);
@@ -451,7 +452,7 @@ class CausalLstmCell : public CellBase {
   }
 
  private:
-  int cin, ch, h, w, k;
+  int cin, cm, ch, h, w, k;
   std::vector<float> wt[7];
 };
 
@@ -793,8 +794,9 @@ Cell* make_stlstm_cell(int precision, int backend, int cin, int ch, int h, int w
   return new StLstmCell(precision, backend, cin, ch, h, w, k, w_x, w_h, w_m, w_o, w_last);
 }
 
-Cell* make_causal_lstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* const* weights) {
-  return new CausalLstmCell(precision, backend, cin, ch, h, w, k, weights);
+Cell* make_causal_lstm_cell(int precision, int backend, int cin, int cm, int ch, int h, int w, int k,
+                            const float* const* weights) {
+  return new CausalLstmCell(precision, backend, cin, cm, ch, h, w, k, weights);
 }
 
 Cell* make_ghu_cell(int precision, int backend, int ch, int h, int w, int k, const float* w_x, const float* w_z) {

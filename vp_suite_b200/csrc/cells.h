@@ -34,7 +34,8 @@ Cell* make_phycell_cell(int precision, int backend, int ch, int hid, int h, int 
                         const float* conv2_b, const float* gate_w, const float* gate_b);
 
 // PredRNN++ (causal.h): weights = conv_x, conv_h, conv_c, conv_m, conv_c2m, conv_om, conv_last (host)
-Cell* make_causal_lstm_cell(int precision, int backend, int cin, int ch, int h, int w, int k, const float* const* weights);
+Cell* make_causal_lstm_cell(int precision, int backend, int cin, int cm, int ch, int h, int w, int k,
+                            const float* const* weights);   // cm: channels of the spatial memory the cell READS
 Cell* make_ghu_cell(int precision, int backend, int ch, int h, int w, int k, const float* w_x, const float* w_z);
 
 }  // namespace vpk

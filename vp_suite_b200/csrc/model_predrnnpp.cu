@@ -8,6 +8,7 @@
 //
 // Per step t (total_frames - 1 steps): layer 0 reads the patch frame x_t (t < context) or x_gen; the spatial memory m
 // zig-zags through the layers (top layer of step t -> layer 0 of step t + 1); z_t = GHU(h_t^1, z_{t-1}) is layer 1's input.
+#include <algorithm>
 #include <cstdlib>
 
 #include "builders.h"
@@ -29,26 +30,30 @@ class PredRnnPP : public Model {
     VPK_REQUIRE(p > 0 && d.img_h % p == 0 && d.img_w % p == 0, "image size must be a multiple of patch_size");
     VPK_REQUIRE(L >= 2 && L <= 8 && k % 2 == 1, "predrnn-pp-causal needs 2..8 layers (the GHU sits between layers 0 and 1) and an odd filter_size");
     VPK_REQUIRE(d.layer_norm == 0 && d.action_conditional == 0, "predrnn-pp-causal: layer_norm / action_conditional are not built");
-    C = d.num_hidden[0];
-    for (int i = 0; i < L; ++i)   // the spatial memory is shared by all layers
-      VPK_REQUIRE(d.num_hidden[i] == C, "all Causal LSTM layers must have the same num_hidden");
+    // widths may differ per layer (the paper's 128-64-64-64): the spatial memory a cell reads has the width of the cell that
+    // wrote it -- the previous layer, or the top layer of the previous step for layer 0
+    for (int i = 0; i < L; ++i) {
+      VPK_REQUIRE(d.num_hidden[i] > 0, "bad num_hidden");
+      Cs[i] = d.num_hidden[i];
+      Cmax = std::max(Cmax, Cs[i]);
+    }
     cp = p * p * d.img_c;
     hp_ = d.img_h / p;
     wp_ = d.img_w / p;
     for (int i = 0; i < L; ++i) {
       const std::string pre = "cell_list." + std::to_string(i) + ".";
-      const int cin = (i == 0) ? cp : C;
+      const int C = Cs[i], cin = (i == 0) ? cp : Cs[i - 1], cm = Cs[(i + L - 1) % L];
       declare(pre + "conv_x.0.weight", {7 * C, cin, k, k});
       declare(pre + "conv_h.0.weight", {4 * C, C, k, k});
       declare(pre + "conv_c.0.weight", {3 * C, C, k, k});
-      declare(pre + "conv_m.0.weight", {3 * C, C, k, k});
+      declare(pre + "conv_m.0.weight", {3 * C, cm, k, k});
       declare(pre + "conv_c2m.0.weight", {4 * C, C, k, k});
       declare(pre + "conv_om.0.weight", {C, C, k, k});
       declare(pre + "conv_last.weight", {C, 2 * C, 1, 1});
     }
-    declare("gradient_highway.x_concat.0.weight", {2 * C, C, k, k});
-    declare("gradient_highway.z_concat.0.weight", {2 * C, C, k, k});
-    declare("conv_last.weight", {cp, C, 1, 1});
+    declare("gradient_highway.x_concat.0.weight", {2 * Cs[0], Cs[0], k, k});
+    declare("gradient_highway.z_concat.0.weight", {2 * Cs[0], Cs[0], k, k});
+    declare("conv_last.weight", {cp, Cs[L - 1], 1, 1});
   }
 
  protected:
@@ -72,12 +77,14 @@ class PredRnnPP : public Model {
     std::vector<void*> hb(2 * L), memb(2 * L);
     std::vector<float*> cb(L);
     for (int i = 0; i < L; ++i) {
+      const int C = Cs[i];
       hb[2 * i] = arena.alloc(px * C * esz);
       hb[2 * i + 1] = arena.alloc(px * C * esz);
       memb[2 * i] = arena.alloc(px * 2 * C * esz);          // (c', m') of layer i, even / odd steps
       memb[2 * i + 1] = arena.alloc(px * 2 * C * esz);
       cb[i] = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     }
+    const int C = Cmax, C0 = Cs[0];      // scratch shared by the layers is sized for the widest one
     float* mstate = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     float* opart = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
     // launch O as two launches once the layer is tensor-bound (stlstm.h: o_raw; bit-identical); VPK_SPLIT_O=0/1 overrides
@@ -85,8 +92,8 @@ class PredRnnPP : public Model {
                    getenv("VPK_NO_REGIONS") != nullptr;   // superseded by accumulator regions in the fused launch (lowering.cu)
     if (const char* env = getenv("VPK_SPLIT_O")) split_o = atoi(env) != 0;
     float* oraw = split_o ? static_cast<float*>(arena.alloc(px * C * sizeof(float))) : nullptr;
-    void* zb[2] = {arena.alloc(px * C * esz), arena.alloc(px * C * esz)};
-    float* zstate = static_cast<float*>(arena.alloc(px * C * sizeof(float)));
+    void* zb[2] = {arena.alloc(px * C0 * esz), arena.alloc(px * C0 * esz)};
+    float* zstate = static_cast<float*>(arena.alloc(px * C0 * sizeof(float)));
     float* xgen32 = static_cast<float*>(arena.alloc(px * cp * sizeof(float)));
     void* xgen_act = (dtype == DT_F32) ? static_cast<void*>(xgen32) : arena.alloc(px * cp * esz);
 
@@ -101,13 +108,13 @@ class PredRnnPP : public Model {
         prog.pre.push_back(std::move(pre));
       }
       for (int i = 0; i < L; ++i) {
-        add_memset(prog, hb[2 * i], px * C * esz, "zero_h");
-        add_memset(prog, cb[i], px * C * sizeof(float), "zero_c");
-        add_memset(prog, memb[2 * i + 1], px * 2 * C * esz, "zero_mem");     // c_{-1} of every layer, m seen by layer 0
+        add_memset(prog, hb[2 * i], px * Cs[i] * esz, "zero_h");
+        add_memset(prog, cb[i], px * Cs[i] * sizeof(float), "zero_c");
+        add_memset(prog, memb[2 * i + 1], px * 2 * Cs[i] * esz, "zero_mem");     // c_{-1} of every layer, m seen by layer 0
       }
       add_memset(prog, mstate, px * C * sizeof(float), "zero_m32");      // write-only state, read (and ignored) by the prefetch
-      add_memset(prog, zb[0], px * C * esz, "zero_z");
-      add_memset(prog, zstate, px * C * sizeof(float), "zero_z32");
+      add_memset(prog, zb[0], px * C0 * esz, "zero_z");
+      add_memset(prog, zstate, px * C0 * sizeof(float), "zero_z32");
     }
 
     std::vector<int> par(L, 0);
@@ -128,21 +135,22 @@ class PredRnnPP : public Model {
       for (int i = 0; i < L; ++i) {
         const std::string pre = "cell_list." + std::to_string(i) + ".";
         const void* inp = (i == 0) ? net : (i == 1) ? zb[(t + 1) & 1] : hb[2 * (i - 1) + par[i - 1]];
-        const int cin = (i == 0) ? cp : C;
+        const int C = Cs[i], cin = (i == 0) ? cp : Cs[i - 1], cm = Cs[(i + L - 1) % L];
         const void* mem_prev = (i == 0) ? memb[2 * (L - 1) + ((t + 1) & 1)] : memb[2 * (i - 1) + (t & 1)];
         CausalArgs a{pre, B, hp_, wp_, cin, C, k, inp, hb[2 * i + par[i]],
                      make_channel_view(memb[2 * i + ((t + 1) & 1)], hp_, wp_, 2 * C, 0, C, esz),
-                     make_channel_view(mem_prev, hp_, wp_, 2 * C, C, C, esz), hb[2 * i + (par[i] ^ 1)], cb[i], mstate, opart,
+                     make_channel_view(mem_prev, hp_, wp_, 2 * cm, cm, cm, esz), hb[2 * i + (par[i] ^ 1)], cb[i], mstate, opart,
                      memb[2 * i + (t & 1)],
                      hp(pre + "conv_x.0.weight"), hp(pre + "conv_h.0.weight"), hp(pre + "conv_c.0.weight"),
                      hp(pre + "conv_m.0.weight"), hp(pre + "conv_c2m.0.weight"), hp(pre + "conv_om.0.weight"),
                      hp(pre + "conv_last.weight")};
         a.c4 = true;
+        a.Cm = cm;
         a.o_raw = oraw;
         for (const ConvSpec& sp : causal_lstm_specs(a, act)) add_conv(prog, sp, measure, stream, dtype);
         par[i] ^= 1;
         if (i == 0) {   // z_t = GHU(h_t^1, z_{t-1}): read zb[t & 1], write zb[(t + 1) & 1]
-          GhuArgs g{"gradient_highway.", B, hp_, wp_, C, k, hb[par[0]], zb[t & 1], zb[(t + 1) & 1], zstate,
+          GhuArgs g{"gradient_highway.", B, hp_, wp_, C0, k, hb[par[0]], zb[t & 1], zb[(t + 1) & 1], zstate,
                     hp("gradient_highway.x_concat.0.weight"), hp("gradient_highway.z_concat.0.weight")};
           g.c4 = true;
           add_conv(prog, ghu_spec(g, act), measure, stream, dtype);
@@ -150,7 +158,7 @@ class PredRnnPP : public Model {
       }
       // head: x_gen = conv_last(h_top)  (1x1, no bias), kept in fp32 so that output frames carry no extra rounding
       int oh, ow;
-      ConvArgs hd{"conv_last.", B, hp_, wp_, C, cp, 1, 1, 0, hb[2 * (L - 1) + par[L - 1]], hp("conv_last.weight"),
+      ConvArgs hd{"conv_last.", B, hp_, wp_, Cs[L - 1], cp, 1, 1, 0, hb[2 * (L - 1) + par[L - 1]], hp("conv_last.weight"),
                   nullptr, ACT_NONE, xgen32};
       hd.f32_strided = true;
       hd.oB = static_cast<long long>(hp_) * wp_ * cp;
@@ -197,7 +205,8 @@ class PredRnnPP : public Model {
   }
 
  private:
-  int p = 4, L = 4, k = 5, C = 128, cp = 16, hp_ = 16, wp_ = 16;
+  int p = 4, L = 4, k = 5, cp = 16, hp_ = 16, wp_ = 16;
+  int Cs[8] = {0, 0, 0, 0, 0, 0, 0, 0}, Cmax = 0;
 };
 
 }  // namespace

@@ -366,14 +366,17 @@ class CausalLSTMCell(_NativeCell, VPModelBlock):
     MATCHES_REFERENCE = "Not Yet"
     _CONVS = ("conv_x", "conv_h", "conv_c", "conv_m", "conv_c2m", "conv_om")
 
-    def __init__(self, in_channel, num_hidden, height, width, filter_size, stride=1, layer_norm=False):
+    def __init__(self, in_channel, num_hidden, height, width, filter_size, stride=1, layer_norm=False, num_hidden_in=None):
         super().__init__()
         self._cell_init()
         if stride != 1 or filter_size % 2 == 0:
             raise ValueError("stride 1 and odd filter sizes only")
         if layer_norm:
             raise NotImplementedError("Causal LSTM drop-in: layer_norm is not built")
+        # num_hidden_in: channels of the spatial memory the cell READS (the width of the cell that wrote it; the paper's
+        # stacks have unequal widths, 128-64-64-64); default: this cell's own width
         self.num_hidden, self.padding, self._forget_bias = num_hidden, filter_size // 2, 1.0
+        self.num_hidden_in = num_hidden if num_hidden_in is None else int(num_hidden_in)
         self._shape = (in_channel, height, width, filter_size)
 
         def conv(ci, co):
@@ -381,7 +384,7 @@ class CausalLSTMCell(_NativeCell, VPModelBlock):
         self.conv_x = conv(in_channel, num_hidden * 7)
         self.conv_h = conv(num_hidden, num_hidden * 4)
         self.conv_c = conv(num_hidden, num_hidden * 3)
-        self.conv_m = conv(num_hidden, num_hidden * 3)
+        self.conv_m = conv(self.num_hidden_in, num_hidden * 3)
         self.conv_c2m = conv(num_hidden, num_hidden * 4)
         self.conv_om = conv(num_hidden, num_hidden)
         self.conv_last = nn.Conv2d(num_hidden * 2, num_hidden, 1, 1, 0, bias=False)
@@ -392,7 +395,7 @@ class CausalLSTMCell(_NativeCell, VPModelBlock):
         ws = [self._host(getattr(self, n)[0].weight) for n in self._CONVS] + [self._host(self.conv_last.weight)]
         wp = (C.c_void_p * 7)(*[t.data_ptr() for t in ws])
         N.check(N.lib().vpk_causal_lstm_cell_create(N.PRECISIONS[self.precision], N.BACKENDS[self.backend], cin,
-                                                    self.num_hidden, h, w, k, wp, C.byref(cell)))
+                                                    self.num_hidden_in, self.num_hidden, h, w, k, wp, C.byref(cell)))
         return cell
 
     def forward(self, x_t, h_t, c_t, m_t):

@@ -418,27 +418,32 @@ class PredRNNpp(NativeRollout, VPModel):
         self.patch_c = self.patch_size * self.patch_size * self.img_c
         self.patch_h = self.rnn_h = self.img_h // self.patch_size
         self.patch_w = self.rnn_w = self.img_w // self.patch_size
-        k, C = self.filter_size, self.num_hidden[0]
+        if len(self.num_hidden) < self.num_layers:
+            raise AttributeError("num_hidden needs one entry per layer")
+        k, L, hid = self.filter_size, self.num_layers, self.num_hidden
 
         def conv(ci, co):
             return nn.Sequential(nn.Conv2d(ci, co, k, 1, k // 2, bias=False))
 
         cells = []
-        for i in range(self.num_layers):
+        for i in range(L):
+            # widths may differ per layer (the paper: 128-64-64-64); the spatial memory a cell reads has the width of the
+            # cell that wrote it: the previous layer, or the top layer for layer 0
+            C, cin, cm = hid[i], (self.patch_c if i == 0 else hid[i - 1]), hid[(i - 1) % L]
             cell = _Params()
-            cell.conv_x = conv(self.patch_c if i == 0 else C, 7 * C)
+            cell.conv_x = conv(cin, 7 * C)
             cell.conv_h = conv(C, 4 * C)
             cell.conv_c = conv(C, 3 * C)
-            cell.conv_m = conv(C, 3 * C)
+            cell.conv_m = conv(cm, 3 * C)
             cell.conv_c2m = conv(C, 4 * C)
             cell.conv_om = conv(C, C)
             cell.conv_last = nn.Conv2d(2 * C, C, 1, 1, 0, bias=False)
             cells.append(cell)
         self.cell_list = nn.ModuleList(cells)
         self.gradient_highway = _Params()
-        self.gradient_highway.x_concat = conv(C, 2 * C)
-        self.gradient_highway.z_concat = conv(C, 2 * C)
-        self.conv_last = nn.Conv2d(C, self.patch_c, 1, 1, 0, bias=False)
+        self.gradient_highway.x_concat = conv(hid[0], 2 * hid[0])
+        self.gradient_highway.z_concat = conv(hid[0], 2 * hid[0])
+        self.conv_last = nn.Conv2d(hid[L - 1], self.patch_c, 1, 1, 0, bias=False)
         self.to(device)
 
     def _native_desc(self):
