@@ -108,23 +108,24 @@ def test_contract_errors():
 
 
 @pytest.mark.parametrize("precision,backend", [("fp32", "auto"), ("bf16", "auto"), ("bf16", "simt")])
-@pytest.mark.parametrize("cin,C,hw,k", [(16, 64, (16, 16), 5), (24, 24, (10, 6), 3)])
-def test_single_step_blocks_match_oracle(cin, C, hw, k, precision, backend):
+@pytest.mark.parametrize("cin,C,hw,k,cm", [(16, 64, (16, 16), 5, 64), (24, 24, (10, 6), 3, 24), (32, 16, (16, 16), 3, 48)])
+def test_single_step_blocks_match_oracle(cin, C, hw, k, cm, precision, backend):
     """CausalLSTMCell.forward(x, h, c, m) -> (h', c', m') and GHU.forward(x, z) as VPModelBlock drop-ins (vpk_causal_lstm_cell_* /
     vpk_ghu_cell_*), one step from random non-zero states; 16-bit mode inside the north star's single-step bound (5e-3),
     and within 2.5e-3 of the oracle with bf16-rounded conv operands."""
     from vp_suite_b200.model_blocks import CausalLSTMCell, GHU
     g = torch.Generator().manual_seed(7)
     shapes = {f"{n}.0.weight": s for n, s in (("conv_x", (7 * C, cin, k, k)), ("conv_h", (4 * C, C, k, k)),
-                                               ("conv_c", (3 * C, C, k, k)), ("conv_m", (3 * C, C, k, k)),
+                                               ("conv_c", (3 * C, C, k, k)), ("conv_m", (3 * C, cm, k, k)),
                                                ("conv_c2m", (4 * C, C, k, k)), ("conv_om", (C, C, k, k)))}
     shapes["conv_last.weight"] = (C, 2 * C, 1, 1)
     sd = synth_state_dict(shapes, seed=21, gain=1.5)
-    cell = CausalLSTMCell(cin, C, hw[0], hw[1], k, 1, False).cuda()
+    cell = CausalLSTMCell(cin, C, hw[0], hw[1], k, 1, False, num_hidden_in=cm).cuda()
     cell.precision, cell.backend = precision, backend
     cell.load_state_dict(sd)
     x = torch.rand(3, cin, *hw, generator=g)
-    h, c, m = (torch.randn(3, C, *hw, generator=g) * s for s in (0.2, 0.3, 0.3))      # states of the size a rollout reaches
+    h, c = (torch.randn(3, C, *hw, generator=g) * s for s in (0.2, 0.3))      # states of the size a rollout reaches
+    m = torch.randn(3, cm, *hw, generator=g) * 0.3                            # the memory has the width of the cell that wrote it
     w = {n: sd[f"{n}.0.weight"] for n in ("conv_x", "conv_h", "conv_c", "conv_m", "conv_c2m", "conv_om")}
     w["conv_last"] = sd["conv_last.weight"]
     want = causal.causal_lstm_step(x, h, c, m, w)
