@@ -1,6 +1,6 @@
 """Writes the SASS evidence committed under profiles/: per-kernel histogram of the Blackwell-specific mnemonics in
 libvpk.so and the SASS of the MMA-issue loop + TMA producers of the ConvLSTM gate-GEMM kernel.
-    python tools/sass_listing.py > profiles/r01_sass_libvpk.md"""
+    python tools/sass_listing.py > profiles/r02_sass_libvpk.md"""
 import os
 import re
 import subprocess
