@@ -42,6 +42,10 @@ constexpr unsigned kMaxSmem = 232448;
 constexpr uint32_t kTapFirstOfBlock = 1, kTapLastOfBlock = 2, kTapFirstOfGroup = 4, kTapLastOfGroup = 8;
 constexpr uint32_t kTapRegionA = 32, kTapRegionB = 64;   // accumulator regions the tap feeds (ConvLaunch::region_g0)
 constexpr uint32_t kTapFuseNext = 16;   // the next tap needs no hand-off in between and both are full (4 K-slices): one asm block
+// taps of this block share streamed weight tiles four at a time (see the tap-table build in the kernel); VPK_HALO_PACK16=0 off
+__device__ __forceinline__ bool halo_block_packed(const HaloPlan& P, const HaloBlock& blk) {
+  return P.pack16 != 0 && !P.resident && blk.kc <= 16 && blk.ntaps > 1;
+}
 
 __device__ __forceinline__ uint64_t smem_desc_sw128_sbo(uint32_t smem_addr, uint32_t sbo_bytes) {
   uint64_t d = 0;
@@ -151,13 +155,18 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     int bi = 0;
     while (bi + 1 < nblocks && P.blocks[bi + 1].first_tap <= i) ++bi;
     const HaloBlock blk = P.blocks[bi];
-    const int q = i - blk.first_tap, g = q % P.bgroup;
+    // Blocks of <= 16 channels (one K = 16 slice per tap; patch frames, EF stage-1 features): the packed weights give
+    // every tap 16 consecutive columns, so the 64-column weight tile fetched for tap 4j already holds taps 4j .. 4j+3.
+    // Four such taps SHARE one streamed tile (K slice q & 3 of it) instead of fetching four overlapping ones: the weight
+    // ring, not the MMA, bounds these layers (a 16-channel source cost a quarter of the FLOPs but a full tile per tap).
+    const bool packed = halo_block_packed(P, blk);
+    const int q = i - blk.first_tap, wt = packed ? q >> 2 : q, sub = packed ? q & 3 : 0, g = wt % P.bgroup;
     uint32_t flags = 0;
     if (q == 0) flags |= kTapFirstOfBlock;
     if (q == blk.ntaps - 1) flags |= kTapLastOfBlock;
     if (!P.resident) {
-      if (g == 0) flags |= kTapFirstOfGroup;
-      if (g == P.bgroup - 1 || q == blk.ntaps - 1) flags |= kTapLastOfGroup;
+      if (g == 0 && sub == 0) flags |= kTapFirstOfGroup;
+      if ((g == P.bgroup - 1 && (!packed || sub == 3)) || q == blk.ntaps - 1) flags |= kTapLastOfGroup;
     }
     const int hwp = kTW + 2 * P.P;
     const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         (P.resident || (g + 1) % P.bgroup != 0) && (P.taps[i + 1].nk >> 8) == (tp.nk >> 8))
       flags |= kTapFuseNext;
     s_tapmma[i] = make_uint2((off >> 4) | (flags << 16) | (nk << 24),
-                             static_cast<uint32_t>(P.resident ? i : g) * (P.b_tap_stride >> 4));
+                             static_cast<uint32_t>(P.resident ? i : g) * (P.b_tap_stride >> 4) + static_cast<uint32_t>(2 * sub));
   }
   if constexpr (MODE == 3) {
     const int np = P.L.N_pad;
@@ -335,8 +344,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
         const int n0 = (t % P.n_tiles) * tileN + static_cast<int>(rank) * (PAIR ? rowsB : 0);
         for (int bi = 0; bi < nblocks; ++bi) {
           const HaloBlock blk = s_blocks[bi];
-          for (int q0 = 0; q0 < blk.ntaps; q0 += P.bgroup) {
-            const int gn = min(P.bgroup, blk.ntaps - q0);
+          const int tstep = halo_block_packed(P, blk) ? 4 : 1;             // taps per streamed weight tile
+          const int ntile = (blk.ntaps + tstep - 1) / tstep;
+          for (int q0 = 0; q0 < ntile; q0 += P.bgroup) {
+            const int gn = min(P.bgroup, ntile - q0);
             ptx::mbar_wait_spin(bempty + 8 * sb, ph ^ 1u);
             const uint32_t fb = bfull + 8 * sb;
             const uint32_t dst = ptx::smem_u32(smem_b + sb * P.b_slot_bytes);
@@ -349,7 +360,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 ptx::mbar_arrive_expect_tx(fb, b_box_bytes * gn);
               }
               for (int q = 0; q < gn; ++q) {
-                const int wk = s_taps[blk.first_tap + q0 + q].wk;
+                const int wk = s_taps[blk.first_tap + (q0 + q) * tstep].wk;
                 if constexpr (PAIR) {
                   if (MC) {    // taps alternate between the two pairs' producers; each load feeds the same-half CTA of both
                     if ((q & 1) == static_cast<int>(prank))
@@ -1426,6 +1437,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   P.debug = 0;
   if (const char* env = dev_env("VPK_TC_DEBUG")) P.debug = atoi(env);
   P.L.epi.debug = P.debug;
+  P.pack16 = 1;
+  if (const char* env = getenv("VPK_HALO_PACK16")) P.pack16 = atoi(env) != 0 ? 1 : 0;
   P.fast_epi = (epi_tc_fast_ok(L.epi) && gates_of(L.epi.kind) == L.G) ? 1 : 0;
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
   P.roll = (P.fast_epi && L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) ? 1 : 0;

@@ -41,6 +41,7 @@ struct alignas(64) HaloPlan {
   const HaloTap* taps;         // device
   int nblocks, ntaps;
   int P;                       // halo radius = max |dy|, |dx|
+  int pack16;                  // taps of <= 16-channel blocks share streamed weight tiles four at a time (conv_halo.cu)
   int tiles_x, tiles_y;        // 8 x 16 output tiles per image
   int n_tiles, tileN;
   int SA, SB;                  // activation / weight ring depths
