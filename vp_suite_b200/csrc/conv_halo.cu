@@ -107,6 +107,8 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
   const int SA = P.SA, SB = P.SB;
   const int tileN = P.tileN;
   const int rowsB = PAIR ? tileN / 2 : tileN;
+  // kernels that may run with accumulator regions (ConvLaunch::region_g0): CTA pairs, general fast epilogue, ST-LSTM kinds
+  constexpr bool kRegionKind = PAIR && MODE == 1 && (KIND == EPI_ST_C || KIND == EPI_ST_O);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + SA * P.a_slot_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + SB * P.b_slot_bytes);
@@ -172,8 +174,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
     const uint32_t off = (P.debug & 32) ? 0u : static_cast<uint32_t>(((P.P + tp.dy) * hwp + (P.P + tp.dx)) * 128);
     const uint32_t nk = (P.debug & 2) ? 0u : static_cast<uint32_t>(tp.nk & 0xFF);
     const uint32_t regions = static_cast<uint32_t>(tp.nk >> 8) & 3u;
-    if (regions & 1u) flags |= kTapRegionA;
-    if (regions & 2u) flags |= kTapRegionB;
+    if constexpr (kRegionKind) {
+      if (regions & 1u) flags |= kTapRegionA;
+      if (regions & 2u) flags |= kTapRegionB;
+    }
     // fuse with the next tap: same block, no group boundary in between, both with 4 K-slices, feeding the same accumulator regions
     if (q + 1 < blk.ntaps && !(flags & (kTapLastOfGroup | kTapLastOfBlock)) && nk == 4 && (P.taps[i + 1].nk & 0xFF) == 4 &&
         (P.resident || (g + 1) % P.bgroup != 0) && (P.taps[i + 1].nk >> 8) == (tp.nk >> 8))
@@ -437,13 +441,17 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             }
           }
           uint32_t lflags = flags;
+          // accumulator regions exist only in the CTA-pair instantiations of the ST-LSTM kinds (kRegionKind): every other
+          // kernel keeps the plain issue loop -- the small-N layers are bound by this thread's instruction count
+          bool region_tap = false;
+          if constexpr (kRegionKind) region_tap = (flags & (kTapRegionA | kTapRegionB)) != 0;
           if (flags & kTapFuseNext) {
             const uint2 nx = ti;              // the table entry after `cur` is consumed by the same asm block
             tab += 8;
             ti = ptx::lds_u2(tab);
             ++i;
             if constexpr (PAIR) {
-              if (flags & (kTapRegionA | kTapRegionB)) {      // accumulator regions (see the single-tap form below)
+              if (kRegionKind && region_tap) {      // accumulator regions (see the single-tap form below)
                 if (flags & kTapRegionA) {
                   ptx::mma_bf16_ss_tap2_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc_ra, accum);
                   accum = 1u;
@@ -455,12 +463,14 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
                 }
               } else {
                 ptx::mma_bf16_ss_tap2_pair(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
+                accum = 1u;
               }
             } else {
               ptx::mma_bf16_ss_tap2(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, a_d + (nx.x & 0xFFFFu), b_d + nx.y, idesc, accum);
+              accum = 1u;
             }
             lflags = nx.x >> 16;
-          } else if (PAIR && (flags & (kTapRegionA | kTapRegionB))) {
+          } else if (kRegionKind && region_tap) {
             // accumulator regions: region A = columns [0, N_A) <- the first rows of each CTA's weight half, region B behind it;
             // a tap multiplies only what its weight tensor feeds (N is constant per region, as cta_group::2's column split needs)
             if constexpr (PAIR) {
@@ -479,7 +489,6 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
             else ptx::mma_bf16_ss_tap(tmem_d, a_d + (cur.x & 0xFFFFu), b_d + cur.y, idesc, accum, (cur.x >> 24) & 0xFFu);
             accum = 1u;
           }
-          if (!(flags & (kTapRegionA | kTapRegionB))) accum = 1u;
           if (lflags & (kTapLastOfGroup | kTapLastOfBlock)) {
             const uint32_t flags = lflags;
             if (flags & kTapLastOfGroup) {
@@ -1039,7 +1048,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_halo_kernel(const __grid
       const int ch_base = nt * Cn;
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * tileN);
       auto tmem_chunk = [&](int ch, uint32_t (&r)[8 * G]) {
-        if constexpr (PAIR && (G == 4 || G == 2)) {
+        if constexpr (kRegionKind) {
           if (P.L.region_g0 > 0) {
             // accumulator regions: columns [0, N_A) hold gates [0, g0), CTA halves side by side inside each region
             // (cta_group::2 takes columns [0, N/2) of an MMA from the leader's weight rows and [N/2, N) from its peer's)
@@ -1441,6 +1450,8 @@ void halo_make_plan(const ConvLaunch& L, const HaloBlock* d_blocks, const HaloTa
   if (const char* env = getenv("VPK_HALO_PACK16")) P.pack16 = atoi(env) != 0 ? 1 : 0;
   P.fast_epi = (epi_tc_fast_ok(L.epi) && gates_of(L.epi.kind) == L.G) ? 1 : 0;
   if (const char* env = getenv("VPK_TC_FAST_EPI")) P.fast_epi = P.fast_epi && atoi(env) != 0;
+  VPK_REQUIRE(L.region_g0 == 0 || (P.fast_epi && (L.epi.kind == EPI_ST_C || L.epi.kind == EPI_ST_O)),
+              "conv_halo: accumulator regions need the specialised epilogue of an ST-LSTM kind");
   P.roll = (P.fast_epi && L.epi.kind == EPI_LSTM && (L.epi.pp16 != nullptr || L.epi.p0 == nullptr)) ? 1 : 0;
   if (const char* env = getenv("VPK_EPI_ROLL")) P.roll = P.roll && atoi(env) != 0;
   {

@@ -291,7 +291,8 @@ std::vector<BuiltConv> build_conv(const ConvSpec& spec, int dtype, int backend, 
   int rg0 = 0;
   if (spec.region_g0 > 0 && backend == 0 && dtype != DT_F32 && spec.biases.empty() && spec.phases.size() == 1 &&
       Cn % 16 == 0 && C % Cn == 0 && ((G == 4 && spec.region_g0 == 3) || (G == 2 && spec.region_g0 == 1)) &&
-      getenv("VPK_NO_REGIONS") == nullptr) {
+      (spec.phases[0].epi.kind == EPI_ST_C || spec.phases[0].epi.kind == EPI_ST_O) && getenv("VPK_NO_REGIONS") == nullptr &&
+      getenv("VPK_TC_FAST_EPI") == nullptr) {
     const char* halo_env = getenv("VPK_TC_HALO");
     if ((halo_env == nullptr || atoi(halo_env) != 0) &&
         halo_will_pair(spec.B, spec.phases[0].H, spec.phases[0].W, Cn * G, N_pad / (Cn * G), num_sms))
