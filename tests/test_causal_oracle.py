@@ -107,3 +107,28 @@ def test_dropin_layout_matches_oracle_and_native_library():
     assert got["cell_list.1.conv_x.0.weight"] == (7 * 16, 32, 3, 3) and got["conv_last.weight"] == (16, 24, 1, 1)
     with pytest.raises(AttributeError):
         cls("cpu", img_shape=(1, 32, 32), num_layers=3, num_hidden=[16, 32], **KW)
+
+
+def test_block_dropins_layout_and_refusals():
+    """CausalLSTMCell / GHU as VPModelBlock drop-ins: parameter layout of the paper's cell (conv_m reads a memory of
+    num_hidden_in channels), constructor refusals, and no CPU path."""
+    from vp_suite_b200.model_blocks import CausalLSTMCell, GHU
+    from vp_suite_b200 import _native as N
+    cell = CausalLSTMCell(16, 32, 8, 8, 5, 1, False, num_hidden_in=48)
+    got = {k: tuple(v.shape) for k, v in cell.state_dict().items()}
+    assert got == {"conv_x.0.weight": (224, 16, 5, 5), "conv_h.0.weight": (128, 32, 5, 5), "conv_c.0.weight": (96, 32, 5, 5),
+                   "conv_m.0.weight": (96, 48, 5, 5), "conv_c2m.0.weight": (128, 32, 5, 5), "conv_om.0.weight": (32, 32, 5, 5),
+                   "conv_last.weight": (32, 64, 1, 1)}
+    ghu = GHU(32, 8, 8, 5)
+    assert {k: tuple(v.shape) for k, v in ghu.state_dict().items()} == {"x_concat.0.weight": (64, 32, 5, 5),
+                                                                          "z_concat.0.weight": (64, 32, 5, 5)}
+    with pytest.raises(ValueError):
+        CausalLSTMCell(16, 32, 8, 8, 4, 1, False)                      # even filter size
+    with pytest.raises(NotImplementedError):
+        GHU(32, 8, 8, 5, 1, True)                                       # layer_norm
+    with pytest.raises(N.NativeError):                                  # CUDA tensors only: there is no CPU path
+        cell(torch.zeros(1, 16, 8, 8), torch.zeros(1, 32, 8, 8), torch.zeros(1, 32, 8, 8), torch.zeros(1, 48, 8, 8))
+    # pickling drops the native handle
+    import pickle
+    c2 = pickle.loads(pickle.dumps(cell))
+    assert c2.num_hidden_in == 48 and c2._cell is None
